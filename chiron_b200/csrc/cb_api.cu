@@ -1,0 +1,522 @@
+// C-ABI of libchiron_b200.so: handle lifecycle, weight preparation, workspace, forward orchestration, host wrappers.
+// See include/chiron_b200.h for the contract and the reference call sites each entry point replaces.
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "cb_internal.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void cb_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* cb_last_error(void) { return g_err; }
+extern "C" const char* cb_version(void) { return "chiron_b200 0.1 (sm_100a)"; }
+
+namespace {
+
+constexpr float BN_EPS = 1e-5f;   // chiron/cnn.py:125,187
+
+struct BlobHeader {               // chiron_b200/model.py: "<4s8i8i8i6iq" (packed, 132 bytes)
+    char magic[4];
+    int32_t version, n_blocks, channels, hidden, n_layers, n_class, rnn_layout, branch1_bn_mask;
+    int32_t k[8], stride[8];
+    int32_t sig_norm, reverse_signal, reserved[4];
+};
+constexpr size_t HEADER_BYTES = 4 + 30 * 4 + 8;
+
+struct HostBuilder {              // accumulates the derived fp32 weights; every tensor starts 16-byte aligned
+    std::vector<float> data;
+    size_t add(const std::vector<float>& v) {
+        while (data.size() & 3) data.push_back(0.f);
+        size_t off = data.size();
+        data.insert(data.end(), v.begin(), v.end());
+        return off;
+    }
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int out_len_of(const CbConfig& c, int L) {
+    int T = L;
+    for (int b = 0; b < c.n_blocks; ++b) T = (T + c.stride[b] - 1) / c.stride[b];
+    return T;
+}
+
+}  // namespace
+
+// -----------------------------------------------------------------------------------------------------------------
+extern "C" int cb_create(const void* blob, size_t nbytes, int device, int precision, cb_handle** out) {
+    if (!blob || !out || nbytes < HEADER_BYTES) { cb_set_error("cb_create: bad arguments"); return CB_ERR_ARG; }
+    if (precision < CB_PREC_FP32 || precision > CB_PREC_TC_FAST) { cb_set_error("cb_create: unknown precision %d", precision); return CB_ERR_ARG; }
+    BlobHeader hd;
+    memcpy(&hd, blob, sizeof(hd));
+    int64_t n_floats;
+    memcpy(&n_floats, (const char*)blob + HEADER_BYTES - 8, 8);
+    if (memcmp(hd.magic, "CBW1", 4) != 0 || hd.version != 1) { cb_set_error("cb_create: not a CBW1 blob"); return CB_ERR_BLOB; }
+    if (hd.n_blocks < 1 || hd.n_blocks > CB_MAX_BLOCKS || hd.n_layers < 1 || hd.n_layers > CB_MAX_LAYERS ||
+        hd.channels < 4 || (hd.channels & 3) || hd.hidden < 4 || (hd.hidden & 3) || hd.n_class < 2 || hd.n_class > 8) {
+        cb_set_error("cb_create: unsupported topology in blob header");
+        return CB_ERR_BLOB;
+    }
+    if (nbytes < HEADER_BYTES + (size_t)n_floats * 4) { cb_set_error("cb_create: truncated blob"); return CB_ERR_BLOB; }
+    const float* w = (const float*)((const char*)blob + HEADER_BYTES);
+
+    cb_handle* h = new cb_handle();
+    memset(h, 0, sizeof(*h));
+    h->device = device;
+    h->precision = precision;
+    CbConfig& c = h->cfg;
+    c.n_blocks = hd.n_blocks; c.channels = hd.channels; c.hidden = hd.hidden; c.n_layers = hd.n_layers;
+    c.n_class = hd.n_class; c.rnn_layout = hd.rnn_layout; c.branch1_bn_mask = hd.branch1_bn_mask;
+    for (int i = 0; i < CB_MAX_BLOCKS; ++i) { c.k[i] = hd.k[i]; c.stride[i] = hd.stride[i]; }
+    c.sig_norm = hd.sig_norm; c.reverse_signal = hd.reverse_signal;
+    const int C = c.channels, H = c.hidden;
+    for (int b = 0; b < c.n_blocks; ++b)
+        if (c.k[b] < 1 || c.stride[b] < 1) { delete h; cb_set_error("cb_create: bad conv geometry"); return CB_ERR_BLOB; }
+
+    // ---- walk the canonical tensor order (model.py: tensor_specs) and derive the kernels' operands ----------------
+    size_t pos = 0;
+    auto take = [&](size_t n) -> const float* { const float* p = w + pos; pos += n; return p; };
+    struct Bn { std::vector<float> inv, shift; };
+    auto take_bn = [&]() {           // tf.nn.batch_normalization, population statistics (cnn.py:160-161)
+        Bn bn; bn.inv.resize(C); bn.shift.resize(C);
+        const float *scale = take(C), *offset = take(C), *mean = take(C), *var = take(C);
+        for (int n = 0; n < C; ++n) {
+            bn.inv[n] = scale[n] * (1.0f / sqrtf(var[n] + BN_EPS));
+            bn.shift[n] = offset[n] - mean[n] * bn.inv[n];
+        }
+        return bn;
+    };
+    HostBuilder hb;
+    size_t o_conv2a[CB_MAX_BLOCKS][2], o_conv2b[CB_MAX_BLOCKS][2], o_convc[CB_MAX_BLOCKS][2];
+    size_t o_g[3] = {0, 0, 0}, o_r[3] = {0, 0, 0};
+    for (int b = 0; b < c.n_blocks; ++b) {
+        const int cin = b == 0 ? 1 : C;
+        const float* w1 = take((size_t)cin * C);
+        Bn bn1; bool has_bn1 = (c.branch1_bn_mask >> b) & 1;
+        if (has_bn1) bn1 = take_bn();
+        const float* w2a = take((size_t)cin * C);
+        Bn bna = take_bn();
+        const float* w2b = take((size_t)c.k[b] * C * C);
+        Bn bnb = take_bn();
+        const float* w2c = take((size_t)C * C);
+        Bn bnc = take_bn();
+        if (b == 0) {
+            o_g[0] = hb.add(std::vector<float>(w2a, w2a + C));
+            o_g[1] = hb.add(bna.inv);
+            o_g[2] = hb.add(bna.shift);
+            o_r[0] = hb.add(std::vector<float>(w1, w1 + C));
+            o_r[1] = hb.add(has_bn1 ? bn1.inv : std::vector<float>(C, 1.0f));
+            o_r[2] = hb.add(has_bn1 ? bn1.shift : std::vector<float>(C, 0.0f));
+            o_conv2a[b][0] = o_conv2a[b][1] = 0;
+        } else {
+            std::vector<float> f((size_t)C * C);
+            for (int k = 0; k < C; ++k)
+                for (int n = 0; n < C; ++n) f[(size_t)k * C + n] = w2a[(size_t)k * C + n] * bna.inv[n];
+            o_conv2a[b][0] = hb.add(f);
+            o_conv2a[b][1] = hb.add(bna.shift);
+        }
+        {
+            std::vector<float> f((size_t)c.k[b] * C * C);
+            for (size_t k = 0; k < (size_t)c.k[b] * C; ++k)
+                for (int n = 0; n < C; ++n) f[k * C + n] = w2b[k * C + n] * bnb.inv[n];
+            o_conv2b[b][0] = hb.add(f);
+            o_conv2b[b][1] = hb.add(bnb.shift);
+        }
+        {   // conv2c (+BN) and, for blocks >= 2, the 1x1 branch1 conv stacked along K (cnn.py:258-261)
+            const int kc = b == 0 ? C : 2 * C;
+            std::vector<float> f((size_t)kc * C), sh(bnc.shift);
+            for (int k = 0; k < C; ++k)
+                for (int n = 0; n < C; ++n) f[(size_t)k * C + n] = w2c[(size_t)k * C + n] * bnc.inv[n];
+            if (b > 0) {
+                for (int k = 0; k < C; ++k)
+                    for (int n = 0; n < C; ++n)
+                        f[(size_t)(C + k) * C + n] = w1[(size_t)k * C + n] * (has_bn1 ? bn1.inv[n] : 1.0f);
+                if (has_bn1) for (int n = 0; n < C; ++n) sh[n] += bn1.shift[n];
+            }
+            o_convc[b][0] = hb.add(f);
+            o_convc[b][1] = hb.add(sh);
+        }
+    }
+    size_t o_wx[CB_MAX_LAYERS][2], o_b[CB_MAX_LAYERS][2], o_whh[CB_MAX_LAYERS][2], o_wxcat[CB_MAX_LAYERS], o_bcat[CB_MAX_LAYERS];
+    for (int l = 0; l < c.n_layers; ++l) {
+        const int in = l == 0 ? C : (c.rnn_layout == 0 ? 2 * H : H);
+        const float* kern[2]; const float* bias[2];
+        for (int d = 0; d < 2; ++d) { kern[d] = take((size_t)(in + H) * 4 * H); bias[d] = take((size_t)4 * H); }
+        std::vector<float> cat((size_t)in * 8 * H), bcat((size_t)8 * H);
+        for (int d = 0; d < 2; ++d) {
+            o_wx[l][d] = hb.add(std::vector<float>(kern[d], kern[d] + (size_t)in * 4 * H));
+            o_whh[l][d] = hb.add(std::vector<float>(kern[d] + (size_t)in * 4 * H, kern[d] + (size_t)(in + H) * 4 * H));
+            o_b[l][d] = hb.add(std::vector<float>(bias[d], bias[d] + 4 * H));
+            for (int k = 0; k < in; ++k)
+                memcpy(&cat[(size_t)k * 8 * H + (size_t)d * 4 * H], kern[d] + (size_t)k * 4 * H, sizeof(float) * 4 * H);
+            memcpy(&bcat[(size_t)d * 4 * H], bias[d], sizeof(float) * 4 * H);
+        }
+        o_wxcat[l] = hb.add(cat);
+        o_bcat[l] = hb.add(bcat);
+    }
+    const float* hw = take((size_t)2 * H);
+    const float* hbias = take(H);
+    const float* hwc = take((size_t)H * c.n_class);
+    const float* hbc = take(c.n_class);
+    size_t o_head[4] = {hb.add(std::vector<float>(hw, hw + 2 * H)), hb.add(std::vector<float>(hbias, hbias + H)),
+                        hb.add(std::vector<float>(hwc, hwc + (size_t)H * c.n_class)),
+                        hb.add(std::vector<float>(hbc, hbc + c.n_class))};
+    if ((int64_t)pos != n_floats) {
+        delete h;
+        cb_set_error("cb_create: blob holds %lld floats, topology needs %zu", (long long)n_floats, pos);
+        return CB_ERR_BLOB;
+    }
+
+    // ---- device ------------------------------------------------------------------------------------------------------
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { delete h; cb_set_error("cudaSetDevice(%d): %s", device, cudaGetErrorString(e)); return CB_ERR_CUDA; }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { delete h; cb_set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return CB_ERR_CUDA; }
+    h->sm_count = prop.multiProcessorCount;
+    if (prop.major != 10) {
+        delete h;
+        cb_set_error("chiron_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+        return CB_ERR_CUDA;
+    }
+    h->weights_floats = hb.data.size();
+    e = cudaMalloc(&h->d_weights, hb.data.size() * sizeof(float));
+    if (e != cudaSuccess) { delete h; cb_set_error("cudaMalloc(weights): %s", cudaGetErrorString(e)); return CB_ERR_NOMEM; }
+    e = cudaMemcpy(h->d_weights, hb.data.data(), hb.data.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(h->d_weights); delete h; cb_set_error("cudaMemcpy(weights): %s", cudaGetErrorString(e)); return CB_ERR_CUDA; }
+    const float* base = h->d_weights;
+    h->g_w = base + o_g[0]; h->g_inv = base + o_g[1]; h->g_sh = base + o_g[2];
+    h->r_w = base + o_r[0]; h->r_inv = base + o_r[1]; h->r_sh = base + o_r[2];
+    for (int b = 0; b < c.n_blocks; ++b) {
+        h->conv2a[b].W = base + o_conv2a[b][0]; h->conv2a[b].shift = base + o_conv2a[b][1];
+        h->conv2b[b].W = base + o_conv2b[b][0]; h->conv2b[b].shift = base + o_conv2b[b][1];
+        h->convc[b].W = base + o_convc[b][0];   h->convc[b].shift = base + o_convc[b][1];
+    }
+    for (int l = 0; l < c.n_layers; ++l) {
+        for (int d = 0; d < 2; ++d) {
+            h->wx[l][d] = base + o_wx[l][d]; h->whh[l][d] = base + o_whh[l][d]; h->bias[l][d] = base + o_b[l][d];
+        }
+        h->wxcat[l] = base + o_wxcat[l]; h->bcat[l] = base + o_bcat[l];
+    }
+    h->head_w = base + o_head[0]; h->head_b = base + o_head[1]; h->head_wc = base + o_head[2]; h->head_bc = base + o_head[3];
+    e = cudaMalloc(&h->d_flag, 64);
+    if (e == cudaSuccess) e = cudaMemset(h->d_flag, 0, 64);
+    for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
+    if (e != cudaSuccess) { cb_set_error("cb_create: %s", cudaGetErrorString(e)); cb_destroy(h); return CB_ERR_CUDA; }
+    if (precision != CB_PREC_FP32) {
+        int rc = cb_tc_prepare(h, hb.data.data());
+        if (rc != CB_OK) { cb_destroy(h); return rc; }
+    }
+    *out = h;
+    return CB_OK;
+}
+
+extern "C" int cb_destroy(cb_handle* h) {
+    if (!h) return CB_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    cb_tc_release(h);
+    if (h->d_weights) cudaFree(h->d_weights);
+    if (h->ws) cudaFree(h->ws);
+    if (h->stage) cudaFree(h->stage);
+    if (h->beam_ws) cudaFree(h->beam_ws);
+    if (h->asm_ws) cudaFree(h->asm_ws);
+    if (h->d_flag) cudaFree(h->d_flag);
+    for (int i = 0; i < 8; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    delete h;
+    return CB_OK;
+}
+
+extern "C" int cb_out_len(const cb_handle* h, int L) { return h ? out_len_of(h->cfg, L) : CB_ERR_ARG; }
+extern "C" int cb_n_class(const cb_handle* h) { return h ? h->cfg.n_class : CB_ERR_ARG; }
+extern "C" int cb_precision(const cb_handle* h) { return h ? h->precision : CB_ERR_ARG; }
+extern "C" size_t cb_workspace_bytes(const cb_handle* h) { return h ? h->ws_bytes + h->stage_bytes + h->beam_ws_bytes + h->asm_ws_bytes : 0; }
+extern "C" long long cb_launch_count(const cb_handle* h) { return h ? h->launches : 0; }
+extern "C" void cb_enable_timing(cb_handle* h, int on) { if (h) h->timing = on; }
+
+extern "C" int cb_last_forward_ms(const cb_handle* h, float* ms, int n) {
+    if (!h || !ms || !h->have_ms) return 0;
+    // events were recorded on the stream of the last cb_forward; the caller has synchronised it
+    float v[4] = {0, 0, 0, 0};
+    if (cudaEventElapsedTime(&v[0], h->ev[0], h->ev[1]) != cudaSuccess) return 0;   // residual conv stack
+    cudaEventElapsedTime(&v[1], h->ev[1], h->ev[2]);                                  // BiLSTM stack
+    cudaEventElapsedTime(&v[2], h->ev[2], h->ev[3]);                                  // head + path_prob
+    cudaEventElapsedTime(&v[3], h->ev[0], h->ev[3]);                                  // total
+    const int m = n < 4 ? n : 4;
+    for (int i = 0; i < m; ++i) ms[i] = v[i];
+    return m;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+static int ensure_workspace(cb_handle* h, int B, int L) {
+    const CbConfig& c = h->cfg;
+    const int T = out_len_of(c, L);
+    const size_t act_floats = (size_t)B * L * c.channels;
+    const size_t pre_floats = (size_t)B * T * 8 * c.hidden;
+    const size_t out_floats = (size_t)B * T * 2 * c.hidden;
+    const size_t need = (3 * align_up(act_floats, 64) + align_up(pre_floats, 64) + 2 * align_up(out_floats, 64)) * sizeof(float);
+    if (need > h->ws_bytes) {
+        if (h->ws) { cudaFree(h->ws); h->ws = nullptr; h->ws_bytes = 0; }
+        cudaError_t e = cudaMalloc(&h->ws, need);
+        if (e != cudaSuccess) { cb_set_error("workspace cudaMalloc(%zu bytes): %s", need, cudaGetErrorString(e)); return CB_ERR_NOMEM; }
+        h->ws_bytes = need;
+    }
+    float* p = (float*)h->ws;
+    for (int i = 0; i < 3; ++i) { h->act[i] = p; p += align_up(act_floats, 64); }
+    h->pre = p; p += align_up(pre_floats, 64);
+    for (int i = 0; i < 2; ++i) { h->lstm_out[i] = p; p += align_up(out_floats, 64); }
+    return CB_OK;
+}
+
+static int run_gemm(cb_handle* h, const GemmProblem& p, cudaStream_t s) {
+    if (h->precision == CB_PREC_FP32) return cb_launch_gemm_simt(h, p, s);
+    return cb_launch_gemm_tc(h, p, s);
+}
+
+extern "C" int cb_seq_len_out(cb_handle* h, const int32_t* seq_len_in, int B, int L, int32_t* seq_len_out, void* stream) {
+    if (!h || !seq_len_in || !seq_len_out || B < 0 || L < 1) { cb_set_error("cb_seq_len_out: bad arguments"); return CB_ERR_ARG; }
+    CB_CUDA(cudaSetDevice(h->device));
+    return cb_launch_seq_len(h, seq_len_in, B, L, out_len_of(h->cfg, L), seq_len_out, (cudaStream_t)stream);
+}
+
+extern "C" int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_out, int B, int L, float* logits,
+                          float* path_prob, void* stream) {
+    if (!h || !x || !seq_len_out || !logits || B < 0 || L < 1) { cb_set_error("cb_forward: bad arguments"); return CB_ERR_ARG; }
+    if (B == 0) return CB_OK;
+    if ((long long)B * L > 0x7fffffffLL / 2) { cb_set_error("cb_forward: B*L too large"); return CB_ERR_ARG; }
+    CB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = ensure_workspace(h, B, L);
+    if (rc != CB_OK) return rc;
+    const CbConfig& c = h->cfg;
+    const int C = c.channels, H = c.hidden;
+    if (h->timing) CB_CUDA(cudaEventRecord(h->ev[0], s));
+
+    // ---- residual conv stack (cnn.py:234-262, 380-389) ----------------------------------------------------------
+    int t_in = L;
+    const float* X = nullptr;          // block input (nullptr = raw signal for block 1)
+    int xi = -1;                       // which act[] buffer holds X
+    for (int b = 0; b < c.n_blocks; ++b) {
+        const int st = c.stride[b], k = c.k[b];
+        const int t_out = (t_in + st - 1) / st;
+        int pad = (t_out - 1) * st + k - t_in; if (pad < 0) pad = 0;     // TF 'SAME'
+        const int left = pad / 2;
+        int ia = (xi + 1) % 3, ib = (xi + 2) % 3;     // scratch buffers that are not X
+        if (xi < 0) { ia = 0; ib = 1; }
+        GemmProblem g;
+        if (b > 0) {                   // conv2a 1x1 + BN + ReLU  -> act[ia]   (block 1 generates it on the fly)
+            memset(&g, 0, sizeof(g));
+            g.M = B * t_in; g.N = C; g.K = C; g.t_out = t_in;
+            g.t_in0 = t_in; g.stride0 = 1; g.taps = 1; g.left = 0; g.c0 = C; g.src0 = X; g.lda0 = C;
+            g.W = h->conv2a[b].W; g.shift = h->conv2a[b].shift; g.relu = 1; g.out = h->act[ia]; g.ldo = C;
+            g.layer_id = b * 4 + 0;
+            if ((rc = run_gemm(h, g, s)) != CB_OK) return rc;
+        }
+        // conv2b 1xk (stride) + BN + ReLU -> act[ib]
+        memset(&g, 0, sizeof(g));
+        g.M = B * t_out; g.N = C; g.K = k * C; g.t_out = t_out;
+        g.t_in0 = t_in; g.stride0 = st; g.taps = k; g.left = left; g.c0 = C;
+        if (b == 0) { g.gen = 1; g.x = x; g.gw = h->g_w; g.ginv = h->g_inv; g.gsh = h->g_sh; }
+        else { g.src0 = h->act[ia]; g.lda0 = C; }
+        g.W = h->conv2b[b].W; g.shift = h->conv2b[b].shift; g.relu = 1; g.out = h->act[ib]; g.ldo = C;
+        g.layer_id = b * 4 + 1;
+        if ((rc = run_gemm(h, g, s)) != CB_OK) return rc;
+        // conv2c 1x1 + BN, + branch1 (1x1 conv of the block input, stride st), ReLU -> act[ia]
+        memset(&g, 0, sizeof(g));
+        g.M = B * t_out; g.N = C; g.t_out = t_out;
+        g.t_in0 = t_out; g.stride0 = 1; g.taps = 1; g.left = 0; g.c0 = C; g.src0 = h->act[ib]; g.lda0 = C;
+        if (b == 0) {
+            g.K = C; g.res = 1; g.x = x; g.t_inr = t_in; g.strider = st; g.rw = h->r_w; g.rinv = h->r_inv; g.rsh = h->r_sh;
+        } else {
+            g.K = 2 * C; g.c1 = C; g.src1 = X; g.lda1 = C; g.t_in1 = t_in; g.stride1 = st;
+        }
+        g.W = h->convc[b].W; g.shift = h->convc[b].shift; g.relu = 1; g.out = h->act[ia]; g.ldo = C;
+        g.layer_id = b * 4 + 2;
+        if ((rc = run_gemm(h, g, s)) != CB_OK) return rc;
+        X = h->act[ia]; xi = ia; t_in = t_out;
+    }
+    const int T = t_in;
+    const int M = B * T;
+    h->fea = X;
+    if (h->timing) CB_CUDA(cudaEventRecord(h->ev[1], s));
+
+    // ---- BiLSTM stack (rnn.py:20-64 stacked-bidirectional; rnn.py:99-145 per-direction MultiRNNCell) ---------------
+    const float* Z = X; int ldz = C;
+    for (int l = 0; l < c.n_layers; ++l) {
+        GemmProblem g;
+        if (l == 0 || c.rnn_layout == 0) {
+            const int in = l == 0 ? C : 2 * H;
+            memset(&g, 0, sizeof(g));
+            g.M = M; g.N = 8 * H; g.K = in; g.t_out = T; g.t_in0 = T; g.stride0 = 1; g.taps = 1; g.c0 = in;
+            g.src0 = Z; g.lda0 = ldz; g.W = h->wxcat[l]; g.shift = h->bcat[l]; g.out = h->pre; g.ldo = 8 * H;
+            g.layer_id = 32 + l * 2;
+            if ((rc = run_gemm(h, g, s)) != CB_OK) return rc;
+        } else {
+            for (int d = 0; d < 2; ++d) {
+                memset(&g, 0, sizeof(g));
+                g.M = M; g.N = 4 * H; g.K = H; g.t_out = T; g.t_in0 = T; g.stride0 = 1; g.taps = 1; g.c0 = H;
+                g.src0 = Z + d * H; g.lda0 = ldz; g.W = h->wx[l][d]; g.shift = h->bias[l][d];
+                g.out = h->pre + d * 4 * H; g.ldo = 8 * H;
+                g.layer_id = 32 + l * 2 + d;
+                if ((rc = run_gemm(h, g, s)) != CB_OK) return rc;
+            }
+        }
+        LstmProblem lp;
+        memset(&lp, 0, sizeof(lp));
+        lp.B = B; lp.T = T; lp.H = H; lp.pre = h->pre; lp.ld_pre = 8 * H; lp.whh[0] = h->whh[l][0]; lp.whh[1] = h->whh[l][1];
+        lp.lens = seq_len_out; lp.out = h->lstm_out[l & 1]; lp.ldo = 2 * H; lp.layer = l;
+        if (h->precision == CB_PREC_FP32) rc = cb_launch_lstm_simt(h, lp, s);
+        else rc = cb_launch_lstm_tc(h, lp, s);
+        if (rc != CB_OK) return rc;
+        Z = h->lstm_out[l & 1]; ldz = 2 * H;
+    }
+    if (h->timing) CB_CUDA(cudaEventRecord(h->ev[2], s));
+
+    // ---- head + path_prob ----------------------------------------------------------------------------------------
+    if ((rc = cb_launch_head(h, Z, M, logits, s)) != CB_OK) return rc;
+    if (path_prob && (rc = cb_launch_path_prob(h, logits, B, T, path_prob, s)) != CB_OK) return rc;
+    if (h->timing) { CB_CUDA(cudaEventRecord(h->ev[3], s)); h->have_ms = 1; }
+    h->last_B = B; h->last_T = T;
+    return CB_OK;
+}
+
+extern "C" int cb_decode_greedy(cb_handle* h, const float* logits, const int32_t* seq_len_out, int B, int T,
+                                int8_t* bases, int32_t* n_bases, void* stream) {
+    if (!h || !logits || !seq_len_out || !bases || !n_bases || B < 0 || T < 1) { cb_set_error("cb_decode_greedy: bad arguments"); return CB_ERR_ARG; }
+    CB_CUDA(cudaSetDevice(h->device));
+    return cb_launch_greedy(h, logits, seq_len_out, B, T, bases, n_bases, (cudaStream_t)stream);
+}
+
+extern "C" int cb_decode_beam(cb_handle* h, const float* logits, const int32_t* seq_len_out, int B, int T, int beam_width,
+                              int8_t* bases, int32_t* n_bases, void* stream) {
+    if (!h || !logits || !seq_len_out || !bases || !n_bases || B < 0 || T < 1 || beam_width < 1) { cb_set_error("cb_decode_beam: bad arguments"); return CB_ERR_ARG; }
+    CB_CUDA(cudaSetDevice(h->device));
+    return cb_launch_beam(h, logits, seq_len_out, B, T, beam_width, bases, n_bases, (cudaStream_t)stream);
+}
+
+extern "C" int cb_assemble(cb_handle* h, const int8_t* bases, const int32_t* n_bases, const float* path_prob,
+                           int n_windows, int T, int jump, int L, int kernel, int8_t* consensus, char* qual,
+                           int32_t* pos, int32_t* out_len, int max_len, void* stream) {
+    if (!h || !bases || !n_bases || !consensus || !pos || !out_len || n_windows < 0 || T < 1 || L < 1 || max_len < 0 ||
+        kernel < CB_ASM_SIMPLE || kernel > CB_ASM_STICK || (qual && !path_prob)) {
+        cb_set_error("cb_assemble: bad arguments");
+        return CB_ERR_ARG;
+    }
+    CB_CUDA(cudaSetDevice(h->device));
+    return cb_launch_assemble(h, bases, n_bases, path_prob, n_windows, T, jump, L, kernel, consensus, qual, pos, out_len,
+                              max_len, (cudaStream_t)stream);
+}
+
+// ---- host-buffer wrappers ----------------------------------------------------------------------------------------
+static int ensure_stage(cb_handle* h, size_t bytes) {
+    if (bytes <= h->stage_bytes) return CB_OK;
+    if (h->stage) { cudaFree(h->stage); h->stage = nullptr; h->stage_bytes = 0; }
+    cudaError_t e = cudaMalloc(&h->stage, bytes);
+    if (e != cudaSuccess) { cb_set_error("staging cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e)); return CB_ERR_NOMEM; }
+    h->stage_bytes = bytes;
+    return CB_OK;
+}
+
+extern "C" int cb_basecall_host(cb_handle* h, const float* x, const int32_t* seq_len_in, int B, int L, int beam_width,
+                                int8_t* bases, int32_t* n_bases, float* path_prob, float* logits) {
+    if (!h || !x || !seq_len_in || !bases || !n_bases || B < 0 || L < 1 || beam_width < 0) { cb_set_error("cb_basecall_host: bad arguments"); return CB_ERR_ARG; }
+    if (B == 0) return CB_OK;
+    CB_CUDA(cudaSetDevice(h->device));
+    const int T = out_len_of(h->cfg, L), C = h->cfg.n_class;
+    const size_t sz_x = align_up((size_t)B * L * 4, 256), sz_i = align_up((size_t)B * 4, 256);
+    const size_t sz_lg = align_up((size_t)B * T * C * 4, 256), sz_b = align_up((size_t)B * T, 256);
+    int rc = ensure_stage(h, sz_x + 4 * sz_i + sz_lg + sz_b);
+    if (rc != CB_OK) return rc;
+    char* p = (char*)h->stage;
+    float* d_x = (float*)p; p += sz_x;
+    int32_t* d_in = (int32_t*)p; p += sz_i;
+    int32_t* d_len = (int32_t*)p; p += sz_i;
+    int32_t* d_nb = (int32_t*)p; p += sz_i;
+    float* d_prob = (float*)p; p += sz_i;
+    float* d_lg = (float*)p; p += sz_lg;
+    int8_t* d_bases = (int8_t*)p;
+    cudaStream_t s = 0;
+    CB_CUDA(cudaMemcpyAsync(d_x, x, (size_t)B * L * 4, cudaMemcpyHostToDevice, s));
+    CB_CUDA(cudaMemcpyAsync(d_in, seq_len_in, (size_t)B * 4, cudaMemcpyHostToDevice, s));
+    if ((rc = cb_launch_seq_len(h, d_in, B, L, T, d_len, s)) != CB_OK) return rc;
+    if ((rc = cb_forward(h, d_x, d_len, B, L, d_lg, d_prob, s)) != CB_OK) return rc;
+    if (beam_width == 0) rc = cb_launch_greedy(h, d_lg, d_len, B, T, d_bases, d_nb, s);
+    else rc = cb_launch_beam(h, d_lg, d_len, B, T, beam_width, d_bases, d_nb, s);
+    if (rc != CB_OK) return rc;
+    CB_CUDA(cudaMemcpyAsync(bases, d_bases, (size_t)B * T, cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaMemcpyAsync(n_bases, d_nb, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    if (path_prob) CB_CUDA(cudaMemcpyAsync(path_prob, d_prob, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    if (logits) CB_CUDA(cudaMemcpyAsync(logits, d_lg, (size_t)B * T * C * 4, cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaStreamSynchronize(s));
+    return CB_OK;
+}
+
+extern "C" int cb_assemble_host(cb_handle* h, const int8_t* bases, const int32_t* n_bases, const float* path_prob,
+                                int n_windows, int T, int jump, int L, int kernel, int8_t* consensus, char* qual,
+                                int32_t* pos, int32_t* out_len, int max_len) {
+    if (!h || !bases || !n_bases || !consensus || !pos || !out_len || n_windows < 0 || T < 1 || max_len < 0) { cb_set_error("cb_assemble_host: bad arguments"); return CB_ERR_ARG; }
+    CB_CUDA(cudaSetDevice(h->device));
+    const size_t sz_b = align_up((size_t)n_windows * T + 1, 256), sz_i = align_up((size_t)n_windows * 4 + 4, 256);
+    const size_t sz_c = align_up((size_t)max_len + 1, 256);
+    char* buf = nullptr;
+    CB_CUDA(cudaMalloc(&buf, sz_b + 3 * sz_i + 2 * sz_c + 256));
+    char* p = buf;
+    int8_t* d_bases = (int8_t*)p; p += sz_b;
+    int32_t* d_nb = (int32_t*)p; p += sz_i;
+    float* d_pp = (float*)p; p += sz_i;
+    int32_t* d_pos = (int32_t*)p; p += sz_i;
+    int8_t* d_cons = (int8_t*)p; p += sz_c;
+    char* d_qual = (char*)p; p += sz_c;
+    int32_t* d_len = (int32_t*)p;
+    cudaStream_t s = 0;
+    int rc = CB_OK;
+    cudaError_t e = cudaSuccess;
+    if (n_windows > 0) {
+        e = cudaMemcpyAsync(d_bases, bases, (size_t)n_windows * T, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_nb, n_bases, (size_t)n_windows * 4, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess && path_prob) e = cudaMemcpyAsync(d_pp, path_prob, (size_t)n_windows * 4, cudaMemcpyHostToDevice, s);
+    }
+    if (e == cudaSuccess)
+        rc = cb_assemble(h, d_bases, d_nb, path_prob ? d_pp : nullptr, n_windows, T, jump, L, kernel, d_cons,
+                         qual ? d_qual : nullptr, d_pos, d_len, max_len, s);
+    if (rc == CB_OK && e == cudaSuccess) {
+        e = cudaMemcpyAsync(out_len, d_len, 4, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && n_windows > 0) e = cudaMemcpyAsync(pos, d_pos, (size_t)n_windows * 4, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && max_len > 0) e = cudaMemcpyAsync(consensus, d_cons, max_len, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && qual && max_len > 0) e = cudaMemcpyAsync(qual, d_qual, max_len, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    }
+    cudaFree(buf);
+    if (e != cudaSuccess) { cb_set_error("cb_assemble_host: %s", cudaGetErrorString(e)); return CB_ERR_CUDA; }
+    return rc;
+}
+
+extern "C" long long cb_debug_fetch(cb_handle* h, int what, float* dst, size_t max_floats) {
+    if (!h || !dst || !h->last_B) { cb_set_error("cb_debug_fetch: nothing to fetch"); return CB_ERR_ARG; }
+    const size_t M = (size_t)h->last_B * h->last_T;
+    const float* src; size_t n;
+    if (what == 0) { src = h->fea; n = M * h->cfg.channels; }
+    else if (what >= 1 && what <= h->cfg.n_layers) { src = h->lstm_out[(what - 1) & 1]; n = M * 2 * h->cfg.hidden; }
+    else { cb_set_error("cb_debug_fetch: unknown tensor %d", what); return CB_ERR_ARG; }
+    if (n > max_floats) { cb_set_error("cb_debug_fetch: destination too small"); return CB_ERR_ARG; }
+    CB_CUDA(cudaSetDevice(h->device));
+    CB_CUDA(cudaDeviceSynchronize());
+    CB_CUDA(cudaMemcpy(dst, src, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return (long long)n;
+}
+
+extern "C" void* cb_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cb_set_error("cudaHostAlloc(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+
+extern "C" void cb_host_free(void* p) { if (p) cudaFreeHost(p); }

@@ -1,0 +1,125 @@
+// Internal declarations shared by the translation units of libchiron_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/chiron_b200.h"
+
+#define CB_MAX_BLOCKS 8
+#define CB_MAX_LAYERS 8
+
+void cb_set_error(const char* fmt, ...);
+
+#define CB_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            cb_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return CB_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+#define CB_CHECK_LAUNCH()                                                                      \
+    do {                                                                                       \
+        cudaError_t e__ = cudaGetLastError();                                                  \
+        if (e__ != cudaSuccess) {                                                              \
+            cb_set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return CB_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+// ---- model (host copy of the CBW1 header) ----------------------------------------------------------------------
+struct CbConfig {
+    int n_blocks, channels, hidden, n_layers, n_class, rnn_layout, branch1_bn_mask;
+    int k[CB_MAX_BLOCKS], stride[CB_MAX_BLOCKS];
+    int sig_norm, reverse_signal;
+};
+
+// ---- one dense contraction  out[M,N] = act(A_gather[M,K] @ W[K,N] + shift[N] (+ rank-1 residual)) -----------------
+// A row m = output frame (b = m / t_out, to = m % t_out).  K is the concatenation of
+//   part 0: `taps` taps of c0 channels: frame ti = to*stride0 + j - left (zero outside [0,t_in0)), read from src0 with
+//           row stride lda0, or generated on the fly from the raw signal (gen != 0, block-1 conv2a, cnn.py:254):
+//           a = relu((x*gw[c])*ginv[c] + gsh[c]);
+//   part 1: c1 channels of src1 at frame to*stride1 of a t_in1-frame window (the 1x1 branch1 conv input,
+//           cnn.py:251), row stride lda1.
+struct GemmProblem {
+    int M, N, K;              // K = taps*c0 + c1
+    int t_out;
+    int t_in0, stride0, taps, left, c0;
+    int t_in1, stride1, c1;
+    const float* src0; int lda0;
+    const float* src1; int lda1;
+    int gen;                  // 1: part 0 generated from x (rank-1 conv + BN + ReLU)
+    const float* x;           // raw window samples: [B*t_in0] for gen, [B*t_inr] for the residual
+    const float *gw, *ginv, *gsh;
+    const float* W;           // [K,N] fp32, BN scale folded in (SIMT path)
+    const float* shift;       // [N]
+    int relu;
+    int res, t_inr, strider;  // res=1: add rank-1 residual (x[to*strider]*rw[n])*rinv[n] + rsh[n] before the ReLU
+    const float *rw, *rinv, *rsh;
+    float* out; int ldo;
+    int layer_id;             // which prepared tensor-core weight image belongs to this contraction
+};
+
+struct LstmProblem {         // both directions of one layer (grid.y = direction)
+    int B, T, H;
+    const float* pre;         // [B*T, ld_pre] hoisted input projection + bias; direction d uses columns [d*4H, (d+1)*4H)
+    int ld_pre;
+    const float* whh[2];      // [H,4H] fp32 recurrent kernels (fw, bw)
+    const int32_t* lens;      // [B]
+    float* out; int ldo;      // h of direction d written to out[(b*T+t)*ldo + d*H + u]; zeros for t >= len
+    int layer;
+};
+
+struct cb_handle {
+    int device;
+    int precision;
+    CbConfig cfg;
+    int sm_count;
+    // device weights (fp32, derived)
+    float* d_weights;                 // one allocation holding everything below
+    size_t weights_floats;
+    struct ConvW { const float *W, *shift; } conv2a[CB_MAX_BLOCKS], conv2b[CB_MAX_BLOCKS], convc[CB_MAX_BLOCKS];
+    const float *g_w, *g_inv, *g_sh;  // block-1 conv2a rank-1 generator
+    const float *r_w, *r_inv, *r_sh;  // block-1 branch1 rank-1 residual
+    const float* wx[CB_MAX_LAYERS][2];   // LSTM input kernels  [in,4H] per direction
+    const float* bias[CB_MAX_LAYERS][2]; // [4H]
+    const float* wxcat[CB_MAX_LAYERS];   // [in, 8H] fw||bw (stacked-bidirectional layout)
+    const float* bcat[CB_MAX_LAYERS];    // [8H]
+    const float* whh[CB_MAX_LAYERS][2];  // [H,4H]
+    const float *head_w, *head_b, *head_wc, *head_bc;
+    // workspace
+    void* ws; size_t ws_bytes;
+    float *act[3]; float* pre; float* lstm_out[2];
+    int ws_B, ws_L;
+    void* stage; size_t stage_bytes;   // device staging of the host-buffer API
+    const float* fea;                  // CNN feature of the last forward (debug fetch)
+    void* tc;                          // tensor-core path state (cb_tc.cu)
+    void* beam_ws; size_t beam_ws_bytes;
+    void* asm_ws; size_t asm_ws_bytes;
+    int* d_flag;
+    long long launches;
+    int timing; cudaEvent_t ev[8]; float last_ms[5]; int have_ms;
+    int last_B, last_T;
+};
+
+// ---- launchers (each returns CB_OK or an error code; they bump h->launches) -----------------------------------------
+int cb_launch_gemm_simt(cb_handle* h, const GemmProblem& p, cudaStream_t s);
+int cb_launch_lstm_simt(cb_handle* h, const LstmProblem& p, cudaStream_t s);
+int cb_launch_gemm_tc(cb_handle* h, const GemmProblem& p, cudaStream_t s);
+int cb_launch_lstm_tc(cb_handle* h, const LstmProblem& p, cudaStream_t s);
+int cb_tc_prepare(cb_handle* h, const float* host_weights);   // build fp16 hi/lo operand images from d_weights layout
+void cb_tc_release(cb_handle* h);
+int cb_launch_head(cb_handle* h, const float* lasth, int M, float* logits, cudaStream_t s);
+int cb_launch_path_prob(cb_handle* h, const float* logits, int B, int T, float* prob, cudaStream_t s);
+int cb_launch_seq_len(cb_handle* h, const int32_t* in, int B, int L, int T, int32_t* out, cudaStream_t s);
+int cb_launch_greedy(cb_handle* h, const float* logits, const int32_t* lens, int B, int T, int8_t* bases,
+                     int32_t* n_bases, cudaStream_t s);
+int cb_launch_beam(cb_handle* h, const float* logits, const int32_t* lens, int B, int T, int W, int8_t* bases,
+                   int32_t* n_bases, cudaStream_t s);
+int cb_launch_assemble(cb_handle* h, const int8_t* bases, const int32_t* n_bases, const float* path_prob, int n_windows,
+                       int T, int jump, int L, int kernel, int8_t* consensus, char* qual, int32_t* pos,
+                       int32_t* out_len, int max_len, cudaStream_t s);

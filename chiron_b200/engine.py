@@ -1,0 +1,166 @@
+"""Python face of the C ABI: one ``Basecaller`` per GPU.
+
+Replaces ``build_eval_graph`` / ``net`` (chiron/chiron_eval.py:244-376): the TF session + queues become a handle on
+libchiron_b200.so.  Host (numpy) calls go through ``cb_basecall_host`` / ``cb_assemble_host``; device calls take torch
+CUDA tensors (torch is plumbing for device memory and streams only) and pass raw pointers."""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .model import load_model
+
+BASES = "ACGT"
+
+
+def index2base(read: Sequence[int]) -> str:
+    """chiron/chiron_eval.py:100-113."""
+    return "".join(BASES[int(x)] for x in read)
+
+
+def get_assembler_kernal(jump: int, segment_len: int) -> str:
+    """chiron/chiron_eval.py:138-150 (same name, same thresholds)."""
+    assembler = "simple"
+    if jump > 0.9 * segment_len:
+        assembler = "glue"
+    if jump >= segment_len:
+        assembler = "stick"
+    return assembler
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Basecaller:
+    def __init__(self, model: str = "DNA_default", device: int = 0, precision: str = "fp32"):
+        self.lib = _lib.load()
+        self.cfg, _, blob = load_model(model)
+        self.device = int(device)
+        self.precision = precision
+        h = ctypes.c_void_p()
+        buf = ctypes.create_string_buffer(blob, len(blob))
+        _lib.check(self.lib.cb_create(ctypes.cast(buf, ctypes.c_void_p), len(blob), self.device,
+                                      _lib.PRECISIONS[precision], ctypes.byref(h)), "cb_create")
+        self.h = h
+        self.n_class = self.lib.cb_n_class(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- facts -------------------------------------------------------------------------------------------------
+    def out_len(self, L: int) -> int:
+        return self.lib.cb_out_len(self.h, int(L))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.cb_launch_count(self.h))
+
+    def enable_timing(self, on: bool = True):
+        self.lib.cb_enable_timing(self.h, int(on))
+
+    def last_forward_ms(self) -> List[float]:
+        arr = (ctypes.c_float * 4)()
+        n = self.lib.cb_last_forward_ms(self.h, arr, 4)
+        return [float(arr[i]) for i in range(n)]
+
+    # ---- host (numpy) path: what `evaluation()` uses -----------------------------------------------------------
+    def basecall_batch(self, x: np.ndarray, seq_len: np.ndarray, beam: int = 0, want_logits: bool = False):
+        """x [B,L] float32 windows, seq_len [B] int32 true lengths.  Returns (bases[B,T] int8, n_bases[B],
+        path_prob[B], logits[B,T,C] or None)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        seq_len = np.ascontiguousarray(seq_len, dtype=np.int32)
+        B, L = x.shape
+        T = self.out_len(L)
+        bases = np.zeros((B, T), dtype=np.int8)
+        n_bases = np.zeros(B, dtype=np.int32)
+        prob = np.zeros(B, dtype=np.float32)
+        logits = np.zeros((B, T, self.n_class), dtype=np.float32) if want_logits else None
+        _lib.check(self.lib.cb_basecall_host(self.h, _ptr(x), _ptr(seq_len), B, L, int(beam), _ptr(bases),
+                                             _ptr(n_bases), _ptr(prob), _ptr(logits)), "cb_basecall_host")
+        return bases, n_bases, prob, logits
+
+    def assemble(self, bases: np.ndarray, n_bases: np.ndarray, path_prob: Optional[np.ndarray], jump: int, L: int,
+                 kernel: Optional[str] = None, with_qs: bool = True) -> Tuple[str, Optional[str], np.ndarray]:
+        """simple_assembly(_qs) + argmax + qs() for one read; windows in true order.  Returns (sequence, quality
+        string or None, pos[n_windows])."""
+        bases = np.ascontiguousarray(bases, dtype=np.int8)
+        n_bases = np.ascontiguousarray(n_bases, dtype=np.int32)
+        n, T = bases.shape
+        kernel = kernel or get_assembler_kernal(jump, L)
+        max_len = int(n_bases.sum()) + 1
+        cons = np.zeros(max_len, dtype=np.int8)
+        qual = np.zeros(max_len, dtype=np.uint8) if with_qs else None
+        pos = np.zeros(max(n, 1), dtype=np.int32)
+        out_len = np.zeros(1, dtype=np.int32)
+        pp = np.ascontiguousarray(path_prob, dtype=np.float32) if path_prob is not None else None
+        if with_qs and pp is None:
+            raise ValueError("quality scores need path_prob")
+        _lib.check(self.lib.cb_assemble_host(self.h, _ptr(bases), _ptr(n_bases), _ptr(pp), n, T, int(jump), int(L),
+                                             _lib.ASM_KERNELS[kernel], _ptr(cons), _ptr(qual), _ptr(pos),
+                                             _ptr(out_len), max_len), "cb_assemble_host")
+        ln = int(out_len[0])
+        seq = index2base(cons[:ln])
+        q = bytes(qual[:ln]).decode("latin-1") if with_qs else None
+        return seq, q, pos[:n]
+
+    # ---- device (torch tensor) path: bench / multi-stream pipelines ----------------------------------------------
+    def forward_device(self, x, seq_len_out, logits=None, path_prob=None, stream=None):
+        """x [B,L] float32 CUDA tensor, seq_len_out [B] int32 CUDA tensor (already divided by ratio)."""
+        import torch
+        B, L = x.shape
+        T = self.out_len(L)
+        if logits is None:
+            logits = torch.empty((B, T, self.n_class), dtype=torch.float32, device=x.device)
+        if path_prob is None:
+            path_prob = torch.empty((B,), dtype=torch.float32, device=x.device)
+        s = stream if stream is not None else torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(self.lib.cb_forward(self.h, x.data_ptr(), seq_len_out.data_ptr(), B, L, logits.data_ptr(),
+                                       path_prob.data_ptr(), ctypes.c_void_p(s)), "cb_forward")
+        return logits, path_prob
+
+    def seq_len_out_device(self, seq_len_in, L: int, out=None, stream=None):
+        import torch
+        B = seq_len_in.shape[0]
+        if out is None:
+            out = torch.empty((B,), dtype=torch.int32, device=seq_len_in.device)
+        s = stream if stream is not None else torch.cuda.current_stream(seq_len_in.device).cuda_stream
+        _lib.check(self.lib.cb_seq_len_out(self.h, seq_len_in.data_ptr(), B, int(L), out.data_ptr(),
+                                           ctypes.c_void_p(s)), "cb_seq_len_out")
+        return out
+
+    def decode_device(self, logits, seq_len_out, beam: int = 0, bases=None, n_bases=None, stream=None):
+        import torch
+        B, T, _ = logits.shape
+        if bases is None:
+            bases = torch.empty((B, T), dtype=torch.int8, device=logits.device)
+        if n_bases is None:
+            n_bases = torch.empty((B,), dtype=torch.int32, device=logits.device)
+        s = stream if stream is not None else torch.cuda.current_stream(logits.device).cuda_stream
+        if beam == 0:
+            _lib.check(self.lib.cb_decode_greedy(self.h, logits.data_ptr(), seq_len_out.data_ptr(), B, T,
+                                                 bases.data_ptr(), n_bases.data_ptr(), ctypes.c_void_p(s)),
+                       "cb_decode_greedy")
+        else:
+            _lib.check(self.lib.cb_decode_beam(self.h, logits.data_ptr(), seq_len_out.data_ptr(), B, T, int(beam),
+                                               bases.data_ptr(), n_bases.data_ptr(), ctypes.c_void_p(s)),
+                       "cb_decode_beam")
+        return bases, n_bases
+
+    def debug_fetch(self, what: int, n_floats: int) -> np.ndarray:
+        out = np.zeros(n_floats, dtype=np.float32)
+        n = self.lib.cb_debug_fetch(self.h, int(what), _ptr(out), n_floats)
+        if n < 0:
+            _lib.check(int(n), "cb_debug_fetch")
+        return out[:n]

@@ -1,0 +1,126 @@
+/* chiron_b200 -- C ABI of the B200-native basecalling hot path.
+ *
+ * The reference (haotianteng/Chiron) has no FFI: its operator boundary is the pair of TensorFlow session calls
+ *   sess.run(logits_enqueue, {x[B,L] f32, seq_length[B] i32, training=False})     chiron/chiron_eval.py:335-342
+ *   sess.run([decoded_fname, decode_idx, decode_predict, decode_prob])            chiron/chiron_eval.py:408-409
+ * restated as a SavedModel signature {x, seq_len} -> {indices, values, dense_shape, logits, prob_logits}
+ * in chiron/export_test.py:103-113.  Every entry point below names the reference code it replaces.
+ *
+ * Conventions: plain C, no torch types.  All functions return 0 on success or a negative CB_ERR_* code;
+ * cb_last_error() gives the message of the last failure on the calling thread.  Unless a function says "host",
+ * pointers are DEVICE pointers on the handle's GPU and work is enqueued asynchronously on `stream`
+ * (a cudaStream_t passed as void*; NULL = the legacy default stream).  One handle per GPU; a handle is not
+ * re-entrant (the reference has a single in-flight forward pass: one feeder thread, chiron_eval.py:369-372).
+ */
+#ifndef CHIRON_B200_H
+#define CHIRON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cb_handle cb_handle;
+
+enum {
+    CB_OK = 0,
+    CB_ERR_ARG = -1,      /* bad argument / unsupported shape */
+    CB_ERR_BLOB = -2,     /* malformed weight blob */
+    CB_ERR_CUDA = -3,     /* CUDA runtime failure (message has the cudaError string) */
+    CB_ERR_NOMEM = -4,    /* workspace allocation failed */
+    CB_ERR_RANGE = -5     /* an activation left the fp16 range of the tensor-core path; rerun with CB_PREC_FP32 */
+};
+
+/* Arithmetic of the dense contractions (convolutions, LSTM gate GEMMs).  Accumulation is always fp32. */
+enum {
+    CB_PREC_FP32 = 0,     /* fp32 FFMA SIMT kernels (reference-grade; slow path kept for A/B checks) */
+    CB_PREC_TC_SPLIT = 1, /* tcgen05 fp16 MMAs on hi/lo-split operands (3 MMAs per product, fp32-class error) */
+    CB_PREC_TC_FAST = 2   /* tcgen05 single-pass fp16 MMAs (~1e-3 relative; not bit-parity safe) */
+};
+
+/* Assembly kernels, chiron/chiron_eval.py:138-150 (get_assembler_kernal). */
+enum { CB_ASM_SIMPLE = 0, CB_ASM_GLUE = 1, CB_ASM_STICK = 2 };
+
+/* -- lifecycle --------------------------------------------------------------------------------------------------- */
+
+/* Upload a CBW1 weight blob (chiron_b200/model.py), fold population BatchNorm into the conv weights, build the
+ * packed operand images.  Replaces build_eval_graph + tf.train.Saver.restore (chiron_eval.py:244-276).
+ * `blob` is a HOST pointer. */
+int cb_create(const void* blob, size_t nbytes, int device, int precision, cb_handle** out);
+int cb_destroy(cb_handle* h);
+const char* cb_last_error(void);
+const char* cb_version(void);
+
+/* Model facts read from the blob header. */
+int cb_out_len(const cb_handle* h, int L);            /* CNN output frames T for an L-sample window (ratio = L/T) */
+int cb_n_class(const cb_handle* h);                   /* 5: A C G T blank */
+int cb_precision(const cb_handle* h);
+size_t cb_workspace_bytes(const cb_handle* h);        /* current device workspace (grown on demand) */
+
+/* -- the per-window hot path (device pointers, async) --------------------------------------------------------------- */
+
+/* seq_len_out[b] = round_half_even(seq_len_in[b] / ratio)  -- chiron_eval.py:337.  */
+int cb_seq_len_out(cb_handle* h, const int32_t* seq_len_in, int B, int L, int32_t* seq_len_out, void* stream);
+
+/* chiron_model.inference (chiron_model.py:134-172: getcnnfeature -> rnn_layers -> logits) + path_prob
+ * (chiron_eval.py:116-136).  x[B,L] normalised signal windows (zero padded); seq_len_out[B] frames per window
+ * (already divided by ratio); logits[B,T,n_class]; path_prob[B] (may be NULL). */
+int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_out, int B, int L,
+               float* logits, float* path_prob, void* stream);
+
+/* tf.nn.ctc_greedy_decoder(merge_repeated=True) (chiron_eval.py:486-487).  Dense padded output replaces the
+ * SparseTensor: bases[B,T] int8 (0..3), n_bases[B]; rows with n_bases == 0 are the rows sparse2dense drops. */
+int cb_decode_greedy(cb_handle* h, const float* logits, const int32_t* seq_len_out, int B, int T,
+                     int8_t* bases, int32_t* n_bases, void* stream);
+
+/* tf.nn.ctc_beam_search_decoder(merge_repeated=False, beam_width, top_paths=1) (chiron_eval.py:489-492). */
+int cb_decode_beam(cb_handle* h, const float* logits, const int32_t* seq_len_out, int B, int T, int beam_width,
+                   int8_t* bases, int32_t* n_bases, void* stream);
+
+/* simple_assembly(_qs) + argmax + qs() for ONE read (easy_assembler.py:302-335,393-442; chiron_eval.py:152-174,457).
+ * bases[n_windows,T] / n_bases[n_windows] / path_prob[n_windows] in TRUE window order (empty windows are skipped like
+ * sparse2dense does).  Outputs: consensus[max_len] int8 base indices, qual[max_len] phred+33 chars (may be NULL),
+ * pos[n_windows] window start coordinates (-1 for skipped windows), *out_len consensus length (device int32). */
+int cb_assemble(cb_handle* h, const int8_t* bases, const int32_t* n_bases, const float* path_prob,
+                int n_windows, int T, int jump, int L, int kernel,
+                int8_t* consensus, char* qual, int32_t* pos, int32_t* out_len, int max_len, void* stream);
+
+/* -- host-buffer convenience (what a Python/ctypes or cgo caller binds) ---------------------------------------------- */
+
+/* One batch through forward + decode with HOST buffers: copies x/seq_len_in to the GPU, runs cb_seq_len_out,
+ * cb_forward, cb_decode_greedy (beam_width == 0) or cb_decode_beam, copies bases/n_bases/path_prob (and logits when
+ * non-NULL) back and synchronises.  Replaces one _worker_fn feed + one decode dequeue (chiron_eval.py:335-342,
+ * 408-409). */
+int cb_basecall_host(cb_handle* h, const float* x, const int32_t* seq_len_in, int B, int L, int beam_width,
+                     int8_t* bases, int32_t* n_bases, float* path_prob, float* logits);
+
+/* Host-buffer form of cb_assemble for one read (synchronous). */
+int cb_assemble_host(cb_handle* h, const int8_t* bases, const int32_t* n_bases, const float* path_prob,
+                     int n_windows, int T, int jump, int L, int kernel,
+                     int8_t* consensus, char* qual, int32_t* pos, int32_t* out_len, int max_len);
+
+/* -- introspection for tests / benchmarks ----------------------------------------------------------------------------- */
+
+/* Number of kernels this library has launched on the handle since creation (bench.py's gpu_launches). */
+long long cb_launch_count(const cb_handle* h);
+
+/* Phase times of the last cb_forward (CUDA events on its stream; call after synchronising it): fills ms[0..n) with
+ * {conv stack, BiLSTM stack, head + path_prob, total}; returns how many entries were written. */
+int cb_last_forward_ms(const cb_handle* h, float* ms, int n);
+void cb_enable_timing(cb_handle* h, int on);
+
+/* Copy an intermediate activation of the last cb_forward to HOST memory (tests only).
+ * what: 0 = CNN feature [B*T,C]; n_layers-1 / n_layers = output [B*T,2H] of the last two LSTM layers (earlier ones are
+ * overwritten by the ping-pong buffers).  Returns floats copied or <0. */
+long long cb_debug_fetch(cb_handle* h, int what, float* dst, size_t max_floats);
+
+/* Pinned host memory for callers that want full-rate host<->device copies in cb_basecall_host. */
+void* cb_host_alloc(size_t bytes);
+void cb_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHIRON_B200_H */
