@@ -1,0 +1,90 @@
+"""GPU parity: CUDA path (through the C ABI) vs the CPU oracle on identical inputs."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import chiron_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 2e-3   # fp32 tolerance on CTC logits (|logit| <= ~20); see DESIGN.md "Numerics"
+
+
+def _read1_windows(cfg, L=400, jump=390):
+    sig = O.read_signal_text(os.path.join(GOLDEN, "DNA", "raw", "read1.signal"))
+    return O.make_windows(O.normalize_signal(sig, cfg.sig_norm), L, jump)
+
+
+@pytest.fixture(scope="module", params=["fp32"])
+def caller(request):
+    from chiron_b200.engine import Basecaller
+    bc = Basecaller("DNA_default", device=0, precision=request.param)
+    yield bc
+    bc.close()
+
+
+def test_logits_and_greedy_match_oracle_read1(caller, dna_model):
+    cfg, t, _ = dna_model
+    x, lens = _read1_windows(cfg)
+    n0 = len(x)
+    x, lens = x[n0 - 48:], lens[n0 - 48:]          # includes the ragged last window
+    ref = O.inference(x, lens, cfg, t)
+    bases, n_bases, prob, logits = caller.basecall_batch(x, lens, beam=0, want_logits=True)
+    assert np.abs(logits - ref).max() < LOGIT_TOL
+    ref_paths = O.ctc_greedy(ref, lens)
+    got = [bases[b, :n_bases[b]].tolist() for b in range(len(x))]
+    assert got == ref_paths
+    np.testing.assert_allclose(prob, O.path_prob(ref), rtol=0, atol=1e-4)
+
+
+def test_intermediates_match_oracle(caller, dna_model):
+    cfg, t, _ = dna_model
+    x, lens = _read1_windows(cfg)
+    x, lens = x[:8].copy(), lens[:8].copy()
+    lens[3] = 57
+    x[3, 57:] = 0
+    caller.basecall_batch(x, lens, beam=0)
+    fea = O.cnn_forward(x, cfg, t)
+    got = caller.debug_fetch(0, fea.size).reshape(fea.shape)
+    assert np.abs(got - fea).max() < 1e-3 * max(1.0, np.abs(fea).max())
+    lasth = O.rnn_forward(fea, lens, cfg, t)
+    got = caller.debug_fetch(cfg.n_layers, lasth.size).reshape(lasth.shape)
+    assert np.abs(got - lasth).max() < 1e-3
+    assert (got[3, 57:] == 0).all()               # dynamic_rnn: zero output past sequence_length
+
+
+def test_ragged_lengths_and_tiny_batches(caller, dna_model):
+    cfg, t, _ = dna_model
+    x, _ = _read1_windows(cfg, L=300, jump=290)
+    x = x[:5].copy()
+    lens = np.array([300, 1, 17, 299, 128], dtype=np.int32)
+    for b in range(5):
+        x[b, lens[b]:] = 0
+    ref = O.inference(x, lens, cfg, t)
+    bases, n_bases, prob, logits = caller.basecall_batch(x, lens, beam=0, want_logits=True)
+    assert np.abs(logits - ref).max() < LOGIT_TOL
+    assert [bases[b, :n_bases[b]].tolist() for b in range(5)] == O.ctc_greedy(ref, lens)
+    b1 = caller.basecall_batch(x[:1], lens[:1], want_logits=True)      # B = 1
+    assert np.abs(b1[3] - ref[:1]).max() < LOGIT_TOL
+
+
+def test_greedy_kernel_exact_on_synthetic_logits(caller):
+    """Decoder in isolation (seeded synthetic logits with exact ties exercising "first maximum wins"): bit-exact
+    against the C oracle, including len = 0 and len = T rows."""
+    import torch
+    rng = np.random.default_rng(3)
+    B, T = 64, 300
+    lg = rng.normal(size=(B, T, 5)).astype(np.float32)
+    lg[:, :, 4] += 2.0                                 # blank-dominant like real logits
+    lg[:, ::7, :] = np.round(lg[:, ::7, :])
+    lens = rng.integers(0, T + 1, size=B).astype(np.int32)
+    lens[0] = T
+    lens[1] = 0
+    ref = O.ctc_decode_c(lg, lens, 0)
+    dl, dn = torch.from_numpy(lg).cuda(), torch.from_numpy(lens).cuda()
+    bases, n_bases = caller.decode_device(dl, dn, beam=0)
+    torch.cuda.synchronize()
+    bases, n_bases = bases.cpu().numpy(), n_bases.cpu().numpy()
+    assert [bases[b, :n_bases[b]].tolist() for b in range(B)] == ref

@@ -1,7 +1,7 @@
 """Quick on-GPU timing of cb_forward phases (development aid, not the bench)."""
-import sys, os, time
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from chiron_b200.engine import Basecaller
 
 prec = sys.argv[1] if len(sys.argv) > 1 else "fp32"
