@@ -44,6 +44,12 @@ SIGNATURES = {
     "cb_host_free": (None, [c_void_p]),
 }
 
+# include/chiron_b200_selftest.h (test-only hooks; never used by the product path)
+SELFTEST_SIGNATURES = {
+    "cb_selftest_beam": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "cb_selftest_disp": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int]),
+}
+
 _LIB = None
 
 
@@ -61,7 +67,7 @@ def load():
             "%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` or "
             "`make -C chiron_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
-    for name, (res, args) in SIGNATURES.items():
+    for name, (res, args) in list(SIGNATURES.items()) + list(SELFTEST_SIGNATURES.items()):
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch, which must be loud
         fn.restype = res
         fn.argtypes = args

@@ -1,4 +1,281 @@
-// beam search + assembly kernels -- placeholder
+// CTC beam search and overlap assembly on the GPU (latency/branch-bound integer work; see cb_seq_algos.cuh for the
+// algorithms and the reference code they restate).
+//
+//  beam_kernel      one thread per window walks TF's trie beam search; the node pool + leaf slots of each window live
+//                   in a global workspace (L1/L2 resident), logits rows are read once (20 B/frame).
+//  assembly         asm_compact (drop empty windows like sparse2dense, chiron_eval.py:56-66) -> asm_disp (one thread per
+//                   adjacent window pair: stick / glue / difflib-exact simple displacement) -> asm_scan (prefix sum ->
+//                   window coordinates, read length) -> asm_vote (count matrix [4,len] + quality sums, atomics) ->
+//                   asm_finish (argmax + phred+33 string, chiron_eval.py:152-174,457).
 #include "cb_internal.cuh"
-int cb_launch_beam(cb_handle*, const float*, const int32_t*, int, int, int, int8_t*, int32_t*, cudaStream_t) { cb_set_error("beam search kernel not built yet"); return CB_ERR_ARG; }
-int cb_launch_assemble(cb_handle*, const int8_t*, const int32_t*, const float*, int, int, int, int, int, int8_t*, char*, int32_t*, int32_t*, int, cudaStream_t) { cb_set_error("assembly kernel not built yet"); return CB_ERR_ARG; }
+#include "cb_seq_algos.cuh"
+#include "../../include/chiron_b200_selftest.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- beam search -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) beam_kernel(const float* __restrict__ logits, const int32_t* __restrict__ lens,
+                                                  int B, int T, int C, int W, int pool, char* __restrict__ work,
+                                                  size_t work_stride, int8_t* __restrict__ bases,
+                                                  int32_t* __restrict__ n_bases, int* __restrict__ overflow) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int len = lens[b];
+    len = len < 0 ? 0 : (len > T ? T : len);
+    CbBeamWork k = cb_beam_work_carve(work + (size_t)b * work_stride, W, pool);
+    int8_t* dst = bases + (size_t)b * T;
+    int n = cb_beam_decode_one(logits + (size_t)b * T * C, len, C, W, k, dst);
+    if (n < 0) { atomicExch(overflow, 1); n = 0; }
+    for (int i = n; i < T; ++i) dst[i] = 0;
+    n_bases[b] = n;
+}
+
+// ---- assembly ----------------------------------------------------------------------------------------------------
+struct AsmWork {
+    int* list;       // [n_windows] indices of non-empty windows, in order
+    int* n_ne;       // [1]
+    int* disp;       // [n_windows] displacement of list[j] against list[j-1]; later the running position
+    int* length;     // [1] consensus length before clamping to max_len
+    int* counts;     // [4][max_len]
+    double* qsum;    // [4][max_len]
+    double* logfact; // [T+2]
+    int* scratch;    // [n_windows][scratch_stride]
+    size_t scratch_stride;
+};
+
+__global__ void __launch_bounds__(1024) asm_compact_kernel(const int32_t* __restrict__ n_bases, int n_windows, int T,
+                                                           AsmWork w, int32_t* __restrict__ pos) {
+    // single block: ordered compaction of the non-empty windows + the log-factorial table
+    __shared__ int warp_tot[32];
+    __shared__ int base;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) base = 0;
+    __syncthreads();
+    for (int start = 0; start < n_windows; start += blockDim.x) {
+        const int i = start + tid;
+        const int keep = (i < n_windows && n_bases[i] > 0) ? 1 : 0;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_tot[wid] = __popc(m);
+        __syncthreads();
+        int off = base;
+        for (int q = 0; q < wid; ++q) off += warp_tot[q];
+        if (keep) w.list[off + __popc(m & ((1u << lane) - 1u))] = i;
+        if (i < n_windows && !keep) pos[i] = -1;
+        __syncthreads();
+        if (tid == 0) { int tot = 0; for (int q = 0; q < (int)(blockDim.x >> 5); ++q) tot += warp_tot[q]; base += tot; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        *w.n_ne = base;
+        double acc = 0.0;                  // sum([np.log(x+1) for x in range(k)]) accumulated left to right
+        w.logfact[0] = 0.0;
+        for (int k = 1; k <= T + 1; ++k) { acc += log((double)k); w.logfact[k] = acc; }
+    }
+}
+
+__global__ void __launch_bounds__(128) asm_disp_kernel(const int8_t* __restrict__ bases, const int32_t* __restrict__ n_bases,
+                                                       int T, int kernel, double jsr, AsmWork w) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = *w.n_ne;
+    if (j >= n) return;
+    if (j == 0) { w.disp[0] = 0; return; }
+    const int wc = w.list[j], wp = w.list[j - 1];
+    const int8_t* cur = bases + (size_t)wc * T;
+    const int8_t* prev = bases + (size_t)wp * T;
+    const int la = n_bases[wc], lb = n_bases[wp];
+    int d;
+    if (kernel == CB_ASM_STICK) d = cb_disp_stick(la, lb);
+    else if (kernel == CB_ASM_GLUE) d = cb_disp_glue(cur, la, prev, lb);
+    else d = cb_disp_simple(cur, la, prev, lb, jsr, w.logfact, w.scratch + (size_t)j * w.scratch_stride);
+    w.disp[j] = d;
+}
+
+__global__ void __launch_bounds__(1024) asm_scan_kernel(const int32_t* __restrict__ n_bases, AsmWork w,
+                                                        int32_t* __restrict__ pos, int32_t* __restrict__ out_len,
+                                                        int max_len) {
+    // single block: inclusive scan of the displacements -> window coordinates; length = max_{j>=1}(pos_j + len_j)
+    __shared__ int warp_tot[32];
+    __shared__ int base, max_end;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = *w.n_ne;
+    if (tid == 0) { base = 0; max_end = 0; }
+    __syncthreads();
+    for (int start = 0; start < n; start += blockDim.x) {
+        const int j = start + tid;
+        int v = j < n ? w.disp[j] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+        if (lane == 31) warp_tot[wid] = v;
+        __syncthreads();
+        int off = base;
+        for (int q = 0; q < wid; ++q) off += warp_tot[q];
+        v += off;
+        if (j < n) {
+            w.disp[j] = v;                               // running position of window list[j]
+            pos[w.list[j]] = v;
+            if (j >= 1) atomicMax(&max_end, v + n_bases[w.list[j]]);   // window 0 never updates `length` (:316-318)
+        }
+        __syncthreads();
+        if (tid == blockDim.x - 1) base = v;
+        __syncthreads();
+    }
+    if (tid == 0) { *w.length = max_end; *out_len = max_end < max_len ? max_end : max_len; }
+}
+
+__global__ void __launch_bounds__(128) asm_vote_kernel(const int8_t* __restrict__ bases, const int32_t* __restrict__ n_bases,
+                                                       const float* __restrict__ path_prob, int T, AsmWork w, int max_len) {
+    // one block per non-empty window: add_count(_qs) (easy_assembler.py:381-388,435-442)
+    const int j = blockIdx.x;
+    if (j >= *w.n_ne) return;
+    const int wi = w.list[j];
+    const int len = n_bases[wi], p0 = w.disp[j];
+    int length = *w.length; if (length > max_len) length = max_len;
+    const double q = path_prob ? (double)path_prob[wi] : 0.0;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+        const int col = p0 + i;
+        if (col < 0 || col >= length) continue;          // negative start trims the head; beyond `length` is cut
+        const int base = bases[(size_t)wi * T + i] & 3;
+        atomicAdd(&w.counts[(size_t)base * max_len + col], 1);
+        if (path_prob) atomicAdd(&w.qsum[(size_t)base * max_len + col], q);
+    }
+}
+
+__global__ void __launch_bounds__(256) asm_finish_kernel(AsmWork w, int max_len, int8_t* __restrict__ consensus,
+                                                         char* __restrict__ qual) {
+    int length = *w.length; if (length > max_len) length = max_len;
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= length) return;
+    int c[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) c[r] = w.counts[(size_t)r * max_len + col];
+    int best = 0;
+#pragma unroll
+    for (int r = 1; r < 4; ++r) if (c[r] > c[best]) best = r;        // np.argmax: first maximum
+    consensus[col] = (int8_t)best;
+    if (!qual) return;
+    // qs(): np.argsort(axis=0) on 4 elements is a stable insertion sort; rows [2] and [3] of the sorted matrix
+    int idx[4] = {0, 1, 2, 3};
+#pragma unroll
+    for (int x = 1; x < 4; ++x) {
+        const int v = idx[x];
+        int y = x;
+        while (y > 0 && c[idx[y - 1]] > c[v]) { idx[y] = idx[y - 1]; --y; }
+        idx[y] = v;
+    }
+    const double c3 = (double)c[idx[3]], c2 = (double)c[idx[2]];
+    const double qs3 = w.qsum[(size_t)idx[3] * max_len + col];
+    char ch = '!';
+    if (c3 > 0.0) {
+        const double q = 10.0 * log10((c3 + 1.0) / (c2 + 1.0)) + qs3 / c3 / log(10.0);
+        ch = (char)((int)q + 33);                                     // astype(int): truncation toward zero
+    }
+    qual[col] = ch;
+}
+
+int ensure_buf(void** buf, size_t* cur, size_t need, const char* what) {
+    if (need <= *cur) return CB_OK;
+    if (*buf) { cudaFree(*buf); *buf = nullptr; *cur = 0; }
+    cudaError_t e = cudaMalloc(buf, need);
+    if (e != cudaSuccess) { cb_set_error("%s cudaMalloc(%zu bytes): %s", what, need, cudaGetErrorString(e)); return CB_ERR_NOMEM; }
+    *cur = need;
+    return CB_OK;
+}
+
+}  // namespace
+
+int cb_launch_beam(cb_handle* h, const float* logits, const int32_t* lens, int B, int T, int W, int8_t* bases,
+                   int32_t* n_bases, cudaStream_t s) {
+    if (B <= 0) return CB_OK;
+    if (W > 4096) { cb_set_error("beam width %d too large", W); return CB_ERR_ARG; }
+    const int C = h->cfg.n_class;
+    // Pool: children are only materialised when they enter the beam and the pool is compacted when full, so a few
+    // thousand nodes cover T*W-sized tries.  2*W*(T+1)+2 nodes can never overflow (every live node is an ancestor of
+    // a leaf or of a current branch); that size is used for a retry if the small pool ever proves too small.
+    const long long cap = 2LL * W * (T + 1) + 2;
+    long long pool = 4LL * W + 4096;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (pool > cap || attempt == 1) pool = cap;
+        if (pool < 2LL * W + 2) pool = 2LL * W + 2;
+        const size_t stride = align_up(cb_beam_work_bytes(W, (int)pool), 16);
+        int rc = ensure_buf(&h->beam_ws, &h->beam_ws_bytes, stride * (size_t)B, "beam workspace");
+        if (rc != CB_OK) return rc;
+        CB_CUDA(cudaMemsetAsync(h->d_flag, 0, sizeof(int), s));
+        beam_kernel<<<(B + 63) / 64, 64, 0, s>>>(logits, lens, B, T, C, W, (int)pool, (char*)h->beam_ws, stride, bases,
+                                                 n_bases, h->d_flag);
+        CB_CHECK_LAUNCH();
+        h->launches++;
+        int flag = 0;                  // the beam decoder is synchronous (like the reference's decode dequeue)
+        CB_CUDA(cudaMemcpyAsync(&flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CB_CUDA(cudaStreamSynchronize(s));
+        if (!flag) return CB_OK;
+        if (pool == cap) break;
+    }
+    cb_set_error("beam search node pool exhausted (beam_width %d, T %d)", W, T);
+    return CB_ERR_NOMEM;
+}
+
+int cb_launch_assemble(cb_handle* h, const int8_t* bases, const int32_t* n_bases, const float* path_prob, int n_windows,
+                       int T, int jump, int L, int kernel, int8_t* consensus, char* qual, int32_t* pos,
+                       int32_t* out_len, int max_len, cudaStream_t s) {
+    if (n_windows == 0) { CB_CUDA(cudaMemsetAsync(out_len, 0, sizeof(int32_t), s)); return CB_OK; }
+    const size_t scratch_stride = kernel == CB_ASM_SIMPLE ? align_up(cb_simple_scratch_ints(T, T), 4) : 0;
+    const size_t ml = (size_t)(max_len > 0 ? max_len : 1);
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+    const size_t o_list = carve(sizeof(int) * n_windows), o_nne = carve(sizeof(int)), o_disp = carve(sizeof(int) * n_windows);
+    const size_t o_len = carve(sizeof(int)), o_counts = carve(sizeof(int) * 4 * ml), o_qsum = carve(sizeof(double) * 4 * ml);
+    const size_t o_lf = carve(sizeof(double) * (T + 2)), o_scr = carve(sizeof(int) * scratch_stride * n_windows);
+    int rc = ensure_buf(&h->asm_ws, &h->asm_ws_bytes, off, "assembly workspace");
+    if (rc != CB_OK) return rc;
+    char* base = (char*)h->asm_ws;
+    AsmWork w;
+    w.list = (int*)(base + o_list); w.n_ne = (int*)(base + o_nne); w.disp = (int*)(base + o_disp);
+    w.length = (int*)(base + o_len); w.counts = (int*)(base + o_counts); w.qsum = (double*)(base + o_qsum);
+    w.logfact = (double*)(base + o_lf); w.scratch = (int*)(base + o_scr); w.scratch_stride = scratch_stride;
+    CB_CUDA(cudaMemsetAsync(base + o_counts, 0, (o_lf - o_counts), s));       // counts + qsum
+    asm_compact_kernel<<<1, 1024, 0, s>>>(n_bases, n_windows, T, w, pos);
+    CB_CHECK_LAUNCH();
+    const double jsr = (double)jump / (double)L;                                // FLAGS.jump / FLAGS.segment_len
+    asm_disp_kernel<<<(n_windows + 127) / 128, 128, 0, s>>>(bases, n_bases, T, kernel, jsr, w);
+    CB_CHECK_LAUNCH();
+    asm_scan_kernel<<<1, 1024, 0, s>>>(n_bases, w, pos, out_len, max_len);
+    CB_CHECK_LAUNCH();
+    asm_vote_kernel<<<n_windows, 128, 0, s>>>(bases, n_bases, path_prob, T, w, (int)ml);
+    CB_CHECK_LAUNCH();
+    if (max_len > 0) {
+        asm_finish_kernel<<<(max_len + 255) / 256, 256, 0, s>>>(w, (int)ml, consensus, qual);
+        CB_CHECK_LAUNCH();
+    }
+    h->launches += 5;
+    return CB_OK;
+}
+
+// ---- host-compiled instantiations of the same routines (unit tests without a GPU; never on the product path) -------
+extern "C" int cb_selftest_beam(const float* logits, int len, int n_class, int beam_width, int pool, int8_t* out) {
+    if (!logits || !out || n_class < 2 || n_class > 8 || beam_width < 1 || pool < 2 * beam_width + 2) return -1;
+    void* mem = malloc(cb_beam_work_bytes(beam_width, pool));
+    if (!mem) return -1;
+    CbBeamWork k = cb_beam_work_carve(mem, beam_width, pool);
+    const int n = cb_beam_decode_one(logits, len, n_class, beam_width, k, out);
+    free(mem);
+    return n;
+}
+
+extern "C" int cb_selftest_disp(const int8_t* cur, int la, const int8_t* prev, int lb, int kernel, int jump, int L) {
+    if (kernel == CB_ASM_STICK) return cb_disp_stick(la, lb);
+    if (kernel == CB_ASM_GLUE) return cb_disp_glue(cur, la, prev, lb);
+    const int mx = la > lb ? la : lb;
+    double* lf = (double*)malloc(sizeof(double) * (mx + 2));
+    int* scratch = (int*)malloc(sizeof(int) * cb_simple_scratch_ints(la, lb));
+    double acc = 0.0;
+    lf[0] = 0.0;
+    for (int k = 1; k <= mx + 1; ++k) { acc += log((double)k); lf[k] = acc; }
+    const int d = cb_disp_simple(cur, la, prev, lb, (double)jump / (double)L, lf, scratch);
+    free(lf); free(scratch);
+    return d;
+}
