@@ -1,0 +1,267 @@
+"""Pipeline driver: the drop-in for chiron/chiron_eval.py (``run(args)`` / ``evaluation()``).
+
+Same flags, same output tree (``result/ segments/ meta/``), same file formats (write_output, chiron_eval.py:176-242);
+the TF session, the logits FIFO queue, the six decode threads and the pure-Python assembly are replaced by calls into
+libchiron_b200.so (forward + CTC decode + assembly on the GPU).  Differences that are deliberate, documented in
+DESIGN.md:
+  * windows of a read are collated in TRUE window order (the reference keys chunks by batch position,
+    chiron_eval.py:413-428,436, which rotates/duplicates segments of multi-batch reads -- SURVEY.md finding 6);
+  * the per-model signal normalisation the shipped weights need is applied (SURVEY.md finding 4);
+  * reads shard across ranks when launched under torchrun (RANK/WORLD_SIZE); no collective on the decode path.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import time
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from .chiron_input import read_data_for_eval
+from .engine import Basecaller, get_assembler_kernal, index2base
+from .shard import assign_reads, rank_world
+from .utils.unix_time import unix_time
+
+FLAGS = None
+
+
+def write_output(segments: List[str], consensus: str, time_list, file_pre: str, global_setting, concise: bool = False,
+                 suffix: str = "fasta", seg_q_score=None, q_score: Optional[str] = None):
+    """Byte-compatible with chiron_eval.py:176-242 (including FASTA-style segment records in .fastq files and the
+    missing trailing newline of fasta results)."""
+    start_time, reading_time, basecall_time, assembly_time = time_list
+    result_folder = os.path.join(global_setting.output, "result")
+    seg_folder = os.path.join(global_setting.output, "segments")
+    meta_folder = os.path.join(global_setting.output, "meta")
+    path_con = os.path.join(result_folder, file_pre + "." + suffix)
+    if global_setting.mode == "rna":
+        consensus = consensus.replace("T", "U").replace("t", "u")
+    if not concise:
+        path_reads = os.path.join(seg_folder, file_pre + "." + suffix)
+        path_meta = os.path.join(meta_folder, file_pre + ".meta")
+    with open(path_con, "w+") as out_con:
+        if not concise:
+            with open(path_reads, "w+") as out_f:
+                for indx, read in enumerate(segments):
+                    out_f.write(">{}{}\n{}\n".format(file_pre, str(indx), read))
+                    if (suffix == "fastq") and (seg_q_score is not None):
+                        out_f.write("@{}{}\n{}\n+\n{}\n".format(file_pre, str(indx), read, seg_q_score[indx]))
+        if (suffix == "fastq") and (q_score is not None):
+            out_con.write("@{}\n{}\n+\n{}\n".format(file_pre, consensus, q_score))
+        else:
+            out_con.write(">{}\n{}".format(file_pre, consensus))
+    if not concise:
+        with open(path_meta, "w+") as out_meta:
+            total_time = time.time() - start_time
+            output_time = total_time - assembly_time
+            assembly_time -= basecall_time
+            basecall_time -= reading_time
+            total_len = len(consensus)
+            total_time = time.time() - start_time
+            out_meta.write("# Reading Basecalling assembly output total rate(bp/s)\n")
+            out_meta.write("%5.3f %5.3f %5.3f %5.3f %5.3f %5.3f\n" % (
+                reading_time, basecall_time, assembly_time, output_time, total_time, total_len / total_time))
+            out_meta.write("# read_len batch_size segment_len jump start_pos\n")
+            out_meta.write("%d %d %d %d %d\n" % (total_len, global_setting.batch_size, global_setting.segment_len,
+                                                 global_setting.jump, global_setting.start))
+            out_meta.write("# input_name model_name\n")
+            out_meta.write("%s %s\n" % (global_setting.input, global_setting.model))
+
+
+def list_input_files(flags) -> (List[str], str):
+    """chiron_eval.py:277-290."""
+    if os.path.isdir(flags.input):
+        if getattr(flags, "recursive", False):
+            file_list = []
+            dir_len = len(flags.input) + 1
+            for (dirpath, _, filenames) in os.walk(flags.input + "/"):
+                for filename in sorted(filenames):
+                    file_list.append(dirpath[dir_len:] + filename)
+        else:
+            file_list = sorted(os.listdir(flags.input))
+        file_dir = flags.input
+    else:
+        file_list = [os.path.basename(flags.input)]
+        file_dir = os.path.abspath(os.path.join(flags.input, os.path.pardir))
+    return [f for f in file_list if f.endswith(".signal") or f.endswith(".fast5")], file_dir
+
+
+class _ReadState:
+    __slots__ = ("name", "n", "bases", "n_bases", "prob", "filled", "start_time", "reading_time")
+
+    def __init__(self, name, n, T, start_time, reading_time):
+        self.name = name
+        self.n = n
+        self.bases = np.zeros((n, T), dtype=np.int8)
+        self.n_bases = np.zeros(n, dtype=np.int32)
+        self.prob = np.zeros(n, dtype=np.float32)
+        self.filled = 0
+        self.start_time = start_time
+        self.reading_time = reading_time
+
+
+def evaluation(flags=None, caller: Optional[Basecaller] = None) -> Dict[str, dict]:
+    """chiron_eval.py:378-463.  Windows are packed ACROSS reads into batches of ``batch_size`` exactly like
+    ``_worker_fn`` (:304-368); the final partial batch is run at its true size (with population BatchNorm a window's
+    result does not depend on the other rows, so the reference's wrap-padding rows are dead work)."""
+    flags = flags or FLAGS
+    rank, world = rank_world()
+    own = caller is None
+    if own:
+        device = int(os.environ.get("LOCAL_RANK", getattr(flags, "device", 0) or 0))
+        caller = Basecaller(flags.model, device=device, precision=getattr(flags, "precision", None) or "fp32")
+    cfg = caller.cfg
+    file_list, file_dir = list_input_files(flags)
+    if world > 1:
+        sizes = [os.path.getsize(os.path.join(file_dir, f)) for f in file_list]
+        file_list = [file_list[i] for i in assign_reads(sizes, world)[rank]]
+    print("Found %d files." % len(file_list))
+    for sub in ("", "segments", "result", "meta"):
+        os.makedirs(os.path.join(flags.output, sub), exist_ok=True)
+    L, jump, B = flags.segment_len, flags.jump, flags.batch_size
+    T = caller.out_len(L)
+    beam = flags.beam
+    with_qs = flags.extension == "fastq"
+    summary: Dict[str, dict] = {}
+
+    pend_x: List[np.ndarray] = []
+    pend_len: List[np.ndarray] = []
+    pend_owner: List[tuple] = []      # (state, first window index, count)
+    pend_n = 0
+    open_reads: List[_ReadState] = []
+
+    def finish(st: _ReadState):
+        basecall_time = time.time() - st.start_time
+        keep = st.n_bases > 0                                   # sparse2dense drops empty rows (chiron_eval.py:56-66)
+        bpreads = [index2base(st.bases[i, :st.n_bases[i]]) for i in np.nonzero(keep)[0]]
+        kernal = get_assembler_kernal(jump, L)
+        seq, qual, pos = caller.assemble(st.bases, st.n_bases, st.prob if with_qs else None, jump, L, kernel=kernal,
+                                         with_qs=with_qs)
+        assembly_time = time.time() - st.start_time
+        file_pre = os.path.splitext(st.name)[0]
+        write_output(bpreads, seq, [st.start_time, st.reading_time, basecall_time, assembly_time], file_pre,
+                     concise=flags.concise, suffix=flags.extension, q_score=qual, global_setting=flags)
+        summary[st.name] = {"windows": st.n, "bases": len(seq), "pos": pos}
+
+    def flush():
+        nonlocal pend_x, pend_len, pend_owner, pend_n
+        if pend_n == 0:
+            return
+        x = np.concatenate(pend_x, axis=0)
+        ln = np.concatenate(pend_len, axis=0)
+        bases, n_bases, prob, _ = caller.basecall_batch(x, ln, beam=beam)
+        off = 0
+        for st, first, cnt in pend_owner:
+            st.bases[first:first + cnt] = bases[off:off + cnt]
+            st.n_bases[first:first + cnt] = n_bases[off:off + cnt]
+            st.prob[first:first + cnt] = prob[off:off + cnt]
+            st.filled += cnt
+            off += cnt
+        pend_x, pend_len, pend_owner, pend_n = [], [], [], 0
+        while open_reads and open_reads[0].filled == open_reads[0].n:
+            finish(open_reads.pop(0))
+
+    for name in file_list:
+        start_time = time.time()
+        input_path = os.path.join(file_dir, name)
+        eval_data = read_data_for_eval(input_path, flags.start, seg_length=L, step=jump,
+                                       reverse_fast5=getattr(flags, "reverse_fast5", False), sig_norm=cfg.sig_norm)
+        st = _ReadState(name, eval_data.reads_n, T, start_time, time.time() - start_time)
+        open_reads.append(st)
+        i = 0
+        if eval_data.reads_n == 0:
+            continue
+        while eval_data.epochs_completed == 0:
+            cur_x, cur_len, _ = eval_data.next_batch(B - pend_n, shuffle=False)
+            cnt = len(cur_x)
+            pend_x.append(cur_x)
+            pend_len.append(cur_len)
+            pend_owner.append((st, i, cnt))
+            pend_n += cnt
+            i += cnt
+            if pend_n >= B:
+                flush()
+    flush()
+    while open_reads:                                            # reads with zero windows
+        finish(open_reads.pop(0))
+    if own:
+        caller.close()
+    return summary
+
+
+def run(args):
+    """chiron_eval.py:525-544."""
+    global FLAGS
+    FLAGS = args
+    print("The result will be written to %s" % (FLAGS.output))
+    os.makedirs(FLAGS.output, exist_ok=True)
+    time_dict = unix_time(evaluation)
+    print("Real time:%5.3f Systime:%5.3f Usertime:%5.3f" % (time_dict["real"], time_dict["sys"], time_dict["user"]))
+    meta_folder = os.path.join(FLAGS.output, "meta")
+    if os.path.isdir(FLAGS.input):
+        file_pre = "all"
+    else:
+        file_pre = os.path.splitext(os.path.basename(FLAGS.input))[0]
+    rank, world = rank_world()
+    if world > 1:
+        file_pre += ".rank%d" % rank
+    path_meta = os.path.join(meta_folder, file_pre + ".meta")
+    with open(path_meta, "a+") as out_meta:
+        out_meta.write("# Wall_time Sys_time User_time Cpu_time\n")
+        out_meta.write("%5.3f %5.3f %5.3f %5.3f\n" % (time_dict["real"], time_dict["sys"], time_dict["user"],
+                                                      time_dict["sys"] + time_dict["user"]))
+
+
+def add_call_arguments(parser: argparse.ArgumentParser, model_default: Optional[str] = None):
+    """The flag surface shared by `chiron call` (entry.py:69-92) and the stand-alone driver (chiron_eval.py:546-575)."""
+    parser.add_argument("-i", "--input", required=True, help="File path or Folder path to the fast5 / signal files.")
+    parser.add_argument("-o", "--output", required=True, help="Output Folder name")
+    parser.add_argument("-m", "--model", required=model_default is None, default=model_default, help="model folder path")
+    parser.add_argument("-s", "--start", type=int, default=None, help="Start index of the signal file.")
+    parser.add_argument("-b", "--batch_size", type=int, default=None, help="Batch size for run.")
+    parser.add_argument("-l", "--segment_len", type=int, default=None, help="Segment length to be divided into.")
+    parser.add_argument("-j", "--jump", type=int, default=None, help="Step size for segment")
+    parser.add_argument("-t", "--threads", type=int, default=None, help="Threads number (host-side parsing only)")
+    parser.add_argument("--beam", type=int, default=None,
+                        help="Beam width of the beam search decoder; 0 = greedy decoder.")
+    parser.add_argument("-e", "--extension", default="fastq", help="Output file extension.")
+    parser.add_argument("--concise", action="store_true", help="Do not write the meta and segments files.")
+    parser.add_argument("--mode", default="dna", help="Output mode, dna or rna.")
+    parser.add_argument("-p", "--preset", default=None, help="Preset evaluation parameters: dna-pre or rna-pre")
+    parser.add_argument("--precision", default="fp32", choices=["fp32", "tc", "tc_fast"],
+                        help="[chiron_b200] arithmetic of the dense contractions (see include/chiron_b200.h)")
+
+
+def apply_preset(args):
+    """entry.py:19-31,53-60 / chiron_eval.py:577-600."""
+    if args.preset is None:
+        p = {"start": 0, "batch_size": 400, "segment_len": 500, "jump": 490, "threads": 0, "beam": 30}
+    elif args.preset == "dna-pre":
+        p = {"start": 0, "batch_size": 400, "segment_len": 400, "jump": 390, "threads": 0, "beam": 30}
+        if args.mode == "rna":
+            raise ValueError("Try to use the DNA preset parameter setting in RNA mode.")
+    elif args.preset == "rna-pre":
+        p = {"start": 0, "batch_size": 300, "segment_len": 2000, "jump": 1900, "threads": 0, "beam": 30}
+        if args.mode == "dna":
+            raise ValueError("Attempt to use the RNA preset parameter setting in DNA mode, enable rna mode by --mode.")
+    else:
+        raise ValueError("Unknown presetting %s undifiend" % (args.preset))
+    for k, v in p.items():
+        if getattr(args, k, None) is None:
+            setattr(args, k, v)
+    args.reverse_fast5 = args.mode == "rna"
+    return args
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser(prog="chiron", description="A deep neural network basecaller (B200-native path).")
+    add_call_arguments(parser)
+    parser.add_argument("-r", "--recursive", action="store_true", help="If read the files recursively.")
+    args = parser.parse_args(sys.argv[1:] if argv is None else argv)
+    run(apply_preset(args))
+
+
+if __name__ == "__main__":
+    main()

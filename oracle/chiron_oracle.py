@@ -438,10 +438,13 @@ def simple_assembly_qs(bpreads: Sequence[str], qs_list: Optional[Sequence[float]
 
 
 def qs_string(consensus: np.ndarray, consensus_qs: np.ndarray) -> str:
-    """chiron/chiron_eval.py:152-174 (phred+33)."""
+    """chiron/chiron_eval.py:152-174 (phred+33).  The reference calls np.argsort(consensus, axis=0) with the default
+    kind; on the numpy of its era (<= 1.16) a 4-element axis is insertion-sorted, i.e. stable, which decides which
+    row's quality sum is used when the two highest counts tie.  Modern numpy's SIMD argsort is not stable, so the
+    restatement asks for kind="stable" explicitly (the golden quality string of read1 pins this)."""
     if consensus.shape[1] == 0:
         return ""
-    sort_ind = np.argsort(consensus, axis=0)
+    sort_ind = np.argsort(consensus, axis=0, kind="stable")
     L = consensus.shape[1]
     sc = consensus[sort_ind, np.arange(L)[np.newaxis, :]]
     sq = consensus_qs[sort_ind, np.arange(L)[np.newaxis, :]]

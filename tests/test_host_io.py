@@ -1,0 +1,131 @@
+"""CPU tests of the host-side I/O mirror: HDF5/fast5 reader, extraction, normalisation, windowing, sharding."""
+import os
+import types
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from chiron_b200 import chiron_input, fast5, shard
+from chiron_b200.chiron_eval import apply_preset, list_input_files
+from chiron_b200.engine import get_assembler_kernal
+from chiron_b200.model import NORM_FULL_MAD, NORM_UNIQUE_MAD
+from chiron_b200.utils.extract_sig_ref import extract
+from oracle import chiron_oracle as O
+
+DNA_FAST5 = os.path.join(GOLDEN, "fast5", "read1.fast5")
+RNA_FAST5 = os.path.join(GOLDEN, "fast5", "rna_read_100_ch_328.fast5")
+
+
+def test_dna_fast5_equals_golden_signal():
+    """Old-style groups + contiguous int16 dataset; the payload equals output/raw/read1.signal sample for sample."""
+    sig = fast5.read_raw_signal(DNA_FAST5)
+    ref = chiron_input.read_signal(os.path.join(GOLDEN, "DNA", "raw", "read1.signal"))
+    assert sig.dtype == np.int16 and len(sig) == 62461
+    assert np.array_equal(sig.astype(np.float32), ref)
+    rec = fast5.read_fast5(DNA_FAST5)[0]
+    assert rec["read_id"] is None                       # the bundled DNA reads carry no read_id attribute
+    assert rec["attrs"]["duration"] == 62461 and rec["channel"]["sampling_rate"] == 4000.0
+
+
+def test_rna_fast5_chunked_deflate_and_link_messages():
+    """New-style compact groups + chunked, deflate-compressed Signal."""
+    rec = fast5.read_fast5(RNA_FAST5)[0]
+    assert rec["read_key"] == "Read_100"
+    assert rec["read_id"] == "ed5cc40d-a190-4ed2-8c2c-02d89e092c59"
+    assert len(rec["signal"]) == rec["attrs"]["duration"] == 10136
+    assert rec["signal"][:5].tolist() == [1129, 559, 551, 571, 576]
+    assert rec["channel"]["sampling_rate"] == 3012.0 and rec["channel"]["digitisation"] == 8192.0
+
+
+def test_extract_writes_signal_files(tmp_path):
+    flags = types.SimpleNamespace(input_dir=os.path.join(GOLDEN, "fast5"), output_dir=str(tmp_path), mode="dna",
+                                  unit=False, recursive=True, delimiter="\n", idname=False, threads=1, test_number=None)
+    assert extract(flags) == 2
+    out = chiron_input.read_signal(os.path.join(str(tmp_path), "raw", "read1.signal"))
+    ref = chiron_input.read_signal(os.path.join(GOLDEN, "DNA", "raw", "read1.signal"))
+    assert np.array_equal(out, ref)
+    flags.mode, flags.output_dir = "rna", str(tmp_path / "rna")
+    extract(flags)
+    rna = chiron_input.read_signal(os.path.join(flags.output_dir, "raw", "rna_read_100_ch_328.signal"))
+    assert rna[-5:].tolist() == [576, 571, 551, 559, 1129]          # rna mode reverses the signal (:165)
+    assert os.path.isdir(os.path.join(flags.output_dir, "reference")) and os.path.isdir(flags.log_folder)
+
+
+def test_normalisation_and_windows_match_oracle():
+    sig = chiron_input.read_signal(os.path.join(GOLDEN, "DNA", "raw", "read1.signal"))
+    for mode in (NORM_UNIQUE_MAD, NORM_FULL_MAD):
+        assert np.array_equal(chiron_input.normalize_signal(sig, mode), O.normalize_signal(sig, mode))
+    norm = chiron_input.normalize_signal(sig, NORM_UNIQUE_MAD)
+    for L, jump, start in ((400, 390, 0), (300, 100, 7), (512, 512, 0), (100000, 5, 62000)):
+        ds = chiron_input.windows_from_signal(norm[start:], jump, L)
+        x, lens = O.make_windows(norm, L, jump, start)
+        assert np.array_equal(ds.event, x) and np.array_equal(ds.event_length, lens)
+    ds = chiron_input.read_data_for_eval(os.path.join(GOLDEN, "DNA", "raw", "read1.signal"), 0, 390, 400)
+    assert ds.reads_n == 161
+    seen = 0
+    while ds.epochs_completed == 0:                                  # sequential, remainder at the end of the read
+        xb, lb, _ = ds.next_batch(50)
+        assert len(xb) == min(50, 161 - seen)
+        seen += len(xb)
+    assert seen == 161
+    empty = chiron_input.windows_from_signal(norm[:0], 390, 400)
+    assert empty.reads_n == 0
+
+
+def test_presets_and_kernel_choice():
+    a = types.SimpleNamespace(preset="dna-pre", mode="dna", start=None, batch_size=None, segment_len=None, jump=None,
+                              threads=None, beam=None)
+    a = apply_preset(a)
+    assert (a.batch_size, a.segment_len, a.jump, a.beam, a.reverse_fast5) == (400, 400, 390, 30, False)
+    b = apply_preset(types.SimpleNamespace(preset="rna-pre", mode="rna", start=None, batch_size=None, segment_len=None,
+                                           jump=1000, threads=None, beam=0))
+    assert (b.batch_size, b.segment_len, b.jump, b.beam, b.reverse_fast5) == (300, 2000, 1000, 0, True)
+    with pytest.raises(ValueError):
+        apply_preset(types.SimpleNamespace(preset="dna-pre", mode="rna", start=None, batch_size=None, segment_len=None,
+                                           jump=None, threads=None, beam=None))
+    assert [get_assembler_kernal(j, 300) for j in (270, 290, 300)] == ["simple", "glue", "stick"]
+    files, d = list_input_files(types.SimpleNamespace(input=os.path.join(GOLDEN, "DNA", "raw"), recursive=True))
+    assert files == ["read1.signal", "read3.signal"]
+
+
+def test_read_assignment_is_a_balanced_partition():
+    rng = np.random.default_rng(0)
+    sizes = rng.integers(1, 10 ** 6, size=57).tolist()
+    for world in (1, 2, 4, 8):
+        parts = shard.assign_reads(sizes, world)
+        assert sorted(i for p in parts for i in p) == list(range(57))
+        loads = [sum(sizes[i] for i in p) for p in parts]
+        assert max(loads) - min(loads) <= max(sizes)
+    assert shard.assign_reads([], 4) == [[], [], [], []]
+
+
+def _bcast_worker(rank, world, port, blob_path, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    blob = open(blob_path, "rb").read() if rank == 0 else None
+    got = shard.broadcast_blob(blob, src=0)
+    files = ["r%d" % i for i in range(9)]
+    mine = shard.assign_reads([9, 8, 7, 6, 5, 4, 3, 2, 1], world)[rank]
+    import zlib
+    q.put((rank, len(got), zlib.crc32(got), [files[i] for i in mine]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_weight_broadcast_and_sharding_gloo(tmp_path):
+    """The N>1 host logic on CPU: one broadcast of the weight blob, disjoint read shards, nothing else exchanged."""
+    import torch.multiprocessing as mp
+    from chiron_b200.model import bundled_blob_path
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_bcast_worker, args=(r, 2, port, bundled_blob_path("DNA_default"), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+    assert res[0][1] == res[1][1] == os.path.getsize(bundled_blob_path("DNA_default"))
+    assert res[0][2] == res[1][2]
+    assert sorted(res[0][3] + res[1][3]) == ["r%d" % i for i in range(9)] and not set(res[0][3]) & set(res[1][3])
