@@ -231,6 +231,8 @@ extern "C" int cb_destroy(cb_handle* h) {
     if (h->asm_ws) cudaFree(h->asm_ws);
     if (h->d_flag) cudaFree(h->d_flag);
     for (int i = 0; i < 8; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < CB_PROF_MAX; ++i)
+        for (int j = 0; j < 2; ++j) if (h->prof_ev[i][j]) cudaEventDestroy(h->prof_ev[i][j]);
     delete h;
     return CB_OK;
 }
@@ -255,6 +257,18 @@ extern "C" int cb_last_forward_ms(const cb_handle* h, float* ms, int n) {
     return m;
 }
 
+extern "C" int cb_last_forward_profile(const cb_handle* h, float* ms, int* count, int n) {
+    if (!h || !ms || !count || !h->have_ms) return 0;
+    const int m = n < CB_CAT_COUNT ? n : CB_CAT_COUNT;
+    for (int i = 0; i < m; ++i) { ms[i] = 0.f; count[i] = 0; }
+    for (int i = 0; i < h->prof_n; ++i) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, h->prof_ev[i][0], h->prof_ev[i][1]) != cudaSuccess) return 0;
+        if (h->prof_cat[i] < m) { ms[h->prof_cat[i]] += t; count[h->prof_cat[i]]++; }
+    }
+    return m;
+}
+
 // -----------------------------------------------------------------------------------------------------------------
 static int ensure_workspace(cb_handle* h, int B, int L) {
     const CbConfig& c = h->cfg;
@@ -276,9 +290,25 @@ static int ensure_workspace(cb_handle* h, int B, int L) {
     return CB_OK;
 }
 
-static int run_gemm(cb_handle* h, const GemmProblem& p, cudaStream_t s) {
-    if (h->precision == CB_PREC_FP32) return cb_launch_gemm_simt(h, p, s);
-    return cb_launch_gemm_tc(h, p, s);
+static int prof_begin(cb_handle* h, int cat, cudaStream_t s) {
+    if (!h->timing || h->prof_n >= CB_PROF_MAX) return -1;
+    const int i = h->prof_n++;
+    if (!h->prof_ev[i][0]) {
+        if (cudaEventCreate(&h->prof_ev[i][0]) != cudaSuccess || cudaEventCreate(&h->prof_ev[i][1]) != cudaSuccess) {
+            h->prof_n--; return -1;
+        }
+    }
+    h->prof_cat[i] = cat;
+    cudaEventRecord(h->prof_ev[i][0], s);
+    return i;
+}
+static void prof_end(cb_handle* h, int i, cudaStream_t s) { if (i >= 0) cudaEventRecord(h->prof_ev[i][1], s); }
+
+static int run_gemm(cb_handle* h, const GemmProblem& p, cudaStream_t s, int cat) {
+    const int pi = prof_begin(h, cat, s);
+    const int rc = h->precision == CB_PREC_FP32 ? cb_launch_gemm_simt(h, p, s) : cb_launch_gemm_tc(h, p, s);
+    prof_end(h, pi, s);
+    return rc;
 }
 
 extern "C" int cb_seq_len_out(cb_handle* h, const int32_t* seq_len_in, int B, int L, int32_t* seq_len_out, void* stream) {
@@ -298,6 +328,7 @@ extern "C" int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_o
     if (rc != CB_OK) return rc;
     const CbConfig& c = h->cfg;
     const int C = c.channels, H = c.hidden;
+    h->prof_n = 0;
     if (h->timing) CB_CUDA(cudaEventRecord(h->ev[0], s));
 
     // ---- residual conv stack (cnn.py:234-262, 380-389) ----------------------------------------------------------
@@ -318,7 +349,7 @@ extern "C" int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_o
             g.t_in0 = t_in; g.stride0 = 1; g.taps = 1; g.left = 0; g.c0 = C; g.src0 = X; g.lda0 = C;
             g.W = h->conv2a[b].W; g.shift = h->conv2a[b].shift; g.relu = 1; g.out = h->act[ia]; g.ldo = C;
             g.layer_id = b * 4 + 0;
-            if ((rc = run_gemm(h, g, s)) != CB_OK) return rc;
+            if ((rc = run_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
         }
         // conv2b 1xk (stride) + BN + ReLU -> act[ib]
         memset(&g, 0, sizeof(g));
@@ -328,7 +359,7 @@ extern "C" int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_o
         else { g.src0 = h->act[ia]; g.lda0 = C; }
         g.W = h->conv2b[b].W; g.shift = h->conv2b[b].shift; g.relu = 1; g.out = h->act[ib]; g.ldo = C;
         g.layer_id = b * 4 + 1;
-        if ((rc = run_gemm(h, g, s)) != CB_OK) return rc;
+        if ((rc = run_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
         // conv2c 1x1 + BN, + branch1 (1x1 conv of the block input, stride st), ReLU -> act[ia]
         memset(&g, 0, sizeof(g));
         g.M = B * t_out; g.N = C; g.t_out = t_out;
@@ -340,7 +371,7 @@ extern "C" int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_o
         }
         g.W = h->convc[b].W; g.shift = h->convc[b].shift; g.relu = 1; g.out = h->act[ia]; g.ldo = C;
         g.layer_id = b * 4 + 2;
-        if ((rc = run_gemm(h, g, s)) != CB_OK) return rc;
+        if ((rc = run_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
         X = h->act[ia]; xi = ia; t_in = t_out;
     }
     const int T = t_in;
@@ -358,7 +389,7 @@ extern "C" int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_o
             g.M = M; g.N = 8 * H; g.K = in; g.t_out = T; g.t_in0 = T; g.stride0 = 1; g.taps = 1; g.c0 = in;
             g.src0 = Z; g.lda0 = ldz; g.W = h->wxcat[l]; g.shift = h->bcat[l]; g.out = h->pre; g.ldo = 8 * H;
             g.layer_id = 32 + l * 2;
-            if ((rc = run_gemm(h, g, s)) != CB_OK) return rc;
+            if ((rc = run_gemm(h, g, s, CB_CAT_LSTM_IN)) != CB_OK) return rc;
         } else {
             for (int d = 0; d < 2; ++d) {
                 memset(&g, 0, sizeof(g));
@@ -366,22 +397,31 @@ extern "C" int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_o
                 g.src0 = Z + d * H; g.lda0 = ldz; g.W = h->wx[l][d]; g.shift = h->bias[l][d];
                 g.out = h->pre + d * 4 * H; g.ldo = 8 * H;
                 g.layer_id = 32 + l * 2 + d;
-                if ((rc = run_gemm(h, g, s)) != CB_OK) return rc;
+                if ((rc = run_gemm(h, g, s, CB_CAT_LSTM_IN)) != CB_OK) return rc;
             }
         }
         LstmProblem lp;
         memset(&lp, 0, sizeof(lp));
         lp.B = B; lp.T = T; lp.H = H; lp.pre = h->pre; lp.ld_pre = 8 * H; lp.whh[0] = h->whh[l][0]; lp.whh[1] = h->whh[l][1];
         lp.lens = seq_len_out; lp.out = h->lstm_out[l & 1]; lp.ldo = 2 * H; lp.layer = l;
-        if (h->precision == CB_PREC_FP32) rc = cb_launch_lstm_simt(h, lp, s);
-        else rc = cb_launch_lstm_tc(h, lp, s);
+        {
+            const int pi = prof_begin(h, CB_CAT_LSTM_REC, s);
+            if (h->precision == CB_PREC_FP32) rc = cb_launch_lstm_simt(h, lp, s);
+            else rc = cb_launch_lstm_tc(h, lp, s);
+            prof_end(h, pi, s);
+        }
         if (rc != CB_OK) return rc;
         Z = h->lstm_out[l & 1]; ldz = 2 * H;
     }
     if (h->timing) CB_CUDA(cudaEventRecord(h->ev[2], s));
 
     // ---- head + path_prob ----------------------------------------------------------------------------------------
-    if ((rc = cb_launch_head(h, Z, M, logits, s)) != CB_OK) return rc;
+    {
+        const int pi = prof_begin(h, CB_CAT_HEAD, s);
+        rc = cb_launch_head(h, Z, M, logits, s);
+        prof_end(h, pi, s);
+        if (rc != CB_OK) return rc;
+    }
     if (path_prob && (rc = cb_launch_path_prob(h, logits, B, T, path_prob, s)) != CB_OK) return rc;
     if (h->timing) { CB_CUDA(cudaEventRecord(h->ev[3], s)); h->have_ms = 1; }
     h->last_B = B; h->last_T = T;

@@ -10,6 +10,8 @@
 
 #define CB_MAX_BLOCKS 8
 #define CB_MAX_LAYERS 8
+#define CB_PROF_MAX 96
+enum { CB_CAT_CONV = 0, CB_CAT_LSTM_IN = 1, CB_CAT_LSTM_REC = 2, CB_CAT_HEAD = 3, CB_CAT_COUNT = 4 };
 
 void cb_set_error(const char* fmt, ...);
 
@@ -102,7 +104,9 @@ struct cb_handle {
     void* asm_ws; size_t asm_ws_bytes;
     int* d_flag;
     long long launches;
-    int timing; cudaEvent_t ev[8]; float last_ms[5]; int have_ms;
+    int timing; cudaEvent_t ev[8]; int have_ms;
+    // per-launch profile of the last cb_forward (timing on): event pairs tagged with a kernel category
+    cudaEvent_t prof_ev[CB_PROF_MAX][2]; int prof_cat[CB_PROF_MAX]; int prof_n; int prof_ready;
     int last_B, last_T;
 };
 

@@ -75,6 +75,14 @@ class Basecaller:
         n = self.lib.cb_last_forward_ms(self.h, arr, 4)
         return [float(arr[i]) for i in range(n)]
 
+    def last_forward_profile(self):
+        """{category: (summed ms, launches)} of the last forward (timing enabled, stream synchronised)."""
+        ms = (ctypes.c_float * 4)()
+        cnt = (ctypes.c_int * 4)()
+        n = self.lib.cb_last_forward_profile(self.h, ms, cnt, 4)
+        names = ["conv", "lstm_in", "lstm_rec", "head"]
+        return {names[i]: (float(ms[i]), int(cnt[i])) for i in range(n)}
+
     # ---- host (numpy) path: what `evaluation()` uses -----------------------------------------------------------
     def basecall_batch(self, x: np.ndarray, seq_len: np.ndarray, beam: int = 0, want_logits: bool = False):
         """x [B,L] float32 windows, seq_len [B] int32 true lengths.  Returns (bases[B,T] int8, n_bases[B],

@@ -111,6 +111,11 @@ long long cb_launch_count(const cb_handle* h);
 int cb_last_forward_ms(const cb_handle* h, float* ms, int n);
 void cb_enable_timing(cb_handle* h, int on);
 
+/* Per-kernel-category device time of the last cb_forward (timing on; CUDA event pairs around every launch on the
+ * forward's stream): category 0 = conv-stack contractions, 1 = LSTM input-projection contractions, 2 = LSTM recurrence,
+ * 3 = logit head.  ms[c] = summed duration, count[c] = launches.  Returns the number of categories written. */
+int cb_last_forward_profile(const cb_handle* h, float* ms, int* count, int n);
+
 /* Copy an intermediate activation of the last cb_forward to HOST memory (tests only).
  * what: 0 = CNN feature [B*T,C]; n_layers-1 / n_layers = output [B*T,2H] of the last two LSTM layers (earlier ones are
  * overwritten by the ping-pong buffers).  Returns floats copied or <0. */
