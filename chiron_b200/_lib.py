@@ -28,6 +28,7 @@ SIGNATURES = {
     "cb_workspace_bytes": (c_size_t, [c_void_p]),
     "cb_seq_len_out": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "cb_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "cb_check_status": (c_int, [c_void_p, c_void_p]),
     "cb_decode_greedy": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "cb_decode_beam": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "cb_assemble": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -273,9 +273,10 @@ extern "C" int cb_last_forward_profile(const cb_handle* h, float* ms, int* count
 static int ensure_workspace(cb_handle* h, int B, int L) {
     const CbConfig& c = h->cfg;
     const int T = out_len_of(c, L);
+    const size_t Bp = ((size_t)B + 127) / 128 * 128;          // the tensor-core LSTM stack pads the batch to 128 rows
     const size_t act_floats = (size_t)B * L * c.channels;
-    const size_t pre_floats = (size_t)B * T * 8 * c.hidden;
-    const size_t out_floats = (size_t)B * T * 2 * c.hidden;
+    const size_t pre_floats = Bp * T * 8 * c.hidden;
+    const size_t out_floats = Bp * T * 2 * c.hidden;
     const size_t need = (3 * align_up(act_floats, 64) + align_up(pre_floats, 64) + 2 * align_up(out_floats, 64)) * sizeof(float);
     if (need > h->ws_bytes) {
         if (h->ws) { cudaFree(h->ws); h->ws = nullptr; h->ws_bytes = 0; }
@@ -381,33 +382,37 @@ extern "C" int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_o
 
     // ---- BiLSTM stack (rnn.py:20-64 stacked-bidirectional; rnn.py:99-145 per-direction MultiRNNCell) ---------------
     const float* Z = X; int ldz = C;
+    const bool tmajor = h->precision != CB_PREC_FP32 && cb_lstm_tc_available(h);
+    const int Bp = (B + 127) / 128 * 128;
     for (int l = 0; l < c.n_layers; ++l) {
         GemmProblem g;
-        if (l == 0 || c.rnn_layout == 0) {
-            const int in = l == 0 ? C : 2 * H;
+        const int n_gemm = (l == 0 || c.rnn_layout == 0) ? 1 : 2;
+        for (int d = 0; d < n_gemm; ++d) {
             memset(&g, 0, sizeof(g));
-            g.M = M; g.N = 8 * H; g.K = in; g.t_out = T; g.t_in0 = T; g.stride0 = 1; g.taps = 1; g.c0 = in;
-            g.src0 = Z; g.lda0 = ldz; g.W = h->wxcat[l]; g.shift = h->bcat[l]; g.out = h->pre; g.ldo = 8 * H;
-            g.layer_id = 32 + l * 2;
-            if ((rc = run_gemm(h, g, s, CB_CAT_LSTM_IN)) != CB_OK) return rc;
-        } else {
-            for (int d = 0; d < 2; ++d) {
-                memset(&g, 0, sizeof(g));
-                g.M = M; g.N = 4 * H; g.K = H; g.t_out = T; g.t_in0 = T; g.stride0 = 1; g.taps = 1; g.c0 = H;
-                g.src0 = Z + d * H; g.lda0 = ldz; g.W = h->wx[l][d]; g.shift = h->bias[l][d];
-                g.out = h->pre + d * 4 * H; g.ldo = 8 * H;
-                g.layer_id = 32 + l * 2 + d;
-                if ((rc = run_gemm(h, g, s, CB_CAT_LSTM_IN)) != CB_OK) return rc;
+            const int in = l == 0 ? C : (c.rnn_layout == 0 ? 2 * H : H);
+            g.N = n_gemm == 1 ? 8 * H : 4 * H; g.K = in; g.t_out = T; g.t_in0 = T; g.stride0 = 1; g.taps = 1; g.c0 = in;
+            g.W = n_gemm == 1 ? h->wxcat[l] : h->wx[l][d];
+            g.shift = n_gemm == 1 ? h->bcat[l] : h->bias[l][d];
+            g.layer_id = 32 + l * 2 + d;
+            g.ldo = 8 * H;
+            if (tmajor) {      // rows m = t*Bp + b; pre[T][8H][Bp]; layer >= 1 reads the time-major LSTM output
+                g.M = T * Bp; g.tmajor = 1; g.Bp = Bp; g.Bvalid = B; g.out_tlayout = 1;
+                g.out = h->pre + (size_t)d * 4 * H * Bp;
+                if (l == 0) { g.src0 = Z; g.lda0 = C; }
+                else { g.a_tlayout = 1; g.src0 = Z + (size_t)d * H * Bp; g.lda0 = 2 * H; }
+            } else {
+                g.M = M; g.src0 = Z + (l == 0 ? 0 : d * H); g.lda0 = ldz; g.out = h->pre + d * 4 * H;
             }
+            if ((rc = run_gemm(h, g, s, CB_CAT_LSTM_IN)) != CB_OK) return rc;
         }
         LstmProblem lp;
         memset(&lp, 0, sizeof(lp));
-        lp.B = B; lp.T = T; lp.H = H; lp.pre = h->pre; lp.ld_pre = 8 * H; lp.whh[0] = h->whh[l][0]; lp.whh[1] = h->whh[l][1];
+        lp.B = B; lp.T = T; lp.H = H; lp.pre = h->pre; lp.ld_pre = tmajor ? Bp : 8 * H;
+        lp.whh[0] = h->whh[l][0]; lp.whh[1] = h->whh[l][1];
         lp.lens = seq_len_out; lp.out = h->lstm_out[l & 1]; lp.ldo = 2 * H; lp.layer = l;
         {
             const int pi = prof_begin(h, CB_CAT_LSTM_REC, s);
-            if (h->precision == CB_PREC_FP32) rc = cb_launch_lstm_simt(h, lp, s);
-            else rc = cb_launch_lstm_tc(h, lp, s);
+            rc = tmajor ? cb_launch_lstm_tc(h, lp, s) : cb_launch_lstm_simt(h, lp, s);
             prof_end(h, pi, s);
         }
         if (rc != CB_OK) return rc;
@@ -418,10 +423,11 @@ extern "C" int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_o
     // ---- head + path_prob ----------------------------------------------------------------------------------------
     {
         const int pi = prof_begin(h, CB_CAT_HEAD, s);
-        rc = cb_launch_head(h, Z, M, logits, s);
+        rc = tmajor ? cb_launch_head_tmajor(h, Z, B, Bp, T, logits, s) : cb_launch_head(h, Z, M, logits, s);
         prof_end(h, pi, s);
         if (rc != CB_OK) return rc;
     }
+    h->last_Bp = Bp; h->last_tmajor = tmajor;
     if (path_prob && (rc = cb_launch_path_prob(h, logits, B, T, path_prob, s)) != CB_OK) return rc;
     if (h->timing) { CB_CUDA(cudaEventRecord(h->ev[3], s)); h->have_ms = 1; }
     h->last_B = B; h->last_T = T;
@@ -496,7 +502,14 @@ extern "C" int cb_basecall_host(cb_handle* h, const float* x, const int32_t* seq
     if (path_prob) CB_CUDA(cudaMemcpyAsync(path_prob, d_prob, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
     if (logits) CB_CUDA(cudaMemcpyAsync(logits, d_lg, (size_t)B * T * C * 4, cudaMemcpyDeviceToHost, s));
     CB_CUDA(cudaStreamSynchronize(s));
-    return CB_OK;
+    return cb_tc_check_range(h, s);
+}
+
+extern "C" int cb_check_status(cb_handle* h, void* stream) {
+    if (!h) { cb_set_error("cb_check_status: bad arguments"); return CB_ERR_ARG; }
+    CB_CUDA(cudaSetDevice(h->device));
+    CB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return cb_tc_check_range(h, (cudaStream_t)stream);
 }
 
 extern "C" int cb_assemble_host(cb_handle* h, const int8_t* bases, const int32_t* n_bases, const float* path_prob,
@@ -549,6 +562,15 @@ extern "C" long long cb_debug_fetch(cb_handle* h, int what, float* dst, size_t m
     if (n > max_floats) { cb_set_error("cb_debug_fetch: destination too small"); return CB_ERR_ARG; }
     CB_CUDA(cudaSetDevice(h->device));
     CB_CUDA(cudaDeviceSynchronize());
+    if (what >= 1 && h->last_tmajor) {          // [T][2H][Bp] -> [B][T][2H]
+        const size_t Bp = h->last_Bp, T = h->last_T, W2 = 2 * h->cfg.hidden, B = h->last_B;
+        std::vector<float> tmp(T * W2 * Bp);
+        CB_CUDA(cudaMemcpy(tmp.data(), src, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        for (size_t b = 0; b < B; ++b)
+            for (size_t t = 0; t < T; ++t)
+                for (size_t u = 0; u < W2; ++u) dst[(b * T + t) * W2 + u] = tmp[(t * W2 + u) * Bp + b];
+        return (long long)n;
+    }
     CB_CUDA(cudaMemcpy(dst, src, n * sizeof(float), cudaMemcpyDeviceToHost));
     return (long long)n;
 }

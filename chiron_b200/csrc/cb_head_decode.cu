@@ -44,6 +44,31 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ las
     }
 }
 
+// Time-major variant for the tensor-core LSTM stack: lasth is [T][2H][Bp]; one thread per frame, consecutive threads =
+// consecutive batch rows, so every load is a 128-byte coalesced row segment.
+__global__ void __launch_bounds__(128) head_tmajor_kernel(const float* __restrict__ lasth, int B, int Bp, int T, int H,
+                                                          int C, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, const float* __restrict__ wc,
+                                                          const float* __restrict__ bc, float* __restrict__ logits) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    if (b >= B) return;
+    const float* src = lasth + (size_t)t * 2 * H * Bp + b;
+    float acc[MAX_CLASS];
+#pragma unroll
+    for (int c = 0; c < MAX_CLASS; ++c) acc[c] = 0.f;
+    for (int u = 0; u < H; ++u) {
+        const float h2 = (src[(size_t)u * Bp] * __ldg(w + u) + src[(size_t)(H + u) * Bp] * __ldg(w + H + u)) + __ldg(bias + u);
+#pragma unroll
+        for (int c = 0; c < MAX_CLASS; ++c)
+            if (c < C) acc[c] = fmaf(h2, __ldg(wc + u * C + c), acc[c]);
+    }
+    float* dst = logits + ((size_t)b * T + t) * C;
+#pragma unroll
+    for (int c = 0; c < MAX_CLASS; ++c)
+        if (c < C) dst[c] = acc[c] + __ldg(bc + c);
+}
+
 __device__ __forceinline__ void top2_argmax(const float* __restrict__ row, int C, float& d, int& am) {
     float v0 = row[0], v1 = -INFINITY;
     am = 0;
@@ -119,6 +144,16 @@ int cb_launch_head(cb_handle* h, const float* lasth, int M, float* logits, cudaS
     if (blocks > cap) blocks = cap;
     head_kernel<<<(unsigned)blocks, 256, 0, s>>>(lasth, M, h->cfg.hidden, h->cfg.n_class, h->head_w, h->head_b,
                                                  h->head_wc, h->head_bc, logits);
+    CB_CHECK_LAUNCH();
+    h->launches++;
+    return CB_OK;
+}
+
+int cb_launch_head_tmajor(cb_handle* h, const float* out_t, int B, int Bp, int T, float* logits, cudaStream_t s) {
+    if (B <= 0 || T <= 0) return CB_OK;
+    if (h->cfg.n_class > MAX_CLASS || T > 65535) { cb_set_error("head: unsupported shape"); return CB_ERR_ARG; }
+    head_tmajor_kernel<<<dim3((B + 127) / 128, T), 128, 0, s>>>(out_t, B, Bp, T, h->cfg.hidden, h->cfg.n_class, h->head_w,
+                                                               h->head_b, h->head_wc, h->head_bc, logits);
     CB_CHECK_LAUNCH();
     h->launches++;
     return CB_OK;

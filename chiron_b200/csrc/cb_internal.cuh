@@ -64,6 +64,10 @@ struct GemmProblem {
     const float *rw, *rinv, *rsh;
     float* out; int ldo;
     int layer_id;             // which prepared tensor-core weight image belongs to this contraction
+    // time-major variant used by the tensor-core LSTM stack (taps = 1, stride 1): row m = t*Bp + b (b < Bvalid);
+    //   a_tlayout  : src0 is [t][lda0][Bp] (element (t,b,k) at (t*lda0 + k)*Bp + b) instead of row-major [b*T+t][lda0]
+    //   out_tlayout: out  is [t][ldo][Bp]
+    int tmajor, Bp, Bvalid, a_tlayout, out_tlayout;
 };
 
 struct LstmProblem {         // both directions of one layer (grid.y = direction)
@@ -100,6 +104,8 @@ struct cb_handle {
     void* stage; size_t stage_bytes;   // device staging of the host-buffer API
     const float* fea;                  // CNN feature of the last forward (debug fetch)
     void* tc;                          // tensor-core path state (cb_tc.cu)
+    void* lstm_tc;                     // tensor-core recurrence state (cb_lstm_tc.cu)
+    int last_Bp, last_tmajor;
     void* beam_ws; size_t beam_ws_bytes;
     void* asm_ws; size_t asm_ws_bytes;
     int* d_flag;
@@ -117,6 +123,11 @@ int cb_launch_gemm_tc(cb_handle* h, const GemmProblem& p, cudaStream_t s);
 int cb_launch_lstm_tc(cb_handle* h, const LstmProblem& p, cudaStream_t s);
 int cb_tc_prepare(cb_handle* h, const float* host_weights);   // build fp16 hi/lo operand images from d_weights layout
 void cb_tc_release(cb_handle* h);
+int cb_tc_check_range(cb_handle* h, cudaStream_t s);   // synchronises s; CB_ERR_RANGE if an activation left fp16 range
+int cb_lstm_tc_prepare(cb_handle* h, const float* host_weights);
+void cb_lstm_tc_release(cb_handle* h);
+bool cb_lstm_tc_available(const cb_handle* h);
+int cb_launch_head_tmajor(cb_handle* h, const float* out_t, int B, int Bp, int T, float* logits, cudaStream_t s);
 int cb_launch_head(cb_handle* h, const float* lasth, int M, float* logits, cudaStream_t s);
 int cb_launch_path_prob(cb_handle* h, const float* logits, int B, int T, float* prob, cudaStream_t s);
 int cb_launch_seq_len(cb_handle* h, const int32_t* in, int B, int L, int T, int32_t* out, cudaStream_t s);

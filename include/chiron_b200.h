@@ -70,6 +70,10 @@ int cb_seq_len_out(cb_handle* h, const int32_t* seq_len_in, int B, int L, int32_
 int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_out, int B, int L,
                float* logits, float* path_prob, void* stream);
 
+/* Synchronise `stream` and report deferred device-side errors of the asynchronous calls above (CB_ERR_RANGE when an
+ * activation left the fp16 range of the tensor-core path).  cb_basecall_host calls this itself. */
+int cb_check_status(cb_handle* h, void* stream);
+
 /* tf.nn.ctc_greedy_decoder(merge_repeated=True) (chiron_eval.py:486-487).  Dense padded output replaces the
  * SparseTensor: bases[B,T] int8 (0..3), n_bases[B]; rows with n_bases == 0 are the rows sparse2dense drops. */
 int cb_decode_greedy(cb_handle* h, const float* logits, const int32_t* seq_len_out, int B, int T,

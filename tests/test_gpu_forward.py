@@ -9,7 +9,10 @@ from oracle import chiron_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-LOGIT_TOL = 2e-3   # fp32 tolerance on CTC logits (|logit| <= ~20); see DESIGN.md "Numerics"
+# Tolerance on CTC logits (|logit| <= ~20) against the float32 oracle; see DESIGN.md "Numerics".  The oracle itself
+# moves by 5e-4 between float32 and float64 (the three LSTM layers amplify rounding noise ~100x).  "fp32" = FFMA kernels
+# with round-to-nearest accumulation; "tc" = tcgen05 fp16 hi/lo split whose accumulator truncates (RZ) on every add.
+LOGIT_TOLS = {"fp32": 2e-3, "tc": 3e-2}
 
 
 def _read1_windows(cfg, L=400, jump=390):
@@ -17,10 +20,11 @@ def _read1_windows(cfg, L=400, jump=390):
     return O.make_windows(O.normalize_signal(sig, cfg.sig_norm), L, jump)
 
 
-@pytest.fixture(scope="module", params=["fp32"])
+@pytest.fixture(scope="module", params=["fp32", "tc"])
 def caller(request):
     from chiron_b200.engine import Basecaller
     bc = Basecaller("DNA_default", device=0, precision=request.param)
+    bc.logit_tol = LOGIT_TOLS[request.param]
     yield bc
     bc.close()
 
@@ -32,11 +36,11 @@ def test_logits_and_greedy_match_oracle_read1(caller, dna_model):
     x, lens = x[n0 - 48:], lens[n0 - 48:]          # includes the ragged last window
     ref = O.inference(x, lens, cfg, t)
     bases, n_bases, prob, logits = caller.basecall_batch(x, lens, beam=0, want_logits=True)
-    assert np.abs(logits - ref).max() < LOGIT_TOL
+    assert np.abs(logits - ref).max() < caller.logit_tol
     ref_paths = O.ctc_greedy(ref, lens)
     got = [bases[b, :n_bases[b]].tolist() for b in range(len(x))]
     assert got == ref_paths
-    np.testing.assert_allclose(prob, O.path_prob(ref), rtol=0, atol=1e-4)
+    np.testing.assert_allclose(prob, O.path_prob(ref), rtol=0, atol=1e-4 if caller.precision == "fp32" else 1e-3)
 
 
 def test_intermediates_match_oracle(caller, dna_model):
@@ -51,7 +55,7 @@ def test_intermediates_match_oracle(caller, dna_model):
     assert np.abs(got - fea).max() < 1e-3 * max(1.0, np.abs(fea).max())
     lasth = O.rnn_forward(fea, lens, cfg, t)
     got = caller.debug_fetch(cfg.n_layers, lasth.size).reshape(lasth.shape)
-    assert np.abs(got - lasth).max() < 1e-3
+    assert np.abs(got - lasth).max() < (1e-3 if caller.precision == "fp32" else 1e-2)
     assert (got[3, 57:] == 0).all()               # dynamic_rnn: zero output past sequence_length
 
 
@@ -64,10 +68,10 @@ def test_ragged_lengths_and_tiny_batches(caller, dna_model):
         x[b, lens[b]:] = 0
     ref = O.inference(x, lens, cfg, t)
     bases, n_bases, prob, logits = caller.basecall_batch(x, lens, beam=0, want_logits=True)
-    assert np.abs(logits - ref).max() < LOGIT_TOL
+    assert np.abs(logits - ref).max() < caller.logit_tol
     assert [bases[b, :n_bases[b]].tolist() for b in range(5)] == O.ctc_greedy(ref, lens)
     b1 = caller.basecall_batch(x[:1], lens[:1], want_logits=True)      # B = 1
-    assert np.abs(b1[3] - ref[:1]).max() < LOGIT_TOL
+    assert np.abs(b1[3] - ref[:1]).max() < caller.logit_tol
 
 
 def test_greedy_kernel_exact_on_synthetic_logits(caller):
