@@ -223,6 +223,7 @@ extern "C" int cb_destroy(cb_handle* h) {
     if (!h) return CB_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    cb_forward_tc_release(h);
     cb_tc_release(h);
     if (h->d_weights) cudaFree(h->d_weights);
     if (h->ws) cudaFree(h->ws);
@@ -240,7 +241,7 @@ extern "C" int cb_destroy(cb_handle* h) {
 extern "C" int cb_out_len(const cb_handle* h, int L) { return h ? out_len_of(h->cfg, L) : CB_ERR_ARG; }
 extern "C" int cb_n_class(const cb_handle* h) { return h ? h->cfg.n_class : CB_ERR_ARG; }
 extern "C" int cb_precision(const cb_handle* h) { return h ? h->precision : CB_ERR_ARG; }
-extern "C" size_t cb_workspace_bytes(const cb_handle* h) { return h ? h->ws_bytes + h->stage_bytes + h->beam_ws_bytes + h->asm_ws_bytes : 0; }
+extern "C" size_t cb_workspace_bytes(const cb_handle* h) { return h ? h->ws_bytes + h->ws_bytes_tc + h->stage_bytes + h->beam_ws_bytes + h->asm_ws_bytes : 0; }
 extern "C" long long cb_launch_count(const cb_handle* h) { return h ? h->launches : 0; }
 extern "C" void cb_enable_timing(cb_handle* h, int on) { if (h) h->timing = on; }
 
@@ -273,10 +274,9 @@ extern "C" int cb_last_forward_profile(const cb_handle* h, float* ms, int* count
 static int ensure_workspace(cb_handle* h, int B, int L) {
     const CbConfig& c = h->cfg;
     const int T = out_len_of(c, L);
-    const size_t Bp = ((size_t)B + 127) / 128 * 128;          // the tensor-core LSTM stack pads the batch to 128 rows
     const size_t act_floats = (size_t)B * L * c.channels;
-    const size_t pre_floats = Bp * T * 8 * c.hidden;
-    const size_t out_floats = Bp * T * 2 * c.hidden;
+    const size_t pre_floats = (size_t)B * T * 8 * c.hidden;
+    const size_t out_floats = (size_t)B * T * 2 * c.hidden;
     const size_t need = (3 * align_up(act_floats, 64) + align_up(pre_floats, 64) + 2 * align_up(out_floats, 64)) * sizeof(float);
     if (need > h->ws_bytes) {
         if (h->ws) { cudaFree(h->ws); h->ws = nullptr; h->ws_bytes = 0; }
@@ -291,7 +291,7 @@ static int ensure_workspace(cb_handle* h, int B, int L) {
     return CB_OK;
 }
 
-static int prof_begin(cb_handle* h, int cat, cudaStream_t s) {
+int cb_prof_begin(cb_handle* h, int cat, cudaStream_t s) {
     if (!h->timing || h->prof_n >= CB_PROF_MAX) return -1;
     const int i = h->prof_n++;
     if (!h->prof_ev[i][0]) {
@@ -303,12 +303,12 @@ static int prof_begin(cb_handle* h, int cat, cudaStream_t s) {
     cudaEventRecord(h->prof_ev[i][0], s);
     return i;
 }
-static void prof_end(cb_handle* h, int i, cudaStream_t s) { if (i >= 0) cudaEventRecord(h->prof_ev[i][1], s); }
+void cb_prof_end(cb_handle* h, int i, cudaStream_t s) { if (i >= 0) cudaEventRecord(h->prof_ev[i][1], s); }
 
 static int run_gemm(cb_handle* h, const GemmProblem& p, cudaStream_t s, int cat) {
-    const int pi = prof_begin(h, cat, s);
-    const int rc = h->precision == CB_PREC_FP32 ? cb_launch_gemm_simt(h, p, s) : cb_launch_gemm_tc(h, p, s);
-    prof_end(h, pi, s);
+    const int pi = cb_prof_begin(h, cat, s);
+    const int rc = cb_launch_gemm_simt(h, p, s);
+    cb_prof_end(h, pi, s);
     return rc;
 }
 
@@ -325,6 +325,7 @@ extern "C" int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_o
     if ((long long)B * L > 0x7fffffffLL / 2) { cb_set_error("cb_forward: B*L too large"); return CB_ERR_ARG; }
     CB_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
+    if (h->precision != CB_PREC_FP32) return cb_forward_tc(h, x, seq_len_out, B, L, logits, path_prob, s);
     int rc = ensure_workspace(h, B, L);
     if (rc != CB_OK) return rc;
     const CbConfig& c = h->cfg;
@@ -349,8 +350,7 @@ extern "C" int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_o
             g.M = B * t_in; g.N = C; g.K = C; g.t_out = t_in;
             g.t_in0 = t_in; g.stride0 = 1; g.taps = 1; g.left = 0; g.c0 = C; g.src0 = X; g.lda0 = C;
             g.W = h->conv2a[b].W; g.shift = h->conv2a[b].shift; g.relu = 1; g.out = h->act[ia]; g.ldo = C;
-            g.layer_id = b * 4 + 0;
-            if ((rc = run_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
+                        if ((rc = run_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
         }
         // conv2b 1xk (stride) + BN + ReLU -> act[ib]
         memset(&g, 0, sizeof(g));
@@ -359,8 +359,7 @@ extern "C" int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_o
         if (b == 0) { g.gen = 1; g.x = x; g.gw = h->g_w; g.ginv = h->g_inv; g.gsh = h->g_sh; }
         else { g.src0 = h->act[ia]; g.lda0 = C; }
         g.W = h->conv2b[b].W; g.shift = h->conv2b[b].shift; g.relu = 1; g.out = h->act[ib]; g.ldo = C;
-        g.layer_id = b * 4 + 1;
-        if ((rc = run_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
+                if ((rc = run_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
         // conv2c 1x1 + BN, + branch1 (1x1 conv of the block input, stride st), ReLU -> act[ia]
         memset(&g, 0, sizeof(g));
         g.M = B * t_out; g.N = C; g.t_out = t_out;
@@ -371,8 +370,7 @@ extern "C" int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_o
             g.K = 2 * C; g.c1 = C; g.src1 = X; g.lda1 = C; g.t_in1 = t_in; g.stride1 = st;
         }
         g.W = h->convc[b].W; g.shift = h->convc[b].shift; g.relu = 1; g.out = h->act[ia]; g.ldo = C;
-        g.layer_id = b * 4 + 2;
-        if ((rc = run_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
+                if ((rc = run_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
         X = h->act[ia]; xi = ia; t_in = t_out;
     }
     const int T = t_in;
@@ -382,38 +380,27 @@ extern "C" int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_o
 
     // ---- BiLSTM stack (rnn.py:20-64 stacked-bidirectional; rnn.py:99-145 per-direction MultiRNNCell) ---------------
     const float* Z = X; int ldz = C;
-    const bool tmajor = h->precision != CB_PREC_FP32 && cb_lstm_tc_available(h);
-    const int Bp = (B + 127) / 128 * 128;
     for (int l = 0; l < c.n_layers; ++l) {
         GemmProblem g;
         const int n_gemm = (l == 0 || c.rnn_layout == 0) ? 1 : 2;
         for (int d = 0; d < n_gemm; ++d) {
             memset(&g, 0, sizeof(g));
             const int in = l == 0 ? C : (c.rnn_layout == 0 ? 2 * H : H);
-            g.N = n_gemm == 1 ? 8 * H : 4 * H; g.K = in; g.t_out = T; g.t_in0 = T; g.stride0 = 1; g.taps = 1; g.c0 = in;
+            g.M = M; g.N = n_gemm == 1 ? 8 * H : 4 * H; g.K = in; g.t_out = T; g.t_in0 = T; g.stride0 = 1; g.taps = 1; g.c0 = in;
             g.W = n_gemm == 1 ? h->wxcat[l] : h->wx[l][d];
             g.shift = n_gemm == 1 ? h->bcat[l] : h->bias[l][d];
-            g.layer_id = 32 + l * 2 + d;
-            g.ldo = 8 * H;
-            if (tmajor) {      // rows m = t*Bp + b; pre[T][8H][Bp]; layer >= 1 reads the time-major LSTM output
-                g.M = T * Bp; g.tmajor = 1; g.Bp = Bp; g.Bvalid = B; g.out_tlayout = 1;
-                g.out = h->pre + (size_t)d * 4 * H * Bp;
-                if (l == 0) { g.src0 = Z; g.lda0 = C; }
-                else { g.a_tlayout = 1; g.src0 = Z + (size_t)d * H * Bp; g.lda0 = 2 * H; }
-            } else {
-                g.M = M; g.src0 = Z + (l == 0 ? 0 : d * H); g.lda0 = ldz; g.out = h->pre + d * 4 * H;
-            }
+            g.src0 = Z + (l == 0 ? 0 : d * H); g.lda0 = ldz; g.out = h->pre + d * 4 * H; g.ldo = 8 * H;
             if ((rc = run_gemm(h, g, s, CB_CAT_LSTM_IN)) != CB_OK) return rc;
         }
         LstmProblem lp;
         memset(&lp, 0, sizeof(lp));
-        lp.B = B; lp.T = T; lp.H = H; lp.pre = h->pre; lp.ld_pre = tmajor ? Bp : 8 * H;
+        lp.B = B; lp.T = T; lp.H = H; lp.pre = h->pre; lp.ld_pre = 8 * H;
         lp.whh[0] = h->whh[l][0]; lp.whh[1] = h->whh[l][1];
         lp.lens = seq_len_out; lp.out = h->lstm_out[l & 1]; lp.ldo = 2 * H; lp.layer = l;
         {
-            const int pi = prof_begin(h, CB_CAT_LSTM_REC, s);
-            rc = tmajor ? cb_launch_lstm_tc(h, lp, s) : cb_launch_lstm_simt(h, lp, s);
-            prof_end(h, pi, s);
+            const int pi = cb_prof_begin(h, CB_CAT_LSTM_REC, s);
+            rc = cb_launch_lstm_simt(h, lp, s);
+            cb_prof_end(h, pi, s);
         }
         if (rc != CB_OK) return rc;
         Z = h->lstm_out[l & 1]; ldz = 2 * H;
@@ -422,12 +409,12 @@ extern "C" int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_o
 
     // ---- head + path_prob ----------------------------------------------------------------------------------------
     {
-        const int pi = prof_begin(h, CB_CAT_HEAD, s);
-        rc = tmajor ? cb_launch_head_tmajor(h, Z, B, Bp, T, logits, s) : cb_launch_head(h, Z, M, logits, s);
-        prof_end(h, pi, s);
+        const int pi = cb_prof_begin(h, CB_CAT_HEAD, s);
+        rc = cb_launch_head(h, Z, M, logits, s);
+        cb_prof_end(h, pi, s);
         if (rc != CB_OK) return rc;
     }
-    h->last_Bp = Bp; h->last_tmajor = tmajor;
+    h->last_Bp = B; h->last_tmajor = 0;
     if (path_prob && (rc = cb_launch_path_prob(h, logits, B, T, path_prob, s)) != CB_OK) return rc;
     if (h->timing) { CB_CUDA(cudaEventRecord(h->ev[3], s)); h->have_ms = 1; }
     h->last_B = B; h->last_T = T;
@@ -554,6 +541,7 @@ extern "C" int cb_assemble_host(cb_handle* h, const int8_t* bases, const int32_t
 
 extern "C" long long cb_debug_fetch(cb_handle* h, int what, float* dst, size_t max_floats) {
     if (!h || !dst || !h->last_B) { cb_set_error("cb_debug_fetch: nothing to fetch"); return CB_ERR_ARG; }
+    if (h->precision != CB_PREC_FP32) { CB_CUDA(cudaSetDevice(h->device)); return cb_debug_fetch_tc(h, what, dst, max_floats); }
     const size_t M = (size_t)h->last_B * h->last_T;
     const float* src; size_t n;
     if (what == 0) { src = h->fea; n = M * h->cfg.channels; }
@@ -562,15 +550,6 @@ extern "C" long long cb_debug_fetch(cb_handle* h, int what, float* dst, size_t m
     if (n > max_floats) { cb_set_error("cb_debug_fetch: destination too small"); return CB_ERR_ARG; }
     CB_CUDA(cudaSetDevice(h->device));
     CB_CUDA(cudaDeviceSynchronize());
-    if (what >= 1 && h->last_tmajor) {          // [T][2H][Bp] -> [B][T][2H]
-        const size_t Bp = h->last_Bp, T = h->last_T, W2 = 2 * h->cfg.hidden, B = h->last_B;
-        std::vector<float> tmp(T * W2 * Bp);
-        CB_CUDA(cudaMemcpy(tmp.data(), src, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
-        for (size_t b = 0; b < B; ++b)
-            for (size_t t = 0; t < T; ++t)
-                for (size_t u = 0; u < W2; ++u) dst[(b * T + t) * W2 + u] = tmp[(t * W2 + u) * Bp + b];
-        return (long long)n;
-    }
     CB_CUDA(cudaMemcpy(dst, src, n * sizeof(float), cudaMemcpyDeviceToHost));
     return (long long)n;
 }

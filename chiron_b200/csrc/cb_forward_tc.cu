@@ -1,0 +1,229 @@
+// Forward pass in tensor-core mode: orchestration of the tcgen05 kernels over operand images.
+// (chiron_model.inference, chiron/chiron_model.py:134-172: getcnnfeature -> rnn_layers -> logits.)
+//
+// Data flow (all activations as fp16 hi/lo k-group-plane images, see cb_tc_common.cuh):
+//   x --[generator producers]--> conv2b(1) --> P0 --conv2c(1)+rank-1 branch--> P1 = block-1 output
+//   block n>=2:  X --conv2a--> A --conv2b (3 taps = 3 row-shifted bulk loads)--> Bt --conv2c ++ branch1(X)--> X'
+//   last block writes its output image in time-major row order (row = t*Bp + b)
+//   LSTM layer l: image --input projection--> pre[T][8H][Bp] fp32 --recurrence--> h image (or fp32 out for the last layer)
+//   head (time-major) -> logits[B][T][n_class]; path_prob.
+#include <string.h>
+
+#include <vector>
+
+#include "cb_internal.cuh"
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct TcWorkspace {
+    void* base; size_t bytes;
+    int B, L;                     // geometry the images were zeroed for
+    CbImg conv[3];                // padded row-major images, rows = B*(T+2)
+    CbImg fea;                    // CNN feature, time-major rows t*Bp + b
+    CbImg himg;                   // LSTM layer output, planes [fw 13][bw 13], time-major rows
+    float* pre;                   // [T][8H][Bp]
+    float* out;                   // [T][2H][Bp] (last layer)
+};
+
+int ensure_ws(cb_handle* h, int B, int L, int T, int Bp, cudaStream_t s) {
+    TcWorkspace* w = (TcWorkspace*)h->tc_ws;
+    if (!w) { w = new TcWorkspace(); memset(w, 0, sizeof(*w)); h->tc_ws = w; }
+    const CbConfig& c = h->cfg;
+    const int planes = c.channels / 8;
+    const long long rows_c = CB_IMG_GUARD + (long long)B * (T + 2) + 128 + CB_IMG_GUARD;
+    const long long rows_t = CB_IMG_GUARD + (long long)T * Bp + 128 + CB_IMG_GUARD;
+    const int hplanes = 32;       // 26 real k-group planes (2 x 13) + zero planes the K padding reads
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+    size_t o_conv[3][2], o_fea[2], o_h[2];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j) o_conv[i][j] = carve(cb_img_halfs(rows_c, planes) * 2);
+    for (int j = 0; j < 2; ++j) o_fea[j] = carve(cb_img_halfs(rows_t, planes) * 2);
+    for (int j = 0; j < 2; ++j) o_h[j] = carve(cb_img_halfs(rows_t, hplanes) * 2);
+    const size_t img_bytes = off;
+    const size_t o_pre = carve((size_t)T * 8 * c.hidden * Bp * sizeof(float));
+    const size_t o_out = carve((size_t)T * 2 * c.hidden * Bp * sizeof(float));
+    bool rezero = w->B != B || w->L != L;
+    if (off > w->bytes) {
+        if (w->base) { cudaFree(w->base); w->base = nullptr; w->bytes = 0; }
+        cudaError_t e = cudaMalloc(&w->base, off);
+        if (e != cudaSuccess) { cb_set_error("tensor-core workspace cudaMalloc(%zu bytes): %s", off, cudaGetErrorString(e)); return CB_ERR_NOMEM; }
+        w->bytes = off;
+        rezero = true;
+    }
+    char* base = (char*)w->base;
+    for (int i = 0; i < 3; ++i) {
+        w->conv[i].hi = (__half*)(base + o_conv[i][0]); w->conv[i].lo = (__half*)(base + o_conv[i][1]);
+        w->conv[i].plane_rows = rows_c; w->conv[i].planes = planes;
+    }
+    w->fea.hi = (__half*)(base + o_fea[0]); w->fea.lo = (__half*)(base + o_fea[1]); w->fea.plane_rows = rows_t; w->fea.planes = planes;
+    w->himg.hi = (__half*)(base + o_h[0]); w->himg.lo = (__half*)(base + o_h[1]); w->himg.plane_rows = rows_t; w->himg.planes = hplanes;
+    w->pre = (float*)(base + o_pre); w->out = (float*)(base + o_out);
+    if (rezero) {     // padding rows, guards and unused planes must read as zero; interiors are rewritten every call
+        CB_CUDA(cudaMemsetAsync(base, 0, img_bytes, s));
+        w->B = B; w->L = L;
+    }
+    h->ws_bytes_tc = w->bytes;
+    return CB_OK;
+}
+
+int timed_gemm(cb_handle* h, const TcGemm& g, cudaStream_t s, int cat) {
+    const int pi = cb_prof_begin(h, cat, s);
+    const int rc = cb_launch_gemm_tc(h, g, s);
+    cb_prof_end(h, pi, s);
+    return rc;
+}
+
+}  // namespace
+
+void cb_forward_tc_release(cb_handle* h) {
+    TcWorkspace* w = (TcWorkspace*)h->tc_ws;
+    if (!w) return;
+    if (w->base) cudaFree(w->base);
+    delete w;
+    h->tc_ws = nullptr;
+}
+
+int cb_forward_tc(cb_handle* h, const float* x, const int32_t* seq_len_out, int B, int L, float* logits,
+                  float* path_prob, cudaStream_t s) {
+    const CbConfig& c = h->cfg;
+    const int C = c.channels, H = c.hidden;
+    const int T0 = (L + c.stride[0] - 1) / c.stride[0];      // frames after block 1; later blocks have stride 1
+    const int T = T0;
+    const int Bp = (B + 127) / 128 * 128;
+    int rc = ensure_ws(h, B, L, T, Bp, s);
+    if (rc != CB_OK) return rc;
+    TcWorkspace* w = (TcWorkspace*)h->tc_ws;
+    h->prof_n = 0;
+    if (h->timing) CB_CUDA(cudaEventRecord(h->ev[0], s));
+
+    const int cpt = C / 32;                                   // 32-channel k-chunks per tap
+    const int Mpad = B * (T + 2);
+    auto base_gemm = [&](int layer_id) {
+        TcGemm g;
+        memset(&g, 0, sizeof(g));
+        g.layer_id = layer_id; g.M = Mpad; g.row_mode = 1; g.t_out = T; g.B = B; g.Bp = Bp;
+        g.p.N = C; g.p.relu = 1; g.out_mode = 2;
+        return g;
+    };
+    // ---- block 1 (cnn.py:383-384): conv2a is generated from x inside the producers of conv2b ---------------------------
+    {
+        const int st = c.stride[0], k = c.k[0];
+        int pad = (T - 1) * st + k - L; if (pad < 0) pad = 0;     // TF 'SAME'
+        TcGemm g = base_gemm(1);
+        g.a_mode = 0;
+        g.p.M = Mpad; g.p.K = k * C; g.p.t_out = T; g.p.t_in0 = L; g.p.stride0 = st; g.p.taps = k; g.p.left = pad / 2; g.p.c0 = C;
+        g.p.gen = 1; g.p.x = x; g.p.gw = h->g_w; g.p.ginv = h->g_inv; g.p.gsh = h->g_sh;
+        g.p.shift = h->conv2b[0].shift; g.o = w->conv[0];
+        if ((rc = timed_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
+        g = base_gemm(2);
+        g.a_mode = 1; g.a0 = w->conv[0]; g.taps = 1; g.a0_chunks_per_tap = cpt;
+        g.p.shift = h->convc[0].shift; g.p.res = 1; g.p.x = x; g.p.t_inr = L; g.p.strider = st;
+        g.p.rw = h->r_w; g.p.rinv = h->r_inv; g.p.rsh = h->r_sh;
+        if (c.n_blocks == 1) { g.o = w->fea; g.o_tmajor = 1; } else g.o = w->conv[1];
+        if ((rc = timed_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
+    }
+    int xi = 1;
+    for (int b = 1; b < c.n_blocks; ++b) {
+        const int ai = (xi + 1) % 3, bi = (xi + 2) % 3;
+        TcGemm g = base_gemm(b * 4 + 0);                          // conv2a 1x1
+        g.a_mode = 1; g.a0 = w->conv[xi]; g.taps = 1; g.a0_chunks_per_tap = cpt; g.p.shift = h->conv2a[b].shift; g.o = w->conv[ai];
+        if ((rc = timed_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
+        g = base_gemm(b * 4 + 1);                                 // conv2b 1x3: three row-shifted views of the same image
+        g.a_mode = 1; g.a0 = w->conv[ai]; g.taps = c.k[b]; g.left = (c.k[b] - 1) / 2; g.a0_chunks_per_tap = cpt;
+        g.p.shift = h->conv2b[b].shift; g.o = w->conv[bi];
+        if ((rc = timed_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
+        g = base_gemm(b * 4 + 2);                                 // conv2c ++ branch1(X), ReLU
+        g.a_mode = 1; g.a0 = w->conv[bi]; g.taps = 1; g.a0_chunks_per_tap = cpt; g.a1 = w->conv[xi]; g.a1_chunks = cpt;
+        g.p.shift = h->convc[b].shift;
+        if (b == c.n_blocks - 1) { g.o = w->fea; g.o_tmajor = 1; } else g.o = w->conv[ai];
+        if ((rc = timed_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
+        xi = ai;
+    }
+    if (h->timing) CB_CUDA(cudaEventRecord(h->ev[1], s));
+
+    // ---- BiLSTM stack -------------------------------------------------------------------------------------------------------
+    for (int l = 0; l < c.n_layers; ++l) {
+        const bool last = l == c.n_layers - 1;
+        const int n_gemm = (l == 0 || c.rnn_layout == 0) ? 1 : 2;
+        for (int d = 0; d < n_gemm; ++d) {
+            TcGemm g;
+            memset(&g, 0, sizeof(g));
+            g.layer_id = 32 + l * 2 + d; g.M = T * Bp; g.row_mode = 2; g.t_out = T; g.B = B; g.Bp = Bp;
+            g.a_mode = 1; g.taps = 1;
+            if (l == 0) { g.a0 = w->fea; g.a0_chunks_per_tap = cpt; }
+            else if (n_gemm == 1) { g.a0 = w->himg; g.a0_chunks_per_tap = 7; }                 // K' = 208 -> 7 chunks
+            else { g.a0 = w->himg; g.a0_plane0 = d * 13; g.a0_chunks_per_tap = 4; }            // K' = 104 -> 4 chunks
+            g.p.N = n_gemm == 1 ? 8 * H : 4 * H;
+            g.p.shift = n_gemm == 1 ? h->bcat[l] : h->bias[l][d];
+            g.out_mode = 1; g.p.out = w->pre + (size_t)d * 4 * H * Bp; g.p.ldo = 8 * H;
+            if ((rc = timed_gemm(h, g, s, CB_CAT_LSTM_IN)) != CB_OK) return rc;
+        }
+        LstmProblem lp;
+        memset(&lp, 0, sizeof(lp));
+        lp.B = B; lp.T = T; lp.H = H; lp.pre = w->pre; lp.ld_pre = Bp; lp.lens = seq_len_out; lp.out = w->out; lp.ldo = 2 * H;
+        lp.layer = l;
+        const int pi = cb_prof_begin(h, CB_CAT_LSTM_REC, s);
+        rc = cb_launch_lstm_tc(h, lp, last ? nullptr : &w->himg, last ? 1 : 0, s);
+        cb_prof_end(h, pi, s);
+        if (rc != CB_OK) return rc;
+    }
+    if (h->timing) CB_CUDA(cudaEventRecord(h->ev[2], s));
+
+    {
+        const int pi = cb_prof_begin(h, CB_CAT_HEAD, s);
+        rc = cb_launch_head_tmajor(h, w->out, B, Bp, T, logits, s);
+        cb_prof_end(h, pi, s);
+        if (rc != CB_OK) return rc;
+    }
+    if (path_prob && (rc = cb_launch_path_prob(h, logits, B, T, path_prob, s)) != CB_OK) return rc;
+    if (h->timing) { CB_CUDA(cudaEventRecord(h->ev[3], s)); h->have_ms = 1; }
+    h->last_B = B; h->last_T = T; h->last_Bp = Bp; h->last_tmajor = 1;
+    return CB_OK;
+}
+
+// Reconstruct fp32 tensors from the operand images for tests: what 0 = CNN feature [B][T][C]; n_layers = last LSTM
+// output [B][T][2H] (fp32 time-major buffer); n_layers-1 = previous layer (h image).
+long long cb_debug_fetch_tc(cb_handle* h, int what, float* dst, size_t max_floats) {
+    TcWorkspace* w = (TcWorkspace*)h->tc_ws;
+    if (!w || !h->last_B) { cb_set_error("cb_debug_fetch: nothing to fetch"); return CB_ERR_ARG; }
+    const size_t B = h->last_B, T = h->last_T, Bp = h->last_Bp, C = h->cfg.channels, H = h->cfg.hidden;
+    CB_CUDA(cudaDeviceSynchronize());
+    auto fetch_img = [&](const CbImg& img, size_t width, auto plane_of, float* out) -> int {
+        const size_t n = cb_img_halfs(img.plane_rows, img.planes);
+        std::vector<__half> hi(n), lo(n);
+        CB_CUDA(cudaMemcpy(hi.data(), img.hi, n * sizeof(__half), cudaMemcpyDeviceToHost));
+        CB_CUDA(cudaMemcpy(lo.data(), img.lo, n * sizeof(__half), cudaMemcpyDeviceToHost));
+        for (size_t b = 0; b < B; ++b)
+            for (size_t t = 0; t < T; ++t)
+                for (size_t ch = 0; ch < width; ++ch) {
+                    size_t plane, e;
+                    plane_of(ch, plane, e);
+                    const size_t i = (plane * img.plane_rows + CB_IMG_GUARD + t * Bp + b) * 8 + e;
+                    out[(b * T + t) * width + ch] = __half2float(hi[i]) + __half2float(lo[i]);
+                }
+        return CB_OK;
+    };
+    if (what == 0) {
+        if (B * T * C > max_floats) { cb_set_error("cb_debug_fetch: destination too small"); return CB_ERR_ARG; }
+        int rc = fetch_img(w->fea, C, [](size_t ch, size_t& pl, size_t& e) { pl = ch / 8; e = ch % 8; }, dst);
+        return rc == CB_OK ? (long long)(B * T * C) : rc;
+    }
+    if (B * T * 2 * H > max_floats) { cb_set_error("cb_debug_fetch: destination too small"); return CB_ERR_ARG; }
+    if (what == h->cfg.n_layers) {
+        std::vector<float> tmp(T * 2 * H * Bp);
+        CB_CUDA(cudaMemcpy(tmp.data(), w->out, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        for (size_t b = 0; b < B; ++b)
+            for (size_t t = 0; t < T; ++t)
+                for (size_t u = 0; u < 2 * H; ++u) dst[(b * T + t) * 2 * H + u] = tmp[(t * 2 * H + u) * Bp + b];
+        return (long long)(B * T * 2 * H);
+    }
+    if (what == h->cfg.n_layers - 1 && what >= 1) {
+        int rc = fetch_img(w->himg, 2 * H, [H](size_t ch, size_t& pl, size_t& e) {
+            const size_t d = ch / H, u = ch % H; pl = d * 13 + u / 8; e = u % 8; }, dst);
+        return rc == CB_OK ? (long long)(B * T * 2 * H) : rc;
+    }
+    cb_set_error("cb_debug_fetch: tensor %d is not retained in tensor-core mode", what);
+    return CB_ERR_ARG;
+}

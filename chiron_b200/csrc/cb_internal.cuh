@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/chiron_b200.h"
+#include "cb_tc_common.cuh"
 
 #define CB_MAX_BLOCKS 8
 #define CB_MAX_LAYERS 8
@@ -64,10 +65,22 @@ struct GemmProblem {
     const float *rw, *rinv, *rsh;
     float* out; int ldo;
     int layer_id;             // which prepared tensor-core weight image belongs to this contraction
-    // time-major variant used by the tensor-core LSTM stack (taps = 1, stride 1): row m = t*Bp + b (b < Bvalid);
-    //   a_tlayout  : src0 is [t][lda0][Bp] (element (t,b,k) at (t*lda0 + k)*Bp + b) instead of row-major [b*T+t][lda0]
-    //   out_tlayout: out  is [t][ldo][Bp]
-    int tmajor, Bp, Bvalid, a_tlayout, out_tlayout;
+};
+
+// ---- one tensor-core contraction (cb_tc.cu) ----------------------------------------------------------------------------
+struct TcGemm {
+    int layer_id;             // prepared weight image
+    // row space of the kernel: 0 plain m = b*t_out + to; 1 padded m = b*(t_out+2) + 1 + to (a zero row around every
+    // window, so conv taps are plain row shifts); 2 time-major m = to*Bp + b
+    int M, row_mode, t_out, B, Bp;
+    int a_mode;               // 0 = SIMT producers gather/generate from `p`; 1 = operand images a0 (taps) ++ a1
+    GemmProblem p;            // gather description (a_mode 0) + epilogue parameters (N, shift, relu, res*, x, out, ldo)
+    CbImg a0, a1;
+    int a0_plane0, a1_plane0;         // first k-group plane of each source
+    int a0_chunks_per_tap, taps, left, a1_chunks;   // K = taps*a0_chunks_per_tap*32 + a1_chunks*32
+    int out_mode;             // 0 fp32 row-major p.out[m][ldo]; 1 fp32 time-major p.out[to][ldo][Bp]; 2 operand image o
+    CbImg o;
+    int o_plane0, o_tmajor;   // image rows: m, or to*Bp + b when o_tmajor
 };
 
 struct LstmProblem {         // both directions of one layer (grid.y = direction)
@@ -105,6 +118,7 @@ struct cb_handle {
     const float* fea;                  // CNN feature of the last forward (debug fetch)
     void* tc;                          // tensor-core path state (cb_tc.cu)
     void* lstm_tc;                     // tensor-core recurrence state (cb_lstm_tc.cu)
+    void* tc_ws; size_t ws_bytes_tc;   // tensor-core workspace: operand images, pre, out (cb_forward_tc.cu)
     int last_Bp, last_tmajor;
     void* beam_ws; size_t beam_ws_bytes;
     void* asm_ws; size_t asm_ws_bytes;
@@ -119,11 +133,17 @@ struct cb_handle {
 // ---- launchers (each returns CB_OK or an error code; they bump h->launches) -----------------------------------------
 int cb_launch_gemm_simt(cb_handle* h, const GemmProblem& p, cudaStream_t s);
 int cb_launch_lstm_simt(cb_handle* h, const LstmProblem& p, cudaStream_t s);
-int cb_launch_gemm_tc(cb_handle* h, const GemmProblem& p, cudaStream_t s);
-int cb_launch_lstm_tc(cb_handle* h, const LstmProblem& p, cudaStream_t s);
+int cb_launch_gemm_tc(cb_handle* h, const TcGemm& g, cudaStream_t s);
+int cb_launch_lstm_tc(cb_handle* h, const LstmProblem& p, const CbImg* o_img, int write_f32, cudaStream_t s);
 int cb_tc_prepare(cb_handle* h, const float* host_weights);   // build fp16 hi/lo operand images from d_weights layout
 void cb_tc_release(cb_handle* h);
 int cb_tc_check_range(cb_handle* h, cudaStream_t s);   // synchronises s; CB_ERR_RANGE if an activation left fp16 range
+int cb_forward_tc(cb_handle* h, const float* x, const int32_t* seq_len_out, int B, int L, float* logits,
+                  float* path_prob, cudaStream_t s);
+void cb_forward_tc_release(cb_handle* h);
+long long cb_debug_fetch_tc(cb_handle* h, int what, float* dst, size_t max_floats);
+int cb_prof_begin(cb_handle* h, int cat, cudaStream_t s);      // event pair around a launch when timing is on
+void cb_prof_end(cb_handle* h, int i, cudaStream_t s);
 int cb_lstm_tc_prepare(cb_handle* h, const float* host_weights);
 void cb_lstm_tc_release(cb_handle* h);
 bool cb_lstm_tc_available(const cb_handle* h);

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "cb_internal.cuh"
+#include "cb_tc_common.cuh"
 
 namespace {
 
@@ -40,104 +41,30 @@ struct LstmTcParams {
     const float* pre;          // [T][8H][Bp]
     const __half* wimg[2];     // per direction: hi image then lo image, [KG][400][8] halfs each
     const int32_t* lens;       // [B]
-    float* out;                // [T][2H][Bp]
+    float* out;                // [T][2H][Bp] fp32 (written when write_f32: the last layer, read by the logit head)
+    CbImg o_img;               // hi/lo operand image of h for the next layer's input projection (when write_img):
+                               //   plane dir*13 + kg, row CB_IMG_GUARD + t*Bp + b
+    int write_f32, write_img;
     int passes;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= 1ULL << 46;
-    return d;
-}
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
-    uint32_t r0, r1, r2, r3;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-                 : "r"(taddr));
-    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
-}
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, float a, float b, float c, float d) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(a)),
-                 "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d))
-                 : "memory");
-}
-// h(t) of one (row, 8-unit K-group) as one 16-byte core-matrix row per hi / lo image
-__device__ __forceinline__ void store_h_row(uint8_t* h_hi, uint8_t* h_lo, int kg, int row, float v0, float v1, float v2,
-                                            float v3, float v4, float v5, float v6, float v7) {
+// h(t) of one (row, 8-unit K-group) as one 16-byte core-matrix row per hi / lo image: into shared memory for the next
+// step's MMA and (optionally) into the global operand image the next layer's input projection bulk-loads.
+__device__ __forceinline__ void store_h_row(uint8_t* h_hi, uint8_t* h_lo, int kg, int row, __half* g_hi, __half* g_lo,
+                                            float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7) {
     const float v[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
-    uint32_t ph[4], pl[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const __half2 hh = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-        const float2 hf = __half22float2(hh);
-        const __half2 ll = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
-        ph[e] = *reinterpret_cast<const uint32_t*>(&hh);
-        pl[e] = *reinterpret_cast<const uint32_t*>(&ll);
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    *reinterpret_cast<uint4*>(h_hi + (size_t)kg * (RM * 16) + row * 16) = hi;
+    *reinterpret_cast<uint4*>(h_lo + (size_t)kg * (RM * 16) + row * 16) = lo;
+    if (g_hi) {
+        *reinterpret_cast<uint4*>(g_hi) = hi;
+        *reinterpret_cast<uint4*>(g_lo) = lo;
     }
-    *reinterpret_cast<uint4*>(h_hi + (size_t)kg * (RM * 16) + row * 16) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-    *reinterpret_cast<uint4*>(h_lo + (size_t)kg * (RM * 16) + row * 16) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
 }
 
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcpf(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float clampf(float x, float lim) { return fminf(fmaxf(x, -lim), lim); }
 
 // One LSTM cell (TF LSTMCell, forget_bias 1.0):  c' = sigmoid(f+1)*c + sigmoid(i)*tanh(j);  h' = sigmoid(o)*tanh(c').
 // sigmoid(x) = 1/(1+e^-x), tanh(x) = (1-e^-2x)/(1+e^-2x); the quotients are merged so a cell costs 5 ex2 + 2 rcp.
@@ -196,6 +123,7 @@ __device__ __forceinline__ void gate_loop(const LstmTcParams& q, uint8_t* h_hi, 
         const int t = frame_of(s);
         const int t_next = s + 1 < q.T ? frame_of(s + 1) : t;
         float* out_t = out_b + (size_t)t * (2 * H) * Bp;
+        const size_t img_row = (size_t)CB_IMG_GUARD + (size_t)t * Bp + b;
         mbar_wait(acc_ready, s & 1);
         tc_fence_after();
         float hlow[4] = {0.f, 0.f, 0.f, 0.f};       // h of the even half-group, carried to the odd one (same K-group)
@@ -222,13 +150,18 @@ __device__ __forceinline__ void gate_loop(const LstmTcParams& q, uint8_t* h_hi, 
                 if (active)
                     lstm_cell(z[e] + pre_cur[e], z[4 + e] + pre_cur[4 + e], z[8 + e] + pre_cur[8 + e],
                               z[12 + e] + pre_cur[12 + e], c[e], hv[e]);
-                out_t[(size_t)(u0 + e) * Bp] = hv[e];
+                if (q.write_f32) out_t[(size_t)(u0 + e) * Bp] = hv[e];
             }
             tmem_st4(t_cell + u0, c[0], c[1], c[2], c[3]);
+            __half *g_hi = nullptr, *g_lo = nullptr;
+            if (q.write_img) {
+                const size_t off = ((size_t)(dir * KG + (hg >> 1)) * q.o_img.plane_rows + img_row) * 8;
+                g_hi = q.o_img.hi + off; g_lo = q.o_img.lo + off;
+            }
             if (hg & 1) {
-                store_h_row(h_hi, h_lo, hg >> 1, row, hlow[0], hlow[1], hlow[2], hlow[3], hv[0], hv[1], hv[2], hv[3]);
+                store_h_row(h_hi, h_lo, hg >> 1, row, g_hi, g_lo, hlow[0], hlow[1], hlow[2], hlow[3], hv[0], hv[1], hv[2], hv[3]);
             } else if (hg == 24) {                   // units 100..103 do not exist: upper half of the last K-group is zero
-                store_h_row(h_hi, h_lo, 12, row, hv[0], hv[1], hv[2], hv[3], 0.f, 0.f, 0.f, 0.f);
+                store_h_row(h_hi, h_lo, 12, row, g_hi, g_lo, hv[0], hv[1], hv[2], hv[3], 0.f, 0.f, 0.f, 0.f);
             } else {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) hlow[e] = hv[e];
@@ -344,7 +277,10 @@ struct LstmTcState {
 }  // namespace
 
 int cb_lstm_tc_prepare(cb_handle* h, const float* hw) {
-    if (h->cfg.hidden != H) return CB_OK;      // other hidden sizes use the FFMA recurrence
+    if (h->cfg.hidden != H) {
+        cb_set_error("tensor-core path is specialised for hidden=%d (model has %d); use precision fp32", H, h->cfg.hidden);
+        return CB_ERR_ARG;
+    }
     LstmTcState* st = new LstmTcState();
     memset(st, 0, sizeof(*st));
     h->lstm_tc = st;
@@ -381,14 +317,17 @@ void cb_lstm_tc_release(cb_handle* h) {
 bool cb_lstm_tc_available(const cb_handle* h) { return h->lstm_tc != nullptr; }
 
 // pre: [T][8H][Bp], out: [T][2H][Bp] (time-major, batch innermost), Bp a multiple of 128.
-int cb_launch_lstm_tc(cb_handle* h, const LstmProblem& p, cudaStream_t s) {
+int cb_launch_lstm_tc(cb_handle* h, const LstmProblem& p, const CbImg* o_img, int write_f32, cudaStream_t s) {
     LstmTcState* st = (LstmTcState*)h->lstm_tc;
     if (!st) { cb_set_error("lstm tensor-core path unavailable for hidden=%d", h->cfg.hidden); return CB_ERR_ARG; }
     if (p.B <= 0 || p.T <= 0) return CB_OK;
     LstmTcParams q;
+    memset(&q, 0, sizeof(q));
     q.B = p.B; q.Bp = p.ld_pre; q.T = p.T; q.pre = p.pre; q.lens = p.lens; q.out = p.out;
     q.wimg[0] = st->wimg[p.layer][0]; q.wimg[1] = st->wimg[p.layer][1];
     q.passes = h->precision == CB_PREC_TC_FAST ? 1 : 3;
+    q.write_f32 = write_f32;
+    if (o_img) { q.o_img = *o_img; q.write_img = 1; }
     if (q.Bp % RM) { cb_set_error("lstm tensor-core path: padded batch %d not a multiple of %d", q.Bp, RM); return CB_ERR_ARG; }
     lstm_tc_kernel<<<dim3(q.Bp / RM, 2), NTHREADS, SMEM_BYTES, s>>>(q);
     CB_CHECK_LAUNCH();

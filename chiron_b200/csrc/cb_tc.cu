@@ -1,30 +1,32 @@
 // tcgen05 tensor-core contractions for the conv stack and the hoisted LSTM input projection
-// (CB_PREC_TC_SPLIT / CB_PREC_TC_FAST).  Same GemmProblem contract as cb_gemm_simt.cu (chiron/cnn.py:60-82,251-261;
+// (CB_PREC_TC_SPLIT / CB_PREC_TC_FAST).  Same maths as cb_gemm_simt.cu (chiron/cnn.py:60-82,251-261;
 // chiron/rnn.py:49-50,64), different machine:
 //
 //   * operands are fp16 hi/lo splits (a = hi + lo, |lo| <= 2^-11 |a|): D = Ah*Wh + Ah*Wl + Al*Wh, three
-//     tcgen05.mma.kind::f16 per K-step with fp32 accumulation in TMEM -> ~2^-21 relative error per product, i.e.
-//     fp32-class, which is what bit-exact greedy bases need.  CB_PREC_TC_FAST issues only Ah*Wh.
-//   * warp-specialised persistent CTAs (one per SM): 8 producer warps gather the fp32 activation rows (im2col taps,
-//     'SAME' padding, strides, the appended 1x1 branch input, or the rank-1 block-1 generator), split them and store the
-//     K-major no-swizzle core-matrix image; one thread streams the pre-packed weight images with cp.async.bulk;
-//     one thread issues the MMAs; 4 epilogue warps drain TMEM (tcgen05.ld 32x32b) -> scale/shift/residual/ReLU -> HBM.
-//   * mbarrier pipelines: smem full/empty ring (STAGES deep) and a double-buffered TMEM accumulator full/empty pair, so
-//     the epilogue of tile i overlaps the MMAs of tile i+1.
-#include <cuda_fp16.h>
+//     tcgen05.mma.kind::f16 per K-step with fp32 accumulation in TMEM.  CB_PREC_TC_FAST issues only Ah*Wh.
+//   * activations travel between layers as operand images (cb_tc_common.cuh): the epilogue of the producing kernel
+//     writes the hi/lo k-group planes, so the A side of a pipeline stage is 8 cp.async.bulk copies of 2 KB (a conv tap
+//     is the same plane shifted by one row; the appended 1x1 branch input is a second image).  Only the first conv2b
+//     (block-1 conv2a is a rank-1 function of the raw signal, cnn.py:254) still uses SIMT producer warps, which
+//     generate relu((x*w)*inv+shift) on the fly, split it and store the core-matrix image.
+//   * persistent CTAs (one per SM), warp-specialised: 4 epilogue warps (TMEM -> scale/shift/residual/ReLU -> fp32 or
+//     hi/lo image), 1 MMA-issuing thread, 1 loader thread (weight images + activation images, mbarrier expect-tx),
+//     8 producer warps (generator mode only); smem full/empty ring (STAGES deep) and a double-buffered TMEM accumulator
+//     so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <math.h>
 #include <string.h>
 
 #include <vector>
 
 #include "cb_internal.cuh"
+#include "cb_tc_common.cuh"
 
 namespace {
 
 constexpr int BM = 128;          // rows (frames) per tile = UMMA M
 constexpr int BK = 32;           // K elements per pipeline stage (2 UMMA K-steps of 16)
 constexpr int STAGES = 4;
-constexpr int N_PROD_WARPS = 8;  // A-operand producers
+constexpr int N_PROD_WARPS = 8;  // A-operand producers (generator mode)
 constexpr int N_EPI_WARPS = 4;   // one per TMEM lane quadrant
 constexpr int NTHREADS = (N_EPI_WARPS + 2 + N_PROD_WARPS) * 32;   // 448
 
@@ -35,99 +37,18 @@ struct TcLayer {                 // one prepared weight image
 };
 
 struct TcState {
-    std::vector<TcLayer> layers; // indexed by GemmProblem::layer_id
+    std::vector<TcLayer> layers; // indexed by layer id
     int* d_range_flag;
 };
 
 struct TcParams {
-    GemmProblem p;
+    TcGemm g;
     const __half* img;
     int BN, n_tiles, k_chunks, m_tiles;
     float out_scale;
     int passes;                  // 3 = hi/lo split, 1 = fast
     int* range_flag;
 };
-
-// ---- PTX helpers -----------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-// K-major, no-swizzle shared-memory matrix descriptor: 16-byte k-group g of row r lives at g*lbo + (r/8)*sbo + (r%8)*16.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= 1ULL << 46;             // descriptor version (Blackwell)
-    return d;                    // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE
-}
-
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
@@ -141,17 +62,30 @@ __device__ __forceinline__ void split4(const float4& a, uint2& hi, uint2& lo, bo
     overflow |= !(fabsf(a.x) <= 65504.f && fabsf(a.y) <= 65504.f && fabsf(a.z) <= 65504.f && fabsf(a.w) <= 65504.f);
 }
 
-// ---- the kernel ----------------------------------------------------------------------------------------------------------
+// Row m of the kernel's row space -> (window b, output frame to); false for padding rows.
+__device__ __forceinline__ bool decode_row(const TcGemm& g, long long m, int& b, int& to) {
+    if (m >= g.M) return false;
+    if (g.row_mode == 0) { b = (int)(m / g.t_out); to = (int)(m - (long long)b * g.t_out); return true; }
+    if (g.row_mode == 1) {                       // every window carries one zero row before and after its frames
+        const int W = g.t_out + 2;
+        b = (int)(m / W); to = (int)(m - (long long)b * W) - 1;
+        return to >= 0 && to < g.t_out && b < g.B;
+    }
+    to = (int)(m / g.Bp); b = (int)(m - (long long)to * g.Bp);     // time-major: m = t*Bp + b
+    return b < g.B;
+}
+
 // shared memory: STAGES x { A_hi[4][128][8], A_lo, B_hi[4][BN][8], B_lo } halfs, then the barriers.
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams q) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const GemmProblem& p = q.p;
+    const TcGemm& g = q.g;
+    const GemmProblem& p = g.p;
     const int BN = q.BN;
-    const uint32_t a_bytes = BM * BK * 2;                 // one of hi / lo
+    constexpr uint32_t a_bytes = BM * BK * 2;             // one of hi / lo
     const uint32_t b_bytes = (uint32_t)BN * BK * 2;
     const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * stage_bytes);
-    uint64_t* full_bar = bars;                            // [STAGES]  producers + weight bytes landed
+    uint64_t* full_bar = bars;                            // [STAGES]  operands landed
     uint64_t* empty_bar = bars + STAGES;                  // [STAGES]  MMAs that read the stage retired
     uint64_t* acc_full = bars + 2 * STAGES;               // [2]       accumulator ready for the epilogue
     uint64_t* acc_empty = bars + 2 * STAGES + 2;          // [2]       accumulator drained
@@ -161,7 +95,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams q) 
     const int total_tiles = q.m_tiles * q.n_tiles;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], N_PROD_WARPS * 32 + 1); mbar_init(&empty_bar[s], 1); }
+        const uint32_t full_count = g.a_mode == 1 ? 1 : N_PROD_WARPS * 32 + 1;
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], full_count); mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], N_EPI_WARPS * 32); }
         fence_barrier_init();
     }
@@ -177,62 +112,82 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams q) 
     if (warp < N_EPI_WARPS) {
         // ============================ epilogue: TMEM -> registers -> scale/shift/residual/ReLU -> HBM =====================
         uint32_t it = 0;
+        bool overflow = false;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int mt = tile / q.n_tiles, nt = tile - mt * q.n_tiles;
             const uint32_t buf = it & 1, par = (it >> 1) & 1;
             mbar_wait(&acc_full[buf], par);
             tc_fence_after();
             const long long m = (long long)mt * BM + warp * 32 + lane;
-            bool row_ok = m < p.M;
-            long long tm_t = 0; int tm_b = 0;
-            if (p.tmajor) { tm_t = m / p.Bp; tm_b = (int)(m - tm_t * p.Bp); row_ok = row_ok && tm_b < p.Bvalid; }
+            int b = 0, to = 0;
+            const bool row_ok = decode_row(g, m, b, to);
             float xr = 0.f;
-            if (p.res && row_ok) {
-                const int b = (int)(m / p.t_out), to = (int)(m % p.t_out);
-                xr = __ldg(p.x + (long long)b * p.t_inr + (long long)to * p.strider);
-            }
+            if (p.res && row_ok) xr = __ldg(p.x + (long long)b * p.t_inr + (long long)to * p.strider);
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * (uint32_t)BN;
+            const long long orow = g.o_tmajor ? (long long)to * g.Bp + b : m;
             for (int c0 = 0; c0 < BN; c0 += 16) {
                 uint32_t v[16];
                 tmem_ld16(taddr + c0, v);
+                tmem_ld_wait();
                 const int n0 = nt * BN + c0;
-                if (row_ok && n0 < p.N && p.out_tlayout) {
-                    float* dst = p.out + ((size_t)tm_t * p.ldo + n0) * (size_t)p.Bp + tm_b;
+                if (!row_ok) continue;
+                float o[16];
 #pragma unroll
-                    for (int e = 0; e < 16; ++e)
-                        dst[(size_t)e * p.Bp] = fmaf(__uint_as_float(v[e]), q.out_scale, __ldg(p.shift + n0 + e));
-                } else if (row_ok && n0 < p.N) {
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const int n = n0 + q4 * 4;
+                    const float4 sh = ldg4(p.shift + n);
+                    o[q4 * 4 + 0] = fmaf(__uint_as_float(v[q4 * 4 + 0]), q.out_scale, sh.x);
+                    o[q4 * 4 + 1] = fmaf(__uint_as_float(v[q4 * 4 + 1]), q.out_scale, sh.y);
+                    o[q4 * 4 + 2] = fmaf(__uint_as_float(v[q4 * 4 + 2]), q.out_scale, sh.z);
+                    o[q4 * 4 + 3] = fmaf(__uint_as_float(v[q4 * 4 + 3]), q.out_scale, sh.w);
+                    if (p.res) {
+                        const float4 w = ldg4(p.rw + n), iv = ldg4(p.rinv + n), rs = ldg4(p.rsh + n);
+                        o[q4 * 4 + 0] += fmaf(xr * w.x, iv.x, rs.x);
+                        o[q4 * 4 + 1] += fmaf(xr * w.y, iv.y, rs.y);
+                        o[q4 * 4 + 2] += fmaf(xr * w.z, iv.z, rs.z);
+                        o[q4 * 4 + 3] += fmaf(xr * w.w, iv.w, rs.w);
+                    }
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) o[e] = fmaxf(o[e], 0.f);
+                }
+                if (g.out_mode == 2) {                    // hi/lo operand image for the next contraction
+#pragma unroll
+                    for (int h8 = 0; h8 < 2; ++h8) {
+                        float v8[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            v8[e] = o[h8 * 8 + e];
+                            overflow |= !(fabsf(v8[e]) <= 65504.f);
+                        }
+                        uint4 hi, lo;
+                        split8(v8, hi, lo);
+                        const size_t off = ((size_t)(g.o_plane0 + (n0 >> 3) + h8) * g.o.plane_rows + CB_IMG_GUARD + orow) * 8;
+                        *reinterpret_cast<uint4*>(g.o.hi + off) = hi;
+                        *reinterpret_cast<uint4*>(g.o.lo + off) = lo;
+                    }
+                } else if (g.out_mode == 1) {             // fp32, time-major [t][ldo][Bp]: coalesced over the warp's rows
+                    float* dst = p.out + ((size_t)to * p.ldo + n0) * (size_t)g.Bp + b;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) dst[(size_t)e * g.Bp] = o[e];
+                } else {                                  // fp32 row-major
                     float* dst = p.out + m * p.ldo + n0;
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int n = n0 + g * 4;
-                        const float4 sh = ldg4(p.shift + n);
-                        float o[4] = {fmaf(__uint_as_float(v[g * 4 + 0]), q.out_scale, sh.x),
-                                      fmaf(__uint_as_float(v[g * 4 + 1]), q.out_scale, sh.y),
-                                      fmaf(__uint_as_float(v[g * 4 + 2]), q.out_scale, sh.z),
-                                      fmaf(__uint_as_float(v[g * 4 + 3]), q.out_scale, sh.w)};
-                        if (p.res) {
-                            const float4 w = ldg4(p.rw + n), iv = ldg4(p.rinv + n), rs = ldg4(p.rsh + n);
-                            o[0] += fmaf(xr * w.x, iv.x, rs.x);
-                            o[1] += fmaf(xr * w.y, iv.y, rs.y);
-                            o[2] += fmaf(xr * w.z, iv.z, rs.z);
-                            o[3] += fmaf(xr * w.w, iv.w, rs.w);
-                        }
-                        if (p.relu) {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
-                        }
-                        *reinterpret_cast<float4*>(dst + g * 4) = make_float4(o[0], o[1], o[2], o[3]);
-                    }
+                    for (int q4 = 0; q4 < 4; ++q4)
+                        *reinterpret_cast<float4*>(dst + q4 * 4) = make_float4(o[q4 * 4], o[q4 * 4 + 1], o[q4 * 4 + 2], o[q4 * 4 + 3]);
                 }
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[buf]);
         }
+        if (overflow) atomicExch(q.range_flag, 1);
     } else if (warp == N_EPI_WARPS) {
         // ============================ MMA issuer (one elected thread) =======================================================
         if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // f16 x f16 -> f32
+            const uint32_t idesc = make_idesc_f16(BM, BN);
+            constexpr uint32_t A_STEP = 2 * BM;               // two k-groups per UMMA K-step, in 16-byte units
+            const uint32_t B_STEP = 2 * (uint32_t)BN;
             uint32_t kit = 0, it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const uint32_t buf = it & 1, par = (it >> 1) & 1;
@@ -244,16 +199,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams q) 
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                    const uint32_t a_hi = sa, a_lo = sa + a_bytes, b_hi = sa + 2 * a_bytes, b_lo = b_hi + b_bytes;
+                    const uint64_t dah = make_desc(sa, BM * 16, 128), dal = make_desc(sa + a_bytes, BM * 16, 128);
+                    const uint64_t dbh = make_desc(sa + 2 * a_bytes, BN * 16, 128);
+                    const uint64_t dbl = make_desc(sa + 2 * a_bytes + b_bytes, BN * 16, 128);
 #pragma unroll
                     for (int ks = 0; ks < BK / 16; ++ks) {
-                        const uint32_t ao = ks * 2 * (BM * 16), bo = ks * 2 * ((uint32_t)BN * 16);
-                        const uint64_t dah = make_desc(a_hi + ao, BM * 16, 128), dal = make_desc(a_lo + ao, BM * 16, 128);
-                        const uint64_t dbh = make_desc(b_hi + bo, BN * 16, 128), dbl = make_desc(b_lo + bo, BN * 16, 128);
-                        umma_f16(d_tmem, dah, dbh, idesc, (kc | ks) != 0);
-                        if (q.passes == 3) {
-                            umma_f16(d_tmem, dah, dbl, idesc, 1);
-                            umma_f16(d_tmem, dal, dbh, idesc, 1);
+                        if (q.passes == 3) {                  // low-order products first (truncating accumulator)
+                            umma_f16(d_tmem, dah + ks * A_STEP, dbl + ks * B_STEP, idesc, (kc | ks) != 0);
+                            umma_f16(d_tmem, dal + ks * A_STEP, dbh + ks * B_STEP, idesc, 1);
+                            umma_f16(d_tmem, dah + ks * A_STEP, dbh + ks * B_STEP, idesc, 1);
+                        } else {
+                            umma_f16(d_tmem, dah + ks * A_STEP, dbh + ks * B_STEP, idesc, (kc | ks) != 0);
                         }
                     }
                     umma_commit(&empty_bar[s]);               // frees the stage once these MMAs retire
@@ -262,23 +218,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams q) 
             }
         }
     } else if (warp == N_EPI_WARPS + 1) {
-        // ============================ weight loader: pre-packed images, one bulk copy per stage ==============================
+        // ============================ loader: weight images (+ activation images) via cp.async.bulk ==========================
         if (lane == 0) {
             uint32_t kit = 0;
+            const int n0c = g.taps * g.a0_chunks_per_tap;     // k-chunks served by image 0
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = tile % q.n_tiles;
-                const __half* src = q.img + (size_t)nt * q.k_chunks * (2 * (size_t)BN * BK);
+                const int mt = tile / q.n_tiles, nt = tile - mt * q.n_tiles;
+                const __half* wsrc = q.img + (size_t)nt * q.k_chunks * (2 * (size_t)BN * BK);
+                const long long r0 = (long long)mt * BM + CB_IMG_GUARD;
                 for (int kc = 0; kc < q.k_chunks; ++kc, ++kit) {
                     const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[s], 2 * b_bytes);
-                    bulk_g2s(smem + (size_t)s * stage_bytes + 2 * a_bytes, src + (size_t)kc * (2 * (size_t)BN * BK),
-                             2 * b_bytes, &full_bar[s]);
+                    uint8_t* st = smem + (size_t)s * stage_bytes;
+                    if (g.a_mode == 1) {
+                        mbar_arrive_expect_tx(&full_bar[s], 2 * a_bytes + 2 * b_bytes);
+                        const __half *hi, *lo; long long row; int plane;
+                        if (kc < n0c) {
+                            const int j = kc / g.a0_chunks_per_tap, cc = kc - j * g.a0_chunks_per_tap;
+                            hi = g.a0.hi; lo = g.a0.lo; row = r0 + j - g.left; plane = g.a0_plane0 + cc * 4;
+                            hi += ((size_t)plane * g.a0.plane_rows + row) * 8; lo += ((size_t)plane * g.a0.plane_rows + row) * 8;
+#pragma unroll
+                            for (int kg = 0; kg < 4; ++kg) {
+                                bulk_g2s(st + kg * (BM * 16), hi + (size_t)kg * g.a0.plane_rows * 8, BM * 16, &full_bar[s]);
+                                bulk_g2s(st + a_bytes + kg * (BM * 16), lo + (size_t)kg * g.a0.plane_rows * 8, BM * 16, &full_bar[s]);
+                            }
+                        } else {
+                            const int cc = kc - n0c;
+                            plane = g.a1_plane0 + cc * 4;
+                            hi = g.a1.hi + ((size_t)plane * g.a1.plane_rows + r0) * 8;
+                            lo = g.a1.lo + ((size_t)plane * g.a1.plane_rows + r0) * 8;
+#pragma unroll
+                            for (int kg = 0; kg < 4; ++kg) {
+                                bulk_g2s(st + kg * (BM * 16), hi + (size_t)kg * g.a1.plane_rows * 8, BM * 16, &full_bar[s]);
+                                bulk_g2s(st + a_bytes + kg * (BM * 16), lo + (size_t)kg * g.a1.plane_rows * 8, BM * 16, &full_bar[s]);
+                            }
+                        }
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[s], 2 * b_bytes);
+                    }
+                    bulk_g2s(st + 2 * a_bytes, wsrc + (size_t)kc * (2 * (size_t)BN * BK), 2 * b_bytes, &full_bar[s]);
                 }
             }
         }
-    } else {
-        // ============================ A producers: gather fp32 rows, split to fp16 hi/lo, store the core-matrix image ========
+    } else if (g.a_mode == 0) {
+        // ============================ A producers (generator / gather mode) ==================================================
         const int pt = threadIdx.x - (N_EPI_WARPS + 2) * 32;      // 0..255
         const int r = pt & 127, hsel = pt >> 7;                   // row of the tile, which 16-wide half of the 32-wide chunk
         const int K0 = p.taps * p.c0;
@@ -287,12 +270,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams q) 
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int mt = tile / q.n_tiles;
             const long long m = (long long)mt * BM + r;
-            bool row_ok = m < p.M;
             int b = 0, to = 0;
-            if (row_ok) {
-                if (p.tmajor) { to = (int)(m / p.Bp); b = (int)(m - (long long)to * p.Bp); row_ok = b < p.Bvalid; }
-                else { b = (int)(m / p.t_out); to = (int)(m % p.t_out); }
-            }
+            const bool row_ok = decode_row(g, m, b, to);
             const long long f0 = (long long)b * p.t_in0;
             const int tbase = to * p.stride0 - p.left;
             for (int kc = 0; kc < q.k_chunks; ++kc, ++kit) {
@@ -300,9 +279,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams q) 
                 float4 a[4];
                 const int kk = kc * BK + hsel * 16;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int kq = kk + g * 4;
-                    a[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int gq = 0; gq < 4; ++gq) {
+                    const int kq = kk + gq * 4;
+                    a[gq] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (!row_ok || kq >= p.K) continue;
                     if (kq < K0) {
                         const int j = kq / p.c0, c = kq - j * p.c0;
@@ -311,24 +290,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams q) 
                         if (p.gen) {
                             const float xv = __ldg(p.x + f0 + ti);
                             const float4 w = ldg4(p.gw + c), iv = ldg4(p.ginv + c), sh = ldg4(p.gsh + c);
-                            a[g].x = fmaxf(fmaf(xv * w.x, iv.x, sh.x), 0.f);
-                            a[g].y = fmaxf(fmaf(xv * w.y, iv.y, sh.y), 0.f);
-                            a[g].z = fmaxf(fmaf(xv * w.z, iv.z, sh.z), 0.f);
-                            a[g].w = fmaxf(fmaf(xv * w.w, iv.w, sh.w), 0.f);
-                        } else if (p.a_tlayout) {
-                            const float* src = p.src0 + ((size_t)ti * p.lda0 + c) * (size_t)p.Bp + b;
-                            a[g].x = __ldg(src); a[g].y = __ldg(src + p.Bp);
-                            a[g].z = __ldg(src + 2 * (size_t)p.Bp); a[g].w = __ldg(src + 3 * (size_t)p.Bp);
+                            a[gq].x = fmaxf(fmaf(xv * w.x, iv.x, sh.x), 0.f);
+                            a[gq].y = fmaxf(fmaf(xv * w.y, iv.y, sh.y), 0.f);
+                            a[gq].z = fmaxf(fmaf(xv * w.z, iv.z, sh.z), 0.f);
+                            a[gq].w = fmaxf(fmaf(xv * w.w, iv.w, sh.w), 0.f);
                         } else {
-                            a[g] = ldg4(p.src0 + (f0 + ti) * p.lda0 + c);
+                            a[gq] = ldg4(p.src0 + (f0 + ti) * p.lda0 + c);
                         }
                     } else {
-                        a[g] = ldg4(p.src1 + ((long long)b * p.t_in1 + (long long)to * p.stride1) * p.lda1 + (kq - K0));
+                        a[gq] = ldg4(p.src1 + ((long long)b * p.t_in1 + (long long)to * p.stride1) * p.lda1 + (kq - K0));
                     }
                 }
                 uint2 hi[4], lo[4];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) split4(a[g], hi[g], lo[g], overflow);
+                for (int gq = 0; gq < 4; ++gq) split4(a[gq], hi[gq], lo[gq], overflow);
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* st = smem + (size_t)s * stage_bytes;
                 // k-group (8 halfs = 16 B) index within the stage: hsel*2 + {0,1}; row r at +r*16
@@ -365,7 +340,9 @@ int pick_bn(int N) {
 }  // namespace
 
 // ---- host: weight images -------------------------------------------------------------------------------------------------
-static int build_layer(TcState* st, int layer_id, const float* W, int K, int N) {
+// W is [K][N] fp32 (row k = input channel in the order the A operand presents it).
+int cb_tc_build_layer(cb_handle* h, int layer_id, const float* W, int K, int N) {
+    TcState* st = (TcState*)h->tc;
     TcLayer L;
     memset(&L, 0, sizeof(L));
     L.K = K; L.N = N; L.BN = pick_bn(N);
@@ -384,15 +361,15 @@ static int build_layer(TcState* st, int layer_id, const float* W, int K, int N) 
     for (int nt = 0; nt < L.n_tiles; ++nt)
         for (int kc = 0; kc < L.k_chunks; ++kc) {
             __half* base = img.data() + ((size_t)nt * L.k_chunks + kc) * per_chunk;
-            for (int g = 0; g < 4; ++g)
+            for (int gq = 0; gq < 4; ++gq)
                 for (int n = 0; n < L.BN; ++n)
                     for (int e = 0; e < 8; ++e) {
-                        const int k = kc * BK + g * 8 + e;
+                        const int k = kc * BK + gq * 8 + e;
                         const float w = k < K ? W[(size_t)k * N + nt * L.BN + n] * scale : 0.f;
                         const __half hi = __float2half_rn(w);
                         const __half lo = __float2half_rn(w - __half2float(hi));
-                        base[(size_t)g * L.BN * 8 + n * 8 + e] = hi;
-                        base[(size_t)L.BN * BK + (size_t)g * L.BN * 8 + n * 8 + e] = lo;
+                        base[(size_t)gq * L.BN * 8 + n * 8 + e] = hi;
+                        base[(size_t)L.BN * BK + (size_t)gq * L.BN * 8 + n * 8 + e] = lo;
                     }
         }
     CB_CUDA(cudaMalloc(&L.img, img.size() * sizeof(__half)));
@@ -408,23 +385,43 @@ int cb_tc_prepare(cb_handle* h, const float* hw) {
     h->tc = st;
     const CbConfig& c = h->cfg;
     const int C = c.channels, H = c.hidden;
+    for (int b = 1; b < c.n_blocks; ++b)
+        if (c.stride[b] != 1 || c.k[b] != 3) {
+            cb_set_error("tensor-core path supports stride-1, width-3 residual blocks after the first; use precision fp32");
+            return CB_ERR_ARG;
+        }
+    if (C % 32) { cb_set_error("tensor-core path needs channels %% 32 == 0"); return CB_ERR_ARG; }
     auto host = [&](const float* dev) { return hw + (dev - h->d_weights); };
     int rc;
     for (int b = 0; b < c.n_blocks; ++b) {
-        if (b > 0 && (rc = build_layer(st, b * 4 + 0, host(h->conv2a[b].W), C, C)) != CB_OK) return rc;
-        if ((rc = build_layer(st, b * 4 + 1, host(h->conv2b[b].W), c.k[b] * C, C)) != CB_OK) return rc;
-        if ((rc = build_layer(st, b * 4 + 2, host(h->convc[b].W), b == 0 ? C : 2 * C, C)) != CB_OK) return rc;
+        if (b > 0 && (rc = cb_tc_build_layer(h, b * 4 + 0, host(h->conv2a[b].W), C, C)) != CB_OK) return rc;
+        if ((rc = cb_tc_build_layer(h, b * 4 + 1, host(h->conv2b[b].W), c.k[b] * C, C)) != CB_OK) return rc;
+        if ((rc = cb_tc_build_layer(h, b * 4 + 2, host(h->convc[b].W), b == 0 ? C : 2 * C, C)) != CB_OK) return rc;
     }
+    // LSTM input projections.  Layer 0 reads the CNN feature image (K = C).  Later layers read the h image written by
+    // the recurrence, whose planes are [fw: 13 k-groups (104 ch, 100 real)][bw: 13 k-groups]: K' = 208 with zero rows.
+    const int HP = (H + 7) / 8 * 8;                         // 104
     for (int l = 0; l < c.n_layers; ++l) {
-        if (l == 0 || c.rnn_layout == 0) {
-            if ((rc = build_layer(st, 32 + l * 2, host(h->wxcat[l]), l == 0 ? C : 2 * H, 8 * H)) != CB_OK) return rc;
-        } else {
+        if (l == 0) {
+            if ((rc = cb_tc_build_layer(h, 32, host(h->wxcat[0]), C, 8 * H)) != CB_OK) return rc;
+        } else if (c.rnn_layout == 0) {
+            std::vector<float> W((size_t)2 * HP * 8 * H, 0.f);
+            const float* src = host(h->wxcat[l]);               // [2H][8H]
             for (int d = 0; d < 2; ++d)
-                if ((rc = build_layer(st, 32 + l * 2 + d, host(h->wx[l][d]), H, 4 * H)) != CB_OK) return rc;
+                for (int u = 0; u < H; ++u)
+                    memcpy(&W[(size_t)(d * HP + u) * 8 * H], src + (size_t)(d * H + u) * 8 * H, sizeof(float) * 8 * H);
+            if ((rc = cb_tc_build_layer(h, 32 + l * 2, W.data(), 2 * HP, 8 * H)) != CB_OK) return rc;
+        } else {
+            for (int d = 0; d < 2; ++d) {
+                std::vector<float> W((size_t)HP * 4 * H, 0.f);
+                memcpy(W.data(), host(h->wx[l][d]), sizeof(float) * (size_t)H * 4 * H);
+                if ((rc = cb_tc_build_layer(h, 32 + l * 2 + d, W.data(), HP, 4 * H)) != CB_OK) return rc;
+            }
         }
     }
     CB_CUDA(cudaMalloc(&st->d_range_flag, sizeof(int)));
     CB_CUDA(cudaMemset(st->d_range_flag, 0, sizeof(int)));
+    CB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for(256)));
     return cb_lstm_tc_prepare(h, hw);
 }
 
@@ -437,6 +434,8 @@ void cb_tc_release(cb_handle* h) {
     delete st;
     h->tc = nullptr;
 }
+
+int* cb_tc_range_flag(cb_handle* h) { return h->tc ? ((TcState*)h->tc)->d_range_flag : nullptr; }
 
 int cb_tc_check_range(cb_handle* h, cudaStream_t s) {
     TcState* st = (TcState*)h->tc;
@@ -452,39 +451,35 @@ int cb_tc_check_range(cb_handle* h, cudaStream_t s) {
     return CB_OK;
 }
 
-int cb_launch_gemm_tc(cb_handle* h, const GemmProblem& p, cudaStream_t s) {
+int cb_launch_gemm_tc(cb_handle* h, const TcGemm& g, cudaStream_t s) {
     TcState* st = (TcState*)h->tc;
-    if (!st || p.layer_id < 0 || p.layer_id >= (int)st->layers.size() || !st->layers[p.layer_id].img) {
-        cb_set_error("tensor-core path: no weight image for layer %d", p.layer_id);
+    if (!st || g.layer_id < 0 || g.layer_id >= (int)st->layers.size() || !st->layers[g.layer_id].img) {
+        cb_set_error("tensor-core path: no weight image for layer %d", g.layer_id);
         return CB_ERR_ARG;
     }
-    if (p.M <= 0) return CB_OK;
-    const TcLayer& L = st->layers[p.layer_id];
-    if (L.K != p.K || L.N != p.N) { cb_set_error("tensor-core path: layer %d shape mismatch", p.layer_id); return CB_ERR_ARG; }
-    if ((p.c0 & 3) || (p.c1 & 3) || (p.lda0 & 3) || (p.lda1 & 3) || (p.ldo & 3) || (p.taps > 1 && (p.c0 % 16))) {
-        cb_set_error("tensor-core path: unsupported channel alignment");
+    if (g.M <= 0) return CB_OK;
+    const TcLayer& L = st->layers[g.layer_id];
+    if (L.N != g.p.N) { cb_set_error("tensor-core path: layer %d N mismatch", g.layer_id); return CB_ERR_ARG; }
+    if (g.a_mode == 1) {
+        if (g.taps * g.a0_chunks_per_tap + g.a1_chunks != L.k_chunks) {
+            cb_set_error("tensor-core path: layer %d K mismatch (%d chunks vs %d)", g.layer_id,
+                         g.taps * g.a0_chunks_per_tap + g.a1_chunks, L.k_chunks);
+            return CB_ERR_ARG;
+        }
+    } else if (L.K != g.p.K || (g.p.c0 & 3) || (g.p.c1 & 3) || (g.p.lda0 & 3) || (g.p.lda1 & 3)) {
+        cb_set_error("tensor-core path: layer %d gather shape mismatch", g.layer_id);
         return CB_ERR_ARG;
     }
+    if ((g.row_mode == 2 || g.o_tmajor) && g.Bp % BM) { cb_set_error("tensor-core path: padded batch must be a multiple of 128"); return CB_ERR_ARG; }
     TcParams q;
-    q.p = p; q.img = L.img; q.BN = L.BN; q.n_tiles = L.n_tiles; q.k_chunks = L.k_chunks;
-    q.m_tiles = (p.M + BM - 1) / BM; q.out_scale = L.out_scale;
-    if (p.tmajor && (p.Bp % BM || p.taps != 1 || p.stride0 != 1 || p.c1 || p.res || p.relu)) {
-        cb_set_error("tensor-core path: unsupported time-major contraction");
-        return CB_ERR_ARG;
-    }
+    q.g = g; q.img = L.img; q.BN = L.BN; q.n_tiles = L.n_tiles; q.k_chunks = L.k_chunks;
+    q.m_tiles = (int)(((long long)g.M + BM - 1) / BM); q.out_scale = L.out_scale;
     q.passes = h->precision == CB_PREC_TC_FAST ? 1 : 3;
     q.range_flag = st->d_range_flag;
-    const size_t smem = smem_bytes_for(L.BN);
-    static bool attr_set = false;
-    if (!attr_set) {
-        CB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for(256)));
-        attr_set = true;
-    }
     const long long tiles = (long long)q.m_tiles * q.n_tiles;
     const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
-    gemm_tc_kernel<<<grid, NTHREADS, smem, s>>>(q);
+    gemm_tc_kernel<<<grid, NTHREADS, smem_bytes_for(L.BN), s>>>(q);
     CB_CHECK_LAUNCH();
     h->launches++;
     return CB_OK;
 }
-
