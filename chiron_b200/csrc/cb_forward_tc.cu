@@ -2,9 +2,9 @@
 // (chiron_model.inference, chiron/chiron_model.py:134-172: getcnnfeature -> rnn_layers -> logits.)
 //
 // Data flow (all activations as fp16 hi/lo k-group-plane images, see cb_tc_common.cuh):
-//   x --[generator producers]--> conv2b(1) --> P0 --conv2c(1)+rank-1 branch--> P1 = block-1 output
-//   block n>=2:  X --conv2a--> A --conv2b (3 taps = 3 row-shifted bulk loads)--> Bt --conv2c ++ branch1(X)--> X'
-//   last block writes its output image in time-major row order (row = t*Bp + b)
+//   x --transpose--> xT --gen_conv2a--> A0 --conv2b(1) (k taps, stride)--> P0 --conv2c(1)+rank-1 branch--> P1 = block-1 output
+//   block n>=2:  X --conv2a--> A --conv2b (3 taps = 3 frame-shifted bulk loads)--> Bt --conv2c ++ branch1(X)--> X'
+//   every image is time-major (row = frame*Bp + window), so the last block's output is the LSTM's A operand as is
 //   LSTM layer l: image --input projection--> pre[T][8H][Bp] fp32 --recurrence--> h image (or fp32 out for the last layer)
 //   head (time-major) -> logits[B][T][n_class]; path_prob.
 #include <string.h>
@@ -20,28 +20,32 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 struct TcWorkspace {
     void* base; size_t bytes;
     int B, L;                     // geometry the images were zeroed for
-    CbImg conv[3];                // padded row-major images, rows = B*(T+2)
-    CbImg fea;                    // CNN feature, time-major rows t*Bp + b
-    CbImg himg;                   // LSTM layer output, planes [fw 13][bw 13], time-major rows
+    CbImg a0;                     // block-1 conv2a output: L frames + the 'SAME' padding frames of conv2b
+    CbImg conv[3];                // block activations: T frames + one zero frame in front and behind
+    CbImg himg;                   // LSTM layer output, planes [fw 13][bw 13]
+    float* xT;                    // [L][Bp] transposed raw windows
     float* pre;                   // [T][8H][Bp]
     float* out;                   // [T][2H][Bp] (last layer)
+    int fea_idx;                  // which conv image holds the CNN feature of the last forward
 };
 
-int ensure_ws(cb_handle* h, int B, int L, int T, int Bp, cudaStream_t s) {
+int ensure_ws(cb_handle* h, int B, int L, int T, int Bp, int pad0, int left0, cudaStream_t s) {
     TcWorkspace* w = (TcWorkspace*)h->tc_ws;
     if (!w) { w = new TcWorkspace(); memset(w, 0, sizeof(*w)); h->tc_ws = w; }
     const CbConfig& c = h->cfg;
     const int planes = c.channels / 8;
-    const long long rows_c = CB_IMG_GUARD + (long long)B * (T + 2) + 128 + CB_IMG_GUARD;
-    const long long rows_t = CB_IMG_GUARD + (long long)T * Bp + 128 + CB_IMG_GUARD;
+    const long long rows_a0 = (long long)(L + pad0) * Bp;
+    const long long rows_c = (long long)(T + 2) * Bp;
+    const long long rows_h = (long long)T * Bp;
     const int hplanes = 32;       // 26 real k-group planes (2 x 13) + zero planes the K padding reads
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
-    size_t o_conv[3][2], o_fea[2], o_h[2];
+    size_t o_a0[2], o_conv[3][2], o_h[2];
+    for (int j = 0; j < 2; ++j) o_a0[j] = carve(cb_img_halfs(rows_a0, planes) * 2);
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j) o_conv[i][j] = carve(cb_img_halfs(rows_c, planes) * 2);
-    for (int j = 0; j < 2; ++j) o_fea[j] = carve(cb_img_halfs(rows_t, planes) * 2);
-    for (int j = 0; j < 2; ++j) o_h[j] = carve(cb_img_halfs(rows_t, hplanes) * 2);
+    for (int j = 0; j < 2; ++j) o_h[j] = carve(cb_img_halfs(rows_h, hplanes) * 2);
     const size_t img_bytes = off;
+    const size_t o_xt = carve((size_t)L * Bp * sizeof(float));
     const size_t o_pre = carve((size_t)T * 8 * c.hidden * Bp * sizeof(float));
     const size_t o_out = carve((size_t)T * 2 * c.hidden * Bp * sizeof(float));
     bool rezero = w->B != B || w->L != L;
@@ -53,14 +57,16 @@ int ensure_ws(cb_handle* h, int B, int L, int T, int Bp, cudaStream_t s) {
         rezero = true;
     }
     char* base = (char*)w->base;
+    w->a0.hi = (__half*)(base + o_a0[0]); w->a0.lo = (__half*)(base + o_a0[1]);
+    w->a0.plane_rows = rows_a0; w->a0.row0 = (long long)left0 * Bp; w->a0.planes = planes;
     for (int i = 0; i < 3; ++i) {
         w->conv[i].hi = (__half*)(base + o_conv[i][0]); w->conv[i].lo = (__half*)(base + o_conv[i][1]);
-        w->conv[i].plane_rows = rows_c; w->conv[i].planes = planes;
+        w->conv[i].plane_rows = rows_c; w->conv[i].row0 = Bp; w->conv[i].planes = planes;
     }
-    w->fea.hi = (__half*)(base + o_fea[0]); w->fea.lo = (__half*)(base + o_fea[1]); w->fea.plane_rows = rows_t; w->fea.planes = planes;
-    w->himg.hi = (__half*)(base + o_h[0]); w->himg.lo = (__half*)(base + o_h[1]); w->himg.plane_rows = rows_t; w->himg.planes = hplanes;
-    w->pre = (float*)(base + o_pre); w->out = (float*)(base + o_out);
-    if (rezero) {     // padding rows, guards and unused planes must read as zero; interiors are rewritten every call
+    w->himg.hi = (__half*)(base + o_h[0]); w->himg.lo = (__half*)(base + o_h[1]);
+    w->himg.plane_rows = rows_h; w->himg.row0 = 0; w->himg.planes = hplanes;
+    w->xT = (float*)(base + o_xt); w->pre = (float*)(base + o_pre); w->out = (float*)(base + o_out);
+    if (rezero) {     // padding frames, rows of windows >= B and unused planes must read as zero; the rest is rewritten
         CB_CUDA(cudaMemsetAsync(base, 0, img_bytes, s));
         w->B = B; w->L = L;
     }
@@ -89,58 +95,56 @@ int cb_forward_tc(cb_handle* h, const float* x, const int32_t* seq_len_out, int 
                   float* path_prob, cudaStream_t s) {
     const CbConfig& c = h->cfg;
     const int C = c.channels, H = c.hidden;
-    const int T0 = (L + c.stride[0] - 1) / c.stride[0];      // frames after block 1; later blocks have stride 1
-    const int T = T0;
+    const int st0 = c.stride[0], k0 = c.k[0];
+    const int T = (L + st0 - 1) / st0;                        // frames after block 1; later blocks have stride 1
+    int pad0 = (T - 1) * st0 + k0 - L; if (pad0 < 0) pad0 = 0;   // TF 'SAME'
+    const int left0 = pad0 / 2;
     const int Bp = (B + 127) / 128 * 128;
-    int rc = ensure_ws(h, B, L, T, Bp, s);
+    int rc = ensure_ws(h, B, L, T, Bp, pad0, left0, s);
     if (rc != CB_OK) return rc;
     TcWorkspace* w = (TcWorkspace*)h->tc_ws;
     h->prof_n = 0;
     if (h->timing) CB_CUDA(cudaEventRecord(h->ev[0], s));
 
     const int cpt = C / 32;                                   // 32-channel k-chunks per tap
-    const int Mpad = B * (T + 2);
     auto base_gemm = [&](int layer_id) {
         TcGemm g;
         memset(&g, 0, sizeof(g));
-        g.layer_id = layer_id; g.M = Mpad; g.row_mode = 1; g.t_out = T; g.B = B; g.Bp = Bp;
-        g.p.N = C; g.p.relu = 1; g.out_mode = 2;
+        g.layer_id = layer_id; g.T = T; g.B = B; g.Bp = Bp; g.taps = 1; g.stride = 1; g.a0_chunks_per_tap = cpt;
+        g.N = C; g.relu = 1; g.out_mode = 2;
         return g;
     };
-    // ---- block 1 (cnn.py:383-384): conv2a is generated from x inside the producers of conv2b ---------------------------
+    // ---- block 1 (cnn.py:383-384): conv2a is a rank-1 function of the raw signal ----------------------------------------
     {
-        const int st = c.stride[0], k = c.k[0];
-        int pad = (T - 1) * st + k - L; if (pad < 0) pad = 0;     // TF 'SAME'
-        TcGemm g = base_gemm(1);
-        g.a_mode = 0;
-        g.p.M = Mpad; g.p.K = k * C; g.p.t_out = T; g.p.t_in0 = L; g.p.stride0 = st; g.p.taps = k; g.p.left = pad / 2; g.p.c0 = C;
-        g.p.gen = 1; g.p.x = x; g.p.gw = h->g_w; g.p.ginv = h->g_inv; g.p.gsh = h->g_sh;
-        g.p.shift = h->conv2b[0].shift; g.o = w->conv[0];
+        int pi = cb_prof_begin(h, CB_CAT_CONV, s);
+        rc = cb_launch_transpose_x(h, x, B, L, Bp, w->xT, s);
+        if (rc == CB_OK) rc = cb_launch_gen_conv2a(h, w->xT, B, Bp, L, w->a0, s);
+        cb_prof_end(h, pi, s);
+        if (rc != CB_OK) return rc;
+        TcGemm g = base_gemm(1);                                  // conv2b: k0 taps, stride st0
+        g.a0 = w->a0; g.taps = k0; g.left = left0; g.stride = st0; g.shift = h->conv2b[0].shift; g.o = w->conv[0];
         if ((rc = timed_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
-        g = base_gemm(2);
-        g.a_mode = 1; g.a0 = w->conv[0]; g.taps = 1; g.a0_chunks_per_tap = cpt;
-        g.p.shift = h->convc[0].shift; g.p.res = 1; g.p.x = x; g.p.t_inr = L; g.p.strider = st;
-        g.p.rw = h->r_w; g.p.rinv = h->r_inv; g.p.rsh = h->r_sh;
-        if (c.n_blocks == 1) { g.o = w->fea; g.o_tmajor = 1; } else g.o = w->conv[1];
+        g = base_gemm(2);                                         // conv2c + rank-1 branch1 of the raw signal
+        g.a0 = w->conv[0]; g.shift = h->convc[0].shift;
+        g.res = 1; g.xT = w->xT; g.res_stride = st0; g.rw = h->r_w; g.rinv = h->r_inv; g.rsh = h->r_sh;
+        g.o = w->conv[1];
         if ((rc = timed_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
     }
     int xi = 1;
     for (int b = 1; b < c.n_blocks; ++b) {
         const int ai = (xi + 1) % 3, bi = (xi + 2) % 3;
         TcGemm g = base_gemm(b * 4 + 0);                          // conv2a 1x1
-        g.a_mode = 1; g.a0 = w->conv[xi]; g.taps = 1; g.a0_chunks_per_tap = cpt; g.p.shift = h->conv2a[b].shift; g.o = w->conv[ai];
+        g.a0 = w->conv[xi]; g.shift = h->conv2a[b].shift; g.o = w->conv[ai];
         if ((rc = timed_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
-        g = base_gemm(b * 4 + 1);                                 // conv2b 1x3: three row-shifted views of the same image
-        g.a_mode = 1; g.a0 = w->conv[ai]; g.taps = c.k[b]; g.left = (c.k[b] - 1) / 2; g.a0_chunks_per_tap = cpt;
-        g.p.shift = h->conv2b[b].shift; g.o = w->conv[bi];
+        g = base_gemm(b * 4 + 1);                                 // conv2b 1x3: three frame-shifted views of the same image
+        g.a0 = w->conv[ai]; g.taps = c.k[b]; g.left = (c.k[b] - 1) / 2; g.shift = h->conv2b[b].shift; g.o = w->conv[bi];
         if ((rc = timed_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
         g = base_gemm(b * 4 + 2);                                 // conv2c ++ branch1(X), ReLU
-        g.a_mode = 1; g.a0 = w->conv[bi]; g.taps = 1; g.a0_chunks_per_tap = cpt; g.a1 = w->conv[xi]; g.a1_chunks = cpt;
-        g.p.shift = h->convc[b].shift;
-        if (b == c.n_blocks - 1) { g.o = w->fea; g.o_tmajor = 1; } else g.o = w->conv[ai];
+        g.a0 = w->conv[bi]; g.a1 = w->conv[xi]; g.a1_chunks = cpt; g.shift = h->convc[b].shift; g.o = w->conv[ai];
         if ((rc = timed_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
         xi = ai;
     }
+    w->fea_idx = xi;
     if (h->timing) CB_CUDA(cudaEventRecord(h->ev[1], s));
 
     // ---- BiLSTM stack -------------------------------------------------------------------------------------------------------
@@ -150,14 +154,13 @@ int cb_forward_tc(cb_handle* h, const float* x, const int32_t* seq_len_out, int 
         for (int d = 0; d < n_gemm; ++d) {
             TcGemm g;
             memset(&g, 0, sizeof(g));
-            g.layer_id = 32 + l * 2 + d; g.M = T * Bp; g.row_mode = 2; g.t_out = T; g.B = B; g.Bp = Bp;
-            g.a_mode = 1; g.taps = 1;
-            if (l == 0) { g.a0 = w->fea; g.a0_chunks_per_tap = cpt; }
+            g.layer_id = 32 + l * 2 + d; g.T = T; g.B = B; g.Bp = Bp; g.taps = 1; g.stride = 1;
+            if (l == 0) { g.a0 = w->conv[xi]; g.a0_chunks_per_tap = cpt; }
             else if (n_gemm == 1) { g.a0 = w->himg; g.a0_chunks_per_tap = 7; }                 // K' = 208 -> 7 chunks
             else { g.a0 = w->himg; g.a0_plane0 = d * 13; g.a0_chunks_per_tap = 4; }            // K' = 104 -> 4 chunks
-            g.p.N = n_gemm == 1 ? 8 * H : 4 * H;
-            g.p.shift = n_gemm == 1 ? h->bcat[l] : h->bias[l][d];
-            g.out_mode = 1; g.p.out = w->pre + (size_t)d * 4 * H * Bp; g.p.ldo = 8 * H;
+            g.N = n_gemm == 1 ? 8 * H : 4 * H;
+            g.shift = n_gemm == 1 ? h->bcat[l] : h->bias[l][d];
+            g.out_mode = 1; g.out = w->pre + (size_t)d * 4 * H * Bp; g.ldo = 8 * H;
             if ((rc = timed_gemm(h, g, s, CB_CAT_LSTM_IN)) != CB_OK) return rc;
         }
         LstmProblem lp;
@@ -200,14 +203,14 @@ long long cb_debug_fetch_tc(cb_handle* h, int what, float* dst, size_t max_float
                 for (size_t ch = 0; ch < width; ++ch) {
                     size_t plane, e;
                     plane_of(ch, plane, e);
-                    const size_t i = (plane * img.plane_rows + CB_IMG_GUARD + t * Bp + b) * 8 + e;
+                    const size_t i = (plane * img.plane_rows + img.row0 + t * Bp + b) * 8 + e;
                     out[(b * T + t) * width + ch] = __half2float(hi[i]) + __half2float(lo[i]);
                 }
         return CB_OK;
     };
     if (what == 0) {
         if (B * T * C > max_floats) { cb_set_error("cb_debug_fetch: destination too small"); return CB_ERR_ARG; }
-        int rc = fetch_img(w->fea, C, [](size_t ch, size_t& pl, size_t& e) { pl = ch / 8; e = ch % 8; }, dst);
+        int rc = fetch_img(w->conv[w->fea_idx], C, [](size_t ch, size_t& pl, size_t& e) { pl = ch / 8; e = ch % 8; }, dst);
         return rc == CB_OK ? (long long)(B * T * C) : rc;
     }
     if (B * T * 2 * H > max_floats) { cb_set_error("cb_debug_fetch: destination too small"); return CB_ERR_ARG; }

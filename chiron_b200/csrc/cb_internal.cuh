@@ -68,19 +68,20 @@ struct GemmProblem {
 };
 
 // ---- one tensor-core contraction (cb_tc.cu) ----------------------------------------------------------------------------
+// Row space: m = to*Bp + b (output frame to < T, window b < B; Bp = B rounded up to 128), so a 128-row tile is 128
+// consecutive windows of one frame.  K is image a0 read at frames to*stride + j - left (j < taps) followed by image a1
+// read at frame to (the appended 1x1 branch input).
 struct TcGemm {
     int layer_id;             // prepared weight image
-    // row space of the kernel: 0 plain m = b*t_out + to; 1 padded m = b*(t_out+2) + 1 + to (a zero row around every
-    // window, so conv taps are plain row shifts); 2 time-major m = to*Bp + b
-    int M, row_mode, t_out, B, Bp;
-    int a_mode;               // 0 = SIMT producers gather/generate from `p`; 1 = operand images a0 (taps) ++ a1
-    GemmProblem p;            // gather description (a_mode 0) + epilogue parameters (N, shift, relu, res*, x, out, ldo)
+    int T, B, Bp;
     CbImg a0, a1;
-    int a0_plane0, a1_plane0;         // first k-group plane of each source
-    int a0_chunks_per_tap, taps, left, a1_chunks;   // K = taps*a0_chunks_per_tap*32 + a1_chunks*32
-    int out_mode;             // 0 fp32 row-major p.out[m][ldo]; 1 fp32 time-major p.out[to][ldo][Bp]; 2 operand image o
-    CbImg o;
-    int o_plane0, o_tmajor;   // image rows: m, or to*Bp + b when o_tmajor
+    int a0_plane0, a1_plane0;                 // first k-group plane of each source
+    int a0_chunks_per_tap, taps, left, stride, a1_chunks;     // K = (taps*a0_chunks_per_tap + a1_chunks) * 32
+    int N; const float* shift; int relu;
+    int res; const float* xT; int res_stride; const float *rw, *rinv, *rsh;   // + (xT[to*res_stride][b]*rw)*rinv + rsh
+    int out_mode;             // 1 fp32 time-major out[to][ldo][Bp]; 2 operand image o
+    float* out; int ldo;
+    CbImg o; int o_plane0;
 };
 
 struct LstmProblem {         // both directions of one layer (grid.y = direction)
@@ -134,6 +135,8 @@ struct cb_handle {
 int cb_launch_gemm_simt(cb_handle* h, const GemmProblem& p, cudaStream_t s);
 int cb_launch_lstm_simt(cb_handle* h, const LstmProblem& p, cudaStream_t s);
 int cb_launch_gemm_tc(cb_handle* h, const TcGemm& g, cudaStream_t s);
+int cb_launch_transpose_x(cb_handle* h, const float* x, int B, int L, int Bp, float* xT, cudaStream_t s);
+int cb_launch_gen_conv2a(cb_handle* h, const float* xT, int B, int Bp, int L, const CbImg& o, cudaStream_t s);
 int cb_launch_lstm_tc(cb_handle* h, const LstmProblem& p, const CbImg* o_img, int write_f32, cudaStream_t s);
 int cb_tc_prepare(cb_handle* h, const float* host_weights);   // build fp16 hi/lo operand images from d_weights layout
 void cb_tc_release(cb_handle* h);

@@ -43,7 +43,7 @@ struct LstmTcParams {
     const int32_t* lens;       // [B]
     float* out;                // [T][2H][Bp] fp32 (written when write_f32: the last layer, read by the logit head)
     CbImg o_img;               // hi/lo operand image of h for the next layer's input projection (when write_img):
-                               //   plane dir*13 + kg, row CB_IMG_GUARD + t*Bp + b
+                               //   plane dir*13 + kg, row row0 + t*Bp + b
     int write_f32, write_img;
     int passes;
 };
@@ -123,7 +123,7 @@ __device__ __forceinline__ void gate_loop(const LstmTcParams& q, uint8_t* h_hi, 
         const int t = frame_of(s);
         const int t_next = s + 1 < q.T ? frame_of(s + 1) : t;
         float* out_t = out_b + (size_t)t * (2 * H) * Bp;
-        const size_t img_row = (size_t)CB_IMG_GUARD + (size_t)t * Bp + b;
+        const size_t img_row = (size_t)q.o_img.row0 + (size_t)t * Bp + b;
         mbar_wait(acc_ready, s & 1);
         tc_fence_after();
         float hlow[4] = {0.f, 0.f, 0.f, 0.f};       // h of the even half-group, carried to the odd one (same K-group)

@@ -4,15 +4,15 @@
 //
 //   * operands are fp16 hi/lo splits (a = hi + lo, |lo| <= 2^-11 |a|): D = Ah*Wh + Ah*Wl + Al*Wh, three
 //     tcgen05.mma.kind::f16 per K-step with fp32 accumulation in TMEM.  CB_PREC_TC_FAST issues only Ah*Wh.
-//   * activations travel between layers as operand images (cb_tc_common.cuh): the epilogue of the producing kernel
-//     writes the hi/lo k-group planes, so the A side of a pipeline stage is 8 cp.async.bulk copies of 2 KB (a conv tap
-//     is the same plane shifted by one row; the appended 1x1 branch input is a second image).  Only the first conv2b
-//     (block-1 conv2a is a rank-1 function of the raw signal, cnn.py:254) still uses SIMT producer warps, which
-//     generate relu((x*w)*inv+shift) on the fly, split it and store the core-matrix image.
-//   * persistent CTAs (one per SM), warp-specialised: 4 epilogue warps (TMEM -> scale/shift/residual/ReLU -> fp32 or
-//     hi/lo image), 1 MMA-issuing thread, 1 loader thread (weight images + activation images, mbarrier expect-tx),
-//     8 producer warps (generator mode only); smem full/empty ring (STAGES deep) and a double-buffered TMEM accumulator
-//     so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   * activations travel between layers as time-major operand images (cb_tc_common.cuh): the epilogue of the producing
+//     kernel writes the hi/lo k-group planes, so the A side of a pipeline stage is 8 cp.async.bulk copies of 2 KB (a conv
+//     tap is the same plane shifted by one frame = Bp rows; a strided conv multiplies the frame index; the appended 1x1
+//     branch input is a second image).  Block-1 conv2a (a rank-1 function of the raw signal, cnn.py:254) is written as an
+//     image by gen_conv2a_kernel.
+//   * persistent CTAs (one per SM), warp-specialised: 8 epilogue warps (TMEM -> scale/shift/residual/ReLU -> hi/lo
+//     image or fp32), 1 MMA-issuing thread, 1 loader thread (weight + activation images, mbarrier expect-tx); smem
+//     full/empty ring (STAGES deep) and a double-buffered TMEM accumulator so the epilogue of tile i overlaps the MMAs
+//     of tile i+1.
 #include <math.h>
 #include <string.h>
 
@@ -23,12 +23,11 @@
 
 namespace {
 
-constexpr int BM = 128;          // rows (frames) per tile = UMMA M
+constexpr int BM = 128;          // rows (windows of one frame) per tile = UMMA M
 constexpr int BK = 32;           // K elements per pipeline stage (2 UMMA K-steps of 16)
 constexpr int STAGES = 4;
-constexpr int N_PROD_WARPS = 8;  // A-operand producers (generator mode)
-constexpr int N_EPI_WARPS = 4;   // one per TMEM lane quadrant
-constexpr int NTHREADS = (N_EPI_WARPS + 2 + N_PROD_WARPS) * 32;   // 448
+constexpr int N_EPI_WARPS = 8;   // two per TMEM lane quadrant (each takes half of the tile's columns)
+constexpr int NTHREADS = (N_EPI_WARPS + 2) * 32;   // 320
 
 struct TcLayer {                 // one prepared weight image
     __half* img;                 // [n_tiles][k_chunks][2 (hi,lo)][4 k-groups][BN rows][8]
@@ -52,34 +51,10 @@ struct TcParams {
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-// fp32 x4 -> fp16 hi x4 (packed in uint2) and fp16 lo x4
-__device__ __forceinline__ void split4(const float4& a, uint2& hi, uint2& lo, bool& overflow) {
-    const __half2 h01 = __floats2half2_rn(a.x, a.y), h23 = __floats2half2_rn(a.z, a.w);
-    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-    const __half2 l01 = __floats2half2_rn(a.x - f01.x, a.y - f01.y), l23 = __floats2half2_rn(a.z - f23.x, a.w - f23.y);
-    hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
-    lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
-    overflow |= !(fabsf(a.x) <= 65504.f && fabsf(a.y) <= 65504.f && fabsf(a.z) <= 65504.f && fabsf(a.w) <= 65504.f);
-}
-
-// Row m of the kernel's row space -> (window b, output frame to); false for padding rows.
-__device__ __forceinline__ bool decode_row(const TcGemm& g, long long m, int& b, int& to) {
-    if (m >= g.M) return false;
-    if (g.row_mode == 0) { b = (int)(m / g.t_out); to = (int)(m - (long long)b * g.t_out); return true; }
-    if (g.row_mode == 1) {                       // every window carries one zero row before and after its frames
-        const int W = g.t_out + 2;
-        b = (int)(m / W); to = (int)(m - (long long)b * W) - 1;
-        return to >= 0 && to < g.t_out && b < g.B;
-    }
-    to = (int)(m / g.Bp); b = (int)(m - (long long)to * g.Bp);     // time-major: m = t*Bp + b
-    return b < g.B;
-}
-
 // shared memory: STAGES x { A_hi[4][128][8], A_lo, B_hi[4][BN][8], B_lo } halfs, then the barriers.
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams q) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const TcGemm& g = q.g;
-    const GemmProblem& p = g.p;
     const int BN = q.BN;
     constexpr uint32_t a_bytes = BM * BK * 2;             // one of hi / lo
     const uint32_t b_bytes = (uint32_t)BN * BK * 2;
@@ -93,10 +68,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams q) 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = q.m_tiles * q.n_tiles;
+    const int tiles_per_frame = g.Bp / BM;
 
     if (threadIdx.x == 0) {
-        const uint32_t full_count = g.a_mode == 1 ? 1 : N_PROD_WARPS * 32 + 1;
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], full_count); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], N_EPI_WARPS * 32); }
         fence_barrier_init();
     }
@@ -111,6 +86,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams q) 
 
     if (warp < N_EPI_WARPS) {
         // ============================ epilogue: TMEM -> registers -> scale/shift/residual/ReLU -> HBM =====================
+        const int quad = warp & 3, chalf = warp >> 2;     // TMEM lane quadrant, which half of the tile's columns
+        const int first = ((BN / 16 + 1) / 2) * 16;       // BN is a multiple of 16; the two column halves are 16-col aligned
+        const int cbeg = chalf ? first : 0, cend = chalf ? BN : first;
         uint32_t it = 0;
         bool overflow = false;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -118,14 +96,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams q) 
             const uint32_t buf = it & 1, par = (it >> 1) & 1;
             mbar_wait(&acc_full[buf], par);
             tc_fence_after();
-            const long long m = (long long)mt * BM + warp * 32 + lane;
-            int b = 0, to = 0;
-            const bool row_ok = decode_row(g, m, b, to);
+            const int to = mt / tiles_per_frame;
+            const int b = (mt - to * tiles_per_frame) * BM + quad * 32 + lane;
+            const bool row_ok = b < g.B;
             float xr = 0.f;
-            if (p.res && row_ok) xr = __ldg(p.x + (long long)b * p.t_inr + (long long)to * p.strider);
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * (uint32_t)BN;
-            const long long orow = g.o_tmajor ? (long long)to * g.Bp + b : m;
-            for (int c0 = 0; c0 < BN; c0 += 16) {
+            if (g.res && row_ok) xr = __ldg(g.xT + (size_t)to * g.res_stride * g.Bp + b);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (uint32_t)BN;
+            const size_t orow = (size_t)g.o.row0 + (size_t)to * g.Bp + b;
+            for (int c0 = cbeg; c0 < cend; c0 += 16) {
                 uint32_t v[16];
                 tmem_ld16(taddr + c0, v);
                 tmem_ld_wait();
@@ -135,20 +113,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams q) 
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
                     const int n = n0 + q4 * 4;
-                    const float4 sh = ldg4(p.shift + n);
+                    const float4 sh = ldg4(g.shift + n);
                     o[q4 * 4 + 0] = fmaf(__uint_as_float(v[q4 * 4 + 0]), q.out_scale, sh.x);
                     o[q4 * 4 + 1] = fmaf(__uint_as_float(v[q4 * 4 + 1]), q.out_scale, sh.y);
                     o[q4 * 4 + 2] = fmaf(__uint_as_float(v[q4 * 4 + 2]), q.out_scale, sh.z);
                     o[q4 * 4 + 3] = fmaf(__uint_as_float(v[q4 * 4 + 3]), q.out_scale, sh.w);
-                    if (p.res) {
-                        const float4 w = ldg4(p.rw + n), iv = ldg4(p.rinv + n), rs = ldg4(p.rsh + n);
+                    if (g.res) {
+                        const float4 w = ldg4(g.rw + n), iv = ldg4(g.rinv + n), rs = ldg4(g.rsh + n);
                         o[q4 * 4 + 0] += fmaf(xr * w.x, iv.x, rs.x);
                         o[q4 * 4 + 1] += fmaf(xr * w.y, iv.y, rs.y);
                         o[q4 * 4 + 2] += fmaf(xr * w.z, iv.z, rs.z);
                         o[q4 * 4 + 3] += fmaf(xr * w.w, iv.w, rs.w);
                     }
                 }
-                if (p.relu) {
+                if (g.relu) {
 #pragma unroll
                     for (int e = 0; e < 16; ++e) o[e] = fmaxf(o[e], 0.f);
                 }
@@ -163,19 +141,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams q) 
                         }
                         uint4 hi, lo;
                         split8(v8, hi, lo);
-                        const size_t off = ((size_t)(g.o_plane0 + (n0 >> 3) + h8) * g.o.plane_rows + CB_IMG_GUARD + orow) * 8;
+                        const size_t off = ((size_t)(g.o_plane0 + (n0 >> 3) + h8) * g.o.plane_rows + orow) * 8;
                         *reinterpret_cast<uint4*>(g.o.hi + off) = hi;
                         *reinterpret_cast<uint4*>(g.o.lo + off) = lo;
                     }
-                } else if (g.out_mode == 1) {             // fp32, time-major [t][ldo][Bp]: coalesced over the warp's rows
-                    float* dst = p.out + ((size_t)to * p.ldo + n0) * (size_t)g.Bp + b;
+                } else {                                  // fp32, time-major [t][ldo][Bp]: coalesced over the warp's rows
+                    float* dst = g.out + ((size_t)to * g.ldo + n0) * (size_t)g.Bp + b;
 #pragma unroll
                     for (int e = 0; e < 16; ++e) dst[(size_t)e * g.Bp] = o[e];
-                } else {                                  // fp32 row-major
-                    float* dst = p.out + m * p.ldo + n0;
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4)
-                        *reinterpret_cast<float4*>(dst + q4 * 4) = make_float4(o[q4 * 4], o[q4 * 4 + 1], o[q4 * 4 + 2], o[q4 * 4 + 3]);
                 }
             }
             tc_fence_before();
@@ -217,107 +190,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams q) 
                 umma_commit(&acc_full[buf]);
             }
         }
-    } else if (warp == N_EPI_WARPS + 1) {
-        // ============================ loader: weight images (+ activation images) via cp.async.bulk ==========================
+    } else {
+        // ============================ loader: weight + activation images via cp.async.bulk ===================================
         if (lane == 0) {
             uint32_t kit = 0;
-            const int n0c = g.taps * g.a0_chunks_per_tap;     // k-chunks served by image 0
+            const int n0c = g.taps * g.a0_chunks_per_tap;     // k-chunks served by image a0
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int mt = tile / q.n_tiles, nt = tile - mt * q.n_tiles;
+                const int to = mt / tiles_per_frame;
+                const long long b0 = (long long)(mt - to * tiles_per_frame) * BM;
                 const __half* wsrc = q.img + (size_t)nt * q.k_chunks * (2 * (size_t)BN * BK);
-                const long long r0 = (long long)mt * BM + CB_IMG_GUARD;
                 for (int kc = 0; kc < q.k_chunks; ++kc, ++kit) {
                     const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* st = smem + (size_t)s * stage_bytes;
-                    if (g.a_mode == 1) {
-                        mbar_arrive_expect_tx(&full_bar[s], 2 * a_bytes + 2 * b_bytes);
-                        const __half *hi, *lo; long long row; int plane;
-                        if (kc < n0c) {
-                            const int j = kc / g.a0_chunks_per_tap, cc = kc - j * g.a0_chunks_per_tap;
-                            hi = g.a0.hi; lo = g.a0.lo; row = r0 + j - g.left; plane = g.a0_plane0 + cc * 4;
-                            hi += ((size_t)plane * g.a0.plane_rows + row) * 8; lo += ((size_t)plane * g.a0.plane_rows + row) * 8;
-#pragma unroll
-                            for (int kg = 0; kg < 4; ++kg) {
-                                bulk_g2s(st + kg * (BM * 16), hi + (size_t)kg * g.a0.plane_rows * 8, BM * 16, &full_bar[s]);
-                                bulk_g2s(st + a_bytes + kg * (BM * 16), lo + (size_t)kg * g.a0.plane_rows * 8, BM * 16, &full_bar[s]);
-                            }
-                        } else {
-                            const int cc = kc - n0c;
-                            plane = g.a1_plane0 + cc * 4;
-                            hi = g.a1.hi + ((size_t)plane * g.a1.plane_rows + r0) * 8;
-                            lo = g.a1.lo + ((size_t)plane * g.a1.plane_rows + r0) * 8;
-#pragma unroll
-                            for (int kg = 0; kg < 4; ++kg) {
-                                bulk_g2s(st + kg * (BM * 16), hi + (size_t)kg * g.a1.plane_rows * 8, BM * 16, &full_bar[s]);
-                                bulk_g2s(st + a_bytes + kg * (BM * 16), lo + (size_t)kg * g.a1.plane_rows * 8, BM * 16, &full_bar[s]);
-                            }
-                        }
+                    mbar_arrive_expect_tx(&full_bar[s], 2 * a_bytes + 2 * b_bytes);
+                    const __half *hi, *lo;
+                    size_t plane_stride;
+                    if (kc < n0c) {
+                        const int j = kc / g.a0_chunks_per_tap, cc = kc - j * g.a0_chunks_per_tap;
+                        const long long row = g.a0.row0 + ((long long)to * g.stride + j - g.left) * g.Bp + b0;
+                        const size_t off = ((size_t)(g.a0_plane0 + cc * 4) * g.a0.plane_rows + row) * 8;
+                        hi = g.a0.hi + off; lo = g.a0.lo + off; plane_stride = (size_t)g.a0.plane_rows * 8;
                     } else {
-                        mbar_arrive_expect_tx(&full_bar[s], 2 * b_bytes);
+                        const long long row = g.a1.row0 + (long long)to * g.Bp + b0;
+                        const size_t off = ((size_t)(g.a1_plane0 + (kc - n0c) * 4) * g.a1.plane_rows + row) * 8;
+                        hi = g.a1.hi + off; lo = g.a1.lo + off; plane_stride = (size_t)g.a1.plane_rows * 8;
+                    }
+#pragma unroll
+                    for (int kg = 0; kg < 4; ++kg) {
+                        bulk_g2s(st + kg * (BM * 16), hi + kg * plane_stride, BM * 16, &full_bar[s]);
+                        bulk_g2s(st + a_bytes + kg * (BM * 16), lo + kg * plane_stride, BM * 16, &full_bar[s]);
                     }
                     bulk_g2s(st + 2 * a_bytes, wsrc + (size_t)kc * (2 * (size_t)BN * BK), 2 * b_bytes, &full_bar[s]);
                 }
             }
         }
-    } else if (g.a_mode == 0) {
-        // ============================ A producers (generator / gather mode) ==================================================
-        const int pt = threadIdx.x - (N_EPI_WARPS + 2) * 32;      // 0..255
-        const int r = pt & 127, hsel = pt >> 7;                   // row of the tile, which 16-wide half of the 32-wide chunk
-        const int K0 = p.taps * p.c0;
-        bool overflow = false;
-        uint32_t kit = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int mt = tile / q.n_tiles;
-            const long long m = (long long)mt * BM + r;
-            int b = 0, to = 0;
-            const bool row_ok = decode_row(g, m, b, to);
-            const long long f0 = (long long)b * p.t_in0;
-            const int tbase = to * p.stride0 - p.left;
-            for (int kc = 0; kc < q.k_chunks; ++kc, ++kit) {
-                const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
-                float4 a[4];
-                const int kk = kc * BK + hsel * 16;
-#pragma unroll
-                for (int gq = 0; gq < 4; ++gq) {
-                    const int kq = kk + gq * 4;
-                    a[gq] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (!row_ok || kq >= p.K) continue;
-                    if (kq < K0) {
-                        const int j = kq / p.c0, c = kq - j * p.c0;
-                        const int ti = tbase + j;
-                        if (ti < 0 || ti >= p.t_in0) continue;
-                        if (p.gen) {
-                            const float xv = __ldg(p.x + f0 + ti);
-                            const float4 w = ldg4(p.gw + c), iv = ldg4(p.ginv + c), sh = ldg4(p.gsh + c);
-                            a[gq].x = fmaxf(fmaf(xv * w.x, iv.x, sh.x), 0.f);
-                            a[gq].y = fmaxf(fmaf(xv * w.y, iv.y, sh.y), 0.f);
-                            a[gq].z = fmaxf(fmaf(xv * w.z, iv.z, sh.z), 0.f);
-                            a[gq].w = fmaxf(fmaf(xv * w.w, iv.w, sh.w), 0.f);
-                        } else {
-                            a[gq] = ldg4(p.src0 + (f0 + ti) * p.lda0 + c);
-                        }
-                    } else {
-                        a[gq] = ldg4(p.src1 + ((long long)b * p.t_in1 + (long long)to * p.stride1) * p.lda1 + (kq - K0));
-                    }
-                }
-                uint2 hi[4], lo[4];
-#pragma unroll
-                for (int gq = 0; gq < 4; ++gq) split4(a[gq], hi[gq], lo[gq], overflow);
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                uint8_t* st = smem + (size_t)s * stage_bytes;
-                // k-group (8 halfs = 16 B) index within the stage: hsel*2 + {0,1}; row r at +r*16
-                uint4* ah = reinterpret_cast<uint4*>(st + (size_t)(hsel * 2) * (BM * 16) + r * 16);
-                uint4* al = reinterpret_cast<uint4*>(st + a_bytes + (size_t)(hsel * 2) * (BM * 16) + r * 16);
-                ah[0] = make_uint4(hi[0].x, hi[0].y, hi[1].x, hi[1].y);
-                ah[BM] = make_uint4(hi[2].x, hi[2].y, hi[3].x, hi[3].y);          // next k-group: + BM*16 bytes
-                al[0] = make_uint4(lo[0].x, lo[0].y, lo[1].x, lo[1].y);
-                al[BM] = make_uint4(lo[2].x, lo[2].y, lo[3].x, lo[3].y);
-                fence_proxy_async();                           // generic-proxy stores -> visible to the tensor core
-                mbar_arrive(&full_bar[s]);
-            }
-        }
-        if (overflow) atomicExch(q.range_flag, 1);
     }
 
     tc_fence_before();
@@ -328,10 +236,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams q) 
     }
 }
 
+// x[B][L] -> xT[L][Bp]  (so that everything downstream reads the raw signal coalesced over windows)
+__global__ void __launch_bounds__(256) transpose_x_kernel(const float* __restrict__ x, int B, int L, int Bp,
+                                                          float* __restrict__ xT) {
+    __shared__ float tile[32][33];
+    const int b0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int b = b0 + i, f = f0 + threadIdx.x;
+        tile[i][threadIdx.x] = (b < B && f < L) ? x[(size_t)b * L + f] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int f = f0 + i, b = b0 + threadIdx.x;
+        if (f < L && b < Bp) xT[(size_t)f * Bp + b] = tile[threadIdx.x][i];
+    }
+}
+
+// Block-1 conv2a (cnn.py:254, C_in = 1): a = relu((x*w[c])*inv[c] + shift[c]) written straight into an operand image.
+// One thread per (frame, window, k-group); consecutive threads = consecutive windows (16-byte coalesced stores).
+__global__ void __launch_bounds__(256) gen_conv2a_kernel(const float* __restrict__ xT, int B, int Bp, int L, int planes,
+                                                         const float* __restrict__ gw, const float* __restrict__ ginv,
+                                                         const float* __restrict__ gsh, CbImg o) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;
+    if (b >= B) return;
+    const float xv = __ldg(xT + (size_t)f * Bp + b);
+    for (int kg = 0; kg < planes; ++kg) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = kg * 8 + e;
+            v[e] = fmaxf(fmaf(xv * __ldg(gw + c), __ldg(ginv + c), __ldg(gsh + c)), 0.f);
+        }
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        const size_t off = ((size_t)kg * o.plane_rows + o.row0 + (size_t)f * Bp + b) * 8;
+        *reinterpret_cast<uint4*>(o.hi + off) = hi;
+        *reinterpret_cast<uint4*>(o.lo + off) = lo;
+    }
+}
+
 size_t smem_bytes_for(int BN) { return (size_t)STAGES * (2 * BM * BK * 2 + 2 * (size_t)BN * BK * 2) + 256; }
 
-int pick_bn(int N) {
-    if (N % 256 == 0) return 256;
+int pick_bn(int N) {            // widest tile <= 256 that divides N (UMMA N must be a multiple of 16 at M = 128)
     for (int bn = 256; bn >= 16; bn -= 16)
         if (N % bn == 0) return bn;
     return 0;
@@ -457,28 +404,38 @@ int cb_launch_gemm_tc(cb_handle* h, const TcGemm& g, cudaStream_t s) {
         cb_set_error("tensor-core path: no weight image for layer %d", g.layer_id);
         return CB_ERR_ARG;
     }
-    if (g.M <= 0) return CB_OK;
+    if (g.T <= 0 || g.B <= 0) return CB_OK;
     const TcLayer& L = st->layers[g.layer_id];
-    if (L.N != g.p.N) { cb_set_error("tensor-core path: layer %d N mismatch", g.layer_id); return CB_ERR_ARG; }
-    if (g.a_mode == 1) {
-        if (g.taps * g.a0_chunks_per_tap + g.a1_chunks != L.k_chunks) {
-            cb_set_error("tensor-core path: layer %d K mismatch (%d chunks vs %d)", g.layer_id,
-                         g.taps * g.a0_chunks_per_tap + g.a1_chunks, L.k_chunks);
-            return CB_ERR_ARG;
-        }
-    } else if (L.K != g.p.K || (g.p.c0 & 3) || (g.p.c1 & 3) || (g.p.lda0 & 3) || (g.p.lda1 & 3)) {
-        cb_set_error("tensor-core path: layer %d gather shape mismatch", g.layer_id);
+    if (L.N != g.N) { cb_set_error("tensor-core path: layer %d N mismatch", g.layer_id); return CB_ERR_ARG; }
+    if (g.taps * g.a0_chunks_per_tap + g.a1_chunks != L.k_chunks) {
+        cb_set_error("tensor-core path: layer %d K mismatch (%d chunks vs %d)", g.layer_id,
+                     g.taps * g.a0_chunks_per_tap + g.a1_chunks, L.k_chunks);
         return CB_ERR_ARG;
     }
-    if ((g.row_mode == 2 || g.o_tmajor) && g.Bp % BM) { cb_set_error("tensor-core path: padded batch must be a multiple of 128"); return CB_ERR_ARG; }
+    if (g.Bp % BM) { cb_set_error("tensor-core path: padded batch must be a multiple of 128"); return CB_ERR_ARG; }
     TcParams q;
     q.g = g; q.img = L.img; q.BN = L.BN; q.n_tiles = L.n_tiles; q.k_chunks = L.k_chunks;
-    q.m_tiles = (int)(((long long)g.M + BM - 1) / BM); q.out_scale = L.out_scale;
+    q.m_tiles = g.T * (g.Bp / BM); q.out_scale = L.out_scale;
     q.passes = h->precision == CB_PREC_TC_FAST ? 1 : 3;
     q.range_flag = st->d_range_flag;
     const long long tiles = (long long)q.m_tiles * q.n_tiles;
     const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
     gemm_tc_kernel<<<grid, NTHREADS, smem_bytes_for(L.BN), s>>>(q);
+    CB_CHECK_LAUNCH();
+    h->launches++;
+    return CB_OK;
+}
+
+int cb_launch_transpose_x(cb_handle* h, const float* x, int B, int L, int Bp, float* xT, cudaStream_t s) {
+    transpose_x_kernel<<<dim3((Bp + 31) / 32, (L + 31) / 32), dim3(32, 8), 0, s>>>(x, B, L, Bp, xT);
+    CB_CHECK_LAUNCH();
+    h->launches++;
+    return CB_OK;
+}
+
+int cb_launch_gen_conv2a(cb_handle* h, const float* xT, int B, int Bp, int L, const CbImg& o, cudaStream_t s) {
+    if (L > 65535) { cb_set_error("segment_len too large for the generator grid"); return CB_ERR_ARG; }
+    gen_conv2a_kernel<<<dim3((B + 255) / 256, L), 256, 0, s>>>(xT, B, Bp, L, h->cfg.channels / 8, h->g_w, h->g_inv, h->g_sh, o);
     CB_CHECK_LAUNCH();
     h->launches++;
     return CB_OK;

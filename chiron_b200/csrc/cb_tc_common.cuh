@@ -5,15 +5,17 @@
 
 // ---- activation operand images ---------------------------------------------------------------------------------------
 // In tensor-core mode activations travel between kernels as fp16 hi/lo splits (a = hi + lo) laid out as "k-group
-// planes": plane kg holds channels [8kg, 8kg+8) of every row as one 16-byte unit, rows consecutive.  A tile of 128
-// consecutive rows of one plane is therefore 2 KB of contiguous memory that is ALREADY a UMMA K-major no-swizzle
-// core-matrix column (row r at +16r bytes), so a pipeline stage is filled with plain cp.async.bulk copies, and a conv
-// tap is the same plane shifted by one row.  CB_IMG_GUARD zero rows in front absorb the -1 row of the first tile.
-#define CB_IMG_GUARD 8
+// planes": plane kg holds channels [8kg, 8kg+8) of every row as one 16-byte unit.  Rows are TIME-MAJOR with the batch
+// innermost: frame f of window b is row row0 + f*Bp + b (Bp = batch rounded up to 128).  A tile of 128 consecutive
+// windows of one frame of one plane is therefore 2 KB of contiguous memory that is ALREADY a UMMA K-major no-swizzle
+// core-matrix column (row r at +16r bytes): a pipeline stage is filled with plain cp.async.bulk copies, a conv tap is
+// the same plane shifted by Bp rows (whole zero frames in front of / behind the data give the 'SAME' padding), and a
+// strided conv just multiplies the frame index.
 struct CbImg {
     __half* hi;
     __half* lo;
-    long long plane_rows;      // rows per plane, guards included
+    long long plane_rows;      // rows per plane (zero padding frames included)
+    long long row0;            // row of frame 0, window 0
     int planes;
 };
 __host__ __device__ inline size_t cb_img_halfs(long long plane_rows, int planes) { return (size_t)plane_rows * planes * 8; }
