@@ -159,8 +159,8 @@ int cb_forward_tc(cb_handle* h, const float* x, const int32_t* seq_len_out, int 
             else if (n_gemm == 1) { g.a0 = w->himg; g.a0_chunks_per_tap = 7; }                 // K' = 208 -> 7 chunks
             else { g.a0 = w->himg; g.a0_plane0 = d * 13; g.a0_chunks_per_tap = 4; }            // K' = 104 -> 4 chunks
             g.N = n_gemm == 1 ? 8 * H : 4 * H;
-            g.shift = n_gemm == 1 ? h->bcat[l] : h->bias[l][d];
-            g.out_mode = 1; g.out = w->pre + (size_t)d * 4 * H * Bp; g.ldo = 8 * H;
+            g.shift = cb_tc_lstm_bias(h, l, d);                    // gate columns in unit-major order
+            g.out_mode = 1; g.out = w->pre + (size_t)d * 4 * H * Bp; g.ldo = 8 * H;    // pre[T][8H/16][Bp][16]
             if ((rc = timed_gemm(h, g, s, CB_CAT_LSTM_IN)) != CB_OK) return rc;
         }
         LstmProblem lp;
@@ -219,7 +219,10 @@ long long cb_debug_fetch_tc(cb_handle* h, int what, float* dst, size_t max_float
         CB_CUDA(cudaMemcpy(tmp.data(), w->out, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
         for (size_t b = 0; b < B; ++b)
             for (size_t t = 0; t < T; ++t)
-                for (size_t u = 0; u < 2 * H; ++u) dst[(b * T + t) * 2 * H + u] = tmp[(t * 2 * H + u) * Bp + b];
+                for (size_t u = 0; u < 2 * H; ++u) {               // out[T][2*25][Bp][4]
+                    const size_t d = u / H, uu = u % H;
+                    dst[(b * T + t) * 2 * H + u] = tmp[(((t * 2 + d) * (H / 4) + uu / 4) * Bp + b) * 4 + (uu & 3)];
+                }
         return (long long)(B * T * 2 * H);
     }
     if (what == h->cfg.n_layers - 1 && what >= 1) {

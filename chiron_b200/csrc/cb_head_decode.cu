@@ -44,8 +44,8 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ las
     }
 }
 
-// Time-major variant for the tensor-core LSTM stack: lasth is [T][2H][Bp]; one thread per frame, consecutive threads =
-// consecutive batch rows, so every load is a 128-byte coalesced row segment.
+// Time-major variant for the tensor-core LSTM stack: lasth is [T][2 x H/4][Bp][4]; one thread per frame, consecutive
+// threads = consecutive batch rows, so every load is a 128-bit piece of a 512-byte coalesced segment.
 __global__ void __launch_bounds__(128) head_tmajor_kernel(const float* __restrict__ lasth, int B, int Bp, int T, int H,
                                                           int C, const float* __restrict__ w,
                                                           const float* __restrict__ bias, const float* __restrict__ wc,
@@ -53,15 +53,22 @@ __global__ void __launch_bounds__(128) head_tmajor_kernel(const float* __restric
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int t = blockIdx.y;
     if (b >= B) return;
-    const float* src = lasth + (size_t)t * 2 * H * Bp + b;
+    const int H4 = H / 4;
+    const float4* src = reinterpret_cast<const float4*>(lasth) + (size_t)t * 2 * H4 * Bp + b;
     float acc[MAX_CLASS];
 #pragma unroll
     for (int c = 0; c < MAX_CLASS; ++c) acc[c] = 0.f;
-    for (int u = 0; u < H; ++u) {
-        const float h2 = (src[(size_t)u * Bp] * __ldg(w + u) + src[(size_t)(H + u) * Bp] * __ldg(w + H + u)) + __ldg(bias + u);
+    for (int g = 0; g < H4; ++g) {
+        const float4 f = src[(size_t)g * Bp], r = src[(size_t)(H4 + g) * Bp];
+        const float fw[4] = {f.x, f.y, f.z, f.w}, bw[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-        for (int c = 0; c < MAX_CLASS; ++c)
-            if (c < C) acc[c] = fmaf(h2, __ldg(wc + u * C + c), acc[c]);
+        for (int e = 0; e < 4; ++e) {
+            const int u = g * 4 + e;
+            const float h2 = (fw[e] * __ldg(w + u) + bw[e] * __ldg(w + H + u)) + __ldg(bias + u);
+#pragma unroll
+            for (int c = 0; c < MAX_CLASS; ++c)
+                if (c < C) acc[c] = fmaf(h2, __ldg(wc + u * C + c), acc[c]);
+        }
     }
     float* dst = logits + ((size_t)b * T + t) * C;
 #pragma unroll

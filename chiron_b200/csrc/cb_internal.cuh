@@ -135,6 +135,7 @@ struct cb_handle {
 int cb_launch_gemm_simt(cb_handle* h, const GemmProblem& p, cudaStream_t s);
 int cb_launch_lstm_simt(cb_handle* h, const LstmProblem& p, cudaStream_t s);
 int cb_launch_gemm_tc(cb_handle* h, const TcGemm& g, cudaStream_t s);
+const float* cb_tc_lstm_bias(cb_handle* h, int layer, int d);   // biases in unit-major gate-column order
 int cb_launch_transpose_x(cb_handle* h, const float* x, int B, int L, int Bp, float* xT, cudaStream_t s);
 int cb_launch_gen_conv2a(cb_handle* h, const float* xT, int B, int Bp, int L, const CbImg& o, cudaStream_t s);
 int cb_launch_lstm_tc(cb_handle* h, const LstmProblem& p, const CbImg* o_img, int write_f32, cudaStream_t s);

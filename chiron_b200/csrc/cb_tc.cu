@@ -38,6 +38,8 @@ struct TcLayer {                 // one prepared weight image
 struct TcState {
     std::vector<TcLayer> layers; // indexed by layer id
     int* d_range_flag;
+    float* d_lstm_bias;          // LSTM biases in the unit-major gate-column order of the recurrence kernel
+    size_t lstm_bias_off[CB_MAX_LAYERS][2];
 };
 
 struct TcParams {
@@ -145,10 +147,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams q) 
                         *reinterpret_cast<uint4*>(g.o.hi + off) = hi;
                         *reinterpret_cast<uint4*>(g.o.lo + off) = lo;
                     }
-                } else {                                  // fp32, time-major [t][ldo][Bp]: coalesced over the warp's rows
-                    float* dst = g.out + ((size_t)to * g.ldo + n0) * (size_t)g.Bp + b;
+                } else {                                  // fp32 [to][n/16][Bp][16]: 64 contiguous bytes per row, 2 KB per warp
+                    float4* dst = reinterpret_cast<float4*>(g.out) + (((size_t)to * (g.ldo >> 4) + (n0 >> 4)) * g.Bp + b) * 4;
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) dst[(size_t)e * g.Bp] = o[e];
+                    for (int q4 = 0; q4 < 4; ++q4) dst[q4] = make_float4(o[q4 * 4], o[q4 * 4 + 1], o[q4 * 4 + 2], o[q4 * 4 + 3]);
                 }
             }
             tc_fence_before();
@@ -329,6 +331,7 @@ int cb_tc_build_layer(cb_handle* h, int layer_id, const float* W, int K, int N) 
 int cb_tc_prepare(cb_handle* h, const float* hw) {
     TcState* st = new TcState();
     st->d_range_flag = nullptr;
+    st->d_lstm_bias = nullptr;
     h->tc = st;
     const CbConfig& c = h->cfg;
     const int C = c.channels, H = c.hidden;
@@ -347,25 +350,43 @@ int cb_tc_prepare(cb_handle* h, const float* hw) {
     }
     // LSTM input projections.  Layer 0 reads the CNN feature image (K = C).  Later layers read the h image written by
     // the recurrence, whose planes are [fw: 13 k-groups (104 ch, 100 real)][bw: 13 k-groups]: K' = 208 with zero rows.
+    // Output (gate) columns are permuted to the unit-major order of the recurrence kernel:
+    //   TF column gate*H + u  ->  (u/4)*16 + gate*4 + u%4   (per direction)
     const int HP = (H + 7) / 8 * 8;                         // 104
+    auto perm = [H](int n) { const int gate = n / H, u = n % H; return (u / 4) * 16 + gate * 4 + (u & 3); };
+    // the recurrence evaluates sigmoid/tanh through ex2: -log2(e) is folded into the i/f/o columns and -2*log2(e) into
+    // the j columns of W_ih (here), W_hh (cb_lstm_tc.cu) and the bias, so the gate sums feed ex2 directly
+    auto gate_scale = [H](int n) { return n / H == 1 ? -2.f * 1.4426950408889634f : -1.4426950408889634f; };
+    std::vector<float> bias_all;
     for (int l = 0; l < c.n_layers; ++l) {
-        if (l == 0) {
-            if ((rc = cb_tc_build_layer(h, 32, host(h->wxcat[0]), C, 8 * H)) != CB_OK) return rc;
-        } else if (c.rnn_layout == 0) {
-            std::vector<float> W((size_t)2 * HP * 8 * H, 0.f);
-            const float* src = host(h->wxcat[l]);               // [2H][8H]
-            for (int d = 0; d < 2; ++d)
-                for (int u = 0; u < H; ++u)
-                    memcpy(&W[(size_t)(d * HP + u) * 8 * H], src + (size_t)(d * H + u) * 8 * H, sizeof(float) * 8 * H);
-            if ((rc = cb_tc_build_layer(h, 32 + l * 2, W.data(), 2 * HP, 8 * H)) != CB_OK) return rc;
-        } else {
-            for (int d = 0; d < 2; ++d) {
-                std::vector<float> W((size_t)HP * 4 * H, 0.f);
-                memcpy(W.data(), host(h->wx[l][d]), sizeof(float) * (size_t)H * 4 * H);
-                if ((rc = cb_tc_build_layer(h, 32 + l * 2 + d, W.data(), HP, 4 * H)) != CB_OK) return rc;
+        const int n_gemm = (l == 0 || c.rnn_layout == 0) ? 1 : 2;
+        for (int d = 0; d < n_gemm; ++d) {
+            const int ndir = n_gemm == 1 ? 2 : 1;           // directions covered by this contraction
+            const int N = ndir * 4 * H;
+            const int Kin = l == 0 ? C : (c.rnn_layout == 0 ? 2 * H : H);
+            const int Kimg = l == 0 ? C : (c.rnn_layout == 0 ? 2 * HP : HP);
+            const float* src = host(n_gemm == 1 ? h->wxcat[l] : h->wx[l][d]);          // [Kin][N]
+            const float* bsrc = host(n_gemm == 1 ? h->bcat[l] : h->bias[l][d]);        // [N]
+            std::vector<float> W((size_t)Kimg * N, 0.f), bperm(N);
+            for (int k = 0; k < Kin; ++k) {
+                const int kk = l == 0 ? k : (k / H) * HP + (k % H);                     // skip the 4 padding channels per direction
+                for (int n = 0; n < N; ++n) {
+                    const int dd = n / (4 * H), nn = n % (4 * H);
+                    W[(size_t)kk * N + dd * 4 * H + perm(nn)] = src[(size_t)k * N + n] * gate_scale(nn);
+                }
             }
+            for (int n = 0; n < N; ++n) {        // forget_bias 1.0 of TF's LSTMCell folded into the bias
+                const int nn = n % (4 * H);
+                bperm[(n / (4 * H)) * 4 * H + perm(nn)] = (bsrc[n] + (nn / H == 2 ? 1.0f : 0.0f)) * gate_scale(nn);
+            }
+            if ((rc = cb_tc_build_layer(h, 32 + l * 2 + d, W.data(), Kimg, N)) != CB_OK) return rc;
+            while (bias_all.size() & 3) bias_all.push_back(0.f);
+            st->lstm_bias_off[l][d] = bias_all.size();
+            bias_all.insert(bias_all.end(), bperm.begin(), bperm.end());
         }
     }
+    CB_CUDA(cudaMalloc(&st->d_lstm_bias, bias_all.size() * sizeof(float)));
+    CB_CUDA(cudaMemcpy(st->d_lstm_bias, bias_all.data(), bias_all.size() * sizeof(float), cudaMemcpyHostToDevice));
     CB_CUDA(cudaMalloc(&st->d_range_flag, sizeof(int)));
     CB_CUDA(cudaMemset(st->d_range_flag, 0, sizeof(int)));
     CB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for(256)));
@@ -378,11 +399,17 @@ void cb_tc_release(cb_handle* h) {
     if (!st) return;
     for (auto& L : st->layers) if (L.img) cudaFree(L.img);
     if (st->d_range_flag) cudaFree(st->d_range_flag);
+    if (st->d_lstm_bias) cudaFree(st->d_lstm_bias);
     delete st;
     h->tc = nullptr;
 }
 
 int* cb_tc_range_flag(cb_handle* h) { return h->tc ? ((TcState*)h->tc)->d_range_flag : nullptr; }
+
+const float* cb_tc_lstm_bias(cb_handle* h, int layer, int d) {
+    TcState* st = (TcState*)h->tc;
+    return st->d_lstm_bias + st->lstm_bias_off[layer][d];
+}
 
 int cb_tc_check_range(cb_handle* h, cudaStream_t s) {
     TcState* st = (TcState*)h->tc;
