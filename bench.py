@@ -153,11 +153,11 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="windows per GPU per step")
-    ap.add_argument("--precision", default=os.environ.get("CHIRON_B200_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("CHIRON_B200_PRECISION", "tc"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
