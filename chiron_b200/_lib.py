@@ -8,7 +8,7 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int8, c_int32, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libchiron_b200.so")
+LIB_PATH = os.environ.get("CHIRON_B200_LIB") or os.path.join(_HERE, "lib", "libchiron_b200.so")   # env override: A/B builds
 
 CB_OK = 0
 PREC_FP32, PREC_TC_SPLIT, PREC_TC_FAST = 0, 1, 2
