@@ -6,19 +6,21 @@
 //   * gate columns are in unit-major order (half-group hg = hidden units 4hg..4hg+3 = 16 consecutive columns
 //     [i0..3 j0..3 f0..3 o0..3]); CTA rank 0 owns half-groups 0-11 (192 columns, units 0-47), rank 1 owns 12-24
 //     (208 columns, units 48-99).  Batch rows are independent: no grid-wide synchronisation.
-//   * each CTA keeps its slice of W_hh resident in shared memory as fp16 hi/lo K-major core-matrix images (<= 86 KB)
-//     and a DOUBLE-BUFFERED copy of the full h operand (2 x 56 KB).  Every step the gate warps write the h K-groups
-//     they produce into their own buffer AND, through distributed shared memory (st.shared::cluster), into the peer
-//     CTA's buffer, then arrive on both CTAs' mbarriers (release/acquire at cluster scope).
+//   * each CTA keeps its slice of W_hh resident in shared memory as fp16 hi/lo K-major core-matrix images (<= 93 KB)
+//     and a DOUBLE-BUFFERED copy of the full h operand (2 x 56 KB).  Every step the gate warps write the h they
+//     produce into the CTA's own buffer and one thread ships the finished K-groups to the peer CTA with
+//     cp.async.bulk shared::cta -> shared::cluster, byte-counted on the peer's mbarrier.
+//   * the fp32 accumulator is DOUBLE-BUFFERED in TMEM by step parity and PRE-LOADED with the hoisted, pre-scaled input
+//     projection: while the tensor core works on step s the gate warps tcgen05.st pre(s+1) into the other buffer, and
+//     the MMAs of step s+1 accumulate h*W_hh on top of it.  The gate math therefore reads finished pre-activations
+//     straight from TMEM -- no global-load latency and no extra registers inside the cell loop.
 //   * per step one thread issues 21 tcgen05.mma (7 K-steps x {h_hi*W_lo, h_lo*W_hi first, then h_hi*W_hi}) per
-//     N-phase into a <= 208-column fp32 TMEM accumulator; the columns are issued in two phases so the gate math of
-//     the first phase overlaps the MMAs of the second.
-//   * 12 gate warps (3 per TMEM lane quadrant, 2 K-groups of 8 units each) read the accumulator with tcgen05.ld.x16,
-//     add the hoisted, pre-scaled input projection (register prefetch one half-group ahead + L2 prefetch two steps
-//     ahead), evaluate the cell with MUFU ex2/rcp (7 per cell), keep c in spare TMEM columns, and write h back as
-//     16-byte core-matrix rows.
+//     column phase; the columns are issued in two phases so the gate math of the first overlaps the MMAs of the second.
+//   * 24 gate warps (6 per TMEM lane quadrant = per SM sub-partition; <= 80 registers each) take one half-group of
+//     each phase (4 cells per thread, evaluated with MUFU ex2/rcp, 7 per cell -- the MUFU pipe is the bound), keep c in
+//     spare TMEM columns, and write h back as 8-byte halves of the 16-byte core-matrix rows.
 // Global layouts are time-major with the batch (almost) innermost -- pre[T][50][Bp][16], out[T][50][Bp][4] -- so that the
-// 32 rows of a warp read and write contiguous, 128-bit vectorised segments at every step.
+// 32 rows of a warp read and write contiguous, vectorised segments at every step.
 #include <cuda_fp16.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -41,12 +43,14 @@ constexpr int KG = 13;             // 16-byte K-groups that hold real data (13*8
 constexpr int KG_A = 14;           // K-groups of the h operand (7 K-steps of 16)
 constexpr int NHG = 25;            // half-groups (4 hidden units = 16 gate columns) per direction
 constexpr int NMAX = 208;          // widest column slice of a CTA
-constexpr int C_COL = 256;         // TMEM columns 256.. hold the cell state c[row][local unit]
-constexpr int GATE_WARPS = 12;
+constexpr int ACC1_COL = 224;      // TMEM: accumulator of even steps at columns [0,208), of odd steps at [224,432)
+constexpr int C_COL = 448;         // TMEM columns 448..499 hold the cell state c[row][local unit]
+constexpr int GATE_WARPS = 24;
+constexpr int SLOTS = GATE_WARPS / 4;   // gate warps per TMEM lane quadrant
 constexpr int NTHREADS = (1 + GATE_WARPS) * 32;
 constexpr uint32_t W_BYTES = KG_A * NMAX * 16;    // one of hi / lo (14th K-group = zeros the K padding multiplies with)
 constexpr uint32_t HS_BYTES = KG_A * RM * 16;     // one of hi / lo of one h buffer: 28,672
-constexpr size_t SMEM_BYTES = 2 * (size_t)W_BYTES + 4 * (size_t)HS_BYTES + 64;
+constexpr size_t SMEM_BYTES = 2 * (size_t)W_BYTES + 4 * (size_t)HS_BYTES + 128;
 
 struct LstmTcParams {
     int B, Bp, T;
@@ -122,142 +126,170 @@ __device__ __forceinline__ void lstm_cell(float yi, float yj, float yf, float yo
     h = active ? hn : 0.f;
 }
 
-// One half-group (4 hidden units, 16 accumulator columns): returns h of its 4 units.
-__device__ __forceinline__ void half_group(uint32_t t_lane, uint32_t t_cell, int hl, bool first_step, bool active,
-                                           const float4 (&pre)[4], float (&hv)[4]) {
-    uint32_t z[16];
-    float c[4];
-    tmem_ld4(t_cell + hl * 4, c);
-    if (!first_step) {
-        tmem_ld16(t_lane + hl * 16, z);
-    } else {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) z[e] = 0u;
-    }
-    tmem_ld_wait();
-    const float pi[4] = {pre[0].x, pre[0].y, pre[0].z, pre[0].w};
-    const float pj[4] = {pre[1].x, pre[1].y, pre[1].z, pre[1].w};
-    const float pf[4] = {pre[2].x, pre[2].y, pre[2].z, pre[2].w};
-    const float po[4] = {pre[3].x, pre[3].y, pre[3].z, pre[3].w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-        lstm_cell(__uint_as_float(z[e]) + pi[e], __uint_as_float(z[4 + e]) + pj[e], __uint_as_float(z[8 + e]) + pf[e],
-                  __uint_as_float(z[12 + e]) + po[e], active, c[e], hv[e]);
-    tmem_st4(t_cell + hl * 4, c[0], c[1], c[2], c[3]);
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float4 (&v)[4]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(__float_as_uint(v[0].x)), "r"(__float_as_uint(v[0].y)), "r"(__float_as_uint(v[0].z)), "r"(__float_as_uint(v[0].w)),
+        "r"(__float_as_uint(v[1].x)), "r"(__float_as_uint(v[1].y)), "r"(__float_as_uint(v[1].z)), "r"(__float_as_uint(v[1].w)),
+        "r"(__float_as_uint(v[2].x)), "r"(__float_as_uint(v[2].y)), "r"(__float_as_uint(v[2].z)), "r"(__float_as_uint(v[2].w)),
+        "r"(__float_as_uint(v[3].x)), "r"(__float_as_uint(v[3].y)), "r"(__float_as_uint(v[3].z)), "r"(__float_as_uint(v[3].w))
+        : "memory");
 }
 
-// Gate loop of one warp: K-groups [kgA0, kgA0+nA) after the first MMA phase, [kgB0, kgB0+nB) after the second.
-// Not unrolled over K-groups on purpose (instruction-cache footprint); c lives in TMEM; the input projection of the
-// next half-group is prefetched into registers while the current one is evaluated.
-__device__ __forceinline__ void gate_loop(const LstmTcParams& q, uint8_t* hbuf, uint64_t* local_done,
-                                          uint64_t* acc_ready, uint32_t tmem_base, int warp, int lane,
-                                          int dir, int b0, int hg_base, int kgA0, int nA, int kgB0, int nB) {
+// 4 fp32 -> the 8-byte half of a core-matrix row of the hi image and of the lo image
+__device__ __forceinline__ void split4(const float (&v)[4], uint2& hi, uint2& lo) {
+    uint32_t ph[2], pl[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const __half2 hh = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+        ph[e] = *reinterpret_cast<const uint32_t*>(&hh);
+        pl[e] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    hi = make_uint2(ph[0], ph[1]);
+    lo = make_uint2(pl[0], pl[1]);
+}
+
+// Gate loop of one warp.  A warp owns up to three half-groups ("items") of its 32 rows: hlA in the first column phase,
+// hlB and (one warp per quadrant of rank 1) hlX in the second; a negative index marks an unused item (warp-uniform).
+// Written for <= 72 registers (25 warps per SM): per-step addresses are rebuilt from 32-bit element indices (every
+// tensor has < 2^32 16-byte elements, checked by the launcher) instead of being carried as 64-bit pointers, and the
+// items are processed one after the other (4 cells of instruction-level parallelism, 6 warps per scheduler).
+__device__ __forceinline__ void gate_loop(const LstmTcParams& q, uint32_t hbuf_s, uint64_t* local_done, uint64_t* acc_ready,
+                                          uint64_t* pre_done, uint32_t tmem_base, int warp, int lane, int dir, int b0,
+                                          int hg_base, int hlA, int hlB, int hlX) {
     const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;
     const int b = b0 + row;
     int len = 0;
     if (b < q.B) { len = q.lens[b]; len = len < 0 ? 0 : (len > q.T ? q.T : len); }
-    const size_t Bp = (size_t)q.Bp;
-    const size_t hg_stride4 = Bp * 4;               // float4 elements between consecutive half-groups of pre
+    const uint32_t Bp = (uint32_t)q.Bp;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const uint32_t t_cell = t_lane + C_COL;
-    const float4* pre_b = reinterpret_cast<const float4*>(q.pre) + ((size_t)dir * NHG * Bp + b) * 4;   // + ((t*50 + hg)*Bp)*4
-    float4* out_b = reinterpret_cast<float4*>(q.out) + (size_t)dir * NHG * Bp + b;                     // + (t*50 + hg)*Bp
-    const size_t t_stride4 = (size_t)(2 * NHG) * Bp * 4;              // float4 elements between frames of pre
-    const int hgA = 2 * kgA0, hgB = 2 * kgB0;
-    const bool tailB = (kgB0 + nB == KG);            // this warp owns K-group 12, whose upper half (units 100..103) is void
+    const uint32_t dhg = (uint32_t)(dir * NHG + hg_base);            // first half-group of this CTA in a frame of pre / out
+    const float4* pre4 = reinterpret_cast<const float4*>(q.pre);     // element ((t*50 + hg)*Bp + b)*4 + e
+    float4* out4 = reinterpret_cast<float4*>(q.out);                 // element (t*50 + hg)*Bp + b
+    auto item_hl = [&](int i) { return i == 0 ? hlA : (i == 1 ? hlB : hlX); };
 
-    for (int k = 0; k < 2 * nA; ++k) tmem_st4(t_cell + (hgA + k - hg_base) * 4, 0.f, 0.f, 0.f, 0.f);
-    for (int k = 0; k < 2 * nB; ++k) tmem_st4(t_cell + (hgB + k - hg_base) * 4, 0.f, 0.f, 0.f, 0.f);
-    tmem_st_wait();
+#pragma unroll 1
+    for (int i = 0; i < 3; ++i)
+        if (item_hl(i) >= 0) tmem_st4(t_lane + C_COL + item_hl(i) * 4, 0.f, 0.f, 0.f, 0.f);
 
     // frame this row works on at step s (inactive rows: frame s, where they write zeros)
     auto frame_of = [&](int s) { return s < len ? (dir ? len - 1 - s : s) : s; };
-    auto load_pre = [&](float4 (&dst)[4], const float4* src) {
+    // The input projection is streamed from HBM exactly once (1.6 KB per row and step): its lines are pulled into L2
+    // four steps ahead (one prefetch instruction per warp and 2 KB); pre(s+2) is requested into registers at the end of
+    // step s -- when the registers of the cell math are dead -- and parked in the other accumulator buffer during the
+    // idle head of step s+1, while the tensor core is busy with that step's recurrent product.
+    // (The seventh half-group of rank 1's second phase, hlX, is not carried in registers -- 72 is all a thread gets -- but
+    // loaded inside park_pre.)
+    float4 pr[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pr[i][e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto load_pre = [&](int s) {
         if (CB_LSTM_DEV && (q.dbg_flags & 1)) return;
+        const uint32_t f50 = (uint32_t)frame_of(s) * (2 * NHG) + dhg;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) dst[e] = __ldg(src + e);
+        for (int i = 0; i < 2; ++i) {
+            const float4* p = pre4 + (size_t)(((f50 + item_hl(i)) * Bp + b) * 4u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pr[i][e] = __ldg(p + e);
+        }
     };
-    // The input projection is streamed from HBM exactly once (1.6 KB per row and step).  Register prefetch alone keeps
-    // too little in flight for ~1 us of DRAM latency, so every half-group also pulls its lines for the step after next
-    // into L2 (one prefetch instruction per warp and 2 KB).
-    auto prefetch_l2 = [&](const float4* src) { if (!(CB_LSTM_DEV && (q.dbg_flags & 4))) asm volatile("prefetch.global.L2 [%0];" ::"l"(src)); };
-
-    float4 pre_e[4], pre_o[4];                       // even / odd half-group of the K-group being processed
+    auto park_pre = [&](int s) {                     // registers -> accumulator buffer of step s
+        const uint32_t t_acc = t_lane + ((s & 1) ? ACC1_COL : 0);
+        if (hlX >= 0 && !(CB_LSTM_DEV && (q.dbg_flags & 1))) {
+            const float4* p = pre4 + (size_t)((((uint32_t)frame_of(s) * (2 * NHG) + dhg + hlX) * Bp + b) * 4u);
+            float4 px[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { pre_e[e] = make_float4(0.f, 0.f, 0.f, 0.f); pre_o[e] = pre_e[e]; }
-    const float4* p_cur = pre_b + (size_t)frame_of(0) * t_stride4;
-    load_pre(pre_e, p_cur + (size_t)hgA * hg_stride4);
-    load_pre(pre_o, p_cur + (size_t)(hgA + 1) * hg_stride4);
+            for (int e = 0; e < 4; ++e) px[e] = __ldg(p + e);
+            tmem_st16(t_acc + hlX * 16, px);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) tmem_st16(t_acc + item_hl(i) * 16, pr[i]);
+        tmem_st_wait();                              // (also covers the c stores of the previous step)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pre_done[s & 1]);
+    };
+    auto prefetch_l2 = [&](int s) {
+        if (CB_LSTM_DEV && (q.dbg_flags & 4)) return;
+        const uint32_t f50 = (uint32_t)frame_of(s) * (2 * NHG) + dhg;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            if (item_hl(i) >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pre4 + (size_t)(((f50 + item_hl(i)) * Bp + b) * 4u)));
+    };
+
+    load_pre(0);
+    park_pre(0);                                     // (also orders the c = 0 stores above before anything else)
+    if (q.T > 1) load_pre(1);
+    for (int s = 2; s < 4 && s < q.T; ++s) prefetch_l2(s);
+
+#pragma unroll 1
     for (int s = 0; s < q.T; ++s) {
         const bool active = s < len;
-        const bool first = s == 0;
         const int t = frame_of(s);
-        const float4* p_nxt = pre_b + (size_t)(s + 1 < q.T ? frame_of(s + 1) : t) * t_stride4;
-        const float4* p_pf = pre_b + (size_t)(s + 2 < q.T ? frame_of(s + 2) : t) * t_stride4;
-        float4* out_t = out_b + (size_t)t * (2 * NHG) * Bp;
-        const size_t img_row = (size_t)q.o_img.row0 + (size_t)t * Bp + b;
         // h(s) goes into buffer s&1 (the MMAs of step s+1 read it while h(s+1) fills the other buffer)
-        uint8_t* h_hi = hbuf + (size_t)(s & 1) * (2 * HS_BYTES);
-        uint8_t* h_lo = h_hi + HS_BYTES;
+        const uint32_t h_hi = hbuf_s + (uint32_t)(s & 1) * (2 * HS_BYTES) + row * 16;
+        const uint32_t t_acc = t_lane + ((s & 1) ? ACC1_COL : 0);
         const bool probe = CB_LSTM_DEV && q.dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && s >= 100 && s < 104;
+        if (CB_LSTM_DEV) { if (probe) q.dbg[((s - 100) * 32 + warp) * 8 + 7] = clock64(); __syncwarp(); }
+        // idle head of the step (the tensor core is busy with step s): park pre(s+1) in the other accumulator buffer.
+        // This warp read its columns of that buffer for the last time in step s-1.
+        if (s + 1 < q.T) park_pre(s + 1);
+        else { __syncwarp(); if (lane == 0) mbar_arrive(&pre_done[(s + 1) & 1]); }
 #pragma unroll 1
         for (int phase = 0; phase < 2; ++phase) {
-            if (probe && phase == 0) q.dbg[((s - 100) * 16 + warp) * 8 + 0] = clock64();
+            if (CB_LSTM_DEV) { if (probe) q.dbg[((s - 100) * 32 + warp) * 8 + 3 * phase + 0] = clock64(); __syncwarp(); }
             mbar_wait(&acc_ready[phase], s & 1);
             tc_fence_after();
-            if (probe && phase == 0) q.dbg[((s - 100) * 16 + warp) * 8 + 1] = clock64();
-            const int kg0 = phase ? kgB0 : kgA0, nk = phase ? nB : nA;
+            if (CB_LSTM_DEV) { if (probe) q.dbg[((s - 100) * 32 + warp) * 8 + 3 * phase + 1] = clock64(); __syncwarp(); }
 #pragma unroll 1
-            for (int k = 0; k < nk; ++k) {
-                const int kg = kg0 + k, hg = 2 * kg, hl = hg - hg_base;
-                const bool void_odd = tailB && phase == 1 && k == nk - 1;
-                float hv[8];
-                half_group(t_lane, t_cell, hl, first, active, pre_e, *reinterpret_cast<float(*)[4]>(&hv[0]));
-                {   // refill the even slot: next K-group of this phase, first K-group of the other phase / the next step
-                    const float4* nx;
-                    if (k + 1 < nk) nx = p_cur + (size_t)(hg + 2) * hg_stride4;
-                    else if (phase == 0) nx = p_cur + (size_t)hgB * hg_stride4;
-                    else nx = p_nxt + (size_t)hgA * hg_stride4;
-                    load_pre(pre_e, nx);
-                    prefetch_l2(p_pf + (size_t)hg * hg_stride4);
-                }
-                half_group(t_lane, t_cell, hl + 1, first, active && !void_odd, pre_o, *reinterpret_cast<float(*)[4]>(&hv[4]));
-                {
-                    const float4* nx;
-                    if (k + 1 < nk) nx = p_cur + (size_t)(hg + 3) * hg_stride4;
-                    else if (phase == 0) nx = p_cur + (size_t)(hgB + 1) * hg_stride4;
-                    else nx = p_nxt + (size_t)(hgA + 1) * hg_stride4;
-                    load_pre(pre_o, nx);             // (for the void upper half of K-group 12 the values are simply unused)
-                    if (!void_odd) prefetch_l2(p_pf + (size_t)(hg + 1) * hg_stride4);
-                }
-                if (q.write_f32) {
-                    out_t[(size_t)hg * Bp] = make_float4(hv[0], hv[1], hv[2], hv[3]);
-                    if (!void_odd) out_t[(size_t)(hg + 1) * Bp] = make_float4(hv[4], hv[5], hv[6], hv[7]);
-                }
-                // h(t) of this (row, K-group) as one 16-byte core-matrix row per hi / lo image: the CTA's buffer (the
-                // exchange thread ships it to the peer) and, for layers that feed another layer, the global operand image
-                uint4 hi, lo;
-                split8(hv, hi, lo);
-                const uint32_t off = (uint32_t)kg * (RM * 16) + row * 16;
-                *reinterpret_cast<uint4*>(h_hi + off) = hi;
-                *reinterpret_cast<uint4*>(h_lo + off) = lo;
+            for (int i = phase; i < 1 + 2 * phase; ++i) {      // first phase: item 0; second phase: items 1 and 2
+                const int hl = item_hl(i);
+                if (hl < 0) continue;
+                const int hg = hg_base + hl, kg = hg >> 1;
+                uint32_t z[16];
+                float c[4], hv[4];
+                tmem_ld16(t_acc + hl * 16, z);
+                tmem_ld4(t_lane + C_COL + hl * 4, c);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    lstm_cell(__uint_as_float(z[e]), __uint_as_float(z[4 + e]), __uint_as_float(z[8 + e]),
+                              __uint_as_float(z[12 + e]), active, c[e], hv[e]);
+                tmem_st4(t_lane + C_COL + hl * 4, c[0], c[1], c[2], c[3]);
+                if (q.write_f32) out4[(size_t)(((uint32_t)t * (2 * NHG) + dir * NHG + hg) * Bp + b)] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                // h(t) of this (row, half K-group) as the 8-byte half of one core-matrix row per hi / lo image: the
+                // CTA's buffer (the exchange thread ships it to the peer) and, for layers that feed another layer,
+                // the global operand image
+                uint2 hi, lo;
+                split4(hv, hi, lo);
+                const uint32_t off = h_hi + (uint32_t)kg * (RM * 16) + (hg & 1) * 8;
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(off), "r"(hi.x), "r"(hi.y) : "memory");
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(off + HS_BYTES), "r"(lo.x), "r"(lo.y) : "memory");
                 if (q.write_img && !(CB_LSTM_DEV && (q.dbg_flags & 2))) {
-                    const size_t goff = ((size_t)(dir * KG + kg) * q.o_img.plane_rows + img_row) * 8;
-                    *reinterpret_cast<uint4*>(q.o_img.hi + goff) = hi;
-                    *reinterpret_cast<uint4*>(q.o_img.lo + goff) = lo;
+                    // uint2 element ((dir*13 + kg)*plane_rows + row0 + t*Bp + b)*2 + (hg&1)
+                    const uint32_t g2 = ((uint32_t)(dir * KG + kg) * (uint32_t)q.o_img.plane_rows + (uint32_t)q.o_img.row0 +
+                                         (uint32_t)t * Bp + b) * 2u + (hg & 1);
+                    reinterpret_cast<uint2*>(q.o_img.hi)[g2] = hi;
+                    reinterpret_cast<uint2*>(q.o_img.lo)[g2] = lo;
                 }
             }
+            if (CB_LSTM_DEV) { if (probe) q.dbg[((s - 100) * 32 + warp) * 8 + 3 * phase + 2] = clock64(); __syncwarp(); }
             // this warp's h rows of the phase are in the CTA's buffer: let the exchange thread ship them to the peer
-            if (phase == 1) tmem_st_wait();
             fence_proxy_async();           // generic-proxy h writes -> visible to the async proxy (bulk copy, tensor core)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&local_done[phase]);
         }
-        if (probe) q.dbg[((s - 100) * 16 + warp) * 8 + 6] = clock64();
-        p_cur = p_nxt;
+        if (s + 2 < q.T) load_pre(s + 2);
+        if (s + 4 < q.T) prefetch_l2(s + 4);
+        if (CB_LSTM_DEV) { if (probe) q.dbg[((s - 100) * 32 + warp) * 8 + 6] = clock64(); __syncwarp(); }
     }
+    tmem_st_wait();
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) lstm_tc_kernel(const LstmTcParams q) {
@@ -270,7 +302,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) lstm_tc
     uint64_t* h_ready = bars + 1;      // the peer's half of h(t) has landed in this CTA's buffer (byte-counted bulk copies)
     uint64_t* acc_ready = bars + 2;    // [2] MMAs of the first / second column phase of the step retired
     uint64_t* local_done = bars + 4;   // [2] this CTA's gate warps finished the phase (h rows written, accumulator free)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    uint64_t* pre_done = bars + 6;     // [2] by step parity: the gate warps parked the step's input projection in its
+                                       //     accumulator buffer (two barriers: a warp arrives for step s+1 without
+                                       //     having waited on anything since its arrival for step s)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
@@ -279,9 +314,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) lstm_tc
     const int hg_base = rank ? 12 : 0;               // half-groups [0,12) | [12,25)
     const int ncol = rank ? 208 : 192;
     const int col0 = rank ? 192 : 0;
-    // column phases (MMA issue order) in K-groups of 32 columns: rank 0: {0,1,2}{3,4,5}; rank 1: {6,7,8,9}{10,11,12}
-    const int kgP0 = rank ? 6 : 0, nP0 = rank ? 4 : 3, kgP1 = rank ? 10 : 3, nP1 = 3;
-    const int NA = nP0 * 32, NB = ncol - NA;         // 96|96 or 128|80 columns
+    // column phases (MMA issue order) in K-groups of 32 columns: rank 0: {0,1,2}{3,4,5}; rank 1: {6,7,8}{9,10,11,12}
+    // (= local half-groups [0,6)[6,12) and [0,6)[6,13))
+    const int kgP0 = rank ? 6 : 0, nP0 = 3, kgP1 = rank ? 9 : 3, nP1 = rank ? 4 : 3;
+    const int NA = nP0 * 32, NB = ncol - NA;         // 96|96 or 96|112 columns
 
     // zero both h buffers (h(0) = 0; padding K-groups stay zero) and the weight region (its 14th K-group and unused
     // rows must read as finite zeros: the K padding of the last MMA K-step multiplies them with zero)
@@ -294,6 +330,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) lstm_tc
         mbar_init(&local_done[1], GATE_WARPS);
         mbar_init(&acc_ready[0], 1);
         mbar_init(&acc_ready[1], 1);
+        mbar_init(&pre_done[0], GATE_WARPS);
+        mbar_init(&pre_done[1], GATE_WARPS);
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -330,37 +368,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) lstm_tc
             for (int s = 0; s < q.T; ++s) {
                 uint64_t da_hi = 0, da_lo = 0;
                 const bool probe = CB_LSTM_DEV && q.dbg && blockIdx.x == 0 && blockIdx.y == 0 && s >= 100 && s < 104;
-                if (probe) q.dbg[((s - 100) * 16 + 0) * 8 + 0] = clock64();
+                if (probe) q.dbg[((s - 100) * 32 + 0) * 8 + 0] = clock64();
+                mbar_wait(&pre_done[s & 1], (s >> 1) & 1);     // pre(s) sits in accumulator buffer s&1
                 if (s > 0) {                                   // h(0) = 0: the first step has no recurrent term
                     mbar_wait_cluster(h_ready, (s - 1) & 1);  // peer's half of h(s-1) landed (own half: local_done, below)
                     tc_fence_after();
                     const uint32_t hb = smem_u32(hbuf) + (uint32_t)((s - 1) & 1) * (2 * HS_BYTES);
                     da_hi = make_desc(hb, RM * 16, 128); da_lo = make_desc(hb + HS_BYTES, RM * 16, 128);
                 }
-                if (probe) q.dbg[((s - 100) * 16 + 0) * 8 + 1] = clock64();
+                tc_fence_after();
+                if (probe) q.dbg[((s - 100) * 32 + 0) * 8 + 1] = clock64();
 #pragma unroll
                 for (int phase = 0; phase < 2; ++phase) {
-                    if (s > 0) {
-                        const uint32_t d = tmem_base + (phase ? NA : 0);
+                    if (s > 0) {                               // accumulate on top of the parked input projection
+                        const uint32_t d = tmem_base + ((s & 1) ? ACC1_COL : 0) + (phase ? NA : 0);
                         const uint32_t idesc = phase ? idescB : idescA;
                         const uint32_t brow = phase ? NA : 0;   // 16 B units
-                        uint32_t acc = 0;
                         if (q.passes == 3) {
 #pragma unroll
                             for (int ks = 0; ks < KG_A / 2; ++ks) {   // low-order products first
-                                umma_f16(d, da_hi + ks * A_STEP, db_lo + (ks * B_STEP + brow), idesc, acc);
-                                acc = 1;
+                                umma_f16(d, da_hi + ks * A_STEP, db_lo + (ks * B_STEP + brow), idesc, 1);
                                 umma_f16(d, da_lo + ks * A_STEP, db_hi + (ks * B_STEP + brow), idesc, 1);
                             }
                         }
 #pragma unroll
-                        for (int ks = 0; ks < KG_A / 2; ++ks) {
-                            umma_f16(d, da_hi + ks * A_STEP, db_hi + (ks * B_STEP + brow), idesc, acc);
-                            acc = 1;
-                        }
+                        for (int ks = 0; ks < KG_A / 2; ++ks)
+                            umma_f16(d, da_hi + ks * A_STEP, db_hi + (ks * B_STEP + brow), idesc, 1);
                     }
                     umma_commit(&acc_ready[phase]);
-                    if (probe) q.dbg[((s - 100) * 16 + 0) * 8 + 2 + phase] = clock64();
+                    if (probe) q.dbg[((s - 100) * 32 + 0) * 8 + 2 + phase] = clock64();
                 }
                 // arm this step's receive barrier BEFORE shipping my half (the peer can only send h(s+1) after it got
                 // my h(s), so bytes of different steps never meet in one barrier phase)
@@ -369,6 +405,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) lstm_tc
 #pragma unroll
                 for (int phase = 0; phase < 2; ++phase) {
                     mbar_wait(&local_done[phase], s & 1);      // my gate warps wrote the phase's K-groups of h(s)
+                    if (probe) q.dbg[((s - 100) * 32 + 0) * 8 + 4 + phase] = clock64();
                     const uint32_t off = buf_off + (phase ? offB : offA), len = phase ? lenB : lenA;
                     bulk_s2s_cluster(hbuf_peer + off, hbuf + off, len, h_ready_peer);                        // hi image rows
                     bulk_s2s_cluster(hbuf_peer + off + HS_BYTES, hbuf + off + HS_BYTES, len, h_ready_peer);  // lo image rows
@@ -379,14 +416,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) lstm_tc
         }
     } else {
         // ============================ gate warps ======================================================================
-        // Warp w may only touch TMEM lanes 32*(w%4)..+31; warps 1..12 give every quadrant three warps (slots 0..2).
-        // Slot j takes K-group j of the first column phase and K-group j of the second (rank 1's first phase has four:
-        // slot 2 takes two, and its second phase ends with the half-empty K-group 12).
+        // Warp w may only touch TMEM lanes 32*(w%4)..+31; warps 1..24 give every quadrant six warps (slots 0..5).
+        // Slot j takes half-group j of the first phase and half-group j of the second; rank 1's second phase has a
+        // seventh half-group, which goes to slot 0.
         const int slot = (warp - 1) >> 2;
-        int kgA0, nA, kgB0, nB;
-        if (rank == 0) { kgA0 = kgP0 + slot; nA = 1; kgB0 = kgP1 + slot; nB = 1; }
-        else { kgA0 = kgP0 + slot; nA = slot == 2 ? 2 : 1; kgB0 = kgP1 + slot; nB = 1; }
-        gate_loop(q, hbuf, local_done, acc_ready, tmem_base, warp, lane, dir, b0, hg_base, kgA0, nA, kgB0, nB);
+        const int hlA = slot, hlB = SLOTS + slot, hlX = (rank && slot == 0) ? 2 * SLOTS : -1;
+        gate_loop(q, smem_u32(hbuf), local_done, acc_ready, pre_done, tmem_base, warp, lane, dir, b0, hg_base, hlA, hlB, hlX);
     }
 
     tc_fence_before();
@@ -461,25 +496,31 @@ int cb_launch_lstm_tc(cb_handle* h, const LstmProblem& p, const CbImg* o_img, in
     q.write_f32 = write_f32;
     if (o_img) { q.o_img = *o_img; q.write_img = 1; }
     if (q.Bp % RM) { cb_set_error("lstm tensor-core path: padded batch %d not a multiple of %d", q.Bp, RM); return CB_ERR_ARG; }
+    // the gate warps address pre / out / the operand image with 32-bit element indices
+    if ((unsigned long long)q.T * (2 * NHG) * q.Bp * 4ull >= (1ull << 32) ||
+        (o_img && (unsigned long long)o_img->planes * o_img->plane_rows * 2ull >= (1ull << 32))) {
+        cb_set_error("lstm tensor-core path: batch %d x %d frames exceeds the 32-bit element index range; split the batch", q.B, q.T);
+        return CB_ERR_ARG;
+    }
     static long long* d_dbg = nullptr;
     const char* probe = getenv("CB_LSTM_PROBE");
-    if (probe && !d_dbg) { cudaMalloc(&d_dbg, 4 * 16 * 8 * sizeof(long long)); cudaMemset(d_dbg, 0, 4 * 16 * 8 * sizeof(long long)); }
+    if (probe && !d_dbg) { cudaMalloc(&d_dbg, 4 * 32 * 8 * sizeof(long long)); cudaMemset(d_dbg, 0, 4 * 32 * 8 * sizeof(long long)); }
     q.dbg = probe ? d_dbg : nullptr;
     q.dbg_flags = getenv("CB_LSTM_DBG") ? atoi(getenv("CB_LSTM_DBG")) : 0;
     lstm_tc_kernel<<<dim3(2 * (q.Bp / RM), 2), NTHREADS, SMEM_BYTES, s>>>(q);     // clusters of 2 along x
     CB_CHECK_LAUNCH();
     h->launches++;
     if (q.dbg && p.layer == 0) {          // development probe: print the timeline of steps 100..103 of CTA (0,0)
-        long long hbuf[4 * 16 * 8];
+        long long hbuf[4 * 32 * 8];
         cudaStreamSynchronize(s);
         cudaMemcpy(hbuf, q.dbg, sizeof(hbuf), cudaMemcpyDeviceToHost);
         const long long t0 = hbuf[1];
         for (int st = 0; st < 4; ++st) {
-            const long long* m = hbuf + (st * 16) * 8;
-            fprintf(stderr, "step %d mma: wait_begin %lld h_ready %lld commitA %lld commitB %lld\n", 100 + st, m[0] - t0, m[1] - t0, m[2] - t0, m[3] - t0);
+            const long long* m = hbuf + (st * 32) * 8;
+            fprintf(stderr, "step %d mma: wait_begin %lld h_ready %lld commitA %lld commitB %lld doneA %lld doneB %lld\n", 100 + st, m[0] - t0, m[1] - t0, m[2] - t0, m[3] - t0, m[4] - t0, m[5] - t0);
             for (int w = 1; w <= GATE_WARPS; ++w) {
-                const long long* g = hbuf + (st * 16 + w) * 8;
-                fprintf(stderr, "   warp %2d: waitA %lld gotA %lld | kg0: tmem_ld %lld sums+ldg %lld cells %lld stores %lld | done %lld arrived %lld\n", w, g[0] - t0, g[1] - t0, g[2] - t0, g[3] - t0, g[4] - t0, g[5] - t0, g[6] - t0, g[7] - t0);
+                const long long* g = hbuf + (st * 32 + w) * 8;
+                fprintf(stderr, "   warp %2d: begin %lld waitA %lld gotA %lld cellsA %lld | waitB %lld gotB %lld cellsB %lld | end %lld\n", w, g[7] - t0, g[0] - t0, g[1] - t0, g[2] - t0, g[3] - t0, g[4] - t0, g[5] - t0, g[6] - t0);
             }
         }
     }
