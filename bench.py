@@ -248,8 +248,21 @@ def main():
     dom_ms, dom_cnt = prof_acc[dom]
     achieved = flops / (dom_ms * 1e-3) / 1e12
     peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    # tensor-pipe work actually issued: the tc path runs every contraction as 3 fp16 MMAs (hi*lo, lo*hi, hi*hi)
+    mma_passes = {"tc": 3, "tc_fast": 1}.get(args.precision, 0)
+    traffic, traffic_src = None, None
+    try:                                   # DRAM bytes per launch of the dominant kernel from the committed ncu capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if tj.get("precision") == args.precision and tj.get("batch") == B and dom in tj.get("per_category", {}):
+            traffic = tj["per_category"][dom]["dram_bytes_per_launch"]
+            traffic_src = tj.get("source")
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf, "traffic": None, "peak_source": "%s (bf16_tflops_sustained)" % peak_kind,
+                "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": "%s (bf16_tflops_sustained)" % peak_kind,
+                "mma_passes": mma_passes, "tensor_pipe_tflops": achieved * max(mma_passes, 1),
+                "tensor_pipe_frac": achieved * max(mma_passes, 1) / peak_tf if mma_passes else None,
                 "launches_per_step": dom_cnt, "avg_launch_ms": dom_ms / max(dom_cnt, 1),
                 "algorithmic_flop_per_launch": flops / max(dom_cnt, 1),
                 "per_category_ms": {k: round(v[0], 3) for k, v in prof_acc.items()},

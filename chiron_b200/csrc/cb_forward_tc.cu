@@ -160,7 +160,7 @@ int cb_forward_tc(cb_handle* h, const float* x, const int32_t* seq_len_out, int 
             else { g.a0 = w->himg; g.a0_plane0 = d * 13; g.a0_chunks_per_tap = 4; }            // K' = 104 -> 4 chunks
             g.N = n_gemm == 1 ? 8 * H : 4 * H;
             g.shift = cb_tc_lstm_bias(h, l, d);                    // gate columns in unit-major order
-            g.out_mode = 1; g.out = w->pre + (size_t)d * 4 * H * Bp; g.ldo = 8 * H;    // pre[T][8H/16][Bp][16]
+            g.out_mode = 1; g.out = w->pre + (size_t)d * 4 * H * Bp; g.ldo = 8 * H;    // pre[T][8H/4][Bp][4]
             if ((rc = timed_gemm(h, g, s, CB_CAT_LSTM_IN)) != CB_OK) return rc;
         }
         LstmProblem lp;

@@ -19,7 +19,7 @@
 //   * 24 gate warps (6 per TMEM lane quadrant = per SM sub-partition; <= 80 registers each) take one half-group of
 //     each phase (4 cells per thread, evaluated with MUFU ex2/rcp, 7 per cell -- the MUFU pipe is the bound), keep c in
 //     spare TMEM columns, and write h back as 8-byte halves of the 16-byte core-matrix rows.
-// Global layouts are time-major with the batch (almost) innermost -- pre[T][50][Bp][16], out[T][50][Bp][4] -- so that the
+// Global layouts are time-major with the batch (almost) innermost -- pre[T][200][Bp][4], out[T][50][Bp][4] -- so that the
 // 32 rows of a warp read and write contiguous, vectorised segments at every step.
 #include <cuda_fp16.h>
 #include <stdio.h>
@@ -54,7 +54,7 @@ constexpr size_t SMEM_BYTES = 2 * (size_t)W_BYTES + 4 * (size_t)HS_BYTES + 128;
 
 struct LstmTcParams {
     int B, Bp, T;
-    const float* pre;          // [T][2*25 half-groups][Bp][16]: per half-group i0..3 j0..3 f0..3 o0..3 (unit-major)
+    const float* pre;          // [T][2*25 half-groups][4 gates i,j,f,o][Bp][4 units]
     const __half* wimg[2];     // per direction: hi image then lo image, [KG][400][8] halfs each
     const int32_t* lens;       // [B]
     float* out;                // [T][2*25][Bp][4] fp32 (written when write_f32: the last layer, read by the logit head)
@@ -167,7 +167,7 @@ __device__ __forceinline__ void gate_loop(const LstmTcParams& q, uint32_t hbuf_s
     const uint32_t Bp = (uint32_t)q.Bp;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
     const uint32_t dhg = (uint32_t)(dir * NHG + hg_base);            // first half-group of this CTA in a frame of pre / out
-    const float4* pre4 = reinterpret_cast<const float4*>(q.pre);     // element ((t*50 + hg)*Bp + b)*4 + e
+    const float4* pre4 = reinterpret_cast<const float4*>(q.pre);     // element ((t*50 + hg)*4 + gate)*Bp + b
     float4* out4 = reinterpret_cast<float4*>(q.out);                 // element (t*50 + hg)*Bp + b
     auto item_hl = [&](int i) { return i == 0 ? hlA : (i == 1 ? hlB : hlX); };
 
@@ -193,18 +193,18 @@ __device__ __forceinline__ void gate_loop(const LstmTcParams& q, uint32_t hbuf_s
         const uint32_t f50 = (uint32_t)frame_of(s) * (2 * NHG) + dhg;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            const float4* p = pre4 + (size_t)(((f50 + item_hl(i)) * Bp + b) * 4u);
+            const float4* p = pre4 + (size_t)((f50 + item_hl(i)) * 4u * Bp + b);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) pr[i][e] = __ldg(p + e);
+            for (int e = 0; e < 4; ++e) pr[i][e] = __ldg(p + (size_t)(e * Bp));
         }
     };
     auto park_pre = [&](int s) {                     // registers -> accumulator buffer of step s
         const uint32_t t_acc = t_lane + ((s & 1) ? ACC1_COL : 0);
         if (hlX >= 0 && !(CB_LSTM_DEV && (q.dbg_flags & 1))) {
-            const float4* p = pre4 + (size_t)((((uint32_t)frame_of(s) * (2 * NHG) + dhg + hlX) * Bp + b) * 4u);
+            const float4* p = pre4 + (size_t)(((uint32_t)frame_of(s) * (2 * NHG) + dhg + hlX) * 4u * Bp + b);
             float4 px[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) px[e] = __ldg(p + e);
+            for (int e = 0; e < 4; ++e) px[e] = __ldg(p + (size_t)(e * Bp));
             tmem_st16(t_acc + hlX * 16, px);
         }
 #pragma unroll
@@ -219,7 +219,9 @@ __device__ __forceinline__ void gate_loop(const LstmTcParams& q, uint32_t hbuf_s
         const uint32_t f50 = (uint32_t)frame_of(s) * (2 * NHG) + dhg;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
-            if (item_hl(i) >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pre4 + (size_t)(((f50 + item_hl(i)) * Bp + b) * 4u)));
+            if (item_hl(i) >= 0)       // 4 gate segments of 512 B per item: lanes 0..15 take one 128-byte line each
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pre4 + (size_t)(((f50 + item_hl(i)) * 4u + ((lane >> 2) & 3)) * Bp +
+                                                                             (b - lane) + (lane & 3) * 8)));
     };
 
     load_pre(0);

@@ -147,10 +147,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams q) 
                         *reinterpret_cast<uint4*>(g.o.hi + off) = hi;
                         *reinterpret_cast<uint4*>(g.o.lo + off) = lo;
                     }
-                } else {                                  // fp32 [to][n/16][Bp][16]: 64 contiguous bytes per row, 2 KB per warp
-                    float4* dst = reinterpret_cast<float4*>(g.out) + (((size_t)to * (g.ldo >> 4) + (n0 >> 4)) * g.Bp + b) * 4;
+                } else {                                  // fp32 [to][n/4][Bp][4]: every store instruction of a warp writes
+                                                          // 512 contiguous bytes (16 full sectors)
+                    float4* dst = reinterpret_cast<float4*>(g.out) + ((size_t)to * (g.ldo >> 2) + (n0 >> 2)) * g.Bp + b;
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) dst[q4] = make_float4(o[q4 * 4], o[q4 * 4 + 1], o[q4 * 4 + 2], o[q4 * 4 + 3]);
+                    for (int q4 = 0; q4 < 4; ++q4)
+                        dst[(size_t)q4 * g.Bp] = make_float4(o[q4 * 4], o[q4 * 4 + 1], o[q4 * 4 + 2], o[q4 * 4 + 3]);
                 }
             }
             tc_fence_before();
