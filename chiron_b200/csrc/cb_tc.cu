@@ -9,11 +9,21 @@
 //     tap is the same plane shifted by one frame = Bp rows; a strided conv multiplies the frame index; the appended 1x1
 //     branch input is a second image).  Block-1 conv2a (a rank-1 function of the raw signal, cnn.py:254) is written as an
 //     image by gen_conv2a_kernel.
+//   * the A side of a stage (hi and lo, 4 k-group planes x 128 rows x 16 B each) is ONE cp.async.bulk.tensor: the image
+//     is described to the TMA unit as a 3-D tensor {256 x 8-byte elements = 128 rows, plane, hi|lo} whose {256,4,2} box
+//     lands in shared memory as [hi|lo][4 k-groups][128 rows][8 halfs] -- the UMMA core-matrix order.  (Eight 2 KB
+//     cp.async.bulk copies per stage made the single loader thread the bound of every contraction: ~120 cycles each.)
 //   * persistent CTAs (one per SM), warp-specialised: 8 epilogue warps (TMEM -> scale/shift/residual/ReLU -> hi/lo
 //     image or fp32), 1 MMA-issuing thread, 1 loader thread (weight + activation images, mbarrier expect-tx); smem
 //     full/empty ring (STAGES deep) and a double-buffered TMEM accumulator so the epilogue of tile i overlaps the MMAs
 //     of tile i+1.
+//   * RESIDENT-WEIGHT mode (contractions whose whole n-tile of W fits beside the A ring -- the N = 8H LSTM input
+//     projection): a CTA is bound to ONE n-tile, loads its hi/lo weight image once and then streams only A tiles.  The
+//     streaming mode re-reads the B tile from L2 for every 128-row tile, which ncu showed to be the bound of that
+//     contraction (xbar->L1 9 TB/s + 2.5 TB/s of stores against the ~12 TB/s the L2 slices sustain).
+#include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -26,6 +36,7 @@ namespace {
 constexpr int BM = 128;          // rows (windows of one frame) per tile = UMMA M
 constexpr int BK = 32;           // K elements per pipeline stage (2 UMMA K-steps of 16)
 constexpr int STAGES = 4;
+constexpr int PREFETCH_AHEAD = 16;  // k-chunks (16 KB boxes) the L2 prefetch runs ahead of the loads
 constexpr int N_EPI_WARPS = 8;   // two per TMEM lane quadrant (each takes half of the tile's columns)
 constexpr int NTHREADS = (N_EPI_WARPS + 2) * 32;   // 320
 
@@ -43,38 +54,80 @@ struct TcState {
 };
 
 struct TcParams {
+    CUtensorMap tm_a0, tm_a1;    // TMA views of the operand images a0 / a1 (see make_img_map)
     TcGemm g;
     const __half* img;
     int BN, n_tiles, k_chunks, m_tiles;
     float out_scale;
     int passes;                  // 3 = hi/lo split, 1 = fast
+    int prefetch_ahead;          // k-chunks the L2 prefetch of the A boxes runs ahead of the loads
+    int resident;                // 1: the CTA keeps its n-tile of W in shared memory (see header)
     int* range_flag;
+};
+
+// Which (m-tile, n-tile) a CTA works on in its i-th iteration.  Streaming mode: tiles round-robin over the CTAs.
+// Resident mode: n-tile = blockIdx.x % n_tiles for the whole launch, m-tiles round-robin over the CTAs sharing it.
+struct TileIter {
+    int resident, n_tiles, m_tiles, total, first, step, nt_fixed;
+    __device__ TileIter(const TcParams& q) {
+        resident = q.resident; n_tiles = q.n_tiles; m_tiles = q.m_tiles; total = q.m_tiles * q.n_tiles;
+        if (resident) {
+            nt_fixed = blockIdx.x % n_tiles;
+            first = blockIdx.x / n_tiles;
+            step = ((int)gridDim.x - nt_fixed + n_tiles - 1) / n_tiles;
+        } else { nt_fixed = 0; first = blockIdx.x; step = gridDim.x; }
+    }
+    __device__ __forceinline__ bool get(int i, int& mt, int& nt) const {
+        const int v = first + i * step;
+        if (resident) { mt = v; nt = nt_fixed; return v < m_tiles; }
+        mt = v / n_tiles; nt = v - mt * n_tiles; return v < total;
+    }
 };
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // shared memory: STAGES x { A_hi[4][128][8], A_lo, B_hi[4][BN][8], B_lo } halfs, then the barriers.
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams q) {
+// one box {256 x u64, 4 planes, hi|lo} = 16 KB of the image -> [hi|lo][4][128 rows][16 B] in shared memory
+__device__ __forceinline__ void tma_img_g2s(void* dst, const CUtensorMap* tm, int row, int plane, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(row * 2), "r"(plane), "r"(0), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_img_prefetch(const CUtensorMap* tm, int row, int plane) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+                 "r"(row * 2), "r"(plane), "r"(0)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams q) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const TcGemm& g = q.g;
     const int BN = q.BN;
     constexpr uint32_t a_bytes = BM * BK * 2;             // one of hi / lo
     const uint32_t b_bytes = (uint32_t)BN * BK * 2;
-    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * stage_bytes);
+    // streaming: STAGES x {A_hi, A_lo, B_hi, B_lo};  resident: k_chunks x {B_hi, B_lo} then STAGES x {A_hi, A_lo}
+    const uint32_t stage_bytes = q.resident ? 2 * a_bytes : 2 * a_bytes + 2 * b_bytes;
+    const uint32_t res_bytes = q.resident ? (uint32_t)q.k_chunks * 2 * b_bytes : 0;
+    uint8_t* ring = smem + res_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)STAGES * stage_bytes);
     uint64_t* full_bar = bars;                            // [STAGES]  operands landed
     uint64_t* empty_bar = bars + STAGES;                  // [STAGES]  MMAs that read the stage retired
     uint64_t* acc_full = bars + 2 * STAGES;               // [2]       accumulator ready for the epilogue
     uint64_t* acc_empty = bars + 2 * STAGES + 2;          // [2]       accumulator drained
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* w_bar = bars + 2 * STAGES + 4;              //           resident weights landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = q.m_tiles * q.n_tiles;
+    const TileIter tiles(q);
     const int tiles_per_frame = g.Bp / BM;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], N_EPI_WARPS * 32); }
+        mbar_init(w_bar, 1);
         fence_barrier_init();
     }
     if (warp == N_EPI_WARPS) {                            // MMA warp owns the TMEM allocation (all 512 columns)
@@ -93,8 +146,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams q) 
         const int cbeg = chalf ? first : 0, cend = chalf ? BN : first;
         uint32_t it = 0;
         bool overflow = false;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int mt = tile / q.n_tiles, nt = tile - mt * q.n_tiles;
+        for (int mt, nt; tiles.get((int)it, mt, nt); ++it) {
             const uint32_t buf = it & 1, par = (it >> 1) & 1;
             mbar_wait(&acc_full[buf], par);
             tc_fence_after();
@@ -166,7 +218,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams q) 
             constexpr uint32_t A_STEP = 2 * BM;               // two k-groups per UMMA K-step, in 16-byte units
             const uint32_t B_STEP = 2 * (uint32_t)BN;
             uint32_t kit = 0, it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            if (q.resident) mbar_wait(w_bar, 0);
+            for (int mt, nt; tiles.get((int)it, mt, nt); ++it) {
                 const uint32_t buf = it & 1, par = (it >> 1) & 1;
                 mbar_wait(&acc_empty[buf], par ^ 1);          // epilogue has drained this accumulator
                 tc_fence_after();
@@ -175,10 +228,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams q) 
                     const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
+                    const uint32_t sb = q.resident ? smem_u32(smem) + (uint32_t)kc * 2 * b_bytes : sa + 2 * a_bytes;
                     const uint64_t dah = make_desc(sa, BM * 16, 128), dal = make_desc(sa + a_bytes, BM * 16, 128);
-                    const uint64_t dbh = make_desc(sa + 2 * a_bytes, BN * 16, 128);
-                    const uint64_t dbl = make_desc(sa + 2 * a_bytes + b_bytes, BN * 16, 128);
+                    const uint64_t dbh = make_desc(sb, BN * 16, 128);
+                    const uint64_t dbl = make_desc(sb + b_bytes, BN * 16, 128);
 #pragma unroll
                     for (int ks = 0; ks < BK / 16; ++ks) {
                         if (q.passes == 3) {                  // low-order products first (truncating accumulator)
@@ -199,34 +253,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const TcParams q) 
         if (lane == 0) {
             uint32_t kit = 0;
             const int n0c = g.taps * g.a0_chunks_per_tap;     // k-chunks served by image a0
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int mt = tile / q.n_tiles, nt = tile - mt * q.n_tiles;
+            if (q.resident) {                                 // the CTA's n-tile of W: one contiguous image
+                const uint32_t chunk = 2 * b_bytes;
+                mbar_arrive_expect_tx(w_bar, (uint32_t)q.k_chunks * chunk);
+                const __half* wsrc = q.img + (size_t)tiles.nt_fixed * q.k_chunks * (2 * (size_t)BN * BK);
+                for (int kc = 0; kc < q.k_chunks; ++kc)
+                    bulk_g2s(smem + (size_t)kc * chunk, wsrc + (size_t)kc * (2 * (size_t)BN * BK), chunk, w_bar);
+            }
+            // A-side box of k-chunk kc of the CTA's it-th tile
+            auto coords = [&](int it_, int kc_, const CUtensorMap*& tm, int& row, int& plane) -> bool {
+                int mt, nt;
+                if (!tiles.get(it_, mt, nt)) return false;
                 const int to = mt / tiles_per_frame;
                 const long long b0 = (long long)(mt - to * tiles_per_frame) * BM;
+                if (kc_ < n0c) {
+                    const int j = kc_ / g.a0_chunks_per_tap, cc = kc_ - j * g.a0_chunks_per_tap;
+                    row = (int)(g.a0.row0 + ((long long)to * g.stride + j - g.left) * g.Bp + b0);
+                    plane = g.a0_plane0 + cc * 4; tm = &q.tm_a0;
+                } else {
+                    row = (int)(g.a1.row0 + (long long)to * g.Bp + b0);
+                    plane = g.a1_plane0 + (kc_ - n0c) * 4; tm = &q.tm_a1;
+                }
+                return true;
+            };
+            // The activation image is streamed from HBM once; with at most STAGES boxes in flight the ring cannot cover
+            // the DRAM latency, so every box is pulled into L2 PREFETCH_AHEAD chunks before it is loaded.
+            const CUtensorMap* tm; int row, plane;
+            int p_it = 0, p_kc = 0;                          // prefetch cursor
+            auto prefetch_next = [&]() {
+                if (p_it < 0) return;
+                if (coords(p_it, p_kc, tm, row, plane)) tma_img_prefetch(tm, row, plane); else { p_it = -1; return; }
+                if (++p_kc == q.k_chunks) { p_kc = 0; ++p_it; }
+            };
+            for (int d = 0; d < q.prefetch_ahead; ++d) prefetch_next();
+            for (int it = 0, mt, nt; tiles.get(it, mt, nt); ++it) {
                 const __half* wsrc = q.img + (size_t)nt * q.k_chunks * (2 * (size_t)BN * BK);
                 for (int kc = 0; kc < q.k_chunks; ++kc, ++kit) {
                     const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
+                    if (q.prefetch_ahead) prefetch_next();
                     mbar_wait(&empty_bar[s], ph ^ 1);
-                    uint8_t* st = smem + (size_t)s * stage_bytes;
-                    mbar_arrive_expect_tx(&full_bar[s], 2 * a_bytes + 2 * b_bytes);
-                    const __half *hi, *lo;
-                    size_t plane_stride;
-                    if (kc < n0c) {
-                        const int j = kc / g.a0_chunks_per_tap, cc = kc - j * g.a0_chunks_per_tap;
-                        const long long row = g.a0.row0 + ((long long)to * g.stride + j - g.left) * g.Bp + b0;
-                        const size_t off = ((size_t)(g.a0_plane0 + cc * 4) * g.a0.plane_rows + row) * 8;
-                        hi = g.a0.hi + off; lo = g.a0.lo + off; plane_stride = (size_t)g.a0.plane_rows * 8;
-                    } else {
-                        const long long row = g.a1.row0 + (long long)to * g.Bp + b0;
-                        const size_t off = ((size_t)(g.a1_plane0 + (kc - n0c) * 4) * g.a1.plane_rows + row) * 8;
-                        hi = g.a1.hi + off; lo = g.a1.lo + off; plane_stride = (size_t)g.a1.plane_rows * 8;
-                    }
-#pragma unroll
-                    for (int kg = 0; kg < 4; ++kg) {
-                        bulk_g2s(st + kg * (BM * 16), hi + kg * plane_stride, BM * 16, &full_bar[s]);
-                        bulk_g2s(st + a_bytes + kg * (BM * 16), lo + kg * plane_stride, BM * 16, &full_bar[s]);
-                    }
-                    bulk_g2s(st + 2 * a_bytes, wsrc + (size_t)kc * (2 * (size_t)BN * BK), 2 * b_bytes, &full_bar[s]);
+                    uint8_t* st = ring + (size_t)s * stage_bytes;
+                    mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+                    coords(it, kc, tm, row, plane);
+                    tma_img_g2s(st, tm, row, plane, &full_bar[s]);
+                    if (!q.resident)
+                        bulk_g2s(st + 2 * a_bytes, wsrc + (size_t)kc * (2 * (size_t)BN * BK), 2 * b_bytes, &full_bar[s]);
                 }
             }
         }
@@ -280,7 +351,39 @@ __global__ void __launch_bounds__(256) gen_conv2a_kernel(const float* __restrict
     }
 }
 
+// TMA view of an operand image: dim0 = 8-byte elements along the rows of a plane (2 per 16-byte row), dim1 = plane,
+// dim2 = hi | lo (the two allocations of an image; lo lies behind hi in the workspace).
+int make_img_map(const CbImg& img, CUtensorMap* tm) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+            cb_set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return CB_ERR_CUDA;
+        }
+        encode = (EncodeFn)fn;
+    }
+    const long long hl = (const char*)img.lo - (const char*)img.hi;
+    if (hl <= 0 || (hl & 15)) { cb_set_error("operand image: lo plane set must lie behind hi, 16-byte aligned"); return CB_ERR_ARG; }
+    const cuuint64_t dims[3] = {(cuuint64_t)img.plane_rows * 2, (cuuint64_t)img.planes, 2};
+    const cuuint64_t strides[2] = {(cuuint64_t)img.plane_rows * 16, (cuuint64_t)hl};
+    const cuuint32_t box[3] = {256, 4, 2}, estr[3] = {1, 1, 1};
+    const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, (void*)img.hi, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { cb_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return CB_ERR_CUDA; }
+    return CB_OK;
+}
+
 size_t smem_bytes_for(int BN) { return (size_t)STAGES * (2 * BM * BK * 2 + 2 * (size_t)BN * BK * 2) + 256; }
+size_t smem_bytes_resident(int BN, int k_chunks) {
+    return (size_t)k_chunks * 2 * BN * BK * 2 + (size_t)STAGES * (2 * BM * BK * 2) + 256;
+}
+constexpr size_t SMEM_MAX = 232448;      // 227 KB of dynamic shared memory per CTA
 
 int pick_bn(int N) {            // widest tile <= 256 that divides N (UMMA N must be a multiple of 16 at M = 128)
     for (int bn = 256; bn >= 16; bn -= 16)
@@ -391,7 +494,7 @@ int cb_tc_prepare(cb_handle* h, const float* hw) {
     CB_CUDA(cudaMemcpy(st->d_lstm_bias, bias_all.data(), bias_all.size() * sizeof(float), cudaMemcpyHostToDevice));
     CB_CUDA(cudaMalloc(&st->d_range_flag, sizeof(int)));
     CB_CUDA(cudaMemset(st->d_range_flag, 0, sizeof(int)));
-    CB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_for(256)));
+    CB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
     return cb_lstm_tc_prepare(h, hw);
 }
 
@@ -443,13 +546,25 @@ int cb_launch_gemm_tc(cb_handle* h, const TcGemm& g, cudaStream_t s) {
     }
     if (g.Bp % BM) { cb_set_error("tensor-core path: padded batch must be a multiple of 128"); return CB_ERR_ARG; }
     TcParams q;
+    int rc = make_img_map(g.a0, &q.tm_a0);
+    if (rc == CB_OK) rc = make_img_map(g.a1_chunks ? g.a1 : g.a0, &q.tm_a1);
+    if (rc != CB_OK) return rc;
     q.g = g; q.img = L.img; q.BN = L.BN; q.n_tiles = L.n_tiles; q.k_chunks = L.k_chunks;
     q.m_tiles = g.T * (g.Bp / BM); q.out_scale = L.out_scale;
     q.passes = h->precision == CB_PREC_TC_FAST ? 1 : 3;
     q.range_flag = st->d_range_flag;
+    static const int prefetch_env = getenv("CB_TC_PREFETCH") ? atoi(getenv("CB_TC_PREFETCH")) : PREFETCH_AHEAD;
+    q.prefetch_ahead = prefetch_env;
     const long long tiles = (long long)q.m_tiles * q.n_tiles;
-    const int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
-    gemm_tc_kernel<<<grid, NTHREADS, smem_bytes_for(L.BN), s>>>(q);
+    // resident weights when the n-tile's image fits beside the A ring, the CTAs can be dealt evenly over the n-tiles
+    // and every CTA gets enough m-tiles to amortise the weight load
+    const int per_nt = h->sm_count / L.n_tiles;
+    q.resident = L.n_tiles > 1 && smem_bytes_resident(L.BN, L.k_chunks) <= SMEM_MAX && per_nt >= 1 &&
+                 q.m_tiles >= 8 * per_nt;
+    int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
+    size_t smem = smem_bytes_for(L.BN);
+    if (q.resident) { grid = per_nt * L.n_tiles; smem = smem_bytes_resident(L.BN, L.k_chunks); }
+    gemm_tc_kernel<<<grid, NTHREADS, smem, s>>>(q);
     CB_CHECK_LAUNCH();
     h->launches++;
     return CB_OK;
