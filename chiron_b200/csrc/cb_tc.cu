@@ -36,7 +36,8 @@ namespace {
 constexpr int BM = 128;          // rows (windows of one frame) per tile = UMMA M
 constexpr int BK = 32;           // K elements per pipeline stage (2 UMMA K-steps of 16)
 constexpr int STAGES = 4;
-constexpr int PREFETCH_AHEAD = 16;  // k-chunks (16 KB boxes) the L2 prefetch runs ahead of the loads
+constexpr int PREFETCH_AHEAD = 0;   // k-chunks an optional L2 prefetch cursor runs ahead of the loads (CB_TC_PREFETCH): measured
+                                   // HARMFUL (conv 10.5 -> 13.0 ms at 16): the extra TMA requests compete with the loads
 constexpr int N_EPI_WARPS = 8;   // two per TMEM lane quadrant (each takes half of the tile's columns)
 constexpr int NTHREADS = (N_EPI_WARPS + 2) * 32;   // 320
 
@@ -212,27 +213,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
         }
         if (overflow) atomicExch(q.range_flag, 1);
     } else if (warp == N_EPI_WARPS) {
-        // ============================ MMA issuer (one elected thread) =======================================================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_f16(BM, BN);
-            constexpr uint32_t A_STEP = 2 * BM;               // two k-groups per UMMA K-step, in 16-byte units
-            const uint32_t B_STEP = 2 * (uint32_t)BN;
-            uint32_t kit = 0, it = 0;
-            if (q.resident) mbar_wait(w_bar, 0);
-            for (int mt, nt; tiles.get((int)it, mt, nt); ++it) {
-                const uint32_t buf = it & 1, par = (it >> 1) & 1;
-                mbar_wait(&acc_empty[buf], par ^ 1);          // epilogue has drained this accumulator
+        // ============================ MMA issuer (whole warp runs the loop, one elected lane issues) =========================
+        const bool leader = elect_one();
+        const uint32_t idesc = make_idesc_f16(BM, BN);
+        constexpr uint32_t A_STEP = 2 * BM;               // two k-groups per UMMA K-step, in 16-byte units
+        const uint32_t B_STEP = 2 * (uint32_t)BN;
+        uint32_t kit = 0, it = 0;
+        if (q.resident) { if (leader) mbar_wait(w_bar, 0); __syncwarp(); }
+        for (int mt, nt; tiles.get((int)it, mt, nt); ++it) {
+            const uint32_t buf = it & 1, par = (it >> 1) & 1;
+            if (leader) mbar_wait(&acc_empty[buf], par ^ 1);          // epilogue has drained this accumulator
+            __syncwarp();
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * (uint32_t)BN;
+            for (int kc = 0; kc < q.k_chunks; ++kc, ++kit) {
+                const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
+                if (leader) mbar_wait(&full_bar[s], ph);
+                __syncwarp();
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * (uint32_t)BN;
-                for (int kc = 0; kc < q.k_chunks; ++kc, ++kit) {
-                    const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
-                    mbar_wait(&full_bar[s], ph);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
-                    const uint32_t sb = q.resident ? smem_u32(smem) + (uint32_t)kc * 2 * b_bytes : sa + 2 * a_bytes;
-                    const uint64_t dah = make_desc(sa, BM * 16, 128), dal = make_desc(sa + a_bytes, BM * 16, 128);
-                    const uint64_t dbh = make_desc(sb, BN * 16, 128);
-                    const uint64_t dbl = make_desc(sb + b_bytes, BN * 16, 128);
+                const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
+                const uint32_t sb = q.resident ? smem_u32(smem) + (uint32_t)kc * 2 * b_bytes : sa + 2 * a_bytes;
+                const uint64_t dah = make_desc(sa, BM * 16, 128), dal = make_desc(sa + a_bytes, BM * 16, 128);
+                const uint64_t dbh = make_desc(sb, BN * 16, 128);
+                const uint64_t dbl = make_desc(sb + b_bytes, BN * 16, 128);
+                if (leader) {
 #pragma unroll
                     for (int ks = 0; ks < BK / 16; ++ks) {
                         if (q.passes == 3) {                  // low-order products first (truncating accumulator)
@@ -245,60 +249,64 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
                     }
                     umma_commit(&empty_bar[s]);               // frees the stage once these MMAs retire
                 }
-                umma_commit(&acc_full[buf]);
             }
+            if (leader) umma_commit(&acc_full[buf]);
         }
+        __syncwarp();
     } else {
-        // ============================ loader: weight + activation images via cp.async.bulk ===================================
-        if (lane == 0) {
-            uint32_t kit = 0;
-            const int n0c = g.taps * g.a0_chunks_per_tap;     // k-chunks served by image a0
-            if (q.resident) {                                 // the CTA's n-tile of W: one contiguous image
-                const uint32_t chunk = 2 * b_bytes;
-                mbar_arrive_expect_tx(w_bar, (uint32_t)q.k_chunks * chunk);
-                const __half* wsrc = q.img + (size_t)tiles.nt_fixed * q.k_chunks * (2 * (size_t)BN * BK);
-                for (int kc = 0; kc < q.k_chunks; ++kc)
-                    bulk_g2s(smem + (size_t)kc * chunk, wsrc + (size_t)kc * (2 * (size_t)BN * BK), chunk, w_bar);
+        // ============================ loader: weight + activation images (TMA / cp.async.bulk) ==============================
+        const bool leader = elect_one();
+        uint32_t kit = 0;
+        const int n0c = g.taps * g.a0_chunks_per_tap;     // k-chunks served by image a0
+        if (q.resident && leader) {                       // the CTA's n-tile of W: one contiguous image
+            const uint32_t chunk = 2 * b_bytes;
+            mbar_arrive_expect_tx(w_bar, (uint32_t)q.k_chunks * chunk);
+            const __half* wsrc = q.img + (size_t)tiles.nt_fixed * q.k_chunks * (2 * (size_t)BN * BK);
+            for (int kc = 0; kc < q.k_chunks; ++kc)
+                bulk_g2s(smem + (size_t)kc * chunk, wsrc + (size_t)kc * (2 * (size_t)BN * BK), chunk, w_bar);
+        }
+        __syncwarp();
+        // A-side box of k-chunk kc of the CTA's it-th tile
+        auto coords = [&](int it_, int kc_, const CUtensorMap*& tm, int& row, int& plane) -> bool {
+            int mt, nt;
+            if (!tiles.get(it_, mt, nt)) return false;
+            const int to = mt / tiles_per_frame;
+            const long long b0 = (long long)(mt - to * tiles_per_frame) * BM;
+            if (kc_ < n0c) {
+                const int j = kc_ / g.a0_chunks_per_tap, cc = kc_ - j * g.a0_chunks_per_tap;
+                row = (int)(g.a0.row0 + ((long long)to * g.stride + j - g.left) * g.Bp + b0);
+                plane = g.a0_plane0 + cc * 4; tm = &q.tm_a0;
+            } else {
+                row = (int)(g.a1.row0 + (long long)to * g.Bp + b0);
+                plane = g.a1_plane0 + (kc_ - n0c) * 4; tm = &q.tm_a1;
             }
-            // A-side box of k-chunk kc of the CTA's it-th tile
-            auto coords = [&](int it_, int kc_, const CUtensorMap*& tm, int& row, int& plane) -> bool {
-                int mt, nt;
-                if (!tiles.get(it_, mt, nt)) return false;
-                const int to = mt / tiles_per_frame;
-                const long long b0 = (long long)(mt - to * tiles_per_frame) * BM;
-                if (kc_ < n0c) {
-                    const int j = kc_ / g.a0_chunks_per_tap, cc = kc_ - j * g.a0_chunks_per_tap;
-                    row = (int)(g.a0.row0 + ((long long)to * g.stride + j - g.left) * g.Bp + b0);
-                    plane = g.a0_plane0 + cc * 4; tm = &q.tm_a0;
-                } else {
-                    row = (int)(g.a1.row0 + (long long)to * g.Bp + b0);
-                    plane = g.a1_plane0 + (kc_ - n0c) * 4; tm = &q.tm_a1;
-                }
-                return true;
-            };
-            // The activation image is streamed from HBM once; with at most STAGES boxes in flight the ring cannot cover
-            // the DRAM latency, so every box is pulled into L2 PREFETCH_AHEAD chunks before it is loaded.
-            const CUtensorMap* tm; int row, plane;
-            int p_it = 0, p_kc = 0;                          // prefetch cursor
-            auto prefetch_next = [&]() {
-                if (p_it < 0) return;
-                if (coords(p_it, p_kc, tm, row, plane)) tma_img_prefetch(tm, row, plane); else { p_it = -1; return; }
-                if (++p_kc == q.k_chunks) { p_kc = 0; ++p_it; }
-            };
-            for (int d = 0; d < q.prefetch_ahead; ++d) prefetch_next();
-            for (int it = 0, mt, nt; tiles.get(it, mt, nt); ++it) {
-                const __half* wsrc = q.img + (size_t)nt * q.k_chunks * (2 * (size_t)BN * BK);
-                for (int kc = 0; kc < q.k_chunks; ++kc, ++kit) {
-                    const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
-                    if (q.prefetch_ahead) prefetch_next();
+            return true;
+        };
+        // The activation image is streamed from HBM once: every box is pulled into L2 prefetch_ahead chunks before it
+        // is loaded, so the STAGES-deep ring only has to cover the L2 latency.
+        const CUtensorMap* tm; int row, plane;
+        int p_it = 0, p_kc = 0;                          // prefetch cursor
+        auto prefetch_next = [&]() {
+            if (p_it < 0) return;
+            if (coords(p_it, p_kc, tm, row, plane)) { if (leader) tma_img_prefetch(tm, row, plane); } else { p_it = -1; return; }
+            if (++p_kc == q.k_chunks) { p_kc = 0; ++p_it; }
+        };
+        for (int d = 0; d < q.prefetch_ahead; ++d) prefetch_next();
+        for (int it = 0, mt, nt; tiles.get(it, mt, nt); ++it) {
+            const __half* wsrc = q.img + (size_t)nt * q.k_chunks * (2 * (size_t)BN * BK);
+            for (int kc = 0; kc < q.k_chunks; ++kc, ++kit) {
+                const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
+                if (q.prefetch_ahead) prefetch_next();
+                coords(it, kc, tm, row, plane);
+                uint8_t* st = ring + (size_t)s * stage_bytes;
+                if (leader) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
-                    uint8_t* st = ring + (size_t)s * stage_bytes;
                     mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-                    coords(it, kc, tm, row, plane);
                     tma_img_g2s(st, tm, row, plane, &full_bar[s]);
                     if (!q.resident)
                         bulk_g2s(st + 2 * a_bytes, wsrc + (size_t)kc * (2 * (size_t)BN * BK), 2 * b_bytes, &full_bar[s]);
                 }
+                __syncwarp();
             }
         }
     }

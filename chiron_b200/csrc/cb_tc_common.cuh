@@ -45,6 +45,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
+// One lane of a fully active warp.  The tcgen05 / TMA / mbarrier-commit instructions take their operands from UNIFORM
+// registers: when a whole role is wrapped in `if (lane == 0)` the compiler must treat every operand as divergent and
+// wraps each such instruction in a R2UR + ELECT + BRA.U.ANY "waterfall" loop (tens of cycles per MMA).  The role loops
+// are therefore executed by all 32 lanes (operands computed convergently -> uniform datapath) and only the issuing
+// instructions are predicated on the elected lane; waits are done by that lane, the others park at __syncwarp().
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
