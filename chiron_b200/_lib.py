@@ -35,6 +35,8 @@ SIGNATURES = {
                             c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "cb_basecall_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p]),
+    "cb_basecall_submit": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int]),
+    "cb_basecall_collect": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "cb_assemble_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "cb_launch_count": (c_longlong, [c_void_p]),

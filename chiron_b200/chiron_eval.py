@@ -8,13 +8,22 @@ DESIGN.md:
     chiron_eval.py:413-428,436, which rotates/duplicates segments of multi-batch reads -- SURVEY.md finding 6);
   * the per-model signal normalisation the shipped weights need is applied (SURVEY.md finding 4);
   * reads shard across ranks when launched under torchrun (RANK/WORLD_SIZE); no collective on the decode path.
+
+Host pipeline (replaces the 1 feeder + 6 decode threads + FIFO queue of chiron_eval.py:262-268,495-521):
+reader threads parse / normalise / window the next reads while the GPU works; batches go through the two-slot
+asynchronous C-ABI call (pinned staging, copy-in / compute / copy-out streams), so the copies and the host-side
+collation of batch i overlap the kernels of batch i+1; a writer thread formats and writes the output files.
 """
 from __future__ import annotations
 
 import argparse
+import collections
 import os
+import queue
 import sys
+import threading
 import time
+from concurrent.futures import ThreadPoolExecutor
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -141,34 +150,75 @@ def evaluation(flags=None, caller: Optional[Basecaller] = None) -> Dict[str, dic
                                          with_qs=with_qs)
         assembly_time = time.time() - st.start_time
         file_pre = os.path.splitext(st.name)[0]
-        write_output(bpreads, seq, [st.start_time, st.reading_time, basecall_time, assembly_time], file_pre,
-                     concise=flags.concise, suffix=flags.extension, q_score=qual, global_setting=flags)
+        write_q.put((bpreads, seq, [st.start_time, st.reading_time, basecall_time, assembly_time], file_pre, qual))
         summary[st.name] = {"windows": st.n, "bases": len(seq), "pos": pos}
 
-    def flush():
-        nonlocal pend_x, pend_len, pend_owner, pend_n
-        if pend_n == 0:
-            return
-        x = np.concatenate(pend_x, axis=0)
-        ln = np.concatenate(pend_len, axis=0)
-        bases, n_bases, prob, _ = caller.basecall_batch(x, ln, beam=beam)
+    # ---- writer thread: formatting and file I/O off the GPU-feeding thread ---------------------------------------------
+    write_q: "queue.Queue" = queue.Queue()
+    write_err: List[BaseException] = []
+
+    def writer():
+        while True:
+            item = write_q.get()
+            if item is None:
+                return
+            try:
+                bpreads, seq, times, file_pre, qual = item
+                write_output(bpreads, seq, times, file_pre, concise=flags.concise, suffix=flags.extension, q_score=qual,
+                             global_setting=flags)
+            except BaseException as e:            # surfaced after the join below
+                write_err.append(e)
+
+    writer_thread = threading.Thread(target=writer, name="chiron-writer", daemon=True)
+    writer_thread.start()
+
+    # ---- two batches in flight on the GPU (slots 0/1 of cb_basecall_submit) ----------------------------------------------
+    inflight = collections.deque()               # (ticket, owners) in submission order
+
+    def collect_oldest():
+        ticket, owners = inflight.popleft()
+        bases, n_bases, prob = caller.basecall_collect(ticket)
         off = 0
-        for st, first, cnt in pend_owner:
+        for st, first, cnt in owners:
             st.bases[first:first + cnt] = bases[off:off + cnt]
             st.n_bases[first:first + cnt] = n_bases[off:off + cnt]
             st.prob[first:first + cnt] = prob[off:off + cnt]
             st.filled += cnt
             off += cnt
-        pend_x, pend_len, pend_owner, pend_n = [], [], [], 0
         while open_reads and open_reads[0].filled == open_reads[0].n:
             finish(open_reads.pop(0))
 
-    for name in file_list:
-        start_time = time.time()
-        input_path = os.path.join(file_dir, name)
-        eval_data = read_data_for_eval(input_path, flags.start, seg_length=L, step=jump,
-                                       reverse_fast5=getattr(flags, "reverse_fast5", False), sig_norm=cfg.sig_norm)
-        st = _ReadState(name, eval_data.reads_n, T, start_time, time.time() - start_time)
+    next_slot = 0
+
+    def flush():
+        nonlocal pend_x, pend_len, pend_owner, pend_n, next_slot
+        if pend_n == 0:
+            return
+        x = np.concatenate(pend_x, axis=0)
+        ln = np.concatenate(pend_len, axis=0)
+        if len(inflight) == 2:                    # the slot about to be reused is the oldest batch
+            collect_oldest()
+        inflight.append((caller.basecall_submit(next_slot, x, ln, beam=beam), pend_owner))
+        next_slot ^= 1
+        pend_x, pend_len, pend_owner, pend_n = [], [], [], 0
+
+    # ---- reader threads: parse / normalise / window ahead of the GPU (results consumed in file order) -------------------
+    n_readers = getattr(flags, "threads", 0) or min(8, os.cpu_count() or 1)
+
+    def load(name):
+        t0 = time.time()
+        data = read_data_for_eval(os.path.join(file_dir, name), flags.start, seg_length=L, step=jump,
+                                  reverse_fast5=getattr(flags, "reverse_fast5", False), sig_norm=cfg.sig_norm)
+        return data, t0, time.time() - t0
+
+    pool = ThreadPoolExecutor(max_workers=n_readers, thread_name_prefix="chiron-reader")
+    lookahead = 2 * n_readers
+    futures = collections.deque(pool.submit(load, n) for n in file_list[:lookahead])
+    for idx, name in enumerate(file_list):
+        eval_data, start_time, reading_time = futures.popleft().result()
+        if idx + lookahead < len(file_list):
+            futures.append(pool.submit(load, file_list[idx + lookahead]))
+        st = _ReadState(name, eval_data.reads_n, T, start_time, reading_time)
         open_reads.append(st)
         i = 0
         if eval_data.reads_n == 0:
@@ -184,8 +234,15 @@ def evaluation(flags=None, caller: Optional[Basecaller] = None) -> Dict[str, dic
             if pend_n >= B:
                 flush()
     flush()
+    while inflight:
+        collect_oldest()
     while open_reads:                                            # reads with zero windows
         finish(open_reads.pop(0))
+    pool.shutdown(wait=True)
+    write_q.put(None)
+    writer_thread.join()
+    if write_err:
+        raise write_err[0]
     if own:
         caller.close()
     return summary

@@ -228,6 +228,17 @@ extern "C" int cb_destroy(cb_handle* h) {
     if (h->d_weights) cudaFree(h->d_weights);
     if (h->ws) cudaFree(h->ws);
     if (h->stage) cudaFree(h->stage);
+    for (int i = 0; i < 2; ++i) {
+        if (h->pipe[i].pin) cudaFreeHost(h->pipe[i].pin);
+        if (h->pipe[i].dev) cudaFree(h->pipe[i].dev);
+        if (h->pipe[i].h2d_done) cudaEventDestroy(h->pipe[i].h2d_done);
+        if (h->pipe[i].compute_done) cudaEventDestroy(h->pipe[i].compute_done);
+        if (h->pipe[i].d2h_done) cudaEventDestroy(h->pipe[i].d2h_done);
+    }
+    if (h->pipe_in) cudaStreamDestroy(h->pipe_in);
+    if (h->pipe_compute) cudaStreamDestroy(h->pipe_compute);
+    if (h->pipe_out) cudaStreamDestroy(h->pipe_out);
+    if (h->asm_stage) cudaFree(h->asm_stage);
     if (h->beam_ws) cudaFree(h->beam_ws);
     if (h->asm_ws) cudaFree(h->asm_ws);
     if (h->d_flag) cudaFree(h->d_flag);
@@ -492,6 +503,98 @@ extern "C" int cb_basecall_host(cb_handle* h, const float* x, const int32_t* seq
     return cb_tc_check_range(h, s);
 }
 
+// ---- two-slot asynchronous host pipeline -----------------------------------------------------------------------------
+static int pipe_init(cb_handle* h) {
+    if (h->pipe_compute) return CB_OK;
+    CB_CUDA(cudaStreamCreateWithFlags(&h->pipe_in, cudaStreamNonBlocking));
+    CB_CUDA(cudaStreamCreateWithFlags(&h->pipe_compute, cudaStreamNonBlocking));
+    CB_CUDA(cudaStreamCreateWithFlags(&h->pipe_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CB_CUDA(cudaEventCreateWithFlags(&h->pipe[i].h2d_done, cudaEventDisableTiming));
+        CB_CUDA(cudaEventCreateWithFlags(&h->pipe[i].compute_done, cudaEventDisableTiming));
+        CB_CUDA(cudaEventCreateWithFlags(&h->pipe[i].d2h_done, cudaEventDisableTiming));
+    }
+    return CB_OK;
+}
+
+struct PipeLayout {              // offsets into the pinned and the device buffer of a slot
+    size_t p_x, p_len, p_bases, p_nb, p_prob, p_total;
+    size_t d_x, d_in, d_len, d_nb, d_prob, d_lg, d_bases, d_total;
+};
+static PipeLayout pipe_layout(int B, int L, int T, int C) {
+    PipeLayout o;
+    const size_t sz_x = align_up((size_t)B * L * 4, 256), sz_i = align_up((size_t)B * 4, 256);
+    const size_t sz_lg = align_up((size_t)B * T * C * 4, 256), sz_b = align_up((size_t)B * T, 256);
+    o.p_x = 0; o.p_len = sz_x; o.p_bases = o.p_len + sz_i; o.p_nb = o.p_bases + sz_b; o.p_prob = o.p_nb + sz_i;
+    o.p_total = o.p_prob + sz_i;
+    o.d_x = 0; o.d_in = sz_x; o.d_len = o.d_in + sz_i; o.d_nb = o.d_len + sz_i; o.d_prob = o.d_nb + sz_i;
+    o.d_lg = o.d_prob + sz_i; o.d_bases = o.d_lg + sz_lg; o.d_total = o.d_bases + sz_b;
+    return o;
+}
+
+extern "C" int cb_basecall_submit(cb_handle* h, int slot, const float* x, const int32_t* seq_len_in, int B, int L,
+                                  int beam_width) {
+    if (!h || slot < 0 || slot > 1 || !x || !seq_len_in || B < 1 || L < 1 || beam_width < 0) { cb_set_error("cb_basecall_submit: bad arguments"); return CB_ERR_ARG; }
+    CB_CUDA(cudaSetDevice(h->device));
+    int rc = pipe_init(h);
+    if (rc != CB_OK) return rc;
+    cb_handle::PipeSlot& sl = h->pipe[slot];
+    if (sl.busy) { cb_set_error("cb_basecall_submit: slot %d has not been collected", slot); return CB_ERR_ARG; }
+    const int T = out_len_of(h->cfg, L), C = h->cfg.n_class;
+    const PipeLayout o = pipe_layout(B, L, T, C);
+    if (o.p_total > sl.pin_bytes) {
+        if (sl.pin) { cudaFreeHost(sl.pin); sl.pin = nullptr; sl.pin_bytes = 0; }
+        cudaError_t e = cudaMallocHost(&sl.pin, o.p_total);
+        if (e != cudaSuccess) { cb_set_error("pinned staging cudaMallocHost(%zu bytes): %s", o.p_total, cudaGetErrorString(e)); return CB_ERR_NOMEM; }
+        sl.pin_bytes = o.p_total;
+    }
+    if (o.d_total > sl.dev_bytes) {
+        if (sl.dev) { cudaFree(sl.dev); sl.dev = nullptr; sl.dev_bytes = 0; }
+        cudaError_t e = cudaMalloc(&sl.dev, o.d_total);
+        if (e != cudaSuccess) { cb_set_error("pipeline staging cudaMalloc(%zu bytes): %s", o.d_total, cudaGetErrorString(e)); return CB_ERR_NOMEM; }
+        sl.dev_bytes = o.d_total;
+    }
+    char* pin = (char*)sl.pin; char* dev = (char*)sl.dev;
+    memcpy(pin + o.p_x, x, (size_t)B * L * 4);
+    memcpy(pin + o.p_len, seq_len_in, (size_t)B * 4);
+    sl.B = B; sl.L = L; sl.T = T;
+    CB_CUDA(cudaMemcpyAsync(dev + o.d_x, pin + o.p_x, (size_t)B * L * 4, cudaMemcpyHostToDevice, h->pipe_in));
+    CB_CUDA(cudaMemcpyAsync(dev + o.d_in, pin + o.p_len, (size_t)B * 4, cudaMemcpyHostToDevice, h->pipe_in));
+    CB_CUDA(cudaEventRecord(sl.h2d_done, h->pipe_in));
+    cudaStream_t s = h->pipe_compute;
+    CB_CUDA(cudaStreamWaitEvent(s, sl.h2d_done, 0));
+    int32_t* d_len = (int32_t*)(dev + o.d_len);
+    float* d_lg = (float*)(dev + o.d_lg);
+    if ((rc = cb_launch_seq_len(h, (const int32_t*)(dev + o.d_in), B, L, T, d_len, s)) != CB_OK) return rc;
+    if ((rc = cb_forward(h, (const float*)(dev + o.d_x), d_len, B, L, d_lg, (float*)(dev + o.d_prob), s)) != CB_OK) return rc;
+    if (beam_width == 0) rc = cb_launch_greedy(h, d_lg, d_len, B, T, (int8_t*)(dev + o.d_bases), (int32_t*)(dev + o.d_nb), s);
+    else rc = cb_launch_beam(h, d_lg, d_len, B, T, beam_width, (int8_t*)(dev + o.d_bases), (int32_t*)(dev + o.d_nb), s);
+    if (rc != CB_OK) return rc;
+    CB_CUDA(cudaEventRecord(sl.compute_done, s));
+    CB_CUDA(cudaStreamWaitEvent(h->pipe_out, sl.compute_done, 0));
+    CB_CUDA(cudaMemcpyAsync(pin + o.p_bases, dev + o.d_bases, (size_t)B * T, cudaMemcpyDeviceToHost, h->pipe_out));
+    CB_CUDA(cudaMemcpyAsync(pin + o.p_nb, dev + o.d_nb, (size_t)B * 4, cudaMemcpyDeviceToHost, h->pipe_out));
+    CB_CUDA(cudaMemcpyAsync(pin + o.p_prob, dev + o.d_prob, (size_t)B * 4, cudaMemcpyDeviceToHost, h->pipe_out));
+    CB_CUDA(cudaEventRecord(sl.d2h_done, h->pipe_out));
+    sl.busy = 1;
+    return CB_OK;
+}
+
+extern "C" int cb_basecall_collect(cb_handle* h, int slot, int8_t* bases, int32_t* n_bases, float* path_prob) {
+    if (!h || slot < 0 || slot > 1 || !bases || !n_bases) { cb_set_error("cb_basecall_collect: bad arguments"); return CB_ERR_ARG; }
+    cb_handle::PipeSlot& sl = h->pipe[slot];
+    if (!sl.busy) { cb_set_error("cb_basecall_collect: slot %d holds no batch", slot); return CB_ERR_ARG; }
+    CB_CUDA(cudaSetDevice(h->device));
+    sl.busy = 0;
+    CB_CUDA(cudaEventSynchronize(sl.d2h_done));
+    const PipeLayout o = pipe_layout(sl.B, sl.L, sl.T, h->cfg.n_class);
+    const char* pin = (const char*)sl.pin;
+    memcpy(bases, pin + o.p_bases, (size_t)sl.B * sl.T);
+    memcpy(n_bases, pin + o.p_nb, (size_t)sl.B * 4);
+    if (path_prob) memcpy(path_prob, pin + o.p_prob, (size_t)sl.B * 4);
+    return cb_tc_check_range(h, h->pipe_out);
+}
+
 extern "C" int cb_check_status(cb_handle* h, void* stream) {
     if (!h) { cb_set_error("cb_check_status: bad arguments"); return CB_ERR_ARG; }
     CB_CUDA(cudaSetDevice(h->device));
@@ -506,8 +609,14 @@ extern "C" int cb_assemble_host(cb_handle* h, const int8_t* bases, const int32_t
     CB_CUDA(cudaSetDevice(h->device));
     const size_t sz_b = align_up((size_t)n_windows * T + 1, 256), sz_i = align_up((size_t)n_windows * 4 + 4, 256);
     const size_t sz_c = align_up((size_t)max_len + 1, 256);
-    char* buf = nullptr;
-    CB_CUDA(cudaMalloc(&buf, sz_b + 3 * sz_i + 2 * sz_c + 256));
+    const size_t need = sz_b + 3 * sz_i + 2 * sz_c + 256;
+    if (need > h->asm_stage_bytes) {            // grow-only: a cudaFree per read would synchronise the whole device
+        if (h->asm_stage) { cudaFree(h->asm_stage); h->asm_stage = nullptr; h->asm_stage_bytes = 0; }
+        cudaError_t em = cudaMalloc(&h->asm_stage, need + need / 2);
+        if (em != cudaSuccess) { cb_set_error("cb_assemble_host: cudaMalloc(%zu bytes): %s", need + need / 2, cudaGetErrorString(em)); return CB_ERR_NOMEM; }
+        h->asm_stage_bytes = need + need / 2;
+    }
+    char* buf = (char*)h->asm_stage;
     char* p = buf;
     int8_t* d_bases = (int8_t*)p; p += sz_b;
     int32_t* d_nb = (int32_t*)p; p += sz_i;
@@ -534,7 +643,6 @@ extern "C" int cb_assemble_host(cb_handle* h, const int8_t* bases, const int32_t
         if (e == cudaSuccess && qual && max_len > 0) e = cudaMemcpyAsync(qual, d_qual, max_len, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     }
-    cudaFree(buf);
     if (e != cudaSuccess) { cb_set_error("cb_assemble_host: %s", cudaGetErrorString(e)); return CB_ERR_CUDA; }
     return rc;
 }

@@ -116,6 +116,14 @@ struct cb_handle {
     float *act[3]; float* pre; float* lstm_out[2];
     int ws_B, ws_L;
     void* stage; size_t stage_bytes;   // device staging of the host-buffer API
+    struct PipeSlot {                  // cb_basecall_submit / cb_basecall_collect
+        void* pin; size_t pin_bytes;   // pinned host staging: x, seq_len | bases, n_bases, path_prob
+        void* dev; size_t dev_bytes;   // device: x, seq_len_in, seq_len_out, n_bases, path_prob, logits, bases
+        cudaEvent_t h2d_done, compute_done, d2h_done;
+        int B, L, T, busy;
+    } pipe[2];
+    cudaStream_t pipe_in, pipe_compute, pipe_out;
+    void* asm_stage; size_t asm_stage_bytes;   // device staging of cb_assemble_host (grow-only: no cudaFree in the read loop)
     const float* fea;                  // CNN feature of the last forward (debug fetch)
     void* tc;                          // tensor-core path state (cb_tc.cu)
     void* lstm_tc;                     // tensor-core recurrence state (cb_lstm_tc.cu)

@@ -99,6 +99,26 @@ class Basecaller:
                                              _ptr(n_bases), _ptr(prob), _ptr(logits)), "cb_basecall_host")
         return bases, n_bases, prob, logits
 
+    def basecall_submit(self, slot: int, x: np.ndarray, seq_len: np.ndarray, beam: int = 0):
+        """Asynchronous two-slot form of ``basecall_batch`` (cb_basecall_submit): returns as soon as the batch sits in
+        the slot's pinned staging buffer and its copies/kernels are enqueued.  Returns the ticket ``collect`` needs."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        seq_len = np.ascontiguousarray(seq_len, dtype=np.int32)
+        B, L = x.shape
+        _lib.check(self.lib.cb_basecall_submit(self.h, int(slot), _ptr(x), _ptr(seq_len), B, L, int(beam)),
+                   "cb_basecall_submit")
+        return int(slot), B, self.out_len(L)
+
+    def basecall_collect(self, ticket):
+        """Wait for a submitted batch: (bases[B,T] int8, n_bases[B], path_prob[B])."""
+        slot, B, T = ticket
+        bases = np.zeros((B, T), dtype=np.int8)
+        n_bases = np.zeros(B, dtype=np.int32)
+        prob = np.zeros(B, dtype=np.float32)
+        _lib.check(self.lib.cb_basecall_collect(self.h, slot, _ptr(bases), _ptr(n_bases), _ptr(prob)),
+                   "cb_basecall_collect")
+        return bases, n_bases, prob
+
     def assemble(self, bases: np.ndarray, n_bases: np.ndarray, path_prob: Optional[np.ndarray], jump: int, L: int,
                  kernel: Optional[str] = None, with_qs: bool = True) -> Tuple[str, Optional[str], np.ndarray]:
         """simple_assembly(_qs) + argmax + qs() for one read; windows in true order.  Returns (sequence, quality

@@ -100,6 +100,16 @@ int cb_assemble(cb_handle* h, const int8_t* bases, const int32_t* n_bases, const
 int cb_basecall_host(cb_handle* h, const float* x, const int32_t* seq_len_in, int B, int L, int beam_width,
                      int8_t* bases, int32_t* n_bases, float* path_prob, float* logits);
 
+/* Two-slot asynchronous form of cb_basecall_host (replaces the feeder thread + FIFO queue + decode
+ * threads of chiron_eval.py:262-268,495-521).  cb_basecall_submit copies the batch into the slot's PINNED staging buffer
+ * (the caller's arrays may be reused as soon as it returns), then enqueues H2D on a copy-in stream, seq_len + forward +
+ * decode on the compute stream and D2H into pinned memory on a copy-out stream, chained by events: the copies of batch
+ * i+1 and the host work of the caller overlap the kernels of batch i.  cb_basecall_collect waits for that slot, copies
+ * bases[B,T] / n_bases[B] / path_prob[B] (may be NULL) out and reports deferred errors.  slot is 0 or 1; a slot must be
+ * collected before it is submitted again; batches complete in submission order. */
+int cb_basecall_submit(cb_handle* h, int slot, const float* x, const int32_t* seq_len_in, int B, int L, int beam_width);
+int cb_basecall_collect(cb_handle* h, int slot, int8_t* bases, int32_t* n_bases, float* path_prob);
+
 /* Host-buffer form of cb_assemble for one read (synchronous). */
 int cb_assemble_host(cb_handle* h, const int8_t* bases, const int32_t* n_bases, const float* path_prob,
                      int n_windows, int T, int jump, int L, int kernel,

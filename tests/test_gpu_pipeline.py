@@ -66,3 +66,30 @@ def test_batch_composition_does_not_change_results(tmp_path):
         chiron_eval.run(flags)
         outs.append(_read(os.path.join(out, "result", "read3.fastq")))
     assert outs[0] == outs[1]
+
+
+def test_two_slot_async_pipeline_matches_synchronous_call(dna_model):
+    """cb_basecall_submit / cb_basecall_collect (pinned staging, copy-in / compute / copy-out streams, two batches in
+    flight) return exactly what the synchronous cb_basecall_host returns, in submission order, for batches of different
+    sizes (the staging buffers and the workspace grow while a batch is in flight)."""
+    import numpy as np
+    from chiron_b200.engine import Basecaller
+    from oracle import chiron_oracle as O
+    cfg, t, _ = dna_model
+    sig = O.read_signal_text(os.path.join(GOLDEN, "DNA", "raw", "read1.signal"))
+    x, lens = O.make_windows(O.normalize_signal(sig, cfg.sig_norm), 300, 290)
+    cuts = [(0, 40), (40, 150), (150, 151), (151, len(x))]
+    bc = Basecaller("DNA_default", device=0, precision="fp32")
+    want = [bc.basecall_batch(x[a:b], lens[a:b], beam=0)[:3] for a, b in cuts]
+    got, inflight = [], []
+    for i, (a, b) in enumerate(cuts):
+        if len(inflight) == 2:
+            got.append(bc.basecall_collect(inflight.pop(0)))
+        inflight.append(bc.basecall_submit(i & 1, x[a:b], lens[a:b], beam=0))
+    while inflight:
+        got.append(bc.basecall_collect(inflight.pop(0)))
+    for (wb, wn, wp), (gb, gn, gp) in zip(want, got):
+        assert np.array_equal(wb, gb) and np.array_equal(wn, gn) and np.array_equal(wp, gp)
+    with pytest.raises(Exception):
+        bc.basecall_collect((0, 1, bc.out_len(300)))          # empty slot
+    bc.close()

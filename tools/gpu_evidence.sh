@@ -1,14 +1,16 @@
 #!/bin/bash
 # Round evidence pass (run under gpurun on one B200): GPU tests, bench arms, ncu launch list and full captures.
-# Usage: tools/gpu_evidence.sh <tag>   -> gpurun_out/<tag>/
+# Usage: tools/gpu_evidence.sh <tag>   -> gpurun_out/<tag>/   (summarise here with tools/ncu_summary.py / ncu_traffic.py)
 tag=${1:-r01}
 out=gpurun_out/$tag
 mkdir -p $out
+python tools/box_speed.py > $out/box_speed.txt 2>&1; cat $out/box_speed.txt
 timeout 900 python -m pytest tests -m gpu -x -q > $out/pytest_gpu.txt 2>&1; tail -2 $out/pytest_gpu.txt
 timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $out/smoke.txt 2>&1; tail -1 $out/smoke.txt
 timeout 400 python bench.py > $out/bench_tc.json 2> $out/bench_tc.err; cat $out/bench_tc.json | cut -c1-400
 timeout 400 python bench.py --precision fp32 --no-cpu-baseline --steps 5 > $out/bench_fp32.json 2> $out/bench_fp32.err
 timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > $out/bench_reference.json 2> $out/bench_reference.err
+timeout 600 python tools/bench_configs.py tc > $out/configs_tc.json 2> $out/configs_tc.err
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/bench_under_ncu.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 12 -c 12 -f -o $out/prof_gemm \
