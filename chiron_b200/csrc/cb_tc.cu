@@ -43,6 +43,8 @@ constexpr int NTHREADS = (N_EPI_WARPS + 2) * 32;   // 320
 
 struct TcLayer {                 // one prepared weight image
     __half* img;                 // [n_tiles][k_chunks][2 (hi,lo)][4 k-groups][BN rows][8]
+    __half* img2;                // CTA-pair form: [n_tiles][k_chunks][2 (cta)][2 (hi,lo)][4 k-groups][BN/2 rows][8]
+    CUtensorMap tm_w2;           // img2 as 2 KB rows (TMA view: a CTA's chunk of a stage = BN/32 rows)
     int K, Kpad, N, BN, n_tiles, k_chunks;
     float out_scale;             // 2^-s, undoes the power-of-two prescale of the weights
 };
@@ -56,6 +58,7 @@ struct TcState {
 
 struct TcParams {
     CUtensorMap tm_a0, tm_a1;    // TMA views of the operand images a0 / a1 (see make_img_map)
+    CUtensorMap tm_w;            // CTA-pair kernel: TMA view of the weight image
     TcGemm g;
     const __half* img;
     int BN, n_tiles, k_chunks, m_tiles;
@@ -66,34 +69,76 @@ struct TcParams {
     int* range_flag;
 };
 
-// Which (m-tile, n-tile) a CTA works on in its i-th iteration.  Streaming mode: tiles round-robin over the CTAs.
-// Resident mode: n-tile = blockIdx.x % n_tiles for the whole launch, m-tiles round-robin over the CTAs sharing it.
+// Which (m-unit, n-tile) a scheduling unit (a CTA, or a CTA pair) works on in its i-th iteration.  Streaming mode: work
+// items round-robin over the units.  Resident mode: n-tile = idx % n_tiles for the whole launch, m-units round-robin over
+// the units sharing it.  An m-unit is one 128-row tile (one CTA) or two consecutive ones (CTA pair, M = 256).
 struct TileIter {
-    int resident, n_tiles, m_tiles, total, first, step, nt_fixed;
-    __device__ TileIter(const TcParams& q) {
-        resident = q.resident; n_tiles = q.n_tiles; m_tiles = q.m_tiles; total = q.m_tiles * q.n_tiles;
+    int resident, n_tiles, m_units, total, first, step, nt_fixed;
+    __device__ TileIter(const TcParams& q, int idx, int cnt, int m_units_) {
+        resident = q.resident; n_tiles = q.n_tiles; m_units = m_units_; total = m_units * q.n_tiles;
         if (resident) {
-            nt_fixed = blockIdx.x % n_tiles;
-            first = blockIdx.x / n_tiles;
-            step = ((int)gridDim.x - nt_fixed + n_tiles - 1) / n_tiles;
-        } else { nt_fixed = 0; first = blockIdx.x; step = gridDim.x; }
+            nt_fixed = idx % n_tiles;
+            first = idx / n_tiles;
+            step = (cnt - nt_fixed + n_tiles - 1) / n_tiles;
+        } else { nt_fixed = 0; first = idx; step = cnt; }
     }
-    __device__ __forceinline__ bool get(int i, int& mt, int& nt) const {
+    __device__ __forceinline__ bool get(int i, int& mu, int& nt) const {
         const int v = first + i * step;
-        if (resident) { mt = v; nt = nt_fixed; return v < m_tiles; }
-        mt = v / n_tiles; nt = v - mt * n_tiles; return v < total;
+        if (resident) { mu = v; nt = nt_fixed; return v < m_units; }
+        mu = v / n_tiles; nt = v - mu * n_tiles; return v < total;
     }
 };
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-// shared memory: STAGES x { A_hi[4][128][8], A_lo, B_hi[4][BN][8], B_lo } halfs, then the barriers.
+// ---- PTX of the two flavours: NC = 1 (one CTA per tile) and NC = 2 (CTA pair, tcgen05 cta_group::2) -------------------------
+template <int NC>
+__device__ __forceinline__ void umma_f16_nc(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    if constexpr (NC == 1) {
+        umma_f16(d_tmem, a_desc, b_desc, idesc, acc);
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+            : "memory");
+    }
+}
+// MMA completion -> mbarrier; the pair form arrives on the barrier at the same offset in BOTH CTAs
+template <int NC>
+__device__ __forceinline__ void umma_commit_nc(uint64_t* bar) {
+    if constexpr (NC == 1) {
+        umma_commit(bar);
+    } else {
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                         smem_u32(bar)),
+                     "h"((uint16_t)3)
+                     : "memory");
+    }
+}
+
 // one box {256 x u64, 4 planes, hi|lo} = 16 KB of the image -> [hi|lo][4][128 rows][16 B] in shared memory
 __device__ __forceinline__ void tma_img_g2s(void* dst, const CUtensorMap* tm, int row, int plane, uint64_t* bar) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
             smem_u32(dst)),
         "l"(reinterpret_cast<uint64_t>(tm)), "r"(row * 2), "r"(plane), "r"(0), "r"(smem_u32(bar))
+        : "memory");
+}
+// CTA-pair forms: data into this CTA's shared memory, completion bytes onto the LEADER CTA's barrier (cluster address)
+__device__ __forceinline__ void tma_img_g2s_pair(void* dst, const CUtensorMap* tm, int row, int plane, uint32_t bar_cluster) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(row * 2), "r"(plane), "r"(0), "r"(bar_cluster)
+        : "memory");
+}
+__device__ __forceinline__ void tma_w_g2s_pair(void* dst, const CUtensorMap* tm, int row, uint32_t bar_cluster) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(0), "r"(row), "r"(bar_cluster)
         : "memory");
 }
 
@@ -103,41 +148,58 @@ __device__ __forceinline__ void tma_img_prefetch(const CUtensorMap* tm, int row,
                  : "memory");
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams q) {
+// shared memory: STAGES x { A_hi[4][128][8], A_lo, B_hi[4][BNL][8], B_lo } halfs (BNL = BN / NC rows of the B tile live in
+// this CTA), then the barriers; resident mode: k_chunks x {B_hi, B_lo} first, stages hold A only.
+template <int NC>
+__device__ __forceinline__ void gemm_tc_body(const TcParams& q) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const TcGemm& g = q.g;
-    const int BN = q.BN;
+    const int BN = q.BN, BNL = q.BN / NC;
     constexpr uint32_t a_bytes = BM * BK * 2;             // one of hi / lo
-    const uint32_t b_bytes = (uint32_t)BN * BK * 2;
-    // streaming: STAGES x {A_hi, A_lo, B_hi, B_lo};  resident: k_chunks x {B_hi, B_lo} then STAGES x {A_hi, A_lo}
+    const uint32_t b_bytes = (uint32_t)BNL * BK * 2;
     const uint32_t stage_bytes = q.resident ? 2 * a_bytes : 2 * a_bytes + 2 * b_bytes;
     const uint32_t res_bytes = q.resident ? (uint32_t)q.k_chunks * 2 * b_bytes : 0;
     uint8_t* ring = smem + res_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)STAGES * stage_bytes);
-    uint64_t* full_bar = bars;                            // [STAGES]  operands landed
+    uint64_t* full_bar = bars;                            // [STAGES]  operands landed (pair: in BOTH CTAs; leader's barrier)
     uint64_t* empty_bar = bars + STAGES;                  // [STAGES]  MMAs that read the stage retired
     uint64_t* acc_full = bars + 2 * STAGES;               // [2]       accumulator ready for the epilogue
-    uint64_t* acc_empty = bars + 2 * STAGES + 2;          // [2]       accumulator drained
+    uint64_t* acc_empty = bars + 2 * STAGES + 2;          // [2]       accumulator drained (pair: by both CTAs; leader's)
     uint64_t* w_bar = bars + 2 * STAGES + 4;              //           resident weights landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const TileIter tiles(q);
+    const uint32_t rank = NC == 2 ? cluster_ctarank() : 0;            // pair: rank 0 = leader (issues the MMAs)
+    const TileIter tiles(q, (int)blockIdx.x / NC, (int)gridDim.x / NC, q.m_tiles / NC);
     const int tiles_per_frame = g.Bp / BM;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], N_EPI_WARPS * 32); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], NC * N_EPI_WARPS); }
         mbar_init(w_bar, 1);
         fence_barrier_init();
+        if (q.resident) {                                 // this CTA's part of its n-tile of W: one contiguous image
+            const uint32_t chunk = 2 * b_bytes;
+            mbar_arrive_expect_tx(w_bar, (uint32_t)q.k_chunks * chunk);
+            const int nt = tiles.nt_fixed;
+            for (int kc = 0; kc < q.k_chunks; ++kc)
+                bulk_g2s(smem + (size_t)kc * chunk, q.img + (((size_t)nt * q.k_chunks + kc) * NC + rank) * (chunk / 2), chunk, w_bar);
+            mbar_wait(w_bar, 0);
+        }
     }
     if (warp == N_EPI_WARPS) {                            // MMA warp owns the TMEM allocation (all 512 columns)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if constexpr (NC == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if constexpr (NC == 2) cluster_sync_all();            // both CTAs' barriers, weights and TMEM exist before any remote signal
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < N_EPI_WARPS) {
@@ -145,9 +207,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
         const int quad = warp & 3, chalf = warp >> 2;     // TMEM lane quadrant, which half of the tile's columns
         const int first = ((BN / 16 + 1) / 2) * 16;       // BN is a multiple of 16; the two column halves are 16-col aligned
         const int cbeg = chalf ? first : 0, cend = chalf ? BN : first;
+        uint32_t acc_empty_leader[2];
+        for (int b = 0; b < 2; ++b)
+            acc_empty_leader[b] = NC == 2 ? mapa_shared(smem_u32(&acc_empty[b]), 0) : smem_u32(&acc_empty[b]);
         uint32_t it = 0;
         bool overflow = false;
-        for (int mt, nt; tiles.get((int)it, mt, nt); ++it) {
+        for (int mu, nt; tiles.get((int)it, mu, nt); ++it) {
+            const int mt = mu * NC + (int)rank;
             const uint32_t buf = it & 1, par = (it >> 1) & 1;
             mbar_wait(&acc_full[buf], par);
             tc_fence_after();
@@ -209,67 +275,66 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
                 }
             }
             tc_fence_before();
-            mbar_arrive(&acc_empty[buf]);
+            __syncwarp();
+            if (lane == 0) {                              // one arrival per epilogue warp (pair: on the leader's barrier)
+                if constexpr (NC == 1) mbar_arrive(&acc_empty[buf]); else mbar_arrive_cluster(acc_empty_leader[buf]);
+            }
         }
         if (overflow) atomicExch(q.range_flag, 1);
     } else if (warp == N_EPI_WARPS) {
-        // ============================ MMA issuer (whole warp runs the loop, one elected lane issues) =========================
+        // ============================ MMA issuer (whole warp runs the loop, one elected lane issues; pair: leader CTA) ======
         const bool leader = elect_one();
-        const uint32_t idesc = make_idesc_f16(BM, BN);
+        const uint32_t idesc = make_idesc_f16(BM * NC, BN);
         constexpr uint32_t A_STEP = 2 * BM;               // two k-groups per UMMA K-step, in 16-byte units
-        const uint32_t B_STEP = 2 * (uint32_t)BN;
+        const uint32_t B_STEP = 2 * (uint32_t)BNL;
         uint32_t kit = 0, it = 0;
-        if (q.resident) { if (leader) mbar_wait(w_bar, 0); __syncwarp(); }
-        for (int mt, nt; tiles.get((int)it, mt, nt); ++it) {
-            const uint32_t buf = it & 1, par = (it >> 1) & 1;
-            if (leader) mbar_wait(&acc_empty[buf], par ^ 1);          // epilogue has drained this accumulator
-            __syncwarp();
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + buf * (uint32_t)BN;
-            for (int kc = 0; kc < q.k_chunks; ++kc, ++kit) {
-                const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
-                if (leader) mbar_wait(&full_bar[s], ph);
+        if (rank == 0) {
+            for (int mu, nt; tiles.get((int)it, mu, nt); ++it) {
+                const uint32_t buf = it & 1, par = (it >> 1) & 1;
+                if (leader) {                             // the epilogue(s) have drained this accumulator
+                    if constexpr (NC == 1) mbar_wait(&acc_empty[buf], par ^ 1); else mbar_wait_cluster(&acc_empty[buf], par ^ 1);
+                }
                 __syncwarp();
                 tc_fence_after();
-                const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
-                const uint32_t sb = q.resident ? smem_u32(smem) + (uint32_t)kc * 2 * b_bytes : sa + 2 * a_bytes;
-                const uint64_t dah = make_desc(sa, BM * 16, 128), dal = make_desc(sa + a_bytes, BM * 16, 128);
-                const uint64_t dbh = make_desc(sb, BN * 16, 128);
-                const uint64_t dbl = make_desc(sb + b_bytes, BN * 16, 128);
-                if (leader) {
+                const uint32_t d_tmem = tmem_base + buf * (uint32_t)BN;
+                for (int kc = 0; kc < q.k_chunks; ++kc, ++kit) {
+                    const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
+                    if (leader) mbar_wait(&full_bar[s], ph);
+                    __syncwarp();
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
+                    const uint32_t sb = q.resident ? smem_u32(smem) + (uint32_t)kc * 2 * b_bytes : sa + 2 * a_bytes;
+                    const uint64_t dah = make_desc(sa, BM * 16, 128), dal = make_desc(sa + a_bytes, BM * 16, 128);
+                    const uint64_t dbh = make_desc(sb, BNL * 16, 128);
+                    const uint64_t dbl = make_desc(sb + b_bytes, BNL * 16, 128);
+                    if (leader) {
 #pragma unroll
-                    for (int ks = 0; ks < BK / 16; ++ks) {
-                        if (q.passes == 3) {                  // low-order products first (truncating accumulator)
-                            umma_f16(d_tmem, dah + ks * A_STEP, dbl + ks * B_STEP, idesc, (kc | ks) != 0);
-                            umma_f16(d_tmem, dal + ks * A_STEP, dbh + ks * B_STEP, idesc, 1);
-                            umma_f16(d_tmem, dah + ks * A_STEP, dbh + ks * B_STEP, idesc, 1);
-                        } else {
-                            umma_f16(d_tmem, dah + ks * A_STEP, dbh + ks * B_STEP, idesc, (kc | ks) != 0);
+                        for (int ks = 0; ks < BK / 16; ++ks) {
+                            if (q.passes == 3) {              // low-order products first (truncating accumulator)
+                                umma_f16_nc<NC>(d_tmem, dah + ks * A_STEP, dbl + ks * B_STEP, idesc, (kc | ks) != 0);
+                                umma_f16_nc<NC>(d_tmem, dal + ks * A_STEP, dbh + ks * B_STEP, idesc, 1);
+                                umma_f16_nc<NC>(d_tmem, dah + ks * A_STEP, dbh + ks * B_STEP, idesc, 1);
+                            } else {
+                                umma_f16_nc<NC>(d_tmem, dah + ks * A_STEP, dbh + ks * B_STEP, idesc, (kc | ks) != 0);
+                            }
                         }
+                        umma_commit_nc<NC>(&empty_bar[s]);    // frees the stage (in both CTAs) once these MMAs retire
                     }
-                    umma_commit(&empty_bar[s]);               // frees the stage once these MMAs retire
                 }
+                if (leader) umma_commit_nc<NC>(&acc_full[buf]);
             }
-            if (leader) umma_commit(&acc_full[buf]);
         }
         __syncwarp();
     } else {
-        // ============================ loader: weight + activation images (TMA / cp.async.bulk) ==============================
+        // ============================ loader: weight + activation images (TMA) ================================================
         const bool leader = elect_one();
         uint32_t kit = 0;
         const int n0c = g.taps * g.a0_chunks_per_tap;     // k-chunks served by image a0
-        if (q.resident && leader) {                       // the CTA's n-tile of W: one contiguous image
-            const uint32_t chunk = 2 * b_bytes;
-            mbar_arrive_expect_tx(w_bar, (uint32_t)q.k_chunks * chunk);
-            const __half* wsrc = q.img + (size_t)tiles.nt_fixed * q.k_chunks * (2 * (size_t)BN * BK);
-            for (int kc = 0; kc < q.k_chunks; ++kc)
-                bulk_g2s(smem + (size_t)kc * chunk, wsrc + (size_t)kc * (2 * (size_t)BN * BK), chunk, w_bar);
-        }
-        __syncwarp();
-        // A-side box of k-chunk kc of the CTA's it-th tile
+        // A-side box of k-chunk kc of this CTA's tile in the unit's it-th iteration
         auto coords = [&](int it_, int kc_, const CUtensorMap*& tm, int& row, int& plane) -> bool {
-            int mt, nt;
-            if (!tiles.get(it_, mt, nt)) return false;
+            int mu, nt;
+            if (!tiles.get(it_, mu, nt)) return false;
+            const int mt = mu * NC + (int)rank;
             const int to = mt / tiles_per_frame;
             const long long b0 = (long long)(mt - to * tiles_per_frame) * BM;
             if (kc_ < n0c) {
@@ -282,29 +347,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
             }
             return true;
         };
-        // The activation image is streamed from HBM once: every box is pulled into L2 prefetch_ahead chunks before it
-        // is loaded, so the STAGES-deep ring only has to cover the L2 latency.
         const CUtensorMap* tm; int row, plane;
-        int p_it = 0, p_kc = 0;                          // prefetch cursor
+        int p_it = 0, p_kc = 0;                          // optional L2 prefetch cursor (off by default, see PREFETCH_AHEAD)
         auto prefetch_next = [&]() {
             if (p_it < 0) return;
             if (coords(p_it, p_kc, tm, row, plane)) { if (leader) tma_img_prefetch(tm, row, plane); } else { p_it = -1; return; }
             if (++p_kc == q.k_chunks) { p_kc = 0; ++p_it; }
         };
         for (int d = 0; d < q.prefetch_ahead; ++d) prefetch_next();
-        for (int it = 0, mt, nt; tiles.get(it, mt, nt); ++it) {
-            const __half* wsrc = q.img + (size_t)nt * q.k_chunks * (2 * (size_t)BN * BK);
+        for (int it = 0, mu, nt; tiles.get(it, mu, nt); ++it) {
             for (int kc = 0; kc < q.k_chunks; ++kc, ++kit) {
                 const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
                 if (q.prefetch_ahead) prefetch_next();
                 coords(it, kc, tm, row, plane);
                 uint8_t* st = ring + (size_t)s * stage_bytes;
-                if (leader) {
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-                    tma_img_g2s(st, tm, row, plane, &full_bar[s]);
-                    if (!q.resident)
-                        bulk_g2s(st + 2 * a_bytes, wsrc + (size_t)kc * (2 * (size_t)BN * BK), 2 * b_bytes, &full_bar[s]);
+                if constexpr (NC == 1) {
+                    const __half* wsrc = q.img + ((size_t)nt * q.k_chunks + kc) * (2 * (size_t)BN * BK);
+                    if (leader) {
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+                        tma_img_g2s(st, tm, row, plane, &full_bar[s]);
+                        if (!q.resident) bulk_g2s(st + 2 * a_bytes, wsrc, 2 * b_bytes, &full_bar[s]);
+                    }
+                } else {
+                    // both CTAs fill their own stage; every byte is counted on the leader's barrier
+                    const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[s]), 0);
+                    const int wrow = (((nt * q.k_chunks + kc) * 2 + (int)rank) * BN) / 32;      // 2 KB rows of the weight image
+                    if (leader) {
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * stage_bytes);
+                        tma_img_g2s_pair(st, tm, row, plane, full_leader);
+                        if (!q.resident) tma_w_g2s_pair(st + 2 * a_bytes, &q.tm_w, wrow, full_leader);
+                    }
                 }
                 __syncwarp();
             }
@@ -313,10 +387,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (NC == 2) cluster_sync_all();            // the leader's MMAs read the peer's shared memory and TMEM
     if (warp == N_EPI_WARPS) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+        if constexpr (NC == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
     }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams q) { gemm_tc_body<1>(q); }
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) gemm_tc_pair_kernel(const __grid_constant__ TcParams q) {
+    gemm_tc_body<2>(q);
 }
 
 // x[B][L] -> xT[L][Bp]  (so that everything downstream reads the raw signal coalesced over windows)
@@ -387,10 +468,32 @@ int make_img_map(const CbImg& img, CUtensorMap* tm) {
     return CB_OK;
 }
 
+// TMA view of a CTA-pair weight image as 2 KB rows: one CTA's chunk of a pipeline stage is BN/32 consecutive rows.
+int make_w_map(const __half* img2, size_t halfs, int BN, CUtensorMap* tm) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+        cb_set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return CB_ERR_CUDA;
+    }
+    const cuuint64_t dims[2] = {256, (cuuint64_t)(halfs * 2 / 2048)};
+    const cuuint64_t strides[1] = {2048};
+    const cuuint32_t box[2] = {256, (cuuint32_t)(BN / 32)}, estr[2] = {1, 1};
+    const CUresult r = ((EncodeFn)fn)(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void*)img2, dims, strides, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { cb_set_error("cuTensorMapEncodeTiled(weights) failed (%d)", (int)r); return CB_ERR_CUDA; }
+    return CB_OK;
+}
+
 size_t smem_bytes_for(int BN) { return (size_t)STAGES * (2 * BM * BK * 2 + 2 * (size_t)BN * BK * 2) + 256; }
 size_t smem_bytes_resident(int BN, int k_chunks) {
     return (size_t)k_chunks * 2 * BN * BK * 2 + (size_t)STAGES * (2 * BM * BK * 2) + 256;
 }
+// (the CTA-pair kernel holds BN/2 rows of B per CTA: pass BN/2)
 constexpr size_t SMEM_MAX = 232448;      // 227 KB of dynamic shared memory per CTA
 
 int pick_bn(int N) {            // widest tile <= 256 that divides N (UMMA N must be a multiple of 16 at M = 128)
@@ -436,6 +539,24 @@ int cb_tc_build_layer(cb_handle* h, int layer_id, const float* W, int K, int N) 
         }
     CB_CUDA(cudaMalloc(&L.img, img.size() * sizeof(__half)));
     CB_CUDA(cudaMemcpy(L.img, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    if (L.BN % 32 == 0) {      // CTA-pair form: CTA r of the pair holds rows [r*BN/2, (r+1)*BN/2) of every B tile
+        const int BH = L.BN / 2;
+        std::vector<__half> img2(img.size());
+        for (int nt = 0; nt < L.n_tiles; ++nt)
+            for (int kc = 0; kc < L.k_chunks; ++kc) {
+                const __half* src = img.data() + ((size_t)nt * L.k_chunks + kc) * per_chunk;
+                for (int r = 0; r < 2; ++r)
+                    for (int hl = 0; hl < 2; ++hl)
+                        for (int gq = 0; gq < 4; ++gq)
+                            for (int n = 0; n < BH; ++n)
+                                memcpy(&img2[(((((size_t)nt * L.k_chunks + kc) * 2 + r) * 2 + hl) * 4 + gq) * BH * 8 + (size_t)n * 8],
+                                       src + (size_t)hl * L.BN * BK + (size_t)gq * L.BN * 8 + (size_t)(r * BH + n) * 8, 8 * sizeof(__half));
+            }
+        CB_CUDA(cudaMalloc(&L.img2, img2.size() * sizeof(__half)));
+        CB_CUDA(cudaMemcpy(L.img2, img2.data(), img2.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        const int rc = make_w_map(L.img2, img2.size(), L.BN, &L.tm_w2);
+        if (rc != CB_OK) return rc;
+    }
     if ((int)st->layers.size() <= layer_id) st->layers.resize(layer_id + 1, TcLayer{});
     st->layers[layer_id] = L;
     return CB_OK;
@@ -503,6 +624,7 @@ int cb_tc_prepare(cb_handle* h, const float* hw) {
     CB_CUDA(cudaMalloc(&st->d_range_flag, sizeof(int)));
     CB_CUDA(cudaMemset(st->d_range_flag, 0, sizeof(int)));
     CB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    CB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
     return cb_lstm_tc_prepare(h, hw);
 }
 
@@ -510,7 +632,7 @@ void cb_tc_release(cb_handle* h) {
     cb_lstm_tc_release(h);
     TcState* st = (TcState*)h->tc;
     if (!st) return;
-    for (auto& L : st->layers) if (L.img) cudaFree(L.img);
+    for (auto& L : st->layers) { if (L.img) cudaFree(L.img); if (L.img2) cudaFree(L.img2); }
     if (st->d_range_flag) cudaFree(st->d_range_flag);
     if (st->d_lstm_bias) cudaFree(st->d_lstm_bias);
     delete st;
@@ -563,16 +685,30 @@ int cb_launch_gemm_tc(cb_handle* h, const TcGemm& g, cudaStream_t s) {
     q.range_flag = st->d_range_flag;
     static const int prefetch_env = getenv("CB_TC_PREFETCH") ? atoi(getenv("CB_TC_PREFETCH")) : PREFETCH_AHEAD;
     q.prefetch_ahead = prefetch_env;
-    const long long tiles = (long long)q.m_tiles * q.n_tiles;
-    // resident weights when the n-tile's image fits beside the A ring, the CTAs can be dealt evenly over the n-tiles
-    // and every CTA gets enough m-tiles to amortise the weight load
-    const int per_nt = h->sm_count / L.n_tiles;
-    q.resident = L.n_tiles > 1 && smem_bytes_resident(L.BN, L.k_chunks) <= SMEM_MAX && per_nt >= 1 &&
-                 q.m_tiles >= 8 * per_nt;
-    int grid = (int)(tiles < h->sm_count ? tiles : h->sm_count);
-    size_t smem = smem_bytes_for(L.BN);
-    if (q.resident) { grid = per_nt * L.n_tiles; smem = smem_bytes_resident(L.BN, L.k_chunks); }
-    gemm_tc_kernel<<<grid, NTHREADS, smem, s>>>(q);
+    // CTA pairs (tcgen05 cta_group::2: M = 256 over two m-tiles, each CTA stages half of the B tile -- the single-CTA
+    // kernel is bound by shared-memory bandwidth: three MMA passes re-read A and B, 96 B/clk + 62 B/clk of TMA writes
+    // against the SM's 128 B/clk) whenever the m-tiles pair up; CB_TC_PAIR=0 forces the single-CTA kernel (A/B timing).
+    static const int pair_env = getenv("CB_TC_PAIR") ? atoi(getenv("CB_TC_PAIR")) : 1;
+    const bool pair = pair_env && L.img2 && q.m_tiles % 2 == 0 && h->sm_count % 2 == 0 && (L.n_tiles == 1 || pair_env == 2);
+    const int nc = pair ? 2 : 1;
+    static const int sms_env = getenv("CB_TC_GEMM_SMS") ? atoi(getenv("CB_TC_GEMM_SMS")) : 0;   // experiment: cap the grid
+    const int sms = sms_env > 0 && sms_env < h->sm_count ? sms_env : h->sm_count;
+    const int units = sms / nc;                           // scheduling units: CTAs or CTA pairs
+    const int m_units = q.m_tiles / nc;
+    // resident weights when the n-tile's image fits beside the A ring, the units can be dealt evenly over the n-tiles
+    // and every unit gets enough m-tiles to amortise the weight load
+    const int per_nt = units / L.n_tiles;
+    q.resident = L.n_tiles > 1 && smem_bytes_resident(L.BN / nc, L.k_chunks) <= SMEM_MAX && per_nt >= 1 &&
+                 m_units >= 8 * per_nt;
+    const long long work = (long long)m_units * q.n_tiles;
+    int grid = (int)(work < units ? work : units) * nc;
+    const size_t smem = q.resident ? smem_bytes_resident(L.BN / nc, L.k_chunks) : smem_bytes_for(L.BN / nc);
+    if (pair) {
+        q.img = L.img2; q.tm_w = L.tm_w2;
+        gemm_tc_pair_kernel<<<grid, NTHREADS, smem, s>>>(q);
+    } else {
+        gemm_tc_kernel<<<grid, NTHREADS, smem, s>>>(q);
+    }
     CB_CHECK_LAUNCH();
     h->launches++;
     return CB_OK;

@@ -23,3 +23,17 @@ for _ in range(10): y.copy_(x)
 e1.record(); torch.cuda.synchronize()
 gb = 10 * 2 * x.numel() * 2 / (e0.elapsed_time(e1) * 1e-3) / 1e9
 print("box speed: cuBLAS bf16 %.0f TF/s sustained, copy %.0f GB/s | after load: %s" % (tf, gb, q))
+# write-only and read-only HBM bandwidth (is a write-heavy kernel bound below the copy figure?)
+z = torch.empty(1 << 31, device="cuda", dtype=torch.uint8)
+for _ in range(3): z.zero_()
+torch.cuda.synchronize(); e0.record()
+for _ in range(10): z.zero_()
+e1.record(); torch.cuda.synchronize()
+wr = 10 * z.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9
+zf = z.view(torch.float32)
+for _ in range(3): zf.sum()
+torch.cuda.synchronize(); e0.record()
+for _ in range(10): zf.sum()
+e1.record(); torch.cuda.synchronize()
+rd = 10 * z.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9
+print("box speed: write-only (memset 2 GiB) %.0f GB/s, read-only (sum 2 GiB) %.0f GB/s" % (wr, rd))
