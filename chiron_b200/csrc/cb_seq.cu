@@ -35,6 +35,38 @@ __global__ void __launch_bounds__(64) beam_kernel(const float* __restrict__ logi
     n_bases[b] = n;
 }
 
+// One WARP per window, workspace and the window's logits in SHARED memory.  The search is a serial, branchy walk: with 32
+// windows per warp (beam_kernel) the lanes serialise each other's divergent paths and every trie / slot access is an
+// uncoalesced global load; here lane 0 walks alone over shared memory (the other lanes stage the logits and clear the
+// output tail).  The node pool is small (compacted often); if it ever overflows the launcher falls back to beam_kernel.
+constexpr int BEAM_WARPS = 4;
+__global__ void __launch_bounds__(BEAM_WARPS * 32) beam_warp_kernel(const float* __restrict__ logits, const int32_t* __restrict__ lens,
+                                                                    int B, int T, int C, int W, int pool, int stride,
+                                                                    int8_t* __restrict__ bases, int32_t* __restrict__ n_bases,
+                                                                    int* __restrict__ overflow) {
+    extern __shared__ __align__(16) char beam_sm[];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * BEAM_WARPS + w;
+    if (b >= B) return;
+    char* base = beam_sm + (size_t)w * stride;
+    float* lg = reinterpret_cast<float*>(base);
+    int len = lens[b];
+    len = len < 0 ? 0 : (len > T ? T : len);
+    const float* src = logits + (size_t)b * T * C;
+    for (int i = lane; i < len * C; i += 32) lg[i] = src[i];
+    __syncwarp();
+    int8_t* dst = bases + (size_t)b * T;
+    int n = 0;
+    if (lane == 0) {
+        CbBeamWork k = cb_beam_work_carve(base + (((size_t)T * C * 4 + 15) & ~(size_t)15), W, pool);
+        n = cb_beam_decode_one(lg, len, C, W, k, dst);
+        if (n < 0) { atomicExch(overflow, 1); n = 0; }
+    }
+    n = __shfl_sync(0xffffffffu, n, 0);
+    for (int i = n + lane; i < T; i += 32) dst[i] = 0;
+    if (lane == 0) n_bases[b] = n;
+}
+
 // ---- assembly ----------------------------------------------------------------------------------------------------
 struct AsmWork {
     int* list;       // [n_windows] indices of non-empty windows, in order
@@ -197,6 +229,30 @@ int cb_launch_beam(cb_handle* h, const float* logits, const int32_t* lens, int B
     // thousand nodes cover T*W-sized tries.  2*W*(T+1)+2 nodes can never overflow (every live node is an ancestor of
     // a leaf or of a current branch); that size is used for a retry if the small pool ever proves too small.
     const long long cap = 2LL * W * (T + 1) + 2;
+    {   // fast path: warp per window over shared memory with a small, frequently compacted pool
+        long long pool_s = 6LL * W;
+        if (pool_s < 2LL * W + 2) pool_s = 2LL * W + 2;
+        if (pool_s < 64) pool_s = 64;
+        if (pool_s > cap) pool_s = cap;
+        const size_t stride = align_up(align_up((size_t)T * C * 4, 16) + cb_beam_work_bytes(W, (int)pool_s), 16);
+        static const int smem_env = getenv("CB_BEAM_SMEM") ? atoi(getenv("CB_BEAM_SMEM")) : 1;
+        if (smem_env && stride * BEAM_WARPS <= 200 * 1024) {
+            static bool attr_set = false;
+            if (!attr_set) {
+                CB_CUDA(cudaFuncSetAttribute(beam_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr_set = true;
+            }
+            CB_CUDA(cudaMemsetAsync(h->d_flag, 0, sizeof(int), s));
+            beam_warp_kernel<<<(B + BEAM_WARPS - 1) / BEAM_WARPS, BEAM_WARPS * 32, stride * BEAM_WARPS, s>>>(
+                logits, lens, B, T, C, W, (int)pool_s, (int)stride, bases, n_bases, h->d_flag);
+            CB_CHECK_LAUNCH();
+            h->launches++;
+            int flag = 0;              // the beam decoder is synchronous (like the reference's decode dequeue)
+            CB_CUDA(cudaMemcpyAsync(&flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+            CB_CUDA(cudaStreamSynchronize(s));
+            if (!flag) return CB_OK;
+        }
+    }
     long long pool = 4LL * W + 4096;
     for (int attempt = 0; attempt < 2; ++attempt) {
         if (pool > cap || attempt == 1) pool = cap;
