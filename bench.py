@@ -29,6 +29,13 @@ if ROOT not in sys.path:
 
 SEG_LEN = 512
 FLOP_PER_FRAME = {"conv": 2 * 1049088, "lstm_in": 2 * 524800, "lstm_rec": 2 * 240000, "head": 2 * 700}
+# Algorithmic HBM bytes per frame, summed over the launches of a category: every contraction reads
+# its A operand image once (hi+lo fp16 = 4 B per channel) and writes its output once.
+#   conv: 8 contractions read 256-channel images (the two K=512 ones read two), all write one: (10 + 8) * 1024 B, + gen 1 KB
+#   lstm_in: reads 1024 + 832 + 832 B (K = 256, 208, 208), writes 3 x 3200 B of fp32 pre-activations
+#   lstm_rec: reads 3 x 3200 B, writes 832 + 832 B of h images and 800 B of fp32 output;  head: 800 B in, 20 B out
+BYTES_PER_FRAME = {"conv": 19 * 1024 + 4, "lstm_in": 1024 + 832 + 832 + 3 * 3200, "lstm_rec": 3 * 3200 + 832 + 832 + 800,
+                   "head": 820}
 
 
 def load_peaks():
@@ -267,6 +274,13 @@ def main():
                 "algorithmic_flop_per_launch": flops / max(dom_cnt, 1),
                 "per_category_ms": {k: round(v[0], 3) for k, v in prof_acc.items()},
                 "per_category_tflops": {k: FLOP_PER_FRAME[k] * frames / (v[0] * 1e-3) / 1e12 for k, v in prof_acc.items() if v[0] > 0},
+                # every category against BOTH ceilings (tensor: FLOP actually issued = algorithmic x mma_passes vs the
+                # sustained cuBLAS figure; hbm: algorithmic bytes vs the measured copy bandwidth) -- the larger is its bound
+                "per_category_fracs": {k: {"tensor_pipe_frac": (FLOP_PER_FRAME[k] * frames * max(mma_passes, 1) / (v[0] * 1e-3) / 1e12 / peak_tf
+                                                                if mma_passes and k != "head" else None),
+                                           "hbm_frac": BYTES_PER_FRAME[k] * frames / (v[0] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                           "hbm_gbs": BYTES_PER_FRAME[k] * frames / (v[0] * 1e-3) / 1e9}
+                                       for k, v in prof_acc.items() if v[0] > 0},
                 "phase_ms": phase_ms}
 
     # ---- end to end through the C-ABI host calls: host buffers, H2D + D2H inside the timed region ---------------------

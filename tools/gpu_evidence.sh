@@ -13,7 +13,7 @@ timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > $out/bench_r
 timeout 600 python tools/bench_configs.py tc > $out/configs_tc.json 2> $out/configs_tc.err
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/bench_under_ncu.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 12 -c 12 -f -o $out/prof_gemm \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 11 -c 11 -f -o $out/prof_gemm \
     python tools/gpu_quick.py tc 4096 512 > $out/ncu_gemm.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm_tc_kernel -s 3 -c 3 -f -o $out/prof_lstm \
     python tools/gpu_quick.py tc 4096 512 > $out/ncu_lstm.log 2>&1
