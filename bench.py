@@ -256,7 +256,7 @@ def main():
     achieved = flops / (dom_ms * 1e-3) / 1e12
     peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     # tensor-pipe work actually issued: the tc path runs every contraction as 3 fp16 MMAs (hi*lo, lo*hi, hi*hi)
-    mma_passes = {"tc": 3, "tc_fast": 1}.get(args.precision, 0)
+    mma_passes = {"tc": 3, "tc_precise": 3, "tc_fast": 1}.get(args.precision, 0)
     traffic, traffic_src = None, None
     try:                                   # DRAM bytes per launch of the dominant kernel from the committed ncu capture
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))

@@ -11,9 +11,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CHIRON_B200_LIB") or os.path.join(_HERE, "lib", "libchiron_b200.so")   # env override: A/B builds
 
 CB_OK = 0
-PREC_FP32, PREC_TC_SPLIT, PREC_TC_FAST = 0, 1, 2
+PREC_FP32, PREC_TC_SPLIT, PREC_TC_FAST, PREC_TC_PRECISE = 0, 1, 2, 3
 ASM_SIMPLE, ASM_GLUE, ASM_STICK = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "tc": PREC_TC_SPLIT, "tc_split": PREC_TC_SPLIT, "tc_fast": PREC_TC_FAST}
+PRECISIONS = {"fp32": PREC_FP32, "tc": PREC_TC_SPLIT, "tc_split": PREC_TC_SPLIT, "tc_fast": PREC_TC_FAST,
+              "tc_precise": PREC_TC_PRECISE}
 ASM_KERNELS = {"simple": ASM_SIMPLE, "glue": ASM_GLUE, "stick": ASM_STICK}
 
 # name -> (restype, argtypes); mirrors include/chiron_b200.h one to one

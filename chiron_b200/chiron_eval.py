@@ -287,7 +287,7 @@ def add_call_arguments(parser: argparse.ArgumentParser, model_default: Optional[
     parser.add_argument("--concise", action="store_true", help="Do not write the meta and segments files.")
     parser.add_argument("--mode", default="dna", help="Output mode, dna or rna.")
     parser.add_argument("-p", "--preset", default=None, help="Preset evaluation parameters: dna-pre or rna-pre")
-    parser.add_argument("--precision", default="fp32", choices=["fp32", "tc", "tc_fast"],
+    parser.add_argument("--precision", default="fp32", choices=["fp32", "tc", "tc_precise", "tc_fast"],
                         help="[chiron_b200] arithmetic of the dense contractions (see include/chiron_b200.h)")
 
 

@@ -54,7 +54,7 @@ int out_len_of(const CbConfig& c, int L) {
 // -----------------------------------------------------------------------------------------------------------------
 extern "C" int cb_create(const void* blob, size_t nbytes, int device, int precision, cb_handle** out) {
     if (!blob || !out || nbytes < HEADER_BYTES) { cb_set_error("cb_create: bad arguments"); return CB_ERR_ARG; }
-    if (precision < CB_PREC_FP32 || precision > CB_PREC_TC_FAST) { cb_set_error("cb_create: unknown precision %d", precision); return CB_ERR_ARG; }
+    if (precision < CB_PREC_FP32 || precision > CB_PREC_TC_PRECISE) { cb_set_error("cb_create: unknown precision %d", precision); return CB_ERR_ARG; }
     BlobHeader hd;
     memcpy(&hd, blob, sizeof(hd));
     int64_t n_floats;

@@ -66,6 +66,8 @@ struct TcParams {
     int passes;                  // 3 = hi/lo split, 1 = fast
     int prefetch_ahead;          // k-chunks the L2 prefetch of the A boxes runs ahead of the loads
     int resident;                // 1: the CTA keeps its n-tile of W in shared memory (see header)
+    int sweeps;                  // 2: K is swept twice -- all low-order products (hi*lo, lo*hi) first, then hi*hi -- so that
+                                 //    only K/16 of the accumulator's truncating adds happen at full magnitude
     int* range_flag;
 };
 
@@ -297,7 +299,9 @@ __device__ __forceinline__ void gemm_tc_body(const TcParams& q) {
                 __syncwarp();
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * (uint32_t)BN;
-                for (int kc = 0; kc < q.k_chunks; ++kc, ++kit) {
+                for (int vk = 0; vk < q.sweeps * q.k_chunks; ++vk, ++kit) {
+                    const int kc = vk < q.k_chunks ? vk : vk - q.k_chunks;
+                    const int part = q.sweeps == 1 ? 3 : (vk < q.k_chunks ? 1 : 2);   // 1 low-order, 2 high-order, 3 both
                     const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
                     if (leader) mbar_wait(&full_bar[s], ph);
                     __syncwarp();
@@ -311,9 +315,11 @@ __device__ __forceinline__ void gemm_tc_body(const TcParams& q) {
 #pragma unroll
                         for (int ks = 0; ks < BK / 16; ++ks) {
                             if (q.passes == 3) {              // low-order products first (truncating accumulator)
-                                umma_f16_nc<NC>(d_tmem, dah + ks * A_STEP, dbl + ks * B_STEP, idesc, (kc | ks) != 0);
-                                umma_f16_nc<NC>(d_tmem, dal + ks * A_STEP, dbh + ks * B_STEP, idesc, 1);
-                                umma_f16_nc<NC>(d_tmem, dah + ks * A_STEP, dbh + ks * B_STEP, idesc, 1);
+                                if (part & 1) {
+                                    umma_f16_nc<NC>(d_tmem, dah + ks * A_STEP, dbl + ks * B_STEP, idesc, (vk | ks) != 0);
+                                    umma_f16_nc<NC>(d_tmem, dal + ks * A_STEP, dbh + ks * B_STEP, idesc, 1);
+                                }
+                                if (part & 2) umma_f16_nc<NC>(d_tmem, dah + ks * A_STEP, dbh + ks * B_STEP, idesc, 1);
                             } else {
                                 umma_f16_nc<NC>(d_tmem, dah + ks * A_STEP, dbh + ks * B_STEP, idesc, (kc | ks) != 0);
                             }
@@ -356,7 +362,8 @@ __device__ __forceinline__ void gemm_tc_body(const TcParams& q) {
         };
         for (int d = 0; d < q.prefetch_ahead; ++d) prefetch_next();
         for (int it = 0, mu, nt; tiles.get(it, mu, nt); ++it) {
-            for (int kc = 0; kc < q.k_chunks; ++kc, ++kit) {
+            for (int vk = 0; vk < q.sweeps * q.k_chunks; ++vk, ++kit) {
+                const int kc = vk < q.k_chunks ? vk : vk - q.k_chunks;
                 const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
                 if (q.prefetch_ahead) prefetch_next();
                 coords(it, kc, tm, row, plane);
@@ -683,6 +690,9 @@ int cb_launch_gemm_tc(cb_handle* h, const TcGemm& g, cudaStream_t s) {
     q.m_tiles = g.T * (g.Bp / BM); q.out_scale = L.out_scale;
     q.passes = h->precision == CB_PREC_TC_FAST ? 1 : 3;
     q.range_flag = st->d_range_flag;
+    static const int sweeps_env = getenv("CB_TC_SWEEPS") ? atoi(getenv("CB_TC_SWEEPS")) : 0;   // bit 0: projections, bit 1: convs
+    q.sweeps = (q.passes == 3 && ((L.n_tiles > 1 && (sweeps_env & 1)) ||
+                                  (L.n_tiles == 1 && ((sweeps_env & 2) || h->precision == CB_PREC_TC_PRECISE)))) ? 2 : 1;
     static const int prefetch_env = getenv("CB_TC_PREFETCH") ? atoi(getenv("CB_TC_PREFETCH")) : PREFETCH_AHEAD;
     q.prefetch_ahead = prefetch_env;
     // CTA pairs (tcgen05 cta_group::2: M = 256 over two m-tiles, each CTA stages half of the B tile -- the single-CTA

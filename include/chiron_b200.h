@@ -37,7 +37,10 @@ enum {
 enum {
     CB_PREC_FP32 = 0,     /* fp32 FFMA SIMT kernels (reference-grade; slow path kept for A/B checks) */
     CB_PREC_TC_SPLIT = 1, /* tcgen05 fp16 MMAs on hi/lo-split operands (3 MMAs per product, fp32-class error) */
-    CB_PREC_TC_FAST = 2   /* tcgen05 single-pass fp16 MMAs (~1e-3 relative; not bit-parity safe) */
+    CB_PREC_TC_FAST = 2,  /* tcgen05 single-pass fp16 MMAs (~1e-3 relative; not bit-parity safe) */
+    CB_PREC_TC_PRECISE = 3 /* CB_PREC_TC_SPLIT with the K range of every convolution swept twice -- all low-order products
+                            * first, then hi*hi -- so that only K/16 of the tensor core's truncating accumulator adds run at
+                            * full magnitude: about a third of the logit error of TC_SPLIT for +48 % convolution time */
 };
 
 /* Assembly kernels, chiron/chiron_eval.py:138-150 (get_assembler_kernal). */

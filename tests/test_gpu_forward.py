@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 # moves by 5e-4 between float32 and float64 (the three LSTM layers amplify rounding noise ~100x).  "fp32" = FFMA kernels
 # with round-to-nearest accumulation; "tc" = tcgen05 fp16 hi/lo split whose accumulator truncates (RZ) on every add
 # (measured maxima: 1.4e-2 on 9,600 frames, 3.7e-2 on 30,000 frames against the float64 oracle, no argmax flips).
-LOGIT_TOLS = {"fp32": 2e-3, "tc": 5e-2}
+LOGIT_TOLS = {"fp32": 2e-3, "tc": 5e-2, "tc_precise": 2.5e-2}
 
 
 def _read1_windows(cfg, L=400, jump=390):
@@ -21,7 +21,7 @@ def _read1_windows(cfg, L=400, jump=390):
     return O.make_windows(O.normalize_signal(sig, cfg.sig_norm), L, jump)
 
 
-@pytest.fixture(scope="module", params=["fp32", "tc"])
+@pytest.fixture(scope="module", params=["fp32", "tc", "tc_precise"])
 def caller(request):
     from chiron_b200.engine import Basecaller
     bc = Basecaller("DNA_default", device=0, precision=request.param)
