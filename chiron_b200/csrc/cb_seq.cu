@@ -37,9 +37,181 @@ __global__ void __launch_bounds__(64) beam_kernel(const float* __restrict__ logi
 
 // One WARP per window, workspace and the window's logits in SHARED memory.  The search is a serial, branchy walk: with 32
 // windows per warp (beam_kernel) the lanes serialise each other's divergent paths and every trie / slot access is an
-// uncoalesced global load; here lane 0 walks alone over shared memory (the other lanes stage the logits and clear the
-// output tail).  The node pool is small (compacted often); if it ever overflows the launcher falls back to beam_kernel.
+// uncoalesced global load.  Here a warp runs cb_beam_decode_one's frame loop COOPERATIVELY with bit-identical results:
+//   * the stable descending sort of the leaves is a rank computation (rank = #greater + #equal-before), the per-branch
+//     copies and the probability updates (two log-sum-exp per branch -- the transcendental bulk of a frame) are
+//     independent per branch and go one branch per lane, the bottom-of-beam search is a warp reduction;
+//   * the extension loop (branch x child, order-dependent: evictions move the threshold) stays on lane 0, but only for the
+//     candidates a parallel pre-filter cannot rule out.  Within a frame a branch's oldp only ever drops to -inf, the
+//     threshold only rises once the beam is full and the beam only fills up, so "passes with the state at the start of
+//     the chunk" is a superset of "passes when reached"; candidates whose child is one of this frame's branches are always
+//     kept (TF's deactivate-child reset).  Lane 0 re-evaluates every kept candidate with the current state, exactly like
+//     the sequential code; chunks are aligned to branches so a branch's entry test is made once.
+// The node pool is small (compacted often); if it ever overflows the launcher falls back to beam_kernel.
 constexpr int BEAM_WARPS = 4;
+
+__device__ int beam_decode_warp(const float* __restrict__ lg, int len, int C, int W, CbBeamWork k, int8_t* out, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    const int blank = C - 1, n_child = C - 1;
+    int n_nodes = 1, n_leaves = 1, n_free = 0, err = 0;
+    if (lane == 0) {
+        k.nodes[0].parent = -1; k.nodes[0].label = -1; k.nodes[0].slot = 0; k.nodes[0].bidx = 0; k.nodes[0].bframe = -1;
+        for (int c = 0; c < CB_BEAM_MAX_CHILD; ++c) k.nodes[0].child[c] = -1;
+        k.slot_node[0] = 0;
+        k.ot[0] = k.ob[0] = -INFINITY;
+        k.nt[0] = 0.f; k.nb[0] = 0.f; k.nl[0] = -INFINITY;
+        k.leaves[0] = 0;
+        for (int s = W - 1; s >= 1; --s) k.freel[n_free++] = s;            // pop order 1,2,3,...
+    }
+    n_free = __shfl_sync(FULL, n_free, 0);
+    __syncwarp();
+    const int bpc = 32 / n_child;                        // branches per chunk of the extension loop
+    float inp[8];
+    for (int t = 0; t < len; ++t) {
+        const float* row = lg + (size_t)t * C;
+        float mx = row[0];
+        for (int c = 1; c < C; ++c) if (row[c] > mx) mx = row[c];
+        for (int c = 0; c < C; ++c) inp[c] = row[c] - mx;
+        const int nb = n_leaves;
+        // leaves_.Extract(): descending newp.total, stable  ==  rank of every leaf
+        for (int i = lane; i < nb; i += 32) {
+            const int v = k.leaves[i];
+            const float key = k.nt[v];
+            int rank = 0;
+            for (int j = 0; j < nb; ++j) {
+                const float o = k.nt[k.leaves[j]];
+                rank += (o > key) || (o == key && j < i);
+            }
+            k.branches[rank] = v;
+        }
+        __syncwarp();
+        for (int i = lane; i < nb; i += 32) {
+            const int s = k.branches[i];
+            k.ot[s] = k.nt[s]; k.ob[s] = k.nb[s];
+            k.bnode[i] = k.slot_node[s]; k.bo_total[i] = k.nt[s]; k.bo_blank[i] = k.nb[s];
+            k.nodes[k.slot_node[s]].bidx = i; k.nodes[k.slot_node[s]].bframe = t;
+        }
+        __syncwarp();
+        for (int i = lane; i < nb; i += 32) {
+            const int s = k.branches[i];
+            const CbBeamNode& nd = k.nodes[k.slot_node[s]];
+            float nl = k.nl[s];
+            if (nd.parent >= 0) {
+                const CbBeamNode& pa = k.nodes[nd.parent];
+                if (pa.slot >= 0) {
+                    const float prev = (nd.label == pa.label) ? k.ob[pa.slot] : k.ot[pa.slot];
+                    nl = cb_lse(nl, prev);
+                }
+                nl += inp[nd.label];
+            }
+            const float nbv = k.ot[s] + inp[blank];
+            k.nl[s] = nl; k.nb[s] = nbv;
+            k.nt[s] = cb_lse(nbv, nl);
+            k.leaves[i] = s;
+        }
+        __syncwarp();
+        n_leaves = nb;
+        // bottom = first minimum in push order
+        float bot_val = INFINITY; int bot = 0x7fffffff;
+        for (int i = lane; i < n_leaves; i += 32) {
+            const float v = k.nt[k.leaves[i]];
+            if (v < bot_val || bot == 0x7fffffff) { bot_val = v; bot = i; }     // strided scan keeps the lowest index per value
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(FULL, bot_val, off);
+            const int oi = __shfl_xor_sync(FULL, bot, off);
+            if (oi != 0x7fffffff && (bot == 0x7fffffff || ov < bot_val || (ov == bot_val && oi < bot))) { bot_val = ov; bot = oi; }
+        }
+        // extension loop, chunks of bpc whole branches
+        for (int ib = 0; ib < nb; ib += bpc) {
+            bool flag = false;
+            {
+                const int i = ib + lane / n_child, c = lane % n_child;
+                if (lane < bpc * n_child && i < nb) {
+                    const float tot = k.bo_total[i];
+                    if (tot > -INFINITY && (n_leaves < W || tot > bot_val)) {
+                        const int bn = k.bnode[i];
+                        const int ch = k.nodes[bn].child[c];
+                        const float prev = (c == k.nodes[bn].label) ? k.bo_blank[i] : tot;
+                        const float lab = inp[c] + prev;
+                        flag = (lab > -INFINITY && (n_leaves < W || lab > bot_val)) || (ch >= 0 && k.nodes[ch].bframe == t);
+                    }
+                }
+            }
+            unsigned mask = __ballot_sync(FULL, flag);
+            if (lane == 0 && mask && !err) {
+                int cur_i = -1; bool cur_pass = false; float tot = 0.f;
+                while (mask) {
+                    const int bit = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int i = ib + bit / n_child, c = bit % n_child;
+                    if (i != cur_i) {                      // the branch's entry test, with the state of this moment
+                        cur_i = i;
+                        tot = k.bo_total[i];
+                        cur_pass = tot > -INFINITY && (n_leaves < W || tot > bot_val);
+                    }
+                    if (!cur_pass) continue;
+                    const int bn = k.bnode[i];
+                    const int ch = k.nodes[bn].child[c];
+                    if (ch >= 0 && k.nodes[ch].slot >= 0) continue;           // already an active beam
+                    const float prev = (c == k.nodes[bn].label) ? k.bo_blank[i] : tot;
+                    const float lab = inp[c] + prev;
+                    if (!(lab > -INFINITY && (n_leaves < W || lab > bot_val))) {
+                        if (ch >= 0 && k.nodes[ch].bframe == t) {
+                            k.bo_total[k.nodes[ch].bidx] = -INFINITY; k.bo_blank[k.nodes[ch].bidx] = -INFINITY;
+                        }
+                        continue;
+                    }
+                    if (n_leaves == W) {                                       // evict the bottom beam
+                        const int bs = k.leaves[bot];
+                        k.nodes[k.slot_node[bs]].slot = -1;
+                        for (int q = bot; q + 1 < n_leaves; ++q) k.leaves[q] = k.leaves[q + 1];
+                        --n_leaves;
+                        k.freel[n_free++] = bs;
+                    }
+                    int node = ch;
+                    if (node < 0) {
+                        if (n_nodes == k.pool) {
+                            n_nodes = cb_beam_compact(k, n_nodes, n_leaves, nb, n_child);
+                            if (n_nodes == k.pool) { err = 1; break; }
+                        }
+                        node = n_nodes++;
+                        CbBeamNode& nn = k.nodes[node];
+                        nn.parent = k.bnode[i]; nn.label = c; nn.slot = -1; nn.bidx = 0; nn.bframe = -1;
+                        for (int q = 0; q < CB_BEAM_MAX_CHILD; ++q) nn.child[q] = -1;
+                        k.nodes[k.bnode[i]].child[c] = node;
+                    }
+                    const int s = k.freel[--n_free];
+                    k.slot_node[s] = node;
+                    k.nodes[node].slot = s;
+                    k.nb[s] = -INFINITY; k.nl[s] = lab; k.nt[s] = lab;
+                    k.ot[s] = k.ob[s] = -INFINITY;
+                    k.leaves[n_leaves++] = s;
+                    bot = 0;
+                    for (int q = 1; q < n_leaves; ++q) if (k.nt[k.leaves[q]] < k.nt[k.leaves[bot]]) bot = q;
+                    bot_val = k.nt[k.leaves[bot]];
+                }
+            }
+            __syncwarp();
+            n_leaves = __shfl_sync(FULL, n_leaves, 0); n_free = __shfl_sync(FULL, n_free, 0);
+            n_nodes = __shfl_sync(FULL, n_nodes, 0); bot = __shfl_sync(FULL, bot, 0);
+            bot_val = __shfl_sync(FULL, bot_val, 0); err = __shfl_sync(FULL, err, 0);
+        }
+        if (err) return -2;
+    }
+    int n = 0;
+    if (lane == 0) {
+        int best = 0;
+        for (int i = 1; i < n_leaves; ++i) if (k.nt[k.leaves[i]] > k.nt[k.leaves[best]]) best = i;
+        for (int cur = k.slot_node[k.leaves[best]]; k.nodes[cur].parent >= 0; cur = k.nodes[cur].parent) ++n;
+        int i = n - 1;
+        for (int cur = k.slot_node[k.leaves[best]]; k.nodes[cur].parent >= 0; cur = k.nodes[cur].parent)
+            out[i--] = (int8_t)k.nodes[cur].label;
+    }
+    return __shfl_sync(FULL, n, 0);
+}
+
 __global__ void __launch_bounds__(BEAM_WARPS * 32) beam_warp_kernel(const float* __restrict__ logits, const int32_t* __restrict__ lens,
                                                                     int B, int T, int C, int W, int pool, int stride,
                                                                     int8_t* __restrict__ bases, int32_t* __restrict__ n_bases,
@@ -56,13 +228,10 @@ __global__ void __launch_bounds__(BEAM_WARPS * 32) beam_warp_kernel(const float*
     for (int i = lane; i < len * C; i += 32) lg[i] = src[i];
     __syncwarp();
     int8_t* dst = bases + (size_t)b * T;
-    int n = 0;
-    if (lane == 0) {
-        CbBeamWork k = cb_beam_work_carve(base + (((size_t)T * C * 4 + 15) & ~(size_t)15), W, pool);
-        n = cb_beam_decode_one(lg, len, C, W, k, dst);
-        if (n < 0) { atomicExch(overflow, 1); n = 0; }
-    }
-    n = __shfl_sync(0xffffffffu, n, 0);
+    CbBeamWork k = cb_beam_work_carve(base + (((size_t)T * C * 4 + 15) & ~(size_t)15), W, pool);
+    int n = beam_decode_warp(lg, len, C, W, k, dst, lane);
+    if (n < 0) { if (lane == 0) atomicExch(overflow, 1); n = 0; }
+    __syncwarp();
     for (int i = n + lane; i < T; i += 32) dst[i] = 0;
     if (lane == 0) n_bases[b] = n;
 }
@@ -235,7 +404,7 @@ int cb_launch_beam(cb_handle* h, const float* logits, const int32_t* lens, int B
         if (pool_s < 64) pool_s = 64;
         if (pool_s > cap) pool_s = cap;
         const size_t stride = align_up(align_up((size_t)T * C * 4, 16) + cb_beam_work_bytes(W, (int)pool_s), 16);
-        static const int smem_env = getenv("CB_BEAM_SMEM") ? atoi(getenv("CB_BEAM_SMEM")) : 1;
+        const int smem_env = getenv("CB_BEAM_SMEM") ? atoi(getenv("CB_BEAM_SMEM")) : 1;    // 0: force the fallback kernel (tests)
         if (smem_env && stride * BEAM_WARPS <= 200 * 1024) {
             static bool attr_set = false;
             if (!attr_set) {

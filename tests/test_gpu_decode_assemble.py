@@ -113,3 +113,37 @@ def test_beam_kernel_matches_oracle_on_synthetic_logits(caller):
         mism = sum(g != r for g, r in zip(got, ref))
         # device expf/log1pf differ from glibc by <= 2 ulp; beam pruning can amplify that on adversarial random logits
         assert mism <= 2, "%d/%d windows differ at beam width %d" % (mism, B, W)
+
+
+def test_cooperative_beam_kernel_is_bit_identical_to_the_sequential_one(caller):
+    """beam_warp_kernel (a warp walks one window cooperatively: parallel rank sort, per-branch probability updates, warp
+    reduction for the beam bottom, pre-filtered extension loop) against beam_kernel (one thread runs cb_beam_decode_one, the
+    routine the CPU tests pin to the oracle): same device libm, so the outputs must be IDENTICAL -- on tie-heavy random
+    logits, ragged lengths, widths from 1 to 100."""
+    import torch
+    rng = np.random.default_rng(11)
+    B, T = 200, 150
+    lg = rng.normal(scale=2.0, size=(B, T, 5)).astype(np.float32)
+    lg[:, :, 4] += 2.0
+    lg[:, ::3, :] = np.round(lg[:, ::3, :])            # exact ties
+    lg[50:60] = 0.0                                    # all candidates equal
+    lens = rng.integers(0, T + 1, size=B).astype(np.int32)
+    lens[:4] = [T, 0, 1, 2]
+    dl, dn = torch.from_numpy(lg).cuda(), torch.from_numpy(lens).cuda()
+    old = os.environ.get("CB_BEAM_SMEM")
+    try:
+        for W in (1, 2, 3, 30, 50, 100):
+            out = {}
+            for mode in ("0", "1"):
+                os.environ["CB_BEAM_SMEM"] = mode
+                bases, nb = caller.decode_device(dl, dn, beam=W)
+                torch.cuda.synchronize()
+                out[mode] = (bases.cpu().numpy().copy(), nb.cpu().numpy().copy())
+            assert np.array_equal(out["0"][1], out["1"][1]), "n_bases differ at width %d" % W
+            assert np.array_equal(out["0"][0], out["1"][0]), "bases differ at width %d" % W
+            assert out["1"][1].sum() > 0
+    finally:
+        if old is None:
+            os.environ.pop("CB_BEAM_SMEM", None)
+        else:
+            os.environ["CB_BEAM_SMEM"] = old
