@@ -130,6 +130,12 @@ def evaluation(flags=None, caller: Optional[Basecaller] = None) -> Dict[str, dic
     for sub in ("", "segments", "result", "meta"):
         os.makedirs(os.path.join(flags.output, sub), exist_ok=True)
     L, jump, B = flags.segment_len, flags.jump, flags.batch_size
+    # GPU batch: a window's result does not depend on the batch it sits in (population BatchNorm; pinned bit-exactly by
+    # tests/test_gpu_forward.py::test_full_size_batch_properties), and the recurrence is a latency chain that costs the
+    # same for 400 windows as for 4096, so windows are packed into batches of at least `gpu_batch` whatever -b says
+    # (the presets' 300-400 windows would leave 90 % of the SMs idle).  The meta files still record flags.batch_size.
+    gpu_batch = int(os.environ.get("CHIRON_B200_GPU_BATCH", min(4096, max(1, (4 << 20) // max(L, 1)))))
+    B = max(B, gpu_batch)
     T = caller.out_len(L)
     beam = flags.beam
     with_qs = flags.extension == "fastq"

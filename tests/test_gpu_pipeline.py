@@ -53,11 +53,16 @@ def test_fast5_input_greedy_fasta_and_concise(tmp_path):
 
 
 def test_batch_composition_does_not_change_results(tmp_path):
-    """Windows are packed across reads; with population BatchNorm the result of a read must not depend on batch size."""
+    """Windows are packed across reads; with population BatchNorm the result of a read must not depend on batch size:
+    batches of 37 windows (GPU batch forced down to the flag) against the default packing (>= 4096 windows per batch)."""
     import types
     from chiron_b200 import chiron_eval
     outs = []
     for bs in (37, 400):
+        if bs == 37:
+            os.environ["CHIRON_B200_GPU_BATCH"] = "1"
+        else:
+            os.environ.pop("CHIRON_B200_GPU_BATCH", None)
         out = str(tmp_path / ("o%d" % bs))
         flags = types.SimpleNamespace(input=os.path.join(GOLDEN, "DNA", "raw"), output=out, model="DNA_default", start=0,
                                       batch_size=bs, segment_len=400, jump=390, threads=0, beam=0, extension="fastq",
@@ -65,6 +70,7 @@ def test_batch_composition_does_not_change_results(tmp_path):
                                       precision="fp32")
         chiron_eval.run(flags)
         outs.append(_read(os.path.join(out, "result", "read3.fastq")))
+    os.environ.pop("CHIRON_B200_GPU_BATCH", None)
     assert outs[0] == outs[1]
 
 
