@@ -1,8 +1,10 @@
 // CTC beam search and overlap assembly on the GPU (latency/branch-bound integer work; see cb_seq_algos.cuh for the
 // algorithms and the reference code they restate).
 //
-//  beam_kernel      one thread per window walks TF's trie beam search; the node pool + leaf slots of each window live
-//                   in a global workspace (L1/L2 resident), logits rows are read once (20 B/frame).
+//  beam_warp_kernel one warp per window walks TF's trie beam search cooperatively over shared memory (bit-identical to the
+//                   sequential routine cb_beam_decode_one); the product path.
+//  beam_kernel      one thread per window runs cb_beam_decode_one over a global workspace: the overflow fallback (and
+//                   the reference the cooperative kernel is tested against).
 //  assembly         asm_compact (drop empty windows like sparse2dense, chiron_eval.py:56-66) -> asm_disp (one thread per
 //                   adjacent window pair: stick / glue / difflib-exact simple displacement) -> asm_scan (prefix sum ->
 //                   window coordinates, read length) -> asm_vote (count matrix [4,len] + quality sums, atomics) ->

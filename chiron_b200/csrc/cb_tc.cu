@@ -1,26 +1,26 @@
 // tcgen05 tensor-core contractions for the conv stack and the hoisted LSTM input projection
-// (CB_PREC_TC_SPLIT / CB_PREC_TC_FAST).  Same maths as cb_gemm_simt.cu (chiron/cnn.py:60-82,251-261;
+// (CB_PREC_TC_SPLIT / CB_PREC_TC_PRECISE / CB_PREC_TC_FAST).  Same maths as cb_gemm_simt.cu (chiron/cnn.py:60-82,251-261;
 // chiron/rnn.py:49-50,64), different machine:
 //
-//   * operands are fp16 hi/lo splits (a = hi + lo, |lo| <= 2^-11 |a|): D = Ah*Wh + Ah*Wl + Al*Wh, three
-//     tcgen05.mma.kind::f16 per K-step with fp32 accumulation in TMEM.  CB_PREC_TC_FAST issues only Ah*Wh.
+//   * operands are fp16 hi/lo splits (a = hi + lo, |lo| <= 2^-11 |a|): D = Ah*Wl + Al*Wh + Ah*Wh, three
+//     tcgen05.mma.kind::f16 per K-step with fp32 accumulation in TMEM.  CB_PREC_TC_FAST issues only Ah*Wh;
+//     CB_PREC_TC_PRECISE sweeps K twice (all low-order products first) to spare the truncating accumulator.
 //   * activations travel between layers as time-major operand images (cb_tc_common.cuh): the epilogue of the producing
-//     kernel writes the hi/lo k-group planes, so the A side of a pipeline stage is 8 cp.async.bulk copies of 2 KB (a conv
-//     tap is the same plane shifted by one frame = Bp rows; a strided conv multiplies the frame index; the appended 1x1
-//     branch input is a second image).  Block-1 conv2a (a rank-1 function of the raw signal, cnn.py:254) is written as an
-//     image by gen_conv2a_kernel.
+//     kernel writes the hi/lo k-group planes; a conv tap is the same plane shifted by one frame = Bp rows, a strided conv
+//     multiplies the frame index, the appended 1x1 branch input is a second image.  Block-1 conv2a (a rank-1 function of
+//     the raw signal, cnn.py:254) is written as an image by gen_conv2a_kernel.
 //   * the A side of a stage (hi and lo, 4 k-group planes x 128 rows x 16 B each) is ONE cp.async.bulk.tensor: the image
 //     is described to the TMA unit as a 3-D tensor {256 x 8-byte elements = 128 rows, plane, hi|lo} whose {256,4,2} box
-//     lands in shared memory as [hi|lo][4 k-groups][128 rows][8 halfs] -- the UMMA core-matrix order.  (Eight 2 KB
-//     cp.async.bulk copies per stage made the single loader thread the bound of every contraction: ~120 cycles each.)
-//   * persistent CTAs (one per SM), warp-specialised: 8 epilogue warps (TMEM -> scale/shift/residual/ReLU -> hi/lo
-//     image or fp32), 1 MMA-issuing thread, 1 loader thread (weight + activation images, mbarrier expect-tx); smem
-//     full/empty ring (STAGES deep) and a double-buffered TMEM accumulator so the epilogue of tile i overlaps the MMAs
-//     of tile i+1.
+//     lands in shared memory as [hi|lo][4 k-groups][128 rows][8 halfs] -- the UMMA K-major no-swizzle core-matrix order.
+//   * persistent CTAs, warp-specialised: 8 epilogue warps (TMEM -> scale/shift/residual/ReLU -> hi/lo image or fp32),
+//     one MMA warp, one loader warp (both run warp-convergent; an elected lane issues); shared-memory full/empty ring
+//     (STAGES deep) and a double-buffered TMEM accumulator so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   * CTA-PAIR form (gemm_tc_pair_kernel, the convolutions): tcgen05 cta_group::2, M = 256 over two m-tiles; each CTA
+//     stages its own A tile and half of the B tile, every byte counted on the leader's barrier; multicast commits.
 //   * RESIDENT-WEIGHT mode (contractions whose whole n-tile of W fits beside the A ring -- the N = 8H LSTM input
-//     projection): a CTA is bound to ONE n-tile, loads its hi/lo weight image once and then streams only A tiles.  The
-//     streaming mode re-reads the B tile from L2 for every 128-row tile, which ncu showed to be the bound of that
-//     contraction (xbar->L1 9 TB/s + 2.5 TB/s of stores against the ~12 TB/s the L2 slices sustain).
+//     projection): a CTA is bound to ONE n-tile, loads its hi/lo weight image once and then streams only A boxes.
+// What bounds them: the convolutions run at the board's power cap (0.87 of the sustained cuBLAS bf16
+// figure), the input projection at the HBM write bandwidth of its 6.65 GB fp32 output.
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
