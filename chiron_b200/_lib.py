@@ -13,6 +13,8 @@ LIB_PATH = os.environ.get("CHIRON_B200_LIB") or os.path.join(_HERE, "lib", "libc
 CB_OK = 0
 PREC_FP32, PREC_TC_SPLIT, PREC_TC_FAST, PREC_TC_PRECISE = 0, 1, 2, 3
 ASM_SIMPLE, ASM_GLUE, ASM_STICK = 0, 1, 2
+BN_POPULATION, BN_BATCH = 0, 1
+BN_MODES = {"population": BN_POPULATION, "batch": BN_BATCH}
 PRECISIONS = {"fp32": PREC_FP32, "tc": PREC_TC_SPLIT, "tc_split": PREC_TC_SPLIT, "tc_fast": PREC_TC_FAST,
               "tc_precise": PREC_TC_PRECISE}
 ASM_KERNELS = {"simple": ASM_SIMPLE, "glue": ASM_GLUE, "stick": ASM_STICK}
@@ -23,6 +25,8 @@ SIGNATURES = {
     "cb_destroy": (c_int, [c_void_p]),
     "cb_last_error": (c_char_p, []),
     "cb_version": (c_char_p, []),
+    "cb_set_bn_mode": (c_int, [c_void_p, c_int]),
+    "cb_bn_mode": (c_int, [c_void_p]),
     "cb_out_len": (c_int, [c_void_p, c_int]),
     "cb_n_class": (c_int, [c_void_p]),
     "cb_precision": (c_int, [c_void_p]),

@@ -16,7 +16,8 @@ from typing import Dict
 import numpy as np
 
 from . import tf_bundle
-from .model import (ModelConfig, NORM_FULL_MAD, NORM_UNIQUE_MAD, RNN_NORMAL, RNN_RNA, pack_blob)
+from .model import (BN_BATCH, BN_POPULATION, ModelConfig, NORM_FULL_MAD, NORM_UNIQUE_MAD, RNN_NORMAL, RNN_RNA,
+                    pack_blob)
 
 
 def convert_tensors(raw: Dict[str, np.ndarray], conv_attrs: Dict[str, dict], model_json: dict) -> bytes:
@@ -27,6 +28,7 @@ def convert_tensors(raw: Dict[str, np.ndarray], conv_attrs: Dict[str, dict], mod
         raise ValueError("checkpoint has no res_layerN/branch2/conv2b/weights")
     C = raw["res_layer1/branch2/conv2b/weights"].shape[-1]
     k, stride, mask = [], [], 0
+    bn_modes = set()
     tensors: Dict[str, np.ndarray] = {}
     for b in range(n_blocks):
         p = "res_layer%d" % (b + 1)
@@ -44,14 +46,29 @@ def convert_tensors(raw: Dict[str, np.ndarray], conv_attrs: Dict[str, dict], mod
             w = raw["%s/%s/weights" % (p, conv)]
             tensors["%s/%s/weights" % (p, conv)] = w.reshape(w.shape[1:]) if conv.endswith("conv2b") \
                 else w.reshape(w.shape[2:])
-            has_bn = "%s/%s_bn/scale" % (p, conv) in raw
+            # Two variable sets exist.  The shipped checkpoints: batchnorm()'s <conv>_bn/{scale,offset,pop_mean,pop_var}
+            # (chiron/cnn.py:140-148) -> population mode.  A model trained at HEAD: simple_global_bn's
+            # <conv>_bn/<conv>_bn_{scale,offset} (chiron/cnn.py:65-68,181-186) and no statistics -> batch mode.
+            leaf = conv.rsplit("/", 1)[-1]
+            head_fmt = "%s/%s_bn/%s_bn_%%s" % (p, conv, leaf)
+            has_pop = "%s/%s_bn/scale" % (p, conv) in raw
+            has_head = head_fmt % "scale" in raw
+            has_bn = has_pop or has_head
             if conv == "branch1/conv1":
                 mask |= int(has_bn) << b
             elif not has_bn:
                 raise ValueError("%s/%s has no BN variables in the checkpoint" % (p, conv))
-            if has_bn:
+            if has_pop:
+                bn_modes.add(BN_POPULATION)
                 for n in ("scale", "offset", "pop_mean", "pop_var"):
                     tensors["%s/%s_bn/%s" % (p, conv, n)] = raw["%s/%s_bn/%s" % (p, conv, n)]
+            elif has_head:
+                bn_modes.add(BN_BATCH)
+                scale = np.asarray(raw[head_fmt % "scale"], dtype=np.float32).reshape(-1)
+                tensors["%s/%s_bn/scale" % (p, conv)] = scale
+                tensors["%s/%s_bn/offset" % (p, conv)] = np.asarray(raw[head_fmt % "offset"], np.float32).reshape(-1)
+                tensors["%s/%s_bn/pop_mean" % (p, conv)] = np.zeros_like(scale)     # unused in batch mode
+                tensors["%s/%s_bn/pop_var" % (p, conv)] = np.ones_like(scale)
     if any(n.startswith("BDLSTM_rnn/") for n in raw):
         layout = RNN_NORMAL
         fmt = "BDLSTM_rnn/cell_{l}/bidirectional_rnn/{d}/lstm_cell/{t}"     # chiron/rnn.py:62-64
@@ -79,9 +96,11 @@ def convert_tensors(raw: Dict[str, np.ndarray], conv_attrs: Dict[str, dict], mod
     # Input normalisation is a property of how the weights were trained (SURVEY.md finding 4): DNA_default needs
     # the unique-value median/MAD (pinned by the golden outputs); RNA_default a scale~1 normalisation (unpinned).
     sig_norm = NORM_UNIQUE_MAD if layout == RNN_NORMAL else NORM_FULL_MAD
+    if len(bn_modes) != 1:
+        raise ValueError("checkpoint mixes population-statistics and batch-statistics BatchNorm variables")
     cfg = ModelConfig(n_blocks=n_blocks, channels=int(C), hidden=int(H), n_layers=n_layers, n_class=int(n_class),
                       rnn_layout=layout, branch1_bn_mask=mask, k=k, stride=stride, sig_norm=sig_norm,
-                      reverse_signal=int(layout == RNN_RNA))
+                      reverse_signal=int(layout == RNN_RNA), bn_mode=bn_modes.pop())
     return pack_blob(cfg, tensors)
 
 

@@ -27,7 +27,7 @@ struct BlobHeader {               // chiron_b200/model.py: "<4s8i8i8i6iq" (packe
     char magic[4];
     int32_t version, n_blocks, channels, hidden, n_layers, n_class, rnn_layout, branch1_bn_mask;
     int32_t k[8], stride[8];
-    int32_t sig_norm, reverse_signal, reserved[4];
+    int32_t sig_norm, reverse_signal, bn_mode, reserved[3];
 };
 constexpr size_t HEADER_BYTES = 4 + 30 * 4 + 8;
 
@@ -84,10 +84,11 @@ extern "C" int cb_create(const void* blob, size_t nbytes, int device, int precis
     // ---- walk the canonical tensor order (model.py: tensor_specs) and derive the kernels' operands ----------------
     size_t pos = 0;
     auto take = [&](size_t n) -> const float* { const float* p = w + pos; pos += n; return p; };
-    struct Bn { std::vector<float> inv, shift; };
+    struct Bn { std::vector<float> inv, shift; const float *scale, *offset; };
     auto take_bn = [&]() {           // tf.nn.batch_normalization, population statistics (cnn.py:160-161)
         Bn bn; bn.inv.resize(C); bn.shift.resize(C);
         const float *scale = take(C), *offset = take(C), *mean = take(C), *var = take(C);
+        bn.scale = scale; bn.offset = offset;
         for (int n = 0; n < C; ++n) {
             bn.inv[n] = scale[n] * (1.0f / sqrtf(var[n] + BN_EPS));
             bn.shift[n] = offset[n] - mean[n] * bn.inv[n];
@@ -97,6 +98,7 @@ extern "C" int cb_create(const void* blob, size_t nbytes, int device, int precis
     HostBuilder hb;
     size_t o_conv2a[CB_MAX_BLOCKS][2], o_conv2b[CB_MAX_BLOCKS][2], o_convc[CB_MAX_BLOCKS][2];
     size_t o_g[3] = {0, 0, 0}, o_r[3] = {0, 0, 0};
+    struct RawOff { size_t W, scale, offset; bool bn; } o_raw[CB_MAX_BLOCKS][4];   // branch1, conv2a, conv2b, conv2c
     for (int b = 0; b < c.n_blocks; ++b) {
         const int cin = b == 0 ? 1 : C;
         const float* w1 = take((size_t)cin * C);
@@ -144,7 +146,21 @@ extern "C" int cb_create(const void* blob, size_t nbytes, int device, int precis
             o_convc[b][0] = hb.add(f);
             o_convc[b][1] = hb.add(sh);
         }
+        {   // the same four convolutions with nothing folded, for the batch-statistics BN mode (cnn.py:166-188)
+            const float* ws[4] = {w1, w2a, w2b, w2c};
+            const size_t wn[4] = {(size_t)cin * C, (size_t)cin * C, (size_t)c.k[b] * C * C, (size_t)C * C};
+            const Bn* bns[4] = {has_bn1 ? &bn1 : nullptr, &bna, &bnb, &bnc};
+            for (int i = 0; i < 4; ++i) {
+                o_raw[b][i].W = hb.add(std::vector<float>(ws[i], ws[i] + wn[i]));
+                o_raw[b][i].bn = bns[i] != nullptr;
+                if (bns[i]) {
+                    o_raw[b][i].scale = hb.add(std::vector<float>(bns[i]->scale, bns[i]->scale + C));
+                    o_raw[b][i].offset = hb.add(std::vector<float>(bns[i]->offset, bns[i]->offset + C));
+                }
+            }
+        }
     }
+    const size_t o_zeros = hb.add(std::vector<float>((size_t)(C > 8 * H ? C : 8 * H), 0.0f));
     size_t o_wx[CB_MAX_LAYERS][2], o_b[CB_MAX_LAYERS][2], o_whh[CB_MAX_LAYERS][2], o_wxcat[CB_MAX_LAYERS], o_bcat[CB_MAX_LAYERS];
     for (int l = 0; l < c.n_layers; ++l) {
         const int in = l == 0 ? C : (c.rnn_layout == 0 ? 2 * H : H);
@@ -199,7 +215,14 @@ extern "C" int cb_create(const void* blob, size_t nbytes, int device, int precis
         h->conv2a[b].W = base + o_conv2a[b][0]; h->conv2a[b].shift = base + o_conv2a[b][1];
         h->conv2b[b].W = base + o_conv2b[b][0]; h->conv2b[b].shift = base + o_conv2b[b][1];
         h->convc[b].W = base + o_convc[b][0];   h->convc[b].shift = base + o_convc[b][1];
+        cb_handle::RawConv* raw[4] = {&h->raw1[b], &h->raw2a[b], &h->raw2b[b], &h->raw2c[b]};
+        for (int i = 0; i < 4; ++i) {
+            raw[i]->W = base + o_raw[b][i].W;
+            raw[i]->scale = o_raw[b][i].bn ? base + o_raw[b][i].scale : nullptr;
+            raw[i]->offset = o_raw[b][i].bn ? base + o_raw[b][i].offset : nullptr;
+        }
     }
+    h->zeros = base + o_zeros;
     for (int l = 0; l < c.n_layers; ++l) {
         for (int d = 0; d < 2; ++d) {
             h->wx[l][d] = base + o_wx[l][d]; h->whh[l][d] = base + o_whh[l][d]; h->bias[l][d] = base + o_b[l][d];
@@ -215,9 +238,31 @@ extern "C" int cb_create(const void* blob, size_t nbytes, int device, int precis
         int rc = cb_tc_prepare(h, hb.data.data());
         if (rc != CB_OK) { cb_destroy(h); return rc; }
     }
+    if (hd.bn_mode != CB_BN_POPULATION) {
+        int rc = cb_set_bn_mode(h, hd.bn_mode);
+        if (rc != CB_OK) { cb_destroy(h); return rc; }
+    }
     *out = h;
     return CB_OK;
 }
+
+extern "C" int cb_set_bn_mode(cb_handle* h, int bn_mode) {
+    if (!h || (bn_mode != CB_BN_POPULATION && bn_mode != CB_BN_BATCH)) { cb_set_error("cb_set_bn_mode: bad arguments"); return CB_ERR_ARG; }
+    if (bn_mode == CB_BN_BATCH) {
+        if (h->precision != CB_PREC_FP32) {
+            cb_set_error("batch-statistics BatchNorm (CB_BN_BATCH) runs on the CB_PREC_FP32 path only");
+            return CB_ERR_ARG;
+        }
+        if (h->cfg.channels > 1024) { cb_set_error("batch-statistics BatchNorm needs channels <= 1024"); return CB_ERR_ARG; }
+        CB_CUDA(cudaSetDevice(h->device));
+        if (!h->bn_part) CB_CUDA(cudaMalloc(&h->bn_part, (size_t)CB_BN_MAX_PART * 2 * h->cfg.channels * sizeof(double)));
+        if (!h->bn_vec) CB_CUDA(cudaMalloc(&h->bn_vec, (size_t)CB_BN_VECS * h->cfg.channels * sizeof(float)));
+    }
+    h->bn_mode = bn_mode;
+    return CB_OK;
+}
+
+extern "C" int cb_bn_mode(const cb_handle* h) { return h ? h->bn_mode : CB_ERR_ARG; }
 
 extern "C" int cb_destroy(cb_handle* h) {
     if (!h) return CB_OK;
@@ -242,6 +287,8 @@ extern "C" int cb_destroy(cb_handle* h) {
     if (h->beam_ws) cudaFree(h->beam_ws);
     if (h->asm_ws) cudaFree(h->asm_ws);
     if (h->d_flag) cudaFree(h->d_flag);
+    if (h->bn_part) cudaFree(h->bn_part);
+    if (h->bn_vec) cudaFree(h->bn_vec);
     for (int i = 0; i < 8; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < CB_PROF_MAX; ++i)
         for (int j = 0; j < 2; ++j) if (h->prof_ev[i][j]) cudaEventDestroy(h->prof_ev[i][j]);
@@ -323,28 +370,91 @@ static int run_gemm(cb_handle* h, const GemmProblem& p, cudaStream_t s, int cat)
     return rc;
 }
 
-extern "C" int cb_seq_len_out(cb_handle* h, const int32_t* seq_len_in, int B, int L, int32_t* seq_len_out, void* stream) {
-    if (!h || !seq_len_in || !seq_len_out || B < 0 || L < 1) { cb_set_error("cb_seq_len_out: bad arguments"); return CB_ERR_ARG; }
-    CB_CUDA(cudaSetDevice(h->device));
-    return cb_launch_seq_len(h, seq_len_in, B, L, out_len_of(h->cfg, L), seq_len_out, (cudaStream_t)stream);
+// Residual conv stack with batch-statistics BN (HEAD's conv_layer -> simple_global_bn, chiron/cnn.py:65-68,166-188;
+// residual_layer cnn.py:234-262): every convolution is run raw (nothing folded, no shift, no ReLU), its output is reduced
+// to per-channel batch moments, and the normalisation + activation (+ the residual sum) is a separate pass.
+// On return *feat is the block stack's output [B*T,C] (one of act[]) and *t_feat its frame count.
+static int conv_stack_batch_bn(cb_handle* h, const float* x, int B, int L, cudaStream_t s, const float** feat, int* t_feat) {
+    const CbConfig& c = h->cfg;
+    const int C = c.channels;
+    int rc;
+    float* vec[CB_BN_VECS];
+    for (int i = 0; i < CB_BN_VECS; ++i) vec[i] = h->bn_vec + (size_t)i * C;
+    int t_in = L;
+    const float* X = nullptr;
+    int xi = -1;
+    auto raw_gemm = [&](GemmProblem& g, const float* W, float* out) {
+        g.N = C; g.W = W; g.shift = h->zeros; g.relu = 0; g.out = out; g.ldo = C;
+        return run_gemm(h, g, s, CB_CAT_CONV);
+    };
+    for (int b = 0; b < c.n_blocks; ++b) {
+        const int st = c.stride[b], k = c.k[b];
+        const int t_out = (t_in + st - 1) / st;
+        int pad = (t_out - 1) * st + k - t_in; if (pad < 0) pad = 0;     // TF 'SAME'
+        const int left = pad / 2;
+        int ia = (xi + 1) % 3, ib = (xi + 2) % 3;
+        if (xi < 0) { ia = 0; ib = 1; }
+        const long long M_in = (long long)B * t_in, M_out = (long long)B * t_out;
+        GemmProblem g;
+        BnApplyArgs ap;
+        // conv2a 1x1 + BN + ReLU
+        if (b == 0) {       // rank-1 in the raw signal: statistics from the samples, tensor generated inside conv2b's loader
+            if ((rc = cb_launch_bn_rank1(h, x, B, t_in, 1, t_in, h->raw2a[b].W, h->raw2a[b].scale, h->raw2a[b].offset,
+                                         vec[0], vec[1], s)) != CB_OK) return rc;
+        } else {
+            memset(&g, 0, sizeof(g));
+            g.M = (int)M_in; g.K = C; g.t_out = t_in; g.t_in0 = t_in; g.stride0 = 1; g.taps = 1; g.c0 = C; g.src0 = X; g.lda0 = C;
+            if ((rc = raw_gemm(g, h->raw2a[b].W, h->act[ia])) != CB_OK) return rc;
+            if ((rc = cb_launch_bn_stats(h, h->act[ia], M_in, h->raw2a[b].scale, h->raw2a[b].offset, vec[0], vec[1], s)) != CB_OK) return rc;
+            memset(&ap, 0, sizeof(ap));
+            ap.a = h->act[ia]; ap.a_inv = vec[0]; ap.a_sh = vec[1]; ap.relu = 1; ap.out = h->act[ia]; ap.M = M_in;
+            if ((rc = cb_launch_bn_apply(h, ap, s)) != CB_OK) return rc;
+        }
+        // conv2b 1xk (stride) + BN + ReLU -> act[ib]
+        memset(&g, 0, sizeof(g));
+        g.M = (int)M_out; g.K = k * C; g.t_out = t_out; g.t_in0 = t_in; g.stride0 = st; g.taps = k; g.left = left; g.c0 = C;
+        if (b == 0) { g.gen = 1; g.x = x; g.gw = h->raw2a[b].W; g.ginv = vec[0]; g.gsh = vec[1]; }
+        else { g.src0 = h->act[ia]; g.lda0 = C; }
+        if ((rc = raw_gemm(g, h->raw2b[b].W, h->act[ib])) != CB_OK) return rc;
+        if ((rc = cb_launch_bn_stats(h, h->act[ib], M_out, h->raw2b[b].scale, h->raw2b[b].offset, vec[2], vec[3], s)) != CB_OK) return rc;
+        memset(&ap, 0, sizeof(ap));
+        ap.a = h->act[ib]; ap.a_inv = vec[2]; ap.a_sh = vec[3]; ap.relu = 1; ap.out = h->act[ib]; ap.M = M_out;
+        if ((rc = cb_launch_bn_apply(h, ap, s)) != CB_OK) return rc;
+        // conv2c 1x1 + BN -> act[ia] (raw), its inv/shift in vec[4], vec[5]
+        memset(&g, 0, sizeof(g));
+        g.M = (int)M_out; g.K = C; g.t_out = t_out; g.t_in0 = t_out; g.stride0 = 1; g.taps = 1; g.c0 = C; g.src0 = h->act[ib]; g.lda0 = C;
+        if ((rc = raw_gemm(g, h->raw2c[b].W, h->act[ia])) != CB_OK) return rc;
+        if ((rc = cb_launch_bn_stats(h, h->act[ia], M_out, h->raw2c[b].scale, h->raw2c[b].offset, vec[4], vec[5], s)) != CB_OK) return rc;
+        // branch1: 1x1 conv (stride) of the block input (+ BN), then relu(branch1 + conv2c)
+        memset(&ap, 0, sizeof(ap));
+        ap.a = h->act[ia]; ap.a_inv = vec[4]; ap.a_sh = vec[5]; ap.relu = 1; ap.out = h->act[ia]; ap.M = M_out;
+        if (b == 0) {
+            if ((rc = cb_launch_bn_rank1(h, x, B, t_in, st, t_out, h->raw1[b].W, h->raw1[b].scale, h->raw1[b].offset,
+                                         vec[6], vec[7], s)) != CB_OK) return rc;
+            ap.x = x; ap.rw = h->raw1[b].W; ap.rinv = vec[6]; ap.rsh = vec[7]; ap.t_out = t_out; ap.t_inr = t_in; ap.strider = st;
+        } else {
+            memset(&g, 0, sizeof(g));     // conv2b's output (act[ib]) has been consumed: reuse it for the raw branch
+            g.M = (int)M_out; g.K = C; g.t_out = t_out; g.t_in0 = t_in; g.stride0 = st; g.taps = 1; g.left = 0; g.c0 = C; g.src0 = X; g.lda0 = C;
+            if ((rc = raw_gemm(g, h->raw1[b].W, h->act[ib])) != CB_OK) return rc;
+            ap.b = h->act[ib];
+            if (h->raw1[b].scale) {
+                if ((rc = cb_launch_bn_stats(h, h->act[ib], M_out, h->raw1[b].scale, h->raw1[b].offset, vec[6], vec[7], s)) != CB_OK) return rc;
+                ap.b_inv = vec[6]; ap.b_sh = vec[7];
+            }
+        }
+        if ((rc = cb_launch_bn_apply(h, ap, s)) != CB_OK) return rc;
+        X = h->act[ia]; xi = ia; t_in = t_out;
+    }
+    *feat = X; *t_feat = t_in;
+    return CB_OK;
 }
 
-extern "C" int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_out, int B, int L, float* logits,
-                          float* path_prob, void* stream) {
-    if (!h || !x || !seq_len_out || !logits || B < 0 || L < 1) { cb_set_error("cb_forward: bad arguments"); return CB_ERR_ARG; }
-    if (B == 0) return CB_OK;
-    if ((long long)B * L > 0x7fffffffLL / 2) { cb_set_error("cb_forward: B*L too large"); return CB_ERR_ARG; }
-    CB_CUDA(cudaSetDevice(h->device));
-    cudaStream_t s = (cudaStream_t)stream;
-    if (h->precision != CB_PREC_FP32) return cb_forward_tc(h, x, seq_len_out, B, L, logits, path_prob, s);
-    int rc = ensure_workspace(h, B, L);
-    if (rc != CB_OK) return rc;
+// Residual conv stack with population BN folded into the weights (the shipped checkpoints' graph: cnn.py:234-262,
+// 380-389 with batchnorm() cnn.py:125-163).  On return *feat is the stack's output [B*T,C] and *t_feat its frame count.
+static int conv_stack_folded(cb_handle* h, const float* x, int B, int L, cudaStream_t s, const float** feat, int* t_feat) {
     const CbConfig& c = h->cfg;
-    const int C = c.channels, H = c.hidden;
-    h->prof_n = 0;
-    if (h->timing) CB_CUDA(cudaEventRecord(h->ev[0], s));
-
-    // ---- residual conv stack (cnn.py:234-262, 380-389) ----------------------------------------------------------
+    const int C = c.channels;
+    int rc;
     int t_in = L;
     const float* X = nullptr;          // block input (nullptr = raw signal for block 1)
     int xi = -1;                       // which act[] buffer holds X
@@ -384,6 +494,39 @@ extern "C" int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_o
                 if ((rc = run_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
         X = h->act[ia]; xi = ia; t_in = t_out;
     }
+    *feat = X; *t_feat = t_in;
+    return CB_OK;
+}
+
+extern "C" int cb_seq_len_out(cb_handle* h, const int32_t* seq_len_in, int B, int L, int32_t* seq_len_out, void* stream) {
+    if (!h || !seq_len_in || !seq_len_out || B < 0 || L < 1) { cb_set_error("cb_seq_len_out: bad arguments"); return CB_ERR_ARG; }
+    CB_CUDA(cudaSetDevice(h->device));
+    return cb_launch_seq_len(h, seq_len_in, B, L, out_len_of(h->cfg, L), seq_len_out, (cudaStream_t)stream);
+}
+
+extern "C" int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_out, int B, int L, float* logits,
+                          float* path_prob, void* stream) {
+    if (!h || !x || !seq_len_out || !logits || B < 0 || L < 1) { cb_set_error("cb_forward: bad arguments"); return CB_ERR_ARG; }
+    if (B == 0) return CB_OK;
+    if ((long long)B * L > 0x7fffffffLL / 2) { cb_set_error("cb_forward: B*L too large"); return CB_ERR_ARG; }
+    CB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h->precision != CB_PREC_FP32) {
+        if (h->bn_mode != CB_BN_POPULATION) { cb_set_error("cb_forward: batch-statistics BatchNorm needs CB_PREC_FP32"); return CB_ERR_ARG; }
+        return cb_forward_tc(h, x, seq_len_out, B, L, logits, path_prob, s);
+    }
+    int rc = ensure_workspace(h, B, L);
+    if (rc != CB_OK) return rc;
+    const CbConfig& c = h->cfg;
+    const int C = c.channels, H = c.hidden;
+    h->prof_n = 0;
+    if (h->timing) CB_CUDA(cudaEventRecord(h->ev[0], s));
+
+    // ---- residual conv stack (cnn.py:234-262, 380-389) ----------------------------------------------------------
+    int t_in = L;
+    const float* X = nullptr;
+    rc = h->bn_mode == CB_BN_BATCH ? conv_stack_batch_bn(h, x, B, L, s, &X, &t_in) : conv_stack_folded(h, x, B, L, s, &X, &t_in);
+    if (rc != CB_OK) return rc;
     const int T = t_in;
     const int M = B * T;
     h->fea = X;

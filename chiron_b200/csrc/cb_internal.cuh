@@ -12,6 +12,8 @@
 #define CB_MAX_BLOCKS 8
 #define CB_MAX_LAYERS 8
 #define CB_PROF_MAX 96
+#define CB_BN_MAX_PART 1024       // per-CTA partial sums of a batch-statistics BN reduction (cb_bn.cu)
+#define CB_BN_VECS 8              // [C]-float scratch vectors holding inv/shift pairs of the BNs in flight
 enum { CB_CAT_CONV = 0, CB_CAT_LSTM_IN = 1, CB_CAT_LSTM_REC = 2, CB_CAT_HEAD = 3, CB_CAT_COUNT = 4 };
 
 void cb_set_error(const char* fmt, ...);
@@ -84,6 +86,17 @@ struct TcGemm {
     CbImg o; int o_plane0;
 };
 
+// ---- batch-statistics BatchNorm (cb_bn.cu): out = act(a*a_inv + a_sh [+ b*b_inv + b_sh | + b] [+ rank-1 branch]) --------
+struct BnApplyArgs {
+    const float *a, *a_inv, *a_sh;
+    const float *b, *b_inv, *b_sh;          // b_inv == nullptr: b is added as it is (branch1 without BN)
+    const float *x, *rw, *rinv, *rsh;       // rank-1 branch of the raw signal: (x[win*t_inr + to*strider]*rw)*rinv + rsh
+    int t_out, t_inr, strider;
+    int relu;
+    float* out;                             // may alias a (every element is read and written by the same thread)
+    long long M;
+};
+
 struct LstmProblem {         // both directions of one layer (grid.y = direction)
     int B, T, H;
     const float* pre;         // [B*T, ld_pre] hoisted input projection + bias; direction d uses columns [d*4H, (d+1)*4H)
@@ -103,6 +116,13 @@ struct cb_handle {
     float* d_weights;                 // one allocation holding everything below
     size_t weights_floats;
     struct ConvW { const float *W, *shift; } conv2a[CB_MAX_BLOCKS], conv2b[CB_MAX_BLOCKS], convc[CB_MAX_BLOCKS];
+    // batch-statistics BN mode: the convolutions as they are in the checkpoint (nothing folded) + BN scale/offset
+    int bn_mode;
+    struct RawConv { const float *W, *scale, *offset; } raw1[CB_MAX_BLOCKS], raw2a[CB_MAX_BLOCKS], raw2b[CB_MAX_BLOCKS],
+        raw2c[CB_MAX_BLOCKS];             // raw1[b].scale == nullptr: block b's branch1 has no BN
+    const float* zeros;                   // [max(C, 8H)] zero shift vector
+    double* bn_part;                      // [CB_BN_MAX_PART][2][C] partial sums
+    float* bn_vec;                        // [CB_BN_VECS][C]
     const float *g_w, *g_inv, *g_sh;  // block-1 conv2a rank-1 generator
     const float *r_w, *r_inv, *r_sh;  // block-1 branch1 rank-1 residual
     const float* wx[CB_MAX_LAYERS][2];   // LSTM input kernels  [in,4H] per direction
@@ -142,6 +162,11 @@ struct cb_handle {
 // ---- launchers (each returns CB_OK or an error code; they bump h->launches) -----------------------------------------
 int cb_launch_gemm_simt(cb_handle* h, const GemmProblem& p, cudaStream_t s);
 int cb_launch_lstm_simt(cb_handle* h, const LstmProblem& p, cudaStream_t s);
+int cb_launch_bn_rank1(cb_handle* h, const float* x, int B, int t_in, int stride, int t_out, const float* w,
+                       const float* scale, const float* offset, float* inv, float* shift, cudaStream_t s);
+int cb_launch_bn_stats(cb_handle* h, const float* X, long long M, const float* scale, const float* offset, float* inv,
+                       float* shift, cudaStream_t s);
+int cb_launch_bn_apply(cb_handle* h, const BnApplyArgs& a, cudaStream_t s);
 int cb_launch_gemm_tc(cb_handle* h, const TcGemm& g, cudaStream_t s);
 const float* cb_tc_lstm_bias(cb_handle* h, int layer, int d);   // biases in unit-major gate-column order
 int cb_launch_transpose_x(cb_handle* h, const float* x, int B, int L, int Bp, float* xT, cudaStream_t s);

@@ -36,7 +36,10 @@ def _ptr(a: Optional[np.ndarray]):
 
 
 class Basecaller:
-    def __init__(self, model: str = "DNA_default", device: int = 0, precision: str = "fp32"):
+    def __init__(self, model: str = "DNA_default", device: int = 0, precision: str = "fp32",
+                 bn_mode: Optional[str] = None):
+        """``bn_mode``: None = what the model's blob header says; "population" / "batch" override it
+        (cb_set_bn_mode; "batch" = HEAD's simple_global_bn, chiron/cnn.py:166-188, fp32 precision only)."""
         self.lib = _lib.load()
         self.cfg, _, blob = load_model(model)
         self.device = int(device)
@@ -46,6 +49,13 @@ class Basecaller:
         _lib.check(self.lib.cb_create(ctypes.cast(buf, ctypes.c_void_p), len(blob), self.device,
                                       _lib.PRECISIONS[precision], ctypes.byref(h)), "cb_create")
         self.h = h
+        if bn_mode is not None:
+            rc = self.lib.cb_set_bn_mode(self.h, _lib.BN_MODES[bn_mode])
+            if rc != _lib.CB_OK:
+                msg = self.lib.cb_last_error().decode("utf-8", "replace")
+                self.close()
+                raise _lib.ChironB200Error("cb_set_bn_mode failed (%d): %s" % (rc, msg))
+        self.bn_mode = self.lib.cb_bn_mode(self.h)
         self.n_class = self.lib.cb_n_class(self.h)
 
     def close(self):

@@ -10,7 +10,9 @@ the blob header.  Blob layout (little endian):
     int32    n_blocks, channels, hidden, n_layers, n_class, rnn_layout (0 = stacked-bidirectional "normal",
              1 = per-direction MultiRNNCell "rna"), branch1_bn_mask (bit b = block b's branch1 conv has BN)
     int32    k[8], stride[8]          (conv2b kernel width / stride of block b; branch1 shares the stride)
-    int32    sig_norm (0 none, 1 unique-median/MAD, 2 full-signal median/MAD), reverse_signal, reserved[4]
+    int32    sig_norm (0 none, 1 unique-median/MAD, 2 full-signal median/MAD), reverse_signal,
+             bn_mode (0 = population statistics, the shipped checkpoints' tf.cond BN, chiron/cnn.py:125-163;
+             1 = batch statistics, HEAD's simple_global_bn, chiron/cnn.py:166-188), reserved[3]
     int64    n_floats
     float32  weights[n_floats]       in the canonical order of ``tensor_specs``
 
@@ -33,6 +35,7 @@ MAX_BLOCKS = 8
 BN_EPS = 1e-5                       # chiron/cnn.py:125 (epsilon=1e-5), :187
 RNN_NORMAL, RNN_RNA = 0, 1
 NORM_NONE, NORM_UNIQUE_MAD, NORM_FULL_MAD = 0, 1, 2
+BN_POPULATION, BN_BATCH = 0, 1
 _HEADER = struct.Struct("<4s8i8i8i6iq")
 
 
@@ -49,6 +52,7 @@ class ModelConfig:
     stride: List[int] = field(default_factory=lambda: [1, 1, 1])
     sig_norm: int = NORM_UNIQUE_MAD
     reverse_signal: int = 0
+    bn_mode: int = BN_POPULATION
 
     def total_stride(self) -> int:
         s = 1
@@ -112,7 +116,7 @@ def pack_blob(cfg: ModelConfig, tensors: Dict[str, np.ndarray]) -> bytes:
     s = list(cfg.stride) + [0] * (MAX_BLOCKS - len(cfg.stride))
     head = _HEADER.pack(MAGIC, 1, cfg.n_blocks, cfg.channels, cfg.hidden, cfg.n_layers, cfg.n_class, cfg.rnn_layout,
                         cfg.branch1_bn_mask, *k[:MAX_BLOCKS], *s[:MAX_BLOCKS], cfg.sig_norm, cfg.reverse_signal,
-                        0, 0, 0, 0, flat.size)
+                        cfg.bn_mode, 0, 0, 0, flat.size)
     return head + flat.tobytes()
 
 
@@ -123,9 +127,10 @@ def unpack_blob(blob: bytes) -> Tuple[ModelConfig, Dict[str, np.ndarray]]:
     n_blocks, channels, hidden, n_layers, n_class, rnn_layout, mask = vals[2:9]
     k = list(vals[9:17])[:n_blocks]
     s = list(vals[17:25])[:n_blocks]
-    sig_norm, reverse_signal = vals[25], vals[26]
+    sig_norm, reverse_signal, bn_mode = vals[25], vals[26], vals[27]
     n_floats = vals[31]
-    cfg = ModelConfig(n_blocks, channels, hidden, n_layers, n_class, rnn_layout, mask, k, s, sig_norm, reverse_signal)
+    cfg = ModelConfig(n_blocks, channels, hidden, n_layers, n_class, rnn_layout, mask, k, s, sig_norm, reverse_signal,
+                      bn_mode)
     flat = np.frombuffer(blob, dtype="<f4", count=n_floats, offset=_HEADER.size)
     tensors: Dict[str, np.ndarray] = {}
     pos = 0
@@ -136,6 +141,40 @@ def unpack_blob(blob: bytes) -> Tuple[ModelConfig, Dict[str, np.ndarray]]:
     if pos != n_floats:
         raise ValueError("weight blob has %d floats, topology needs %d" % (n_floats, pos))
     return cfg, tensors
+
+
+def random_tensors(cfg: ModelConfig, seed: int = 0) -> Dict[str, np.ndarray]:
+    """Random-init weights of an arbitrary residual-stack + BiLSTM topology (there are shipped checkpoints only for
+    DNA_default and RNA_default): the reference's initialisers where they matter for the scale of the activations --
+    Xavier-normal convolutions (chiron/cnn.py:41-45), truncated-normal head (chiron/rnn.py:73-88), TF's default
+    Glorot-uniform LSTM kernels -- and BN statistics of a plausible trained model.  Used by the parity tests and the
+    configuration sweeps for topologies such as the 5-block ``rna_test`` (chiron/cnn.py:555-566)."""
+    rng = np.random.default_rng(seed)
+    out: Dict[str, np.ndarray] = {}
+    for name, shape in tensor_specs(cfg):
+        leaf = name.rsplit("/", 1)[-1]
+        if leaf == "scale":
+            v = rng.uniform(0.6, 1.4, size=shape)
+        elif leaf == "offset":
+            v = rng.normal(0.0, 0.1, size=shape)
+        elif leaf == "pop_mean":
+            v = rng.normal(0.0, 0.1, size=shape)
+        elif leaf == "pop_var":
+            v = rng.uniform(0.5, 1.5, size=shape)
+        elif leaf == "kernel":
+            lim = 3.0 * np.sqrt(6.0 / (shape[0] + shape[1]))     # 3x Glorot: gates that move with the input
+            v = rng.uniform(-lim, lim, size=shape)
+        elif leaf in ("bias", "bias_class"):
+            v = rng.normal(0.0, 0.05, size=shape)
+        elif name == "rnn_fnn_layer/weights":
+            v = rng.normal(0.0, np.sqrt(2.0 / (2 * cfg.hidden)), size=shape) + 0.5
+        elif name == "rnn_fnn_layer/weights_class":
+            v = rng.normal(0.0, 8.0 * np.sqrt(2.0 / cfg.hidden), size=shape)    # logits of a trained model's magnitude
+        else:                                   # convolution weights [.., fan_in, C]
+            fan_in = int(np.prod(shape[:-1]))
+            v = rng.normal(0.0, np.sqrt(2.0 / (fan_in + shape[-1])) * (3.0 if fan_in == 1 else 1.4), size=shape)
+        out[name] = v.astype(np.float32)
+    return out
 
 
 def header_size() -> int:

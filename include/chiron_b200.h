@@ -43,6 +43,13 @@ enum {
                             * full magnitude: about a third of the logit error of TC_SPLIT for +48 % convolution time */
 };
 
+/* BatchNorm statistics of the residual conv stack.  The shipped checkpoints hold pop_mean/pop_var and their graph uses
+ * them at inference (batchnorm(), chiron/cnn.py:125-163): CB_BN_POPULATION, folded into the weights by cb_create.
+ * HEAD's conv_layer calls simple_global_bn (chiron/cnn.py:65-68,166-188), which normalises with the moments of the
+ * CURRENT batch (tf.nn.moments over every frame of every window) even at inference: CB_BN_BATCH, for models trained at
+ * HEAD.  In that mode a window's result depends on the batch it is in, exactly as in the reference. */
+enum { CB_BN_POPULATION = 0, CB_BN_BATCH = 1 };
+
 /* Assembly kernels, chiron/chiron_eval.py:138-150 (get_assembler_kernal). */
 enum { CB_ASM_SIMPLE = 0, CB_ASM_GLUE = 1, CB_ASM_STICK = 2 };
 
@@ -55,6 +62,11 @@ int cb_create(const void* blob, size_t nbytes, int device, int precision, cb_han
 int cb_destroy(cb_handle* h);
 const char* cb_last_error(void);
 const char* cb_version(void);
+
+/* Override the BatchNorm mode the blob header asks for (CBW1 header field bn_mode).  CB_BN_BATCH is available on
+ * CB_PREC_FP32 handles only (CB_ERR_ARG otherwise). */
+int cb_set_bn_mode(cb_handle* h, int bn_mode);
+int cb_bn_mode(const cb_handle* h);
 
 /* Model facts read from the blob header. */
 int cb_out_len(const cb_handle* h, int L);            /* CNN output frames T for an L-sample window (ratio = L/T) */

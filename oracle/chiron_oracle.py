@@ -72,13 +72,24 @@ def seq_len_out(lens: np.ndarray, ratio: float) -> np.ndarray:
 # ----------------------------------------------------------------------------------------------------------------------
 # A.3 / A.4  CNN
 # ----------------------------------------------------------------------------------------------------------------------
-def _bn(x, t, prefix, dtype):
-    """tf.nn.batch_normalization with population statistics (chiron/cnn.py:160-161):
-    inv = scale*rsqrt(var+eps); y = x*inv + (offset - mean*inv)."""
+def _bn(x, t, prefix, dtype, bn_mode=0, stats_out=None):
+    """bn_mode 0: tf.nn.batch_normalization with population statistics (chiron/cnn.py:160-161, the graph of the shipped
+    checkpoints).  bn_mode 1: HEAD's simple_global_bn (chiron/cnn.py:166-188): tf.nn.moments(inp, [0, 1, 2]) of THIS
+    batch -- every frame of every window, zero padding included -- mean = E[x], var = E[(x - mean)^2], even at
+    inference.  Either way  inv = scale*rsqrt(var+eps); y = x*inv + (offset - mean*inv).
+    ``stats_out`` (dict) receives the (mean, var) used, keyed by ``prefix``.
+    Parity of mode 1 is UNPINNED: no checkpoint trained at HEAD ships with the reference (SURVEY.md finding 2)."""
     scale = t[prefix + "_bn/scale"].astype(dtype)
     offset = t[prefix + "_bn/offset"].astype(dtype)
-    mean = t[prefix + "_bn/pop_mean"].astype(dtype)
-    var = t[prefix + "_bn/pop_var"].astype(dtype)
+    if bn_mode == 0:
+        mean = t[prefix + "_bn/pop_mean"].astype(dtype)
+        var = t[prefix + "_bn/pop_var"].astype(dtype)
+    else:
+        flat = x.reshape(-1, x.shape[-1])
+        mean = flat.mean(axis=0, dtype=dtype)
+        var = np.square(flat - mean).mean(axis=0, dtype=dtype)
+    if stats_out is not None:
+        stats_out[prefix] = (mean, var)
     inv = scale * (dtype(1.0) / np.sqrt(var + dtype(BN_EPS)))
     return x * inv + (offset - mean * inv)
 
@@ -100,8 +111,12 @@ def _conv_same(x, w, stride):
     return out
 
 
-def cnn_forward(x: np.ndarray, cfg, t: Dict[str, np.ndarray], dtype=np.float32) -> np.ndarray:
-    """getcnnfeature -> DNA_model1 -> residual_layer (chiron/cnn.py:334-371, 380-389, 234-262).  x [B,L] -> [B,T,C]."""
+def cnn_forward(x: np.ndarray, cfg, t: Dict[str, np.ndarray], dtype=np.float32, bn_mode=None,
+                stats_out=None) -> np.ndarray:
+    """getcnnfeature -> DNA_model1 / rna_test / ... -> residual_layer (chiron/cnn.py:334-371, 380-389, 555-566,
+    234-262).  x [B,L] -> [B,T,C].  ``bn_mode`` None = the model's own (cfg.bn_mode); see ``_bn``."""
+    if bn_mode is None:
+        bn_mode = getattr(cfg, "bn_mode", 0)
     net = np.asarray(x, dtype=dtype)[:, :, None]
     for b in range(cfg.n_blocks):
         p = "res_layer%d" % (b + 1)
@@ -109,13 +124,13 @@ def cnn_forward(x: np.ndarray, cfg, t: Dict[str, np.ndarray], dtype=np.float32) 
         w1 = t[p + "/branch1/conv1/weights"].astype(dtype)[None]
         b1 = _conv_same(net, w1, s)
         if cfg.branch1_bn_mask >> b & 1:
-            b1 = _bn(b1, t, p + "/branch1/conv1", dtype)
+            b1 = _bn(b1, t, p + "/branch1/conv1", dtype, bn_mode, stats_out)
         a = _conv_same(net, t[p + "/branch2/conv2a/weights"].astype(dtype)[None], 1)
-        a = np.maximum(_bn(a, t, p + "/branch2/conv2a", dtype), 0)
+        a = np.maximum(_bn(a, t, p + "/branch2/conv2a", dtype, bn_mode, stats_out), 0)
         bb = _conv_same(a, t[p + "/branch2/conv2b/weights"].astype(dtype), s)
-        bb = np.maximum(_bn(bb, t, p + "/branch2/conv2b", dtype), 0)
+        bb = np.maximum(_bn(bb, t, p + "/branch2/conv2b", dtype, bn_mode, stats_out), 0)
         c = _conv_same(bb, t[p + "/branch2/conv2c/weights"].astype(dtype)[None], 1)
-        c = _bn(c, t, p + "/branch2/conv2c", dtype)
+        c = _bn(c, t, p + "/branch2/conv2c", dtype, bn_mode, stats_out)
         net = np.maximum(b1 + c, 0)
     return net
 
@@ -201,9 +216,9 @@ def head_forward(lasth: np.ndarray, cfg, t: Dict[str, np.ndarray], dtype=np.floa
     return logits.reshape(B, T, cfg.n_class)
 
 
-def inference(x: np.ndarray, lens_out: np.ndarray, cfg, t, dtype=np.float32) -> np.ndarray:
+def inference(x: np.ndarray, lens_out: np.ndarray, cfg, t, dtype=np.float32, bn_mode=None) -> np.ndarray:
     """chiron/chiron_model.py:134-172: CNN -> RNN -> logits[B,T,n_class].  ``lens_out`` already divided by ratio."""
-    fea = cnn_forward(x, cfg, t, dtype)
+    fea = cnn_forward(x, cfg, t, dtype, bn_mode)
     lasth = rnn_forward(fea, lens_out, cfg, t, dtype)
     return head_forward(lasth, cfg, t, dtype)
 

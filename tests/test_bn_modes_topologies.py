@@ -1,0 +1,169 @@
+"""CPU tests of SURVEY.md 8f-3 / 8f-4: the batch-statistics BatchNorm mode (HEAD's simple_global_bn,
+chiron/cnn.py:166-188) and residual stacks other than the two shipped ones (e.g. the 5-block rna_test,
+chiron/cnn.py:555-566).
+
+No checkpoint trained at HEAD or with those topologies ships with the reference, so the oracle's restatement of them is
+"parity unpinned" against the reference itself; what pins it here is an INDEPENDENT restatement with torch's own
+conv1d / batch_norm / LSTM-free primitives on CPU (torch is not used by the oracle), plus structural identities."""
+import numpy as np
+import pytest
+
+from chiron_b200 import model as M
+from chiron_b200.convert_weights import convert_tensors
+from oracle import chiron_oracle as O
+
+
+def _torch_cnn(x, cfg, t, bn_mode):
+    """The residual stack written with torch.nn.functional (float64): F.conv1d on explicitly 'SAME'-padded input and
+    F.batch_norm with training=True (batch moments, biased variance = tf.nn.moments) or the stored statistics."""
+    import torch
+    import torch.nn.functional as F
+
+    def conv(inp, w, stride):                     # inp [B,Cin,T], w [k,Cin,Cout] (TF HWIO without the H axis)
+        k = w.shape[0]
+        T = inp.shape[2]
+        t_out = -(-T // stride)
+        pad = max((t_out - 1) * stride + k - T, 0)
+        inp = F.pad(inp, (pad // 2, pad - pad // 2))
+        return F.conv1d(inp, torch.from_numpy(np.array(w.transpose(2, 1, 0), dtype=np.float64)), stride=stride)
+
+    def bn(inp, prefix):
+        g = lambda n: torch.from_numpy(np.array(t[prefix + "_bn/" + n], dtype=np.float64))
+        if bn_mode == 1:
+            return F.batch_norm(inp, None, None, g("scale"), g("offset"), training=True, eps=1e-5)
+        return F.batch_norm(inp, g("pop_mean"), g("pop_var"), g("scale"), g("offset"), training=False, eps=1e-5)
+
+    net = torch.from_numpy(np.asarray(x, dtype=np.float64))[:, None, :]
+    for b in range(cfg.n_blocks):
+        p = "res_layer%d" % (b + 1)
+        s = cfg.stride[b]
+        b1 = conv(net, t[p + "/branch1/conv1/weights"][None], s)
+        if cfg.branch1_bn_mask >> b & 1:
+            b1 = bn(b1, p + "/branch1/conv1")
+        a = torch.relu(bn(conv(net, t[p + "/branch2/conv2a/weights"][None], 1), p + "/branch2/conv2a"))
+        bb = torch.relu(bn(conv(a, t[p + "/branch2/conv2b/weights"], s), p + "/branch2/conv2b"))
+        c = bn(conv(bb, t[p + "/branch2/conv2c/weights"][None], 1), p + "/branch2/conv2c")
+        net = torch.relu(b1 + c)
+    return net.permute(0, 2, 1).numpy()
+
+
+def _signal(B, L, seed=0):
+    rng = np.random.default_rng(seed)
+    x = rng.normal(-0.16, 0.43, size=(B, L)).astype(np.float32)
+    x[1, L // 2:] = 0                              # a zero-padded short window: padding counts in the batch moments
+    return x
+
+
+@pytest.mark.parametrize("bn_mode", [0, 1])
+def test_oracle_cnn_matches_torch_on_dna_default(dna_model, bn_mode):
+    cfg, t, _ = dna_model
+    x = _signal(5, 96)
+    ref = _torch_cnn(x, cfg, t, bn_mode)
+    got = O.cnn_forward(x, cfg, t, np.float64, bn_mode)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
+    got32 = O.cnn_forward(x, cfg, t, np.float32, bn_mode)
+    assert np.abs(got32 - ref).max() < 2e-4 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("bn_mode", [0, 1])
+def test_oracle_cnn_matches_torch_on_rna_default(rna_model, bn_mode):
+    """k=13 / stride-5 first block: the strided 'SAME' padding and the strided 1x1 branch."""
+    cfg, t, _ = rna_model
+    x = _signal(3, 203, seed=1)                    # 203 is not a multiple of 5: asymmetric padding
+    ref = _torch_cnn(x, cfg, t, bn_mode)
+    got = O.cnn_forward(x, cfg, t, np.float64, bn_mode)
+    assert got.shape == (3, 41, cfg.channels) == ref.shape
+    assert np.abs(got - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("k,stride,mask", [([3] * 5, [1] * 5, 1),            # rna_test (cnn.py:555-566)
+                                           ([5, 3, 7, 3], [2, 1, 3, 1], 0b0101),
+                                           ([1, 2], [1, 2], 0b11)])
+def test_oracle_cnn_matches_torch_on_other_topologies(k, stride, mask):
+    cfg = M.ModelConfig(n_blocks=len(k), channels=32, hidden=12, k=k, stride=stride, branch1_bn_mask=mask)
+    t = M.random_tensors(cfg, seed=3)
+    x = _signal(4, 77, seed=2)
+    for bn_mode in (0, 1):
+        ref = _torch_cnn(x, cfg, t, bn_mode)
+        got = O.cnn_forward(x, cfg, t, np.float64, bn_mode)
+        assert got.shape == (4, cfg.out_len(77), 32) == ref.shape
+        assert np.abs(got - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
+
+
+def test_batch_mode_equals_population_mode_fed_with_the_batch_moments(dna_model):
+    """Structural identity: storing the moments batch mode computed as pop_mean / pop_var and running population mode
+    reproduces the batch-mode result exactly; and batch mode really differs from the shipped statistics."""
+    cfg, t, _ = dna_model
+    x = _signal(6, 120)
+    stats = {}
+    f_batch = O.cnn_forward(x, cfg, t, np.float32, 1, stats)
+    assert len(stats) == 3 * cfg.n_blocks + bin(cfg.branch1_bn_mask).count("1")
+    t2 = dict(t)
+    for prefix, (mean, var) in stats.items():
+        t2[prefix + "_bn/pop_mean"], t2[prefix + "_bn/pop_var"] = mean, var
+    assert np.array_equal(O.cnn_forward(x, cfg, t2, np.float32, 0), f_batch)
+    assert np.abs(O.cnn_forward(x, cfg, t, np.float32, 0) - f_batch).max() > 1e-2
+    # a window's batch-mode result depends on its batch (HEAD behaviour) -- population mode's does not
+    assert np.abs(O.cnn_forward(x[:3], cfg, t, np.float32, 1) - f_batch[:3]).max() > 1e-4
+    assert np.array_equal(O.cnn_forward(x[:3], cfg, t, np.float32, 0), O.cnn_forward(x, cfg, t, np.float32, 0)[:3])
+
+
+def test_blob_header_carries_bn_mode():
+    cfg = M.ModelConfig(n_blocks=2, channels=8, hidden=4, k=[3, 5], stride=[1, 2], bn_mode=M.BN_BATCH)
+    t = M.random_tensors(cfg, 0)
+    cfg2, t2 = M.unpack_blob(M.pack_blob(cfg, t))
+    assert cfg2 == cfg and cfg2.bn_mode == M.BN_BATCH
+    assert all(np.array_equal(t[n], t2[n]) for n in t)
+    assert M.unpack_blob(M.pack_blob(M.ModelConfig(), M.random_tensors(M.ModelConfig(), 0)))[0].bn_mode == M.BN_POPULATION
+
+
+def _tf_checkpoint_names(cfg, t, head_literal):
+    """The variable set tf.train.Saver would hold for this model: batchnorm()'s names (the shipped checkpoints,
+    chiron/cnn.py:140-148) or simple_global_bn's (a model trained at HEAD, chiron/cnn.py:65-68,181-186)."""
+    raw = {}
+    for b in range(cfg.n_blocks):
+        p = "res_layer%d" % (b + 1)
+        for conv in ("branch1/conv1", "branch2/conv2a", "branch2/conv2b", "branch2/conv2c"):
+            w = t["%s/%s/weights" % (p, conv)]
+            raw["%s/%s/weights" % (p, conv)] = w[None] if conv.endswith("conv2b") else w[None, None]
+            if "%s/%s_bn/scale" % (p, conv) not in t:
+                continue
+            leaf = conv.rsplit("/", 1)[-1]
+            if head_literal:
+                raw["%s/%s_bn/%s_bn_scale" % (p, conv, leaf)] = t["%s/%s_bn/scale" % (p, conv)]
+                raw["%s/%s_bn/%s_bn_offset" % (p, conv, leaf)] = t["%s/%s_bn/offset" % (p, conv)]
+            else:
+                for n in ("scale", "offset", "pop_mean", "pop_var"):
+                    raw["%s/%s_bn/%s" % (p, conv, n)] = t["%s/%s_bn/%s" % (p, conv, n)]
+    for l in range(cfg.n_layers):
+        for d in ("fw", "bw"):
+            for leaf in ("kernel", "bias"):
+                raw["BDLSTM_rnn/cell_%d/bidirectional_rnn/%s/lstm_cell/%s" % (l, d, leaf)] = t["lstm/%d/%s/%s" % (l, d, leaf)]
+    for n in ("weights", "bias", "weights_class", "bias_class"):
+        raw["rnn_fnn_layer/" + n] = t["rnn_fnn_layer/" + n]
+    return raw
+
+
+def test_converter_maps_both_bn_variable_sets():
+    cfg = M.ModelConfig(n_blocks=5, channels=16, hidden=8, k=[3] * 5, stride=[1] * 5, branch1_bn_mask=1)
+    t = M.random_tensors(cfg, 5)
+    c_pop, t_pop = M.unpack_blob(convert_tensors(_tf_checkpoint_names(cfg, t, False), {}, {}))
+    assert c_pop == cfg and all(np.array_equal(t[n], t_pop[n]) for n in t)
+    c_head, t_head = M.unpack_blob(convert_tensors(_tf_checkpoint_names(cfg, t, True), {}, {}))
+    assert c_head.bn_mode == M.BN_BATCH and c_head.n_blocks == 5 and c_head.branch1_bn_mask == 1
+    for n in t:
+        if n.endswith("pop_mean"):
+            assert not t_head[n].any()
+        elif n.endswith("pop_var"):
+            assert (t_head[n] == 1).all()
+        else:
+            assert np.array_equal(t[n], t_head[n])
+    x = _signal(3, 40)
+    assert np.array_equal(O.cnn_forward(x, c_head, t_head), O.cnn_forward(x, cfg, t, bn_mode=1))   # header's mode is used
+    mixed = _tf_checkpoint_names(cfg, t, False)
+    mixed.update({k: v for k, v in _tf_checkpoint_names(cfg, t, True).items() if "res_layer2" in k and "_bn_" in k})
+    for k in [k for k in mixed if "res_layer2" in k and k.rsplit("/", 1)[-1] in ("scale", "offset", "pop_mean", "pop_var")]:
+        del mixed[k]
+    with pytest.raises(ValueError):
+        convert_tensors(mixed, {}, {})
