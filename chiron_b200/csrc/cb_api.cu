@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include "cb_internal.cuh"
+#include "cb_conv_stack.cuh"
 
 static thread_local char g_err[1024] = "";
 
@@ -215,7 +216,7 @@ extern "C" int cb_create(const void* blob, size_t nbytes, int device, int precis
         h->conv2a[b].W = base + o_conv2a[b][0]; h->conv2a[b].shift = base + o_conv2a[b][1];
         h->conv2b[b].W = base + o_conv2b[b][0]; h->conv2b[b].shift = base + o_conv2b[b][1];
         h->convc[b].W = base + o_convc[b][0];   h->convc[b].shift = base + o_convc[b][1];
-        cb_handle::RawConv* raw[4] = {&h->raw1[b], &h->raw2a[b], &h->raw2b[b], &h->raw2c[b]};
+        CbRawConv* raw[4] = {&h->raw1[b], &h->raw2a[b], &h->raw2b[b], &h->raw2c[b]};
         for (int i = 0; i < 4; ++i) {
             raw[i]->W = base + o_raw[b][i].W;
             raw[i]->scale = o_raw[b][i].bn ? base + o_raw[b][i].scale : nullptr;
@@ -370,133 +371,21 @@ static int run_gemm(cb_handle* h, const GemmProblem& p, cudaStream_t s, int cat)
     return rc;
 }
 
-// Residual conv stack with batch-statistics BN (HEAD's conv_layer -> simple_global_bn, chiron/cnn.py:65-68,166-188;
-// residual_layer cnn.py:234-262): every convolution is run raw (nothing folded, no shift, no ReLU), its output is reduced
-// to per-channel batch moments, and the normalisation + activation (+ the residual sum) is a separate pass.
-// On return *feat is the block stack's output [B*T,C] (one of act[]) and *t_feat its frame count.
-static int conv_stack_batch_bn(cb_handle* h, const float* x, int B, int L, cudaStream_t s, const float** feat, int* t_feat) {
-    const CbConfig& c = h->cfg;
-    const int C = c.channels;
-    int rc;
-    float* vec[CB_BN_VECS];
-    for (int i = 0; i < CB_BN_VECS; ++i) vec[i] = h->bn_vec + (size_t)i * C;
-    int t_in = L;
-    const float* X = nullptr;
-    int xi = -1;
-    auto raw_gemm = [&](GemmProblem& g, const float* W, float* out) {
-        g.N = C; g.W = W; g.shift = h->zeros; g.relu = 0; g.out = out; g.ldo = C;
-        return run_gemm(h, g, s, CB_CAT_CONV);
-    };
-    for (int b = 0; b < c.n_blocks; ++b) {
-        const int st = c.stride[b], k = c.k[b];
-        const int t_out = (t_in + st - 1) / st;
-        int pad = (t_out - 1) * st + k - t_in; if (pad < 0) pad = 0;     // TF 'SAME'
-        const int left = pad / 2;
-        int ia = (xi + 1) % 3, ib = (xi + 2) % 3;
-        if (xi < 0) { ia = 0; ib = 1; }
-        const long long M_in = (long long)B * t_in, M_out = (long long)B * t_out;
-        GemmProblem g;
-        BnApplyArgs ap;
-        // conv2a 1x1 + BN + ReLU
-        if (b == 0) {       // rank-1 in the raw signal: statistics from the samples, tensor generated inside conv2b's loader
-            if ((rc = cb_launch_bn_rank1(h, x, B, t_in, 1, t_in, h->raw2a[b].W, h->raw2a[b].scale, h->raw2a[b].offset,
-                                         vec[0], vec[1], s)) != CB_OK) return rc;
-        } else {
-            memset(&g, 0, sizeof(g));
-            g.M = (int)M_in; g.K = C; g.t_out = t_in; g.t_in0 = t_in; g.stride0 = 1; g.taps = 1; g.c0 = C; g.src0 = X; g.lda0 = C;
-            if ((rc = raw_gemm(g, h->raw2a[b].W, h->act[ia])) != CB_OK) return rc;
-            if ((rc = cb_launch_bn_stats(h, h->act[ia], M_in, h->raw2a[b].scale, h->raw2a[b].offset, vec[0], vec[1], s)) != CB_OK) return rc;
-            memset(&ap, 0, sizeof(ap));
-            ap.a = h->act[ia]; ap.a_inv = vec[0]; ap.a_sh = vec[1]; ap.relu = 1; ap.out = h->act[ia]; ap.M = M_in;
-            if ((rc = cb_launch_bn_apply(h, ap, s)) != CB_OK) return rc;
-        }
-        // conv2b 1xk (stride) + BN + ReLU -> act[ib]
-        memset(&g, 0, sizeof(g));
-        g.M = (int)M_out; g.K = k * C; g.t_out = t_out; g.t_in0 = t_in; g.stride0 = st; g.taps = k; g.left = left; g.c0 = C;
-        if (b == 0) { g.gen = 1; g.x = x; g.gw = h->raw2a[b].W; g.ginv = vec[0]; g.gsh = vec[1]; }
-        else { g.src0 = h->act[ia]; g.lda0 = C; }
-        if ((rc = raw_gemm(g, h->raw2b[b].W, h->act[ib])) != CB_OK) return rc;
-        if ((rc = cb_launch_bn_stats(h, h->act[ib], M_out, h->raw2b[b].scale, h->raw2b[b].offset, vec[2], vec[3], s)) != CB_OK) return rc;
-        memset(&ap, 0, sizeof(ap));
-        ap.a = h->act[ib]; ap.a_inv = vec[2]; ap.a_sh = vec[3]; ap.relu = 1; ap.out = h->act[ib]; ap.M = M_out;
-        if ((rc = cb_launch_bn_apply(h, ap, s)) != CB_OK) return rc;
-        // conv2c 1x1 + BN -> act[ia] (raw), its inv/shift in vec[4], vec[5]
-        memset(&g, 0, sizeof(g));
-        g.M = (int)M_out; g.K = C; g.t_out = t_out; g.t_in0 = t_out; g.stride0 = 1; g.taps = 1; g.c0 = C; g.src0 = h->act[ib]; g.lda0 = C;
-        if ((rc = raw_gemm(g, h->raw2c[b].W, h->act[ia])) != CB_OK) return rc;
-        if ((rc = cb_launch_bn_stats(h, h->act[ia], M_out, h->raw2c[b].scale, h->raw2c[b].offset, vec[4], vec[5], s)) != CB_OK) return rc;
-        // branch1: 1x1 conv (stride) of the block input (+ BN), then relu(branch1 + conv2c)
-        memset(&ap, 0, sizeof(ap));
-        ap.a = h->act[ia]; ap.a_inv = vec[4]; ap.a_sh = vec[5]; ap.relu = 1; ap.out = h->act[ia]; ap.M = M_out;
-        if (b == 0) {
-            if ((rc = cb_launch_bn_rank1(h, x, B, t_in, st, t_out, h->raw1[b].W, h->raw1[b].scale, h->raw1[b].offset,
-                                         vec[6], vec[7], s)) != CB_OK) return rc;
-            ap.x = x; ap.rw = h->raw1[b].W; ap.rinv = vec[6]; ap.rsh = vec[7]; ap.t_out = t_out; ap.t_inr = t_in; ap.strider = st;
-        } else {
-            memset(&g, 0, sizeof(g));     // conv2b's output (act[ib]) has been consumed: reuse it for the raw branch
-            g.M = (int)M_out; g.K = C; g.t_out = t_out; g.t_in0 = t_in; g.stride0 = st; g.taps = 1; g.left = 0; g.c0 = C; g.src0 = X; g.lda0 = C;
-            if ((rc = raw_gemm(g, h->raw1[b].W, h->act[ib])) != CB_OK) return rc;
-            ap.b = h->act[ib];
-            if (h->raw1[b].scale) {
-                if ((rc = cb_launch_bn_stats(h, h->act[ib], M_out, h->raw1[b].scale, h->raw1[b].offset, vec[6], vec[7], s)) != CB_OK) return rc;
-                ap.b_inv = vec[6]; ap.b_sh = vec[7];
-            }
-        }
-        if ((rc = cb_launch_bn_apply(h, ap, s)) != CB_OK) return rc;
-        X = h->act[ia]; xi = ia; t_in = t_out;
+// The two conv-stack orchestrations (cb_conv_stack.cuh) issue their work through this adapter: CUDA launches on stream s.
+namespace {
+struct CudaConvOps {
+    cb_handle* h; cudaStream_t s;
+    int gemm(const GemmProblem& g) { return run_gemm(h, g, s, CB_CAT_CONV); }
+    int bn_rank1(const float* x, int B, int t_in, int stride, int t_out, const float* w, const float* scale,
+                 const float* offset, float* inv, float* shift) {
+        return cb_launch_bn_rank1(h, x, B, t_in, stride, t_out, w, scale, offset, inv, shift, s);
     }
-    *feat = X; *t_feat = t_in;
-    return CB_OK;
-}
-
-// Residual conv stack with population BN folded into the weights (the shipped checkpoints' graph: cnn.py:234-262,
-// 380-389 with batchnorm() cnn.py:125-163).  On return *feat is the stack's output [B*T,C] and *t_feat its frame count.
-static int conv_stack_folded(cb_handle* h, const float* x, int B, int L, cudaStream_t s, const float** feat, int* t_feat) {
-    const CbConfig& c = h->cfg;
-    const int C = c.channels;
-    int rc;
-    int t_in = L;
-    const float* X = nullptr;          // block input (nullptr = raw signal for block 1)
-    int xi = -1;                       // which act[] buffer holds X
-    for (int b = 0; b < c.n_blocks; ++b) {
-        const int st = c.stride[b], k = c.k[b];
-        const int t_out = (t_in + st - 1) / st;
-        int pad = (t_out - 1) * st + k - t_in; if (pad < 0) pad = 0;     // TF 'SAME'
-        const int left = pad / 2;
-        int ia = (xi + 1) % 3, ib = (xi + 2) % 3;     // scratch buffers that are not X
-        if (xi < 0) { ia = 0; ib = 1; }
-        GemmProblem g;
-        if (b > 0) {                   // conv2a 1x1 + BN + ReLU  -> act[ia]   (block 1 generates it on the fly)
-            memset(&g, 0, sizeof(g));
-            g.M = B * t_in; g.N = C; g.K = C; g.t_out = t_in;
-            g.t_in0 = t_in; g.stride0 = 1; g.taps = 1; g.left = 0; g.c0 = C; g.src0 = X; g.lda0 = C;
-            g.W = h->conv2a[b].W; g.shift = h->conv2a[b].shift; g.relu = 1; g.out = h->act[ia]; g.ldo = C;
-                        if ((rc = run_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
-        }
-        // conv2b 1xk (stride) + BN + ReLU -> act[ib]
-        memset(&g, 0, sizeof(g));
-        g.M = B * t_out; g.N = C; g.K = k * C; g.t_out = t_out;
-        g.t_in0 = t_in; g.stride0 = st; g.taps = k; g.left = left; g.c0 = C;
-        if (b == 0) { g.gen = 1; g.x = x; g.gw = h->g_w; g.ginv = h->g_inv; g.gsh = h->g_sh; }
-        else { g.src0 = h->act[ia]; g.lda0 = C; }
-        g.W = h->conv2b[b].W; g.shift = h->conv2b[b].shift; g.relu = 1; g.out = h->act[ib]; g.ldo = C;
-                if ((rc = run_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
-        // conv2c 1x1 + BN, + branch1 (1x1 conv of the block input, stride st), ReLU -> act[ia]
-        memset(&g, 0, sizeof(g));
-        g.M = B * t_out; g.N = C; g.t_out = t_out;
-        g.t_in0 = t_out; g.stride0 = 1; g.taps = 1; g.left = 0; g.c0 = C; g.src0 = h->act[ib]; g.lda0 = C;
-        if (b == 0) {
-            g.K = C; g.res = 1; g.x = x; g.t_inr = t_in; g.strider = st; g.rw = h->r_w; g.rinv = h->r_inv; g.rsh = h->r_sh;
-        } else {
-            g.K = 2 * C; g.c1 = C; g.src1 = X; g.lda1 = C; g.t_in1 = t_in; g.stride1 = st;
-        }
-        g.W = h->convc[b].W; g.shift = h->convc[b].shift; g.relu = 1; g.out = h->act[ia]; g.ldo = C;
-                if ((rc = run_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
-        X = h->act[ia]; xi = ia; t_in = t_out;
+    int bn_stats(const float* X, long long M, const float* scale, const float* offset, float* inv, float* shift) {
+        return cb_launch_bn_stats(h, X, M, scale, offset, inv, shift, s);
     }
-    *feat = X; *t_feat = t_in;
-    return CB_OK;
-}
+    int bn_apply(const BnApplyArgs& a) { return cb_launch_bn_apply(h, a, s); }
+};
+}  // namespace
 
 extern "C" int cb_seq_len_out(cb_handle* h, const int32_t* seq_len_in, int B, int L, int32_t* seq_len_out, void* stream) {
     if (!h || !seq_len_in || !seq_len_out || B < 0 || L < 1) { cb_set_error("cb_seq_len_out: bad arguments"); return CB_ERR_ARG; }
@@ -525,8 +414,19 @@ extern "C" int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_o
     // ---- residual conv stack (cnn.py:234-262, 380-389) ----------------------------------------------------------
     int t_in = L;
     const float* X = nullptr;
-    rc = h->bn_mode == CB_BN_BATCH ? conv_stack_batch_bn(h, x, B, L, s, &X, &t_in) : conv_stack_folded(h, x, B, L, s, &X, &t_in);
-    if (rc != CB_OK) return rc;
+    {
+        CudaConvOps ops{h, s};
+        CbConvStackBufs bufs;
+        for (int i = 0; i < 3; ++i) bufs.act[i] = h->act[i];
+        for (int i = 0; i < CB_BN_VECS; ++i) bufs.vec[i] = h->bn_vec ? h->bn_vec + (size_t)i * C : nullptr;
+        bufs.zeros = h->zeros;
+        if (h->bn_mode == CB_BN_BATCH)
+            rc = cb_conv_stack_batch_bn(ops, c, h->raw1, h->raw2a, h->raw2b, h->raw2c, bufs, x, B, L, &X, &t_in);
+        else
+            rc = cb_conv_stack_folded(ops, c, h->conv2a, h->conv2b, h->convc, h->g_w, h->g_inv, h->g_sh, h->r_w, h->r_inv,
+                                      h->r_sh, bufs, x, B, L, &X, &t_in);
+        if (rc != CB_OK) return rc;
+    }
     const int T = t_in;
     const int M = B * T;
     h->fea = X;

@@ -9,11 +9,9 @@
 #include "../../include/chiron_b200.h"
 #include "cb_tc_common.cuh"
 
-#define CB_MAX_BLOCKS 8
-#define CB_MAX_LAYERS 8
+#include "cb_simt_types.h"
+
 #define CB_PROF_MAX 96
-#define CB_BN_MAX_PART 1024       // per-CTA partial sums of a batch-statistics BN reduction (cb_bn.cu)
-#define CB_BN_VECS 8              // [C]-float scratch vectors holding inv/shift pairs of the BNs in flight
 enum { CB_CAT_CONV = 0, CB_CAT_LSTM_IN = 1, CB_CAT_LSTM_REC = 2, CB_CAT_HEAD = 3, CB_CAT_COUNT = 4 };
 
 void cb_set_error(const char* fmt, ...);
@@ -36,39 +34,6 @@ void cb_set_error(const char* fmt, ...);
         }                                                                                      \
     } while (0)
 
-// ---- model (host copy of the CBW1 header) ----------------------------------------------------------------------
-struct CbConfig {
-    int n_blocks, channels, hidden, n_layers, n_class, rnn_layout, branch1_bn_mask;
-    int k[CB_MAX_BLOCKS], stride[CB_MAX_BLOCKS];
-    int sig_norm, reverse_signal;
-};
-
-// ---- one dense contraction  out[M,N] = act(A_gather[M,K] @ W[K,N] + shift[N] (+ rank-1 residual)) -----------------
-// A row m = output frame (b = m / t_out, to = m % t_out).  K is the concatenation of
-//   part 0: `taps` taps of c0 channels: frame ti = to*stride0 + j - left (zero outside [0,t_in0)), read from src0 with
-//           row stride lda0, or generated on the fly from the raw signal (gen != 0, block-1 conv2a, cnn.py:254):
-//           a = relu((x*gw[c])*ginv[c] + gsh[c]);
-//   part 1: c1 channels of src1 at frame to*stride1 of a t_in1-frame window (the 1x1 branch1 conv input,
-//           cnn.py:251), row stride lda1.
-struct GemmProblem {
-    int M, N, K;              // K = taps*c0 + c1
-    int t_out;
-    int t_in0, stride0, taps, left, c0;
-    int t_in1, stride1, c1;
-    const float* src0; int lda0;
-    const float* src1; int lda1;
-    int gen;                  // 1: part 0 generated from x (rank-1 conv + BN + ReLU)
-    const float* x;           // raw window samples: [B*t_in0] for gen, [B*t_inr] for the residual
-    const float *gw, *ginv, *gsh;
-    const float* W;           // [K,N] fp32, BN scale folded in (SIMT path)
-    const float* shift;       // [N]
-    int relu;
-    int res, t_inr, strider;  // res=1: add rank-1 residual (x[to*strider]*rw[n])*rinv[n] + rsh[n] before the ReLU
-    const float *rw, *rinv, *rsh;
-    float* out; int ldo;
-    int layer_id;             // which prepared tensor-core weight image belongs to this contraction
-};
-
 // ---- one tensor-core contraction (cb_tc.cu) ----------------------------------------------------------------------------
 // Row space: m = to*Bp + b (output frame to < T, window b < B; Bp = B rounded up to 128), so a 128-row tile is 128
 // consecutive windows of one frame.  K is image a0 read at frames to*stride + j - left (j < taps) followed by image a1
@@ -84,17 +49,6 @@ struct TcGemm {
     int out_mode;             // 1 fp32 time-major out[to][ldo][Bp]; 2 operand image o
     float* out; int ldo;
     CbImg o; int o_plane0;
-};
-
-// ---- batch-statistics BatchNorm (cb_bn.cu): out = act(a*a_inv + a_sh [+ b*b_inv + b_sh | + b] [+ rank-1 branch]) --------
-struct BnApplyArgs {
-    const float *a, *a_inv, *a_sh;
-    const float *b, *b_inv, *b_sh;          // b_inv == nullptr: b is added as it is (branch1 without BN)
-    const float *x, *rw, *rinv, *rsh;       // rank-1 branch of the raw signal: (x[win*t_inr + to*strider]*rw)*rinv + rsh
-    int t_out, t_inr, strider;
-    int relu;
-    float* out;                             // may alias a (every element is read and written by the same thread)
-    long long M;
 };
 
 struct LstmProblem {         // both directions of one layer (grid.y = direction)
@@ -115,11 +69,10 @@ struct cb_handle {
     // device weights (fp32, derived)
     float* d_weights;                 // one allocation holding everything below
     size_t weights_floats;
-    struct ConvW { const float *W, *shift; } conv2a[CB_MAX_BLOCKS], conv2b[CB_MAX_BLOCKS], convc[CB_MAX_BLOCKS];
+    CbConvW conv2a[CB_MAX_BLOCKS], conv2b[CB_MAX_BLOCKS], convc[CB_MAX_BLOCKS];
     // batch-statistics BN mode: the convolutions as they are in the checkpoint (nothing folded) + BN scale/offset
     int bn_mode;
-    struct RawConv { const float *W, *scale, *offset; } raw1[CB_MAX_BLOCKS], raw2a[CB_MAX_BLOCKS], raw2b[CB_MAX_BLOCKS],
-        raw2c[CB_MAX_BLOCKS];             // raw1[b].scale == nullptr: block b's branch1 has no BN
+    CbRawConv raw1[CB_MAX_BLOCKS], raw2a[CB_MAX_BLOCKS], raw2b[CB_MAX_BLOCKS], raw2c[CB_MAX_BLOCKS];
     const float* zeros;                   // [max(C, 8H)] zero shift vector
     double* bn_part;                      // [CB_BN_MAX_PART][2][C] partial sums
     float* bn_vec;                        // [CB_BN_VECS][C]

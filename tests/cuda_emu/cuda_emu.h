@@ -1,0 +1,96 @@
+// Minimal host emulation of the CUDA execution model -- TEST INFRASTRUCTURE ONLY (tests/test_cuda_emu.py).
+//
+// Lets g++ compile the kernel headers of the fp32 path (chiron_b200/csrc/cb_bn_kernels.cuh, cb_gemm_simt_kernel.cuh) and
+// run them on a machine without a GPU: every CUDA thread of a block is a std::thread, __syncthreads() is a std::barrier
+// over the block, warp shuffles exchange through a per-warp buffer between two warp barriers, __shared__ variables are
+// function-local statics (blocks run one after the other).  Only what those kernels use is provided.  Nothing in the
+// product path includes this file.
+#pragma once
+#include <algorithm>
+#include <array>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
+
+struct alignas(16) float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+
+namespace emu {
+struct Dim { unsigned x, y, z; };
+struct BlockCtx {
+    std::barrier<>* block_bar;
+    std::vector<std::unique_ptr<std::barrier<>>>* warp_bar;
+    std::vector<std::array<double, 32>>* shfl;
+    unsigned n_threads;
+};
+inline thread_local Dim t_idx{0, 0, 0}, b_idx{0, 0, 0};
+inline thread_local BlockCtx* ctx = nullptr;
+inline Dim b_dim{1, 1, 1}, g_dim{1, 1, 1};
+inline long long launches = 0, threads_run = 0;
+
+// Run body() once per CUDA thread of a grid x block launch (1-D grid and block).
+template <class F>
+void launch(unsigned grid, unsigned block, F&& body) {
+    g_dim = Dim{grid, 1, 1};
+    b_dim = Dim{block, 1, 1};
+    const unsigned warps = (block + 31) / 32;
+    for (unsigned blk = 0; blk < grid; ++blk) {
+        std::barrier<> bb((std::ptrdiff_t)block);
+        std::vector<std::unique_ptr<std::barrier<>>> wb;
+        for (unsigned w = 0; w < warps; ++w)
+            wb.emplace_back(new std::barrier<>((std::ptrdiff_t)std::min(32u, block - 32 * w)));
+        std::vector<std::array<double, 32>> sh(warps);
+        BlockCtx c{&bb, &wb, &sh, block};
+        std::vector<std::thread> th;
+        th.reserve(block);
+        for (unsigned t = 0; t < block; ++t)
+            th.emplace_back([&, t, blk] {
+                t_idx = Dim{t, 0, 0};
+                b_idx = Dim{blk, 0, 0};
+                ctx = &c;
+                body();
+                // a thread that leaves early must not strand the others at a later barrier
+                c.block_bar->arrive_and_drop();
+                (*c.warp_bar)[t / 32]->arrive_and_drop();
+            });
+        for (auto& x : th) x.join();
+        threads_run += block;
+    }
+    ++launches;
+}
+}  // namespace emu
+
+#define threadIdx (emu::t_idx)
+#define blockIdx (emu::b_idx)
+#define blockDim (emu::b_dim)
+#define gridDim (emu::g_dim)
+
+template <class T>
+static inline T __ldg(const T* p) { return *p; }
+
+static inline void __syncthreads() { emu::ctx->block_bar->arrive_and_wait(); }
+
+// All lanes of the calling warp take part (the kernels only shuffle warp-uniformly).
+static inline double __shfl_down_sync(unsigned, double v, int delta) {
+    emu::BlockCtx* c = emu::ctx;
+    const unsigned t = emu::t_idx.x, w = t / 32, lane = t % 32;
+    const unsigned lanes = std::min(32u, c->n_threads - 32 * w);
+    (*c->shfl)[w][lane] = v;
+    (*c->warp_bar)[w]->arrive_and_wait();
+    const double r = lane + (unsigned)delta < lanes ? (*c->shfl)[w][lane + delta] : v;
+    (*c->warp_bar)[w]->arrive_and_wait();
+    return r;
+}

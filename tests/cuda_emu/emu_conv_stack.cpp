@@ -1,0 +1,107 @@
+// Host build of the fp32 conv-stack path for tests/test_cuda_emu.py -- TEST INFRASTRUCTURE ONLY.
+// Compiles the SAME kernel and orchestration sources the CUDA library is built from
+// (cb_gemm_simt_kernel.cuh, cb_bn_kernels.cuh, cb_conv_stack.cuh) against the host emulation in cuda_emu.h.
+#include "cuda_emu.h"
+
+#include "../../include/chiron_b200.h"
+#include "../../chiron_b200/csrc/cb_simt_types.h"
+#include "../../chiron_b200/csrc/cb_gemm_simt_kernel.cuh"
+#include "../../chiron_b200/csrc/cb_bn_kernels.cuh"
+#include "../../chiron_b200/csrc/cb_conv_stack.cuh"
+
+namespace {
+
+struct EmuOps {          // mirrors the launchers of cb_gemm_simt.cu / cb_bn.cu: same checks, same grid plans
+    int sm_count, C;
+    std::vector<double> part;
+    EmuOps(int sms, int c) : sm_count(sms), C(c), part((size_t)CB_BN_MAX_PART * 2 * c) {}
+    int gemm(const GemmProblem& p) {
+        if (p.M <= 0) return CB_OK;
+        if ((p.c0 & 3) || (p.c1 & 3) || (p.N & 3) || (p.lda0 & 3) || (p.lda1 & 3) || (p.ldo & 3)) return CB_ERR_ARG;
+        const long long blocks = (long long)((p.N + cb_simt::BN - 1) / cb_simt::BN) * ((p.M + cb_simt::BM - 1) / cb_simt::BM);
+        emu::launch((unsigned)blocks, cb_simt::NT, [&] { cb_simt::gemm_simt_kernel(p); });
+        return CB_OK;
+    }
+    int bn_rank1(const float* x, int B, int t_in, int stride, int t_out, const float* w, const float* scale,
+                 const float* offset, float* inv, float* shift) {
+        int n_part = 0;
+        if (scale) {
+            n_part = cb_bn::bn_grid(sm_count, (long long)B * t_out, cb_bn::BN_THREADS);
+            emu::launch(n_part, cb_bn::BN_THREADS, [&] { cb_bn::bn_x_stats_kernel(x, B, t_in, stride, t_out, part.data()); });
+        }
+        emu::launch((C + 127) / 128, 128, [&] {
+            cb_bn::bn_finalize_kernel(part.data(), n_part, C, (double)B * t_out, w, scale, offset, inv, shift);
+        });
+        return CB_OK;
+    }
+    int bn_stats(const float* X, long long M, const float* scale, const float* offset, float* inv, float* shift) {
+        if ((C & 3) || C > 1024) return CB_ERR_ARG;
+        const int n_part = cb_bn::bn_grid(sm_count, M, cb_bn::BN_THREADS / (C >> 2));
+        emu::launch(n_part, cb_bn::BN_THREADS, [&] { cb_bn::bn_col_stats_kernel(X, M, C, part.data()); });
+        emu::launch((C + 127) / 128, 128, [&] {
+            cb_bn::bn_finalize_kernel(part.data(), n_part, C, (double)M, nullptr, scale, offset, inv, shift);
+        });
+        return CB_OK;
+    }
+    int bn_apply(const BnApplyArgs& a) {
+        if (a.M <= 0) return CB_OK;
+        const cb_bn::BnApply p = cb_bn::bn_apply_params(a, C);
+        const int grid = cb_bn::bn_grid(sm_count, p.M * (p.C >> 2), cb_bn::BN_THREADS);
+        emu::launch(grid, cb_bn::BN_THREADS, [&] { cb_bn::bn_apply_kernel(p); });
+        return CB_OK;
+    }
+};
+
+}  // namespace
+
+// geom: n_blocks, channels, branch1_bn_mask, k[8], stride[8].
+// bn_mode CB_BN_BATCH:      w[(b*4 + i)*3 + {0,1,2}] = W, scale, offset of block b's conv i (branch1, conv2a, conv2b, conv2c).
+// bn_mode CB_BN_POPULATION: w[(b*3 + i)*2 + {0,1}] = folded W, shift of conv2a / conv2b / conv2c(++branch1);
+//                           rank1[0..5] = g_w, g_inv, g_sh, r_w, r_inv, r_sh of block 1.
+// out[B*T*C] receives the stack's output; returns T (>0) or a negative CB_ERR_* code.
+extern "C" int emu_conv_stack(int bn_mode, const int* geom, const float* const* w, const float* const* rank1, const float* x,
+                              int B, int L, int sm_count, float* out, long long* launches) {
+    CbConfig c;
+    memset(&c, 0, sizeof(c));
+    c.n_blocks = geom[0]; c.channels = geom[1]; c.branch1_bn_mask = geom[2];
+    for (int i = 0; i < CB_MAX_BLOCKS; ++i) { c.k[i] = geom[3 + i]; c.stride[i] = geom[3 + CB_MAX_BLOCKS + i]; }
+    const int C = c.channels;
+    std::vector<float> act[3], vec((size_t)CB_BN_VECS * C), zeros((size_t)C, 0.f);
+    CbConvStackBufs bufs;
+    for (int i = 0; i < 3; ++i) { act[i].assign((size_t)B * L * C, -777.f); bufs.act[i] = act[i].data(); }
+    for (int i = 0; i < CB_BN_VECS; ++i) bufs.vec[i] = vec.data() + (size_t)i * C;
+    bufs.zeros = zeros.data();
+    EmuOps ops(sm_count, C);
+    const float* feat = nullptr;
+    int T = 0, rc;
+    const long long l0 = emu::launches;
+    if (bn_mode == CB_BN_BATCH) {
+        CbRawConv raw[4][CB_MAX_BLOCKS];
+        for (int b = 0; b < c.n_blocks; ++b)
+            for (int i = 0; i < 4; ++i) raw[i][b] = CbRawConv{w[(b * 4 + i) * 3], w[(b * 4 + i) * 3 + 1], w[(b * 4 + i) * 3 + 2]};
+        rc = cb_conv_stack_batch_bn(ops, c, raw[0], raw[1], raw[2], raw[3], bufs, x, B, L, &feat, &T);
+    } else {
+        CbConvW cw[3][CB_MAX_BLOCKS];
+        for (int b = 0; b < c.n_blocks; ++b)
+            for (int i = 0; i < 3; ++i) cw[i][b] = CbConvW{w[(b * 3 + i) * 2], w[(b * 3 + i) * 2 + 1]};
+        rc = cb_conv_stack_folded(ops, c, cw[0], cw[1], cw[2], rank1[0], rank1[1], rank1[2], rank1[3], rank1[4], rank1[5],
+                                  bufs, x, B, L, &feat, &T);
+    }
+    if (rc != CB_OK) return rc;
+    memcpy(out, feat, sizeof(float) * (size_t)B * T * C);
+    if (launches) *launches = emu::launches - l0;
+    return T;
+}
+
+// The reduction kernels on their own (odd channel counts, more partials than rows, strided sample walks).
+extern "C" int emu_bn_stats(const float* X, long long M, int C, int sm_count, const float* scale, const float* offset,
+                            float* inv, float* shift) {
+    EmuOps ops(sm_count, C);
+    return ops.bn_stats(X, M, scale, offset, inv, shift);
+}
+
+extern "C" int emu_bn_rank1(const float* x, int B, int t_in, int stride, int t_out, int C, int sm_count, const float* w,
+                            const float* scale, const float* offset, float* inv, float* shift) {
+    EmuOps ops(sm_count, C);
+    return ops.bn_rank1(x, B, t_in, stride, t_out, w, scale, offset, inv, shift);
+}

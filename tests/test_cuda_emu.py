@@ -1,0 +1,166 @@
+"""The fp32 conv-stack path compiled for the HOST and run under a thread-per-CUDA-thread emulation (tests/cuda_emu):
+the same kernel sources (cb_gemm_simt_kernel.cuh, cb_bn_kernels.cuh) and the same orchestration (cb_conv_stack.cuh) the
+CUDA library is built from, checked against the oracle without a GPU.  This is what covers the batch-statistics
+BatchNorm kernels and the buffer rotation of both BatchNorm modes on the CPU side; the `-m gpu` tests
+cover the real launches."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from chiron_b200 import model as M
+from oracle import chiron_oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "cuda_emu", "emu_conv_stack.cpp")
+LIB = os.path.join(HERE, "cuda_emu", "_build", "libemu_conv_stack.so")
+CSRC = os.path.join(os.path.dirname(HERE), "chiron_b200", "csrc")
+BN_EPS = np.float32(1e-5)
+FP = ctypes.POINTER(ctypes.c_float)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    deps = [SRC, os.path.join(HERE, "cuda_emu", "cuda_emu.h")] + [
+        os.path.join(CSRC, f) for f in ("cb_simt_types.h", "cb_gemm_simt_kernel.cuh", "cb_bn_kernels.cuh", "cb_conv_stack.cuh")]
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
+        os.makedirs(os.path.dirname(LIB), exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-Wno-unknown-pragmas",
+                               "-o", LIB, SRC])
+    lib = ctypes.CDLL(LIB)
+    lib.emu_conv_stack.restype = ctypes.c_int
+    lib.emu_bn_stats.restype = ctypes.c_int
+    lib.emu_bn_rank1.restype = ctypes.c_int
+    return lib
+
+
+def _fp(a):
+    return None if a is None else a.ctypes.data_as(FP)
+
+
+def _ref_inv_shift(mean, var, scale, offset):
+    inv = scale * (np.float32(1.0) / np.sqrt(var.astype(np.float32) + BN_EPS))
+    return inv, offset - mean.astype(np.float32) * inv
+
+
+@pytest.mark.parametrize("M_rows,C,sms", [(1, 4, 1), (37, 20, 1), (1000, 256, 1), (513, 64, 3), (300, 1024, 1), (5, 8, 148)])
+def test_column_statistics_kernels(emu, M_rows, C, sms):
+    rng = np.random.default_rng(M_rows + C)
+    X = (rng.normal(size=(M_rows, C)) * rng.uniform(0.1, 30, size=C) + rng.normal(size=C) * 5).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, size=C).astype(np.float32)
+    offset = rng.normal(size=C).astype(np.float32)
+    inv, shift = np.zeros(C, np.float32), np.zeros(C, np.float32)
+    assert emu.emu_bn_stats(_fp(X), ctypes.c_longlong(M_rows), C, sms, _fp(scale), _fp(offset), _fp(inv), _fp(shift)) == 0
+    x64 = X.astype(np.float64)
+    r_inv, r_shift = _ref_inv_shift(x64.mean(axis=0), x64.var(axis=0), scale, offset)
+    np.testing.assert_allclose(inv, r_inv, rtol=2e-6, atol=0)
+    np.testing.assert_allclose(shift, r_shift, rtol=0, atol=2e-6 * max(1.0, np.abs(r_shift).max()))
+
+
+@pytest.mark.parametrize("B,t_in,stride,sms", [(3, 50, 1, 1), (7, 503, 5, 1), (2, 9, 4, 148), (300, 40, 2, 2)])
+def test_rank1_statistics_kernels(emu, B, t_in, stride, sms):
+    rng = np.random.default_rng(B * t_in)
+    C = 12
+    t_out = -(-t_in // stride)
+    x = rng.normal(-0.2, 0.5, size=(B, t_in)).astype(np.float32)
+    w = rng.normal(size=C).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, size=C).astype(np.float32)
+    offset = rng.normal(size=C).astype(np.float32)
+    inv, shift = np.zeros(C, np.float32), np.zeros(C, np.float32)
+    assert emu.emu_bn_rank1(_fp(x), B, t_in, stride, t_out, C, sms, _fp(w), _fp(scale), _fp(offset), _fp(inv), _fp(shift)) == 0
+    prod = x[:, ::stride][:, :t_out].astype(np.float64)[:, :, None] * w.astype(np.float64)
+    r_inv, r_shift = _ref_inv_shift(prod.mean(axis=(0, 1)), prod.var(axis=(0, 1)), scale, offset)
+    np.testing.assert_allclose(inv, r_inv, rtol=5e-6, atol=0)
+    np.testing.assert_allclose(shift, r_shift, rtol=0, atol=5e-6 * max(1.0, np.abs(r_shift).max()))
+    # a branch without BatchNorm: identity
+    assert emu.emu_bn_rank1(_fp(x), B, t_in, stride, t_out, C, sms, _fp(w), None, None, _fp(inv), _fp(shift)) == 0
+    assert (inv == 1).all() and (shift == 0).all()
+
+
+def _geom(cfg):
+    k = list(cfg.k) + [0] * (8 - len(cfg.k))
+    s = list(cfg.stride) + [0] * (8 - len(cfg.stride))
+    return (ctypes.c_int * 19)(cfg.n_blocks, cfg.channels, cfg.branch1_bn_mask, *k[:8], *s[:8])
+
+
+def _run_stack(emu, bn_mode, cfg, ptr_arrays, rank1, x, sms):
+    B, L = x.shape
+    keep = [np.ascontiguousarray(a, dtype=np.float32) if a is not None else None for a in ptr_arrays]
+    tab = (FP * len(keep))(*[_fp(a) for a in keep])
+    r_keep = [np.ascontiguousarray(a, dtype=np.float32) for a in rank1]
+    r_tab = (FP * max(len(r_keep), 1))(*[_fp(a) for a in r_keep])
+    out = np.zeros(B * L * cfg.channels, np.float32)
+    n_launch = ctypes.c_longlong(0)
+    T = emu.emu_conv_stack(bn_mode, _geom(cfg), tab, r_tab, _fp(np.ascontiguousarray(x)), B, L, sms, _fp(out),
+                           ctypes.byref(n_launch))
+    assert T > 0, "emu_conv_stack failed (%d)" % T
+    return out[:B * T * cfg.channels].reshape(B, T, cfg.channels), n_launch.value
+
+
+def _fold(t, prefix):                                  # cb_create: population BN -> inv / shift
+    inv = t[prefix + "_bn/scale"] * (np.float32(1.0) / np.sqrt(t[prefix + "_bn/pop_var"] + BN_EPS))
+    return inv, t[prefix + "_bn/offset"] - t[prefix + "_bn/pop_mean"] * inv
+
+
+TOPOLOGIES = [dict(n_blocks=3, channels=8, k=[3, 3, 3], stride=[1, 1, 1], branch1_bn_mask=1),            # DNA_default shape
+              dict(n_blocks=3, channels=20, k=[13, 3, 3], stride=[5, 1, 1], branch1_bn_mask=1),         # RNA_default shape
+              dict(n_blocks=4, channels=12, k=[5, 3, 7, 2], stride=[2, 1, 3, 1], branch1_bn_mask=0b0110),
+              dict(n_blocks=5, channels=8, k=[3] * 5, stride=[1] * 5, branch1_bn_mask=1)]             # rna_test
+
+
+def _inputs(cfg, seed):
+    rng = np.random.default_rng(seed)
+    B, L = 3, 53
+    x = rng.normal(-0.16, 0.43, size=(B, L)).astype(np.float32)
+    x[2, 31:] = 0
+    return x
+
+
+@pytest.mark.parametrize("topo", TOPOLOGIES)
+@pytest.mark.parametrize("sms", [1, 148])
+def test_conv_stack_batch_statistics_mode(emu, topo, sms):
+    cfg = M.ModelConfig(hidden=4, **topo)
+    t = M.random_tensors(cfg, seed=21)
+    x = _inputs(cfg, 4)
+    ptrs = []
+    for b in range(cfg.n_blocks):
+        p = "res_layer%d" % (b + 1)
+        for conv in ("branch1/conv1", "branch2/conv2a", "branch2/conv2b", "branch2/conv2c"):
+            has_bn = (p + "/" + conv + "_bn/scale") in t
+            ptrs += [t[p + "/" + conv + "/weights"], t[p + "/" + conv + "_bn/scale"] if has_bn else None,
+                     t[p + "/" + conv + "_bn/offset"] if has_bn else None]
+    got, n_launch = _run_stack(emu, 1, cfg, ptrs, [], x, sms)
+    ref = O.cnn_forward(x, cfg, t, np.float64, bn_mode=1)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() < 2e-4 * max(1.0, np.abs(ref).max())
+    assert n_launch > 10 * cfg.n_blocks
+
+
+@pytest.mark.parametrize("topo", TOPOLOGIES)
+def test_conv_stack_population_mode(emu, topo):
+    cfg = M.ModelConfig(hidden=4, **topo)
+    t = M.random_tensors(cfg, seed=22)
+    x = _inputs(cfg, 5)
+    C = cfg.channels
+    ptrs, rank1 = [], []
+    for b in range(cfg.n_blocks):
+        p = "res_layer%d" % (b + 1)
+        has1 = cfg.branch1_bn_mask >> b & 1
+        inv1, sh1 = _fold(t, p + "/branch1/conv1") if has1 else (np.ones(C, np.float32), np.zeros(C, np.float32))
+        inva, sha = _fold(t, p + "/branch2/conv2a")
+        invb, shb = _fold(t, p + "/branch2/conv2b")
+        invc, shc = _fold(t, p + "/branch2/conv2c")
+        w1, w2a = t[p + "/branch1/conv1/weights"], t[p + "/branch2/conv2a/weights"]
+        w2b, w2c = t[p + "/branch2/conv2b/weights"], t[p + "/branch2/conv2c/weights"]
+        if b == 0:
+            rank1 = [w2a.reshape(-1), inva, sha, w1.reshape(-1), inv1, sh1]
+            ptrs += [np.zeros(4, np.float32), np.zeros(4, np.float32)]                      # conv2a of block 1 is generated
+            ptrs += [w2b.reshape(-1, C) * invb, shb, w2c * invc, shc]
+        else:
+            ptrs += [w2a * inva, sha, w2b.reshape(-1, C) * invb, shb, np.concatenate([w2c * invc, w1 * inv1]), shc + sh1]
+    got, _ = _run_stack(emu, 0, cfg, ptrs, rank1, x, 1)
+    ref = O.cnn_forward(x, cfg, t, np.float64, bn_mode=0)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())
