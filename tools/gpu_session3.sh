@@ -1,0 +1,10 @@
+#!/bin/bash
+# Session-3 GPU pass (one short gpurun call): all GPU tests, a bench line, timing + ncu traffic of the bn_* kernels.
+out=gpurun_out/r01_s3
+mkdir -p $out
+timeout 200 python -m pytest tests -m gpu -x -q > $out/pytest_gpu.txt 2>&1; tail -15 $out/pytest_gpu.txt
+timeout 60 python tools/bn_bench.py 1024 512 3 > $out/bn_bench.json 2> $out/bn_bench.err; cat $out/bn_bench.json
+timeout 150 python bench.py --steps 10 --warmup 3 > $out/bench_tc.json 2> $out/bench_tc.err; cut -c1-300 $out/bench_tc.json
+timeout 90 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+    -k regex:bn_ --csv --log-file $out/bn_kernels.csv python tools/bn_bench.py 1024 512 1 > $out/bn_ncu.log 2>&1
+tail -3 $out/bn_kernels.csv
