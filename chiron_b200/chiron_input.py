@@ -3,21 +3,40 @@
 Mirrors the eval side of chiron/chiron_input.py (read_signal :527-539, read_signal_fast5 :541-555,
 read_data_for_eval :253-292, padding :681-692, DataSet.next_batch(shuffle=False) :194-250) with numpy arrays instead of
 Python lists.  Normalisation is a per-model property stored in the weight blob (SURVEY.md finding 4): DNA_default needs
-the unique-value median/MAD that read_signal_fast5's MEDIAN branch computes."""
+the unique-value median/MAD that read_signal_fast5's MEDIAN branch computes.
+
+The three per-read hot spots -- the token loop of read_signal, the np.unique sort behind the normalisation and the
+per-window slicing -- run in the native library's host-side helpers (cb_host_parse_signal / cb_host_normalize /
+cb_host_windows, csrc/cb_host_signal.cu): single C passes that release the GIL, so the reader threads of
+chiron_eval.evaluation() work in parallel.  They are bit-identical to the numpy formulation the oracle keeps
+(tests/test_host_signal.py)."""
 from __future__ import annotations
+
+import ctypes
 
 import numpy as np
 
+from . import _lib
 from .model import NORM_FULL_MAD, NORM_NONE, NORM_UNIQUE_MAD
 
 MEAN, MEDIAN = "mean", "median"            # chiron/chiron_input.py:33-34
-_MAD_C = 0.6744897501960817                # statsmodels.robust.mad: median(|x - median|) / Phi^-1(3/4)
+
+
+def parse_signal_text(data: bytes) -> np.ndarray:
+    """Whitespace-separated numbers -> float32 samples (the token loop of chiron_input.py:527-532)."""
+    lib = _lib.load()
+    cap = len(data) // 2 + 1                # every sample takes at least one character and one separator
+    out = np.empty(cap, dtype=np.float32)
+    n = lib.cb_host_parse_signal(data, len(data), out.ctypes.data_as(ctypes.c_void_p), cap)
+    if n < 0:
+        _lib.check(int(n), "cb_host_parse_signal")
+    return out[:n].copy()
 
 
 def read_signal(file_path: str) -> np.ndarray:
     """Whitespace-separated samples of a ``.signal`` file (chiron_input.py:527-532), as float32."""
-    with open(file_path, "r") as f:
-        return np.asarray(f.read().split(), dtype=np.float32)
+    with open(file_path, "rb") as f:
+        return parse_signal_text(f.read())
 
 
 def read_signal_fast5(fast5_path: str) -> np.ndarray:
@@ -28,19 +47,15 @@ def read_signal_fast5(fast5_path: str) -> np.ndarray:
 
 def normalize_signal(signal: np.ndarray, mode: int) -> np.ndarray:
     """mode NORM_UNIQUE_MAD: (s - median(unique(s))) / mad(unique(s))   (chiron_input.py:548,553-554)
-    mode NORM_FULL_MAD:   (s - median(s)) / mad(s)                       (chiron_input.py:537-538)."""
-    s = np.asarray(signal, dtype=np.float64)
-    if mode == NORM_NONE or s.size == 0:
-        return s.astype(np.float32)
-    if mode == NORM_UNIQUE_MAD:
-        ref = np.unique(s)
-    elif mode == NORM_FULL_MAD:
-        ref = s
-    else:
+    mode NORM_FULL_MAD:   (s - median(s)) / mad(s)                       (chiron_input.py:537-538)
+    with mad = statsmodels.robust.mad = median(|x - median|) / 0.6745; float64 statistics, float32 result."""
+    if mode not in (NORM_NONE, NORM_UNIQUE_MAD, NORM_FULL_MAD):
         raise ValueError("unknown signal normalisation %r" % (mode,))
-    med = np.median(ref)
-    mad = np.median(np.abs(ref - med)) / _MAD_C
-    return ((s - med) / mad).astype(np.float32)
+    s = np.ascontiguousarray(signal, dtype=np.float32)
+    out = np.empty_like(s)
+    _lib.check(_lib.load().cb_host_normalize(s.ctypes.data_as(ctypes.c_void_p), s.size, int(mode),
+                                             out.ctypes.data_as(ctypes.c_void_p)), "cb_host_normalize")
+    return out
 
 
 class DataSet:
@@ -86,12 +101,13 @@ def read_data_for_eval(file_path: str, start_index: int = 0, step: int = 20, seg
 
 
 def windows_from_signal(f_signal: np.ndarray, step: int, seg_length: int) -> DataSet:
-    n = int(f_signal.shape[0])
-    starts = np.arange(0, n, step, dtype=np.int64)
-    event = np.zeros((len(starts), seg_length), dtype=np.float32)
-    lens = np.minimum(seg_length, n - starts).astype(np.int32)
-    if len(starts):
-        idx = starts[:, None] + np.arange(seg_length, dtype=np.int64)[None, :]
-        valid = idx < n
-        event[valid] = f_signal[idx[valid]]
+    sig = np.ascontiguousarray(f_signal, dtype=np.float32)
+    lib = _lib.load()
+    n_win = -(-sig.size // int(step)) if step > 0 else 0
+    event = np.empty((n_win, seg_length), dtype=np.float32)
+    lens = np.empty(n_win, dtype=np.int32)
+    n = lib.cb_host_windows(sig.ctypes.data_as(ctypes.c_void_p), sig.size, int(step), int(seg_length),
+                            event.ctypes.data_as(ctypes.c_void_p), lens.ctypes.data_as(ctypes.c_void_p), n_win)
+    if n < 0:
+        _lib.check(int(n), "cb_host_windows")
     return DataSet(event, lens)

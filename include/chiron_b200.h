@@ -130,6 +130,23 @@ int cb_assemble_host(cb_handle* h, const int8_t* bases, const int32_t* n_bases, 
                      int n_windows, int T, int jump, int L, int kernel,
                      int8_t* consensus, char* qual, int32_t* pos, int32_t* out_len, int max_len);
 
+/* -- host-side signal preparation (no GPU work; rows a1-a2 of the path) ------------------------------------------------ */
+
+/* The token loop of read_signal (chiron/chiron_input.py:527-532): ASCII-whitespace-separated numbers -> float32 samples
+ * (parsed as double, rounded once, like numpy's string -> float32 cast).  Returns the number of samples, or CB_ERR_ARG for
+ * a token that is not a number or when more than `cap` samples are present.  out == NULL only counts. */
+long long cb_host_parse_signal(const char* text, size_t nbytes, float* out, size_t cap);
+
+/* Signal normalisation (chiron/chiron_input.py:535-538, 548-554): mode = the CBW1 header's sig_norm --
+ * 0 none, 1 (s - median(unique(s))) / mad(unique(s)), 2 (s - median(s)) / mad(s), mad = median(|x - median|) / 0.6745
+ * (statsmodels.robust.mad); float64 statistics, result rounded once to float32.  in and out may alias. */
+int cb_host_normalize(const float* in, size_t n, int mode, float* out);
+
+/* read_data_for_eval + padding (chiron/chiron_input.py:253-292, 681-692): windows of L samples starting at 0, jump,
+ * 2*jump ... < n; tails zero padded, lens[w] = true length.  Returns the window count ceil(n / jump); with x == NULL or
+ * lens == NULL it only counts. */
+long long cb_host_windows(const float* sig, size_t n, int jump, int L, float* x, int32_t* lens, size_t cap_windows);
+
 /* -- introspection for tests / benchmarks ----------------------------------------------------------------------------- */
 
 /* Number of kernels this library has launched on the handle since creation (bench.py's gpu_launches). */
