@@ -47,6 +47,7 @@ SIGNATURES = {
     "cb_host_parse_signal": (c_longlong, [c_char_p, c_size_t, c_void_p, c_size_t]),
     "cb_host_normalize": (c_int, [c_void_p, c_size_t, c_int, c_void_p]),
     "cb_host_windows": (c_longlong, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p, c_size_t]),
+    "cb_host_format_segments": (c_longlong, [c_char_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t]),
     "cb_launch_count": (c_longlong, [c_void_p]),
     "cb_last_forward_ms": (c_int, [c_void_p, POINTER(c_float), c_int]),
     "cb_enable_timing": (None, [c_void_p, c_int]),

@@ -29,17 +29,18 @@ from typing import Dict, List, Optional
 import numpy as np
 
 from .chiron_input import read_data_for_eval
-from .engine import Basecaller, get_assembler_kernal, index2base
+from .engine import Basecaller, format_segments, get_assembler_kernal, index2base
 from .shard import assign_reads, rank_world
 from .utils.unix_time import unix_time
 
 FLAGS = None
 
 
-def write_output(segments: List[str], consensus: str, time_list, file_pre: str, global_setting, concise: bool = False,
+def write_output(segments, consensus: str, time_list, file_pre: str, global_setting, concise: bool = False,
                  suffix: str = "fasta", seg_q_score=None, q_score: Optional[str] = None):
     """Byte-compatible with chiron_eval.py:176-242 (including FASTA-style segment records in .fastq files and the
-    missing trailing newline of fasta results)."""
+    missing trailing newline of fasta results).  ``segments`` is the reference's list of base strings, or the already
+    formatted records as ``bytes`` (engine.format_segments: what evaluation() passes)."""
     start_time, reading_time, basecall_time, assembly_time = time_list
     result_folder = os.path.join(global_setting.output, "result")
     seg_folder = os.path.join(global_setting.output, "segments")
@@ -52,11 +53,17 @@ def write_output(segments: List[str], consensus: str, time_list, file_pre: str, 
         path_meta = os.path.join(meta_folder, file_pre + ".meta")
     with open(path_con, "w+") as out_con:
         if not concise:
-            with open(path_reads, "w+") as out_f:
-                for indx, read in enumerate(segments):
-                    out_f.write(">{}{}\n{}\n".format(file_pre, str(indx), read))
-                    if (suffix == "fastq") and (seg_q_score is not None):
-                        out_f.write("@{}{}\n{}\n+\n{}\n".format(file_pre, str(indx), read, seg_q_score[indx]))
+            if isinstance(segments, (bytes, bytearray)):
+                with open(path_reads, "wb") as out_f:
+                    out_f.write(segments)
+            else:
+                with open(path_reads, "w+") as out_f:
+                    records = []
+                    for indx, read in enumerate(segments):
+                        records.append(">{}{}\n{}\n".format(file_pre, str(indx), read))
+                        if (suffix == "fastq") and (seg_q_score is not None):
+                            records.append("@{}{}\n{}\n+\n{}\n".format(file_pre, str(indx), read, seg_q_score[indx]))
+                    out_f.write("".join(records))
         if (suffix == "fastq") and (q_score is not None):
             out_con.write("@{}\n{}\n+\n{}\n".format(file_pre, consensus, q_score))
         else:
@@ -149,17 +156,16 @@ def evaluation(flags=None, caller: Optional[Basecaller] = None) -> Dict[str, dic
 
     def finish(st: _ReadState):
         basecall_time = time.time() - st.start_time
-        keep = st.n_bases > 0                                   # sparse2dense drops empty rows (chiron_eval.py:56-66)
-        bpreads = [index2base(st.bases[i, :st.n_bases[i]]) for i in np.nonzero(keep)[0]]
         kernal = get_assembler_kernal(jump, L)
         seq, qual, pos = caller.assemble(st.bases, st.n_bases, st.prob if with_qs else None, jump, L, kernel=kernal,
                                          with_qs=with_qs)
         assembly_time = time.time() - st.start_time
         file_pre = os.path.splitext(st.name)[0]
-        write_q.put((bpreads, seq, [st.start_time, st.reading_time, basecall_time, assembly_time], file_pre, qual))
+        # the segment strings are built by the writer thread: this thread's job is to keep the GPU fed
+        write_q.put((st.bases, st.n_bases, seq, [st.start_time, st.reading_time, basecall_time, assembly_time], file_pre, qual))
         summary[st.name] = {"windows": st.n, "bases": len(seq), "pos": pos}
 
-    # ---- writer thread: formatting and file I/O off the GPU-feeding thread ---------------------------------------------
+    # ---- writer threads: formatting and file I/O off the GPU-feeding thread (one file set per read: order-free) ----------
     write_q: "queue.Queue" = queue.Queue()
     write_err: List[BaseException] = []
 
@@ -169,14 +175,17 @@ def evaluation(flags=None, caller: Optional[Basecaller] = None) -> Dict[str, dic
             if item is None:
                 return
             try:
-                bpreads, seq, times, file_pre, qual = item
-                write_output(bpreads, seq, times, file_pre, concise=flags.concise, suffix=flags.extension, q_score=qual,
+                bases, n_bases, seq, times, file_pre, qual = item
+                records = format_segments(file_pre, bases, n_bases)
+                write_output(records, seq, times, file_pre, concise=flags.concise, suffix=flags.extension, q_score=qual,
                              global_setting=flags)
-            except BaseException as e:            # surfaced after the join below
+            except BaseException as e:            # surfaced after the joins below
                 write_err.append(e)
 
-    writer_thread = threading.Thread(target=writer, name="chiron-writer", daemon=True)
-    writer_thread.start()
+    n_writers = max(1, min(4, (os.cpu_count() or 2) // 4))
+    writer_threads = [threading.Thread(target=writer, name="chiron-writer-%d" % i, daemon=True) for i in range(n_writers)]
+    for t in writer_threads:
+        t.start()
 
     # ---- two batches in flight on the GPU (slots 0/1 of cb_basecall_submit) ----------------------------------------------
     inflight = collections.deque()               # (ticket, owners) in submission order
@@ -245,8 +254,10 @@ def evaluation(flags=None, caller: Optional[Basecaller] = None) -> Dict[str, dic
     while open_reads:                                            # reads with zero windows
         finish(open_reads.pop(0))
     pool.shutdown(wait=True)
-    write_q.put(None)
-    writer_thread.join()
+    for _ in writer_threads:
+        write_q.put(None)
+    for t in writer_threads:
+        t.join()
     if write_err:
         raise write_err[0]
     if own:

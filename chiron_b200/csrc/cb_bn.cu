@@ -10,12 +10,12 @@ int cb_launch_bn_rank1(cb_handle* h, const float* x, int B, int t_in, int stride
     const int C = h->cfg.channels;
     int n_part = 0;
     if (scale) {
-        n_part = bn_grid(h->sm_count, (long long)B * t_out, BN_THREADS);
+        n_part = bn_grid(h->sm_count, (long long)B * t_out, BN_THREADS, BN_STATS_CTAS);
         bn_x_stats_kernel<<<n_part, BN_THREADS, 0, s>>>(x, B, t_in, stride, t_out, h->bn_part);
         CB_CHECK_LAUNCH();
         h->launches++;
     }
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(h->bn_part, n_part, C, (double)B * t_out, w, scale, offset, inv, shift);
+    bn_finalize_kernel<<<(C + 31) / 32, BN_FIN_THREADS, 0, s>>>(h->bn_part, n_part, C, (double)B * t_out, w, scale, offset, inv, shift);
     CB_CHECK_LAUNCH();
     h->launches++;
     return CB_OK;
@@ -27,11 +27,11 @@ int cb_launch_bn_stats(cb_handle* h, const float* X, long long M, const float* s
     const int C = h->cfg.channels;
     if ((C & 3) || C > 1024) { cb_set_error("batch-statistics BatchNorm needs channels %% 4 == 0 and <= 1024"); return CB_ERR_ARG; }
     const int rpp = BN_THREADS / (C >> 2);
-    const int n_part = bn_grid(h->sm_count, M, rpp);
+    const int n_part = bn_grid(h->sm_count, M, rpp, BN_STATS_CTAS);
     bn_col_stats_kernel<<<n_part, BN_THREADS, 0, s>>>(X, M, C, h->bn_part);
     CB_CHECK_LAUNCH();
     h->launches++;
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(h->bn_part, n_part, C, (double)M, nullptr, scale, offset, inv, shift);
+    bn_finalize_kernel<<<(C + 31) / 32, BN_FIN_THREADS, 0, s>>>(h->bn_part, n_part, C, (double)M, nullptr, scale, offset, inv, shift);
     CB_CHECK_LAUNCH();
     h->launches++;
     return CB_OK;
@@ -40,7 +40,7 @@ int cb_launch_bn_stats(cb_handle* h, const float* X, long long M, const float* s
 int cb_launch_bn_apply(cb_handle* h, const BnApplyArgs& a, cudaStream_t s) {
     const BnApply p = bn_apply_params(a, h->cfg.channels);
     if (p.M <= 0) return CB_OK;
-    const int grid = bn_grid(h->sm_count, p.M * (p.C >> 2), BN_THREADS);
+    const int grid = bn_grid(h->sm_count, (p.M * (p.C >> 2) + BN_APPLY_U - 1) / BN_APPLY_U, BN_THREADS, BN_APPLY_CTAS);
     bn_apply_kernel<<<grid, BN_THREADS, 0, s>>>(p);
     CB_CHECK_LAUNCH();
     h->launches++;

@@ -21,8 +21,9 @@
 
 namespace cb_bn {
 
-
 constexpr int BN_THREADS = 256;
+constexpr int BN_STATS_CTAS = 4;      // resident CTAs per SM of the statistics kernels (<= 64 registers)
+constexpr int BN_APPLY_CTAS = 3;      // ... of the apply kernel (<= 85 registers): 3 x 256 threads x 4 x 16 B = 48 KB of loads in flight per SM
 constexpr float BN_EPS = 1e-5f;   // chiron/cnn.py:187
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_x_stats_kernel(const float* __r
 }
 
 // part[blockIdx.x][0][c] / [1][c] = sum / sum of squares of channel c over the CTA's rows.  C % 4 == 0, C <= 1024.
-__global__ void __launch_bounds__(BN_THREADS) bn_col_stats_kernel(const float* __restrict__ X, long long M, int C,
+__global__ void __launch_bounds__(BN_THREADS, BN_STATS_CTAS) bn_col_stats_kernel(const float* __restrict__ X, long long M, int C,
                                                                   double* __restrict__ part) {
     __shared__ double red[2][BN_THREADS * 4];         // [row group][channel]: rpp * C <= 1024 entries
     const int qw = C >> 2;                            // channel quads per row
@@ -69,12 +70,20 @@ __global__ void __launch_bounds__(BN_THREADS) bn_col_stats_kernel(const float* _
     const int q = threadIdx.x % qw, r = threadIdx.x / qw;
     double s[4] = {0.0, 0.0, 0.0, 0.0}, ss[4] = {0.0, 0.0, 0.0, 0.0};
     if (r < rpp) {
-        for (long long m = (long long)blockIdx.x * rpp + r; m < M; m += (long long)gridDim.x * rpp) {
-            const float4 v = ldg4(X + m * C + q * 4);
+        auto add = [&](const float4& v) {
             const double d[4] = {(double)v.x, (double)v.y, (double)v.z, (double)v.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) { s[j] += d[j]; ss[j] += d[j] * d[j]; }
+        };
+        const long long step = (long long)gridDim.x * rpp;
+        const float* src = X + q * 4;
+        long long m = (long long)blockIdx.x * rpp + r;
+        for (; m + 3 * step < M; m += 4 * step) {       // four independent 128-bit loads in flight per thread
+            const float4 v0 = ldg4(src + m * C), v1 = ldg4(src + (m + step) * C), v2 = ldg4(src + (m + 2 * step) * C),
+                         v3 = ldg4(src + (m + 3 * step) * C);
+            add(v0); add(v1); add(v2); add(v3);
         }
+        for (; m < M; m += step) add(ldg4(src + m * C));
 #pragma unroll
         for (int j = 0; j < 4; ++j) { red[0][r * C + q * 4 + j] = s[j]; red[1][r * C + q * 4 + j] = ss[j]; }
     }
@@ -89,18 +98,30 @@ __global__ void __launch_bounds__(BN_THREADS) bn_col_stats_kernel(const float* _
 
 // w == nullptr: part is [n_part][2][C] (bn_col_stats_kernel).  w != nullptr: part is [n_part][2] statistics of the raw
 // samples and the normalised tensor is the rank-1 product w[c] * x.  scale == nullptr: no BN on this branch (inv 1, shift 0).
-__global__ void bn_finalize_kernel(const double* __restrict__ part, int n_part, int C, double count,
-                                   const float* __restrict__ w, const float* __restrict__ scale,
-                                   const float* __restrict__ offset, float* __restrict__ inv, float* __restrict__ shift) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    if (!scale) { inv[c] = 1.0f; shift[c] = 0.0f; return; }
+// One CTA of 32 warps per 32 channels: lanes = channels (256-byte coalesced loads), warp w sums the partials
+// w, w + 32, ... and the 32 warp sums are added in warp order -- a fixed tree, so the moments are deterministic.
+constexpr int BN_FIN_THREADS = 1024;
+__global__ void __launch_bounds__(BN_FIN_THREADS) bn_finalize_kernel(const double* __restrict__ part, int n_part, int C,
+                                                                     double count, const float* __restrict__ w,
+                                                                     const float* __restrict__ scale,
+                                                                     const float* __restrict__ offset,
+                                                                     float* __restrict__ inv, float* __restrict__ shift) {
+    __shared__ double red[2][32][33];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    const bool ok = c < C;
     double s = 0.0, q = 0.0;
-    if (w) {
-        for (int i = 0; i < n_part; ++i) { s += part[(size_t)i * 2]; q += part[(size_t)i * 2 + 1]; }
-    } else {
-        for (int i = 0; i < n_part; ++i) { s += part[(size_t)i * 2 * C + c]; q += part[(size_t)i * 2 * C + C + c]; }
+    if (scale && ok) {
+        const size_t step = w ? 2 : (size_t)2 * C, off_s = w ? 0 : (size_t)c, off_q = w ? 1 : (size_t)C + c;
+        for (int i = wp; i < n_part; i += 32) { s += part[i * step + off_s]; q += part[i * step + off_q]; }
     }
+    red[0][wp][lane] = s;
+    red[1][wp][lane] = q;
+    __syncthreads();
+    if (wp != 0 || !ok) return;
+    if (!scale) { inv[c] = 1.0f; shift[c] = 0.0f; return; }
+    s = 0.0; q = 0.0;
+    for (int i = 0; i < 32; ++i) { s += red[0][i][lane]; q += red[1][i][lane]; }
     double mean = s / count;
     double var = q / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -121,47 +142,75 @@ struct BnApply {
     int C;
 };
 
-__global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const BnApply p) {
+// Grid-stride over float4 elements in batches of BN_APPLY_U: all loads of a batch are issued before the first store (the
+// tensors may alias `out`, which would otherwise serialise every load behind the previous store), and the (row, channel)
+// position advances incrementally instead of by a 64-bit division per element.
+constexpr int BN_APPLY_U = 4;
+__global__ void __launch_bounds__(BN_THREADS, BN_APPLY_CTAS) bn_apply_kernel(const BnApply p) {
     const int qw = p.C >> 2;
     const long long n = p.M * qw;
-    for (long long i = (long long)blockIdx.x * BN_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * BN_THREADS) {
-        const long long m = i / qw;
-        const int c = (int)(i - m * qw) * 4;
-        // a and b may alias out: plain loads (ld.global.nc must not see memory this kernel writes)
-        const float4 v = *reinterpret_cast<const float4*>(p.a + m * p.C + c), iv = ldg4(p.a_inv + c), sh = ldg4(p.a_sh + c);
-        float o[4] = {fmaf(v.x, iv.x, sh.x), fmaf(v.y, iv.y, sh.y), fmaf(v.z, iv.z, sh.z), fmaf(v.w, iv.w, sh.w)};
-        if (p.b) {
-            const float4 u = *reinterpret_cast<const float4*>(p.b + m * p.C + c);
-            if (p.b_inv) {
-                const float4 bi = ldg4(p.b_inv + c), bs = ldg4(p.b_sh + c);
-                o[0] += fmaf(u.x, bi.x, bs.x); o[1] += fmaf(u.y, bi.y, bs.y);
-                o[2] += fmaf(u.z, bi.z, bs.z); o[3] += fmaf(u.w, bi.w, bs.w);
-            } else {
-                o[0] += u.x; o[1] += u.y; o[2] += u.z; o[3] += u.w;
+    const long long S = (long long)gridDim.x * BN_THREADS;
+    const long long dm = S / qw;
+    const int dq = (int)(S - dm * qw);
+    long long i = (long long)blockIdx.x * BN_THREADS + threadIdx.x;
+    long long m = i / qw;
+    int cq = (int)(i - m * qw);
+    while (i < n) {
+        float4 va[BN_APPLY_U], vb[BN_APPLY_U];
+        long long mm[BN_APPLY_U];
+        int cc[BN_APPLY_U];
+        int cnt = 0;
+#pragma unroll
+        for (int u = 0; u < BN_APPLY_U; ++u) {
+            if (i < n) {
+                mm[u] = m; cc[u] = cq * 4; cnt = u + 1;
+                // a and b may alias out: plain loads (ld.global.nc must not see memory this kernel writes)
+                va[u] = *reinterpret_cast<const float4*>(p.a + m * p.C + cq * 4);
+                if (p.b) vb[u] = *reinterpret_cast<const float4*>(p.b + m * p.C + cq * 4);
+                i += S; m += dm; cq += dq;
+                if (cq >= qw) { cq -= qw; ++m; }
             }
         }
-        if (p.x) {
-            const long long win = m / p.t_out;
-            const long long to = m - win * p.t_out;
-            const float xr = __ldg(p.x + win * p.t_inr + to * p.strider);
-            const float4 w = ldg4(p.rw + c), ri = ldg4(p.rinv + c), rs = ldg4(p.rsh + c);
-            o[0] += fmaf(xr * w.x, ri.x, rs.x); o[1] += fmaf(xr * w.y, ri.y, rs.y);
-            o[2] += fmaf(xr * w.z, ri.z, rs.z); o[3] += fmaf(xr * w.w, ri.w, rs.w);
-        }
-        if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
+        for (int u = 0; u < BN_APPLY_U; ++u) {
+            if (u < cnt) {
+                const int c = cc[u];
+                const float4 v = va[u], iv = ldg4(p.a_inv + c), sh = ldg4(p.a_sh + c);
+                float o[4] = {fmaf(v.x, iv.x, sh.x), fmaf(v.y, iv.y, sh.y), fmaf(v.z, iv.z, sh.z), fmaf(v.w, iv.w, sh.w)};
+                if (p.b) {
+                    const float4 t = vb[u];
+                    if (p.b_inv) {
+                        const float4 bi = ldg4(p.b_inv + c), bs = ldg4(p.b_sh + c);
+                        o[0] += fmaf(t.x, bi.x, bs.x); o[1] += fmaf(t.y, bi.y, bs.y);
+                        o[2] += fmaf(t.z, bi.z, bs.z); o[3] += fmaf(t.w, bi.w, bs.w);
+                    } else {
+                        o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
+                    }
+                }
+                if (p.x) {
+                    const long long win = mm[u] / p.t_out;
+                    const long long to = mm[u] - win * p.t_out;
+                    const float xr = __ldg(p.x + win * p.t_inr + to * p.strider);
+                    const float4 w = ldg4(p.rw + c), ri = ldg4(p.rinv + c), rs = ldg4(p.rsh + c);
+                    o[0] += fmaf(xr * w.x, ri.x, rs.x); o[1] += fmaf(xr * w.y, ri.y, rs.y);
+                    o[2] += fmaf(xr * w.z, ri.z, rs.z); o[3] += fmaf(xr * w.w, ri.w, rs.w);
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
+                }
+                *reinterpret_cast<float4*>(p.out + mm[u] * p.C + c) = make_float4(o[0], o[1], o[2], o[3]);
+            }
         }
-        *reinterpret_cast<float4*>(p.out + m * p.C + c) = make_float4(o[0], o[1], o[2], o[3]);
     }
 }
 
 // ---- launch plans shared by cb_bn.cu and the host emulation ---------------------------------------------------------------
-// Grid of a grid-stride kernel: enough CTAs for the work, at most four resident 256-thread CTAs per SM (a multiple of the
-// SM count) and at most CB_BN_MAX_PART (the partial-sum buffer).
-inline int bn_grid(int sm_count, long long work_items, int per_block) {
+// Grid of a grid-stride kernel: enough CTAs for the work, at most the CTAs that are resident at once (ctas_per_sm x SM
+// count: one wave, no tail) and at most CB_BN_MAX_PART (the partial-sum buffer).
+inline int bn_grid(int sm_count, long long work_items, int per_block, int ctas_per_sm) {
     long long g = (work_items + per_block - 1) / per_block;
-    const long long cap = (long long)(sm_count > 0 ? sm_count : 148) * 4;
+    const long long cap = (long long)(sm_count > 0 ? sm_count : 148) * ctas_per_sm;
     if (g > cap) g = cap;
     if (g > CB_BN_MAX_PART) g = CB_BN_MAX_PART;
     return g < 1 ? 1 : (int)g;

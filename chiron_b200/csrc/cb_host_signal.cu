@@ -3,6 +3,7 @@
 //   cb_host_parse_signal   chiron_input.read_signal           chiron/chiron_input.py:527-532   text -> float32 samples
 //   cb_host_normalize      read_signal / read_signal_fast5     chiron/chiron_input.py:535-538, 548-554   median / MAD
 //   cb_host_windows        read_data_for_eval + padding        chiron/chiron_input.py:253-292, 681-692   sliding windows
+//   cb_host_format_segments  write_output's segment records    chiron/chiron_eval.py:211-214             dense bases -> text
 //
 // In the reference these are a Python token loop, np.unique (a sort) and per-window list slicing; here they are single
 // passes in C that release the GIL (ctypes), so the reader threads of chiron_eval.evaluation() run in parallel and keep up
@@ -10,6 +11,7 @@
 // float32): tests/test_host_signal.py.
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -122,4 +124,34 @@ extern "C" long long cb_host_windows(const float* sig, size_t n, int jump, int L
         lens[w] = (int32_t)len;
     }
     return (long long)n_win;
+}
+
+extern "C" long long cb_host_format_segments(const char* name, const int8_t* bases, const int32_t* n_bases, int n_windows, int T,
+                                             char* out, size_t cap) {
+    if (!name || n_windows < 0 || T < 1 || ((!bases || !n_bases) && n_windows)) { cb_set_error("cb_host_format_segments: bad arguments"); return CB_ERR_ARG; }
+    static const char LUT[4] = {'A', 'C', 'G', 'T'};
+    const size_t name_len = strlen(name);
+    size_t pos = 0;
+    int kept = 0;
+    for (int w = 0; w < n_windows; ++w) {
+        int n = n_bases[w];
+        if (n <= 0) continue;                          // sparse2dense drops windows without bases (chiron_eval.py:56-66)
+        if (n > T) n = T;
+        char idx[16];
+        const int idx_len = snprintf(idx, sizeof(idx), "%d", kept++);
+        const size_t need = 1 + name_len + (size_t)idx_len + 1 + (size_t)n + 1;
+        if (out) {
+            if (pos + need > cap) { cb_set_error("cb_host_format_segments: output buffer of %zu bytes is too small", cap); return CB_ERR_ARG; }
+            char* p = out + pos;
+            *p++ = '>';
+            memcpy(p, name, name_len); p += name_len;
+            memcpy(p, idx, (size_t)idx_len); p += idx_len;
+            *p++ = '\n';
+            const int8_t* row = bases + (size_t)w * T;
+            for (int i = 0; i < n; ++i) p[i] = LUT[row[i] & 3];
+            p[n] = '\n';
+        }
+        pos += need;
+    }
+    return (long long)pos;
 }

@@ -14,11 +14,22 @@ from . import _lib
 from .model import load_model
 
 BASES = "ACGT"
+_BASE_LUT = np.frombuffer(BASES.encode("ascii"), dtype=np.uint8)
 
 
 def index2base(read: Sequence[int]) -> str:
-    """chiron/chiron_eval.py:100-113."""
-    return "".join(BASES[int(x)] for x in read)
+    """chiron/chiron_eval.py:100-113 (one table lookup over the whole read instead of a Python loop per base)."""
+    idx = np.asarray(read, dtype=np.int64)
+    if idx.size and (idx.min() < 0 or idx.max() > 3):
+        raise IndexError("base index outside 0..3")
+    return _BASE_LUT[idx].tobytes().decode("ascii")
+
+
+def windows2bases(bases: np.ndarray, n_bases: np.ndarray) -> List[str]:
+    """index2base of every non-empty row of a dense [n, T] decode result (sparse2dense drops the empty rows,
+    chiron/chiron_eval.py:56-66)."""
+    chars = _BASE_LUT[np.asarray(bases, dtype=np.int64) & 3]
+    return [chars[i, :n_bases[i]].tobytes().decode("ascii") for i in np.nonzero(np.asarray(n_bases) > 0)[0]]
 
 
 def get_assembler_kernal(jump: int, segment_len: int) -> str:
@@ -33,6 +44,22 @@ def get_assembler_kernal(jump: int, segment_len: int) -> str:
 
 def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def format_segments(file_pre: str, bases: np.ndarray, n_bases: np.ndarray) -> bytes:
+    """The text of segments/<file_pre>.<ext> for a dense [n, T] decode result: ``">{}{}\\n{}\\n".format(file_pre, idx,
+    read)`` per non-empty window (write_output, chiron/chiron_eval.py:211-214), formatted natively without the GIL."""
+    bases = np.ascontiguousarray(bases, dtype=np.int8)
+    n_bases = np.ascontiguousarray(n_bases, dtype=np.int32)
+    n, T = bases.shape
+    name = file_pre.encode("utf-8")
+    kept = int((n_bases > 0).sum())
+    cap = kept * (len(name) + 13) + int(np.clip(n_bases, 0, T).sum()) + 1
+    buf = ctypes.create_string_buffer(cap)
+    got = _lib.load().cb_host_format_segments(name, _ptr(bases), _ptr(n_bases), n, T, buf, cap)
+    if got < 0:
+        _lib.check(int(got), "cb_host_format_segments")
+    return buf.raw[:got]
 
 
 class Basecaller:

@@ -147,6 +147,12 @@ int cb_host_normalize(const float* in, size_t n, int mode, float* out);
  * lens == NULL it only counts. */
 long long cb_host_windows(const float* sig, size_t n, int jump, int L, float* x, int32_t* lens, size_t cap_windows);
 
+/* The segment records write_output puts into segments/<name>.<ext> (chiron/chiron_eval.py:211-214): for every window with
+ * n_bases > 0 (sparse2dense drops the others, :56-66), in window order, ">" name idx "\n" ACGT... "\n" with idx counting
+ * the kept windows.  Returns the bytes written (out == NULL: the bytes needed). */
+long long cb_host_format_segments(const char* name, const int8_t* bases, const int32_t* n_bases, int n_windows, int T,
+                                  char* out, size_t cap);
+
 /* -- introspection for tests / benchmarks ----------------------------------------------------------------------------- */
 
 /* Number of kernels this library has launched on the handle since creation (bench.py's gpu_launches). */

@@ -26,19 +26,19 @@ struct EmuOps {          // mirrors the launchers of cb_gemm_simt.cu / cb_bn.cu:
                  const float* offset, float* inv, float* shift) {
         int n_part = 0;
         if (scale) {
-            n_part = cb_bn::bn_grid(sm_count, (long long)B * t_out, cb_bn::BN_THREADS);
+            n_part = cb_bn::bn_grid(sm_count, (long long)B * t_out, cb_bn::BN_THREADS, cb_bn::BN_STATS_CTAS);
             emu::launch(n_part, cb_bn::BN_THREADS, [&] { cb_bn::bn_x_stats_kernel(x, B, t_in, stride, t_out, part.data()); });
         }
-        emu::launch((C + 127) / 128, 128, [&] {
+        emu::launch((C + 31) / 32, cb_bn::BN_FIN_THREADS, [&] {
             cb_bn::bn_finalize_kernel(part.data(), n_part, C, (double)B * t_out, w, scale, offset, inv, shift);
         });
         return CB_OK;
     }
     int bn_stats(const float* X, long long M, const float* scale, const float* offset, float* inv, float* shift) {
         if ((C & 3) || C > 1024) return CB_ERR_ARG;
-        const int n_part = cb_bn::bn_grid(sm_count, M, cb_bn::BN_THREADS / (C >> 2));
+        const int n_part = cb_bn::bn_grid(sm_count, M, cb_bn::BN_THREADS / (C >> 2), cb_bn::BN_STATS_CTAS);
         emu::launch(n_part, cb_bn::BN_THREADS, [&] { cb_bn::bn_col_stats_kernel(X, M, C, part.data()); });
-        emu::launch((C + 127) / 128, 128, [&] {
+        emu::launch((C + 31) / 32, cb_bn::BN_FIN_THREADS, [&] {
             cb_bn::bn_finalize_kernel(part.data(), n_part, C, (double)M, nullptr, scale, offset, inv, shift);
         });
         return CB_OK;
@@ -46,7 +46,7 @@ struct EmuOps {          // mirrors the launchers of cb_gemm_simt.cu / cb_bn.cu:
     int bn_apply(const BnApplyArgs& a) {
         if (a.M <= 0) return CB_OK;
         const cb_bn::BnApply p = cb_bn::bn_apply_params(a, C);
-        const int grid = cb_bn::bn_grid(sm_count, p.M * (p.C >> 2), cb_bn::BN_THREADS);
+        const int grid = cb_bn::bn_grid(sm_count, (p.M * (p.C >> 2) + cb_bn::BN_APPLY_U - 1) / cb_bn::BN_APPLY_U, cb_bn::BN_THREADS, cb_bn::BN_APPLY_CTAS);
         emu::launch(grid, cb_bn::BN_THREADS, [&] { cb_bn::bn_apply_kernel(p); });
         return CB_OK;
     }

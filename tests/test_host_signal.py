@@ -124,3 +124,16 @@ def test_reader_threads_run_in_parallel():
         t.join()
     four = time.perf_counter() - t0
     assert four < 2.5 * one, "4 threads took %.1f ms, one thread %.1f ms" % (four * 1e3, one * 1e3)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(0, 40), st.integers(1, 30), st.integers(0, 2**31 - 1), st.sampled_from(["read1", "r", "a/b_c.d-é"]))
+def test_segment_records_match_the_reference_format(n, T, seed, name):
+    """cb_host_format_segments == write_output's loop over index2base strings (chiron_eval.py:211-214)."""
+    from chiron_b200.engine import format_segments, index2base
+    rng = np.random.default_rng(seed)
+    bases = rng.integers(0, 4, size=(n, T)).astype(np.int8)
+    n_bases = rng.integers(0, T + 1, size=n).astype(np.int32)
+    kept = [index2base(bases[i, :n_bases[i]]) for i in range(n) if n_bases[i] > 0]      # sparse2dense drops empty rows
+    ref = "".join(">{}{}\n{}\n".format(name, str(i), r) for i, r in enumerate(kept)).encode("utf-8")
+    assert format_segments(name, bases, n_bases) == ref
