@@ -16,7 +16,7 @@ from typing import Dict
 import numpy as np
 
 from . import tf_bundle
-from .model import (BN_BATCH, BN_POPULATION, ModelConfig, NORM_FULL_MAD, NORM_UNIQUE_MAD, RNN_NORMAL, RNN_RNA,
+from .model import (BN_BATCH, BN_POPULATION, CELL_GRU, CELL_LSTM, ModelConfig, NORM_FULL_MAD, NORM_UNIQUE_MAD, RNN_NORMAL, RNN_RNA,
                     pack_blob)
 
 
@@ -77,22 +77,37 @@ def convert_tensors(raw: Dict[str, np.ndarray], conv_attrs: Dict[str, dict], mod
         fmt = "BDGRU_rnn/{d}/multi_rnn_cell/cell_{l}/lstm_cell/{t}"        # chiron/rnn.py:140-143
     else:
         raise ValueError("checkpoint has no LSTM variables")
+    # LSTMCell: .../lstm_cell/{kernel,bias}; GRUCell: .../gru_cell/{gates,candidate}/{kernel,bias} (chiron/rnn.py:47-53)
+    cell_type = CELL_GRU if fmt.replace("lstm_cell", "gru_cell").format(l=0, d="fw", t="gates/kernel") in raw else CELL_LSTM
+    if cell_type == CELL_GRU:
+        fmt = fmt.replace("lstm_cell", "gru_cell")
+    first = "gates/kernel" if cell_type == CELL_GRU else "kernel"
     n_layers = 0
-    while fmt.format(l=n_layers, d="fw", t="kernel") in raw:
+    while fmt.format(l=n_layers, d="fw", t=first) in raw:
         n_layers += 1
-    H = raw[fmt.format(l=0, d="fw", t="bias")].shape[0] // 4
-    for l in range(n_layers):
-        for d in ("fw", "bw"):
-            tensors["lstm/%d/%s/kernel" % (l, d)] = raw[fmt.format(l=l, d=d, t="kernel")]
-            tensors["lstm/%d/%s/bias" % (l, d)] = raw[fmt.format(l=l, d=d, t="bias")]
+    if n_layers == 0:
+        raise ValueError("checkpoint has no LSTMCell / GRUCell variables (BNLSTM is not supported)")
+    if cell_type == CELL_GRU:
+        H = raw[fmt.format(l=0, d="fw", t="candidate/bias")].shape[0]
+        for l in range(n_layers):
+            for d in ("fw", "bw"):
+                for leaf in ("gates/kernel", "gates/bias", "candidate/kernel", "candidate/bias"):
+                    tensors["gru/%d/%s/%s" % (l, d, leaf)] = raw[fmt.format(l=l, d=d, t=leaf)]
+    else:
+        H = raw[fmt.format(l=0, d="fw", t="bias")].shape[0] // 4
+        for l in range(n_layers):
+            for d in ("fw", "bw"):
+                tensors["lstm/%d/%s/kernel" % (l, d)] = raw[fmt.format(l=l, d=d, t="kernel")]
+                tensors["lstm/%d/%s/bias" % (l, d)] = raw[fmt.format(l=l, d=d, t="bias")]
     for n in ("weights", "bias", "weights_class", "bias_class"):
         tensors["rnn_fnn_layer/" + n] = raw["rnn_fnn_layer/" + n]
     n_class = raw["rnn_fnn_layer/bias_class"].shape[0]
     rnn_json = model_json.get("rnn", {})
     if rnn_json.get("layer_num", n_layers) != n_layers or rnn_json.get("hidden_num", H) != H:
         raise ValueError("model.json rnn section disagrees with the checkpoint")
-    if rnn_json.get("cell_type", "LSTM") != "LSTM":
-        raise ValueError("only LSTM cells have shipped weights (chiron/rnn.py:47-60)")
+    if rnn_json.get("cell_type", "LSTM") not in ("LSTM", "GRU") or (rnn_json.get("cell_type", "LSTM") == "GRU") != (cell_type == CELL_GRU):
+        raise ValueError("model.json cell_type %r disagrees with the checkpoint or is unsupported (LSTM and GRU cells only, "
+                         "chiron/rnn.py:47-60)" % rnn_json.get("cell_type"))
     # Input normalisation is a property of how the weights were trained (SURVEY.md finding 4): DNA_default needs
     # the unique-value median/MAD (pinned by the golden outputs); RNA_default a scale~1 normalisation (unpinned).
     sig_norm = NORM_UNIQUE_MAD if layout == RNN_NORMAL else NORM_FULL_MAD
@@ -100,7 +115,7 @@ def convert_tensors(raw: Dict[str, np.ndarray], conv_attrs: Dict[str, dict], mod
         raise ValueError("checkpoint mixes population-statistics and batch-statistics BatchNorm variables")
     cfg = ModelConfig(n_blocks=n_blocks, channels=int(C), hidden=int(H), n_layers=n_layers, n_class=int(n_class),
                       rnn_layout=layout, branch1_bn_mask=mask, k=k, stride=stride, sig_norm=sig_norm,
-                      reverse_signal=int(layout == RNN_RNA), bn_mode=bn_modes.pop())
+                      reverse_signal=int(layout == RNN_RNA), bn_mode=bn_modes.pop(), cell_type=cell_type)
     return pack_blob(cfg, tensors)
 
 

@@ -28,7 +28,7 @@ struct BlobHeader {               // chiron_b200/model.py: "<4s8i8i8i6iq" (packe
     char magic[4];
     int32_t version, n_blocks, channels, hidden, n_layers, n_class, rnn_layout, branch1_bn_mask;
     int32_t k[8], stride[8];
-    int32_t sig_norm, reverse_signal, bn_mode, reserved[3];
+    int32_t sig_norm, reverse_signal, bn_mode, cell_type, reserved[2];
 };
 constexpr size_t HEADER_BYTES = 4 + 30 * 4 + 8;
 
@@ -77,7 +77,13 @@ extern "C" int cb_create(const void* blob, size_t nbytes, int device, int precis
     c.n_blocks = hd.n_blocks; c.channels = hd.channels; c.hidden = hd.hidden; c.n_layers = hd.n_layers;
     c.n_class = hd.n_class; c.rnn_layout = hd.rnn_layout; c.branch1_bn_mask = hd.branch1_bn_mask;
     for (int i = 0; i < CB_MAX_BLOCKS; ++i) { c.k[i] = hd.k[i]; c.stride[i] = hd.stride[i]; }
-    c.sig_norm = hd.sig_norm; c.reverse_signal = hd.reverse_signal;
+    c.sig_norm = hd.sig_norm; c.reverse_signal = hd.reverse_signal; c.cell_type = hd.cell_type;
+    if (c.cell_type != CB_CELL_LSTM && c.cell_type != CB_CELL_GRU) { delete h; cb_set_error("cb_create: unknown RNN cell type %d", c.cell_type); return CB_ERR_BLOB; }
+    if (c.cell_type == CB_CELL_GRU && precision != CB_PREC_FP32) {
+        delete h;
+        cb_set_error("cb_create: GRU cells run on the CB_PREC_FP32 path only (the tensor-core recurrence is an LSTM kernel)");
+        return CB_ERR_ARG;
+    }
     const int C = c.channels, H = c.hidden;
     for (int b = 0; b < c.n_blocks; ++b)
         if (c.k[b] < 1 || c.stride[b] < 1) { delete h; cb_set_error("cb_create: bad conv geometry"); return CB_ERR_BLOB; }
@@ -163,18 +169,38 @@ extern "C" int cb_create(const void* blob, size_t nbytes, int device, int precis
     }
     const size_t o_zeros = hb.add(std::vector<float>((size_t)(C > 8 * H ? C : 8 * H), 0.0f));
     size_t o_wx[CB_MAX_LAYERS][2], o_b[CB_MAX_LAYERS][2], o_whh[CB_MAX_LAYERS][2], o_wxcat[CB_MAX_LAYERS], o_bcat[CB_MAX_LAYERS];
+    size_t o_gwc[CB_MAX_LAYERS][2] = {};
+    const int G = c.cell_type == CB_CELL_GRU ? 3 : 4;         // hoisted input-projection columns per direction: G*H
     for (int l = 0; l < c.n_layers; ++l) {
         const int in = l == 0 ? C : (c.rnn_layout == 0 ? 2 * H : H);
-        const float* kern[2]; const float* bias[2];
-        for (int d = 0; d < 2; ++d) { kern[d] = take((size_t)(in + H) * 4 * H); bias[d] = take((size_t)4 * H); }
-        std::vector<float> cat((size_t)in * 8 * H), bcat((size_t)8 * H);
+        std::vector<float> wx[2], bx[2];                      // per direction: input kernel [in, G*H], bias [G*H]
         for (int d = 0; d < 2; ++d) {
-            o_wx[l][d] = hb.add(std::vector<float>(kern[d], kern[d] + (size_t)in * 4 * H));
-            o_whh[l][d] = hb.add(std::vector<float>(kern[d] + (size_t)in * 4 * H, kern[d] + (size_t)(in + H) * 4 * H));
-            o_b[l][d] = hb.add(std::vector<float>(bias[d], bias[d] + 4 * H));
+            wx[d].resize((size_t)in * G * H); bx[d].resize((size_t)G * H);
+            if (c.cell_type == CB_CELL_GRU) {                 // TF GRUCell: gates/kernel [in+H,2H] (r|u), candidate/kernel [in+H,H]
+                const float* gk = take((size_t)(in + H) * 2 * H); const float* gb = take((size_t)2 * H);
+                const float* ck = take((size_t)(in + H) * H);     const float* cb = take((size_t)H);
+                for (int k = 0; k < in; ++k) {
+                    memcpy(&wx[d][(size_t)k * 3 * H], gk + (size_t)k * 2 * H, sizeof(float) * 2 * H);
+                    memcpy(&wx[d][(size_t)k * 3 * H + 2 * H], ck + (size_t)k * H, sizeof(float) * H);
+                }
+                memcpy(&bx[d][0], gb, sizeof(float) * 2 * H);
+                memcpy(&bx[d][2 * H], cb, sizeof(float) * H);
+                o_whh[l][d] = hb.add(std::vector<float>(gk + (size_t)in * 2 * H, gk + (size_t)(in + H) * 2 * H));
+                o_gwc[l][d] = hb.add(std::vector<float>(ck + (size_t)in * H, ck + (size_t)(in + H) * H));
+            } else {                                          // TF LSTMCell: kernel [in+H,4H] (i,j,f,o), bias [4H]
+                const float* kern = take((size_t)(in + H) * 4 * H); const float* bias = take((size_t)4 * H);
+                wx[d].assign(kern, kern + (size_t)in * 4 * H);
+                bx[d].assign(bias, bias + 4 * H);
+                o_whh[l][d] = hb.add(std::vector<float>(kern + (size_t)in * 4 * H, kern + (size_t)(in + H) * 4 * H));
+            }
+            o_wx[l][d] = hb.add(wx[d]);
+            o_b[l][d] = hb.add(bx[d]);
+        }
+        std::vector<float> cat((size_t)in * 2 * G * H), bcat((size_t)2 * G * H);      // fw || bw (stacked-bidirectional layout)
+        for (int d = 0; d < 2; ++d) {
             for (int k = 0; k < in; ++k)
-                memcpy(&cat[(size_t)k * 8 * H + (size_t)d * 4 * H], kern[d] + (size_t)k * 4 * H, sizeof(float) * 4 * H);
-            memcpy(&bcat[(size_t)d * 4 * H], bias[d], sizeof(float) * 4 * H);
+                memcpy(&cat[(size_t)k * 2 * G * H + (size_t)d * G * H], &wx[d][(size_t)k * G * H], sizeof(float) * G * H);
+            memcpy(&bcat[(size_t)d * G * H], bx[d].data(), sizeof(float) * G * H);
         }
         o_wxcat[l] = hb.add(cat);
         o_bcat[l] = hb.add(bcat);
@@ -227,6 +253,7 @@ extern "C" int cb_create(const void* blob, size_t nbytes, int device, int precis
     for (int l = 0; l < c.n_layers; ++l) {
         for (int d = 0; d < 2; ++d) {
             h->wx[l][d] = base + o_wx[l][d]; h->whh[l][d] = base + o_whh[l][d]; h->bias[l][d] = base + o_b[l][d];
+            h->gru_wc[l][d] = c.cell_type == CB_CELL_GRU ? base + o_gwc[l][d] : nullptr;
         }
         h->wxcat[l] = base + o_wxcat[l]; h->bcat[l] = base + o_bcat[l];
     }
@@ -434,28 +461,36 @@ extern "C" int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_o
 
     // ---- BiLSTM stack (rnn.py:20-64 stacked-bidirectional; rnn.py:99-145 per-direction MultiRNNCell) ---------------
     const float* Z = X; int ldz = C;
+    const int G = c.cell_type == CB_CELL_GRU ? 3 : 4;          // pre-activation columns per direction: G*H
     for (int l = 0; l < c.n_layers; ++l) {
         GemmProblem g;
         const int n_gemm = (l == 0 || c.rnn_layout == 0) ? 1 : 2;
         for (int d = 0; d < n_gemm; ++d) {
             memset(&g, 0, sizeof(g));
             const int in = l == 0 ? C : (c.rnn_layout == 0 ? 2 * H : H);
-            g.M = M; g.N = n_gemm == 1 ? 8 * H : 4 * H; g.K = in; g.t_out = T; g.t_in0 = T; g.stride0 = 1; g.taps = 1; g.c0 = in;
+            g.M = M; g.N = n_gemm == 1 ? 2 * G * H : G * H; g.K = in; g.t_out = T; g.t_in0 = T; g.stride0 = 1; g.taps = 1; g.c0 = in;
             g.W = n_gemm == 1 ? h->wxcat[l] : h->wx[l][d];
             g.shift = n_gemm == 1 ? h->bcat[l] : h->bias[l][d];
-            g.src0 = Z + (l == 0 ? 0 : d * H); g.lda0 = ldz; g.out = h->pre + d * 4 * H; g.ldo = 8 * H;
+            g.src0 = Z + (l == 0 ? 0 : d * H); g.lda0 = ldz; g.out = h->pre + d * G * H; g.ldo = 2 * G * H;
             if ((rc = run_gemm(h, g, s, CB_CAT_LSTM_IN)) != CB_OK) return rc;
         }
-        LstmProblem lp;
-        memset(&lp, 0, sizeof(lp));
-        lp.B = B; lp.T = T; lp.H = H; lp.pre = h->pre; lp.ld_pre = 8 * H;
-        lp.whh[0] = h->whh[l][0]; lp.whh[1] = h->whh[l][1];
-        lp.lens = seq_len_out; lp.out = h->lstm_out[l & 1]; lp.ldo = 2 * H; lp.layer = l;
-        {
-            const int pi = cb_prof_begin(h, CB_CAT_LSTM_REC, s);
+        const int pi = cb_prof_begin(h, CB_CAT_LSTM_REC, s);
+        if (c.cell_type == CB_CELL_GRU) {
+            GruProblem gp;
+            memset(&gp, 0, sizeof(gp));
+            gp.B = B; gp.T = T; gp.H = H; gp.pre = h->pre; gp.ld_pre = 2 * G * H;
+            for (int d = 0; d < 2; ++d) { gp.wg[d] = h->whh[l][d]; gp.wc[d] = h->gru_wc[l][d]; }
+            gp.lens = seq_len_out; gp.out = h->lstm_out[l & 1]; gp.ldo = 2 * H; gp.layer = l;
+            rc = cb_launch_gru_simt(h, gp, s);
+        } else {
+            LstmProblem lp;
+            memset(&lp, 0, sizeof(lp));
+            lp.B = B; lp.T = T; lp.H = H; lp.pre = h->pre; lp.ld_pre = 2 * G * H;
+            lp.whh[0] = h->whh[l][0]; lp.whh[1] = h->whh[l][1];
+            lp.lens = seq_len_out; lp.out = h->lstm_out[l & 1]; lp.ldo = 2 * H; lp.layer = l;
             rc = cb_launch_lstm_simt(h, lp, s);
-            cb_prof_end(h, pi, s);
         }
+        cb_prof_end(h, pi, s);
         if (rc != CB_OK) return rc;
         Z = h->lstm_out[l & 1]; ldz = 2 * H;
     }

@@ -51,16 +51,6 @@ struct TcGemm {
     CbImg o; int o_plane0;
 };
 
-struct LstmProblem {         // both directions of one layer (grid.y = direction)
-    int B, T, H;
-    const float* pre;         // [B*T, ld_pre] hoisted input projection + bias; direction d uses columns [d*4H, (d+1)*4H)
-    int ld_pre;
-    const float* whh[2];      // [H,4H] fp32 recurrent kernels (fw, bw)
-    const int32_t* lens;      // [B]
-    float* out; int ldo;      // h of direction d written to out[(b*T+t)*ldo + d*H + u]; zeros for t >= len
-    int layer;
-};
-
 struct cb_handle {
     int device;
     int precision;
@@ -82,7 +72,8 @@ struct cb_handle {
     const float* bias[CB_MAX_LAYERS][2]; // [4H]
     const float* wxcat[CB_MAX_LAYERS];   // [in, 8H] fw||bw (stacked-bidirectional layout)
     const float* bcat[CB_MAX_LAYERS];    // [8H]
-    const float* whh[CB_MAX_LAYERS][2];  // [H,4H]
+    const float* whh[CB_MAX_LAYERS][2];  // [H,4H] (LSTM) or [H,2H] recurrent gate kernel (GRU)
+    const float* gru_wc[CB_MAX_LAYERS][2];  // [H,H] recurrent candidate kernel (GRU)
     const float *head_w, *head_b, *head_wc, *head_bc;
     // workspace
     void* ws; size_t ws_bytes;
@@ -115,6 +106,7 @@ struct cb_handle {
 // ---- launchers (each returns CB_OK or an error code; they bump h->launches) -----------------------------------------
 int cb_launch_gemm_simt(cb_handle* h, const GemmProblem& p, cudaStream_t s);
 int cb_launch_lstm_simt(cb_handle* h, const LstmProblem& p, cudaStream_t s);
+int cb_launch_gru_simt(cb_handle* h, const GruProblem& p, cudaStream_t s);
 int cb_launch_bn_rank1(cb_handle* h, const float* x, int B, int t_in, int stride, int t_out, const float* w,
                        const float* scale, const float* offset, float* inv, float* shift, cudaStream_t s);
 int cb_launch_bn_stats(cb_handle* h, const float* X, long long M, const float* scale, const float* offset, float* inv,

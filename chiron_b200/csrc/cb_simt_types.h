@@ -14,6 +14,7 @@ struct CbConfig {
     int n_blocks, channels, hidden, n_layers, n_class, rnn_layout, branch1_bn_mask;
     int k[CB_MAX_BLOCKS], stride[CB_MAX_BLOCKS];
     int sig_norm, reverse_signal;
+    int cell_type;            // 0 LSTMCell, 1 GRUCell
 };
 
 // ---- one dense contraction  out[M,N] = act(A_gather[M,K] @ W[K,N] + shift[N] (+ rank-1 residual)) -----------------
@@ -51,6 +52,28 @@ struct BnApplyArgs {
     int relu;
     float* out;                             // may alias a (every element is read and written by the same thread)
     long long M;
+};
+
+// ---- recurrences (fp32 path): both directions of one layer (grid.y = direction) -------------------------------------------------
+struct LstmProblem {
+    int B, T, H;
+    const float* pre;         // [B*T, ld_pre] hoisted input projection + bias; direction d uses columns [d*4H, (d+1)*4H)
+    int ld_pre;
+    const float* whh[2];      // [H,4H] fp32 recurrent kernels (fw, bw)
+    const int32_t* lens;      // [B]
+    float* out; int ldo;      // h of direction d written to out[(b*T+t)*ldo + d*H + u]; zeros for t >= len
+    int layer;
+};
+
+struct GruProblem {
+    int B, T, H;
+    const float* pre;         // [B*T, ld_pre]; direction d uses columns [d*3H, (d+1)*3H) = r | u | candidate
+    int ld_pre;
+    const float* wg[2];       // [H,2H] recurrent gate kernels (fw, bw), columns r | u
+    const float* wc[2];       // [H,H] recurrent candidate kernels
+    const int32_t* lens;      // [B]
+    float* out; int ldo;      // as LstmProblem
+    int layer;
 };
 
 // ---- weights of the residual blocks --------------------------------------------------------------------------------------

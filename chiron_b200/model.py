@@ -12,13 +12,15 @@ the blob header.  Blob layout (little endian):
     int32    k[8], stride[8]          (conv2b kernel width / stride of block b; branch1 shares the stride)
     int32    sig_norm (0 none, 1 unique-median/MAD, 2 full-signal median/MAD), reverse_signal,
              bn_mode (0 = population statistics, the shipped checkpoints' tf.cond BN, chiron/cnn.py:125-163;
-             1 = batch statistics, HEAD's simple_global_bn, chiron/cnn.py:166-188), reserved[3]
+             1 = batch statistics, HEAD's simple_global_bn, chiron/cnn.py:166-188),
+             cell_type (0 = LSTMCell, 1 = GRUCell; chiron/rnn.py:47-53,126-131), reserved[2]
     int64    n_floats
     float32  weights[n_floats]       in the canonical order of ``tensor_specs``
 
 Canonical tensor order: for every block ``branch1/conv1`` W[cin,C] (+bn), ``conv2a`` W[cin,C] +bn, ``conv2b``
 W[k,C,C] +bn, ``conv2c`` W[C,C] +bn, where bn = scale, offset, pop_mean, pop_var (each [C]); then for every LSTM layer
-and direction (fw, bw) kernel[in+H,4H] and bias[4H] (TF LSTMCell layout, gate column order i,j,f,o); then the head
+and direction (fw, bw) kernel[in+H,4H] and bias[4H] (TF LSTMCell layout, gate column order i,j,f,o) -- or, for GRU cells,
+gates/kernel[in+H,2H], gates/bias[2H] (columns r,u), candidate/kernel[in+H,H], candidate/bias[H] (TF GRUCell) --; then the head
 ``weights[2,H]``, ``bias[H]``, ``weights_class[H,n_class]``, ``bias_class[n_class]`` (chiron/rnn.py:73-88).
 """
 from __future__ import annotations
@@ -36,6 +38,7 @@ BN_EPS = 1e-5                       # chiron/cnn.py:125 (epsilon=1e-5), :187
 RNN_NORMAL, RNN_RNA = 0, 1
 NORM_NONE, NORM_UNIQUE_MAD, NORM_FULL_MAD = 0, 1, 2
 BN_POPULATION, BN_BATCH = 0, 1
+CELL_LSTM, CELL_GRU = 0, 1
 _HEADER = struct.Struct("<4s8i8i8i6iq")
 
 
@@ -53,6 +56,7 @@ class ModelConfig:
     sig_norm: int = NORM_UNIQUE_MAD
     reverse_signal: int = 0
     bn_mode: int = BN_POPULATION
+    cell_type: int = CELL_LSTM
 
     def total_stride(self) -> int:
         s = 1
@@ -95,8 +99,14 @@ def tensor_specs(cfg: ModelConfig) -> List[Tuple[str, Tuple[int, ...]]]:
         bn(p + "/branch2/conv2c")
     for l in range(cfg.n_layers):
         for d in ("fw", "bw"):
-            specs.append(("lstm/%d/%s/kernel" % (l, d), (cfg.lstm_in(l) + H, 4 * H)))
-            specs.append(("lstm/%d/%s/bias" % (l, d), (4 * H,)))
+            if cfg.cell_type == CELL_GRU:
+                specs.append(("gru/%d/%s/gates/kernel" % (l, d), (cfg.lstm_in(l) + H, 2 * H)))
+                specs.append(("gru/%d/%s/gates/bias" % (l, d), (2 * H,)))
+                specs.append(("gru/%d/%s/candidate/kernel" % (l, d), (cfg.lstm_in(l) + H, H)))
+                specs.append(("gru/%d/%s/candidate/bias" % (l, d), (H,)))
+            else:
+                specs.append(("lstm/%d/%s/kernel" % (l, d), (cfg.lstm_in(l) + H, 4 * H)))
+                specs.append(("lstm/%d/%s/bias" % (l, d), (4 * H,)))
     specs.append(("rnn_fnn_layer/weights", (2, H)))
     specs.append(("rnn_fnn_layer/bias", (H,)))
     specs.append(("rnn_fnn_layer/weights_class", (H, cfg.n_class)))
@@ -116,7 +126,7 @@ def pack_blob(cfg: ModelConfig, tensors: Dict[str, np.ndarray]) -> bytes:
     s = list(cfg.stride) + [0] * (MAX_BLOCKS - len(cfg.stride))
     head = _HEADER.pack(MAGIC, 1, cfg.n_blocks, cfg.channels, cfg.hidden, cfg.n_layers, cfg.n_class, cfg.rnn_layout,
                         cfg.branch1_bn_mask, *k[:MAX_BLOCKS], *s[:MAX_BLOCKS], cfg.sig_norm, cfg.reverse_signal,
-                        cfg.bn_mode, 0, 0, 0, flat.size)
+                        cfg.bn_mode, cfg.cell_type, 0, 0, flat.size)
     return head + flat.tobytes()
 
 
@@ -127,10 +137,10 @@ def unpack_blob(blob: bytes) -> Tuple[ModelConfig, Dict[str, np.ndarray]]:
     n_blocks, channels, hidden, n_layers, n_class, rnn_layout, mask = vals[2:9]
     k = list(vals[9:17])[:n_blocks]
     s = list(vals[17:25])[:n_blocks]
-    sig_norm, reverse_signal, bn_mode = vals[25], vals[26], vals[27]
+    sig_norm, reverse_signal, bn_mode, cell_type = vals[25], vals[26], vals[27], vals[28]
     n_floats = vals[31]
     cfg = ModelConfig(n_blocks, channels, hidden, n_layers, n_class, rnn_layout, mask, k, s, sig_norm, reverse_signal,
-                      bn_mode)
+                      bn_mode, cell_type)
     flat = np.frombuffer(blob, dtype="<f4", count=n_floats, offset=_HEADER.size)
     tensors: Dict[str, np.ndarray] = {}
     pos = 0
@@ -166,6 +176,8 @@ def random_tensors(cfg: ModelConfig, seed: int = 0) -> Dict[str, np.ndarray]:
             v = rng.uniform(-lim, lim, size=shape)
         elif leaf in ("bias", "bias_class"):
             v = rng.normal(0.0, 0.05, size=shape)
+            if name.endswith("gates/bias"):
+                v = v + 1.0                      # GRUCell's gate bias initialiser
         elif name == "rnn_fnn_layer/weights":
             v = rng.normal(0.0, np.sqrt(2.0 / (2 * cfg.hidden)), size=shape) + 0.5
         elif name == "rnn_fnn_layer/weights_class":

@@ -50,6 +50,10 @@ enum {
  * HEAD.  In that mode a window's result depends on the batch it is in, exactly as in the reference. */
 enum { CB_BN_POPULATION = 0, CB_BN_BATCH = 1 };
 
+/* Recurrent cell of the model (CBW1 header field cell_type; model.json "cell_type", chiron/rnn.py:47-53,126-131).
+ * GRU models run on CB_PREC_FP32 handles only (cb_create fails with CB_ERR_ARG otherwise); BNLSTM is not supported. */
+enum { CB_CELL_LSTM = 0, CB_CELL_GRU = 1 };
+
 /* Assembly kernels, chiron/chiron_eval.py:138-150 (get_assembler_kernal). */
 enum { CB_ASM_SIMPLE = 0, CB_ASM_GLUE = 1, CB_ASM_STICK = 2 };
 

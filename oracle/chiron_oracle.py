@@ -179,6 +179,45 @@ def lstm_direction(x: np.ndarray, lens: np.ndarray, kernel: np.ndarray, bias: np
     return out
 
 
+def gru_direction(x: np.ndarray, lens: np.ndarray, gate_kernel: np.ndarray, gate_bias: np.ndarray,
+                  cand_kernel: np.ndarray, cand_bias: np.ndarray, reverse: bool, dtype=np.float32) -> np.ndarray:
+    """One GRUCell run by dynamic_rnn (chiron/rnn.py:51-53,129-131; TF 1.15 rnn_cell_impl.GRUCell.call):
+    r, u = split(sigmoid(concat[x_t, h] @ Kg + bg));  c = tanh(concat[x_t, r*h] @ Kc + bc);  h' = u*h + (1-u)*c.
+    sequence_length / reverse semantics as in ``lstm_direction``.  PARITY UNPINNED: no GRU checkpoint ships."""
+    B, T, D = x.shape
+    H = cand_bias.shape[0]
+    gate_kernel, cand_kernel = gate_kernel.astype(dtype), cand_kernel.astype(dtype)
+    gate_bias, cand_bias = gate_bias.astype(dtype), cand_bias.astype(dtype)
+    pre_g = (x.reshape(B * T, D) @ gate_kernel[:D]).reshape(B, T, 2 * H)
+    pre_c = (x.reshape(B * T, D) @ cand_kernel[:D]).reshape(B, T, H)
+    wg_h, wc_h = gate_kernel[D:], cand_kernel[D:]
+    h = np.zeros((B, H), dtype=dtype)
+    out = np.zeros((B, T, H), dtype=dtype)
+    one = dtype(1.0)
+    lens = np.asarray(lens)
+    max_len = int(lens.max()) if B else 0
+    rows_all = np.arange(B)
+    for step in range(max_len):
+        active = step < lens
+        tt = np.where(active, lens - 1 - step, 0) if reverse else np.full(B, step)
+        g = _sigmoid(pre_g[rows_all, tt] + h @ wg_h + gate_bias)
+        r, u = g[:, :H], g[:, H:]
+        c = np.tanh(pre_c[rows_all, tt] + (r * h) @ wc_h + cand_bias)
+        h_new = u * h + (one - u) * c
+        h = np.where(active[:, None], h_new, h).astype(dtype)
+        rows = np.nonzero(active)[0]
+        out[rows, tt[rows]] = h_new[rows]
+    return out
+
+
+def _cell_direction(x, lens, cfg, t, l, d, reverse, dtype):
+    if getattr(cfg, "cell_type", 0) == 1:
+        p = "gru/%d/%s/" % (l, d)
+        return gru_direction(x, lens, t[p + "gates/kernel"], t[p + "gates/bias"], t[p + "candidate/kernel"],
+                             t[p + "candidate/bias"], reverse, dtype)
+    return lstm_direction(x, lens, t["lstm/%d/%s/kernel" % (l, d)], t["lstm/%d/%s/bias" % (l, d)], reverse, dtype)
+
+
 def rnn_forward(fea: np.ndarray, lens: np.ndarray, cfg, t: Dict[str, np.ndarray], dtype=np.float32) -> np.ndarray:
     """rnn_layers (stack_bidirectional_dynamic_rnn, chiron/rnn.py:20-64) or rnn_layers_rna (MultiRNNCell per direction
     + bidirectional_dynamic_rnn, chiron/rnn.py:99-145).  Returns lasth [B,T,2H]."""
@@ -186,8 +225,8 @@ def rnn_forward(fea: np.ndarray, lens: np.ndarray, cfg, t: Dict[str, np.ndarray]
     if cfg.rnn_layout == 0:
         x = fea
         for l in range(cfg.n_layers):
-            fw = lstm_direction(x, lens, t["lstm/%d/fw/kernel" % l], t["lstm/%d/fw/bias" % l], False, dtype)
-            bw = lstm_direction(x, lens, t["lstm/%d/bw/kernel" % l], t["lstm/%d/bw/bias" % l], True, dtype)
+            fw = _cell_direction(x, lens, cfg, t, l, "fw", False, dtype)
+            bw = _cell_direction(x, lens, cfg, t, l, "bw", True, dtype)
             x = np.concatenate([fw, bw], axis=2)
         return x
     outs = []
@@ -196,7 +235,7 @@ def rnn_forward(fea: np.ndarray, lens: np.ndarray, cfg, t: Dict[str, np.ndarray]
         for l in range(cfg.n_layers):
             # inside MultiRNNCell every layer sees the same (possibly reversed) time order, so running each layer as
             # its own reversed pass is identical to reversing once around the stack.
-            x = lstm_direction(x, lens, t["lstm/%d/%s/kernel" % (l, d)], t["lstm/%d/%s/bias" % (l, d)], rev, dtype)
+            x = _cell_direction(x, lens, cfg, t, l, d, rev, dtype)
         outs.append(x)
     return np.concatenate(outs, axis=2)
 

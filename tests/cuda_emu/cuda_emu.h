@@ -8,6 +8,7 @@
 #pragma once
 #include <algorithm>
 #include <array>
+#include <atomic>
 #include <barrier>
 #include <cmath>
 #include <cstdint>
@@ -31,6 +32,7 @@ static inline float4 make_float4(float x, float y, float z, float w) { return fl
 namespace emu {
 struct Dim { unsigned x, y, z; };
 struct BlockCtx {
+    unsigned char* dyn_smem;
     std::barrier<>* block_bar;
     std::vector<std::unique_ptr<std::barrier<>>>* warp_bar;
     std::vector<std::array<double, 32>>* shfl;
@@ -41,25 +43,30 @@ inline thread_local BlockCtx* ctx = nullptr;
 inline Dim b_dim{1, 1, 1}, g_dim{1, 1, 1};
 inline long long launches = 0, threads_run = 0;
 
-// Run body() once per CUDA thread of a grid x block launch (1-D grid and block).
+inline unsigned char* dyn_smem() { return ctx->dyn_smem; }
+
+// Run body() once per CUDA thread of a (grid_x, grid_y) x block launch (1-D blocks) with dyn_bytes of dynamic shared memory.
 template <class F>
-void launch(unsigned grid, unsigned block, F&& body) {
-    g_dim = Dim{grid, 1, 1};
+void launch2d(unsigned grid_x, unsigned grid_y, unsigned block, size_t dyn_bytes, F&& body) {
+    g_dim = Dim{grid_x, grid_y, 1};
     b_dim = Dim{block, 1, 1};
     const unsigned warps = (block + 31) / 32;
-    for (unsigned blk = 0; blk < grid; ++blk) {
+    std::vector<unsigned char> dyn(dyn_bytes + 64);
+    unsigned char* dyn_base = dyn.data() + (64 - reinterpret_cast<uintptr_t>(dyn.data()) % 64) % 64;
+    for (unsigned by = 0; by < grid_y; ++by)
+    for (unsigned blk = 0; blk < grid_x; ++blk) {
         std::barrier<> bb((std::ptrdiff_t)block);
         std::vector<std::unique_ptr<std::barrier<>>> wb;
         for (unsigned w = 0; w < warps; ++w)
             wb.emplace_back(new std::barrier<>((std::ptrdiff_t)std::min(32u, block - 32 * w)));
         std::vector<std::array<double, 32>> sh(warps);
-        BlockCtx c{&bb, &wb, &sh, block};
+        BlockCtx c{dyn_base, &bb, &wb, &sh, block};
         std::vector<std::thread> th;
         th.reserve(block);
         for (unsigned t = 0; t < block; ++t)
-            th.emplace_back([&, t, blk] {
+            th.emplace_back([&, t, blk, by] {
                 t_idx = Dim{t, 0, 0};
-                b_idx = Dim{blk, 0, 0};
+                b_idx = Dim{blk, by, 0};
                 ctx = &c;
                 body();
                 // a thread that leaves early must not strand the others at a later barrier
@@ -71,6 +78,9 @@ void launch(unsigned grid, unsigned block, F&& body) {
     }
     ++launches;
 }
+
+template <class F>
+void launch(unsigned grid, unsigned block, F&& body) { launch2d(grid, 1, block, 0, static_cast<F&&>(body)); }
 }  // namespace emu
 
 #define threadIdx (emu::t_idx)
@@ -80,6 +90,13 @@ void launch(unsigned grid, unsigned block, F&& body) {
 
 template <class T>
 static inline T __ldg(const T* p) { return *p; }
+
+static inline int atomicMax(int* addr, int v) {
+    std::atomic_ref<int> a(*addr);
+    int old = a.load();
+    while (old < v && !a.compare_exchange_weak(old, v)) {}
+    return old;
+}
 
 static inline void __syncthreads() { emu::ctx->block_bar->arrive_and_wait(); }
 

@@ -1,6 +1,7 @@
 // Host build of the fp32 conv-stack path for tests/test_cuda_emu.py -- TEST INFRASTRUCTURE ONLY.
 // Compiles the SAME kernel and orchestration sources the CUDA library is built from
 // (cb_gemm_simt_kernel.cuh, cb_bn_kernels.cuh, cb_conv_stack.cuh) against the host emulation in cuda_emu.h.
+#define CB_HOST_EMU 1
 #include "cuda_emu.h"
 
 #include "../../include/chiron_b200.h"
@@ -8,6 +9,7 @@
 #include "../../chiron_b200/csrc/cb_gemm_simt_kernel.cuh"
 #include "../../chiron_b200/csrc/cb_bn_kernels.cuh"
 #include "../../chiron_b200/csrc/cb_conv_stack.cuh"
+#include "../../chiron_b200/csrc/cb_gru_simt_kernel.cuh"
 
 namespace {
 
@@ -104,4 +106,22 @@ extern "C" int emu_bn_rank1(const float* x, int B, int t_in, int stride, int t_o
                             const float* scale, const float* offset, float* inv, float* shift) {
     EmuOps ops(sm_count, C);
     return ops.bn_rank1(x, B, t_in, stride, t_out, w, scale, offset, inv, shift);
+}
+
+// The GRU recurrence (cb_gru_simt_kernel.cuh) for both directions of one layer, RG = 1 / 2 / 4 row groups per CTA.
+extern "C" int emu_gru(int rg, int B, int T, int H, const float* pre, int ld_pre, const float* wg_fw, const float* wg_bw,
+                       const float* wc_fw, const float* wc_bw, const int32_t* lens, float* out, int ldo) {
+    GruProblem p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.T = T; p.H = H; p.pre = pre; p.ld_pre = ld_pre; p.wg[0] = wg_fw; p.wg[1] = wg_bw; p.wc[0] = wc_fw; p.wc[1] = wc_bw;
+    p.lens = lens; p.out = out; p.ldo = ldo;
+    if (H > 128 || (H & 3)) return CB_ERR_ARG;
+    const int R = cb_gru::RPT * rg;
+    const size_t smem = cb_gru::gru_smem_bytes(H, rg);
+    const unsigned gx = (B + R - 1) / R;
+    if (rg == 1) emu::launch2d(gx, 2, 128, smem, [&] { cb_gru::gru_simt_kernel<1>(p); });
+    else if (rg == 2) emu::launch2d(gx, 2, 256, smem, [&] { cb_gru::gru_simt_kernel<2>(p); });
+    else if (rg == 4) emu::launch2d(gx, 2, 512, smem, [&] { cb_gru::gru_simt_kernel<4>(p); });
+    else return CB_ERR_ARG;
+    return CB_OK;
 }

@@ -167,3 +167,81 @@ def test_converter_maps_both_bn_variable_sets():
         del mixed[k]
     with pytest.raises(ValueError):
         convert_tensors(mixed, {}, {})
+
+
+def _tf_gru_literal(x, lens, gk, gb, ck, cb, reverse):
+    """rnn_cell_impl.GRUCell.call written literally with torch (concat, one matmul per gate set) inside dynamic_rnn's
+    sequence_length rule -- no hoisting, no kernel splitting (the oracle does both)."""
+    import torch
+    B, T, D = x.shape
+    H = cb.shape[0]
+    xt = torch.from_numpy(np.asarray(x, np.float64))
+    gk, gb, ck, cb = (torch.from_numpy(np.array(a, dtype=np.float64)) for a in (gk, gb, ck, cb))
+    out = torch.zeros(B, T, H, dtype=torch.float64)
+    for b in range(B):
+        n = int(lens[b])
+        seq = xt[b, :n].flip(0) if reverse else xt[b, :n]          # array_ops.reverse_sequence over the first len frames
+        h = torch.zeros(H, dtype=torch.float64)
+        hs = []
+        for t in range(n):
+            value = torch.sigmoid(torch.cat([seq[t], h]) @ gk + gb)
+            r, u = value[:H], value[H:]
+            c = torch.tanh(torch.cat([seq[t], r * h]) @ ck + cb)
+            h = u * h + (1 - u) * c
+            hs.append(h)
+        if n:
+            ys = torch.stack(hs)
+            out[b, :n] = ys.flip(0) if reverse else ys
+    return out.numpy()
+
+
+@pytest.mark.parametrize("reverse", [False, True])
+def test_oracle_gru_matches_literal_tf_formulation(reverse):
+    rng = np.random.default_rng(9)
+    B, T, D, H = 5, 11, 6, 8
+    x = rng.normal(size=(B, T, D)).astype(np.float32)
+    lens = np.array([T, 0, 1, 7, T - 1], dtype=np.int32)
+    gk = rng.uniform(-0.5, 0.5, size=(D + H, 2 * H)).astype(np.float32)
+    gb = (rng.normal(0, 0.1, size=2 * H) + 1).astype(np.float32)
+    ck = rng.uniform(-0.5, 0.5, size=(D + H, H)).astype(np.float32)
+    cb = rng.normal(0, 0.1, size=H).astype(np.float32)
+    ref = _tf_gru_literal(x, lens, gk, gb, ck, cb, reverse)
+    got = O.gru_direction(x, lens, gk, gb, ck, cb, reverse, np.float64)
+    assert np.abs(got - ref).max() < 1e-12
+    assert np.abs(O.gru_direction(x, lens, gk, gb, ck, cb, reverse, np.float32) - ref).max() < 1e-5
+
+
+def test_gru_models_pack_convert_and_run_in_the_oracle():
+    for layout in (M.RNN_NORMAL, M.RNN_RNA):
+        cfg = M.ModelConfig(n_blocks=2, channels=16, hidden=8, n_layers=2, k=[3, 3], stride=[1, 1], rnn_layout=layout,
+                            cell_type=M.CELL_GRU)
+        t = M.random_tensors(cfg, 4)
+        cfg2, t2 = M.unpack_blob(M.pack_blob(cfg, t))
+        assert cfg2 == cfg and cfg2.cell_type == M.CELL_GRU and sorted(t2) == sorted(t)
+        x = _signal(3, 30)
+        lens = np.array([30, 12, 0], dtype=np.int32)
+        lg = O.inference(x, lens, cfg, t)
+        assert lg.shape == (3, 30, 5) and np.isfinite(lg).all()
+        # TF variable names of a GRU checkpoint -> the same blob
+        raw = {}
+        for b in range(cfg.n_blocks):
+            p = "res_layer%d" % (b + 1)
+            for conv in ("branch1/conv1", "branch2/conv2a", "branch2/conv2b", "branch2/conv2c"):
+                w = t["%s/%s/weights" % (p, conv)]
+                raw["%s/%s/weights" % (p, conv)] = w[None] if conv.endswith("conv2b") else w[None, None]
+                for n in ("scale", "offset", "pop_mean", "pop_var"):
+                    if "%s/%s_bn/%s" % (p, conv, n) in t:
+                        raw["%s/%s_bn/%s" % (p, conv, n)] = t["%s/%s_bn/%s" % (p, conv, n)]
+        fmt = ("BDLSTM_rnn/cell_{l}/bidirectional_rnn/{d}/gru_cell/{t}" if layout == M.RNN_NORMAL
+               else "BDGRU_rnn/{d}/multi_rnn_cell/cell_{l}/gru_cell/{t}")
+        for l in range(cfg.n_layers):
+            for d in ("fw", "bw"):
+                for leaf in ("gates/kernel", "gates/bias", "candidate/kernel", "candidate/bias"):
+                    raw[fmt.format(l=l, d=d, t=leaf)] = t["gru/%d/%s/%s" % (l, d, leaf)]
+        for n in ("weights", "bias", "weights_class", "bias_class"):
+            raw["rnn_fnn_layer/" + n] = t["rnn_fnn_layer/" + n]
+        cfg3, t3 = M.unpack_blob(convert_tensors(raw, {}, {"rnn": {"cell_type": "GRU", "layer_num": 2, "hidden_num": 8}}))
+        assert cfg3.cell_type == M.CELL_GRU and cfg3.rnn_layout == layout
+        assert all(np.array_equal(t[n], t3[n]) for n in t)
+        with pytest.raises(ValueError):
+            convert_tensors(raw, {}, {"rnn": {"cell_type": "LSTM"}})

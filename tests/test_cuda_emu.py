@@ -24,7 +24,8 @@ FP = ctypes.POINTER(ctypes.c_float)
 @pytest.fixture(scope="module")
 def emu():
     deps = [SRC, os.path.join(HERE, "cuda_emu", "cuda_emu.h")] + [
-        os.path.join(CSRC, f) for f in ("cb_simt_types.h", "cb_gemm_simt_kernel.cuh", "cb_bn_kernels.cuh", "cb_conv_stack.cuh")]
+        os.path.join(CSRC, f) for f in ("cb_simt_types.h", "cb_gemm_simt_kernel.cuh", "cb_bn_kernels.cuh", "cb_conv_stack.cuh",
+                                        "cb_gru_simt_kernel.cuh")]
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
         subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-Wno-unknown-pragmas",
@@ -33,6 +34,7 @@ def emu():
     lib.emu_conv_stack.restype = ctypes.c_int
     lib.emu_bn_stats.restype = ctypes.c_int
     lib.emu_bn_rank1.restype = ctypes.c_int
+    lib.emu_gru.restype = ctypes.c_int
     return lib
 
 
@@ -164,3 +166,39 @@ def test_conv_stack_population_mode(emu, topo):
     ref = O.cnn_forward(x, cfg, t, np.float64, bn_mode=0)
     assert got.shape == ref.shape
     assert np.abs(got - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("rg,B,T,H", [(1, 5, 9, 8), (2, 37, 6, 20), (4, 70, 5, 12), (1, 3, 4, 100)])
+def test_gru_recurrence_kernel(emu, rg, B, T, H):
+    """gru_simt_kernel (both directions, ragged lengths incl. 0 and T, partial last CTA) against the oracle's GRUCell
+    restatement fed with the same hoisted input projection."""
+    rng = np.random.default_rng(rg * 1000 + B)
+    D = 16
+    x = rng.normal(size=(B, T, D)).astype(np.float32)
+    lens = rng.integers(0, T + 1, size=B).astype(np.int32)
+    lens[0] = T
+    if B > 1:
+        lens[1] = 0
+    w = {}
+    for d in ("fw", "bw"):
+        w[d] = dict(gk=rng.uniform(-0.4, 0.4, size=(D + H, 2 * H)).astype(np.float32),
+                    gb=(rng.normal(0, 0.1, size=2 * H) + 1).astype(np.float32),
+                    ck=rng.uniform(-0.4, 0.4, size=(D + H, H)).astype(np.float32),
+                    cb=rng.normal(0, 0.1, size=H).astype(np.float32))
+    # hoisted projection as the GEMM produces it: per direction r | u | candidate columns, biases folded in
+    pre = np.zeros((B * T, 6 * H), np.float32)
+    xf = x.reshape(B * T, D)
+    for i, d in enumerate(("fw", "bw")):
+        pre[:, i * 3 * H:i * 3 * H + 2 * H] = xf @ w[d]["gk"][:D] + w[d]["gb"]
+        pre[:, i * 3 * H + 2 * H:(i + 1) * 3 * H] = xf @ w[d]["ck"][:D] + w[d]["cb"]
+    out = np.full((B * T, 2 * H), -7.0, np.float32)
+    rec = {d: (np.ascontiguousarray(w[d]["gk"][D:]), np.ascontiguousarray(w[d]["ck"][D:])) for d in w}
+    rc = emu.emu_gru(rg, B, T, H, _fp(pre), 6 * H, _fp(rec["fw"][0]), _fp(rec["bw"][0]), _fp(rec["fw"][1]), _fp(rec["bw"][1]),
+                     lens.ctypes.data_as(ctypes.c_void_p), _fp(out), 2 * H)
+    assert rc == 0
+    ref = np.concatenate([O.gru_direction(x, lens, w[d]["gk"], w[d]["gb"], w[d]["ck"], w[d]["cb"], d == "bw", np.float64)
+                          for d in ("fw", "bw")], axis=2)
+    got = out.reshape(B, T, 2 * H)
+    assert np.abs(got - ref).max() < 2e-5
+    for b in range(B):
+        assert (got[b, lens[b]:] == 0).all()              # dynamic_rnn: zero output past sequence_length
