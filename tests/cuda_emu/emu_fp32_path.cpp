@@ -1,6 +1,7 @@
-// Host build of the fp32 conv-stack path for tests/test_cuda_emu.py -- TEST INFRASTRUCTURE ONLY.
-// Compiles the SAME kernel and orchestration sources the CUDA library is built from
-// (cb_gemm_simt_kernel.cuh, cb_bn_kernels.cuh, cb_conv_stack.cuh) against the host emulation in cuda_emu.h.
+// Host build of the fp32 (SIMT) path for tests/test_cuda_emu.py -- TEST INFRASTRUCTURE ONLY.
+// Compiles the SAME kernel and orchestration sources the CUDA library is built from (cb_gemm_simt_kernel.cuh,
+// cb_bn_kernels.cuh, cb_conv_stack.cuh, cb_lstm_simt_kernel.cuh, cb_gru_simt_kernel.cuh) against the host emulation in
+// cuda_emu.h.
 #define CB_HOST_EMU 1
 #include "cuda_emu.h"
 
@@ -10,6 +11,7 @@
 #include "../../chiron_b200/csrc/cb_bn_kernels.cuh"
 #include "../../chiron_b200/csrc/cb_conv_stack.cuh"
 #include "../../chiron_b200/csrc/cb_gru_simt_kernel.cuh"
+#include "../../chiron_b200/csrc/cb_lstm_simt_kernel.cuh"
 
 namespace {
 
@@ -122,6 +124,24 @@ extern "C" int emu_gru(int rg, int B, int T, int H, const float* pre, int ld_pre
     if (rg == 1) emu::launch2d(gx, 2, 128, smem, [&] { cb_gru::gru_simt_kernel<1>(p); });
     else if (rg == 2) emu::launch2d(gx, 2, 256, smem, [&] { cb_gru::gru_simt_kernel<2>(p); });
     else if (rg == 4) emu::launch2d(gx, 2, 512, smem, [&] { cb_gru::gru_simt_kernel<4>(p); });
+    else return CB_ERR_ARG;
+    return CB_OK;
+}
+
+// The LSTM recurrence (cb_lstm_simt_kernel.cuh) for both directions of one layer.
+extern "C" int emu_lstm(int rg, int B, int T, int H, const float* pre, int ld_pre, const float* whh_fw, const float* whh_bw,
+                        const int32_t* lens, float* out, int ldo) {
+    LstmProblem p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.T = T; p.H = H; p.pre = pre; p.ld_pre = ld_pre; p.whh[0] = whh_fw; p.whh[1] = whh_bw;
+    p.lens = lens; p.out = out; p.ldo = ldo;
+    if (H > 128 || (H & 3)) return CB_ERR_ARG;
+    const int R = cb_lstm::RPT * rg;
+    const size_t smem = cb_lstm::lstm_smem_bytes(H, rg);
+    const unsigned gx = (B + R - 1) / R;
+    if (rg == 1) emu::launch2d(gx, 2, 128, smem, [&] { cb_lstm::lstm_simt_kernel<1>(p); });
+    else if (rg == 2) emu::launch2d(gx, 2, 256, smem, [&] { cb_lstm::lstm_simt_kernel<2>(p); });
+    else if (rg == 4) emu::launch2d(gx, 2, 512, smem, [&] { cb_lstm::lstm_simt_kernel<4>(p); });
     else return CB_ERR_ARG;
     return CB_OK;
 }

@@ -1,6 +1,6 @@
-"""The fp32 conv-stack path compiled for the HOST and run under a thread-per-CUDA-thread emulation (tests/cuda_emu):
-the same kernel sources (cb_gemm_simt_kernel.cuh, cb_bn_kernels.cuh) and the same orchestration (cb_conv_stack.cuh) the
-CUDA library is built from, checked against the oracle without a GPU.  This is what covers the batch-statistics
+"""The fp32 path compiled for the HOST and run under a thread-per-CUDA-thread emulation (tests/cuda_emu): the same kernel
+sources (cb_gemm_simt_kernel.cuh, cb_bn_kernels.cuh, cb_lstm_simt_kernel.cuh, cb_gru_simt_kernel.cuh) and the same
+conv-stack orchestration (cb_conv_stack.cuh) the CUDA library is built from, checked against the oracle without a GPU.  This is what covers the batch-statistics
 BatchNorm kernels and the buffer rotation of both BatchNorm modes on the CPU side; the `-m gpu` tests
 cover the real launches."""
 import ctypes
@@ -14,8 +14,8 @@ from chiron_b200 import model as M
 from oracle import chiron_oracle as O
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "cuda_emu", "emu_conv_stack.cpp")
-LIB = os.path.join(HERE, "cuda_emu", "_build", "libemu_conv_stack.so")
+SRC = os.path.join(HERE, "cuda_emu", "emu_fp32_path.cpp")
+LIB = os.path.join(HERE, "cuda_emu", "_build", "libemu_fp32_path.so")
 CSRC = os.path.join(os.path.dirname(HERE), "chiron_b200", "csrc")
 BN_EPS = np.float32(1e-5)
 FP = ctypes.POINTER(ctypes.c_float)
@@ -25,7 +25,7 @@ FP = ctypes.POINTER(ctypes.c_float)
 def emu():
     deps = [SRC, os.path.join(HERE, "cuda_emu", "cuda_emu.h")] + [
         os.path.join(CSRC, f) for f in ("cb_simt_types.h", "cb_gemm_simt_kernel.cuh", "cb_bn_kernels.cuh", "cb_conv_stack.cuh",
-                                        "cb_gru_simt_kernel.cuh")]
+                                        "cb_gru_simt_kernel.cuh", "cb_lstm_simt_kernel.cuh")]
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
         subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-Wno-unknown-pragmas",
@@ -35,6 +35,7 @@ def emu():
     lib.emu_bn_stats.restype = ctypes.c_int
     lib.emu_bn_rank1.restype = ctypes.c_int
     lib.emu_gru.restype = ctypes.c_int
+    lib.emu_lstm.restype = ctypes.c_int
     return lib
 
 
@@ -202,3 +203,30 @@ def test_gru_recurrence_kernel(emu, rg, B, T, H):
     assert np.abs(got - ref).max() < 2e-5
     for b in range(B):
         assert (got[b, lens[b]:] == 0).all()              # dynamic_rnn: zero output past sequence_length
+
+
+@pytest.mark.parametrize("rg,B,T,H", [(1, 5, 9, 8), (2, 37, 6, 20), (4, 70, 5, 12), (1, 3, 4, 100)])
+def test_lstm_recurrence_kernel(emu, rg, B, T, H):
+    """lstm_simt_kernel (both directions, ragged lengths) against the oracle's LSTMCell fed with the same projection."""
+    rng = np.random.default_rng(rg * 100 + B)
+    D = 16
+    x = rng.normal(size=(B, T, D)).astype(np.float32)
+    lens = rng.integers(0, T + 1, size=B).astype(np.int32)
+    lens[0] = T
+    if B > 1:
+        lens[1] = 0
+    kern = {d: rng.uniform(-0.4, 0.4, size=(D + H, 4 * H)).astype(np.float32) for d in ("fw", "bw")}
+    bias = {d: rng.normal(0, 0.1, size=4 * H).astype(np.float32) for d in ("fw", "bw")}
+    pre = np.zeros((B * T, 8 * H), np.float32)
+    for i, d in enumerate(("fw", "bw")):
+        pre[:, i * 4 * H:(i + 1) * 4 * H] = x.reshape(B * T, D) @ kern[d][:D] + bias[d]
+    out = np.full((B * T, 2 * H), -7.0, np.float32)
+    whh = {d: np.ascontiguousarray(kern[d][D:]) for d in kern}
+    rc = emu.emu_lstm(rg, B, T, H, _fp(pre), 8 * H, _fp(whh["fw"]), _fp(whh["bw"]), lens.ctypes.data_as(ctypes.c_void_p),
+                      _fp(out), 2 * H)
+    assert rc == 0
+    ref = np.concatenate([O.lstm_direction(x, lens, kern[d], bias[d], d == "bw", np.float64) for d in ("fw", "bw")], axis=2)
+    got = out.reshape(B, T, 2 * H)
+    assert np.abs(got - ref).max() < 2e-5
+    for b in range(B):
+        assert (got[b, lens[b]:] == 0).all()
