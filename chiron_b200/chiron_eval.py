@@ -154,7 +154,7 @@ def evaluation(flags=None, caller: Optional[Basecaller] = None) -> Dict[str, dic
     pend_n = 0
     open_reads: List[_ReadState] = []
 
-    def finish(st: _ReadState):
+    def assemble_read(st: _ReadState):
         basecall_time = time.time() - st.start_time
         kernal = get_assembler_kernal(jump, L)
         seq, qual, pos = caller.assemble(st.bases, st.n_bases, st.prob if with_qs else None, jump, L, kernel=kernal,
@@ -164,6 +164,37 @@ def evaluation(flags=None, caller: Optional[Basecaller] = None) -> Dict[str, dic
         # the segment strings are built by the writer thread: this thread's job is to keep the GPU fed
         write_q.put((st.bases, st.n_bases, seq, [st.start_time, st.reading_time, basecall_time, assembly_time], file_pre, qual))
         summary[st.name] = {"windows": st.n, "bases": len(seq), "pos": pos}
+
+    # ---- finisher thread: per-read assembly off the GPU-feeding thread ---------------------------------------------------
+    # cb_assemble_host synchronises its own (default) stream; while the forward kernels of two batches occupy the SMs the
+    # small assembly kernels of a read can wait milliseconds for a slot, and a thread that waited for them could not submit
+    # the next batch.  The assembly staging of a handle is separate from the submit/collect slots, so one finisher thread
+    # may run cb_assemble_host while the main thread runs cb_basecall_submit / cb_basecall_collect (include/chiron_b200.h).
+    # CHIRON_B200_FINISHER=0 assembles on the main thread instead.
+    use_finisher = os.environ.get("CHIRON_B200_FINISHER", "1") != "0"
+    finish_q: "queue.Queue" = queue.Queue()
+    finish_err: List[BaseException] = []
+
+    def finisher():
+        while True:
+            st = finish_q.get()
+            if st is None:
+                return
+            try:
+                if not finish_err:
+                    assemble_read(st)
+            except BaseException as e:            # surfaced after the join below
+                finish_err.append(e)
+
+    finisher_thread = threading.Thread(target=finisher, name="chiron-finisher", daemon=True)
+    if use_finisher:
+        finisher_thread.start()
+
+    def finish(st: _ReadState):
+        if use_finisher:
+            finish_q.put(st)
+        else:
+            assemble_read(st)
 
     # ---- writer threads: formatting and file I/O off the GPU-feeding thread (one file set per read: order-free) ----------
     write_q: "queue.Queue" = queue.Queue()
@@ -254,6 +285,11 @@ def evaluation(flags=None, caller: Optional[Basecaller] = None) -> Dict[str, dic
     while open_reads:                                            # reads with zero windows
         finish(open_reads.pop(0))
     pool.shutdown(wait=True)
+    if use_finisher:
+        finish_q.put(None)
+        finisher_thread.join()
+    if finish_err:
+        write_err.insert(0, finish_err[0])
     for _ in writer_threads:
         write_q.put(None)
     for t in writer_threads:

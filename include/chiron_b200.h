@@ -10,7 +10,10 @@
  * cb_last_error() gives the message of the last failure on the calling thread.  Unless a function says "host",
  * pointers are DEVICE pointers on the handle's GPU and work is enqueued asynchronously on `stream`
  * (a cudaStream_t passed as void*; NULL = the legacy default stream).  One handle per GPU; a handle is not
- * re-entrant (the reference has a single in-flight forward pass: one feeder thread, chiron_eval.py:369-372).
+ * re-entrant (the reference has a single in-flight forward pass: one feeder thread, chiron_eval.py:369-372), with one
+ * exception: cb_assemble_host / cb_assemble keep their own staging and workspace, so ONE other thread may run them while
+ * the forward/decode entry points (cb_forward, cb_decode_*, cb_basecall_*) run on the first -- the reference likewise
+ * assembles on its main thread while the feeder thread keeps the session busy (chiron_eval.py:369-372,446-457).
  */
 #ifndef CHIRON_B200_H
 #define CHIRON_B200_H
