@@ -20,6 +20,31 @@ from .model import (BN_BATCH, BN_POPULATION, CELL_GRU, CELL_LSTM, ModelConfig, N
                     pack_blob)
 
 
+def _take_bn(raw, tensors, bn_modes, p: str, conv: str, required: bool) -> bool:
+    """Collect the BN variables of ``<p>/<conv>``.  Two variable sets exist.  The shipped checkpoints: batchnorm()'s
+    <conv>_bn/{scale,offset,pop_mean,pop_var} (chiron/cnn.py:140-148) -> population mode.  A model trained at HEAD:
+    simple_global_bn's <conv>_bn/<conv>_bn_{scale,offset} (chiron/cnn.py:65-68,181-186) and no statistics -> batch mode.
+    Returns whether the convolution has BN at all."""
+    leaf = conv.rsplit("/", 1)[-1]
+    head_fmt = "%s/%s_bn/%s_bn_%%s" % (p, conv, leaf)
+    has_pop = "%s/%s_bn/scale" % (p, conv) in raw
+    has_head = head_fmt % "scale" in raw
+    if required and not (has_pop or has_head):
+        raise ValueError("%s/%s has no BN variables in the checkpoint" % (p, conv))
+    if has_pop:
+        bn_modes.add(BN_POPULATION)
+        for n in ("scale", "offset", "pop_mean", "pop_var"):
+            tensors["%s/%s_bn/%s" % (p, conv, n)] = raw["%s/%s_bn/%s" % (p, conv, n)]
+    elif has_head:
+        bn_modes.add(BN_BATCH)
+        scale = np.asarray(raw[head_fmt % "scale"], dtype=np.float32).reshape(-1)
+        tensors["%s/%s_bn/scale" % (p, conv)] = scale
+        tensors["%s/%s_bn/offset" % (p, conv)] = np.asarray(raw[head_fmt % "offset"], np.float32).reshape(-1)
+        tensors["%s/%s_bn/pop_mean" % (p, conv)] = np.zeros_like(scale)     # unused in batch mode
+        tensors["%s/%s_bn/pop_var" % (p, conv)] = np.ones_like(scale)
+    return has_pop or has_head
+
+
 def convert_tensors(raw: Dict[str, np.ndarray], conv_attrs: Dict[str, dict], model_json: dict) -> bytes:
     n_blocks = 0
     while "res_layer%d/branch2/conv2b/weights" % (n_blocks + 1) in raw:
@@ -30,6 +55,18 @@ def convert_tensors(raw: Dict[str, np.ndarray], conv_attrs: Dict[str, dict], mod
     k, stride, mask = [], [], 0
     bn_modes = set()
     tensors: Dict[str, np.ndarray] = {}
+    stem_k = stem_stride = 0
+    if "conv_layer/conv1/weights" in raw:                      # RNA_model2 / RNA_model3 stem (chiron/cnn.py:454-476)
+        w = raw["conv_layer/conv1/weights"]                    # (1, k, 1, C) HWIO
+        stem_k = int(w.shape[1])
+        attr = conv_attrs.get("conv_layer/conv1/conv1")
+        if attr and attr["strides"]:
+            stem_stride = int(attr["strides"][2])
+        else:                                                  # no .meta: the two stems HEAD defines
+            stem_stride = {9: 5, 14: 7}.get(stem_k, 0)
+        if stem_stride < 1:
+            raise ValueError("cannot determine the stride of conv_layer/conv1 (no .meta graph)")
+        tensors["conv_layer/conv1/weights"] = w.reshape(stem_k, C)
     for b in range(n_blocks):
         p = "res_layer%d" % (b + 1)
         w2b = raw[p + "/branch2/conv2b/weights"]            # (1, k, C, C) HWIO
@@ -46,29 +83,11 @@ def convert_tensors(raw: Dict[str, np.ndarray], conv_attrs: Dict[str, dict], mod
             w = raw["%s/%s/weights" % (p, conv)]
             tensors["%s/%s/weights" % (p, conv)] = w.reshape(w.shape[1:]) if conv.endswith("conv2b") \
                 else w.reshape(w.shape[2:])
-            # Two variable sets exist.  The shipped checkpoints: batchnorm()'s <conv>_bn/{scale,offset,pop_mean,pop_var}
-            # (chiron/cnn.py:140-148) -> population mode.  A model trained at HEAD: simple_global_bn's
-            # <conv>_bn/<conv>_bn_{scale,offset} (chiron/cnn.py:65-68,181-186) and no statistics -> batch mode.
-            leaf = conv.rsplit("/", 1)[-1]
-            head_fmt = "%s/%s_bn/%s_bn_%%s" % (p, conv, leaf)
-            has_pop = "%s/%s_bn/scale" % (p, conv) in raw
-            has_head = head_fmt % "scale" in raw
-            has_bn = has_pop or has_head
+            has_bn = _take_bn(raw, tensors, bn_modes, p, conv, required=conv != "branch1/conv1")
             if conv == "branch1/conv1":
                 mask |= int(has_bn) << b
-            elif not has_bn:
-                raise ValueError("%s/%s has no BN variables in the checkpoint" % (p, conv))
-            if has_pop:
-                bn_modes.add(BN_POPULATION)
-                for n in ("scale", "offset", "pop_mean", "pop_var"):
-                    tensors["%s/%s_bn/%s" % (p, conv, n)] = raw["%s/%s_bn/%s" % (p, conv, n)]
-            elif has_head:
-                bn_modes.add(BN_BATCH)
-                scale = np.asarray(raw[head_fmt % "scale"], dtype=np.float32).reshape(-1)
-                tensors["%s/%s_bn/scale" % (p, conv)] = scale
-                tensors["%s/%s_bn/offset" % (p, conv)] = np.asarray(raw[head_fmt % "offset"], np.float32).reshape(-1)
-                tensors["%s/%s_bn/pop_mean" % (p, conv)] = np.zeros_like(scale)     # unused in batch mode
-                tensors["%s/%s_bn/pop_var" % (p, conv)] = np.ones_like(scale)
+    if stem_k:
+        _take_bn(raw, tensors, bn_modes, "conv_layer", "conv1", required=True)
     if any(n.startswith("BDLSTM_rnn/") for n in raw):
         layout = RNN_NORMAL
         fmt = "BDLSTM_rnn/cell_{l}/bidirectional_rnn/{d}/lstm_cell/{t}"     # chiron/rnn.py:62-64
@@ -115,7 +134,8 @@ def convert_tensors(raw: Dict[str, np.ndarray], conv_attrs: Dict[str, dict], mod
         raise ValueError("checkpoint mixes population-statistics and batch-statistics BatchNorm variables")
     cfg = ModelConfig(n_blocks=n_blocks, channels=int(C), hidden=int(H), n_layers=n_layers, n_class=int(n_class),
                       rnn_layout=layout, branch1_bn_mask=mask, k=k, stride=stride, sig_norm=sig_norm,
-                      reverse_signal=int(layout == RNN_RNA), bn_mode=bn_modes.pop(), cell_type=cell_type)
+                      reverse_signal=int(layout == RNN_RNA), bn_mode=bn_modes.pop(), cell_type=cell_type,
+                      stem_k=stem_k, stem_stride=stem_stride)
     return pack_blob(cfg, tensors)
 
 

@@ -28,7 +28,7 @@ struct BlobHeader {               // chiron_b200/model.py: "<4s8i8i8i6iq" (packe
     char magic[4];
     int32_t version, n_blocks, channels, hidden, n_layers, n_class, rnn_layout, branch1_bn_mask;
     int32_t k[8], stride[8];
-    int32_t sig_norm, reverse_signal, bn_mode, cell_type, reserved[2];
+    int32_t sig_norm, reverse_signal, bn_mode, cell_type, stem_k, stem_stride;
 };
 constexpr size_t HEADER_BYTES = 4 + 30 * 4 + 8;
 
@@ -45,7 +45,7 @@ struct HostBuilder {              // accumulates the derived fp32 weights; every
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int out_len_of(const CbConfig& c, int L) {
-    int T = L;
+    int T = c.stem_k > 0 ? (L + c.stem_stride - 1) / c.stem_stride : L;
     for (int b = 0; b < c.n_blocks; ++b) T = (T + c.stride[b] - 1) / c.stride[b];
     return T;
 }
@@ -79,6 +79,15 @@ extern "C" int cb_create(const void* blob, size_t nbytes, int device, int precis
     for (int i = 0; i < CB_MAX_BLOCKS; ++i) { c.k[i] = hd.k[i]; c.stride[i] = hd.stride[i]; }
     c.sig_norm = hd.sig_norm; c.reverse_signal = hd.reverse_signal; c.cell_type = hd.cell_type;
     if (c.cell_type != CB_CELL_LSTM && c.cell_type != CB_CELL_GRU) { delete h; cb_set_error("cb_create: unknown RNN cell type %d", c.cell_type); return CB_ERR_BLOB; }
+    c.stem_k = hd.stem_k; c.stem_stride = hd.stem_stride;
+    if (c.stem_k < 0 || c.stem_k > 64 || (c.stem_k > 0) != (c.stem_stride > 0) || c.stem_stride < 0) {
+        delete h; cb_set_error("cb_create: bad stem convolution geometry in blob header"); return CB_ERR_BLOB;
+    }
+    if (c.stem_k > 0 && precision != CB_PREC_FP32) {
+        delete h;
+        cb_set_error("cb_create: models with a stem convolution (RNA_model2/3) run on the CB_PREC_FP32 path only");
+        return CB_ERR_ARG;
+    }
     if (c.cell_type == CB_CELL_GRU && precision != CB_PREC_FP32) {
         delete h;
         cb_set_error("cb_create: GRU cells run on the CB_PREC_FP32 path only (the tensor-core recurrence is an LSTM kernel)");
@@ -106,8 +115,19 @@ extern "C" int cb_create(const void* blob, size_t nbytes, int device, int precis
     size_t o_conv2a[CB_MAX_BLOCKS][2], o_conv2b[CB_MAX_BLOCKS][2], o_convc[CB_MAX_BLOCKS][2];
     size_t o_g[3] = {0, 0, 0}, o_r[3] = {0, 0, 0};
     struct RawOff { size_t W, scale, offset; bool bn; } o_raw[CB_MAX_BLOCKS][4];   // branch1, conv2a, conv2b, conv2c
+    size_t o_stem[5] = {0, 0, 0, 0, 0};
+    if (c.stem_k > 0) {                  // conv_layer/conv1 [k,C] + BN (cnn.py:454-476): raw weights, folded and raw BN vectors
+        const float* ws = take((size_t)c.stem_k * C);
+        Bn bns = take_bn();
+        o_stem[0] = hb.add(std::vector<float>(ws, ws + (size_t)c.stem_k * C));
+        o_stem[1] = hb.add(bns.inv);
+        o_stem[2] = hb.add(bns.shift);
+        o_stem[3] = hb.add(std::vector<float>(bns.scale, bns.scale + C));
+        o_stem[4] = hb.add(std::vector<float>(bns.offset, bns.offset + C));
+    }
     for (int b = 0; b < c.n_blocks; ++b) {
-        const int cin = b == 0 ? 1 : C;
+        const bool rank1 = b == 0 && c.stem_k == 0;       // block 1 reads the one-channel signal itself
+        const int cin = rank1 ? 1 : C;
         const float* w1 = take((size_t)cin * C);
         Bn bn1; bool has_bn1 = (c.branch1_bn_mask >> b) & 1;
         if (has_bn1) bn1 = take_bn();
@@ -117,7 +137,7 @@ extern "C" int cb_create(const void* blob, size_t nbytes, int device, int precis
         Bn bnb = take_bn();
         const float* w2c = take((size_t)C * C);
         Bn bnc = take_bn();
-        if (b == 0) {
+        if (rank1) {
             o_g[0] = hb.add(std::vector<float>(w2a, w2a + C));
             o_g[1] = hb.add(bna.inv);
             o_g[2] = hb.add(bna.shift);
@@ -140,11 +160,11 @@ extern "C" int cb_create(const void* blob, size_t nbytes, int device, int precis
             o_conv2b[b][1] = hb.add(bnb.shift);
         }
         {   // conv2c (+BN) and, for blocks >= 2, the 1x1 branch1 conv stacked along K (cnn.py:258-261)
-            const int kc = b == 0 ? C : 2 * C;
+            const int kc = rank1 ? C : 2 * C;
             std::vector<float> f((size_t)kc * C), sh(bnc.shift);
             for (int k = 0; k < C; ++k)
                 for (int n = 0; n < C; ++n) f[(size_t)k * C + n] = w2c[(size_t)k * C + n] * bnc.inv[n];
-            if (b > 0) {
+            if (!rank1) {
                 for (int k = 0; k < C; ++k)
                     for (int n = 0; n < C; ++n)
                         f[(size_t)(C + k) * C + n] = w1[(size_t)k * C + n] * (has_bn1 ? bn1.inv[n] : 1.0f);
@@ -250,6 +270,7 @@ extern "C" int cb_create(const void* blob, size_t nbytes, int device, int precis
         }
     }
     h->zeros = base + o_zeros;
+    if (c.stem_k > 0) h->stem = CbStem{base + o_stem[0], base + o_stem[1], base + o_stem[2], base + o_stem[3], base + o_stem[4]};
     for (int l = 0; l < c.n_layers; ++l) {
         for (int d = 0; d < 2; ++d) {
             h->wx[l][d] = base + o_wx[l][d]; h->whh[l][d] = base + o_whh[l][d]; h->bias[l][d] = base + o_b[l][d];
@@ -410,6 +431,12 @@ struct CudaConvOps {
     int bn_stats(const float* X, long long M, const float* scale, const float* offset, float* inv, float* shift) {
         return cb_launch_bn_stats(h, X, M, scale, offset, inv, shift, s);
     }
+    int stem(const StemProblem& p) {
+        const int pi = cb_prof_begin(h, CB_CAT_CONV, s);
+        const int rc = cb_launch_stem(h, p, s);
+        cb_prof_end(h, pi, s);
+        return rc;
+    }
     int bn_apply(const BnApplyArgs& a) { return cb_launch_bn_apply(h, a, s); }
 };
 }  // namespace
@@ -448,10 +475,10 @@ extern "C" int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_o
         for (int i = 0; i < CB_BN_VECS; ++i) bufs.vec[i] = h->bn_vec ? h->bn_vec + (size_t)i * C : nullptr;
         bufs.zeros = h->zeros;
         if (h->bn_mode == CB_BN_BATCH)
-            rc = cb_conv_stack_batch_bn(ops, c, h->raw1, h->raw2a, h->raw2b, h->raw2c, bufs, x, B, L, &X, &t_in);
+            rc = cb_conv_stack_batch_bn(ops, c, h->raw1, h->raw2a, h->raw2b, h->raw2c, &h->stem, bufs, x, B, L, &X, &t_in);
         else
             rc = cb_conv_stack_folded(ops, c, h->conv2a, h->conv2b, h->convc, h->g_w, h->g_inv, h->g_sh, h->r_w, h->r_inv,
-                                      h->r_sh, bufs, x, B, L, &X, &t_in);
+                                      h->r_sh, &h->stem, bufs, x, B, L, &X, &t_in);
         if (rc != CB_OK) return rc;
     }
     const int T = t_in;

@@ -64,6 +64,7 @@ struct cb_handle {
     int bn_mode;
     CbRawConv raw1[CB_MAX_BLOCKS], raw2a[CB_MAX_BLOCKS], raw2b[CB_MAX_BLOCKS], raw2c[CB_MAX_BLOCKS];
     const float* zeros;                   // [max(C, 8H)] zero shift vector
+    CbStem stem;                          // stem convolution (cfg.stem_k > 0)
     double* bn_part;                      // [CB_BN_MAX_PART][2][C] partial sums
     float* bn_vec;                        // [CB_BN_VECS][C]
     const float *g_w, *g_inv, *g_sh;  // block-1 conv2a rank-1 generator
@@ -107,6 +108,7 @@ struct cb_handle {
 int cb_launch_gemm_simt(cb_handle* h, const GemmProblem& p, cudaStream_t s);
 int cb_launch_lstm_simt(cb_handle* h, const LstmProblem& p, cudaStream_t s);
 int cb_launch_gru_simt(cb_handle* h, const GruProblem& p, cudaStream_t s);
+int cb_launch_stem(cb_handle* h, const StemProblem& p, cudaStream_t s);
 int cb_launch_bn_rank1(cb_handle* h, const float* x, int B, int t_in, int stride, int t_out, const float* w,
                        const float* scale, const float* offset, float* inv, float* shift, cudaStream_t s);
 int cb_launch_bn_stats(cb_handle* h, const float* X, long long M, const float* scale, const float* offset, float* inv,

@@ -15,6 +15,7 @@ struct CbConfig {
     int k[CB_MAX_BLOCKS], stride[CB_MAX_BLOCKS];
     int sig_norm, reverse_signal;
     int cell_type;            // 0 LSTMCell, 1 GRUCell
+    int stem_k, stem_stride;  // 0, 0 = none; else a strided 1 x stem_k conv + BN + ReLU of the raw signal before block 1
 };
 
 // ---- one dense contraction  out[M,N] = act(A_gather[M,K] @ W[K,N] + shift[N] (+ rank-1 residual)) -----------------
@@ -75,6 +76,17 @@ struct GruProblem {
     float* out; int ldo;      // as LstmProblem
     int layer;
 };
+
+// ---- stem convolution of the raw signal (RNA_model2 / RNA_model3, chiron/cnn.py:454-476; cb_stem_kernel.cuh) -----------------
+// out[(b*t_out + to)*C + c] = act((sum_j x[b*t_in + to*stride + j - left] * w[j*C + c]) * inv[c] + shift[c]), 'SAME' padding.
+struct StemProblem {
+    const float* x; int B, t_in, t_out, k, stride, left, C;
+    const float* w;                     // [k][C]
+    const float *inv, *shift;           // nullptr: raw convolution output (batch-statistics BN normalises it afterwards)
+    int relu;
+    float* out;
+};
+struct CbStem { const float *w, *inv, *shift, *scale, *offset; };   // inv/shift: population BN folded; scale/offset: raw
 
 // ---- weights of the residual blocks --------------------------------------------------------------------------------------
 struct CbConvW { const float *W, *shift; };                 // population BN folded: W[K,N] * inv[n], shift[N]

@@ -13,11 +13,14 @@ the blob header.  Blob layout (little endian):
     int32    sig_norm (0 none, 1 unique-median/MAD, 2 full-signal median/MAD), reverse_signal,
              bn_mode (0 = population statistics, the shipped checkpoints' tf.cond BN, chiron/cnn.py:125-163;
              1 = batch statistics, HEAD's simple_global_bn, chiron/cnn.py:166-188),
-             cell_type (0 = LSTMCell, 1 = GRUCell; chiron/rnn.py:47-53,126-131), reserved[2]
+             cell_type (0 = LSTMCell, 1 = GRUCell; chiron/rnn.py:47-53,126-131),
+             stem_k, stem_stride (0, 0 = no stem; otherwise the strided 1 x stem_k convolution + BN + ReLU of the raw
+             signal in front of the residual blocks: RNA_model2 = 9 / 5, RNA_model3 = 14 / 7, chiron/cnn.py:454-476)
     int64    n_floats
     float32  weights[n_floats]       in the canonical order of ``tensor_specs``
 
-Canonical tensor order: for every block ``branch1/conv1`` W[cin,C] (+bn), ``conv2a`` W[cin,C] +bn, ``conv2b``
+Canonical tensor order: with a stem, ``conv_layer/conv1`` W[stem_k,C] + bn first (and block 1 then reads C channels
+instead of the one-channel signal); for every block ``branch1/conv1`` W[cin,C] (+bn), ``conv2a`` W[cin,C] +bn, ``conv2b``
 W[k,C,C] +bn, ``conv2c`` W[C,C] +bn, where bn = scale, offset, pop_mean, pop_var (each [C]); then for every LSTM layer
 and direction (fw, bw) kernel[in+H,4H] and bias[4H] (TF LSTMCell layout, gate column order i,j,f,o) -- or, for GRU cells,
 gates/kernel[in+H,2H], gates/bias[2H] (columns r,u), candidate/kernel[in+H,H], candidate/bias[H] (TF GRUCell) --; then the head
@@ -57,16 +60,18 @@ class ModelConfig:
     reverse_signal: int = 0
     bn_mode: int = BN_POPULATION
     cell_type: int = CELL_LSTM
+    stem_k: int = 0
+    stem_stride: int = 0
 
     def total_stride(self) -> int:
-        s = 1
+        s = self.stem_stride if self.stem_k else 1
         for v in self.stride[: self.n_blocks]:
             s *= v
         return s
 
     def out_len(self, L: int) -> int:
         """CNN output length for an L-sample window (TF 'SAME': ceil(T/stride) per strided conv)."""
-        T = L
+        T = -(-L // self.stem_stride) if self.stem_k else L
         for b in range(self.n_blocks):
             T = -(-T // self.stride[b])
         return T
@@ -85,8 +90,11 @@ def tensor_specs(cfg: ModelConfig) -> List[Tuple[str, Tuple[int, ...]]]:
         for n in ("scale", "offset", "pop_mean", "pop_var"):
             specs.append(("%s_bn/%s" % (prefix, n), (C,)))
 
+    if cfg.stem_k:
+        specs.append(("conv_layer/conv1/weights", (cfg.stem_k, C)))
+        bn("conv_layer/conv1")
     for b in range(cfg.n_blocks):
-        cin = 1 if b == 0 else C
+        cin = 1 if (b == 0 and not cfg.stem_k) else C
         p = "res_layer%d" % (b + 1)
         specs.append((p + "/branch1/conv1/weights", (cin, C)))
         if cfg.branch1_bn_mask >> b & 1:
@@ -126,7 +134,7 @@ def pack_blob(cfg: ModelConfig, tensors: Dict[str, np.ndarray]) -> bytes:
     s = list(cfg.stride) + [0] * (MAX_BLOCKS - len(cfg.stride))
     head = _HEADER.pack(MAGIC, 1, cfg.n_blocks, cfg.channels, cfg.hidden, cfg.n_layers, cfg.n_class, cfg.rnn_layout,
                         cfg.branch1_bn_mask, *k[:MAX_BLOCKS], *s[:MAX_BLOCKS], cfg.sig_norm, cfg.reverse_signal,
-                        cfg.bn_mode, cfg.cell_type, 0, 0, flat.size)
+                        cfg.bn_mode, cfg.cell_type, cfg.stem_k, cfg.stem_stride, flat.size)
     return head + flat.tobytes()
 
 
@@ -137,10 +145,10 @@ def unpack_blob(blob: bytes) -> Tuple[ModelConfig, Dict[str, np.ndarray]]:
     n_blocks, channels, hidden, n_layers, n_class, rnn_layout, mask = vals[2:9]
     k = list(vals[9:17])[:n_blocks]
     s = list(vals[17:25])[:n_blocks]
-    sig_norm, reverse_signal, bn_mode, cell_type = vals[25], vals[26], vals[27], vals[28]
+    sig_norm, reverse_signal, bn_mode, cell_type, stem_k, stem_stride = vals[25:31]
     n_floats = vals[31]
     cfg = ModelConfig(n_blocks, channels, hidden, n_layers, n_class, rnn_layout, mask, k, s, sig_norm, reverse_signal,
-                      bn_mode, cell_type)
+                      bn_mode, cell_type, stem_k, stem_stride)
     flat = np.frombuffer(blob, dtype="<f4", count=n_floats, offset=_HEADER.size)
     tensors: Dict[str, np.ndarray] = {}
     pos = 0
@@ -184,7 +192,8 @@ def random_tensors(cfg: ModelConfig, seed: int = 0) -> Dict[str, np.ndarray]:
             v = rng.normal(0.0, 8.0 * np.sqrt(2.0 / cfg.hidden), size=shape)    # logits of a trained model's magnitude
         else:                                   # convolution weights [.., fan_in, C]
             fan_in = int(np.prod(shape[:-1]))
-            v = rng.normal(0.0, np.sqrt(2.0 / (fan_in + shape[-1])) * (3.0 if fan_in == 1 else 1.4), size=shape)
+            from_signal = fan_in == 1 or name.startswith("conv_layer/")        # reads the raw one-channel signal
+            v = rng.normal(0.0, np.sqrt(2.0 / (fan_in + shape[-1])) * (3.0 if from_signal else 1.4), size=shape)
         out[name] = v.astype(np.float32)
     return out
 

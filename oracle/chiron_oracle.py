@@ -118,6 +118,9 @@ def cnn_forward(x: np.ndarray, cfg, t: Dict[str, np.ndarray], dtype=np.float32, 
     if bn_mode is None:
         bn_mode = getattr(cfg, "bn_mode", 0)
     net = np.asarray(x, dtype=dtype)[:, :, None]
+    if getattr(cfg, "stem_k", 0):        # RNA_model2 / RNA_model3 (chiron/cnn.py:454-476): conv_layer [1,k,1,C], stride, BN, ReLU
+        w = t["conv_layer/conv1/weights"].astype(dtype)[:, None, :]
+        net = np.maximum(_bn(_conv_same(net, w, cfg.stem_stride), t, "conv_layer/conv1", dtype, bn_mode, stats_out), 0)
     for b in range(cfg.n_blocks):
         p = "res_layer%d" % (b + 1)
         s = cfg.stride[b]

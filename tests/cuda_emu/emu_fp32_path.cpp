@@ -9,6 +9,7 @@
 #include "../../chiron_b200/csrc/cb_simt_types.h"
 #include "../../chiron_b200/csrc/cb_gemm_simt_kernel.cuh"
 #include "../../chiron_b200/csrc/cb_bn_kernels.cuh"
+#include "../../chiron_b200/csrc/cb_stem_kernel.cuh"
 #include "../../chiron_b200/csrc/cb_conv_stack.cuh"
 #include "../../chiron_b200/csrc/cb_gru_simt_kernel.cuh"
 #include "../../chiron_b200/csrc/cb_lstm_simt_kernel.cuh"
@@ -47,6 +48,13 @@ struct EmuOps {          // mirrors the launchers of cb_gemm_simt.cu / cb_bn.cu:
         });
         return CB_OK;
     }
+    int stem(const StemProblem& p) {
+        if (p.B <= 0 || p.t_out <= 0) return CB_OK;
+        if ((p.C & 3) || p.k < 1 || p.stride < 1) return CB_ERR_ARG;
+        const int grid = cb_stem::stem_grid(sm_count, (long long)p.B * p.t_out * (p.C >> 2));
+        emu::launch(grid, cb_stem::STEM_THREADS, [&] { cb_stem::stem_conv_kernel(p); });
+        return CB_OK;
+    }
     int bn_apply(const BnApplyArgs& a) {
         if (a.M <= 0) return CB_OK;
         const cb_bn::BnApply p = cb_bn::bn_apply_params(a, C);
@@ -58,17 +66,23 @@ struct EmuOps {          // mirrors the launchers of cb_gemm_simt.cu / cb_bn.cu:
 
 }  // namespace
 
-// geom: n_blocks, channels, branch1_bn_mask, k[8], stride[8].
+// geom: n_blocks, channels, branch1_bn_mask, k[8], stride[8], stem_k, stem_stride.
+// stem[0..4] = W[k,C], folded inv, folded shift, scale, offset of the stem convolution (stem_k > 0).
 // bn_mode CB_BN_BATCH:      w[(b*4 + i)*3 + {0,1,2}] = W, scale, offset of block b's conv i (branch1, conv2a, conv2b, conv2c).
 // bn_mode CB_BN_POPULATION: w[(b*3 + i)*2 + {0,1}] = folded W, shift of conv2a / conv2b / conv2c(++branch1);
 //                           rank1[0..5] = g_w, g_inv, g_sh, r_w, r_inv, r_sh of block 1.
 // out[B*T*C] receives the stack's output; returns T (>0) or a negative CB_ERR_* code.
-extern "C" int emu_conv_stack(int bn_mode, const int* geom, const float* const* w, const float* const* rank1, const float* x,
-                              int B, int L, int sm_count, float* out, long long* launches) {
+extern "C" int emu_conv_stack(int bn_mode, const int* geom, const float* const* w, const float* const* rank1,
+                              const float* const* stem, const float* x, int B, int L, int sm_count, float* out,
+                              long long* launches) {
     CbConfig c;
     memset(&c, 0, sizeof(c));
     c.n_blocks = geom[0]; c.channels = geom[1]; c.branch1_bn_mask = geom[2];
     for (int i = 0; i < CB_MAX_BLOCKS; ++i) { c.k[i] = geom[3 + i]; c.stride[i] = geom[3 + CB_MAX_BLOCKS + i]; }
+    c.stem_k = geom[3 + 2 * CB_MAX_BLOCKS]; c.stem_stride = geom[4 + 2 * CB_MAX_BLOCKS];
+    CbStem st;
+    memset(&st, 0, sizeof(st));
+    if (c.stem_k > 0) st = CbStem{stem[0], stem[1], stem[2], stem[3], stem[4]};
     const int C = c.channels;
     std::vector<float> act[3], vec((size_t)CB_BN_VECS * C), zeros((size_t)C, 0.f);
     CbConvStackBufs bufs;
@@ -83,13 +97,13 @@ extern "C" int emu_conv_stack(int bn_mode, const int* geom, const float* const* 
         CbRawConv raw[4][CB_MAX_BLOCKS];
         for (int b = 0; b < c.n_blocks; ++b)
             for (int i = 0; i < 4; ++i) raw[i][b] = CbRawConv{w[(b * 4 + i) * 3], w[(b * 4 + i) * 3 + 1], w[(b * 4 + i) * 3 + 2]};
-        rc = cb_conv_stack_batch_bn(ops, c, raw[0], raw[1], raw[2], raw[3], bufs, x, B, L, &feat, &T);
+        rc = cb_conv_stack_batch_bn(ops, c, raw[0], raw[1], raw[2], raw[3], &st, bufs, x, B, L, &feat, &T);
     } else {
         CbConvW cw[3][CB_MAX_BLOCKS];
         for (int b = 0; b < c.n_blocks; ++b)
             for (int i = 0; i < 3; ++i) cw[i][b] = CbConvW{w[(b * 3 + i) * 2], w[(b * 3 + i) * 2 + 1]};
         rc = cb_conv_stack_folded(ops, c, cw[0], cw[1], cw[2], rank1[0], rank1[1], rank1[2], rank1[3], rank1[4], rank1[5],
-                                  bufs, x, B, L, &feat, &T);
+                                  &st, bufs, x, B, L, &feat, &T);
     }
     if (rc != CB_OK) return rc;
     memcpy(out, feat, sizeof(float) * (size_t)B * T * C);

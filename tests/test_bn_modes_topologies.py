@@ -34,6 +34,8 @@ def _torch_cnn(x, cfg, t, bn_mode):
         return F.batch_norm(inp, g("pop_mean"), g("pop_var"), g("scale"), g("offset"), training=False, eps=1e-5)
 
     net = torch.from_numpy(np.asarray(x, dtype=np.float64))[:, None, :]
+    if cfg.stem_k:
+        net = torch.relu(bn(conv(net, t["conv_layer/conv1/weights"][:, None, :], cfg.stem_stride), "conv_layer/conv1"))
     for b in range(cfg.n_blocks):
         p = "res_layer%d" % (b + 1)
         s = cfg.stride[b]
@@ -77,11 +79,14 @@ def test_oracle_cnn_matches_torch_on_rna_default(rna_model, bn_mode):
     assert np.abs(got - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
 
 
-@pytest.mark.parametrize("k,stride,mask", [([3] * 5, [1] * 5, 1),            # rna_test (cnn.py:555-566)
-                                           ([5, 3, 7, 3], [2, 1, 3, 1], 0b0101),
-                                           ([1, 2], [1, 2], 0b11)])
-def test_oracle_cnn_matches_torch_on_other_topologies(k, stride, mask):
-    cfg = M.ModelConfig(n_blocks=len(k), channels=32, hidden=12, k=k, stride=stride, branch1_bn_mask=mask)
+@pytest.mark.parametrize("k,stride,mask,stem", [([3] * 5, [1] * 5, 1, (0, 0)),            # rna_test (cnn.py:555-566)
+                                                ([5, 3, 7, 3], [2, 1, 3, 1], 0b0101, (0, 0)),
+                                                ([1, 2], [1, 2], 0b11, (0, 0)),
+                                                ([3] * 3, [1] * 3, 1, (9, 5)),             # RNA_model2 (cnn.py:454-464)
+                                                ([3] * 3, [1] * 3, 1, (14, 7))])           # RNA_model3 (cnn.py:466-476)
+def test_oracle_cnn_matches_torch_on_other_topologies(k, stride, mask, stem):
+    cfg = M.ModelConfig(n_blocks=len(k), channels=32, hidden=12, k=k, stride=stride, branch1_bn_mask=mask,
+                        stem_k=stem[0], stem_stride=stem[1])
     t = M.random_tensors(cfg, seed=3)
     x = _signal(4, 77, seed=2)
     for bn_mode in (0, 1):
@@ -122,11 +127,17 @@ def _tf_checkpoint_names(cfg, t, head_literal):
     """The variable set tf.train.Saver would hold for this model: batchnorm()'s names (the shipped checkpoints,
     chiron/cnn.py:140-148) or simple_global_bn's (a model trained at HEAD, chiron/cnn.py:65-68,181-186)."""
     raw = {}
-    for b in range(cfg.n_blocks):
-        p = "res_layer%d" % (b + 1)
-        for conv in ("branch1/conv1", "branch2/conv2a", "branch2/conv2b", "branch2/conv2c"):
+    convs = [("res_layer%d" % (b + 1), conv) for b in range(cfg.n_blocks)
+             for conv in ("branch1/conv1", "branch2/conv2a", "branch2/conv2b", "branch2/conv2c")]
+    if cfg.stem_k:
+        convs.insert(0, ("conv_layer", "conv1"))
+    for p, conv in convs:
+        if True:
             w = t["%s/%s/weights" % (p, conv)]
-            raw["%s/%s/weights" % (p, conv)] = w[None] if conv.endswith("conv2b") else w[None, None]
+            if p == "conv_layer":
+                raw["%s/%s/weights" % (p, conv)] = w[None, :, None, :]           # (1, k, 1, C) HWIO
+            else:
+                raw["%s/%s/weights" % (p, conv)] = w[None] if conv.endswith("conv2b") else w[None, None]
             if "%s/%s_bn/scale" % (p, conv) not in t:
                 continue
             leaf = conv.rsplit("/", 1)[-1]
@@ -245,3 +256,23 @@ def test_gru_models_pack_convert_and_run_in_the_oracle():
         assert all(np.array_equal(t[n], t3[n]) for n in t)
         with pytest.raises(ValueError):
             convert_tensors(raw, {}, {"rnn": {"cell_type": "LSTM"}})
+
+
+@pytest.mark.parametrize("head_literal", [False, True])
+def test_converter_recognises_the_stem_convolution(head_literal):
+    """RNA_model2 / RNA_model3 checkpoints (chiron/cnn.py:454-476): conv_layer/conv1 in front of the residual blocks."""
+    cfg = M.ModelConfig(n_blocks=3, channels=16, hidden=8, k=[3] * 3, stride=[1] * 3, branch1_bn_mask=1, stem_k=14,
+                        stem_stride=7)
+    t = M.random_tensors(cfg, 6)
+    assert t["res_layer1/branch1/conv1/weights"].shape == (16, 16)        # block 1 reads C channels behind a stem
+    raw = _tf_checkpoint_names(cfg, t, head_literal)
+    attrs = {"conv_layer/conv1/conv1": {"strides": [1, 1, 7, 1]}}
+    for a in (attrs, {}):                                                 # with the .meta attrs, and from the kernel width alone
+        cfg2, t2 = M.unpack_blob(convert_tensors(raw, a, {}))
+        assert (cfg2.stem_k, cfg2.stem_stride, cfg2.n_blocks) == (14, 7, 3)
+        assert cfg2.bn_mode == (M.BN_BATCH if head_literal else M.BN_POPULATION)
+        assert np.array_equal(t2["conv_layer/conv1/weights"], t["conv_layer/conv1/weights"])
+        assert cfg2.out_len(2000) == 286 and cfg2.total_stride() == 7
+    x = _signal(3, 75)
+    want = O.cnn_forward(x, cfg, t, bn_mode=int(head_literal))
+    assert np.array_equal(O.cnn_forward(x, cfg2, t2), want) and want.shape == (3, 11, 16)

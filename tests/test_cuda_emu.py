@@ -25,7 +25,7 @@ FP = ctypes.POINTER(ctypes.c_float)
 def emu():
     deps = [SRC, os.path.join(HERE, "cuda_emu", "cuda_emu.h")] + [
         os.path.join(CSRC, f) for f in ("cb_simt_types.h", "cb_gemm_simt_kernel.cuh", "cb_bn_kernels.cuh", "cb_conv_stack.cuh",
-                                        "cb_gru_simt_kernel.cuh", "cb_lstm_simt_kernel.cuh")]
+                                        "cb_gru_simt_kernel.cuh", "cb_lstm_simt_kernel.cuh", "cb_stem_kernel.cuh")]
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
         subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-Wno-unknown-pragmas",
@@ -85,18 +85,27 @@ def test_rank1_statistics_kernels(emu, B, t_in, stride, sms):
 def _geom(cfg):
     k = list(cfg.k) + [0] * (8 - len(cfg.k))
     s = list(cfg.stride) + [0] * (8 - len(cfg.stride))
-    return (ctypes.c_int * 19)(cfg.n_blocks, cfg.channels, cfg.branch1_bn_mask, *k[:8], *s[:8])
+    return (ctypes.c_int * 21)(cfg.n_blocks, cfg.channels, cfg.branch1_bn_mask, *k[:8], *s[:8], cfg.stem_k, cfg.stem_stride)
 
 
-def _run_stack(emu, bn_mode, cfg, ptr_arrays, rank1, x, sms):
+def _stem_arrays(cfg, t):
+    if not cfg.stem_k:
+        return []
+    inv, sh = _fold(t, "conv_layer/conv1")
+    return [t["conv_layer/conv1/weights"], inv, sh, t["conv_layer/conv1_bn/scale"], t["conv_layer/conv1_bn/offset"]]
+
+
+def _run_stack(emu, bn_mode, cfg, ptr_arrays, rank1, x, sms, stem=()):
     B, L = x.shape
     keep = [np.ascontiguousarray(a, dtype=np.float32) if a is not None else None for a in ptr_arrays]
     tab = (FP * len(keep))(*[_fp(a) for a in keep])
     r_keep = [np.ascontiguousarray(a, dtype=np.float32) for a in rank1]
     r_tab = (FP * max(len(r_keep), 1))(*[_fp(a) for a in r_keep])
+    s_keep = [np.ascontiguousarray(a, dtype=np.float32) for a in stem]
+    s_tab = (FP * max(len(s_keep), 1))(*[_fp(a) for a in s_keep])
     out = np.zeros(B * L * cfg.channels, np.float32)
     n_launch = ctypes.c_longlong(0)
-    T = emu.emu_conv_stack(bn_mode, _geom(cfg), tab, r_tab, _fp(np.ascontiguousarray(x)), B, L, sms, _fp(out),
+    T = emu.emu_conv_stack(bn_mode, _geom(cfg), tab, r_tab, s_tab, _fp(np.ascontiguousarray(x)), B, L, sms, _fp(out),
                            ctypes.byref(n_launch))
     assert T > 0, "emu_conv_stack failed (%d)" % T
     return out[:B * T * cfg.channels].reshape(B, T, cfg.channels), n_launch.value
@@ -110,7 +119,9 @@ def _fold(t, prefix):                                  # cb_create: population B
 TOPOLOGIES = [dict(n_blocks=3, channels=8, k=[3, 3, 3], stride=[1, 1, 1], branch1_bn_mask=1),            # DNA_default shape
               dict(n_blocks=3, channels=20, k=[13, 3, 3], stride=[5, 1, 1], branch1_bn_mask=1),         # RNA_default shape
               dict(n_blocks=4, channels=12, k=[5, 3, 7, 2], stride=[2, 1, 3, 1], branch1_bn_mask=0b0110),
-              dict(n_blocks=5, channels=8, k=[3] * 5, stride=[1] * 5, branch1_bn_mask=1)]             # rna_test
+              dict(n_blocks=5, channels=8, k=[3] * 5, stride=[1] * 5, branch1_bn_mask=1),             # rna_test
+              dict(n_blocks=3, channels=8, k=[3] * 3, stride=[1] * 3, branch1_bn_mask=1, stem_k=9, stem_stride=5),    # RNA_model2
+              dict(n_blocks=2, channels=12, k=[3] * 2, stride=[1, 2], branch1_bn_mask=1, stem_k=14, stem_stride=7)]   # RNA_model3-like
 
 
 def _inputs(cfg, seed):
@@ -134,7 +145,7 @@ def test_conv_stack_batch_statistics_mode(emu, topo, sms):
             has_bn = (p + "/" + conv + "_bn/scale") in t
             ptrs += [t[p + "/" + conv + "/weights"], t[p + "/" + conv + "_bn/scale"] if has_bn else None,
                      t[p + "/" + conv + "_bn/offset"] if has_bn else None]
-    got, n_launch = _run_stack(emu, 1, cfg, ptrs, [], x, sms)
+    got, n_launch = _run_stack(emu, 1, cfg, ptrs, [], x, sms, _stem_arrays(cfg, t))
     ref = O.cnn_forward(x, cfg, t, np.float64, bn_mode=1)
     assert got.shape == ref.shape
     assert np.abs(got - ref).max() < 2e-4 * max(1.0, np.abs(ref).max())
@@ -157,13 +168,15 @@ def test_conv_stack_population_mode(emu, topo):
         invc, shc = _fold(t, p + "/branch2/conv2c")
         w1, w2a = t[p + "/branch1/conv1/weights"], t[p + "/branch2/conv2a/weights"]
         w2b, w2c = t[p + "/branch2/conv2b/weights"], t[p + "/branch2/conv2c/weights"]
-        if b == 0:
+        if b == 0 and not cfg.stem_k:
             rank1 = [w2a.reshape(-1), inva, sha, w1.reshape(-1), inv1, sh1]
             ptrs += [np.zeros(4, np.float32), np.zeros(4, np.float32)]                      # conv2a of block 1 is generated
             ptrs += [w2b.reshape(-1, C) * invb, shb, w2c * invc, shc]
         else:
             ptrs += [w2a * inva, sha, w2b.reshape(-1, C) * invb, shb, np.concatenate([w2c * invc, w1 * inv1]), shc + sh1]
-    got, _ = _run_stack(emu, 0, cfg, ptrs, rank1, x, 1)
+    if not rank1:
+        rank1 = [np.zeros(4, np.float32)] * 6
+    got, _ = _run_stack(emu, 0, cfg, ptrs, rank1, x, 1, _stem_arrays(cfg, t))
     ref = O.cnn_forward(x, cfg, t, np.float64, bn_mode=0)
     assert got.shape == ref.shape
     assert np.abs(got - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())

@@ -1,4 +1,4 @@
-"""GPU parity of GRU-cell models (model.json "cell_type": "GRU", chiron/rnn.py:51-53,129-131) through the
+"""GPU parity of GRU-cell models and stem-convolution models (model.json "cell_type": "GRU", chiron/rnn.py:51-53,129-131) through the
 C ABI against the CPU oracle, on random-init weights -- no GRU checkpoint ships with the reference, so this is "parity
 unpinned" against the reference; the oracle's GRUCell is pinned to a literal restatement of TF's cell in
 test_bn_modes_topologies.py and the kernel source to the oracle under host emulation in test_cuda_emu.py."""
@@ -47,4 +47,40 @@ def test_gru_model_matches_oracle_fp32(tmp_path, layout):
             assert bases[b, :n_bases[b]].tolist() == ref_paths[b]
     bc.close()
     with pytest.raises(_lib.ChironB200Error):       # the tensor-core recurrence is an LSTM kernel: refused loudly
+        Basecaller(path, device=0, precision="tc")
+
+
+@pytest.mark.parametrize("bn_mode", ["population", "batch"])
+def test_stem_convolution_model_matches_oracle_fp32(tmp_path, bn_mode):
+    """RNA_model3-shaped model (chiron/cnn.py:466-476): 1x14 stride-7 stem conv + BN + ReLU, then three residual blocks that
+    all read 256 channels; random-init weights, fp32 path, both BatchNorm modes."""
+    from chiron_b200 import _lib
+    from chiron_b200.engine import Basecaller
+    cfg = M.ModelConfig(n_blocks=3, channels=256, hidden=100, n_layers=3, k=[3, 3, 3], stride=[1, 1, 1], branch1_bn_mask=1,
+                        rnn_layout=M.RNN_RNA, stem_k=14, stem_stride=7)
+    t = M.random_tensors(cfg, seed=17)
+    path = os.path.join(str(tmp_path), "rna_model3.cbw")
+    with open(path, "wb") as f:
+        f.write(M.pack_blob(cfg, t))
+    rng = np.random.default_rng(9)
+    B, L = 20, 500
+    x = rng.normal(0.15, 0.9, size=(B, L)).astype(np.float32)
+    lens = rng.integers(1, L + 1, size=B).astype(np.int32)
+    lens[:2] = (L, 3)
+    for b in range(B):
+        x[b, lens[b]:] = 0
+    T = cfg.out_len(L)
+    assert T == 72
+    lens_o = O.seq_len_out(lens, L / T)
+    mode = M.BN_BATCH if bn_mode == "batch" else M.BN_POPULATION
+    ref_fea = O.cnn_forward(x, cfg, t, np.float64, bn_mode=mode)
+    ref = O.inference(x, lens_o, cfg, t, np.float64, bn_mode=mode)
+    bc = Basecaller(path, device=0, precision="fp32", bn_mode=bn_mode)
+    assert bc.out_len(L) == T and bc.out_len(2000) == 286
+    bases, n_bases, prob, logits = bc.basecall_batch(x, lens, beam=0, want_logits=True)
+    fea = bc.debug_fetch(0, ref_fea.size).reshape(ref_fea.shape)
+    assert np.abs(fea - ref_fea).max() < 1e-3 * max(1.0, np.abs(ref_fea).max())
+    assert np.abs(logits - ref).max() < (1e-2 if bn_mode == "batch" else 2e-3)
+    bc.close()
+    with pytest.raises(_lib.ChironB200Error):       # the tensor-core conv stack has no stem: refused loudly
         Basecaller(path, device=0, precision="tc")
