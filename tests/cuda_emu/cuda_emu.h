@@ -100,14 +100,52 @@ static inline int atomicMax(int* addr, int v) {
 
 static inline void __syncthreads() { emu::ctx->block_bar->arrive_and_wait(); }
 
-// All lanes of the calling warp take part (the kernels only shuffle warp-uniformly).
-static inline double __shfl_down_sync(unsigned, double v, int delta) {
-    emu::BlockCtx* c = emu::ctx;
-    const unsigned t = emu::t_idx.x, w = t / 32, lane = t % 32;
-    const unsigned lanes = std::min(32u, c->n_threads - 32 * w);
-    (*c->shfl)[w][lane] = v;
-    (*c->warp_bar)[w]->arrive_and_wait();
-    const double r = lane + (unsigned)delta < lanes ? (*c->shfl)[w][lane + delta] : v;
-    (*c->warp_bar)[w]->arrive_and_wait();
+// Warp collectives: all live lanes of the calling warp take part (the kernels only call them warp-uniformly).  A value is
+// published in the warp's exchange buffer between two warp barriers.
+namespace emu {
+struct WarpPos { BlockCtx* c; unsigned w, lane, lanes; };
+inline WarpPos warp_pos() {
+    BlockCtx* c = ctx;
+    const unsigned t = t_idx.x, w = t / 32;
+    return WarpPos{c, w, t % 32, std::min(32u, c->n_threads - 32 * w)};
+}
+template <class T, class Pick>
+inline T exchange(T v, Pick pick) {           // pick(lane, lanes) -> source lane, or -1 to keep the own value
+    static_assert(sizeof(T) <= sizeof(double), "exchange slot is 8 bytes");
+    const WarpPos p = warp_pos();
+    std::memcpy(&(*p.c->shfl)[p.w][p.lane], &v, sizeof(T));
+    (*p.c->warp_bar)[p.w]->arrive_and_wait();
+    const int src = pick((int)p.lane, (int)p.lanes);
+    T r = v;
+    if (src >= 0 && src < (int)p.lanes) std::memcpy(&r, &(*p.c->shfl)[p.w][src], sizeof(T));
+    (*p.c->warp_bar)[p.w]->arrive_and_wait();
     return r;
 }
+}  // namespace emu
+
+template <class T>
+static inline T __shfl_down_sync(unsigned, T v, int delta) {
+    return emu::exchange(v, [delta](int lane, int lanes) { return lane + delta < lanes ? lane + delta : -1; });
+}
+template <class T>
+static inline T __shfl_up_sync(unsigned, T v, int delta) {
+    return emu::exchange(v, [delta](int lane, int) { return lane - delta >= 0 ? lane - delta : -1; });
+}
+template <class T>
+static inline T __shfl_xor_sync(unsigned, T v, int mask) {
+    return emu::exchange(v, [mask](int lane, int lanes) { return (lane ^ mask) < lanes ? (lane ^ mask) : -1; });
+}
+template <class T>
+static inline T __shfl_sync(unsigned, T v, int src) {
+    return emu::exchange(v, [src](int, int) { return src & 31; });
+}
+static inline unsigned __ballot_sync(unsigned, bool pred) {
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l) {
+        const int bit = emu::exchange((int)pred, [l](int, int) { return l; });
+        const emu::WarpPos p = emu::warp_pos();
+        if (l < (int)p.lanes && bit) m |= 1u << l;
+    }
+    return m;
+}
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }

@@ -13,6 +13,7 @@
 #include "../../chiron_b200/csrc/cb_conv_stack.cuh"
 #include "../../chiron_b200/csrc/cb_gru_simt_kernel.cuh"
 #include "../../chiron_b200/csrc/cb_lstm_simt_kernel.cuh"
+#include "../../chiron_b200/csrc/cb_head_decode_kernels.cuh"
 
 namespace {
 
@@ -157,5 +158,30 @@ extern "C" int emu_lstm(int rg, int B, int T, int H, const float* pre, int ld_pr
     else if (rg == 2) emu::launch2d(gx, 2, 256, smem, [&] { cb_lstm::lstm_simt_kernel<2>(p); });
     else if (rg == 4) emu::launch2d(gx, 2, 512, smem, [&] { cb_lstm::lstm_simt_kernel<4>(p); });
     else return CB_ERR_ARG;
+    return CB_OK;
+}
+
+// Logit head (row-major and time-major forms), path_prob, seq_len scaling and greedy CTC (cb_head_decode_kernels.cuh), with
+// the grids of their launchers in cb_head_decode.cu.
+extern "C" int emu_head(const float* lasth, long long M, int H, int C, const float* w, const float* bias, const float* wc,
+                        const float* bc, float* logits, int blocks) {
+    emu::launch(blocks, 256, [&] { cb_hd::head_kernel(lasth, M, H, C, w, bias, wc, bc, logits); });
+    return CB_OK;
+}
+extern "C" int emu_head_tmajor(const float* lasth, int B, int Bp, int T, int H, int C, const float* w, const float* bias,
+                               const float* wc, const float* bc, float* logits) {
+    emu::launch2d((B + 127) / 128, T, 128, 0, [&] { cb_hd::head_tmajor_kernel(lasth, B, Bp, T, H, C, w, bias, wc, bc, logits); });
+    return CB_OK;
+}
+extern "C" int emu_path_prob(const float* logits, int B, int T, int C, float* prob) {
+    emu::launch((B + 3) / 4, 128, [&] { cb_hd::path_prob_kernel(logits, B, T, C, prob); });
+    return CB_OK;
+}
+extern "C" int emu_seq_len(const int32_t* in, int B, int L, int T, int32_t* out) {
+    emu::launch((B + 255) / 256, 256, [&] { cb_hd::seq_len_kernel(in, B, L, T, out); });
+    return CB_OK;
+}
+extern "C" int emu_greedy(const float* logits, const int32_t* lens, int B, int T, int C, int8_t* bases, int32_t* n_bases) {
+    emu::launch((B + 3) / 4, 128, [&] { cb_hd::greedy_kernel(logits, lens, B, T, C, bases, n_bases); });
     return CB_OK;
 }

@@ -125,32 +125,37 @@ def test_blob_header_carries_bn_mode():
 
 def _tf_checkpoint_names(cfg, t, head_literal):
     """The variable set tf.train.Saver would hold for this model: batchnorm()'s names (the shipped checkpoints,
-    chiron/cnn.py:140-148) or simple_global_bn's (a model trained at HEAD, chiron/cnn.py:65-68,181-186)."""
+    chiron/cnn.py:140-148) or simple_global_bn's (a model trained at HEAD, chiron/cnn.py:65-68,181-186); LSTM or GRU
+    cells in either RNN layout; with or without the stem convolution."""
     raw = {}
     convs = [("res_layer%d" % (b + 1), conv) for b in range(cfg.n_blocks)
              for conv in ("branch1/conv1", "branch2/conv2a", "branch2/conv2b", "branch2/conv2c")]
     if cfg.stem_k:
         convs.insert(0, ("conv_layer", "conv1"))
     for p, conv in convs:
-        if True:
-            w = t["%s/%s/weights" % (p, conv)]
-            if p == "conv_layer":
-                raw["%s/%s/weights" % (p, conv)] = w[None, :, None, :]           # (1, k, 1, C) HWIO
-            else:
-                raw["%s/%s/weights" % (p, conv)] = w[None] if conv.endswith("conv2b") else w[None, None]
-            if "%s/%s_bn/scale" % (p, conv) not in t:
-                continue
-            leaf = conv.rsplit("/", 1)[-1]
-            if head_literal:
-                raw["%s/%s_bn/%s_bn_scale" % (p, conv, leaf)] = t["%s/%s_bn/scale" % (p, conv)]
-                raw["%s/%s_bn/%s_bn_offset" % (p, conv, leaf)] = t["%s/%s_bn/offset" % (p, conv)]
-            else:
-                for n in ("scale", "offset", "pop_mean", "pop_var"):
-                    raw["%s/%s_bn/%s" % (p, conv, n)] = t["%s/%s_bn/%s" % (p, conv, n)]
+        w = t["%s/%s/weights" % (p, conv)]
+        if p == "conv_layer":
+            raw["%s/%s/weights" % (p, conv)] = w[None, :, None, :]               # (1, k, 1, C) HWIO
+        else:
+            raw["%s/%s/weights" % (p, conv)] = w[None] if conv.endswith("conv2b") else w[None, None]
+        if "%s/%s_bn/scale" % (p, conv) not in t:
+            continue
+        leaf = conv.rsplit("/", 1)[-1]
+        if head_literal:
+            raw["%s/%s_bn/%s_bn_scale" % (p, conv, leaf)] = t["%s/%s_bn/scale" % (p, conv)]
+            raw["%s/%s_bn/%s_bn_offset" % (p, conv, leaf)] = t["%s/%s_bn/offset" % (p, conv)]
+        else:
+            for n in ("scale", "offset", "pop_mean", "pop_var"):
+                raw["%s/%s_bn/%s" % (p, conv, n)] = t["%s/%s_bn/%s" % (p, conv, n)]
+    gru = cfg.cell_type == M.CELL_GRU
+    cell = "gru_cell" if gru else "lstm_cell"
+    fmt = ("BDLSTM_rnn/cell_{l}/bidirectional_rnn/{d}/%s/{t}" if cfg.rnn_layout == M.RNN_NORMAL
+           else "BDGRU_rnn/{d}/multi_rnn_cell/cell_{l}/%s/{t}") % cell
+    leaves = ("gates/kernel", "gates/bias", "candidate/kernel", "candidate/bias") if gru else ("kernel", "bias")
     for l in range(cfg.n_layers):
         for d in ("fw", "bw"):
-            for leaf in ("kernel", "bias"):
-                raw["BDLSTM_rnn/cell_%d/bidirectional_rnn/%s/lstm_cell/%s" % (l, d, leaf)] = t["lstm/%d/%s/%s" % (l, d, leaf)]
+            for leaf in leaves:
+                raw[fmt.format(l=l, d=d, t=leaf)] = t["%s/%d/%s/%s" % ("gru" if gru else "lstm", l, d, leaf)]
     for n in ("weights", "bias", "weights_class", "bias_class"):
         raw["rnn_fnn_layer/" + n] = t["rnn_fnn_layer/" + n]
     return raw
@@ -233,24 +238,7 @@ def test_gru_models_pack_convert_and_run_in_the_oracle():
         lens = np.array([30, 12, 0], dtype=np.int32)
         lg = O.inference(x, lens, cfg, t)
         assert lg.shape == (3, 30, 5) and np.isfinite(lg).all()
-        # TF variable names of a GRU checkpoint -> the same blob
-        raw = {}
-        for b in range(cfg.n_blocks):
-            p = "res_layer%d" % (b + 1)
-            for conv in ("branch1/conv1", "branch2/conv2a", "branch2/conv2b", "branch2/conv2c"):
-                w = t["%s/%s/weights" % (p, conv)]
-                raw["%s/%s/weights" % (p, conv)] = w[None] if conv.endswith("conv2b") else w[None, None]
-                for n in ("scale", "offset", "pop_mean", "pop_var"):
-                    if "%s/%s_bn/%s" % (p, conv, n) in t:
-                        raw["%s/%s_bn/%s" % (p, conv, n)] = t["%s/%s_bn/%s" % (p, conv, n)]
-        fmt = ("BDLSTM_rnn/cell_{l}/bidirectional_rnn/{d}/gru_cell/{t}" if layout == M.RNN_NORMAL
-               else "BDGRU_rnn/{d}/multi_rnn_cell/cell_{l}/gru_cell/{t}")
-        for l in range(cfg.n_layers):
-            for d in ("fw", "bw"):
-                for leaf in ("gates/kernel", "gates/bias", "candidate/kernel", "candidate/bias"):
-                    raw[fmt.format(l=l, d=d, t=leaf)] = t["gru/%d/%s/%s" % (l, d, leaf)]
-        for n in ("weights", "bias", "weights_class", "bias_class"):
-            raw["rnn_fnn_layer/" + n] = t["rnn_fnn_layer/" + n]
+        raw = _tf_checkpoint_names(cfg, t, False)          # TF variable names of a GRU checkpoint -> the same blob
         cfg3, t3 = M.unpack_blob(convert_tensors(raw, {}, {"rnn": {"cell_type": "GRU", "layer_num": 2, "hidden_num": 8}}))
         assert cfg3.cell_type == M.CELL_GRU and cfg3.rnn_layout == layout
         assert all(np.array_equal(t[n], t3[n]) for n in t)

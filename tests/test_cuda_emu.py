@@ -25,7 +25,8 @@ FP = ctypes.POINTER(ctypes.c_float)
 def emu():
     deps = [SRC, os.path.join(HERE, "cuda_emu", "cuda_emu.h")] + [
         os.path.join(CSRC, f) for f in ("cb_simt_types.h", "cb_gemm_simt_kernel.cuh", "cb_bn_kernels.cuh", "cb_conv_stack.cuh",
-                                        "cb_gru_simt_kernel.cuh", "cb_lstm_simt_kernel.cuh", "cb_stem_kernel.cuh")]
+                                        "cb_gru_simt_kernel.cuh", "cb_lstm_simt_kernel.cuh", "cb_stem_kernel.cuh",
+                                        "cb_head_decode_kernels.cuh")]
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
         subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-Wno-unknown-pragmas",
@@ -243,3 +244,46 @@ def test_lstm_recurrence_kernel(emu, rg, B, T, H):
     assert np.abs(got - ref).max() < 2e-5
     for b in range(B):
         assert (got[b, lens[b]:] == 0).all()
+
+
+def test_head_path_prob_seq_len_and_greedy_kernels(emu, dna_model):
+    """cb_head_decode_kernels.cuh: both layouts of the logit head, path_prob (warp shuffle reduction), seq_len scaling
+    (round half to even in f64) and the greedy CTC decoder (shuffle / ballot / popc stream compaction, exact ties: first
+    maximum wins) against the oracle."""
+    cfg, t, _ = dna_model
+    H, C = cfg.hidden, cfg.n_class
+    rng = np.random.default_rng(12)
+    B, T = 37, 45
+    lasth = rng.normal(size=(B, T, 2 * H)).astype(np.float32)
+    ref = O.head_forward(lasth, cfg, t)
+    w = [np.ascontiguousarray(t["rnn_fnn_layer/" + n], dtype=np.float32) for n in ("weights", "bias", "weights_class", "bias_class")]
+    got = np.zeros((B, T, C), np.float32)
+    assert emu.emu_head(_fp(lasth), ctypes.c_longlong(B * T), H, C, _fp(w[0]), _fp(w[1]), _fp(w[2]), _fp(w[3]), _fp(got), 3) == 0
+    assert np.abs(got - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())
+    # time-major layout of the tensor-core LSTM stack: [T][2 x H/4][Bp][4]
+    Bp = 128
+    tm = np.zeros((T, 2 * (H // 4), Bp, 4), np.float32)
+    tm[:, :, :B, :] = lasth.reshape(B, T, 2 * (H // 4), 4).transpose(1, 2, 0, 3)
+    got_tm = np.zeros((B, T, C), np.float32)
+    assert emu.emu_head_tmajor(_fp(tm), B, Bp, T, H, C, _fp(w[0]), _fp(w[1]), _fp(w[2]), _fp(w[3]), _fp(got_tm)) == 0
+    assert np.abs(got_tm - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())
+    # decoder inputs with exact ties
+    lg = rng.normal(size=(B, T, C)).astype(np.float32)
+    lg[:, :, C - 1] += 1.5
+    lg[:, ::5, :] = np.round(lg[:, ::5, :])
+    prob = np.zeros(B, np.float32)
+    assert emu.emu_path_prob(_fp(lg), B, T, C, _fp(prob)) == 0
+    np.testing.assert_allclose(prob, O.path_prob(lg), rtol=0, atol=2e-6)
+    lens = rng.integers(0, T + 1, size=B).astype(np.int32)
+    lens[0], lens[1] = T, 0
+    bases = np.full((B, T), 9, np.int8)
+    n_bases = np.zeros(B, np.int32)
+    assert emu.emu_greedy(_fp(lg), lens.ctypes.data_as(ctypes.c_void_p), B, T, C, bases.ctypes.data_as(ctypes.c_void_p),
+                          n_bases.ctypes.data_as(ctypes.c_void_p)) == 0
+    assert [bases[b, :n_bases[b]].tolist() for b in range(B)] == O.ctc_greedy(lg, lens)
+    assert all((bases[b, n_bases[b]:] == 0).all() for b in range(B))
+    for L, Tq in ((400, 400), (500, 100), (503, 101), (2000, 286)):
+        raw = np.concatenate([np.arange(0, L + 1, 7), [L, 1, L - 1, 5 * (L // 10)]]).astype(np.int32)
+        out = np.zeros_like(raw)
+        assert emu.emu_seq_len(raw.ctypes.data_as(ctypes.c_void_p), len(raw), L, Tq, out.ctypes.data_as(ctypes.c_void_p)) == 0
+        assert np.array_equal(out, O.seq_len_out(raw, L / Tq))
