@@ -1,384 +1,15 @@
-// CTC beam search and overlap assembly on the GPU (latency/branch-bound integer work; see cb_seq_algos.cuh for the
-// algorithms and the reference code they restate).
-//
-//  beam_warp_kernel one warp per window walks TF's trie beam search cooperatively over shared memory (bit-identical to the
-//                   sequential routine cb_beam_decode_one); the product path.
-//  beam_kernel      one thread per window runs cb_beam_decode_one over a global workspace: the overflow fallback (and
-//                   the reference the cooperative kernel is tested against).
-//  assembly         asm_compact (drop empty windows like sparse2dense, chiron_eval.py:56-66) -> asm_disp (one thread per
-//                   adjacent window pair: stick / glue / difflib-exact simple displacement) -> asm_scan (prefix sum ->
-//                   window coordinates, read length) -> asm_vote (count matrix [4,len] + quality sums, atomics) ->
-//                   asm_finish (argmax + phred+33 string, chiron_eval.py:152-174,457).
+// Launchers of the CTC beam search and overlap assembly kernels (cb_seq_kernels.cuh; algorithms in cb_seq_algos.cuh), and the
+// host-compiled self-test hooks of the sequential routines.
 #include "cb_internal.cuh"
-#include "cb_seq_algos.cuh"
+#include "cb_seq_kernels.cuh"
 #include "../../include/chiron_b200_selftest.h"
 
 #include <stdlib.h>
 #include <string.h>
 
+using namespace cb_seq;
+
 namespace {
-
-inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-// ---- beam search -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) beam_kernel(const float* __restrict__ logits, const int32_t* __restrict__ lens,
-                                                  int B, int T, int C, int W, int pool, char* __restrict__ work,
-                                                  size_t work_stride, int8_t* __restrict__ bases,
-                                                  int32_t* __restrict__ n_bases, int* __restrict__ overflow) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    int len = lens[b];
-    len = len < 0 ? 0 : (len > T ? T : len);
-    CbBeamWork k = cb_beam_work_carve(work + (size_t)b * work_stride, W, pool);
-    int8_t* dst = bases + (size_t)b * T;
-    int n = cb_beam_decode_one(logits + (size_t)b * T * C, len, C, W, k, dst);
-    if (n < 0) { atomicExch(overflow, 1); n = 0; }
-    for (int i = n; i < T; ++i) dst[i] = 0;
-    n_bases[b] = n;
-}
-
-// One WARP per window, workspace and the window's logits in SHARED memory.  The search is a serial, branchy walk: with 32
-// windows per warp (beam_kernel) the lanes serialise each other's divergent paths and every trie / slot access is an
-// uncoalesced global load.  Here a warp runs cb_beam_decode_one's frame loop COOPERATIVELY with bit-identical results:
-//   * the stable descending sort of the leaves is a rank computation (rank = #greater + #equal-before), the per-branch
-//     copies and the probability updates (two log-sum-exp per branch -- the transcendental bulk of a frame) are
-//     independent per branch and go one branch per lane, the bottom-of-beam search is a warp reduction;
-//   * the extension loop (branch x child, order-dependent: evictions move the threshold) stays on lane 0, but only for the
-//     candidates a parallel pre-filter cannot rule out.  Within a frame a branch's oldp only ever drops to -inf, the
-//     threshold only rises once the beam is full and the beam only fills up, so "passes with the state at the start of
-//     the chunk" is a superset of "passes when reached"; candidates whose child is one of this frame's branches are always
-//     kept (TF's deactivate-child reset).  Lane 0 re-evaluates every kept candidate with the current state, exactly like
-//     the sequential code; chunks are aligned to branches so a branch's entry test is made once.
-// The node pool is small (compacted often); if it ever overflows the launcher falls back to beam_kernel.
-constexpr int BEAM_WARPS = 4;
-
-__device__ int beam_decode_warp(const float* __restrict__ lg, int len, int C, int W, CbBeamWork k, int8_t* out, int lane) {
-    const unsigned FULL = 0xffffffffu;
-    const int blank = C - 1, n_child = C - 1;
-    int n_nodes = 1, n_leaves = 1, n_free = 0, err = 0;
-    if (lane == 0) {
-        k.nodes[0].parent = -1; k.nodes[0].label = -1; k.nodes[0].slot = 0; k.nodes[0].bidx = 0; k.nodes[0].bframe = -1;
-        for (int c = 0; c < CB_BEAM_MAX_CHILD; ++c) k.nodes[0].child[c] = -1;
-        k.slot_node[0] = 0;
-        k.ot[0] = k.ob[0] = -INFINITY;
-        k.nt[0] = 0.f; k.nb[0] = 0.f; k.nl[0] = -INFINITY;
-        k.leaves[0] = 0;
-        for (int s = W - 1; s >= 1; --s) k.freel[n_free++] = s;            // pop order 1,2,3,...
-    }
-    n_free = __shfl_sync(FULL, n_free, 0);
-    __syncwarp();
-    const int bpc = 32 / n_child;                        // branches per chunk of the extension loop
-    float inp[8];
-    for (int t = 0; t < len; ++t) {
-        const float* row = lg + (size_t)t * C;
-        float mx = row[0];
-        for (int c = 1; c < C; ++c) if (row[c] > mx) mx = row[c];
-        for (int c = 0; c < C; ++c) inp[c] = row[c] - mx;
-        const int nb = n_leaves;
-        // leaves_.Extract(): descending newp.total, stable  ==  rank of every leaf
-        for (int i = lane; i < nb; i += 32) {
-            const int v = k.leaves[i];
-            const float key = k.nt[v];
-            int rank = 0;
-            for (int j = 0; j < nb; ++j) {
-                const float o = k.nt[k.leaves[j]];
-                rank += (o > key) || (o == key && j < i);
-            }
-            k.branches[rank] = v;
-        }
-        __syncwarp();
-        for (int i = lane; i < nb; i += 32) {
-            const int s = k.branches[i];
-            k.ot[s] = k.nt[s]; k.ob[s] = k.nb[s];
-            k.bnode[i] = k.slot_node[s]; k.bo_total[i] = k.nt[s]; k.bo_blank[i] = k.nb[s];
-            k.nodes[k.slot_node[s]].bidx = i; k.nodes[k.slot_node[s]].bframe = t;
-        }
-        __syncwarp();
-        for (int i = lane; i < nb; i += 32) {
-            const int s = k.branches[i];
-            const CbBeamNode& nd = k.nodes[k.slot_node[s]];
-            float nl = k.nl[s];
-            if (nd.parent >= 0) {
-                const CbBeamNode& pa = k.nodes[nd.parent];
-                if (pa.slot >= 0) {
-                    const float prev = (nd.label == pa.label) ? k.ob[pa.slot] : k.ot[pa.slot];
-                    nl = cb_lse(nl, prev);
-                }
-                nl += inp[nd.label];
-            }
-            const float nbv = k.ot[s] + inp[blank];
-            k.nl[s] = nl; k.nb[s] = nbv;
-            k.nt[s] = cb_lse(nbv, nl);
-            k.leaves[i] = s;
-        }
-        __syncwarp();
-        n_leaves = nb;
-        // bottom = first minimum in push order
-        float bot_val = INFINITY; int bot = 0x7fffffff;
-        for (int i = lane; i < n_leaves; i += 32) {
-            const float v = k.nt[k.leaves[i]];
-            if (v < bot_val || bot == 0x7fffffff) { bot_val = v; bot = i; }     // strided scan keeps the lowest index per value
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const float ov = __shfl_xor_sync(FULL, bot_val, off);
-            const int oi = __shfl_xor_sync(FULL, bot, off);
-            if (oi != 0x7fffffff && (bot == 0x7fffffff || ov < bot_val || (ov == bot_val && oi < bot))) { bot_val = ov; bot = oi; }
-        }
-        // extension loop, chunks of bpc whole branches
-        for (int ib = 0; ib < nb; ib += bpc) {
-            bool flag = false;
-            {
-                const int i = ib + lane / n_child, c = lane % n_child;
-                if (lane < bpc * n_child && i < nb) {
-                    const float tot = k.bo_total[i];
-                    if (tot > -INFINITY && (n_leaves < W || tot > bot_val)) {
-                        const int bn = k.bnode[i];
-                        const int ch = k.nodes[bn].child[c];
-                        const float prev = (c == k.nodes[bn].label) ? k.bo_blank[i] : tot;
-                        const float lab = inp[c] + prev;
-                        flag = (lab > -INFINITY && (n_leaves < W || lab > bot_val)) || (ch >= 0 && k.nodes[ch].bframe == t);
-                    }
-                }
-            }
-            unsigned mask = __ballot_sync(FULL, flag);
-            if (lane == 0 && mask && !err) {
-                int cur_i = -1; bool cur_pass = false; float tot = 0.f;
-                while (mask) {
-                    const int bit = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const int i = ib + bit / n_child, c = bit % n_child;
-                    if (i != cur_i) {                      // the branch's entry test, with the state of this moment
-                        cur_i = i;
-                        tot = k.bo_total[i];
-                        cur_pass = tot > -INFINITY && (n_leaves < W || tot > bot_val);
-                    }
-                    if (!cur_pass) continue;
-                    const int bn = k.bnode[i];
-                    const int ch = k.nodes[bn].child[c];
-                    if (ch >= 0 && k.nodes[ch].slot >= 0) continue;           // already an active beam
-                    const float prev = (c == k.nodes[bn].label) ? k.bo_blank[i] : tot;
-                    const float lab = inp[c] + prev;
-                    if (!(lab > -INFINITY && (n_leaves < W || lab > bot_val))) {
-                        if (ch >= 0 && k.nodes[ch].bframe == t) {
-                            k.bo_total[k.nodes[ch].bidx] = -INFINITY; k.bo_blank[k.nodes[ch].bidx] = -INFINITY;
-                        }
-                        continue;
-                    }
-                    if (n_leaves == W) {                                       // evict the bottom beam
-                        const int bs = k.leaves[bot];
-                        k.nodes[k.slot_node[bs]].slot = -1;
-                        for (int q = bot; q + 1 < n_leaves; ++q) k.leaves[q] = k.leaves[q + 1];
-                        --n_leaves;
-                        k.freel[n_free++] = bs;
-                    }
-                    int node = ch;
-                    if (node < 0) {
-                        if (n_nodes == k.pool) {
-                            n_nodes = cb_beam_compact(k, n_nodes, n_leaves, nb, n_child);
-                            if (n_nodes == k.pool) { err = 1; break; }
-                        }
-                        node = n_nodes++;
-                        CbBeamNode& nn = k.nodes[node];
-                        nn.parent = k.bnode[i]; nn.label = c; nn.slot = -1; nn.bidx = 0; nn.bframe = -1;
-                        for (int q = 0; q < CB_BEAM_MAX_CHILD; ++q) nn.child[q] = -1;
-                        k.nodes[k.bnode[i]].child[c] = node;
-                    }
-                    const int s = k.freel[--n_free];
-                    k.slot_node[s] = node;
-                    k.nodes[node].slot = s;
-                    k.nb[s] = -INFINITY; k.nl[s] = lab; k.nt[s] = lab;
-                    k.ot[s] = k.ob[s] = -INFINITY;
-                    k.leaves[n_leaves++] = s;
-                    bot = 0;
-                    for (int q = 1; q < n_leaves; ++q) if (k.nt[k.leaves[q]] < k.nt[k.leaves[bot]]) bot = q;
-                    bot_val = k.nt[k.leaves[bot]];
-                }
-            }
-            __syncwarp();
-            n_leaves = __shfl_sync(FULL, n_leaves, 0); n_free = __shfl_sync(FULL, n_free, 0);
-            n_nodes = __shfl_sync(FULL, n_nodes, 0); bot = __shfl_sync(FULL, bot, 0);
-            bot_val = __shfl_sync(FULL, bot_val, 0); err = __shfl_sync(FULL, err, 0);
-        }
-        if (err) return -2;
-    }
-    int n = 0;
-    if (lane == 0) {
-        int best = 0;
-        for (int i = 1; i < n_leaves; ++i) if (k.nt[k.leaves[i]] > k.nt[k.leaves[best]]) best = i;
-        for (int cur = k.slot_node[k.leaves[best]]; k.nodes[cur].parent >= 0; cur = k.nodes[cur].parent) ++n;
-        int i = n - 1;
-        for (int cur = k.slot_node[k.leaves[best]]; k.nodes[cur].parent >= 0; cur = k.nodes[cur].parent)
-            out[i--] = (int8_t)k.nodes[cur].label;
-    }
-    return __shfl_sync(FULL, n, 0);
-}
-
-__global__ void __launch_bounds__(BEAM_WARPS * 32) beam_warp_kernel(const float* __restrict__ logits, const int32_t* __restrict__ lens,
-                                                                    int B, int T, int C, int W, int pool, int stride,
-                                                                    int8_t* __restrict__ bases, int32_t* __restrict__ n_bases,
-                                                                    int* __restrict__ overflow) {
-    extern __shared__ __align__(16) char beam_sm[];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * BEAM_WARPS + w;
-    if (b >= B) return;
-    char* base = beam_sm + (size_t)w * stride;
-    float* lg = reinterpret_cast<float*>(base);
-    int len = lens[b];
-    len = len < 0 ? 0 : (len > T ? T : len);
-    const float* src = logits + (size_t)b * T * C;
-    for (int i = lane; i < len * C; i += 32) lg[i] = src[i];
-    __syncwarp();
-    int8_t* dst = bases + (size_t)b * T;
-    CbBeamWork k = cb_beam_work_carve(base + (((size_t)T * C * 4 + 15) & ~(size_t)15), W, pool);
-    int n = beam_decode_warp(lg, len, C, W, k, dst, lane);
-    if (n < 0) { if (lane == 0) atomicExch(overflow, 1); n = 0; }
-    __syncwarp();
-    for (int i = n + lane; i < T; i += 32) dst[i] = 0;
-    if (lane == 0) n_bases[b] = n;
-}
-
-// ---- assembly ----------------------------------------------------------------------------------------------------
-struct AsmWork {
-    int* list;       // [n_windows] indices of non-empty windows, in order
-    int* n_ne;       // [1]
-    int* disp;       // [n_windows] displacement of list[j] against list[j-1]; later the running position
-    int* length;     // [1] consensus length before clamping to max_len
-    int* counts;     // [4][max_len]
-    double* qsum;    // [4][max_len]
-    double* logfact; // [T+2]
-    int* scratch;    // [n_windows][scratch_stride]
-    size_t scratch_stride;
-};
-
-__global__ void __launch_bounds__(1024) asm_compact_kernel(const int32_t* __restrict__ n_bases, int n_windows, int T,
-                                                           AsmWork w, int32_t* __restrict__ pos) {
-    // single block: ordered compaction of the non-empty windows + the log-factorial table
-    __shared__ int warp_tot[32];
-    __shared__ int base;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) base = 0;
-    __syncthreads();
-    for (int start = 0; start < n_windows; start += blockDim.x) {
-        const int i = start + tid;
-        const int keep = (i < n_windows && n_bases[i] > 0) ? 1 : 0;
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) warp_tot[wid] = __popc(m);
-        __syncthreads();
-        int off = base;
-        for (int q = 0; q < wid; ++q) off += warp_tot[q];
-        if (keep) w.list[off + __popc(m & ((1u << lane) - 1u))] = i;
-        if (i < n_windows && !keep) pos[i] = -1;
-        __syncthreads();
-        if (tid == 0) { int tot = 0; for (int q = 0; q < (int)(blockDim.x >> 5); ++q) tot += warp_tot[q]; base += tot; }
-        __syncthreads();
-    }
-    if (tid == 0) {
-        *w.n_ne = base;
-        double acc = 0.0;                  // sum([np.log(x+1) for x in range(k)]) accumulated left to right
-        w.logfact[0] = 0.0;
-        for (int k = 1; k <= T + 1; ++k) { acc += log((double)k); w.logfact[k] = acc; }
-    }
-}
-
-__global__ void __launch_bounds__(128) asm_disp_kernel(const int8_t* __restrict__ bases, const int32_t* __restrict__ n_bases,
-                                                       int T, int kernel, double jsr, AsmWork w) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = *w.n_ne;
-    if (j >= n) return;
-    if (j == 0) { w.disp[0] = 0; return; }
-    const int wc = w.list[j], wp = w.list[j - 1];
-    const int8_t* cur = bases + (size_t)wc * T;
-    const int8_t* prev = bases + (size_t)wp * T;
-    const int la = n_bases[wc], lb = n_bases[wp];
-    int d;
-    if (kernel == CB_ASM_STICK) d = cb_disp_stick(la, lb);
-    else if (kernel == CB_ASM_GLUE) d = cb_disp_glue(cur, la, prev, lb);
-    else d = cb_disp_simple(cur, la, prev, lb, jsr, w.logfact, w.scratch + (size_t)j * w.scratch_stride);
-    w.disp[j] = d;
-}
-
-__global__ void __launch_bounds__(1024) asm_scan_kernel(const int32_t* __restrict__ n_bases, AsmWork w,
-                                                        int32_t* __restrict__ pos, int32_t* __restrict__ out_len,
-                                                        int max_len) {
-    // single block: inclusive scan of the displacements -> window coordinates; length = max_{j>=1}(pos_j + len_j)
-    __shared__ int warp_tot[32];
-    __shared__ int base, max_end;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int n = *w.n_ne;
-    if (tid == 0) { base = 0; max_end = 0; }
-    __syncthreads();
-    for (int start = 0; start < n; start += blockDim.x) {
-        const int j = start + tid;
-        int v = j < n ? w.disp[j] : 0;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
-        if (lane == 31) warp_tot[wid] = v;
-        __syncthreads();
-        int off = base;
-        for (int q = 0; q < wid; ++q) off += warp_tot[q];
-        v += off;
-        if (j < n) {
-            w.disp[j] = v;                               // running position of window list[j]
-            pos[w.list[j]] = v;
-            if (j >= 1) atomicMax(&max_end, v + n_bases[w.list[j]]);   // window 0 never updates `length` (:316-318)
-        }
-        __syncthreads();
-        if (tid == blockDim.x - 1) base = v;
-        __syncthreads();
-    }
-    if (tid == 0) { *w.length = max_end; *out_len = max_end < max_len ? max_end : max_len; }
-}
-
-__global__ void __launch_bounds__(128) asm_vote_kernel(const int8_t* __restrict__ bases, const int32_t* __restrict__ n_bases,
-                                                       const float* __restrict__ path_prob, int T, AsmWork w, int max_len) {
-    // one block per non-empty window: add_count(_qs) (easy_assembler.py:381-388,435-442)
-    const int j = blockIdx.x;
-    if (j >= *w.n_ne) return;
-    const int wi = w.list[j];
-    const int len = n_bases[wi], p0 = w.disp[j];
-    int length = *w.length; if (length > max_len) length = max_len;
-    const double q = path_prob ? (double)path_prob[wi] : 0.0;
-    for (int i = threadIdx.x; i < len; i += blockDim.x) {
-        const int col = p0 + i;
-        if (col < 0 || col >= length) continue;          // negative start trims the head; beyond `length` is cut
-        const int base = bases[(size_t)wi * T + i] & 3;
-        atomicAdd(&w.counts[(size_t)base * max_len + col], 1);
-        if (path_prob) atomicAdd(&w.qsum[(size_t)base * max_len + col], q);
-    }
-}
-
-__global__ void __launch_bounds__(256) asm_finish_kernel(AsmWork w, int max_len, int8_t* __restrict__ consensus,
-                                                         char* __restrict__ qual) {
-    int length = *w.length; if (length > max_len) length = max_len;
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= length) return;
-    int c[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) c[r] = w.counts[(size_t)r * max_len + col];
-    int best = 0;
-#pragma unroll
-    for (int r = 1; r < 4; ++r) if (c[r] > c[best]) best = r;        // np.argmax: first maximum
-    consensus[col] = (int8_t)best;
-    if (!qual) return;
-    // qs(): np.argsort(axis=0) on 4 elements is a stable insertion sort; rows [2] and [3] of the sorted matrix
-    int idx[4] = {0, 1, 2, 3};
-#pragma unroll
-    for (int x = 1; x < 4; ++x) {
-        const int v = idx[x];
-        int y = x;
-        while (y > 0 && c[idx[y - 1]] > c[v]) { idx[y] = idx[y - 1]; --y; }
-        idx[y] = v;
-    }
-    const double c3 = (double)c[idx[3]], c2 = (double)c[idx[2]];
-    const double qs3 = w.qsum[(size_t)idx[3] * max_len + col];
-    char ch = '!';
-    if (c3 > 0.0) {
-        const double q = 10.0 * log10((c3 + 1.0) / (c2 + 1.0)) + qs3 / c3 / log(10.0);
-        ch = (char)((int)q + 33);                                     // astype(int): truncation toward zero
-    }
-    qual[col] = ch;
-}
 
 int ensure_buf(void** buf, size_t* cur, size_t need, const char* what) {
     if (need <= *cur) return CB_OK;
@@ -405,7 +36,7 @@ int cb_launch_beam(cb_handle* h, const float* logits, const int32_t* lens, int B
         if (pool_s < 2LL * W + 2) pool_s = 2LL * W + 2;
         if (pool_s < 64) pool_s = 64;
         if (pool_s > cap) pool_s = cap;
-        const size_t stride = align_up(align_up((size_t)T * C * 4, 16) + cb_beam_work_bytes(W, (int)pool_s), 16);
+        const size_t stride = beam_warp_stride(T, C, W, (int)pool_s);
         const int smem_env = getenv("CB_BEAM_SMEM") ? atoi(getenv("CB_BEAM_SMEM")) : 1;    // 0: force the fallback kernel (tests)
         if (smem_env && stride * BEAM_WARPS <= 200 * 1024) {
             static bool attr_set = false;
@@ -450,21 +81,13 @@ int cb_launch_assemble(cb_handle* h, const int8_t* bases, const int32_t* n_bases
                        int T, int jump, int L, int kernel, int8_t* consensus, char* qual, int32_t* pos,
                        int32_t* out_len, int max_len, cudaStream_t s) {
     if (n_windows == 0) { CB_CUDA(cudaMemsetAsync(out_len, 0, sizeof(int32_t), s)); return CB_OK; }
-    const size_t scratch_stride = kernel == CB_ASM_SIMPLE ? align_up(cb_simple_scratch_ints(T, T), 4) : 0;
-    const size_t ml = (size_t)(max_len > 0 ? max_len : 1);
-    size_t off = 0;
-    auto carve = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
-    const size_t o_list = carve(sizeof(int) * n_windows), o_nne = carve(sizeof(int)), o_disp = carve(sizeof(int) * n_windows);
-    const size_t o_len = carve(sizeof(int)), o_counts = carve(sizeof(int) * 4 * ml), o_qsum = carve(sizeof(double) * 4 * ml);
-    const size_t o_lf = carve(sizeof(double) * (T + 2)), o_scr = carve(sizeof(int) * scratch_stride * n_windows);
-    int rc = ensure_buf(&h->asm_ws, &h->asm_ws_bytes, off, "assembly workspace");
+    const AsmPlan plan = asm_plan(n_windows, T, kernel, max_len);
+    const size_t ml = plan.ml;
+    int rc = ensure_buf(&h->asm_ws, &h->asm_ws_bytes, plan.total, "assembly workspace");
     if (rc != CB_OK) return rc;
     char* base = (char*)h->asm_ws;
-    AsmWork w;
-    w.list = (int*)(base + o_list); w.n_ne = (int*)(base + o_nne); w.disp = (int*)(base + o_disp);
-    w.length = (int*)(base + o_len); w.counts = (int*)(base + o_counts); w.qsum = (double*)(base + o_qsum);
-    w.logfact = (double*)(base + o_lf); w.scratch = (int*)(base + o_scr); w.scratch_stride = scratch_stride;
-    CB_CUDA(cudaMemsetAsync(base + o_counts, 0, (o_lf - o_counts), s));       // counts + qsum
+    AsmWork w = asm_work(base, plan);
+    CB_CUDA(cudaMemsetAsync(base + plan.counts, 0, plan.logfact - plan.counts, s));       // counts + qsum
     asm_compact_kernel<<<1, 1024, 0, s>>>(n_bases, n_windows, T, w, pos);
     CB_CHECK_LAUNCH();
     const double jsr = (double)jump / (double)L;                                // FLAGS.jump / FLAGS.segment_len

@@ -149,3 +149,16 @@ static inline unsigned __ballot_sync(unsigned, bool pred) {
     return m;
 }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline void __syncwarp(unsigned = 0xffffffffu) {
+    const emu::WarpPos p = emu::warp_pos();
+    (*p.c->warp_bar)[p.w]->arrive_and_wait();
+}
+static inline int atomicExch(int* addr, int v) { return std::atomic_ref<int>(*addr).exchange(v); }
+static inline int atomicAdd(int* addr, int v) { return std::atomic_ref<int>(*addr).fetch_add(v); }
+static inline double atomicAdd(double* addr, double v) {
+    std::atomic_ref<double> a(*addr);
+    double old = a.load();
+    while (!a.compare_exchange_weak(old, old + v)) {}
+    return old;
+}

@@ -14,6 +14,7 @@
 #include "../../chiron_b200/csrc/cb_gru_simt_kernel.cuh"
 #include "../../chiron_b200/csrc/cb_lstm_simt_kernel.cuh"
 #include "../../chiron_b200/csrc/cb_head_decode_kernels.cuh"
+#include "../../chiron_b200/csrc/cb_seq_kernels.cuh"
 
 namespace {
 
@@ -183,5 +184,44 @@ extern "C" int emu_seq_len(const int32_t* in, int B, int L, int T, int32_t* out)
 }
 extern "C" int emu_greedy(const float* logits, const int32_t* lens, int B, int T, int C, int8_t* bases, int32_t* n_bases) {
     emu::launch((B + 3) / 4, 128, [&] { cb_hd::greedy_kernel(logits, lens, B, T, C, bases, n_bases); });
+    return CB_OK;
+}
+
+// CTC beam search: the warp-cooperative shared-memory kernel (warp = 1) or the thread-per-window fallback (warp = 0), with
+// the pool sizes of cb_launch_beam.  Returns the overflow flag (0 = every window decoded), or a negative CB_ERR_* code.
+extern "C" int emu_beam(int warp, const float* logits, const int32_t* lens, int B, int T, int C, int W, int pool,
+                        int8_t* bases, int32_t* n_bases) {
+    int overflow = 0;
+    if (pool < 2 * W + 2) return CB_ERR_ARG;
+    if (warp) {
+        const size_t stride = cb_seq::beam_warp_stride(T, C, W, pool);
+        emu::launch2d((B + cb_seq::BEAM_WARPS - 1) / cb_seq::BEAM_WARPS, 1, cb_seq::BEAM_WARPS * 32, stride * cb_seq::BEAM_WARPS, [&] {
+            cb_seq::beam_warp_kernel(logits, lens, B, T, C, W, pool, (int)stride, bases, n_bases, &overflow);
+        });
+    } else {
+        const size_t stride = cb_seq::align_up(cb_beam_work_bytes(W, pool), 16);
+        std::vector<char> ws(stride * (size_t)B + 64);
+        emu::launch((B + 63) / 64, 64, [&] {
+            cb_seq::beam_kernel(logits, lens, B, T, C, W, pool, ws.data(), stride, bases, n_bases, &overflow);
+        });
+    }
+    return overflow;
+}
+
+// Overlap assembly of one read: the five kernels of cb_launch_assemble with its grids and workspace plan.
+extern "C" int emu_assemble(const int8_t* bases, const int32_t* n_bases, const float* path_prob, int n_windows, int T, int jump,
+                            int L, int kernel, int8_t* consensus, char* qual, int32_t* pos, int32_t* out_len, int max_len) {
+    if (n_windows == 0) { *out_len = 0; return CB_OK; }
+    const cb_seq::AsmPlan plan = cb_seq::asm_plan(n_windows, T, kernel, max_len);
+    std::vector<char> buf(plan.total + 256, 0);
+    char* base = buf.data() + (256 - reinterpret_cast<uintptr_t>(buf.data()) % 256) % 256;
+    cb_seq::AsmWork w = cb_seq::asm_work(base, plan);
+    const int ml = (int)plan.ml;
+    emu::launch(1, 1024, [&] { cb_seq::asm_compact_kernel(n_bases, n_windows, T, w, pos); });
+    const double jsr = (double)jump / (double)L;
+    emu::launch((n_windows + 127) / 128, 128, [&] { cb_seq::asm_disp_kernel(bases, n_bases, T, kernel, jsr, w); });
+    emu::launch(1, 1024, [&] { cb_seq::asm_scan_kernel(n_bases, w, pos, out_len, max_len); });
+    emu::launch(n_windows, 128, [&] { cb_seq::asm_vote_kernel(bases, n_bases, path_prob, T, w, ml); });
+    if (max_len > 0) emu::launch((max_len + 255) / 256, 256, [&] { cb_seq::asm_finish_kernel(w, ml, consensus, qual); });
     return CB_OK;
 }

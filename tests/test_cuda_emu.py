@@ -26,7 +26,7 @@ def emu():
     deps = [SRC, os.path.join(HERE, "cuda_emu", "cuda_emu.h")] + [
         os.path.join(CSRC, f) for f in ("cb_simt_types.h", "cb_gemm_simt_kernel.cuh", "cb_bn_kernels.cuh", "cb_conv_stack.cuh",
                                         "cb_gru_simt_kernel.cuh", "cb_lstm_simt_kernel.cuh", "cb_stem_kernel.cuh",
-                                        "cb_head_decode_kernels.cuh")]
+                                        "cb_head_decode_kernels.cuh", "cb_seq_kernels.cuh", "cb_seq_algos.cuh")]
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
         subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-Wno-unknown-pragmas",
@@ -287,3 +287,72 @@ def test_head_path_prob_seq_len_and_greedy_kernels(emu, dna_model):
         out = np.zeros_like(raw)
         assert emu.emu_seq_len(raw.ctypes.data_as(ctypes.c_void_p), len(raw), L, Tq, out.ctypes.data_as(ctypes.c_void_p)) == 0
         assert np.array_equal(out, O.seq_len_out(raw, L / Tq))
+
+
+@pytest.mark.parametrize("warp", [1, 0], ids=["beam_warp_kernel", "beam_kernel"])
+def test_beam_search_kernels_are_bit_identical_to_the_c_oracle(emu, warp):
+    """The warp-cooperative shared-memory beam search (the product path) and the thread-per-window fallback against the C
+    oracle's restatement of TF's CTCBeamSearchDecoder: widths 1..30, ragged lengths incl. 0, exact ties, with the launcher's
+    small pool (the trie is compacted in place when it fills up) and with the pool that can never overflow."""
+    rng = np.random.default_rng(31 + warp)
+    B, T, C = 9, 36, 5
+    lg = rng.normal(size=(B, T, C)).astype(np.float32) * 2
+    lg[:, :, C - 1] += 1.0
+    lg[:, ::4, :] = np.round(lg[:, ::4, :])
+    lens = rng.integers(0, T + 1, size=B).astype(np.int32)
+    lens[0], lens[1] = T, 0
+    overflowed, compared = [], 0
+    for W in (1, 2, 5, 13, 30):
+        for pool in sorted({max(6 * W, 64), 2 * W * (T + 1) + 2}):      # cb_launch_beam's small pool, and the no-overflow bound
+            bases = np.full((B, T), 9, np.int8)
+            n_bases = np.full(B, -1, np.int32)
+            rc = emu.emu_beam(warp, _fp(lg), lens.ctypes.data_as(ctypes.c_void_p), B, T, C, W, pool,
+                              bases.ctypes.data_as(ctypes.c_void_p), n_bases.ctypes.data_as(ctypes.c_void_p))
+            if pool < 2 * W * (T + 1) + 2 and rc == 1:
+                overflowed.append(W)          # legitimate on random logits: cb_launch_beam then falls back / retries
+                continue
+            assert rc == 0, "error %d at W=%d pool=%d" % (rc, W, pool)
+            compared += 1
+            assert [bases[b, :n_bases[b]].tolist() for b in range(B)] == O.ctc_decode_c(lg, lens, W), (W, pool)
+            assert all((bases[b, n_bases[b]:] == 0).all() for b in range(B))
+    assert compared >= 7 and set(overflowed) <= {13, 30}
+
+
+def test_assembly_kernels_reproduce_the_reference_fixtures(emu):
+    """asm_compact -> asm_disp -> asm_scan -> asm_vote -> asm_finish (with the launcher's grids and workspace plan) on the
+    fixtures produced by the reference's own easy_assembler + qs() (tests/golden/assembly_ref): consensus, quality string
+    and window positions for the simple / glue / stick kernels, with empty windows mixed in."""
+    from test_assembly_reference_fixtures import BASE_IDX, FIXTURES, _load
+    code = {"simple": 0, "glue": 1, "stick": 2}
+    for path in FIXTURES[:3]:
+        fx, segs, wts = _load(path)
+        T = max(len(s) for s in segs) + 3
+        n = len(segs) + 2
+        rows = [i for i in range(n) if i not in (4, n - 1)]         # two empty windows: dropped like sparse2dense does
+        bases = np.zeros((n, T), np.int8)
+        n_bases = np.zeros(n, np.int32)
+        prob = np.zeros(n, np.float32)
+        for r, sgm, q in zip(rows, segs, wts):
+            bases[r, :len(sgm)] = [BASE_IDX[c] for c in sgm]
+            n_bases[r] = len(sgm)
+            prob[r] = q
+        for case in fx["cases"]:
+            L = 400
+            jump = int(round(case["jump_step_ratio"] * L))
+            max_len = int(n_bases.sum()) + 1
+            cons = np.zeros(max_len, np.int8)
+            qual = np.zeros(max_len, np.uint8)
+            pos = np.full(n, -5, np.int32)
+            out_len = np.zeros(1, np.int32)
+            rc = emu.emu_assemble(bases.ctypes.data_as(ctypes.c_void_p), n_bases.ctypes.data_as(ctypes.c_void_p), _fp(prob), n, T,
+                                  jump, L, code[case["kernal"]], cons.ctypes.data_as(ctypes.c_void_p),
+                                  qual.ctypes.data_as(ctypes.c_void_p), pos.ctypes.data_as(ctypes.c_void_p),
+                                  out_len.ctypes.data_as(ctypes.c_void_p), max_len)
+            assert rc == 0
+            ln = int(out_len[0])
+            assert O.index2base(cons[:ln]) == case["consensus"], (os.path.basename(path), case["kernal"])
+            ref_cons, _, ref_pos = O.simple_assembly_qs(segs, wts, case["jump_step_ratio"], kernal=case["kernal"])
+            assert pos[rows].tolist() == ref_pos.tolist() and pos[4] == -1 and pos[n - 1] == -1
+            covered = ref_cons.sum(axis=0) > 0
+            got_q = bytes(qual[:ln]).decode("latin-1")
+            assert [c for c, ok in zip(got_q, covered) if ok] == [c for c, ok in zip(case["quality"], covered) if ok]
