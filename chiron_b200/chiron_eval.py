@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import argparse
 import collections
+import json
 import os
 import queue
 import sys
@@ -105,11 +106,12 @@ def list_input_files(flags) -> (List[str], str):
 
 
 class _ReadState:
-    __slots__ = ("name", "n", "bases", "n_bases", "prob", "filled", "start_time", "reading_time")
+    __slots__ = ("name", "n", "samples", "bases", "n_bases", "prob", "filled", "start_time", "reading_time")
 
-    def __init__(self, name, n, T, start_time, reading_time):
+    def __init__(self, name, n, T, start_time, reading_time, samples=0):
         self.name = name
         self.n = n
+        self.samples = samples
         self.bases = np.zeros((n, T), dtype=np.int8)
         self.n_bases = np.zeros(n, dtype=np.int32)
         self.prob = np.zeros(n, dtype=np.float32)
@@ -163,7 +165,7 @@ def evaluation(flags=None, caller: Optional[Basecaller] = None) -> Dict[str, dic
         file_pre = os.path.splitext(st.name)[0]
         # the segment strings are built by the writer thread: this thread's job is to keep the GPU fed
         write_q.put((st.bases, st.n_bases, seq, [st.start_time, st.reading_time, basecall_time, assembly_time], file_pre, qual))
-        summary[st.name] = {"windows": st.n, "bases": len(seq), "pos": pos}
+        summary[st.name] = {"windows": st.n, "samples": st.samples, "bases": len(seq), "pos": pos}
 
     # ---- finisher thread: per-read assembly off the GPU-feeding thread ---------------------------------------------------
     # cb_assemble_host synchronises its own (default) stream; while the forward kernels of two batches occupy the SMs the
@@ -264,7 +266,7 @@ def evaluation(flags=None, caller: Optional[Basecaller] = None) -> Dict[str, dic
         eval_data, start_time, reading_time = futures.popleft().result()
         if idx + lookahead < len(file_list):
             futures.append(pool.submit(load, file_list[idx + lookahead]))
-        st = _ReadState(name, eval_data.reads_n, T, start_time, reading_time)
+        st = _ReadState(name, eval_data.reads_n, T, start_time, reading_time, getattr(eval_data, "samples", 0))
         open_reads.append(st)
         i = 0
         if eval_data.reads_n == 0:
@@ -307,7 +309,8 @@ def run(args):
     FLAGS = args
     print("The result will be written to %s" % (FLAGS.output))
     os.makedirs(FLAGS.output, exist_ok=True)
-    time_dict = unix_time(evaluation)
+    result = {}
+    time_dict = unix_time(lambda: result.update(evaluation()))
     print("Real time:%5.3f Systime:%5.3f Usertime:%5.3f" % (time_dict["real"], time_dict["sys"], time_dict["user"]))
     meta_folder = os.path.join(FLAGS.output, "meta")
     if os.path.isdir(FLAGS.input):
@@ -322,6 +325,26 @@ def run(args):
         out_meta.write("# Wall_time Sys_time User_time Cpu_time\n")
         out_meta.write("%5.3f %5.3f %5.3f %5.3f\n" % (time_dict["real"], time_dict["sys"], time_dict["user"],
                                                       time_dict["sys"] + time_dict["user"]))
+    write_perf_report(os.path.join(meta_folder, file_pre + ".perf.json"), FLAGS, result, time_dict, rank, world)
+
+
+def write_perf_report(path: str, flags, summary: Dict[str, dict], time_dict: dict, rank: int = 0, world: int = 1) -> dict:
+    """Machine-readable twin of meta/all.meta ("add JSON perf report"): what this rank processed and
+    the raw-signal Msamples/s / kbases/s it delivered end to end, files in to files out.  The reference has no such file;
+    it sits next to all.meta and changes nothing else in the output tree."""
+    samples = sum(v.get("samples", 0) for v in summary.values())
+    bases = sum(v["bases"] for v in summary.values())
+    wall = max(time_dict["real"], 1e-9)
+    report = {"reads": len(summary), "windows": sum(v["windows"] for v in summary.values()), "samples": samples, "bases": bases,
+              "wall_s": time_dict["real"], "cpu_s": time_dict["sys"] + time_dict["user"],
+              "Msamples_per_s": samples / wall / 1e6, "kbases_per_s": bases / wall / 1e3,
+              "segment_len": flags.segment_len, "jump": flags.jump, "batch_size": flags.batch_size, "beam": flags.beam,
+              "precision": getattr(flags, "precision", None) or "fp32", "model": flags.model, "mode": flags.mode,
+              "rank": rank, "world_size": world}
+    with open(path, "w") as f:
+        json.dump(report, f, indent=1)
+        f.write("\n")
+    return report
 
 
 def add_call_arguments(parser: argparse.ArgumentParser, model_default: Optional[str] = None):

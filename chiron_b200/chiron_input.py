@@ -61,9 +61,10 @@ def normalize_signal(signal: np.ndarray, mode: int) -> np.ndarray:
 class DataSet:
     """The windows of one read.  ``next_batch`` keeps the reference's sequential, no-shuffle contract."""
 
-    def __init__(self, event: np.ndarray, event_length: np.ndarray):
+    def __init__(self, event: np.ndarray, event_length: np.ndarray, samples: int = 0):
         self.event = event                  # [n, seg_length] float32, zero padded
         self.event_length = event_length    # [n] int32
+        self.samples = int(samples)         # raw samples the windows were cut from (perf report)
         self._index = 0
         self.epochs_completed = 0
 
@@ -110,4 +111,4 @@ def windows_from_signal(f_signal: np.ndarray, step: int, seg_length: int) -> Dat
                             event.ctypes.data_as(ctypes.c_void_p), lens.ctypes.data_as(ctypes.c_void_p), n_win)
     if n < 0:
         _lib.check(int(n), "cb_host_windows")
-    return DataSet(event, lens)
+    return DataSet(event, lens, samples=sig.size)

@@ -129,3 +129,91 @@ def test_two_rank_weight_broadcast_and_sharding_gloo(tmp_path):
     assert res[0][1] == res[1][1] == os.path.getsize(bundled_blob_path("DNA_default"))
     assert res[0][2] == res[1][2]
     assert sorted(res[0][3] + res[1][3]) == ["r%d" % i for i in range(9)] and not set(res[0][3]) & set(res[1][3])
+
+
+def test_host_pipeline_end_to_end_with_a_stub_gpu(tmp_path, monkeypatch):
+    """chiron_eval.run() from files to files with the GPU replaced by a do-nothing Basecaller of the same surface
+    (tools/call_bench.py's StubCaller): reader threads, cross-read batching, the two-slot submit/collect protocol, the
+    finisher thread, the writer pool, the output tree and the JSON perf report -- everything but the kernels."""
+    import json
+    import shutil
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "tools"))
+    from call_bench import StubCaller
+    from chiron_b200 import chiron_eval
+    src = tmp_path / "in"
+    src.mkdir()
+    n_samples = {}
+    for i in range(7):
+        name = "read1.signal" if i % 2 == 0 else "read3.signal"
+        shutil.copy(os.path.join(GOLDEN, "DNA", "raw", name), str(src / ("r%02d.signal" % i)))
+        n_samples["r%02d" % i] = len(chiron_input.read_signal(os.path.join(GOLDEN, "DNA", "raw", name)))
+    (src / "empty.signal").write_text("")                               # a read without samples still gets its files
+    (src / "notes.txt").write_text("ignored")
+    submitted = []
+
+    class Recorder(StubCaller):
+        def basecall_submit(self, slot, x, seq_len, beam=0):
+            submitted.append((slot, x.shape[0], int(seq_len.sum())))
+            return super().basecall_submit(slot, x, seq_len, beam)
+
+    monkeypatch.setattr(chiron_eval, "Basecaller", lambda model, device=0, precision="fp32": Recorder(model))
+    monkeypatch.setenv("CHIRON_B200_GPU_BATCH", "300")
+    out = str(tmp_path / "out")
+    args = types.SimpleNamespace(input=str(src), output=out, model="DNA_default", start=None, batch_size=None, segment_len=None,
+                                 jump=None, threads=3, beam=0, extension="fastq", concise=False, mode="dna", preset="dna-pre",
+                                 precision="tc", recursive=False)
+    chiron_eval.run(apply_preset(args))
+    names = sorted(n_samples) + ["empty"]
+    for sub in ("result", "segments"):
+        assert sorted(os.listdir(os.path.join(out, sub))) == sorted(n + ".fastq" for n in names)
+    assert {f for f in os.listdir(os.path.join(out, "meta"))} == {n + ".meta" for n in names} | {"all.meta", "all.perf.json"}
+    with open(os.path.join(out, "meta", "all.perf.json")) as f:
+        perf = json.load(f)
+    assert perf["reads"] == 8 and perf["samples"] == sum(n_samples.values()) and perf["precision"] == "tc"
+    assert perf["windows"] == sum(-(-n // 390) for n in n_samples.values())
+    assert perf["Msamples_per_s"] > 0 and perf["world_size"] == 1 and perf["segment_len"] == 400 and perf["jump"] == 390
+    # batching: windows are packed ACROSS reads into batches of >= 400 (the flag; the GPU batch was forced to 300), slots
+    # alternate, every sample is submitted exactly once, only the last batch is partial
+    assert [s[0] for s in submitted] == [i % 2 for i in range(len(submitted))]
+    assert all(s[1] == 400 for s in submitted[:-1]) and 0 < submitted[-1][1] <= 400
+    assert sum(s[1] for s in submitted) == perf["windows"]
+    total_len = sum(min(400, n - st) for n in n_samples.values() for st in range(0, n, 390))
+    assert sum(s[2] for s in submitted) == total_len
+    # the stub calls 20 bases per window: every read's segment file has one record per window
+    records = open(os.path.join(out, "segments", "r00.fastq")).read().split("\n")
+    assert len([l for l in records if l.startswith(">r00")]) == -(-n_samples["r00"] // 390)
+    assert open(os.path.join(out, "result", "empty.fastq")).read() == "@empty\n\n+\n\n"
+
+
+def test_read_sharding_of_the_host_pipeline_with_a_stub_gpu(tmp_path, monkeypatch):
+    """Two ranks (RANK / WORLD_SIZE as torchrun sets them) each basecall their own reads and write their own files: the
+    result files of the ranks partition the input, and each rank leaves its own all.rank<r>.meta / .perf.json."""
+    import json
+    import shutil
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "tools"))
+    from call_bench import StubCaller
+    from chiron_b200 import chiron_eval
+    src = tmp_path / "in"
+    src.mkdir()
+    for i in range(9):
+        shutil.copy(os.path.join(GOLDEN, "DNA", "raw", "read1.signal" if i % 3 else "read3.signal"), str(src / ("r%02d.signal" % i)))
+    monkeypatch.setattr(chiron_eval, "Basecaller", lambda model, device=0, precision="fp32": StubCaller(model))
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    done = []
+    for rank in (0, 1):
+        monkeypatch.setenv("RANK", str(rank))
+        monkeypatch.setenv("LOCAL_RANK", str(rank))
+        out = str(tmp_path / ("out%d" % rank))
+        args = types.SimpleNamespace(input=str(src), output=out, model="DNA_default", start=None, batch_size=None,
+                                     segment_len=None, jump=None, threads=2, beam=0, extension="fasta", concise=True, mode="dna",
+                                     preset="dna-pre", precision="fp32", recursive=False)
+        chiron_eval.run(apply_preset(args))
+        done.append({f[:-6] for f in os.listdir(os.path.join(out, "result"))})
+        with open(os.path.join(out, "meta", "all.rank%d.perf.json" % rank)) as f:
+            perf = json.load(f)
+        assert perf["rank"] == rank and perf["world_size"] == 2 and perf["reads"] == len(done[-1])
+        assert os.path.exists(os.path.join(out, "meta", "all.rank%d.meta" % rank))
+    assert done[0] | done[1] == {"r%02d" % i for i in range(9)} and not (done[0] & done[1])
+    assert 3 <= len(done[0]) <= 6                                    # balanced by file size (shard.assign_reads)
