@@ -9,6 +9,10 @@
 
 using namespace cb_seq;
 
+#ifndef CB_BEAM_STAGE_DEFAULT
+#define CB_BEAM_STAGE_DEFAULT false      // logits read from global memory (prefetched), shared memory = workspace only
+#endif
+
 namespace {
 
 int ensure_buf(void** buf, size_t* cur, size_t need, const char* what) {
@@ -36,17 +40,25 @@ int cb_launch_beam(cb_handle* h, const float* logits, const int32_t* lens, int B
         if (pool_s < 2LL * W + 2) pool_s = 2LL * W + 2;
         if (pool_s < 64) pool_s = 64;
         if (pool_s > cap) pool_s = cap;
-        const size_t stride = beam_warp_stride(T, C, W, (int)pool_s);
         const int smem_env = getenv("CB_BEAM_SMEM") ? atoi(getenv("CB_BEAM_SMEM")) : 1;    // 0: force the fallback kernel (tests)
+        // CB_BEAM_STAGE_LOGITS=1: copy each window's logits to shared memory first (the earlier variant, kept for A/B)
+        const bool staged = getenv("CB_BEAM_STAGE_LOGITS") ? atoi(getenv("CB_BEAM_STAGE_LOGITS")) != 0 : CB_BEAM_STAGE_DEFAULT;
+        const size_t stride = beam_warp_stride(T, C, W, (int)pool_s, staged);
         if (smem_env && stride * BEAM_WARPS <= 200 * 1024) {
             static bool attr_set = false;
             if (!attr_set) {
-                CB_CUDA(cudaFuncSetAttribute(beam_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                CB_CUDA(cudaFuncSetAttribute(beam_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                CB_CUDA(cudaFuncSetAttribute(beam_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                 attr_set = true;
             }
             CB_CUDA(cudaMemsetAsync(h->d_flag, 0, sizeof(int), s));
-            beam_warp_kernel<<<(B + BEAM_WARPS - 1) / BEAM_WARPS, BEAM_WARPS * 32, stride * BEAM_WARPS, s>>>(
-                logits, lens, B, T, C, W, (int)pool_s, (int)stride, bases, n_bases, h->d_flag);
+            const dim3 grid((B + BEAM_WARPS - 1) / BEAM_WARPS);
+            if (staged)
+                beam_warp_kernel<true><<<grid, BEAM_WARPS * 32, stride * BEAM_WARPS, s>>>(
+                    logits, lens, B, T, C, W, (int)pool_s, (int)stride, bases, n_bases, h->d_flag);
+            else
+                beam_warp_kernel<false><<<grid, BEAM_WARPS * 32, stride * BEAM_WARPS, s>>>(
+                    logits, lens, B, T, C, W, (int)pool_s, (int)stride, bases, n_bases, h->d_flag);
             CB_CHECK_LAUNCH();
             h->launches++;
             int flag = 0;              // the beam decoder is synchronous (like the reference's decode dequeue)

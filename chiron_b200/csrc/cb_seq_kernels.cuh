@@ -50,6 +50,8 @@ __global__ void __launch_bounds__(64) beam_kernel(const float* __restrict__ logi
 // The node pool is small (compacted often); if it ever overflows the launcher falls back to beam_kernel.
 constexpr int BEAM_WARPS = 4;
 
+// `lg` is the window's logits [len][C] in shared memory (staged by the caller) or in global memory; either way the row of
+// frame t + 1 is fetched into registers while frame t is processed, so its latency hides behind the frame's work.
 __device__ int beam_decode_warp(const float* __restrict__ lg, int len, int C, int W, CbBeamWork k, int8_t* out, int lane) {
     const unsigned FULL = 0xffffffffu;
     const int blank = C - 1, n_child = C - 1;
@@ -66,12 +68,20 @@ __device__ int beam_decode_warp(const float* __restrict__ lg, int len, int C, in
     n_free = __shfl_sync(FULL, n_free, 0);
     __syncwarp();
     const int bpc = 32 / n_child;                        // branches per chunk of the extension loop
-    float inp[8];
+    float inp[8], row[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) row[c] = (c < C && len > 0) ? lg[c] : 0.f;
     for (int t = 0; t < len; ++t) {
-        const float* row = lg + (size_t)t * C;
         float mx = row[0];
-        for (int c = 1; c < C; ++c) if (row[c] > mx) mx = row[c];
-        for (int c = 0; c < C; ++c) inp[c] = row[c] - mx;
+#pragma unroll
+        for (int c = 1; c < 8; ++c) if (c < C && row[c] > mx) mx = row[c];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) inp[c] = row[c] - mx;
+        if (t + 1 < len) {                               // prefetch the next frame's row
+            const float* nx = lg + (size_t)(t + 1) * C;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) if (c < C) row[c] = nx[c];
+        }
         const int nb = n_leaves;
         // leaves_.Extract(): descending newp.total, stable  ==  rank of every leaf
         for (int i = lane; i < nb; i += 32) {
@@ -212,6 +222,11 @@ __device__ int beam_decode_warp(const float* __restrict__ lg, int len, int C, in
     return __shfl_sync(FULL, n, 0);
 }
 
+// STAGED: the window's logits are copied to shared memory first (T*C*4 bytes per window).  Not staged: the search reads
+// its one row per frame straight from global memory (prefetched a frame ahead), shared memory holds the workspace only --
+// for T=512, W=30 that is 10.8 KB instead of 21 KB per window, i.e. 5 instead of 2 resident CTAs per SM, and the search is
+// a latency chain per warp, so the extra resident warps are what raises its throughput.
+template <bool STAGED>
 __global__ void __launch_bounds__(BEAM_WARPS * 32) beam_warp_kernel(const float* __restrict__ logits, const int32_t* __restrict__ lens,
                                                                     int B, int T, int C, int W, int pool, int stride,
                                                                     int8_t* __restrict__ bases, int32_t* __restrict__ n_bases,
@@ -225,14 +240,20 @@ __global__ void __launch_bounds__(BEAM_WARPS * 32) beam_warp_kernel(const float*
     const int b = blockIdx.x * BEAM_WARPS + w;
     if (b >= B) return;
     char* base = beam_sm + (size_t)w * stride;
-    float* lg = reinterpret_cast<float*>(base);
     int len = lens[b];
     len = len < 0 ? 0 : (len > T ? T : len);
     const float* src = logits + (size_t)b * T * C;
-    for (int i = lane; i < len * C; i += 32) lg[i] = src[i];
-    __syncwarp();
+    const float* lg = src;
+    size_t work_off = 0;
+    if (STAGED) {
+        float* stage = reinterpret_cast<float*>(base);
+        for (int i = lane; i < len * C; i += 32) stage[i] = src[i];
+        __syncwarp();
+        lg = stage;
+        work_off = ((size_t)T * C * 4 + 15) & ~(size_t)15;
+    }
     int8_t* dst = bases + (size_t)b * T;
-    CbBeamWork k = cb_beam_work_carve(base + (((size_t)T * C * 4 + 15) & ~(size_t)15), W, pool);
+    CbBeamWork k = cb_beam_work_carve(base + work_off, W, pool);
     int n = beam_decode_warp(lg, len, C, W, k, dst, lane);
     if (n < 0) { if (lane == 0) atomicExch(overflow, 1); n = 0; }
     __syncwarp();
@@ -406,9 +427,9 @@ inline AsmWork asm_work(char* base, const AsmPlan& p) {
     return w;
 }
 
-// Shared-memory footprint of one window of beam_warp_kernel (logits + workspace) for a pool of `pool` nodes.
-inline size_t beam_warp_stride(int T, int C, int W, int pool) {
-    return align_up(align_up((size_t)T * C * 4, 16) + cb_beam_work_bytes(W, pool), 16);
+// Shared-memory footprint of one window of beam_warp_kernel ((staged logits +) workspace) for a pool of `pool` nodes.
+inline size_t beam_warp_stride(int T, int C, int W, int pool, bool staged) {
+    return align_up((staged ? align_up((size_t)T * C * 4, 16) : 0) + cb_beam_work_bytes(W, pool), 16);
 }
 
 }  // namespace cb_seq

@@ -187,17 +187,25 @@ extern "C" int emu_greedy(const float* logits, const int32_t* lens, int B, int T
     return CB_OK;
 }
 
-// CTC beam search: the warp-cooperative shared-memory kernel (warp = 1) or the thread-per-window fallback (warp = 0), with
+// CTC beam search: the warp-cooperative shared-memory kernel (warp = 1: logits from global memory, 2: staged in shared
+// memory) or the thread-per-window fallback (warp = 0), with
 // the pool sizes of cb_launch_beam.  Returns the overflow flag (0 = every window decoded), or a negative CB_ERR_* code.
 extern "C" int emu_beam(int warp, const float* logits, const int32_t* lens, int B, int T, int C, int W, int pool,
                         int8_t* bases, int32_t* n_bases) {
     int overflow = 0;
     if (pool < 2 * W + 2) return CB_ERR_ARG;
     if (warp) {
-        const size_t stride = cb_seq::beam_warp_stride(T, C, W, pool);
-        emu::launch2d((B + cb_seq::BEAM_WARPS - 1) / cb_seq::BEAM_WARPS, 1, cb_seq::BEAM_WARPS * 32, stride * cb_seq::BEAM_WARPS, [&] {
-            cb_seq::beam_warp_kernel(logits, lens, B, T, C, W, pool, (int)stride, bases, n_bases, &overflow);
-        });
+        const bool staged = warp == 2;
+        const size_t stride = cb_seq::beam_warp_stride(T, C, W, pool, staged);
+        const unsigned grid = (B + cb_seq::BEAM_WARPS - 1) / cb_seq::BEAM_WARPS;
+        if (staged)
+            emu::launch2d(grid, 1, cb_seq::BEAM_WARPS * 32, stride * cb_seq::BEAM_WARPS, [&] {
+                cb_seq::beam_warp_kernel<true>(logits, lens, B, T, C, W, pool, (int)stride, bases, n_bases, &overflow);
+            });
+        else
+            emu::launch2d(grid, 1, cb_seq::BEAM_WARPS * 32, stride * cb_seq::BEAM_WARPS, [&] {
+                cb_seq::beam_warp_kernel<false>(logits, lens, B, T, C, W, pool, (int)stride, bases, n_bases, &overflow);
+            });
     } else {
         const size_t stride = cb_seq::align_up(cb_beam_work_bytes(W, pool), 16);
         std::vector<char> ws(stride * (size_t)B + 64);

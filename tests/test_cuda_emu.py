@@ -289,12 +289,12 @@ def test_head_path_prob_seq_len_and_greedy_kernels(emu, dna_model):
         assert np.array_equal(out, O.seq_len_out(raw, L / Tq))
 
 
-@pytest.mark.parametrize("warp", [1, 0], ids=["beam_warp_kernel", "beam_kernel"])
+@pytest.mark.parametrize("warp", [1, 2, 0], ids=["beam_warp_kernel", "beam_warp_kernel_staged", "beam_kernel"])
 def test_beam_search_kernels_are_bit_identical_to_the_c_oracle(emu, warp):
     """The warp-cooperative shared-memory beam search (the product path) and the thread-per-window fallback against the C
     oracle's restatement of TF's CTCBeamSearchDecoder: widths 1..30, ragged lengths incl. 0, exact ties, with the launcher's
     small pool (the trie is compacted in place when it fills up) and with the pool that can never overflow."""
-    rng = np.random.default_rng(31 + warp)
+    rng = np.random.default_rng(31)
     B, T, C = 9, 36, 5
     lg = rng.normal(size=(B, T, C)).astype(np.float32) * 2
     lg[:, :, C - 1] += 1.0
@@ -315,7 +315,7 @@ def test_beam_search_kernels_are_bit_identical_to_the_c_oracle(emu, warp):
             compared += 1
             assert [bases[b, :n_bases[b]].tolist() for b in range(B)] == O.ctc_decode_c(lg, lens, W), (W, pool)
             assert all((bases[b, n_bases[b]:] == 0).all() for b in range(B))
-    assert compared >= 7 and set(overflowed) <= {13, 30}
+    assert compared >= 7 and set(overflowed) <= {13, 30}      # random logits: wide beams may outgrow the small pool
 
 
 def test_assembly_kernels_reproduce_the_reference_fixtures(emu):
