@@ -130,20 +130,24 @@ def test_cooperative_beam_kernel_is_bit_identical_to_the_sequential_one(caller):
     lens = rng.integers(0, T + 1, size=B).astype(np.int32)
     lens[:4] = [T, 0, 1, 2]
     dl, dn = torch.from_numpy(lg).cuda(), torch.from_numpy(lens).cuda()
-    old = os.environ.get("CB_BEAM_SMEM")
+    old = {k: os.environ.get(k) for k in ("CB_BEAM_SMEM", "CB_BEAM_STAGE_LOGITS")}
     try:
         for W in (1, 2, 3, 30, 50, 100):
             out = {}
-            for mode in ("0", "1"):
-                os.environ["CB_BEAM_SMEM"] = mode
+            # the thread-per-window fallback, and the cooperative kernel with the logits read from global memory / staged in
+            # shared memory (the launcher picks between the last two by occupancy; here each is forced)
+            for mode, (smem, stage) in {"fallback": ("0", "0"), "global": ("1", "0"), "staged": ("1", "1")}.items():
+                os.environ["CB_BEAM_SMEM"], os.environ["CB_BEAM_STAGE_LOGITS"] = smem, stage
                 bases, nb = caller.decode_device(dl, dn, beam=W)
                 torch.cuda.synchronize()
                 out[mode] = (bases.cpu().numpy().copy(), nb.cpu().numpy().copy())
-            assert np.array_equal(out["0"][1], out["1"][1]), "n_bases differ at width %d" % W
-            assert np.array_equal(out["0"][0], out["1"][0]), "bases differ at width %d" % W
-            assert out["1"][1].sum() > 0
+            for mode in ("global", "staged"):
+                assert np.array_equal(out["fallback"][1], out[mode][1]), "n_bases differ at width %d (%s)" % (W, mode)
+                assert np.array_equal(out["fallback"][0], out[mode][0]), "bases differ at width %d (%s)" % (W, mode)
+            assert out["global"][1].sum() > 0
     finally:
-        if old is None:
-            os.environ.pop("CB_BEAM_SMEM", None)
-        else:
-            os.environ["CB_BEAM_SMEM"] = old
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
