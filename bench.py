@@ -334,10 +334,11 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, kb, dt, threads = cpu_oracle_msamples(192, L, 99)
+        n_cpu = 640                                             # ~10 s of CPU work on 16 threads (bounded sample)
+        v, kb, dt, threads = cpu_oracle_msamples(n_cpu, L, 99)
         cpu = {"value": v, "unit": "Msamples/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": "192 windows x %d samples of the same synthetic workload, one pass (%.1f s); numpy/BLAS oracle, %d threads"
-                         % (L, dt, threads), "kbases_per_s": kb}
+               "sample": "%d windows x %d samples of the same synthetic workload, one pass (%.1f s); numpy/BLAS oracle, %d threads"
+                         % (n_cpu, L, dt, threads), "kbases_per_s": kb}
     if rank == 0:
         line = {"metric": "raw-signal Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
