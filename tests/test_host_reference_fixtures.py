@@ -63,3 +63,21 @@ def test_dense_rows_to_reads_matches_sparse2dense_and_index2base():
     assert engine.windows2bases(bases, n_bases) == fx["reads"]
     assert np.nonzero(n_bases > 0)[0].tolist() == fx["uniq"]          # the rows sparse2dense keeps
     assert [engine.index2base(bases[b, :n_bases[b]]) for b in fx["uniq"]] == fx["reads"]
+
+
+def test_signal_windows_match_the_reference_reader():
+    """chiron_input.read_signal + read_data_for_eval + padding run from the reference (sig_norm None as at HEAD) against
+    the native parse + window path, for several (start, step, seg_length) incl. windows longer than the read."""
+    import hashlib
+    from chiron_b200 import chiron_input
+    from chiron_b200.model import NORM_NONE
+    fx = FX["read_data_for_eval"]
+    path = os.path.join(os.path.dirname(GOLDEN), "..", fx["file"])
+    for case in fx["cases"]:
+        ds = chiron_input.read_data_for_eval(path, case["start_index"], step=case["step"], seg_length=case["seg_length"],
+                                             sig_norm=NORM_NONE)
+        assert ds.reads_n == case["n_windows"]
+        assert ds.event_length.tolist() == case["event_length"]
+        assert ds.event.dtype == np.float32 and ds.event.shape == (case["n_windows"], case["seg_length"])
+        assert hashlib.sha256(np.ascontiguousarray(ds.event).tobytes()).hexdigest() == case["event_sha256"]
+        assert ds.event[0, :8].tolist() == case["first_window_head"]

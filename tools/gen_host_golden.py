@@ -10,7 +10,11 @@ Nothing is copied into the repository; only arguments and outputs are stored.
 The fixture pins rows a12, a13 and a16 of the path to the reference's own code:
   * write_output: result / segments / meta file contents for fastq, fasta, concise, rna mode and per-segment qualities;
   * get_assembler_kernal: the kernel chosen for a grid of (jump, segment_len);
-  * sparse2dense + index2base on a SparseTensor-shaped greedy result with empty windows (the rows that disappear)."""
+  * sparse2dense + index2base on a SparseTensor-shaped greedy result with empty windows (the rows that disappear);
+  * chiron_input.read_signal + read_data_for_eval + padding (rows a1-a2; compiled the same way from chiron/chiron_input.py,
+    which imports h5py / statsmodels; FLAGS.sig_norm = None as at HEAD, DataSet replaced by a recorder of its arguments)
+    on the bundled read1.signal for several (start, step, seg_length): window count, true lengths and a SHA-256 of the
+    float32 window matrix."""
 import ast
 import collections
 import json
@@ -23,6 +27,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_EVAL = "/root/reference/chiron/chiron_eval.py"
+REF_INPUT = "/root/reference/chiron/chiron_input.py"
 OUT = os.path.join(ROOT, "tests", "golden", "host_ref", "host_ref.json")
 FIXED_NOW = 1000.0
 
@@ -35,6 +40,16 @@ def load_functions(names):
         if isinstance(node, ast.FunctionDef) and node.name in names:
             exec(compile(ast.Module(body=[node], type_ignores=[]), "chiron_eval." + node.name, "exec"), ns)
     return [ns[n] for n in names]
+
+
+def load_input_functions():
+    tree = ast.parse(open(REF_INPUT).read())
+    ns = {"np": np, "MEAN": "mean", "MEDIAN": "median", "FLAGS": types.SimpleNamespace(sig_norm=None),
+          "DataSet": lambda **kw: kw}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("read_signal", "padding", "read_data_for_eval"):
+            exec(compile(ast.Module(body=[node], type_ignores=[]), "chiron_input." + node.name, "exec"), ns)
+    return ns["read_data_for_eval"]
 
 
 def main():
@@ -92,6 +107,19 @@ def main():
     predict_read, uniq = sparse2dense(([Sparse(idx, vals, np.array([B, T]))], np.zeros((B, 1), np.float32)))
     fixture["sparse2dense"] = {"bases": bases.tolist(), "n_bases": n_bases.tolist(),
                                "reads": [index2base(r) for r in predict_read[0]], "uniq": [int(u) for u in uniq[0]]}
+    # ---- read_signal + read_data_for_eval + padding ---------------------------------------------------------------------------
+    import hashlib
+    read_data_for_eval = load_input_functions()
+    sig_path = os.path.join(ROOT, "tests", "golden", "DNA", "raw", "read1.signal")
+    windows = []
+    for start, step, seg in ((0, 390, 400), (0, 290, 300), (7, 100, 300), (0, 512, 512), (62000, 5, 100000), (0, 1900, 2000)):
+        ds = read_data_for_eval(sig_path, start_index=start, step=step, seg_length=seg)
+        event = np.asarray(ds["event"], dtype=np.float32)
+        windows.append({"start_index": start, "step": step, "seg_length": seg, "n_windows": int(event.shape[0]),
+                        "event_length": [int(v) for v in ds["event_length"]],
+                        "event_sha256": hashlib.sha256(np.ascontiguousarray(event).tobytes()).hexdigest(),
+                        "first_window_head": [float(v) for v in event[0, :8]], "last_window_sum": float(event[-1].sum())})
+    fixture["read_data_for_eval"] = {"file": "tests/golden/DNA/raw/read1.signal", "sig_norm": None, "cases": windows}
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     with open(OUT, "w") as f:
         json.dump(fixture, f, indent=0)
