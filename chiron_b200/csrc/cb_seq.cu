@@ -51,12 +51,10 @@ int cb_launch_beam(cb_handle* h, const float* logits, const int32_t* lens, int B
         const bool staged = getenv("CB_BEAM_STAGE_LOGITS") ? atoi(getenv("CB_BEAM_STAGE_LOGITS")) != 0 : one_wave;
         const size_t stride = beam_warp_stride(T, C, W, (int)pool_s, staged);
         if (smem_env && stride * BEAM_WARPS <= 200 * 1024) {
-            static bool attr_set = false;
-            if (!attr_set) {
-                CB_CUDA(cudaFuncSetAttribute(beam_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                CB_CUDA(cudaFuncSetAttribute(beam_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                attr_set = true;
-            }
+            // per launch, like the recurrence launchers: the attribute belongs to the current device's copy of the kernel, so
+            // a process-wide "already set" flag would miss every GPU but the first in a one-process multi-GPU host
+            if (staged) CB_CUDA(cudaFuncSetAttribute(beam_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            else CB_CUDA(cudaFuncSetAttribute(beam_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             CB_CUDA(cudaMemsetAsync(h->d_flag, 0, sizeof(int), s));
             const dim3 grid((B + BEAM_WARPS - 1) / BEAM_WARPS);
             if (staged)
