@@ -356,3 +356,25 @@ def test_assembly_kernels_reproduce_the_reference_fixtures(emu):
             covered = ref_cons.sum(axis=0) > 0
             got_q = bytes(qual[:ln]).decode("latin-1")
             assert [c for c, ok in zip(got_q, covered) if ok] == [c for c, ok in zip(case["quality"], covered) if ok]
+
+
+def test_kernels_are_race_free_under_thread_sanitizer():
+    """tests/cuda_emu/race_check.cpp: every SIMT kernel of the library (fp32 conv stack in both BatchNorm modes with and
+    without stem, LSTM / GRU recurrences, head, path_prob, seq_len, greedy, the three beam-search kernels, the five assembly
+    kernels) run under the host emulation with -fsanitize=thread.  The emulation's only synchronisation is what the
+    kernel asks for (__syncthreads, __syncwarp, warp collectives, atomics), so a missing barrier -- what compute-sanitizer's
+    racecheck looks for -- is a ThreadSanitizer data race.  A deliberately racy kernel proves the check can fail."""
+    exe = os.path.join(HERE, "cuda_emu", "_build", "race_check")
+    src = os.path.join(HERE, "cuda_emu", "race_check.cpp")
+    deps = [src, SRC, os.path.join(HERE, "cuda_emu", "cuda_emu.h")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)
+                                                                         if f.endswith((".cuh", ".h"))]
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-pthread", "-Wno-unknown-pragmas",
+                               "-o", exe, src])
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=66")
+    control = subprocess.run([exe, "--self-test"], capture_output=True, text=True, env=env, timeout=300)
+    assert control.returncode == 66 and "ThreadSanitizer: data race" in control.stderr, "the race check cannot detect a race"
+    run = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=900)
+    assert "ThreadSanitizer" not in run.stderr, run.stderr[:4000]
+    assert run.returncode == 0 and "race_check:" in run.stdout, (run.returncode, run.stdout[-500:], run.stderr[-2000:])
