@@ -378,3 +378,20 @@ def test_kernels_are_race_free_under_thread_sanitizer():
     run = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=900)
     assert "ThreadSanitizer" not in run.stderr, run.stderr[:4000]
     assert run.returncode == 0 and "race_check:" in run.stdout, (run.returncode, run.stdout[-500:], run.stderr[-2000:])
+
+
+def test_kernels_are_memory_clean_under_address_sanitizer():
+    """The same driver built with -fsanitize=address,undefined: global buffers are heap vectors and __shared__ arrays are
+    statics with redzones, so an out-of-bounds or misaligned access of a kernel (compute-sanitizer memcheck's findings)
+    aborts the run."""
+    exe = os.path.join(HERE, "cuda_emu", "_build", "mem_check")
+    src = os.path.join(HERE, "cuda_emu", "race_check.cpp")
+    deps = [src, SRC, os.path.join(HERE, "cuda_emu", "cuda_emu.h")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)
+                                                                         if f.endswith((".cuh", ".h"))]
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                               "-pthread", "-Wno-unknown-pragmas", "-o", exe, src])
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert run.returncode == 0 and "race_check:" in run.stdout, (run.returncode, run.stderr[-3000:])
+    assert "ERROR: AddressSanitizer" not in run.stderr and "runtime error" not in run.stderr, run.stderr[:3000]
