@@ -60,7 +60,8 @@ def _worker(job):
                 raise ValueError("Got empty raw signal")
             stem = read_id if (idname and read_id) else os.path.splitext(name)[0] + suffix
             with open(os.path.join(raw_folder, stem + ".signal"), "w+") as f:
-                f.write(delimiter.join(str(v) for v in sig.tolist()))
+                # single-read files use FLAGS.delimiter (:133-134), the multi-read branch a blank (:145-146)
+                f.write((" " if suffix else delimiter).join(str(v) for v in sig.tolist()))
             n += 1
         return n
     except Exception as e:                       # extract_sig_ref.py:115-117: log and skip the file

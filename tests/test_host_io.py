@@ -217,3 +217,49 @@ def test_read_sharding_of_the_host_pipeline_with_a_stub_gpu(tmp_path, monkeypatc
         assert os.path.exists(os.path.join(out, "meta", "all.rank%d.meta" % rank))
     assert done[0] | done[1] == {"r%02d" % i for i in range(9)} and not (done[0] & done[1])
     assert 3 <= len(done[0]) <= 6                                    # balanced by file size (shard.assign_reads)
+
+
+def test_multi_read_and_single_read_fast5_layouts(tmp_path):
+    """The multi-read layout ``read_*/Raw/Signal`` (extract_sig_ref.py:137-150,178-193) and the single-read layout with
+    ``read_id`` / ``channel_id`` attributes, on files synthesised by tests/h5_writer.py (the bundled examples are all
+    single-read without read_id): reader, extraction file names and separators, pA conversion, RNA reversal."""
+    from h5_writer import write_multi_read_fast5, write_single_read_fast5
+    from chiron_b200.utils.extract_sig_ref import extract, extract_file
+    rng = np.random.default_rng(3)
+    reads = {"read_%s" % k: (rng.integers(200, 900, size=n).astype(np.int16), rid)
+             for k, n, rid in (("0a1b", 57, "id-a"), ("77ff", 64, None), ("c0de", 31, "id-c"))}
+    src = tmp_path / "in"
+    src.mkdir()
+    write_multi_read_fast5(str(src / "batch0.fast5"), reads)
+    chan = {"offset": np.float64(3.0), "range": np.float64(1400.5), "digitisation": np.float64(8192.0),
+            "sampling_rate": np.float64(4000.0)}
+    single = rng.integers(200, 900, size=45).astype(np.int16)
+    write_single_read_fast5(str(src / "lone.fast5"), single, read_number=12, read_id="id-lone", channel=chan)
+
+    got = fast5.read_fast5(str(src / "batch0.fast5"))
+    assert [r["read_key"] for r in got] == sorted(reads)
+    for r in got:
+        assert np.array_equal(r["signal"], reads[r["read_key"]][0]) and r["read_id"] == reads[r["read_key"]][1]
+    lone = fast5.read_fast5(str(src / "lone.fast5"))
+    assert len(lone) == 1 and lone[0]["read_key"] == "Read_12" and lone[0]["read_id"] == "id-lone"
+    assert lone[0]["channel"]["digitisation"] == 8192.0 and np.array_equal(fast5.read_raw_signal(str(src / "lone.fast5")), single)
+    # unit=True: (raw + offset) * range / digitisation (extract_sig_ref.py:158-163); rna mode reverses
+    (_, pa, _), = extract_file(str(src / "lone.fast5"), mode="dna", unit=True)
+    np.testing.assert_allclose(pa, (single + 3.0) * 1400.5 / 8192.0)
+    (_, rev, _), = extract_file(str(src / "lone.fast5"), mode="rna")
+    assert np.array_equal(rev, single[::-1])
+
+    flags = types.SimpleNamespace(input_dir=str(src), output_dir=str(tmp_path / "out"), unit=False, recursive=True, mode="dna",
+                                  delimiter="\n", idname=False, threads=1, test_number=None)
+    assert extract(flags) == 4
+    raw = tmp_path / "out" / "raw"
+    assert sorted(os.listdir(str(raw))) == sorted(["batch0%s.signal" % k for k in reads] + ["lone.signal"])
+    for k, (sig, _) in reads.items():
+        text = (raw / ("batch0%s.signal" % k)).read_text()
+        assert text == " ".join(str(v) for v in sig.tolist())               # the multi-read branch joins with blanks
+        assert np.array_equal(chiron_input.read_signal(str(raw / ("batch0%s.signal" % k))), sig.astype(np.float32))
+    assert (raw / "lone.signal").read_text() == "\n".join(str(v) for v in single.tolist())
+    flags.idname, flags.output_dir = True, str(tmp_path / "out2")
+    assert extract(flags) == 4                                              # read_id names where present, file names otherwise
+    assert sorted(os.listdir(str(tmp_path / "out2" / "raw"))) == sorted(
+        ["id-a.signal", "batch0read_77ff.signal", "id-c.signal", "id-lone.signal"])
