@@ -17,4 +17,14 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm
     python tools/gpu_quick.py tc 4096 512 > $out/ncu_gemm.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm_tc_kernel -s 3 -c 3 -f -o $out/prof_lstm \
     python tools/gpu_quick.py tc 4096 512 > $out/ncu_lstm.log 2>&1
+# batch-statistics BatchNorm kernels: fp32 forward in both BN modes + ncu launch list with DRAM bytes (tools/ncu_bn_summary.py)
+timeout 60 python tools/bn_bench.py 1024 512 3 > $out/bn_bench.json 2> $out/bn_bench.err
+timeout 120 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+    -k regex:bn_ --csv --log-file $out/bn_kernels.csv python tools/bn_bench.py 1024 512 1 > $out/bn_ncu.log 2>&1
+# `chiron call` on files -> fastq (and the host pipeline alone), beam-search variants
+timeout 90 python tools/call_bench.py --reads 800 --fmt signal > $out/call_signal.json 2> $out/call_signal.err
+timeout 90 python tools/call_bench.py --reads 800 --fmt fast5 > $out/call_fast5.json 2> $out/call_fast5.err
+timeout 90 python tools/call_bench.py --reads 800 --fmt signal --beam 30 > $out/call_signal_beam30.json 2> $out/call_signal_beam30.err
+timeout 90 python tools/call_bench.py --reads 800 --fmt signal --stub > $out/call_signal_stub.json 2> $out/call_signal_stub.err
+timeout 120 python tools/experiments/beam_stage_ab.py > $out/beam_stage_ab.jsonl 2> $out/beam_stage_ab.err
 ls -la $out
