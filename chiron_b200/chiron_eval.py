@@ -261,45 +261,57 @@ def evaluation(flags=None, caller: Optional[Basecaller] = None) -> Dict[str, dic
 
     pool = ThreadPoolExecutor(max_workers=n_readers, thread_name_prefix="chiron-reader")
     lookahead = 2 * n_readers
-    futures = collections.deque(pool.submit(load, n) for n in file_list[:lookahead])
-    for idx, name in enumerate(file_list):
-        eval_data, start_time, reading_time = futures.popleft().result()
-        if idx + lookahead < len(file_list):
-            futures.append(pool.submit(load, file_list[idx + lookahead]))
-        st = _ReadState(name, eval_data.reads_n, T, start_time, reading_time, getattr(eval_data, "samples", 0))
-        open_reads.append(st)
-        i = 0
-        if eval_data.reads_n == 0:
-            continue
-        while eval_data.epochs_completed == 0:
-            cur_x, cur_len, _ = eval_data.next_batch(B - pend_n, shuffle=False)
-            cnt = len(cur_x)
-            pend_x.append(cur_x)
-            pend_len.append(cur_len)
-            pend_owner.append((st, i, cnt))
-            pend_n += cnt
-            i += cnt
-            if pend_n >= B:
-                flush()
-    flush()
-    while inflight:
-        collect_oldest()
-    while open_reads:                                            # reads with zero windows
-        finish(open_reads.pop(0))
-    pool.shutdown(wait=True)
-    if use_finisher:
-        finish_q.put(None)
-        finisher_thread.join()
+    failed = True
+    try:
+        futures = collections.deque(pool.submit(load, n) for n in file_list[:lookahead])
+        for idx, name in enumerate(file_list):
+            eval_data, start_time, reading_time = futures.popleft().result()
+            if idx + lookahead < len(file_list):
+                futures.append(pool.submit(load, file_list[idx + lookahead]))
+            st = _ReadState(name, eval_data.reads_n, T, start_time, reading_time, getattr(eval_data, "samples", 0))
+            open_reads.append(st)
+            i = 0
+            if eval_data.reads_n == 0:
+                continue
+            while eval_data.epochs_completed == 0:
+                cur_x, cur_len, _ = eval_data.next_batch(B - pend_n, shuffle=False)
+                cnt = len(cur_x)
+                pend_x.append(cur_x)
+                pend_len.append(cur_len)
+                pend_owner.append((st, i, cnt))
+                pend_n += cnt
+                i += cnt
+                if pend_n >= B:
+                    flush()
+        flush()
+        while inflight:
+            collect_oldest()
+        while open_reads:                                            # reads with zero windows
+            finish(open_reads.pop(0))
+        failed = False
+    finally:
+        # Wind the helper threads down on every path: an exception (unreadable input, a CUDA error) must surface with no
+        # reader / finisher / writer thread and no GPU handle left behind when evaluation() is used as a library call.
+        pool.shutdown(wait=True, cancel_futures=True)
+        if failed:
+            while inflight:                                          # slots must be collected before the handle goes
+                try:
+                    caller.basecall_collect(inflight.popleft()[0])
+                except Exception:
+                    pass
+        if use_finisher:
+            finish_q.put(None)
+            finisher_thread.join()
+        for _ in writer_threads:
+            write_q.put(None)
+        for t in writer_threads:
+            t.join()
+        if own:
+            caller.close()
     if finish_err:
-        write_err.insert(0, finish_err[0])
-    for _ in writer_threads:
-        write_q.put(None)
-    for t in writer_threads:
-        t.join()
+        raise finish_err[0]
     if write_err:
         raise write_err[0]
-    if own:
-        caller.close()
     return summary
 
 

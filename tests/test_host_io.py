@@ -1,5 +1,6 @@
 """CPU tests of the host-side I/O mirror: HDF5/fast5 reader, extraction, normalisation, windowing, sharding."""
 import os
+import time
 import types
 
 import numpy as np
@@ -263,3 +264,30 @@ def test_multi_read_and_single_read_fast5_layouts(tmp_path):
     assert extract(flags) == 4                                              # read_id names where present, file names otherwise
     assert sorted(os.listdir(str(tmp_path / "out2" / "raw"))) == sorted(
         ["id-a.signal", "batch0read_77ff.signal", "id-c.signal", "id-lone.signal"])
+
+
+def test_unreadable_input_fails_loudly_and_promptly(tmp_path, monkeypatch):
+    """A signal file with a token that is not a number stops the run with the library's error (the reference's reader
+    raises ValueError from float() at the same place) instead of hanging the reader / finisher / writer threads."""
+    import shutil
+    import sys
+    import threading
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "tools"))
+    from call_bench import StubCaller
+    from chiron_b200 import _lib, chiron_eval
+    src = tmp_path / "in"
+    src.mkdir()
+    shutil.copy(os.path.join(GOLDEN, "DNA", "raw", "read1.signal"), str(src / "a.signal"))
+    (src / "b.signal").write_text("487 421 4x3 438\n")
+    shutil.copy(os.path.join(GOLDEN, "DNA", "raw", "read1.signal"), str(src / "c.signal"))
+    monkeypatch.setattr(chiron_eval, "Basecaller", lambda model, device=0, precision="fp32": StubCaller(model))
+    args = types.SimpleNamespace(input=str(src), output=str(tmp_path / "out"), model="DNA_default", start=None, batch_size=None,
+                                 segment_len=None, jump=None, threads=2, beam=0, extension="fastq", concise=False, mode="dna",
+                                 preset="dna-pre", precision="fp32", recursive=False)
+    before = threading.active_count()
+    with pytest.raises(_lib.ChironB200Error, match="4x3"):
+        chiron_eval.run(apply_preset(args))
+    deadline = time.time() + 10
+    while threading.active_count() > before and time.time() < deadline:
+        time.sleep(0.05)
+    assert threading.active_count() <= before, "worker threads were left behind"
