@@ -9,7 +9,8 @@ from __future__ import annotations
 import logging
 import os
 import shutil
-from multiprocessing import Pool, cpu_count
+import multiprocessing
+from multiprocessing import cpu_count
 
 import numpy as np
 
@@ -101,8 +102,10 @@ def extract(FLAGS) -> int:
     if limit is not None:
         jobs = jobs[:limit]
     if threads > 1 and len(jobs) > 1:
-        with Pool(min(threads, len(jobs))) as pool:
-            counts = pool.map(_worker, jobs)
+        # "spawn", not the reference's default fork (extract_sig_ref.py:83-90): by the time a long-lived caller extracts, the
+        # process may hold CUDA state and the pipeline's helper threads, and forking such a process can deadlock the children
+        with multiprocessing.get_context("spawn").Pool(min(threads, len(jobs))) as pool:
+            counts = pool.map(_worker, jobs, chunksize=max(1, len(jobs) // (8 * threads)))
     else:
         counts = [_worker(j) for j in jobs]
     FLAGS.count = int(sum(counts))

@@ -260,7 +260,7 @@ def test_multi_read_and_single_read_fast5_layouts(tmp_path):
         assert text == " ".join(str(v) for v in sig.tolist())               # the multi-read branch joins with blanks
         assert np.array_equal(chiron_input.read_signal(str(raw / ("batch0%s.signal" % k))), sig.astype(np.float32))
     assert (raw / "lone.signal").read_text() == "\n".join(str(v) for v in single.tolist())
-    flags.idname, flags.output_dir = True, str(tmp_path / "out2")
+    flags.idname, flags.output_dir, flags.threads = True, str(tmp_path / "out2"), 2      # two spawned worker processes
     assert extract(flags) == 4                                              # read_id names where present, file names otherwise
     assert sorted(os.listdir(str(tmp_path / "out2" / "raw"))) == sorted(
         ["id-a.signal", "batch0read_77ff.signal", "id-c.signal", "id-lone.signal"])
