@@ -291,3 +291,31 @@ def test_unreadable_input_fails_loudly_and_promptly(tmp_path, monkeypatch):
     while threading.active_count() > before and time.time() < deadline:
         time.sleep(0.05)
     assert threading.active_count() <= before, "worker threads were left behind"
+
+
+def test_chiron_call_cli_from_fast5_with_a_stub_gpu(tmp_path, monkeypatch):
+    """`chiron call` (entry.main) end to end on the CPU: fast5 folder (a bundled single-read file and a synthesised multi-read
+    file) -> raw/*.signal -> result / segments / meta, with the GPU stubbed out."""
+    import shutil
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "tools"))
+    from call_bench import StubCaller
+    from h5_writer import write_multi_read_fast5
+    from chiron_b200 import chiron_eval, entry
+    src = tmp_path / "in"
+    src.mkdir()
+    shutil.copy(os.path.join(GOLDEN, "fast5", "read1.fast5"), str(src / "read1.fast5"))
+    rng = np.random.default_rng(4)
+    write_multi_read_fast5(str(src / "multi.fast5"), {"read_%02d" % i: (rng.integers(300, 800, size=900 + 400 * i).astype(np.int16),
+                                                                       "uuid-%d" % i) for i in range(3)})
+    monkeypatch.setattr(chiron_eval, "Basecaller", lambda model, device=0, precision="fp32": StubCaller(model))
+    out = str(tmp_path / "out")
+    entry.main(["call", "-i", str(src), "-o", out, "-p", "dna-pre", "--beam", "0", "-t", "2"])
+    reads = ["multiread_00", "multiread_01", "multiread_02", "read1"]
+    assert sorted(os.listdir(os.path.join(out, "raw"))) == [r + ".signal" for r in reads]
+    assert sorted(os.listdir(os.path.join(out, "result"))) == [r + ".fastq" for r in reads]
+    assert np.array_equal(chiron_input.read_signal(os.path.join(out, "raw", "read1.signal")),
+                          chiron_input.read_signal(os.path.join(GOLDEN, "DNA", "raw", "read1.signal")))
+    meta = open(os.path.join(out, "meta", "multiread_02.meta")).read().split("\n")
+    assert meta[2] == "# read_len batch_size segment_len jump start_pos" and meta[3].split()[1:] == ["400", "400", "390", "0"]
+    assert os.path.exists(os.path.join(out, "meta", "all.meta")) and os.path.exists(os.path.join(out, "log", "extract.log"))
