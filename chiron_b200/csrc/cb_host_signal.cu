@@ -84,6 +84,11 @@ extern "C" int cb_host_normalize(const float* in, size_t n, int mode, float* out
     if ((!in || !out) && n) { cb_set_error("cb_host_normalize: bad arguments"); return CB_ERR_ARG; }
     if (mode < 0 || mode > 2) { cb_set_error("cb_host_normalize: unknown signal normalisation %d", mode); return CB_ERR_ARG; }
     if (mode == 0 || n == 0) { if (out != in && n) memmove(out, in, n * sizeof(float)); return CB_OK; }
+    for (size_t i = 0; i < n; ++i)
+        if (in[i] != in[i]) {                        // a NaN sample: np.median is NaN, so every output is (sorting NaNs is undefined)
+            for (size_t j = 0; j < n; ++j) out[j] = NAN;
+            return CB_OK;
+        }
     std::vector<double> ref;
     if (mode == 1) {                                 // statistics over the UNIQUE sample values (chiron_input.py:548)
         bool integral = true;

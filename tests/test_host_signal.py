@@ -137,3 +137,16 @@ def test_segment_records_match_the_reference_format(n, T, seed, name):
     kept = [index2base(bases[i, :n_bases[i]]) for i in range(n) if n_bases[i] > 0]      # sparse2dense drops empty rows
     ref = "".join(">{}{}\n{}\n".format(name, str(i), r) for i, r in enumerate(kept)).encode("utf-8")
     assert format_segments(name, bases, n_bases) == ref
+
+
+def test_nan_and_inf_samples_normalise_like_numpy():
+    base = np.array([3, 7, 7, 1, 9, 4], dtype=np.float32)
+    for bad in (np.nan, np.inf, -np.inf):
+        s = base.copy()
+        s[2] = bad
+        for mode in (NORM_UNIQUE_MAD, NORM_FULL_MAD):
+            with np.errstate(all="ignore"):
+                ref = O.normalize_signal(s, mode)
+            got = chiron_input.normalize_signal(s, mode)
+            assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(got[~np.isnan(got)], ref[~np.isnan(ref)])
+    assert np.isnan(chiron_input.parse_signal_text(b"1 nan 3")[1])
