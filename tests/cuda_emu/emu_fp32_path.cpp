@@ -233,3 +233,14 @@ extern "C" int emu_assemble(const int8_t* bases, const int32_t* n_bases, const f
     if (max_len > 0) emu::launch((max_len + 255) / 256, 256, [&] { cb_seq::asm_finish_kernel(w, ml, consensus, qual); });
     return CB_OK;
 }
+
+// One plain contraction out[M,N] = act(A[M,K] @ W[K,N] + shift[N]) through gemm_simt_kernel (the hoisted LSTM input projection).
+extern "C" int emu_gemm(const float* A, int lda, const float* W, const float* shift, int M, int N, int K, int relu, float* out,
+                        int ldo) {
+    GemmProblem g;
+    memset(&g, 0, sizeof(g));
+    g.M = M; g.N = N; g.K = K; g.t_out = M; g.t_in0 = M; g.stride0 = 1; g.taps = 1; g.c0 = K; g.src0 = A; g.lda0 = lda;
+    g.W = W; g.shift = shift; g.relu = relu; g.out = out; g.ldo = ldo;
+    EmuOps ops(1, 4);
+    return ops.gemm(g);
+}

@@ -395,3 +395,65 @@ def test_kernels_are_memory_clean_under_address_sanitizer():
     run = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     assert run.returncode == 0 and "race_check:" in run.stdout, (run.returncode, run.stderr[-3000:])
     assert "ERROR: AddressSanitizer" not in run.stderr and "runtime error" not in run.stderr, run.stderr[:3000]
+
+
+def test_golden_windows_through_the_emulated_kernels(emu, dna_model):
+    """The reference's golden output reproduced on the CPU by the CUDA kernel SOURCES: two windows of the bundled read1
+    signal go through the emulated fp32 kernels end to end -- conv stack (folded population BN), hoisted input projections,
+    the three BiLSTM layers, the logit head, beam search of width 30 -- and must decode to the reference's own
+    segments/read1.fastq records (example_data/DNA/output), with logits within the fp32 tolerance of the oracle."""
+    from conftest import GOLDEN, read_fasta_records
+    cfg, t, _ = dna_model
+    C, H = cfg.channels, cfg.hidden
+    sig = O.read_signal_text(os.path.join(GOLDEN, "DNA", "raw", "read1.signal"))
+    x, lens = O.make_windows(O.normalize_signal(sig, cfg.sig_norm), 400, 390)
+    pick = [0, 160]                                   # the first window and the ragged last one of the read
+    x, lens = np.ascontiguousarray(x[pick]), lens[pick]
+    B, L = x.shape
+    # conv stack with population BN folded exactly as cb_create does
+    ptrs, rank1 = [], []
+    for b in range(cfg.n_blocks):
+        p = "res_layer%d" % (b + 1)
+        has1 = cfg.branch1_bn_mask >> b & 1
+        inv1, sh1 = _fold(t, p + "/branch1/conv1") if has1 else (np.ones(C, np.float32), np.zeros(C, np.float32))
+        inva, sha = _fold(t, p + "/branch2/conv2a")
+        invb, shb = _fold(t, p + "/branch2/conv2b")
+        invc, shc = _fold(t, p + "/branch2/conv2c")
+        w1, w2a = t[p + "/branch1/conv1/weights"], t[p + "/branch2/conv2a/weights"]
+        w2b, w2c = t[p + "/branch2/conv2b/weights"], t[p + "/branch2/conv2c/weights"]
+        if b == 0:
+            rank1 = [w2a.reshape(-1), inva, sha, w1.reshape(-1), inv1, sh1]
+            ptrs += [np.zeros(4, np.float32), np.zeros(4, np.float32), w2b.reshape(-1, C) * invb, shb, w2c * invc, shc]
+        else:
+            ptrs += [w2a * inva, sha, w2b.reshape(-1, C) * invb, shb, np.concatenate([w2c * invc, w1 * inv1]), shc + sh1]
+    fea, _ = _run_stack(emu, 0, cfg, ptrs, rank1, x, 4)
+    T = fea.shape[1]
+    Z = np.ascontiguousarray(fea.reshape(B * T, C))
+    vp = ctypes.c_void_p
+    lens32 = lens.astype(np.int32)
+    for l in range(cfg.n_layers):                     # stacked-bidirectional layout: one projection for both directions
+        D = Z.shape[1]
+        kern = {d: t["lstm/%d/%s/kernel" % (l, d)] for d in ("fw", "bw")}
+        wx = np.ascontiguousarray(np.concatenate([kern["fw"][:D], kern["bw"][:D]], axis=1), dtype=np.float32)
+        bias = np.concatenate([t["lstm/%d/fw/bias" % l], t["lstm/%d/bw/bias" % l]]).astype(np.float32)
+        pre = np.zeros((B * T, 8 * H), np.float32)
+        assert emu.emu_gemm(_fp(Z), D, _fp(wx), _fp(bias), B * T, 8 * H, D, 0, _fp(pre), 8 * H) == 0
+        whh = {d: np.ascontiguousarray(kern[d][D:], dtype=np.float32) for d in kern}
+        out = np.zeros((B * T, 2 * H), np.float32)
+        assert emu.emu_lstm(1, B, T, H, _fp(pre), 8 * H, _fp(whh["fw"]), _fp(whh["bw"]), lens32.ctypes.data_as(vp), _fp(out),
+                            2 * H) == 0
+        Z = out
+    hw = [np.ascontiguousarray(t["rnn_fnn_layer/" + n], dtype=np.float32) for n in ("weights", "bias", "weights_class", "bias_class")]
+    logits = np.zeros((B, T, cfg.n_class), np.float32)
+    assert emu.emu_head(_fp(Z), ctypes.c_longlong(B * T), H, cfg.n_class, _fp(hw[0]), _fp(hw[1]), _fp(hw[2]), _fp(hw[3]),
+                        _fp(logits), 4) == 0
+    ref = O.inference(x, lens, cfg, t)
+    assert np.abs(logits - ref).max() < 2e-3
+    W = 30
+    bases = np.zeros((B, T), np.int8)
+    n_bases = np.zeros(B, np.int32)
+    assert emu.emu_beam(1, _fp(logits), lens32.ctypes.data_as(vp), B, T, cfg.n_class, W, 2 * W * (T + 1) + 2,
+                        bases.ctypes.data_as(vp), n_bases.ctypes.data_as(vp)) == 0
+    golden = read_fasta_records(os.path.join(GOLDEN, "DNA", "segments", "read1.fastq"))
+    assert len(golden) == 161
+    assert [O.index2base(bases[i, :n_bases[i]]) for i in range(B)] == [golden[k] for k in pick]
