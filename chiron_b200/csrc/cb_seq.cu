@@ -33,24 +33,22 @@ int cb_launch_beam(cb_handle* h, const float* logits, const int32_t* lens, int B
     // a leaf or of a current branch); that size is used for a retry if the small pool ever proves too small.
     const long long cap = 2LL * W * (T + 1) + 2;
     {   // fast path: warp per window over shared memory with a small, frequently compacted pool
-        long long pool_s = 6LL * W;
-        if (pool_s < 2LL * W + 2) pool_s = 2LL * W + 2;
-        if (pool_s < 64) pool_s = 64;
-        if (pool_s > cap) pool_s = cap;
+        const long long pool_s = beam_small_pool(T, W);
         const int smem_env = getenv("CB_BEAM_SMEM") ? atoi(getenv("CB_BEAM_SMEM")) : 1;    // 0: force the fallback kernel (tests)
         // Two variants of the same search (bit-identical outputs).  Staging a window's logits in shared memory saves the
-        // per-frame global row read (3-5 % when every window is resident anyway: 400 x 400 beam 30 3.51 vs 3.61 ms, RNA
-        // 512 x 500 beam 50 1.74 vs 1.82 ms) but doubles the footprint; reading the rows from global memory (prefetched a
-        // frame ahead) keeps 5 instead of 2 CTAs resident per SM at T=512, W=30 and wins as soon as the windows do not fit
-        // in one wave (4096 x 512 beam 30: 18.3 -> 10.3 ms).  So: stage iff the staged launch is a single wave.
+        // per-frame global row read (3-5 % when every window is resident anyway) but enlarges the footprint; reading the
+        // rows from global memory (prefetched a frame ahead) keeps more CTAs resident per SM and wins as soon as the windows
+        // do not fit in one wave.  So: stage iff the staged launch fits the budget and is a single wave.
         // CB_BEAM_STAGE_LOGITS=0/1 forces a variant (tests, A/B).
         const size_t stride_staged = beam_warp_stride(T, C, W, (int)pool_s, true);
+        const bool staged_fits = (long long)(stride_staged * BEAM_WARPS) <= BEAM_SMEM_BUDGET + 4096;
         const long long n_ctas = (B + BEAM_WARPS - 1) / BEAM_WARPS;
         const long long staged_ctas_per_sm = (227LL * 1024) / (long long)(stride_staged * BEAM_WARPS + 1024);
         const bool one_wave = n_ctas <= (long long)(h->sm_count > 0 ? h->sm_count : 148) * staged_ctas_per_sm;
-        const bool staged = getenv("CB_BEAM_STAGE_LOGITS") ? atoi(getenv("CB_BEAM_STAGE_LOGITS")) != 0 : one_wave;
+        const bool want_staged = getenv("CB_BEAM_STAGE_LOGITS") ? atoi(getenv("CB_BEAM_STAGE_LOGITS")) != 0 : one_wave;
+        const bool staged = want_staged && staged_fits;
         const size_t stride = beam_warp_stride(T, C, W, (int)pool_s, staged);
-        if (smem_env && stride * BEAM_WARPS <= 200 * 1024) {
+        if (smem_env && pool_s >= 2LL * W + 2 && stride * BEAM_WARPS <= 200 * 1024) {
             // per launch, like the recurrence launchers: the attribute belongs to the current device's copy of the kernel, so
             // a process-wide "already set" flag would miss every GPU but the first in a one-process multi-GPU host
             if (staged) CB_CUDA(cudaFuncSetAttribute(beam_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

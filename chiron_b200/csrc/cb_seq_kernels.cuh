@@ -432,4 +432,23 @@ inline size_t beam_warp_stride(int T, int C, int W, int pool, bool staged) {
     return align_up((staged ? align_up((size_t)T * C * 4, 16) : 0) + cb_beam_work_bytes(W, pool), 16);
 }
 
+// Node pool of the shared-memory beam search.  Live nodes are the ancestors of the W leaves and of the current branches.  On
+// real logits a pool of 6W nodes is far too small: of the reference's chiron/utils/logits_sample.npy (1100 windows, T=300) only
+// 55 % of the windows fit 6W at W=30, 99.3 % fit 12W and all fit 16W; of 64 oracle-basecalled T=512 windows of the bundled
+// read3, 27 % fit 6W and all fit 16W (2 of them only just).  One overflowing window sends the WHOLE batch to the
+// thread-per-window fallback kernel (ten times slower), and a batch holds thousands of windows, so the pool is sized for the
+// tail, not the median: 24W nodes, bounded by what four windows can hold in 192 KB of shared memory (wide beams get fewer
+// nodes per beam and lean on the in-place compaction) and by the never-overflows bound.  Occupancy pays for it (one or two
+// CTAs per SM instead of five at W=30); the search stays correct either way.
+constexpr long long BEAM_SMEM_BUDGET = 192 * 1024;          // of the 200 KB the launcher opts in to
+inline long long beam_small_pool(int T, int W) {
+    const long long cap = 2LL * W * (T + 1) + 2;
+    long long pool = 24LL * W;
+    const long long fit = (BEAM_SMEM_BUDGET / BEAM_WARPS - 12LL * 4 * W - 16) / (long long)(sizeof(CbBeamNode) + sizeof(int));
+    if (pool > fit) pool = fit;
+    if (pool < 64 && fit >= 64) pool = 64;
+    if (pool > cap) pool = cap;
+    return pool;                                   // usable iff >= 2W + 2
+}
+
 }  // namespace cb_seq

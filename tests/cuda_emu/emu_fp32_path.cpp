@@ -244,3 +244,6 @@ extern "C" int emu_gemm(const float* A, int lda, const float* W, const float* sh
     EmuOps ops(1, 4);
     return ops.gemm(g);
 }
+
+// The node pool cb_launch_beam gives the shared-memory beam search (cb_seq_kernels.cuh: beam_small_pool).
+extern "C" long long emu_beam_small_pool(int T, int W) { return cb_seq::beam_small_pool(T, W); }

@@ -37,6 +37,7 @@ def emu():
     lib.emu_bn_rank1.restype = ctypes.c_int
     lib.emu_gru.restype = ctypes.c_int
     lib.emu_lstm.restype = ctypes.c_int
+    lib.emu_beam_small_pool.restype = ctypes.c_longlong
     return lib
 
 
@@ -457,3 +458,48 @@ def test_golden_windows_through_the_emulated_kernels(emu, dna_model):
     golden = read_fasta_records(os.path.join(GOLDEN, "DNA", "segments", "read1.fastq"))
     assert len(golden) == 161
     assert [O.index2base(bases[i, :n_bases[i]]) for i in range(B)] == [golden[k] for k in pick]
+
+
+def test_decoders_on_the_reference_logits_sample(emu):
+    """chiron/utils/logits_sample.npy (the reference's sample of real CTC logits; 24 of its 1100 windows are kept under
+    tests/golden/logits): greedy and beam-search kernels (width 30 and 50, as the presets and the README use) under emulation
+    against the C oracle, and the C oracle against the Python restatement of TF's decoder on a few windows."""
+    lg = np.load(os.path.join(os.path.dirname(HERE), "tests", "golden", "logits", "logits_sample_24.npy"))
+    B, T, C = lg.shape
+    assert (B, T, C) == (24, 300, 5) and lg.dtype == np.float32
+    rng = np.random.default_rng(2)
+    lens = np.full(B, T, np.int32)
+    lens[::5] = rng.integers(1, T, size=len(lens[::5]))
+    vp = ctypes.c_void_p
+    bases = np.zeros((B, T), np.int8)
+    n_bases = np.zeros(B, np.int32)
+    assert emu.emu_greedy(_fp(lg), lens.ctypes.data_as(vp), B, T, C, bases.ctypes.data_as(vp), n_bases.ctypes.data_as(vp)) == 0
+    greedy = [bases[b, :n_bases[b]].tolist() for b in range(B)]
+    assert greedy == O.ctc_greedy(lg, lens) == O.ctc_decode_c(lg, lens, 0)
+    assert 10 < np.mean([len(g) for g in greedy]) < 40              # ~20 bases per 300-sample window on real data
+    from chiron_b200 import _lib
+    lib = _lib.load()
+    out = np.zeros(T, np.int8)
+    sub = [0, 5, 9, 14, 20, 23]                        # emulation is slow: six windows go through the kernels ...
+    for W in (30, 50):
+        ref = O.ctc_decode_c(lg, lens, W)
+        pool = emu.emu_beam_small_pool(T, W)           # the launcher's pool: no window of real logits may overflow it
+        assert pool == (24 * W if W == 30 else 898)    # 24W, or what four windows can hold in 192 KB of shared memory
+        small = 0
+        for b in range(B):                             # ... and all 24 through the same search, host-compiled (cb_selftest_beam)
+            row = np.ascontiguousarray(lg[b])
+            n = lib.cb_selftest_beam(row.ctypes.data_as(vp), int(lens[b]), C, W, pool, out.ctypes.data_as(vp))
+            assert n >= 0 and out[:n].tolist() == ref[b], (W, b, n)
+            small += lib.cb_selftest_beam(row.ctypes.data_as(vp), int(lens[b]), C, W, 6 * W, out.ctypes.data_as(vp)) == -2
+        assert small >= 3                              # why the pool is not 6W: real logits overflow it regularly
+        lg_s, lens_s = np.ascontiguousarray(lg[sub]), np.ascontiguousarray(lens[sub])
+        for warp in ((1, 2) if W == 30 else (1,)):
+            bases[:] = 9
+            assert emu.emu_beam(warp, _fp(lg_s), lens_s.ctypes.data_as(vp), len(sub), T, C, W, pool, bases.ctypes.data_as(vp),
+                                n_bases.ctypes.data_as(vp)) == 0
+            assert [bases[i, :n_bases[i]].tolist() for i in range(len(sub))] == [ref[b] for b in sub], (W, warp)
+    for b in (0, 7, 23):
+        assert O.ctc_beam_search_one(lg[b], int(lens[b]), 30) == O.ctc_decode_c(lg[b:b + 1], lens[b:b + 1], 30)[0]
+    # wide beams get what four windows can hold in the shared-memory budget, never less than the algorithm's minimum
+    assert 2 * 100 + 2 <= emu.emu_beam_small_pool(150, 100) < 24 * 100
+    assert emu.emu_beam_small_pool(3, 30) == 2 * 30 * 4 + 2 and emu.emu_beam_small_pool(300, 1) == 64
