@@ -437,16 +437,24 @@ inline size_t beam_warp_stride(int T, int C, int W, int pool, bool staged) {
 // 55 % of the windows fit 6W at W=30, 99.3 % fit 12W and all fit 16W; of 64 oracle-basecalled T=512 windows of the bundled
 // read3, 27 % fit 6W and all fit 16W (2 of them only just).  One overflowing window sends the WHOLE batch to the
 // thread-per-window fallback kernel (ten times slower), and a batch holds thousands of windows, so the pool is sized for the
-// tail, not the median: 24W nodes, bounded by what four windows can hold in 192 KB of shared memory (wide beams get fewer
-// nodes per beam and lean on the in-place compaction) and by the never-overflows bound.  Occupancy pays for it (one or two
+// tail, not the median: at least 24W nodes, grown into whatever shared memory the resulting CTAs-per-SM leaves unused,
+// bounded by what four windows can hold in 192 KB (wide beams get fewer nodes per beam and lean on the in-place
+// compaction) and by the never-overflows bound.  Occupancy pays for it (one or two
 // CTAs per SM instead of five at W=30); the search stays correct either way.
 constexpr long long BEAM_SMEM_BUDGET = 192 * 1024;          // of the 200 KB the launcher opts in to
 inline long long beam_small_pool(int T, int W) {
     const long long cap = 2LL * W * (T + 1) + 2;
+    const long long node = (long long)(sizeof(CbBeamNode) + sizeof(int)), fixed = 12LL * 4 * W + 16;
     long long pool = 24LL * W;
-    const long long fit = (BEAM_SMEM_BUDGET / BEAM_WARPS - 12LL * 4 * W - 16) / (long long)(sizeof(CbBeamNode) + sizeof(int));
+    const long long fit = (BEAM_SMEM_BUDGET / BEAM_WARPS - fixed) / node;
     if (pool > fit) pool = fit;
     if (pool < 64 && fit >= 64) pool = 64;
+    // nodes are free up to the next occupancy step: grow the pool into the slack of the CTAs-per-SM it already costs
+    const long long ctas = (227LL * 1024) / ((node * pool + fixed) * BEAM_WARPS + 1024);
+    if (ctas >= 1) {
+        const long long grown = (((227LL * 1024) / ctas - 1024) / BEAM_WARPS - fixed) / node;
+        if (grown > pool) pool = grown < fit ? grown : fit;
+    }
     if (pool > cap) pool = cap;
     return pool;                                   // usable iff >= 2W + 2
 }

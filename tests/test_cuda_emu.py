@@ -484,7 +484,7 @@ def test_decoders_on_the_reference_logits_sample(emu):
     for W in (30, 50):
         ref = O.ctc_decode_c(lg, lens, W)
         pool = emu.emu_beam_small_pool(T, W)           # the launcher's pool: no window of real logits may overflow it
-        assert pool == (24 * W if W == 30 else 898)    # 24W, or what four windows can hold in 192 KB of shared memory
+        assert pool == (917 if W == 30 else 898) and pool >= 16 * W    # what four windows can hold in 192 KB of shared memory
         small = 0
         for b in range(B):                             # ... and all 24 through the same search, host-compiled (cb_selftest_beam)
             row = np.ascontiguousarray(lg[b])
@@ -502,4 +502,4 @@ def test_decoders_on_the_reference_logits_sample(emu):
         assert O.ctc_beam_search_one(lg[b], int(lens[b]), 30) == O.ctc_decode_c(lg[b:b + 1], lens[b:b + 1], 30)[0]
     # wide beams get what four windows can hold in the shared-memory budget, never less than the algorithm's minimum
     assert 2 * 100 + 2 <= emu.emu_beam_small_pool(150, 100) < 24 * 100
-    assert emu.emu_beam_small_pool(3, 30) == 2 * 30 * 4 + 2 and emu.emu_beam_small_pool(300, 1) == 64
+    assert emu.emu_beam_small_pool(3, 30) == 2 * 30 * 4 + 2 and 64 <= emu.emu_beam_small_pool(300, 1) <= 128
