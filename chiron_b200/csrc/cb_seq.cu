@@ -33,7 +33,12 @@ int cb_launch_beam(cb_handle* h, const float* logits, const int32_t* lens, int B
     // a leaf or of a current branch); that size is used for a retry if the small pool ever proves too small.
     const long long cap = 2LL * W * (T + 1) + 2;
     {   // fast path: warp per window over shared memory with a small, frequently compacted pool
-        const long long pool_s = beam_small_pool(T, W);
+        // CB_BEAM_RETRY=1 (experimental, not yet run on a GPU): a small first-pass pool at high occupancy + a one-window-per-CTA
+        // second pass for the windows that overflow it, instead of a first-pass pool sized for the tail.
+        const bool retry = getenv("CB_BEAM_RETRY") && atoi(getenv("CB_BEAM_RETRY")) != 0;
+        long long pool_first = beam_small_pool(T, W);
+        if (retry && 8LL * W >= 64 && 8LL * W < pool_first) pool_first = 8LL * W;
+        const long long pool_s = pool_first;
         const int smem_env = getenv("CB_BEAM_SMEM") ? atoi(getenv("CB_BEAM_SMEM")) : 1;    // 0: force the fallback kernel (tests)
         // Two variants of the same search (bit-identical outputs).  Staging a window's logits in shared memory saves the
         // per-frame global row read (3-5 % when every window is resident anyway) but enlarges the footprint; reading the
@@ -51,22 +56,46 @@ int cb_launch_beam(cb_handle* h, const float* logits, const int32_t* lens, int B
         if (smem_env && pool_s >= 2LL * W + 2 && stride * BEAM_WARPS <= 200 * 1024) {
             // per launch, like the recurrence launchers: the attribute belongs to the current device's copy of the kernel, so
             // a process-wide "already set" flag would miss every GPU but the first in a one-process multi-GPU host
-            if (staged) CB_CUDA(cudaFuncSetAttribute(beam_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            else CB_CUDA(cudaFuncSetAttribute(beam_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            CB_CUDA(cudaMemsetAsync(h->d_flag, 0, sizeof(int), s));
             const dim3 grid((B + BEAM_WARPS - 1) / BEAM_WARPS);
-            if (staged)
-                beam_warp_kernel<true><<<grid, BEAM_WARPS * 32, stride * BEAM_WARPS, s>>>(
+            const size_t smem = stride * BEAM_WARPS;
+            CB_CUDA(cudaMemsetAsync(h->d_flag, 0, sizeof(int), s));
+            if (retry) {            // first pass marks the windows that overflow its pool (n_bases = -1)
+                if (staged) {
+                    CB_CUDA(cudaFuncSetAttribute(beam_warp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    beam_warp_kernel<true, true><<<grid, BEAM_WARPS * 32, smem, s>>>(
+                        logits, lens, B, T, C, W, (int)pool_s, (int)stride, bases, n_bases, h->d_flag);
+                } else {
+                    CB_CUDA(cudaFuncSetAttribute(beam_warp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    beam_warp_kernel<false, true><<<grid, BEAM_WARPS * 32, smem, s>>>(
+                        logits, lens, B, T, C, W, (int)pool_s, (int)stride, bases, n_bases, h->d_flag);
+                }
+            } else if (staged) {
+                CB_CUDA(cudaFuncSetAttribute(beam_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                beam_warp_kernel<true><<<grid, BEAM_WARPS * 32, smem, s>>>(
                     logits, lens, B, T, C, W, (int)pool_s, (int)stride, bases, n_bases, h->d_flag);
-            else
-                beam_warp_kernel<false><<<grid, BEAM_WARPS * 32, stride * BEAM_WARPS, s>>>(
+            } else {
+                CB_CUDA(cudaFuncSetAttribute(beam_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                beam_warp_kernel<false><<<grid, BEAM_WARPS * 32, smem, s>>>(
                     logits, lens, B, T, C, W, (int)pool_s, (int)stride, bases, n_bases, h->d_flag);
+            }
             CB_CHECK_LAUNCH();
             h->launches++;
             int flag = 0;              // the beam decoder is synchronous (like the reference's decode dequeue)
             CB_CUDA(cudaMemcpyAsync(&flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
             CB_CUDA(cudaStreamSynchronize(s));
             if (!flag) return CB_OK;
+            if (retry) {            // second pass: the marked windows alone, one per CTA with a pool of ~130 W nodes
+                const long long pool_r = beam_retry_pool(T, W);
+                const size_t smem_r = align_up(cb_beam_work_bytes(W, (int)pool_r), 16);
+                CB_CUDA(cudaFuncSetAttribute(beam_retry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                CB_CUDA(cudaMemsetAsync(h->d_flag, 0, sizeof(int), s));
+                beam_retry_kernel<<<B, 32, smem_r, s>>>(logits, lens, B, T, C, W, (int)pool_r, bases, n_bases, h->d_flag);
+                CB_CHECK_LAUNCH();
+                h->launches++;
+                CB_CUDA(cudaMemcpyAsync(&flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+                CB_CUDA(cudaStreamSynchronize(s));
+                if (!flag) return CB_OK;
+            }
         }
     }
     long long pool = 4LL * W + 4096;

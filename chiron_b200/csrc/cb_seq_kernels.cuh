@@ -226,7 +226,8 @@ __device__ int beam_decode_warp(const float* __restrict__ lg, int len, int C, in
 // its one row per frame straight from global memory (prefetched a frame ahead), shared memory holds the workspace only --
 // for T=512, W=30 that is 10.8 KB instead of 21 KB per window, i.e. 5 instead of 2 resident CTAs per SM, and the search is
 // a latency chain per warp, so the extra resident warps are what raises its throughput.
-template <bool STAGED>
+// MARK: a window whose pool overflows is reported as n_bases = -1 (for beam_retry_kernel) instead of as an empty read.
+template <bool STAGED, bool MARK = false>
 __global__ void __launch_bounds__(BEAM_WARPS * 32) beam_warp_kernel(const float* __restrict__ logits, const int32_t* __restrict__ lens,
                                                                     int B, int T, int C, int W, int pool, int stride,
                                                                     int8_t* __restrict__ bases, int32_t* __restrict__ n_bases,
@@ -255,6 +256,32 @@ __global__ void __launch_bounds__(BEAM_WARPS * 32) beam_warp_kernel(const float*
     int8_t* dst = bases + (size_t)b * T;
     CbBeamWork k = cb_beam_work_carve(base + work_off, W, pool);
     int n = beam_decode_warp(lg, len, C, W, k, dst, lane);
+    if (n < 0) { if (lane == 0) atomicExch(overflow, 1); n = MARK ? -1 : 0; }
+    __syncwarp();
+    const int n0 = MARK ? (n < 0 ? 0 : n) : n;
+    for (int i = n0 + lane; i < T; i += 32) dst[i] = 0;
+    if (lane == 0) n_bases[b] = n;
+}
+
+// Second pass for the windows a MARK first pass reported as overflowed (n_bases == -1): the same cooperative search, one
+// window per CTA with the CTA's whole shared-memory allotment as its node pool (about 130 W nodes at W=30), logits from global
+// memory.  Experimental (CB_BEAM_RETRY=1, off by default: not yet run on a GPU): it would let the first pass use a small,
+// high-occupancy pool sized for the median window instead of the tail.
+__global__ void __launch_bounds__(32) beam_retry_kernel(const float* __restrict__ logits, const int32_t* __restrict__ lens, int B, int T,
+                                                        int C, int W, int pool, int8_t* __restrict__ bases,
+                                                        int32_t* __restrict__ n_bases, int* __restrict__ overflow) {
+#ifdef CB_HOST_EMU
+    char* beam_sm = reinterpret_cast<char*>(emu::dyn_smem());
+#else
+    extern __shared__ __align__(16) char beam_sm[];
+#endif
+    const int b = blockIdx.x, lane = threadIdx.x;
+    if (b >= B || n_bases[b] != -1) return;
+    int len = lens[b];
+    len = len < 0 ? 0 : (len > T ? T : len);
+    int8_t* dst = bases + (size_t)b * T;
+    CbBeamWork k = cb_beam_work_carve(beam_sm, W, pool);
+    int n = beam_decode_warp(logits + (size_t)b * T * C, len, C, W, k, dst, lane);
     if (n < 0) { if (lane == 0) atomicExch(overflow, 1); n = 0; }
     __syncwarp();
     for (int i = n + lane; i < T; i += 32) dst[i] = 0;
@@ -457,6 +484,13 @@ inline long long beam_small_pool(int T, int W) {
     }
     if (pool > cap) pool = cap;
     return pool;                                   // usable iff >= 2W + 2
+}
+
+// Pool of beam_retry_kernel: what one window can hold in the 200 KB the launcher opts in to, at most the never-overflows bound.
+inline long long beam_retry_pool(int T, int W) {
+    const long long cap = 2LL * W * (T + 1) + 2;
+    const long long fit = (200LL * 1024 - 12LL * 4 * W - 16) / (long long)(sizeof(CbBeamNode) + sizeof(int));
+    return fit < cap ? fit : cap;
 }
 
 }  // namespace cb_seq

@@ -247,3 +247,26 @@ extern "C" int emu_gemm(const float* A, int lda, const float* W, const float* sh
 
 // The node pool cb_launch_beam gives the shared-memory beam search (cb_seq_kernels.cuh: beam_small_pool).
 extern "C" long long emu_beam_small_pool(int T, int W) { return cb_seq::beam_small_pool(T, W); }
+
+// The experimental two-pass beam search (CB_BEAM_RETRY): a first pass with a small pool that marks the windows overflowing it
+// (n_bases = -1), then beam_retry_kernel on the marked windows alone.  *n_marked receives how many windows the first pass
+// marked.  Returns the retry pass's overflow flag.
+extern "C" int emu_beam_retry(const float* logits, const int32_t* lens, int B, int T, int C, int W, int pool_first,
+                              int8_t* bases, int32_t* n_bases, int* n_marked) {
+    int overflow = 0;
+    const size_t stride = cb_seq::beam_warp_stride(T, C, W, pool_first, false);
+    emu::launch2d((B + cb_seq::BEAM_WARPS - 1) / cb_seq::BEAM_WARPS, 1, cb_seq::BEAM_WARPS * 32, stride * cb_seq::BEAM_WARPS, [&] {
+        cb_seq::beam_warp_kernel<false, true>(logits, lens, B, T, C, W, pool_first, (int)stride, bases, n_bases, &overflow);
+    });
+    int marked = 0;
+    for (int b = 0; b < B; ++b) marked += n_bases[b] == -1;
+    if (n_marked) *n_marked = marked;
+    if (!overflow) return marked ? -100 : 0;          // marks without the flag would be a bug
+    overflow = 0;
+    const long long pool_r = cb_seq::beam_retry_pool(T, W);
+    const size_t smem_r = cb_seq::align_up(cb_beam_work_bytes(W, (int)pool_r), 16);
+    emu::launch2d(B, 1, 32, smem_r, [&] {
+        cb_seq::beam_retry_kernel(logits, lens, B, T, C, W, (int)pool_r, bases, n_bases, &overflow);
+    });
+    return overflow;
+}

@@ -89,6 +89,10 @@ int main(int argc, char** argv) {
         for (int warp : {1, 2, 0})
             for (int W : {1, 5, 12})
                 if (emu_beam(warp, logits.data(), lens.data(), B, T, C, W, 2 * W * (T + 1) + 2, bases.data(), nbs.data()) != 0) return 4;
+        {   // the experimental two-pass search: a tiny first-pass pool so that windows are marked and retried
+            int marked = 0;
+            if (emu_beam_retry(logits.data(), lens.data(), B, T, C, 12, 2 * 12 + 2, bases.data(), nbs.data(), &marked) != 0) return 6;
+        }
         // ---- assembly: every kernel --------------------------------------------------------------------------------------------------
         std::uniform_int_distribution<int> base4(0, 3);
         const int n = 14, Tb = 30;

@@ -503,3 +503,23 @@ def test_decoders_on_the_reference_logits_sample(emu):
     # wide beams get what four windows can hold in the shared-memory budget, never less than the algorithm's minimum
     assert 2 * 100 + 2 <= emu.emu_beam_small_pool(150, 100) < 24 * 100
     assert emu.emu_beam_small_pool(3, 30) == 2 * 30 * 4 + 2 and 64 <= emu.emu_beam_small_pool(300, 1) <= 128
+
+
+def test_experimental_two_pass_beam_search_on_real_logits(emu):
+    """CB_BEAM_RETRY (off by default, not yet run on a GPU): a first pass with a pool of 8W nodes marks the windows of the
+    reference's logits sample that overflow it, beam_retry_kernel redoes those alone with a CTA-sized pool; together they are
+    bit-identical to the C oracle."""
+    lg = np.load(os.path.join(os.path.dirname(HERE), "tests", "golden", "logits", "logits_sample_24.npy"))[:12]
+    B, T, C = lg.shape
+    lens = np.full(B, T, np.int32)
+    lens[3] = 120
+    W = 30
+    vp = ctypes.c_void_p
+    bases = np.full((B, T), 9, np.int8)
+    n_bases = np.zeros(B, np.int32)
+    marked = ctypes.c_int(0)
+    rc = emu.emu_beam_retry(_fp(lg), lens.ctypes.data_as(vp), B, T, C, W, 6 * W, bases.ctypes.data_as(vp),
+                            n_bases.ctypes.data_as(vp), ctypes.byref(marked))
+    assert rc == 0 and 1 <= marked.value < B, (rc, marked.value)         # some windows overflow 6W, none the retry pool
+    assert [bases[b, :n_bases[b]].tolist() for b in range(B)] == O.ctc_decode_c(lg, lens, W)
+    assert all((bases[b, n_bases[b]:] == 0).all() for b in range(B))
