@@ -58,33 +58,52 @@ int cb_launch_beam(cb_handle* h, const float* logits, const int32_t* lens, int B
             // a process-wide "already set" flag would miss every GPU but the first in a one-process multi-GPU host
             const dim3 grid((B + BEAM_WARPS - 1) / BEAM_WARPS);
             const size_t smem = stride * BEAM_WARPS;
+            const int attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
             CB_CUDA(cudaMemsetAsync(h->d_flag, 0, sizeof(int), s));
+            // A refused shared-memory opt-in or launch configuration is not an error of the decode: the thread-per-window
+            // kernel below needs no shared memory and gives the same result.
+            cudaError_t fe;
             if (retry) {            // first pass marks the windows that overflow its pool (n_bases = -1)
                 if (staged) {
-                    CB_CUDA(cudaFuncSetAttribute(beam_warp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                    beam_warp_kernel<true, true><<<grid, BEAM_WARPS * 32, smem, s>>>(
-                        logits, lens, B, T, C, W, (int)pool_s, (int)stride, bases, n_bases, h->d_flag);
+                    fe = cudaFuncSetAttribute(beam_warp_kernel<true, true>, (cudaFuncAttribute)attr, 200 * 1024);
+                    if (fe == cudaSuccess)
+                        beam_warp_kernel<true, true><<<grid, BEAM_WARPS * 32, smem, s>>>(
+                            logits, lens, B, T, C, W, (int)pool_s, (int)stride, bases, n_bases, h->d_flag);
                 } else {
-                    CB_CUDA(cudaFuncSetAttribute(beam_warp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                    beam_warp_kernel<false, true><<<grid, BEAM_WARPS * 32, smem, s>>>(
-                        logits, lens, B, T, C, W, (int)pool_s, (int)stride, bases, n_bases, h->d_flag);
+                    fe = cudaFuncSetAttribute(beam_warp_kernel<false, true>, (cudaFuncAttribute)attr, 200 * 1024);
+                    if (fe == cudaSuccess)
+                        beam_warp_kernel<false, true><<<grid, BEAM_WARPS * 32, smem, s>>>(
+                            logits, lens, B, T, C, W, (int)pool_s, (int)stride, bases, n_bases, h->d_flag);
                 }
             } else if (staged) {
-                CB_CUDA(cudaFuncSetAttribute(beam_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                beam_warp_kernel<true><<<grid, BEAM_WARPS * 32, smem, s>>>(
-                    logits, lens, B, T, C, W, (int)pool_s, (int)stride, bases, n_bases, h->d_flag);
+                fe = cudaFuncSetAttribute(beam_warp_kernel<true>, (cudaFuncAttribute)attr, 200 * 1024);
+                if (fe == cudaSuccess)
+                    beam_warp_kernel<true><<<grid, BEAM_WARPS * 32, smem, s>>>(
+                        logits, lens, B, T, C, W, (int)pool_s, (int)stride, bases, n_bases, h->d_flag);
             } else {
-                CB_CUDA(cudaFuncSetAttribute(beam_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                beam_warp_kernel<false><<<grid, BEAM_WARPS * 32, smem, s>>>(
-                    logits, lens, B, T, C, W, (int)pool_s, (int)stride, bases, n_bases, h->d_flag);
+                fe = cudaFuncSetAttribute(beam_warp_kernel<false>, (cudaFuncAttribute)attr, 200 * 1024);
+                if (fe == cudaSuccess)
+                    beam_warp_kernel<false><<<grid, BEAM_WARPS * 32, smem, s>>>(
+                        logits, lens, B, T, C, W, (int)pool_s, (int)stride, bases, n_bases, h->d_flag);
             }
-            CB_CHECK_LAUNCH();
-            h->launches++;
-            int flag = 0;              // the beam decoder is synchronous (like the reference's decode dequeue)
-            CB_CUDA(cudaMemcpyAsync(&flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
-            CB_CUDA(cudaStreamSynchronize(s));
-            if (!flag) return CB_OK;
-            if (retry) {            // second pass: the marked windows alone, one per CTA with a pool of ~130 W nodes
+            if (fe == cudaSuccess) fe = cudaGetLastError();
+            int flag = 1;              // 1 = take the fallback below
+            if (fe == cudaSuccess) {
+                h->launches++;
+                // the beam decoder is synchronous (like the reference's decode dequeue)
+                CB_CUDA(cudaMemcpyAsync(&flag, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+                CB_CUDA(cudaStreamSynchronize(s));
+                if (!flag) return CB_OK;
+            } else {
+                static bool told = false;          // say so once: it is a tenfold slowdown of the decode, not an error
+                if (!told) {
+                    fprintf(stderr, "chiron_b200: shared-memory beam search refused (%s, %zu bytes per CTA); using the "
+                                    "thread-per-window kernel\n", cudaGetErrorString(fe), smem);
+                    told = true;
+                }
+                (void)cudaGetLastError();          // launch-configuration errors are not sticky: clear and fall back
+            }
+            if (retry && fe == cudaSuccess) {   // second pass: the marked windows alone, one per CTA with a pool of ~130 W nodes
                 const long long pool_r = beam_retry_pool(T, W);
                 const size_t smem_r = align_up(cb_beam_work_bytes(W, (int)pool_r), 16);
                 CB_CUDA(cudaFuncSetAttribute(beam_retry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
