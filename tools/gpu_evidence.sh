@@ -27,4 +27,5 @@ timeout 90 python tools/call_bench.py --reads 800 --fmt fast5 > $out/call_fast5.
 timeout 90 python tools/call_bench.py --reads 800 --fmt signal --beam 30 > $out/call_signal_beam30.json 2> $out/call_signal_beam30.err
 timeout 90 python tools/call_bench.py --reads 800 --fmt signal --stub > $out/call_signal_stub.json 2> $out/call_signal_stub.err
 timeout 120 python tools/experiments/beam_stage_ab.py > $out/beam_stage_ab.jsonl 2> $out/beam_stage_ab.err
+timeout 300 python tools/experiments/beam_real_ab.py > $out/beam_real_ab.jsonl 2> $out/beam_real_ab.err     # real logits: the numbers that count
 ls -la $out
