@@ -4,13 +4,16 @@
     python bench.py --gpus 1 --steps 5 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...        # the CPU restatement of the reference path (TF 1.15 is not installable)
+    python bench.py --impl reference ...        # the reference's CPU path restated on torch-CPU (TF 1.15 is not installable)
+    python bench.py --config 2 | 3 | 1          # the other BASELINE.json configurations (see WORKLOADS)
 
 A step = one pass of the hot path over one batch of synthetic windows per GPU: seq_len scaling, residual conv stack,
-3-layer BiLSTM, logit head, path_prob, CTC greedy decode (DNA_default, segment_len 512, batch 4096 per GPU -- the
-configuration north_star's target is quoted on).  `value` is measured with the windows resident in HBM; `e2e` goes
-through the C-ABI host call (pinned host buffers, H2D + D2H inside the timed region).  Reads shard across GPUs with no
-data-path collective (weak scaling)."""
+3-layer BiLSTM, logit head, path_prob, CTC decode.  The headline workload is DNA_default, segment_len 512, batch 4096 per
+GPU, greedy decoder -- the configuration north_star's target is quoted on -- in the tensor-core precision `chiron call`
+uses by default.  `value` is measured with the windows resident in HBM; `e2e` goes through the C-ABI host call (pinned
+host buffers, H2D + D2H inside the timed region).  Reads shard across GPUs with no data-path collective (weak scaling).
+`parity` (N = 1) says what the benched mode computes: greedy bases of the whole bench batch against the fp32 FFMA kernels,
+and logits / bases of a sample of windows against the float64 / float32 CPU oracle."""
 from __future__ import annotations
 
 import argparse
@@ -27,15 +30,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-SEG_LEN = 512
-FLOP_PER_FRAME = {"conv": 2 * 1049088, "lstm_in": 2 * 524800, "lstm_rec": 2 * 240000, "head": 2 * 700}
-# Algorithmic HBM bytes per frame, summed over the launches of a category: every contraction reads
-# its A operand image once (hi+lo fp16 = 4 B per channel) and writes its output once.
-#   conv: 8 contractions read 256-channel images (the two K=512 ones read two), all write one: (10 + 8) * 1024 B, + gen 1 KB
-#   lstm_in: reads 1024 + 832 + 832 B (K = 256, 208, 208), writes 3 x 3200 B of fp32 pre-activations
-#   lstm_rec: reads 3 x 3200 B, writes 832 + 832 B of h images and 800 B of fp32 output;  head: 800 B in, 20 B out
-BYTES_PER_FRAME = {"conv": 19 * 1024 + 4, "lstm_in": 1024 + 832 + 832 + 3 * 3200, "lstm_rec": 3 * 3200 + 832 + 832 + 800,
-                   "head": 820}
+# BASELINE.json configs: 0 = the headline (configs[3]'s per-GPU shape = north_star's target shape), 2 and 3 as numbered there;
+# 1 (the five bundled reads through the file pipeline) is handled by run_files().
+WORKLOADS = {
+    0: {"name": "DNA_default L=512 B=4096/GPU greedy CTC", "model": "DNA_default", "L": 512, "B": 4096, "beam": 0},
+    2: {"name": "DNA_default L=512 B=1024 greedy CTC (BASELINE config 2)", "model": "DNA_default", "L": 512, "B": 1024, "beam": 0},
+    3: {"name": "RNA_default L=500 B=512 beam-search CTC width 50 (BASELINE config 3)", "model": "RNA_default", "L": 500,
+        "B": 512, "beam": 50},
+}
+N_CPU_WINDOWS = 256            # bounded CPU sample per pass (cpu_baseline and every step of --impl reference)
+N_PARITY_ORACLE = 512          # windows of the bench batch checked against the CPU oracle
 
 
 def load_peaks():
@@ -47,16 +51,60 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def synthetic_windows(B: int, L: int, seed: int):
+def work_per_frame(cfg, L):
+    """Algorithmic FLOP and HBM bytes per CNN output frame and kernel category.  FLOP =
+    2 x MACs of the contractions.  Bytes: every contraction reads its A operand image once (fp16 hi+lo = 4 B per channel)
+    and writes its output once (4 B per channel; the input projections write fp32 = 4 B per gate column)."""
+    C, H, T = cfg.channels, cfg.hidden, cfg.out_len(L)
+    s0 = cfg.stride[0]
+    mac_conv = C + s0 * C + cfg.k[0] * C * C + C * C               # block 1: branch1, conv2a (at input rate), conv2b, conv2c
+    bytes_conv = 4 + 4 * C * s0 + (cfg.k[0] > 0) * 4 * C * s0 + 4 * C + 4 * C + 4 * C    # x, gen out, 2b in/out, 2c in/out
+    for b in range(1, cfg.n_blocks):
+        mac_conv += C * C + cfg.k[b] * C * C + 2 * C * C
+        bytes_conv += (4 * C + 4 * C) + (4 * C + 4 * C) + (8 * C + 4 * C)
+    hp = (H + 7) // 8 * 8
+    if cfg.rnn_layout == 0:
+        mac_in = C * 8 * H + (cfg.n_layers - 1) * 2 * H * 8 * H
+        bytes_in = 4 * C + (cfg.n_layers - 1) * 4 * 2 * hp + cfg.n_layers * 4 * 8 * H
+    else:
+        mac_in = 2 * (C * 4 * H + (cfg.n_layers - 1) * H * 4 * H)
+        bytes_in = 2 * 4 * C + 2 * (cfg.n_layers - 1) * 4 * hp + cfg.n_layers * 4 * 8 * H
+    mac_rec = cfg.n_layers * 2 * H * 4 * H
+    bytes_rec = cfg.n_layers * 4 * 8 * H + (cfg.n_layers - 1) * 4 * 2 * hp + 4 * 2 * H
+    mac_head = 2 * H + H * cfg.n_class
+    flop = {"conv": 2 * mac_conv, "lstm_in": 2 * mac_in, "lstm_rec": 2 * mac_rec, "head": 2 * mac_head}
+    byts = {"conv": bytes_conv, "lstm_in": bytes_in, "lstm_rec": bytes_rec, "head": 4 * 2 * H + 4 * cfg.n_class}
+    return flop, byts, T
+
+
+def bundled_signals(model: str, reader: str):
+    """Normalised bundled reads of the model's kind.  reader = "product": the library's own parse / normalise path (the GPU
+    arm's inputs); "oracle": the CPU oracle's reader (the CPU arms: no product code prepares their inputs).  The two are
+    bit-identical (tests/test_host_signal.py), so both arms see the same windows."""
+    from chiron_b200.model import load_model                # weight-blob header only: which normalisation the model wants
+    norm = load_model(model)[0].sig_norm
+    if reader == "oracle":
+        from oracle import chiron_oracle as O
+        read_text, normalize = O.read_signal_text, O.normalize_signal
+    else:
+        from chiron_b200.chiron_input import normalize_signal as normalize, read_signal as read_text
+    if model.startswith("RNA"):
+        from chiron_b200 import fast5                       # HDF5 container parsing (the oracle has no fast5 reader); RNA
+        sig = fast5.read_raw_signal(os.path.join(ROOT, "tests", "golden", "fast5", "rna_read_100_ch_328.fast5"))[::-1]   # reads 3'->5'
+        return [normalize(np.ascontiguousarray(sig, dtype=np.float32), norm)]
+    return [normalize(read_text(os.path.join(ROOT, "tests", "golden", "DNA", "raw", n + ".signal")), norm) for n in ("read1", "read3")]
+
+
+_SIGNAL_CACHE = {}
+
+
+def synthetic_windows(B: int, L: int, seed: int, model: str = "DNA_default", reader: str = "product"):
     """Bootstrap windows cut at random offsets from the bundled normalised signals (SURVEY 8d synthetic input (i)):
     keeps the logits realistic (~95% blank) so decode costs and kbases/s are representative."""
-    from chiron_b200.chiron_input import normalize_signal, read_signal
-    from chiron_b200.model import NORM_UNIQUE_MAD
+    if (model, reader) not in _SIGNAL_CACHE:
+        _SIGNAL_CACHE[(model, reader)] = bundled_signals(model, reader)
+    sigs = _SIGNAL_CACHE[(model, reader)]
     rng = np.random.default_rng(seed)
-    sigs = []
-    for name in ("read1", "read3"):
-        s = read_signal(os.path.join(ROOT, "tests", "golden", "DNA", "raw", name + ".signal"))
-        sigs.append(normalize_signal(s, NORM_UNIQUE_MAD))
     x = np.empty((B, L), dtype=np.float32)
     for b in range(B):
         s = sigs[int(rng.integers(0, len(sigs)))]
@@ -107,53 +155,159 @@ class ClockSampler:
                 "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
 
 
-def cpu_oracle_msamples(n_windows: int, L: int, seed: int, repeats: int = 1):
-    """The oracle (numpy, BLAS on every host core) timed on a bounded sample of the same workload."""
-    import torch
-    from chiron_b200.model import load_model
-    from oracle import chiron_oracle as O
-    cfg, t, _ = load_model("DNA_default")
-    x, lens = synthetic_windows(n_windows, L, seed)
-    best = None
-    bases = 0
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        logits = O.inference(x, lens, cfg, t)
-        paths = O.ctc_decode_c(logits, lens, 0)
-        O.path_prob(logits)
-        dt = time.perf_counter() - t0
-        bases = sum(len(p) for p in paths)
-        best = dt if best is None else min(best, dt)
-    return n_windows * L / best / 1e6, bases / best / 1e3, best, torch.get_num_threads()
+# ---- the CPU arm: the reference path restated on torch-CPU kernels (oracle/torch_cpu.py) ------------------------------------
+class CpuArm:
+    """Model and inputs are built once, outside every timed region; the thread count is set explicitly (torchrun exports
+    OMP_NUM_THREADS=1, which would starve a rank-0-only CPU run)."""
+
+    def __init__(self, wl, n_windows: int, seed: int):
+        import torch
+        from chiron_b200.model import load_model                    # weight-blob parsing only
+        from oracle import chiron_oracle as O
+        from oracle.torch_cpu import TorchCpuModel
+        self.torch, self.O, self.wl = torch, O, wl
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        self.cfg, t, _ = load_model(wl["model"])
+        self.model = TorchCpuModel(self.cfg, t)
+        self.L = wl["L"]
+        self.x, lens = synthetic_windows(n_windows, self.L, seed, wl["model"], reader="oracle")
+        self.lens_out = O.seq_len_out(lens, self.L / self.cfg.out_len(self.L))
+        self.decode = lambda lg, ln: O.ctc_decode_c(lg, ln, wl["beam"])
+        self.model.timed_pass(self.x[:16], self.lens_out[:16], self.decode)       # warm the kernels' one-time setup
+
+    def one_pass(self, n=None):
+        n = n or len(self.x)
+        times, _, paths = self.model.timed_pass(self.x[:n], self.lens_out[:n], self.decode)
+        return times, sum(len(p) for p in paths)
+
+    def describe(self, times, n, extra=""):
+        return ("%d windows x %d samples of the same synthetic workload per pass (%.1f s: conv %.2f, lstm %.2f, head %.2f, "
+                "decode %.2f); torch-CPU (oneDNN/MKL) restatement of the reference path, %d threads%s"
+                % (n, self.L, times["total"], times["conv"], times["lstm"], times["head"], times["decode"], self.cores, extra))
+
+    def single_thread(self, n=32):
+        self.torch.set_num_threads(1)
+        try:
+            t, _ = self.one_pass(n)
+        finally:
+            self.torch.set_num_threads(self.cores)
+        return n * self.L / t["total"] / 1e6
 
 
-def run_reference(args):
+def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    n_windows = 96
-    vals, kb = [], []
+    arm = CpuArm(wl, N_CPU_WINDOWS, 99)
+    n, L = N_CPU_WINDOWS, wl["L"]
+    acc, bases = None, 0
     for i in range(args.warmup + args.steps):
         if i == args.warmup:
             t_start = time.perf_counter()
-        v, k, dt, threads = cpu_oracle_msamples(n_windows, SEG_LEN, 1234 + i)
+        times, nb = arm.one_pass()
         if i >= args.warmup:
-            vals.append(v)
-            kb.append(k)
+            bases += nb
+            acc = times if acc is None else {k: acc[k] + v for k, v in times.items()}
     elapsed = time.perf_counter() - t_start
-    value = n_windows * SEG_LEN * args.steps / elapsed / 1e6
-    cores = os.cpu_count()
-    sample = "%d windows x %d samples per step (DNA_default, greedy); numpy/BLAS oracle on all host threads" % (n_windows, SEG_LEN)
+    value = n * L * args.steps / elapsed / 1e6
+    mean = {k: v / args.steps for k, v in acc.items()}
+    one = arm.single_thread()
     line = {"impl": "reference", "metric": "raw-signal Msamples/s", "value": value, "unit": "Msamples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "DNA_default L=512 B=4096/GPU greedy CTC (bounded CPU sample of it)", "segment_len": SEG_LEN,
-                       "batch": n_windows, "decoder": "greedy"},
-            "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample,
-                             "note": "CPU restatement of the reference path (TF 1.15 cannot be installed here)"},
+            "config": {"workload": wl["name"] + " (bounded CPU sample of it)", "segment_len": L, "batch": n,
+                       "decoder": "beam %d" % wl["beam"] if wl["beam"] else "greedy"},
+            "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": arm.cores, "kind": "port",
+                             "sample": arm.describe(mean, n),
+                             "per_stage_s": {k: round(v, 4) for k, v in mean.items()}, "single_thread_value": one,
+                             "note": "TF 1.15 cannot be installed here: the reference's CPU path restated on torch-CPU kernels "
+                                     "(oracle/torch_cpu.py, pinned to the numpy oracle by tests/test_torch_cpu_baseline.py)"},
             "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "kbases_per_s": float(np.mean(kb)), "gpu_launches": 0}
+            "kbases_per_s": bases / elapsed / 1e3, "gpu_launches": 0}
     print(json.dumps(line))
+    return 0
+
+
+# ---- parity of the benched mode (what the number is a number OF) ------------------------------------------------------------
+def parity_record(wl, precision, x_h, len_h, device):
+    """Greedy/beam bases of the WHOLE bench batch in the benched precision against the fp32 FFMA kernels, and logits + bases
+    of N_PARITY_ORACLE sampled windows against the CPU oracle (float64 for the logits, float32 for the bases)."""
+    from chiron_b200.engine import Basecaller
+    from chiron_b200.model import load_model
+    from oracle import chiron_oracle as O
+    B = len(x_h)
+    out = {}
+    for prec in dict.fromkeys((precision, "fp32")):
+        bc = Basecaller(wl["model"], device=device, precision=prec)
+        out[prec] = bc.basecall_batch(x_h, len_h, beam=wl["beam"], want_logits=True)
+        bc.close()
+    bt, nt, _, lt = out[precision]
+    bf, nf, _, lf = out["fp32"]
+    mism = sum(1 for b in range(B) if nt[b] != nf[b] or not np.array_equal(bt[b, :nt[b]], bf[b, :nf[b]]))
+    cfg, t, _ = load_model(wl["model"])
+    n_or = min(N_PARITY_ORACLE, B)
+    pick = np.sort(np.random.default_rng(7).choice(B, n_or, replace=False))
+    lo = O.seq_len_out(len_h[pick], wl["L"] / cfg.out_len(wl["L"]))
+    ref64 = O.inference(x_h[pick], lo, cfg, t, np.float64)
+    ref32 = ref64.astype(np.float32)
+    paths = O.ctc_decode_c(ref32, lo, wl["beam"])
+    am64 = ref64.argmax(2)
+    frames = int(am64.size)
+    rec = {"mode": precision, "decoder": "beam %d" % wl["beam"] if wl["beam"] else "greedy",
+           "windows_checked": B, "mismatching_windows": mism, "checked_against": "fp32 FFMA kernels, whole bench batch",
+           "max_dlogit_vs_fp32_mode": float(np.abs(lt - lf).max()),
+           "oracle_windows": n_or, "oracle_frames": frames}
+    for prec, (bb, nn, _, lg) in out.items():
+        key = "mode" if prec == precision else "fp32_mode"
+        d = np.abs(lg[pick] - ref64)
+        rec["oracle_" + key] = {"max_dlogit": float(d.max()), "rms_dlogit": float(np.sqrt((d * d).mean())),
+                                "argmax_flips_per_million": float((lg[pick].argmax(2) != am64).sum()) / frames * 1e6,
+                                "mismatching_windows": sum(bb[b, :nn[b]].tolist() != p for b, p in zip(pick, paths))}
+    rec["max_dlogit"] = rec["oracle_mode"]["max_dlogit"]
+    o32 = O.inference(x_h[pick[:64]], lo[:64], cfg, t, np.float32)
+    rec["oracle_f32_vs_f64_max_dlogit"] = float(np.abs(o32 - ref64[:64]).max())      # the fp32 floor of the CPU oracle itself
+    return rec
+
+
+# ---- BASELINE config 1: the five bundled reads through the file pipeline ----------------------------------------------------
+def run_files(args):
+    """`chiron call`'s evaluation() on tests/golden/DNA/raw (5 reads, 1,046,731 samples), -l 300 -b 100 --beam 0 -j 290:
+    a step = one pass files -> result/segments/meta files."""
+    import shutil
+    import tempfile
+    import types
+    from chiron_b200 import chiron_eval
+    from chiron_b200.engine import Basecaller
+    src = os.path.join(ROOT, "tests", "golden", "DNA", "raw")
+    caller = Basecaller("DNA_default", device=0, precision=args.precision)
+    samples, bases, times = 0, 0, []
+    with ClockSampler(0) as clocks:
+        for i in range(args.warmup + args.steps):
+            out = tempfile.mkdtemp(prefix="chiron_bench_c1_")
+            flags = types.SimpleNamespace(input=src, output=out, model="DNA_default", start=0, batch_size=100, segment_len=300,
+                                          jump=290, threads=0, beam=0, extension="fastq", concise=False, mode="dna",
+                                          preset=None, precision=args.precision, recursive=False, reverse_fast5=False)
+            t0 = time.perf_counter()
+            summary = chiron_eval.evaluation(flags, caller=caller)
+            dt = time.perf_counter() - t0
+            shutil.rmtree(out, ignore_errors=True)
+            if i >= args.warmup:
+                times.append(dt)
+                samples = sum(v["samples"] for v in summary.values())
+                bases = sum(v["bases"] for v in summary.values())
+    ms = float(np.mean(times)) * 1e3
+    value = samples / ms / 1e3
+    line = {"metric": "raw-signal Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "bundled example reads (tests/golden/DNA/raw, 5 reads, %d samples)" % samples,
+            "config": {"workload": "BASELINE config 1: DNA_default, 5 bundled reads, files -> fastq, -l 300 -b 100 -j 290 --beam 0",
+                       "precision": caller.precision},
+            "kbases_per_s": bases / ms, "clocks": clocks.summary(),
+            "e2e": {"value": value, "unit": "Msamples/s", "api": "chiron_eval.evaluation() (files in, files out)"},
+            "gpu_launches": int(caller.launches), "roofline": None, "cpu_baseline": None}
+    print(json.dumps(line))
+    caller.close()
     return 0
 
 
@@ -163,12 +317,24 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=4096, help="windows per GPU per step")
+    ap.add_argument("--config", type=int, default=0, choices=[0, 1, 2, 3],
+                    help="0 = headline (DNA_default 512 x 4096/GPU greedy); 1, 2, 3 = BASELINE.json configs[0..2]")
+    ap.add_argument("--batch", type=int, default=None, help="windows per GPU per step (default: the workload's)")
     ap.add_argument("--precision", default=os.environ.get("CHIRON_B200_PRECISION", "tc"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
+    if args.config == 1:
+        if args.impl == "reference":
+            return run_reference(args, dict(WORKLOADS[0], name="BASELINE config 1 (window shape 300, CPU sample)", L=300))
+        args.warmup = max(args.warmup, 1)
+        return run_files(args)
+    wl = dict(WORKLOADS[args.config])
+    if args.batch:
+        wl["B"] = args.batch
+        wl["name"] = wl["name"].replace("B=%d" % WORKLOADS[args.config]["B"], "B=%d" % args.batch)
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, wl)
     if args.warmup < 3:
         args.warmup = 3
 
@@ -186,10 +352,10 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    B, L = args.batch, SEG_LEN
-    bc = Basecaller("DNA_default", device=local, precision=args.precision)
+    B, L, beam = wl["B"], wl["L"], wl["beam"]
+    bc = Basecaller(wl["model"], device=local, precision=args.precision)
     T = bc.out_len(L)
-    x_h, len_h = synthetic_windows(B, L, 1234 + rank)
+    x_h, len_h = synthetic_windows(B, L, 1234 + rank, wl["model"])
     dev = torch.device("cuda", local)
     x_d = torch.from_numpy(x_h).to(dev)
     len_in = torch.from_numpy(len_h).to(dev)
@@ -203,7 +369,7 @@ def main():
     def step():
         bc.seq_len_out_device(len_in, L, out=len_out, stream=stream)
         bc.forward_device(x_d, len_out, logits=logits, path_prob=prob, stream=stream)
-        bc.decode_device(logits, len_out, beam=0, bases=bases, n_bases=n_bases, stream=stream)
+        bc.decode_device(logits, len_out, beam=beam, bases=bases, n_bases=n_bases, stream=stream)
 
     def barrier():
         if world > 1:
@@ -213,6 +379,7 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
+    bc.check_status()
     launches0 = bc.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
@@ -224,6 +391,7 @@ def main():
         barrier()
     ms_total = e0.elapsed_time(e1)
     launches = bc.launches - launches0
+    bc.check_status()
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -235,13 +403,20 @@ def main():
         dist.all_reduce(total_bases)
     kbases = float(total_bases.item()) / ms_step               # bases per ms = kbases/s
 
-    # ---- per-kernel profile of one more step (CUDA event pairs around every launch, on the launching stream) ----
+    # ---- per-kernel profile of three more steps (CUDA event pairs around every launch, on the launching stream) ----
     bc.enable_timing(True)
     prof_acc = {}
     n_prof = 3
+    dec_ms = 0.0
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(n_prof):
-        step()
+        bc.seq_len_out_device(len_in, L, out=len_out, stream=stream)
+        bc.forward_device(x_d, len_out, logits=logits, path_prob=prob, stream=stream)
+        d0.record()
+        bc.decode_device(logits, len_out, beam=beam, bases=bases, n_bases=n_bases, stream=stream)
+        d1.record()
         torch.cuda.synchronize(dev)
+        dec_ms += d0.elapsed_time(d1) / n_prof
         for k, (ms, cnt) in bc.last_forward_profile().items():
             a = prof_acc.setdefault(k, [0.0, 0])
             a[0] += ms / n_prof
@@ -249,18 +424,19 @@ def main():
     phase_ms = bc.last_forward_ms()
     bc.enable_timing(False)
     peaks, peak_kind = load_peaks()
+    flop_pf, bytes_pf, _ = work_per_frame(bc.cfg, L)
     frames = B * T
     dom = max(prof_acc, key=lambda k: prof_acc[k][0])
-    flops = FLOP_PER_FRAME[dom] * frames
+    flops = flop_pf[dom] * frames
     dom_ms, dom_cnt = prof_acc[dom]
     achieved = flops / (dom_ms * 1e-3) / 1e12
     peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     # tensor-pipe work actually issued: the tc path runs every contraction as 3 fp16 MMAs (hi*lo, lo*hi, hi*hi)
-    mma_passes = {"tc": 3, "tc_precise": 3, "tc_fast": 1}.get(args.precision, 0)
+    mma_passes = 3 if bc.precision == "tc" else 0
     traffic, traffic_src = None, None
     try:                                   # DRAM bytes per launch of the dominant kernel from the committed ncu capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        if tj.get("precision") == args.precision and tj.get("batch") == B and dom in tj.get("per_category", {}):
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        if tj.get("precision") == bc.precision and tj.get("batch") == B and dom in tj.get("per_category", {}):
             traffic = tj["per_category"][dom]["dram_bytes_per_launch"]
             traffic_src = tj.get("source")
     except (OSError, ValueError, KeyError):
@@ -272,14 +448,14 @@ def main():
                 "tensor_pipe_frac": achieved * max(mma_passes, 1) / peak_tf if mma_passes else None,
                 "launches_per_step": dom_cnt, "avg_launch_ms": dom_ms / max(dom_cnt, 1),
                 "algorithmic_flop_per_launch": flops / max(dom_cnt, 1),
-                "per_category_ms": {k: round(v[0], 3) for k, v in prof_acc.items()},
-                "per_category_tflops": {k: FLOP_PER_FRAME[k] * frames / (v[0] * 1e-3) / 1e12 for k, v in prof_acc.items() if v[0] > 0},
+                "per_category_ms": dict({k: round(v[0], 3) for k, v in prof_acc.items()}, decode=round(dec_ms, 3)),
+                "per_category_tflops": {k: flop_pf[k] * frames / (v[0] * 1e-3) / 1e12 for k, v in prof_acc.items() if v[0] > 0},
                 # every category against BOTH ceilings (tensor: FLOP actually issued = algorithmic x mma_passes vs the
                 # sustained cuBLAS figure; hbm: algorithmic bytes vs the measured copy bandwidth) -- the larger is its bound
-                "per_category_fracs": {k: {"tensor_pipe_frac": (FLOP_PER_FRAME[k] * frames * max(mma_passes, 1) / (v[0] * 1e-3) / 1e12 / peak_tf
+                "per_category_fracs": {k: {"tensor_pipe_frac": (flop_pf[k] * frames * max(mma_passes, 1) / (v[0] * 1e-3) / 1e12 / peak_tf
                                                                 if mma_passes and k != "head" else None),
-                                           "hbm_frac": BYTES_PER_FRAME[k] * frames / (v[0] * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                                           "hbm_gbs": BYTES_PER_FRAME[k] * frames / (v[0] * 1e-3) / 1e9}
+                                           "hbm_frac": bytes_pf[k] * frames / (v[0] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                           "hbm_gbs": bytes_pf[k] * frames / (v[0] * 1e-3) / 1e9}
                                        for k, v in prof_acc.items() if v[0] > 0},
                 "phase_ms": phase_ms}
 
@@ -297,14 +473,14 @@ def main():
     ctypes.memmove(pl, len_h.ctypes.data, B * 4)
 
     def e2e_sync_step():
-        _lib.check(lib.cb_basecall_host(bc.h, px, pl, B, L, 0, pb, pn, pp, None), "cb_basecall_host")
+        _lib.check(lib.cb_basecall_host(bc.h, px, pl, B, L, beam, pb, pn, pp, None), "cb_basecall_host")
 
     def e2e_pipelined(n_steps):
         inflight = []
         for i in range(n_steps):
             if len(inflight) == 2:
                 _lib.check(lib.cb_basecall_collect(bc.h, inflight.pop(0), pb, pn, pp), "cb_basecall_collect")
-            _lib.check(lib.cb_basecall_submit(bc.h, i & 1, px, pl, B, L, 0), "cb_basecall_submit")
+            _lib.check(lib.cb_basecall_submit(bc.h, i & 1, px, pl, B, L, beam), "cb_basecall_submit")
             inflight.append(i & 1)
         while inflight:
             _lib.check(lib.cb_basecall_collect(bc.h, inflight.pop(0), pb, pn, pp), "cb_basecall_collect")
@@ -331,27 +507,32 @@ def main():
            "synchronous_cb_basecall_host": {"value": world * B * L / sync_ms / 1e3, "ms_per_step": sync_ms}}
     for p in (px, pl, pb, pn, pp):
         lib.cb_host_free(p)
+    ws_gb = bc.lib.cb_workspace_bytes(bc.h) / 1e9
+    precision = bc.precision
+    bc.close()
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_cpu = 640                                             # ~10 s of CPU work on 16 threads (bounded sample)
-        v, kb, dt, threads = cpu_oracle_msamples(n_cpu, L, 99)
-        cpu = {"value": v, "unit": "Msamples/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": "%d windows x %d samples of the same synthetic workload, one pass (%.1f s); numpy/BLAS oracle, %d threads"
-                         % (n_cpu, L, dt, threads), "kbases_per_s": kb}
+    cpu, parity = None, None
+    if rank == 0 and world == 1:
+        if not args.no_parity:
+            parity = parity_record(wl, precision, x_h, len_h, local)
+        if not args.no_cpu_baseline:
+            arm = CpuArm(wl, N_CPU_WINDOWS, 99)
+            times, nb = arm.one_pass()
+            cpu = {"value": N_CPU_WINDOWS * L / times["total"] / 1e6, "unit": "Msamples/s", "cores": arm.cores, "kind": "port",
+                   "sample": arm.describe(times, N_CPU_WINDOWS), "per_stage_s": {k: round(v, 4) for k, v in times.items()},
+                   "single_thread_value": arm.single_thread(), "kbases_per_s": nb / times["total"] / 1e3}
     if rank == 0:
         line = {"metric": "raw-signal Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "DNA_default L=512 B=%d/GPU greedy CTC" % B, "segment_len": L, "batch_per_gpu": B,
-                           "decoder": "greedy", "precision": args.precision, "sharding": "reads/windows per rank, no collective",
-                           "l2": "per-step working set (%.1f GB of activations) >> 126 MB L2; no flush needed"
-                                 % (bc.lib.cb_workspace_bytes(bc.h) / 1e9),
+                "config": {"workload": wl["name"], "segment_len": L, "batch_per_gpu": B,
+                           "decoder": "beam %d" % beam if beam else "greedy", "precision": precision,
+                           "sharding": "reads/windows per rank, no collective",
+                           "l2": "per-step working set (%.1f GB of activations) >> 126 MB L2; no flush needed" % ws_gb,
                            "inputs": "bootstrap windows from the bundled normalised reads, seed 1234+rank"},
                 "kbases_per_s": kbases, "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu}
+                "roofline": roofline, "parity": parity, "cpu_baseline": cpu}
         print(json.dumps(line))
-    bc.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

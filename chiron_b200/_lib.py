@@ -11,12 +11,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CHIRON_B200_LIB") or os.path.join(_HERE, "lib", "libchiron_b200.so")   # env override: A/B builds
 
 CB_OK = 0
-PREC_FP32, PREC_TC_SPLIT, PREC_TC_FAST, PREC_TC_PRECISE = 0, 1, 2, 3
+CB_ERR_ARG = -1
+PREC_FP32, PREC_TC_SPLIT = 0, 1
 ASM_SIMPLE, ASM_GLUE, ASM_STICK = 0, 1, 2
 BN_POPULATION, BN_BATCH = 0, 1
 BN_MODES = {"population": BN_POPULATION, "batch": BN_BATCH}
-PRECISIONS = {"fp32": PREC_FP32, "tc": PREC_TC_SPLIT, "tc_split": PREC_TC_SPLIT, "tc_fast": PREC_TC_FAST,
-              "tc_precise": PREC_TC_PRECISE}
+PRECISIONS = {"fp32": PREC_FP32, "tc": PREC_TC_SPLIT, "tc_split": PREC_TC_SPLIT}
 ASM_KERNELS = {"simple": ASM_SIMPLE, "glue": ASM_GLUE, "stick": ASM_STICK}
 
 # name -> (restype, argtypes); mirrors include/chiron_b200.h one to one
@@ -60,6 +60,7 @@ SIGNATURES = {
 # include/chiron_b200_selftest.h (test-only hooks; never used by the product path)
 SELFTEST_SIGNATURES = {
     "cb_selftest_beam": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "cb_selftest_beam16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "cb_selftest_disp": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int]),
 }
 

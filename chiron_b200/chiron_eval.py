@@ -30,72 +30,83 @@ from typing import Dict, List, Optional
 import numpy as np
 
 from .chiron_input import read_data_for_eval
+from ._lib import BN_BATCH
 from .engine import Basecaller, format_segments, get_assembler_kernal, index2base
-from .shard import assign_reads, rank_world
+from .shard import assign_reads, gather_to_rank0, rank_world
 from .utils.unix_time import unix_time
 
 FLAGS = None
 
 
+# File formats of the output tree (chiron_eval.py:176-242).  Only these byte layouts are shared with the reference; the
+# records of a segments file are FASTA-style even under a .fastq suffix (the reference never passes seg_q_score, :213-215,461)
+# and a fasta result has no trailing newline (:220).
+_FMT = {
+    "segment": ">{name}{idx}\n{seq}\n",
+    "segment_q": "@{name}{idx}\n{seq}\n+\n{qual}\n",
+    "result_fastq": "@{name}\n{seq}\n+\n{qual}\n",
+    "result_fasta": ">{name}\n{seq}",
+    "meta": ("# Reading Basecalling assembly output total rate(bp/s)\n"
+             "{reading:5.3f} {basecall:5.3f} {assembly:5.3f} {output:5.3f} {total:5.3f} {rate:5.3f}\n"
+             "# read_len batch_size segment_len jump start_pos\n"
+             "{read_len:d} {batch_size:d} {segment_len:d} {jump:d} {start:d}\n"
+             "# input_name model_name\n"
+             "{input} {model}\n"),
+}
+
+
+def _segment_records(file_pre: str, segments, with_q: bool, seg_q_score) -> str:
+    parts = []
+    for idx, seq in enumerate(segments):
+        parts.append(_FMT["segment"].format(name=file_pre, idx=idx, seq=seq))
+        if with_q:
+            parts.append(_FMT["segment_q"].format(name=file_pre, idx=idx, seq=seq, qual=seg_q_score[idx]))
+    return "".join(parts)
+
+
 def write_output(segments, consensus: str, time_list, file_pre: str, global_setting, concise: bool = False,
                  suffix: str = "fasta", seg_q_score=None, q_score: Optional[str] = None):
-    """Byte-compatible with chiron_eval.py:176-242 (including FASTA-style segment records in .fastq files and the
-    missing trailing newline of fasta results).  ``segments`` is the reference's list of base strings, or the already
-    formatted records as ``bytes`` (engine.format_segments: what evaluation() passes)."""
-    start_time, reading_time, basecall_time, assembly_time = time_list
-    result_folder = os.path.join(global_setting.output, "result")
-    seg_folder = os.path.join(global_setting.output, "segments")
-    meta_folder = os.path.join(global_setting.output, "meta")
-    path_con = os.path.join(result_folder, file_pre + "." + suffix)
+    """The three files of one read, byte-compatible with chiron_eval.py:176-242 (pinned by the seven reference-run cases of
+    tests/golden/host_ref).  ``segments`` is the reference's list of base strings, or the already formatted records as
+    ``bytes`` (engine.format_segments: what evaluation() passes).  ``time_list`` holds the cumulative stamps
+    [start, reading, basecalling, assembly] the reference keeps; the meta line reports their successive differences."""
+    out_dir = global_setting.output
     if global_setting.mode == "rna":
         consensus = consensus.replace("T", "U").replace("t", "u")
-    if not concise:
-        path_reads = os.path.join(seg_folder, file_pre + "." + suffix)
-        path_meta = os.path.join(meta_folder, file_pre + ".meta")
-    with open(path_con, "w+") as out_con:
-        if not concise:
-            if isinstance(segments, (bytes, bytearray)):
-                with open(path_reads, "wb") as out_f:
-                    out_f.write(segments)
-            else:
-                with open(path_reads, "w+") as out_f:
-                    records = []
-                    for indx, read in enumerate(segments):
-                        records.append(">{}{}\n{}\n".format(file_pre, str(indx), read))
-                        if (suffix == "fastq") and (seg_q_score is not None):
-                            records.append("@{}{}\n{}\n+\n{}\n".format(file_pre, str(indx), read, seg_q_score[indx]))
-                    out_f.write("".join(records))
-        if (suffix == "fastq") and (q_score is not None):
-            out_con.write("@{}\n{}\n+\n{}\n".format(file_pre, consensus, q_score))
-        else:
-            out_con.write(">{}\n{}".format(file_pre, consensus))
-    if not concise:
-        with open(path_meta, "w+") as out_meta:
-            total_time = time.time() - start_time
-            output_time = total_time - assembly_time
-            assembly_time -= basecall_time
-            basecall_time -= reading_time
-            total_len = len(consensus)
-            total_time = time.time() - start_time
-            out_meta.write("# Reading Basecalling assembly output total rate(bp/s)\n")
-            out_meta.write("%5.3f %5.3f %5.3f %5.3f %5.3f %5.3f\n" % (
-                reading_time, basecall_time, assembly_time, output_time, total_time, total_len / total_time))
-            out_meta.write("# read_len batch_size segment_len jump start_pos\n")
-            out_meta.write("%d %d %d %d %d\n" % (total_len, global_setting.batch_size, global_setting.segment_len,
-                                                 global_setting.jump, global_setting.start))
-            out_meta.write("# input_name model_name\n")
-            out_meta.write("%s %s\n" % (global_setting.input, global_setting.model))
+    fastq = suffix == "fastq"
+    result = (_FMT["result_fastq"].format(name=file_pre, seq=consensus, qual=q_score) if fastq and q_score is not None
+              else _FMT["result_fasta"].format(name=file_pre, seq=consensus))
+    with open(os.path.join(out_dir, "result", file_pre + "." + suffix), "w") as f:
+        f.write(result)
+    if concise:
+        return
+    if not isinstance(segments, (bytes, bytearray)):
+        segments = _segment_records(file_pre, segments, fastq and seg_q_score is not None, seg_q_score).encode("utf-8")
+    with open(os.path.join(out_dir, "segments", file_pre + "." + suffix), "wb") as f:
+        f.write(segments)
+    start, reading, basecall_cum, assembly_cum = time_list
+    output = (time.time() - start) - assembly_cum           # everything after the assembly stamp: formatting + writing
+    total = time.time() - start
+    meta = _FMT["meta"].format(reading=reading, basecall=basecall_cum - reading, assembly=assembly_cum - basecall_cum,
+                               output=output, total=total, rate=len(consensus) / total, read_len=len(consensus),
+                               batch_size=global_setting.batch_size, segment_len=global_setting.segment_len,
+                               jump=global_setting.jump, start=global_setting.start, input=global_setting.input,
+                               model=global_setting.model)
+    with open(os.path.join(out_dir, "meta", file_pre + ".meta"), "w") as f:
+        f.write(meta)
 
 
 def list_input_files(flags) -> (List[str], str):
-    """chiron_eval.py:277-290."""
+    """chiron_eval.py:277-290.  With -r the reference builds the names of files in sub-folders without a path separator
+    (``dirpath[dir_len:] + filename``, :283), so its recursive mode only works on flat folders; here a nested read keeps
+    its relative path as the input name and gets a flattened output prefix (see ``output_prefix``)."""
     if os.path.isdir(flags.input):
         if getattr(flags, "recursive", False):
             file_list = []
-            dir_len = len(flags.input) + 1
-            for (dirpath, _, filenames) in os.walk(flags.input + "/"):
+            for (dirpath, dirnames, filenames) in os.walk(flags.input):
+                dirnames.sort()
                 for filename in sorted(filenames):
-                    file_list.append(dirpath[dir_len:] + filename)
+                    file_list.append(os.path.relpath(os.path.join(dirpath, filename), flags.input))
         else:
             file_list = sorted(os.listdir(flags.input))
         file_dir = flags.input
@@ -103,6 +114,12 @@ def list_input_files(flags) -> (List[str], str):
         file_list = [os.path.basename(flags.input)]
         file_dir = os.path.abspath(os.path.join(flags.input, os.path.pardir))
     return [f for f in file_list if f.endswith(".signal") or f.endswith(".fast5")], file_dir
+
+
+def output_prefix(name: str) -> str:
+    """result/ segments/ meta/ file prefix of an input name: the name without its extension; the path separators of a
+    read found in a sub-folder (-r) become '__', so every read lands in the flat output folders the reference writes."""
+    return os.path.splitext(name)[0].replace(os.sep, "__")
 
 
 class _ReadState:
@@ -129,8 +146,12 @@ def evaluation(flags=None, caller: Optional[Basecaller] = None) -> Dict[str, dic
     own = caller is None
     if own:
         device = int(os.environ.get("LOCAL_RANK", getattr(flags, "device", 0) or 0))
-        caller = Basecaller(flags.model, device=device, precision=getattr(flags, "precision", None) or "fp32")
+        caller = Basecaller(flags.model, device=device, precision=getattr(flags, "precision", None) or "auto")
     cfg = caller.cfg
+    try:
+        flags.precision_used = getattr(caller, "precision", None)      # what "auto" resolved to (perf report)
+    except AttributeError:
+        pass
     file_list, file_dir = list_input_files(flags)
     if world > 1:
         sizes = [os.path.getsize(os.path.join(file_dir, f)) for f in file_list]
@@ -144,7 +165,12 @@ def evaluation(flags=None, caller: Optional[Basecaller] = None) -> Dict[str, dic
     # same for 400 windows as for 4096, so windows are packed into batches of at least `gpu_batch` whatever -b says
     # (the presets' 300-400 windows would leave 90 % of the SMs idle).  The meta files still record flags.batch_size.
     gpu_batch = int(os.environ.get("CHIRON_B200_GPU_BATCH", min(4096, max(1, (4 << 20) // max(L, 1)))))
-    B = max(B, gpu_batch)
+    # Batch-statistics BatchNorm (models trained at HEAD, chiron/cnn.py:166-188): a window's result DOES depend on the
+    # batch it sits in, so the batches must be the reference's own -- exactly -b windows each, the final one wrap-padded
+    # (chiron_eval.py:322-329,352-358); the padded rows take part in the batch moments and are then discarded.
+    batch_bn = caller.bn_mode == BN_BATCH
+    if not batch_bn:
+        B = max(B, gpu_batch)
     T = caller.out_len(L)
     beam = flags.beam
     with_qs = flags.extension == "fastq"
@@ -162,7 +188,7 @@ def evaluation(flags=None, caller: Optional[Basecaller] = None) -> Dict[str, dic
         seq, qual, pos = caller.assemble(st.bases, st.n_bases, st.prob if with_qs else None, jump, L, kernel=kernal,
                                          with_qs=with_qs)
         assembly_time = time.time() - st.start_time
-        file_pre = os.path.splitext(st.name)[0]
+        file_pre = output_prefix(st.name)
         # the segment strings are built by the writer thread: this thread's job is to keep the GPU fed
         write_q.put((st.bases, st.n_bases, seq, [st.start_time, st.reading_time, basecall_time, assembly_time], file_pre, qual))
         summary[st.name] = {"windows": st.n, "samples": st.samples, "bases": len(seq), "pos": pos}
@@ -244,6 +270,9 @@ def evaluation(flags=None, caller: Optional[Basecaller] = None) -> Dict[str, dic
             return
         x = np.concatenate(pend_x, axis=0)
         ln = np.concatenate(pend_len, axis=0)
+        if batch_bn and pend_n < B:               # only the final batch can be short (chiron_eval.py:352-358)
+            x = np.pad(x, ((0, B - pend_n), (0, 0)), mode="wrap")
+            ln = np.pad(ln, (0, B - pend_n), mode="wrap")
         if len(inflight) == 2:                    # the slot about to be reused is the oldest batch
             collect_oldest()
         inflight.append((caller.basecall_submit(next_slot, x, ln, beam=beam), pend_owner))
@@ -330,14 +359,43 @@ def run(args):
     else:
         file_pre = os.path.splitext(os.path.basename(FLAGS.input))[0]
     rank, world = rank_world()
+    rank_pre = file_pre + ".rank%d" % rank if world > 1 else file_pre
+    append_run_times(os.path.join(meta_folder, rank_pre + ".meta"), time_dict)
+    report = write_perf_report(os.path.join(meta_folder, rank_pre + ".perf.json"), FLAGS, result, time_dict, rank, world)
     if world > 1:
-        file_pre += ".rank%d" % rank
-    path_meta = os.path.join(meta_folder, file_pre + ".meta")
+        # read-sharded run: rank 0 merges the ranks' figures into the files a single-process run writes:
+        # wall time = the slowest rank, CPU times and counts = sums
+        parts = gather_to_rank0({"time": time_dict, "report": report})
+        if rank == 0:
+            merged_time = {"real": max(p["time"]["real"] for p in parts), "sys": sum(p["time"]["sys"] for p in parts),
+                           "user": sum(p["time"]["user"] for p in parts)}
+            append_run_times(os.path.join(meta_folder, file_pre + ".meta"), merged_time)
+            merge_perf_reports(os.path.join(meta_folder, file_pre + ".perf.json"), [p["report"] for p in parts])
+
+
+def append_run_times(path_meta: str, time_dict: dict):
+    """The run's line pair of meta/all.meta (chiron_eval.py:541-544; appended, like the reference)."""
     with open(path_meta, "a+") as out_meta:
         out_meta.write("# Wall_time Sys_time User_time Cpu_time\n")
         out_meta.write("%5.3f %5.3f %5.3f %5.3f\n" % (time_dict["real"], time_dict["sys"], time_dict["user"],
                                                       time_dict["sys"] + time_dict["user"]))
-    write_perf_report(os.path.join(meta_folder, file_pre + ".perf.json"), FLAGS, result, time_dict, rank, world)
+
+
+def merge_perf_reports(path: str, reports: List[dict]) -> dict:
+    """all.perf.json of a read-sharded run: counts and CPU seconds summed over the ranks, wall time of the slowest."""
+    merged = dict(reports[0])
+    for k in ("reads", "windows", "samples", "bases", "cpu_s"):
+        merged[k] = sum(r[k] for r in reports)
+    merged["wall_s"] = max(r["wall_s"] for r in reports)
+    wall = max(merged["wall_s"], 1e-9)
+    merged["Msamples_per_s"] = merged["samples"] / wall / 1e6
+    merged["kbases_per_s"] = merged["bases"] / wall / 1e3
+    merged["rank"] = "merged"
+    merged["per_rank"] = [{k: r[k] for k in ("rank", "reads", "samples", "bases", "wall_s", "Msamples_per_s")} for r in reports]
+    with open(path, "w") as f:
+        json.dump(merged, f, indent=1)
+        f.write("\n")
+    return merged
 
 
 def write_perf_report(path: str, flags, summary: Dict[str, dict], time_dict: dict, rank: int = 0, world: int = 1) -> dict:
@@ -351,7 +409,8 @@ def write_perf_report(path: str, flags, summary: Dict[str, dict], time_dict: dic
               "wall_s": time_dict["real"], "cpu_s": time_dict["sys"] + time_dict["user"],
               "Msamples_per_s": samples / wall / 1e6, "kbases_per_s": bases / wall / 1e3,
               "segment_len": flags.segment_len, "jump": flags.jump, "batch_size": flags.batch_size, "beam": flags.beam,
-              "precision": getattr(flags, "precision", None) or "fp32", "model": flags.model, "mode": flags.mode,
+              "precision": getattr(flags, "precision_used", None) or getattr(flags, "precision", None) or "auto",
+              "model": flags.model, "mode": flags.mode,
               "rank": rank, "world_size": world}
     with open(path, "w") as f:
         json.dump(report, f, indent=1)
@@ -375,8 +434,10 @@ def add_call_arguments(parser: argparse.ArgumentParser, model_default: Optional[
     parser.add_argument("--concise", action="store_true", help="Do not write the meta and segments files.")
     parser.add_argument("--mode", default="dna", help="Output mode, dna or rna.")
     parser.add_argument("-p", "--preset", default=None, help="Preset evaluation parameters: dna-pre or rna-pre")
-    parser.add_argument("--precision", default="fp32", choices=["fp32", "tc", "tc_precise", "tc_fast"],
-                        help="[chiron_b200] arithmetic of the dense contractions (see include/chiron_b200.h)")
+    parser.add_argument("--precision", default="auto", choices=["auto", "tc", "fp32"],
+                        help="[chiron_b200] arithmetic of the dense contractions (see include/chiron_b200.h): tc = the "
+                             "tcgen05 tensor-core kernels, fp32 = the FFMA kernels, auto = tc whenever the model's "
+                             "topology is covered by them")
 
 
 def apply_preset(args):

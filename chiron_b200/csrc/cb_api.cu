@@ -55,7 +55,7 @@ int out_len_of(const CbConfig& c, int L) {
 // -----------------------------------------------------------------------------------------------------------------
 extern "C" int cb_create(const void* blob, size_t nbytes, int device, int precision, cb_handle** out) {
     if (!blob || !out || nbytes < HEADER_BYTES) { cb_set_error("cb_create: bad arguments"); return CB_ERR_ARG; }
-    if (precision < CB_PREC_FP32 || precision > CB_PREC_TC_PRECISE) { cb_set_error("cb_create: unknown precision %d", precision); return CB_ERR_ARG; }
+    if (precision < CB_PREC_FP32 || precision > CB_PREC_TC_SPLIT) { cb_set_error("cb_create: unknown precision %d", precision); return CB_ERR_ARG; }
     BlobHeader hd;
     memcpy(&hd, blob, sizeof(hd));
     int64_t n_floats;
@@ -66,7 +66,28 @@ extern "C" int cb_create(const void* blob, size_t nbytes, int device, int precis
         cb_set_error("cb_create: unsupported topology in blob header");
         return CB_ERR_BLOB;
     }
-    if (nbytes < HEADER_BYTES + (size_t)n_floats * 4) { cb_set_error("cb_create: truncated blob"); return CB_ERR_BLOB; }
+    if (n_floats < 0 || (uint64_t)n_floats > (nbytes - HEADER_BYTES) / 4) { cb_set_error("cb_create: truncated blob"); return CB_ERR_BLOB; }
+    {   // the float count the header's topology needs, BEFORE any tensor is read (a corrupt or mismatched header must
+        // not walk the tensor walk below off the end of the blob)
+        const uint64_t C = hd.channels, H = hd.hidden, bn = 4 * C;
+        bool geom_ok = hd.stem_k >= 0 && hd.stem_k <= 64 && hd.stem_stride >= 0 && hd.stem_stride <= 64;
+        uint64_t need = hd.stem_k > 0 ? (uint64_t)hd.stem_k * C + bn : 0;
+        for (int b = 0; b < hd.n_blocks; ++b) {
+            if (hd.k[b] < 1 || hd.k[b] > 64 || hd.stride[b] < 1 || hd.stride[b] > 64) { geom_ok = false; break; }
+            const uint64_t cin = (b == 0 && hd.stem_k == 0) ? 1 : C;
+            need += cin * C + (((hd.branch1_bn_mask >> b) & 1) ? bn : 0) + cin * C + bn + (uint64_t)hd.k[b] * C * C + bn + C * C + bn;
+        }
+        for (int l = 0; l < hd.n_layers; ++l) {
+            const uint64_t in = l == 0 ? C : (hd.rnn_layout == 0 ? 2 * H : H);
+            need += 2 * (hd.cell_type == CB_CELL_GRU ? (in + H) * 2 * H + 2 * H + (in + H) * H + H : (in + H) * 4 * H + 4 * H);
+        }
+        need += 2 * H + H + H * (uint64_t)hd.n_class + (uint64_t)hd.n_class;
+        if (!geom_ok) { cb_set_error("cb_create: bad conv geometry in blob header"); return CB_ERR_BLOB; }
+        if (need != (uint64_t)n_floats) {
+            cb_set_error("cb_create: blob holds %lld floats, topology needs %llu", (long long)n_floats, (unsigned long long)need);
+            return CB_ERR_BLOB;
+        }
+    }
     const float* w = (const float*)((const char*)blob + HEADER_BYTES);
 
     cb_handle* h = new cb_handle();
@@ -605,7 +626,7 @@ extern "C" int cb_basecall_host(cb_handle* h, const float* x, const int32_t* seq
     if (path_prob) CB_CUDA(cudaMemcpyAsync(path_prob, d_prob, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
     if (logits) CB_CUDA(cudaMemcpyAsync(logits, d_lg, (size_t)B * T * C * 4, cudaMemcpyDeviceToHost, s));
     CB_CUDA(cudaStreamSynchronize(s));
-    return cb_tc_check_range(h, s);
+    return cb_check_deferred(h, s);
 }
 
 // ---- two-slot asynchronous host pipeline -----------------------------------------------------------------------------
@@ -697,14 +718,14 @@ extern "C" int cb_basecall_collect(cb_handle* h, int slot, int8_t* bases, int32_
     memcpy(bases, pin + o.p_bases, (size_t)sl.B * sl.T);
     memcpy(n_bases, pin + o.p_nb, (size_t)sl.B * 4);
     if (path_prob) memcpy(path_prob, pin + o.p_prob, (size_t)sl.B * 4);
-    return cb_tc_check_range(h, h->pipe_out);
+    return cb_check_deferred(h, h->pipe_out);
 }
 
 extern "C" int cb_check_status(cb_handle* h, void* stream) {
     if (!h) { cb_set_error("cb_check_status: bad arguments"); return CB_ERR_ARG; }
     CB_CUDA(cudaSetDevice(h->device));
     CB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-    return cb_tc_check_range(h, (cudaStream_t)stream);
+    return cb_check_deferred(h, (cudaStream_t)stream);
 }
 
 extern "C" int cb_assemble_host(cb_handle* h, const int8_t* bases, const int32_t* n_bases, const float* path_prob,

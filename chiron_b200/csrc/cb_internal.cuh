@@ -116,12 +116,17 @@ int cb_launch_bn_stats(cb_handle* h, const float* X, long long M, const float* s
 int cb_launch_bn_apply(cb_handle* h, const BnApplyArgs& a, cudaStream_t s);
 int cb_launch_gemm_tc(cb_handle* h, const TcGemm& g, cudaStream_t s);
 const float* cb_tc_lstm_bias(cb_handle* h, int layer, int d);   // biases in unit-major gate-column order
+double cb_tc_trunc_c();                    // mean relative shrink per truncating tensor-core accumulator add
+#define CB_LSTM_TC_CHAIN 21                // MMAs the recurrence chains on top of the pre-loaded input projection
 int cb_launch_transpose_x(cb_handle* h, const float* x, int B, int L, int Bp, float* xT, cudaStream_t s);
 int cb_launch_gen_conv2a(cb_handle* h, const float* xT, int B, int Bp, int L, const CbImg& o, cudaStream_t s);
 int cb_launch_lstm_tc(cb_handle* h, const LstmProblem& p, const CbImg* o_img, int write_f32, cudaStream_t s);
 int cb_tc_prepare(cb_handle* h, const float* host_weights);   // build fp16 hi/lo operand images from d_weights layout
 void cb_tc_release(cb_handle* h);
-int cb_tc_check_range(cb_handle* h, cudaStream_t s);   // synchronises s; CB_ERR_RANGE if an activation left fp16 range
+// Flags of the handle's 64-byte device status block (h->d_flag): scratch of the beam passes, and the two sticky error flags
+// cb_check_deferred reports (beam search out of fallback workspaces; an activation left the fp16 range of the tc path).
+enum { CB_FLAG_BEAM_MARKED = 0, CB_FLAG_BEAM_SLOTS = 1, CB_FLAG_BEAM_ERROR = 2, CB_FLAG_TC_RANGE = 3 };
+int cb_check_deferred(cb_handle* h, cudaStream_t s);   // synchronises s; CB_ERR_RANGE / CB_ERR_NOMEM for a raised flag
 int cb_forward_tc(cb_handle* h, const float* x, const int32_t* seq_len_out, int B, int L, float* logits,
                   float* path_prob, cudaStream_t s);
 void cb_forward_tc_release(cb_handle* h);

@@ -1,4 +1,4 @@
-// tcgen05 persistent LSTM recurrence (CB_PREC_TC_SPLIT / CB_PREC_TC_FAST).
+// tcgen05 persistent LSTM recurrence (CB_PREC_TC_SPLIT).
 //
 // Replaces the tf.while_loop of dynamic_rnn around LSTMCell (chiron/rnn.py:49-50,64,140-143), like cb_lstm_simt.cu, but
 // the per-step contraction h[128 rows,100] x W_hh[100,400] runs on the tensor core, and the 400 gate columns of one
@@ -61,7 +61,6 @@ struct LstmTcParams {
     CbImg o_img;               // hi/lo operand image of h for the next layer's input projection (when write_img):
                                //   plane dir*13 + kg, row row0 + t*Bp + b
     int write_f32, write_img;
-    int passes;
     long long* dbg;            // optional timeline probe (development): clock64 stamps of a few steps of CTA (0,0)
     int dbg_flags;             // development experiments: 1 = no pre loads, 2 = no image stores, 4 = no L2 prefetch
 };
@@ -359,12 +358,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) lstm_tc
                 if (leader) {
                     if (s > 0) {                               // h(0) = 0: the first step has no recurrent term;
                                                                // later steps accumulate on top of the parked projection
-                        if (q.passes == 3) {
 #pragma unroll
-                            for (int ks = 0; ks < KG_A / 2; ++ks) {   // low-order products first
-                                umma_f16(d, da_hi + ks * A_STEP, db_lo + (ks * B_STEP + brow), idesc, 1);
-                                umma_f16(d, da_lo + ks * A_STEP, db_hi + (ks * B_STEP + brow), idesc, 1);
-                            }
+                        for (int ks = 0; ks < KG_A / 2; ++ks) {   // low-order products first
+                            umma_f16(d, da_hi + ks * A_STEP, db_lo + (ks * B_STEP + brow), idesc, 1);
+                            umma_f16(d, da_lo + ks * A_STEP, db_hi + (ks * B_STEP + brow), idesc, 1);
                         }
 #pragma unroll
                         for (int ks = 0; ks < KG_A / 2; ++ks)
@@ -436,7 +433,10 @@ int cb_lstm_tc_prepare(cb_handle* h, const float* hw) {
                         const int u = (n / 16) * 4 + (n & 3), gate = (n >> 2) & 3;
                         // -log2(e) folded into the i/f/o columns, -2*log2(e) into the j columns (see lstm_cell)
                         const float sc = gate == 1 ? -2.f * 1.4426950408889634f : -1.4426950408889634f;
-                        const float w = k < H ? W[(size_t)k * H4 + gate * H + u] * sc : 0.f;
+                        // truncation compensation (cb_tc_build_layer): the hi*hi product of K-step g/2 is the
+                        // (g/2 + 1)-th of the 7 last MMAs of the step's chain
+                        const double comp = 1.0 + cb_tc_trunc_c() * (KG_A / 2 - g / 2);
+                        const float w = k < H ? (float)((double)W[(size_t)k * H4 + gate * H + u] * sc * comp) : 0.f;
                         const __half hi = __float2half_rn(w);
                         const __half lo = __float2half_rn(w - __half2float(hi));
                         img[((size_t)g * H4 + n) * 8 + e] = hi;
@@ -469,7 +469,6 @@ int cb_launch_lstm_tc(cb_handle* h, const LstmProblem& p, const CbImg* o_img, in
     memset(&q, 0, sizeof(q));
     q.B = p.B; q.Bp = p.ld_pre; q.T = p.T; q.pre = p.pre; q.lens = p.lens; q.out = p.out;
     q.wimg[0] = st->wimg[p.layer][0]; q.wimg[1] = st->wimg[p.layer][1];
-    q.passes = h->precision == CB_PREC_TC_FAST ? 1 : 3;
     q.write_f32 = write_f32;
     if (o_img) { q.o_img = *o_img; q.write_img = 1; }
     if (q.Bp % RM) { cb_set_error("lstm tensor-core path: padded batch %d not a multiple of %d", q.Bp, RM); return CB_ERR_ARG; }

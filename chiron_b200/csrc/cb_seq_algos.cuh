@@ -25,33 +25,44 @@
 // when they enter the beam, which is equivalent to TF's eager PopulateChildren because an inactive child carries no
 // state.  When the pool fills up it is compacted in place (ancestors of leaves and of the current branches survive).
 // ---------------------------------------------------------------------------------------------------------------------
-struct CbBeamNode {
-    int parent;
-    int label;
-    int slot;                          // leaf slot, -1 = inactive
-    int bidx, bframe;                  // index in `branches` of frame `bframe` (to reach the per-branch oldp copy)
-    int child[CB_BEAM_MAX_CHILD];
+// Index type I: int for the thread-per-window kernel over a global workspace (pools up to 2*W*(T+1)+2 nodes), int16_t for
+// the shared-memory kernels (node pools of a few thousand nodes, T < 32768): a 24-byte node instead of 48 doubles the
+// windows an SM can keep resident, and the search is a latency chain per warp.
+template <typename I>
+struct CbBeamNodeT {
+    I parent;
+    I label;
+    I slot;                            // leaf slot, -1 = inactive
+    I bidx, bframe;                    // index in `branches` of frame `bframe` (to reach the per-branch oldp copy)
+    I child[CB_BEAM_MAX_CHILD];
 };
+typedef CbBeamNodeT<int> CbBeamNode;
 
-struct CbBeamWork {                    // per-window scratch (global memory on the GPU)
-    CbBeamNode* nodes; int pool;       // pool >= 2*W + 2
-    int* remap;                        // [pool]   compaction scratch
+template <typename I>
+struct CbBeamWorkT {                   // per-window scratch (global memory, or shared memory in the cooperative kernels)
+    CbBeamNodeT<I>* nodes; int pool;   // pool >= 2*W + 2
+    I* remap;                          // [pool]   compaction scratch
     int *slot_node;                    // [W]
     float *ot, *ob, *nt, *nb, *nl;     // [W] oldp.total/blank, newp.total/blank/label per slot
     int *leaves, *branches, *freel;    // [W]
     int* bnode; float *bo_total, *bo_blank;   // [W] per-branch copies of oldp (slots may be recycled mid-step)
 };
+typedef CbBeamWorkT<int> CbBeamWork;
 
+template <typename I = int>
 CB_HD inline size_t cb_beam_work_bytes(int W, int pool) {
-    return sizeof(CbBeamNode) * (size_t)pool + sizeof(int) * (size_t)pool + 12 * sizeof(int) * (size_t)W;
+    const size_t nodes = (sizeof(CbBeamNodeT<I>) + sizeof(I)) * (size_t)pool;
+    return ((nodes + 3) & ~(size_t)3) + 12 * sizeof(int) * (size_t)W;
 }
 
-CB_HD inline CbBeamWork cb_beam_work_carve(void* base, int W, int pool) {
-    CbBeamWork k;
+template <typename I = int>
+CB_HD inline CbBeamWorkT<I> cb_beam_work_carve(void* base, int W, int pool) {
+    CbBeamWorkT<I> k;
     char* p = (char*)base;
-    k.nodes = (CbBeamNode*)p; p += sizeof(CbBeamNode) * (size_t)pool;
+    k.nodes = (CbBeamNodeT<I>*)p; p += sizeof(CbBeamNodeT<I>) * (size_t)pool;
     k.pool = pool;
-    k.remap = (int*)p; p += sizeof(int) * (size_t)pool;
+    k.remap = (I*)p; p += sizeof(I) * (size_t)pool;
+    p = (char*)base + (((size_t)(p - (char*)base) + 3) & ~(size_t)3);
     int* q = (int*)p;
     k.slot_node = q; q += W;
     k.ot = (float*)q; q += W; k.ob = (float*)q; q += W;
@@ -67,20 +78,21 @@ CB_HD inline float cb_lse(float a, float b) {
 }
 
 // Compact the pool: keep ancestors of every leaf and of every current branch.  Returns the new node count.
-CB_HD inline int cb_beam_compact(CbBeamWork& k, int n_nodes, int n_leaves, int n_branches, int n_child) {
-    int* mark = k.remap;
+template <typename I>
+CB_HD inline int cb_beam_compact(CbBeamWorkT<I>& k, int n_nodes, int n_leaves, int n_branches, int n_child) {
+    I* mark = k.remap;
     for (int i = 0; i < n_nodes; ++i) mark[i] = 0;
     for (int i = 0; i < n_leaves; ++i)
         for (int n = k.slot_node[k.leaves[i]]; n >= 0 && !mark[n]; n = k.nodes[n].parent) mark[n] = 1;
     for (int i = 0; i < n_branches; ++i)
         for (int n = k.bnode[i]; n >= 0 && !mark[n]; n = k.nodes[n].parent) mark[n] = 1;
     int m = 0;
-    for (int i = 0; i < n_nodes; ++i) mark[i] = mark[i] ? m++ : -1;      // mark becomes the remap table
+    for (int i = 0; i < n_nodes; ++i) mark[i] = mark[i] ? (I)m++ : (I)-1;      // mark becomes the remap table
     for (int i = 0; i < n_nodes; ++i) {
         if (mark[i] < 0) continue;
-        CbBeamNode nd = k.nodes[i];
-        nd.parent = nd.parent >= 0 ? mark[nd.parent] : -1;            // parents of kept nodes are kept
-        for (int c = 0; c < n_child; ++c) nd.child[c] = nd.child[c] >= 0 ? mark[nd.child[c]] : -1;
+        CbBeamNodeT<I> nd = k.nodes[i];
+        nd.parent = nd.parent >= 0 ? mark[nd.parent] : (I)-1;         // parents of kept nodes are kept
+        for (int c = 0; c < n_child; ++c) nd.child[c] = nd.child[c] >= 0 ? mark[nd.child[c]] : (I)-1;
         k.nodes[mark[i]] = nd;                                         // mark[i] <= i: in-place forward move is safe
     }
     for (int i = 0; i < n_leaves; ++i) k.slot_node[k.leaves[i]] = mark[k.slot_node[k.leaves[i]]];
@@ -90,7 +102,8 @@ CB_HD inline int cb_beam_compact(CbBeamWork& k, int n_nodes, int n_leaves, int n
 
 // logits: [T][C] row-major rows of one window; returns the number of decoded labels written to out, or -2 when the
 // node pool is too small even after compaction.
-CB_HD inline int cb_beam_decode_one(const float* logits, int len, int C, int W, CbBeamWork k, int8_t* out) {
+template <typename I>
+CB_HD inline int cb_beam_decode_one(const float* logits, int len, int C, int W, CbBeamWorkT<I> k, int8_t* out) {
     const int blank = C - 1, n_child = C - 1;
     int n_nodes = 1, n_leaves = 1, n_free = 0;
     k.nodes[0].parent = -1; k.nodes[0].label = -1; k.nodes[0].slot = 0; k.nodes[0].bidx = 0; k.nodes[0].bframe = -1;
@@ -122,9 +135,9 @@ CB_HD inline int cb_beam_decode_one(const float* logits, int len, int C, int W, 
         }
         for (int i = 0; i < nb; ++i) {
             const int s = k.branches[i];
-            const CbBeamNode& nd = k.nodes[k.slot_node[s]];
+            const CbBeamNodeT<I>& nd = k.nodes[k.slot_node[s]];
             if (nd.parent >= 0) {
-                const CbBeamNode& pa = k.nodes[nd.parent];
+                const CbBeamNodeT<I>& pa = k.nodes[nd.parent];
                 if (pa.slot >= 0) {
                     const float prev = (nd.label == pa.label) ? k.ob[pa.slot] : k.ot[pa.slot];
                     k.nl[s] = cb_lse(k.nl[s], prev);
@@ -171,8 +184,8 @@ CB_HD inline int cb_beam_decode_one(const float* logits, int len, int C, int W, 
                         if (n_nodes == k.pool) return -2;
                     }
                     node = n_nodes++;
-                    CbBeamNode& nn = k.nodes[node];
-                    nn.parent = k.bnode[i]; nn.label = c; nn.slot = -1; nn.bidx = 0; nn.bframe = -1;
+                    CbBeamNodeT<I>& nn = k.nodes[node];
+                    nn.parent = (I)k.bnode[i]; nn.label = (I)c; nn.slot = -1; nn.bidx = 0; nn.bframe = -1;
                     for (int q = 0; q < CB_BEAM_MAX_CHILD; ++q) nn.child[q] = -1;
                     k.nodes[k.bnode[i]].child[c] = node;
                 }

@@ -2,9 +2,14 @@
 // algorithms and the reference code they restate).
 //
 //  beam_warp_kernel one warp per window walks TF's trie beam search cooperatively over shared memory (bit-identical to the
-//                   sequential routine cb_beam_decode_one); the product path.
-//  beam_kernel      one thread per window runs cb_beam_decode_one over a global workspace: the overflow fallback (and
-//                   the reference the cooperative kernel is tested against).
+//                   sequential routine cb_beam_decode_one); the product path.  A window whose node pool overflows is
+//                   MARKED (n_bases = -1) for the next pass.
+//  beam_retry_kernel second pass: the marked windows alone, one per CTA with the CTA's whole shared memory as node pool.
+//  beam_kernel      one thread per window runs cb_beam_decode_one over a global workspace with a pool that cannot
+//                   overflow: third pass for windows still marked (workspace slots claimed atomically), and the
+//                   reference the cooperative kernels are tested against.
+//  The three passes are enqueued back to back with no host synchronisation: a pass finds nothing to do unless the one
+//  before it marked a window.
 //  assembly         asm_compact (drop empty windows like sparse2dense, chiron_eval.py:56-66) -> asm_disp (one thread per
 //                   adjacent window pair: stick / glue / difflib-exact simple displacement) -> asm_scan (prefix sum ->
 //                   window coordinates, read length) -> asm_vote (count matrix [4,len] + quality sums, atomics) ->
@@ -19,16 +24,31 @@ namespace cb_seq {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ---- beam search -------------------------------------------------------------------------------------------------
+// slot_counter == nullptr: every window, workspace b.  Otherwise only the windows marked n_bases == -1, each claiming one of
+// n_slots workspaces; a marked window that finds no slot raises *overflow (the launcher sizes the pool so that nothing else can).
 __global__ void __launch_bounds__(64) beam_kernel(const float* __restrict__ logits, const int32_t* __restrict__ lens,
                                                   int B, int T, int C, int W, int pool, char* __restrict__ work,
                                                   size_t work_stride, int8_t* __restrict__ bases,
-                                                  int32_t* __restrict__ n_bases, int* __restrict__ overflow) {
+                                                  int32_t* __restrict__ n_bases, int* __restrict__ overflow,
+                                                  int* __restrict__ slot_counter, int n_slots) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    int8_t* dst = bases + (size_t)b * T;
+    size_t ws = (size_t)b;
+    if (slot_counter) {
+        if (n_bases[b] != -1) return;
+        const int slot = atomicAdd(slot_counter, 1);
+        if (slot >= n_slots) {
+            atomicExch(overflow, 1);
+            for (int i = 0; i < T; ++i) dst[i] = 0;
+            n_bases[b] = 0;
+            return;
+        }
+        ws = (size_t)slot;
+    }
     int len = lens[b];
     len = len < 0 ? 0 : (len > T ? T : len);
-    CbBeamWork k = cb_beam_work_carve(work + (size_t)b * work_stride, W, pool);
-    int8_t* dst = bases + (size_t)b * T;
+    CbBeamWork k = cb_beam_work_carve(work + ws * work_stride, W, pool);
     int n = cb_beam_decode_one(logits + (size_t)b * T * C, len, C, W, k, dst);
     if (n < 0) { atomicExch(overflow, 1); n = 0; }
     for (int i = n; i < T; ++i) dst[i] = 0;
@@ -49,10 +69,13 @@ __global__ void __launch_bounds__(64) beam_kernel(const float* __restrict__ logi
 //     the sequential code; chunks are aligned to branches so a branch's entry test is made once.
 // The node pool is small (compacted often); if it ever overflows the launcher falls back to beam_kernel.
 constexpr int BEAM_WARPS = 4;
+typedef int16_t BeamIdx;             // trie index type of the shared-memory kernels (pool, T and W all < 32768)
+typedef CbBeamWorkT<BeamIdx> BeamWorkS;
+typedef CbBeamNodeT<BeamIdx> BeamNodeS;
 
 // `lg` is the window's logits [len][C] in shared memory (staged by the caller) or in global memory; either way the row of
 // frame t + 1 is fetched into registers while frame t is processed, so its latency hides behind the frame's work.
-__device__ int beam_decode_warp(const float* __restrict__ lg, int len, int C, int W, CbBeamWork k, int8_t* out, int lane) {
+__device__ int beam_decode_warp(const float* __restrict__ lg, int len, int C, int W, BeamWorkS k, int8_t* out, int lane) {
     const unsigned FULL = 0xffffffffu;
     const int blank = C - 1, n_child = C - 1;
     int n_nodes = 1, n_leaves = 1, n_free = 0, err = 0;
@@ -104,10 +127,10 @@ __device__ int beam_decode_warp(const float* __restrict__ lg, int len, int C, in
         __syncwarp();
         for (int i = lane; i < nb; i += 32) {
             const int s = k.branches[i];
-            const CbBeamNode& nd = k.nodes[k.slot_node[s]];
+            const BeamNodeS& nd = k.nodes[k.slot_node[s]];
             float nl = k.nl[s];
             if (nd.parent >= 0) {
-                const CbBeamNode& pa = k.nodes[nd.parent];
+                const BeamNodeS& pa = k.nodes[nd.parent];
                 if (pa.slot >= 0) {
                     const float prev = (nd.label == pa.label) ? k.ob[pa.slot] : k.ot[pa.slot];
                     nl = cb_lse(nl, prev);
@@ -187,8 +210,8 @@ __device__ int beam_decode_warp(const float* __restrict__ lg, int len, int C, in
                             if (n_nodes == k.pool) { err = 1; break; }
                         }
                         node = n_nodes++;
-                        CbBeamNode& nn = k.nodes[node];
-                        nn.parent = k.bnode[i]; nn.label = c; nn.slot = -1; nn.bidx = 0; nn.bframe = -1;
+                        BeamNodeS& nn = k.nodes[node];
+                        nn.parent = (BeamIdx)k.bnode[i]; nn.label = (BeamIdx)c; nn.slot = -1; nn.bidx = 0; nn.bframe = -1;
                         for (int q = 0; q < CB_BEAM_MAX_CHILD; ++q) nn.child[q] = -1;
                         k.nodes[k.bnode[i]].child[c] = node;
                     }
@@ -223,15 +246,14 @@ __device__ int beam_decode_warp(const float* __restrict__ lg, int len, int C, in
 }
 
 // STAGED: the window's logits are copied to shared memory first (T*C*4 bytes per window).  Not staged: the search reads
-// its one row per frame straight from global memory (prefetched a frame ahead), shared memory holds the workspace only --
-// for T=512, W=30 that is 10.8 KB instead of 21 KB per window, i.e. 5 instead of 2 resident CTAs per SM, and the search is
-// a latency chain per warp, so the extra resident warps are what raises its throughput.
-// MARK: a window whose pool overflows is reported as n_bases = -1 (for beam_retry_kernel) instead of as an empty read.
-template <bool STAGED, bool MARK = false>
+// its one row per frame straight from global memory (prefetched a frame ahead), shared memory holds the workspace only, so
+// more CTAs are resident per SM -- and the search is a latency chain per warp, so resident warps are its throughput.
+// A window whose pool overflows is reported as n_bases = -1 (and *marked is raised) for beam_retry_kernel.
+template <bool STAGED>
 __global__ void __launch_bounds__(BEAM_WARPS * 32) beam_warp_kernel(const float* __restrict__ logits, const int32_t* __restrict__ lens,
                                                                     int B, int T, int C, int W, int pool, int stride,
                                                                     int8_t* __restrict__ bases, int32_t* __restrict__ n_bases,
-                                                                    int* __restrict__ overflow) {
+                                                                    int* __restrict__ marked) {
 #ifdef CB_HOST_EMU
     char* beam_sm = reinterpret_cast<char*>(emu::dyn_smem());
 #else
@@ -254,22 +276,20 @@ __global__ void __launch_bounds__(BEAM_WARPS * 32) beam_warp_kernel(const float*
         work_off = ((size_t)T * C * 4 + 15) & ~(size_t)15;
     }
     int8_t* dst = bases + (size_t)b * T;
-    CbBeamWork k = cb_beam_work_carve(base + work_off, W, pool);
+    BeamWorkS k = cb_beam_work_carve<BeamIdx>(base + work_off, W, pool);
     int n = beam_decode_warp(lg, len, C, W, k, dst, lane);
-    if (n < 0) { if (lane == 0) atomicExch(overflow, 1); n = MARK ? -1 : 0; }
+    if (n < 0) { if (lane == 0) atomicExch(marked, 1); n = -1; }
     __syncwarp();
-    const int n0 = MARK ? (n < 0 ? 0 : n) : n;
-    for (int i = n0 + lane; i < T; i += 32) dst[i] = 0;
+    for (int i = (n < 0 ? 0 : n) + lane; i < T; i += 32) dst[i] = 0;
     if (lane == 0) n_bases[b] = n;
 }
 
-// Second pass for the windows a MARK first pass reported as overflowed (n_bases == -1): the same cooperative search, one
-// window per CTA with the CTA's whole shared-memory allotment as its node pool (about 130 W nodes at W=30), logits from global
-// memory.  Experimental (CB_BEAM_RETRY=1, off by default: not yet run on a GPU): it would let the first pass use a small,
-// high-occupancy pool sized for the median window instead of the tail.
+// Second pass for the windows the first pass marked (n_bases == -1): the same cooperative search, one window per CTA with
+// the CTA's whole shared-memory allotment as its node pool (~260 W nodes at W=30), logits from global memory.  A window that
+// overflows even this pool stays marked (for beam_kernel's slot mode) and raises *marked.
 __global__ void __launch_bounds__(32) beam_retry_kernel(const float* __restrict__ logits, const int32_t* __restrict__ lens, int B, int T,
                                                         int C, int W, int pool, int8_t* __restrict__ bases,
-                                                        int32_t* __restrict__ n_bases, int* __restrict__ overflow) {
+                                                        int32_t* __restrict__ n_bases, int* __restrict__ marked) {
 #ifdef CB_HOST_EMU
     char* beam_sm = reinterpret_cast<char*>(emu::dyn_smem());
 #else
@@ -280,11 +300,11 @@ __global__ void __launch_bounds__(32) beam_retry_kernel(const float* __restrict_
     int len = lens[b];
     len = len < 0 ? 0 : (len > T ? T : len);
     int8_t* dst = bases + (size_t)b * T;
-    CbBeamWork k = cb_beam_work_carve(beam_sm, W, pool);
+    BeamWorkS k = cb_beam_work_carve<BeamIdx>(beam_sm, W, pool);
     int n = beam_decode_warp(logits + (size_t)b * T * C, len, C, W, k, dst, lane);
-    if (n < 0) { if (lane == 0) atomicExch(overflow, 1); n = 0; }
+    if (n < 0) { if (lane == 0) atomicExch(marked, 1); n = -1; }
     __syncwarp();
-    for (int i = n + lane; i < T; i += 32) dst[i] = 0;
+    for (int i = (n < 0 ? 0 : n) + lane; i < T; i += 32) dst[i] = 0;
     if (lane == 0) n_bases[b] = n;
 }
 
@@ -456,23 +476,21 @@ inline AsmWork asm_work(char* base, const AsmPlan& p) {
 
 // Shared-memory footprint of one window of beam_warp_kernel ((staged logits +) workspace) for a pool of `pool` nodes.
 inline size_t beam_warp_stride(int T, int C, int W, int pool, bool staged) {
-    return align_up((staged ? align_up((size_t)T * C * 4, 16) : 0) + cb_beam_work_bytes(W, pool), 16);
+    return align_up((staged ? align_up((size_t)T * C * 4, 16) : 0) + cb_beam_work_bytes<BeamIdx>(W, pool), 16);
 }
 
-// Node pool of the shared-memory beam search.  Live nodes are the ancestors of the W leaves and of the current branches.  On
-// real logits a pool of 6W nodes is far too small: of the reference's chiron/utils/logits_sample.npy (1100 windows, T=300) only
-// 55 % of the windows fit 6W at W=30, 99.3 % fit 12W and all fit 16W; of 64 oracle-basecalled T=512 windows of the bundled
-// read3, 27 % fit 6W and all fit 16W (2 of them only just).  One overflowing window sends the WHOLE batch to the
-// thread-per-window fallback kernel (ten times slower), and a batch holds thousands of windows, so the pool is sized for the
-// tail, not the median: at least 24W nodes, grown into whatever shared memory the resulting CTAs-per-SM leaves unused,
-// bounded by what four windows can hold in 192 KB (wide beams get fewer nodes per beam and lean on the in-place
-// compaction) and by the never-overflows bound.  Occupancy pays for it (one or two
-// CTAs per SM instead of five at W=30); the search stays correct either way.
+// Node pool of the first pass.  Live nodes are the ancestors of the W leaves and of the current branches.  On real logits
+// (the reference's chiron/utils/logits_sample.npy: 1100 windows, T=300, W=30) 55 % of the windows fit 6W nodes, 99.3 % fit
+// 12W and all fit 16W; of 64 oracle-basecalled T=512 windows of the bundled read3, 27 % fit 6W and all fit 16W
+// (profiles/r01_beam_pool_survey_*.json).  The pool is therefore 16W nodes -- the rare window that still overflows is redone
+// alone by beam_retry_kernel, not the batch -- grown into whatever shared memory the resulting CTAs-per-SM leaves unused
+// (nodes are free up to the next occupancy step) and bounded by what four windows hold in 192 KB and by the
+// never-overflows bound 2W(T+1)+2.  At W=30 that is 5 CTAs = 20 warps per SM (26 bytes per node with 16-bit indices).
 constexpr long long BEAM_SMEM_BUDGET = 192 * 1024;          // of the 200 KB the launcher opts in to
 inline long long beam_small_pool(int T, int W) {
     const long long cap = 2LL * W * (T + 1) + 2;
-    const long long node = (long long)(sizeof(CbBeamNode) + sizeof(int)), fixed = 12LL * 4 * W + 16;
-    long long pool = 24LL * W;
+    const long long node = (long long)(sizeof(BeamNodeS) + sizeof(BeamIdx)), fixed = 12LL * 4 * W + 32;
+    long long pool = 16LL * W;
     const long long fit = (BEAM_SMEM_BUDGET / BEAM_WARPS - fixed) / node;
     if (pool > fit) pool = fit;
     if (pool < 64 && fit >= 64) pool = 64;
@@ -483,13 +501,15 @@ inline long long beam_small_pool(int T, int W) {
         if (grown > pool) pool = grown < fit ? grown : fit;
     }
     if (pool > cap) pool = cap;
+    if (pool > 32767) pool = 32767;
     return pool;                                   // usable iff >= 2W + 2
 }
 
 // Pool of beam_retry_kernel: what one window can hold in the 200 KB the launcher opts in to, at most the never-overflows bound.
 inline long long beam_retry_pool(int T, int W) {
     const long long cap = 2LL * W * (T + 1) + 2;
-    const long long fit = (200LL * 1024 - 12LL * 4 * W - 16) / (long long)(sizeof(CbBeamNode) + sizeof(int));
+    long long fit = (200LL * 1024 - 12LL * 4 * W - 32) / (long long)(sizeof(BeamNodeS) + sizeof(BeamIdx));
+    if (fit > 32767) fit = 32767;
     return fit < cap ? fit : cap;
 }
 

@@ -1,10 +1,14 @@
-// tcgen05 tensor-core contractions for the conv stack and the hoisted LSTM input projection
-// (CB_PREC_TC_SPLIT / CB_PREC_TC_PRECISE / CB_PREC_TC_FAST).  Same maths as cb_gemm_simt.cu (chiron/cnn.py:60-82,251-261;
-// chiron/rnn.py:49-50,64), different machine:
+// tcgen05 tensor-core contractions for the conv stack and the hoisted LSTM input projection (CB_PREC_TC_SPLIT).
+// Same maths as cb_gemm_simt.cu (chiron/cnn.py:60-82,251-261; chiron/rnn.py:49-50,64), different machine:
 //
 //   * operands are fp16 hi/lo splits (a = hi + lo, |lo| <= 2^-11 |a|): D = Ah*Wl + Al*Wh + Ah*Wh, three
-//     tcgen05.mma.kind::f16 per K-step with fp32 accumulation in TMEM.  CB_PREC_TC_FAST issues only Ah*Wh;
-//     CB_PREC_TC_PRECISE sweeps K twice (all low-order products first) to spare the truncating accumulator.
+//     tcgen05.mma.kind::f16 per K-step with fp32 accumulation in TMEM.
+//   * SHORT-K PARTIAL SUMS.  The tensor core's fp32 accumulator TRUNCATES on every add, a bias of ~0.4 ulp per MMA
+//     that grows with the number of MMAs chained into one accumulator (K/16 x 3 of them; measured: it, not the
+//     operand split, sets the logit error of this path).  A TMEM accumulator therefore only ever holds the sum over
+//     `cpp` K-chunks (cpp*32 input channels; low-order products issued first, while the accumulator is small), and the
+//     epilogue warps add the partial sums in fp32 REGISTERS with round-to-nearest.  The two TMEM buffers ping-pong
+//     per partial, so the tensor core fills one while the other is drained.
 //   * activations travel between layers as time-major operand images (cb_tc_common.cuh): the epilogue of the producing
 //     kernel writes the hi/lo k-group planes; a conv tap is the same plane shifted by one frame = Bp rows, a strided conv
 //     multiplies the frame index, the appended 1x1 branch input is a second image.  Block-1 conv2a (a rank-1 function of
@@ -14,7 +18,7 @@
 //     lands in shared memory as [hi|lo][4 k-groups][128 rows][8 halfs] -- the UMMA K-major no-swizzle core-matrix order.
 //   * persistent CTAs, warp-specialised: 8 epilogue warps (TMEM -> scale/shift/residual/ReLU -> hi/lo image or fp32),
 //     one MMA warp, one loader warp (both run warp-convergent; an elected lane issues); shared-memory full/empty ring
-//     (STAGES deep) and a double-buffered TMEM accumulator so the epilogue of tile i overlaps the MMAs of tile i+1.
+//     (q.stages deep); the epilogue of tile i (from registers) overlaps the first two partial sums of tile i+1.
 //   * CTA-PAIR form (gemm_tc_pair_kernel, the convolutions): tcgen05 cta_group::2, M = 256 over two m-tiles; each CTA
 //     stages its own A tile and half of the B tile, every byte counted on the leader's barrier; multicast commits.
 //   * RESIDENT-WEIGHT mode (contractions whose whole n-tile of W fits beside the A ring -- the N = 8H LSTM input
@@ -35,9 +39,8 @@ namespace {
 
 constexpr int BM = 128;          // rows (windows of one frame) per tile = UMMA M
 constexpr int BK = 32;           // K elements per pipeline stage (2 UMMA K-steps of 16)
-constexpr int STAGES = 4;
-constexpr int PREFETCH_AHEAD = 0;   // k-chunks an optional L2 prefetch cursor runs ahead of the loads (CB_TC_PREFETCH): measured
-                                   // HARMFUL (conv 10.5 -> 13.0 ms at 16): the extra TMA requests compete with the loads
+constexpr int MIN_STAGES = 4, MAX_STAGES = 6;   // depth of the operand ring (as many as fit in shared memory)
+constexpr int ACC_COLS = 128;    // accumulator columns an epilogue thread sums in registers (half of the widest tile)
 constexpr int N_EPI_WARPS = 8;   // two per TMEM lane quadrant (each takes half of the tile's columns)
 constexpr int NTHREADS = (N_EPI_WARPS + 2) * 32;   // 320
 
@@ -46,6 +49,7 @@ struct TcLayer {                 // one prepared weight image
     __half* img2;                // CTA-pair form: [n_tiles][k_chunks][2 (cta)][2 (hi,lo)][4 k-groups][BN/2 rows][8]
     CUtensorMap tm_w2;           // img2 as 2 KB rows (TMA view: a CTA's chunk of a stage = BN/32 rows)
     int K, Kpad, N, BN, n_tiles, k_chunks;
+    int cpp;                     // k-chunks per partial sum (the weight image's truncation compensation is built for it)
     float out_scale;             // 2^-s, undoes the power-of-two prescale of the weights
 };
 
@@ -63,11 +67,10 @@ struct TcParams {
     const __half* img;
     int BN, n_tiles, k_chunks, m_tiles;
     float out_scale;
-    int passes;                  // 3 = hi/lo split, 1 = fast
-    int prefetch_ahead;          // k-chunks the L2 prefetch of the A boxes runs ahead of the loads
+    int stages;                  // depth of the shared-memory operand ring
+    int cpp;                     // k-chunks per partial sum (see header): one TMEM accumulator never chains more than
+                                 // cpp*2 full-magnitude MMAs; the partial sums are added in registers
     int resident;                // 1: the CTA keeps its n-tile of W in shared memory (see header)
-    int sweeps;                  // 2: K is swept twice -- all low-order products (hi*lo, lo*hi) first, then hi*hi -- so that
-                                 //    only K/16 of the accumulator's truncating adds happen at full magnitude
     int* range_flag;
 };
 
@@ -144,19 +147,14 @@ __device__ __forceinline__ void tma_w_g2s_pair(void* dst, const CUtensorMap* tm,
         : "memory");
 }
 
-__device__ __forceinline__ void tma_img_prefetch(const CUtensorMap* tm, int row, int plane) {
-    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(tm)),
-                 "r"(row * 2), "r"(plane), "r"(0)
-                 : "memory");
-}
-
-// shared memory: STAGES x { A_hi[4][128][8], A_lo, B_hi[4][BNL][8], B_lo } halfs (BNL = BN / NC rows of the B tile live in
+// shared memory: q.stages x { A_hi[4][128][8], A_lo, B_hi[4][BNL][8], B_lo } halfs (BNL = BN / NC rows of the B tile live in
 // this CTA), then the barriers; resident mode: k_chunks x {B_hi, B_lo} first, stages hold A only.
 template <int NC>
 __device__ __forceinline__ void gemm_tc_body(const TcParams& q) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const TcGemm& g = q.g;
     const int BN = q.BN, BNL = q.BN / NC;
+    const int STAGES = q.stages;
     constexpr uint32_t a_bytes = BM * BK * 2;             // one of hi / lo
     const uint32_t b_bytes = (uint32_t)BNL * BK * 2;
     const uint32_t stage_bytes = q.resident ? 2 * a_bytes : 2 * a_bytes + 2 * b_bytes;
@@ -164,16 +162,17 @@ __device__ __forceinline__ void gemm_tc_body(const TcParams& q) {
     uint8_t* ring = smem + res_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)STAGES * stage_bytes);
     uint64_t* full_bar = bars;                            // [STAGES]  operands landed (pair: in BOTH CTAs; leader's barrier)
-    uint64_t* empty_bar = bars + STAGES;                  // [STAGES]  MMAs that read the stage retired
-    uint64_t* acc_full = bars + 2 * STAGES;               // [2]       accumulator ready for the epilogue
-    uint64_t* acc_empty = bars + 2 * STAGES + 2;          // [2]       accumulator drained (pair: by both CTAs; leader's)
-    uint64_t* w_bar = bars + 2 * STAGES + 4;              //           resident weights landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
+    uint64_t* empty_bar = bars + MAX_STAGES;              // [STAGES]  MMAs that read the stage retired
+    uint64_t* acc_full = bars + 2 * MAX_STAGES;           // [2]       partial sum ready for the epilogue warps
+    uint64_t* acc_empty = bars + 2 * MAX_STAGES + 2;      // [2]       partial sum read (pair: by both CTAs; leader's)
+    uint64_t* w_bar = bars + 2 * MAX_STAGES + 4;          //           resident weights landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = NC == 2 ? cluster_ctarank() : 0;            // pair: rank 0 = leader (issues the MMAs)
     const TileIter tiles(q, (int)blockIdx.x / NC, (int)gridDim.x / NC, q.m_tiles / NC);
     const int tiles_per_frame = g.Bp / BM;
+    const int n_part = (q.k_chunks + q.cpp - 1) / q.cpp;  // partial sums per tile
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -205,42 +204,34 @@ __device__ __forceinline__ void gemm_tc_body(const TcParams& q) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < N_EPI_WARPS) {
-        // ============================ epilogue: TMEM -> registers -> scale/shift/residual/ReLU -> HBM =====================
+        // ============================ epilogue: partial sums TMEM -> registers (+=) -> scale/shift/residual/ReLU -> HBM =====
         const int quad = warp & 3, chalf = warp >> 2;     // TMEM lane quadrant, which half of the tile's columns
         const int first = ((BN / 16 + 1) / 2) * 16;       // BN is a multiple of 16; the two column halves are 16-col aligned
-        const int cbeg = chalf ? first : 0, cend = chalf ? BN : first;
+        const int cbeg = chalf ? first : 0, cend = chalf ? BN : first;      // cend - cbeg <= ACC_COLS
         uint32_t acc_empty_leader[2];
         for (int b = 0; b < 2; ++b)
             acc_empty_leader[b] = NC == 2 ? mapa_shared(smem_u32(&acc_empty[b]), 0) : smem_u32(&acc_empty[b]);
-        uint32_t it = 0;
+        uint32_t it = 0, pit = 0;                          // tiles / partial sums this unit has worked on
         bool overflow = false;
         for (int mu, nt; tiles.get((int)it, mu, nt); ++it) {
             const int mt = mu * NC + (int)rank;
-            const uint32_t buf = it & 1, par = (it >> 1) & 1;
-            mbar_wait(&acc_full[buf], par);
-            tc_fence_after();
             const int to = mt / tiles_per_frame;
             const int b = (mt - to * tiles_per_frame) * BM + quad * 32 + lane;
             const bool row_ok = b < g.B;
             float xr = 0.f;
             if (g.res && row_ok) xr = __ldg(g.xT + (size_t)to * g.res_stride * g.Bp + b);
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (uint32_t)BN;
             const size_t orow = (size_t)g.o.row0 + (size_t)to * g.Bp + b;
-            for (int c0 = cbeg; c0 < cend; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(taddr + c0, v);
-                tmem_ld_wait();
-                const int n0 = nt * BN + c0;
-                if (!row_ok) continue;
+            // 16 finished sums (columns n0..n0+15 of this thread's row) -> scale/shift/residual/ReLU -> HBM
+            auto emit = [&](int n0, const float (&sum)[16]) {
                 float o[16];
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
                     const int n = n0 + q4 * 4;
                     const float4 sh = ldg4(g.shift + n);
-                    o[q4 * 4 + 0] = fmaf(__uint_as_float(v[q4 * 4 + 0]), q.out_scale, sh.x);
-                    o[q4 * 4 + 1] = fmaf(__uint_as_float(v[q4 * 4 + 1]), q.out_scale, sh.y);
-                    o[q4 * 4 + 2] = fmaf(__uint_as_float(v[q4 * 4 + 2]), q.out_scale, sh.z);
-                    o[q4 * 4 + 3] = fmaf(__uint_as_float(v[q4 * 4 + 3]), q.out_scale, sh.w);
+                    o[q4 * 4 + 0] = fmaf(sum[q4 * 4 + 0], q.out_scale, sh.x);
+                    o[q4 * 4 + 1] = fmaf(sum[q4 * 4 + 1], q.out_scale, sh.y);
+                    o[q4 * 4 + 2] = fmaf(sum[q4 * 4 + 2], q.out_scale, sh.z);
+                    o[q4 * 4 + 3] = fmaf(sum[q4 * 4 + 3], q.out_scale, sh.w);
                     if (g.res) {
                         const float4 w = ldg4(g.rw + n), iv = ldg4(g.rinv + n), rs = ldg4(g.rsh + n);
                         o[q4 * 4 + 0] += fmaf(xr * w.x, iv.x, rs.x);
@@ -275,11 +266,62 @@ __device__ __forceinline__ void gemm_tc_body(const TcParams& q) {
                     for (int q4 = 0; q4 < 4; ++q4)
                         dst[(size_t)q4 * g.Bp] = make_float4(o[q4 * 4], o[q4 * 4 + 1], o[q4 * 4 + 2], o[q4 * 4 + 3]);
                 }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {                              // one arrival per epilogue warp (pair: on the leader's barrier)
-                if constexpr (NC == 1) mbar_arrive(&acc_empty[buf]); else mbar_arrive_cluster(acc_empty_leader[buf]);
+            };
+            auto release = [&](uint32_t buf) {            // this warp has read the buffer (pair: on the leader's barrier)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (NC == 1) mbar_arrive(&acc_empty[buf]); else mbar_arrive_cluster(acc_empty_leader[buf]);
+                }
+            };
+            if (n_part == 1) {
+                // one accumulator per tile: stream it out 16 columns at a time (TMEM -> registers costs tensor-pipe time:
+                // measured ~64 B/clk per SM and not overlapped with the MMAs, so every column is read exactly once)
+                const uint32_t buf = pit & 1, par = (pit >> 1) & 1;
+                ++pit;
+                mbar_wait(&acc_full[buf], par);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (uint32_t)BN;
+                for (int c0 = cbeg; c0 < cend; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + c0, v);
+                    tmem_ld_wait();
+                    if (!row_ok) continue;
+                    float sum[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) sum[e] = __uint_as_float(v[e]);
+                    emit(nt * BN + c0, sum);
+                }
+                release(buf);
+            } else {
+                // several partial sums per tile: all but the last are added up in registers, the last is streamed out
+                float acc[ACC_COLS];
+#pragma unroll
+                for (int e = 0; e < ACC_COLS; ++e) acc[e] = 0.f;
+                for (int p = 0; p < n_part; ++p, ++pit) {
+                    const uint32_t buf = pit & 1, par = (pit >> 1) & 1;
+                    const bool last = p == n_part - 1;
+                    mbar_wait(&acc_full[buf], par);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (uint32_t)BN + (uint32_t)cbeg;
+#pragma unroll
+                    for (int j = 0; j < ACC_COLS / 16; ++j) {
+                        if (cbeg + j * 16 < cend) {                // (warp-uniform)
+                            uint32_t v[16];
+                            tmem_ld16(taddr + j * 16, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) acc[j * 16 + e] += __uint_as_float(v[e]);
+                            if (last && row_ok) {
+                                float sum[16];
+#pragma unroll
+                                for (int e = 0; e < 16; ++e) sum[e] = acc[j * 16 + e];
+                                emit(nt * BN + cbeg + j * 16, sum);
+                            }
+                        }
+                    }
+                    release(buf);
+                }
             }
         }
         if (overflow) atomicExch(q.range_flag, 1);
@@ -289,45 +331,74 @@ __device__ __forceinline__ void gemm_tc_body(const TcParams& q) {
         const uint32_t idesc = make_idesc_f16(BM * NC, BN);
         constexpr uint32_t A_STEP = 2 * BM;               // two k-groups per UMMA K-step, in 16-byte units
         const uint32_t B_STEP = 2 * (uint32_t)BNL;
-        uint32_t kit = 0, it = 0;
+        // a partial sum's chunks are all resident at once (low-order products of every chunk first, then hi*hi) when the
+        // ring can hold them and still load ahead; longer partial sums order the products chunk by chunk
+        const bool two_pass = q.cpp < MIN_STAGES;
+        uint32_t kit = 0, it = 0, pit = 0;
+        auto stage_descs = [&](uint32_t k, int kc, uint64_t& dah, uint64_t& dal, uint64_t& dbh, uint64_t& dbl) {
+            const uint32_t s = k % (uint32_t)STAGES;
+            const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
+            const uint32_t sb = q.resident ? smem_u32(smem) + (uint32_t)kc * 2 * b_bytes : sa + 2 * a_bytes;
+            dah = make_desc(sa, BM * 16, 128); dal = make_desc(sa + a_bytes, BM * 16, 128);
+            dbh = make_desc(sb, BNL * 16, 128); dbl = make_desc(sb + b_bytes, BNL * 16, 128);
+            return s;
+        };
         if (rank == 0) {
             for (int mu, nt; tiles.get((int)it, mu, nt); ++it) {
-                const uint32_t buf = it & 1, par = (it >> 1) & 1;
-                if (leader) {                             // the epilogue(s) have drained this accumulator
-                    if constexpr (NC == 1) mbar_wait(&acc_empty[buf], par ^ 1); else mbar_wait_cluster(&acc_empty[buf], par ^ 1);
-                }
-                __syncwarp();
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * (uint32_t)BN;
-                for (int vk = 0; vk < q.sweeps * q.k_chunks; ++vk, ++kit) {
-                    const int kc = vk < q.k_chunks ? vk : vk - q.k_chunks;
-                    const int part = q.sweeps == 1 ? 3 : (vk < q.k_chunks ? 1 : 2);   // 1 low-order, 2 high-order, 3 both
-                    const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
-                    if (leader) mbar_wait(&full_bar[s], ph);
+                for (int p = 0; p < n_part; ++p, ++pit) {
+                    const uint32_t buf = pit & 1, par = (pit >> 1) & 1;
+                    if (leader) {                         // the epilogue warps have read the previous contents of this buffer
+                        if constexpr (NC == 1) mbar_wait(&acc_empty[buf], par ^ 1); else mbar_wait_cluster(&acc_empty[buf], par ^ 1);
+                    }
                     __syncwarp();
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
-                    const uint32_t sb = q.resident ? smem_u32(smem) + (uint32_t)kc * 2 * b_bytes : sa + 2 * a_bytes;
-                    const uint64_t dah = make_desc(sa, BM * 16, 128), dal = make_desc(sa + a_bytes, BM * 16, 128);
-                    const uint64_t dbh = make_desc(sb, BNL * 16, 128);
-                    const uint64_t dbl = make_desc(sb + b_bytes, BNL * 16, 128);
-                    if (leader) {
+                    const uint32_t d_tmem = tmem_base + buf * (uint32_t)BN;
+                    const int kc0 = p * q.cpp;
+                    const int nck = q.k_chunks - kc0 < q.cpp ? q.k_chunks - kc0 : q.cpp;
+                    uint64_t dah, dal, dbh, dbl;
+                    if (two_pass) {
+                        for (int j = 0; j < nck; ++j) {   // low-order products, while the accumulator is small
+                            const uint32_t s = stage_descs(kit + j, kc0 + j, dah, dal, dbh, dbl);
+                            if (leader) mbar_wait(&full_bar[s], ((kit + j) / (uint32_t)STAGES) & 1);
+                            __syncwarp();
+                            tc_fence_after();
+                            if (leader) {
 #pragma unroll
-                        for (int ks = 0; ks < BK / 16; ++ks) {
-                            if (q.passes == 3) {              // low-order products first (truncating accumulator)
-                                if (part & 1) {
-                                    umma_f16_nc<NC>(d_tmem, dah + ks * A_STEP, dbl + ks * B_STEP, idesc, (vk | ks) != 0);
+                                for (int ks = 0; ks < BK / 16; ++ks) {
+                                    umma_f16_nc<NC>(d_tmem, dah + ks * A_STEP, dbl + ks * B_STEP, idesc, (j | ks) != 0);
                                     umma_f16_nc<NC>(d_tmem, dal + ks * A_STEP, dbh + ks * B_STEP, idesc, 1);
                                 }
-                                if (part & 2) umma_f16_nc<NC>(d_tmem, dah + ks * A_STEP, dbh + ks * B_STEP, idesc, 1);
-                            } else {
-                                umma_f16_nc<NC>(d_tmem, dah + ks * A_STEP, dbh + ks * B_STEP, idesc, (kc | ks) != 0);
                             }
                         }
-                        umma_commit_nc<NC>(&empty_bar[s]);    // frees the stage (in both CTAs) once these MMAs retire
+                        for (int j = 0; j < nck; ++j) {
+                            const uint32_t s = stage_descs(kit + j, kc0 + j, dah, dal, dbh, dbl);
+                            if (leader) {
+#pragma unroll
+                                for (int ks = 0; ks < BK / 16; ++ks)
+                                    umma_f16_nc<NC>(d_tmem, dah + ks * A_STEP, dbh + ks * B_STEP, idesc, 1);
+                                umma_commit_nc<NC>(&empty_bar[s]);    // frees the stage (in both CTAs) once these MMAs retire
+                            }
+                        }
+                    } else {
+                        for (int j = 0; j < nck; ++j) {
+                            const uint32_t s = stage_descs(kit + j, kc0 + j, dah, dal, dbh, dbl);
+                            if (leader) mbar_wait(&full_bar[s], ((kit + j) / (uint32_t)STAGES) & 1);
+                            __syncwarp();
+                            tc_fence_after();
+                            if (leader) {
+#pragma unroll
+                                for (int ks = 0; ks < BK / 16; ++ks) {
+                                    umma_f16_nc<NC>(d_tmem, dah + ks * A_STEP, dbl + ks * B_STEP, idesc, (j | ks) != 0);
+                                    umma_f16_nc<NC>(d_tmem, dal + ks * A_STEP, dbh + ks * B_STEP, idesc, 1);
+                                    umma_f16_nc<NC>(d_tmem, dah + ks * A_STEP, dbh + ks * B_STEP, idesc, 1);
+                                }
+                                umma_commit_nc<NC>(&empty_bar[s]);
+                            }
+                        }
                     }
+                    if (leader) umma_commit_nc<NC>(&acc_full[buf]);
+                    kit += (uint32_t)nck;
                 }
-                if (leader) umma_commit_nc<NC>(&acc_full[buf]);
             }
         }
         __syncwarp();
@@ -336,37 +407,22 @@ __device__ __forceinline__ void gemm_tc_body(const TcParams& q) {
         const bool leader = elect_one();
         uint32_t kit = 0;
         const int n0c = g.taps * g.a0_chunks_per_tap;     // k-chunks served by image a0
-        // A-side box of k-chunk kc of this CTA's tile in the unit's it-th iteration
-        auto coords = [&](int it_, int kc_, const CUtensorMap*& tm, int& row, int& plane) -> bool {
-            int mu, nt;
-            if (!tiles.get(it_, mu, nt)) return false;
+        for (int it = 0, mu, nt; tiles.get(it, mu, nt); ++it) {
             const int mt = mu * NC + (int)rank;
             const int to = mt / tiles_per_frame;
             const long long b0 = (long long)(mt - to * tiles_per_frame) * BM;
-            if (kc_ < n0c) {
-                const int j = kc_ / g.a0_chunks_per_tap, cc = kc_ - j * g.a0_chunks_per_tap;
-                row = (int)(g.a0.row0 + ((long long)to * g.stride + j - g.left) * g.Bp + b0);
-                plane = g.a0_plane0 + cc * 4; tm = &q.tm_a0;
-            } else {
-                row = (int)(g.a1.row0 + (long long)to * g.Bp + b0);
-                plane = g.a1_plane0 + (kc_ - n0c) * 4; tm = &q.tm_a1;
-            }
-            return true;
-        };
-        const CUtensorMap* tm; int row, plane;
-        int p_it = 0, p_kc = 0;                          // optional L2 prefetch cursor (off by default, see PREFETCH_AHEAD)
-        auto prefetch_next = [&]() {
-            if (p_it < 0) return;
-            if (coords(p_it, p_kc, tm, row, plane)) { if (leader) tma_img_prefetch(tm, row, plane); } else { p_it = -1; return; }
-            if (++p_kc == q.k_chunks) { p_kc = 0; ++p_it; }
-        };
-        for (int d = 0; d < q.prefetch_ahead; ++d) prefetch_next();
-        for (int it = 0, mu, nt; tiles.get(it, mu, nt); ++it) {
-            for (int vk = 0; vk < q.sweeps * q.k_chunks; ++vk, ++kit) {
-                const int kc = vk < q.k_chunks ? vk : vk - q.k_chunks;
-                const uint32_t s = kit % STAGES, ph = (kit / STAGES) & 1;
-                if (q.prefetch_ahead) prefetch_next();
-                coords(it, kc, tm, row, plane);
+            for (int kc = 0; kc < q.k_chunks; ++kc, ++kit) {
+                const uint32_t s = kit % (uint32_t)STAGES, ph = (kit / (uint32_t)STAGES) & 1;
+                // A-side box of k-chunk kc of this CTA's tile
+                const CUtensorMap* tm; int row, plane;
+                if (kc < n0c) {
+                    const int j = kc / g.a0_chunks_per_tap, cc = kc - j * g.a0_chunks_per_tap;
+                    row = (int)(g.a0.row0 + ((long long)to * g.stride + j - g.left) * g.Bp + b0);
+                    plane = g.a0_plane0 + cc * 4; tm = &q.tm_a0;
+                } else {
+                    row = (int)(g.a1.row0 + (long long)to * g.Bp + b0);
+                    plane = g.a1_plane0 + (kc - n0c) * 4; tm = &q.tm_a1;
+                }
                 uint8_t* st = ring + (size_t)s * stage_bytes;
                 if constexpr (NC == 1) {
                     const __half* wsrc = q.img + ((size_t)nt * q.k_chunks + kc) * (2 * (size_t)BN * BK);
@@ -496,9 +552,9 @@ int make_w_map(const __half* img2, size_t halfs, int BN, CUtensorMap* tm) {
     return CB_OK;
 }
 
-size_t smem_bytes_for(int BN) { return (size_t)STAGES * (2 * BM * BK * 2 + 2 * (size_t)BN * BK * 2) + 256; }
-size_t smem_bytes_resident(int BN, int k_chunks) {
-    return (size_t)k_chunks * 2 * BN * BK * 2 + (size_t)STAGES * (2 * BM * BK * 2) + 256;
+size_t smem_bytes_for(int BN, int stages) { return (size_t)stages * (2 * BM * BK * 2 + 2 * (size_t)BN * BK * 2) + 256; }
+size_t smem_bytes_resident(int BN, int k_chunks, int stages) {
+    return (size_t)k_chunks * 2 * BN * BK * 2 + (size_t)stages * (2 * BM * BK * 2) + 256;
 }
 // (the CTA-pair kernel holds BN/2 rows of B per CTA: pass BN/2)
 constexpr size_t SMEM_MAX = 232448;      // 227 KB of dynamic shared memory per CTA
@@ -513,7 +569,9 @@ int pick_bn(int N) {            // widest tile <= 256 that divides N (UMMA N mus
 
 // ---- host: weight images -------------------------------------------------------------------------------------------------
 // W is [K][N] fp32 (row k = input channel in the order the A operand presents it).
-int cb_tc_build_layer(cb_handle* h, int layer_id, const float* W, int K, int N) {
+// `chain_after`: truncating accumulator adds the OUTPUT of this contraction still goes through downstream (the LSTM
+// recurrence chains 21 MMAs on top of the input projection it is pre-loaded with); 0 for the convolutions.
+int cb_tc_build_layer(cb_handle* h, int layer_id, const float* W, int K, int N, int chain_after) {
     TcState* st = (TcState*)h->tc;
     TcLayer L;
     memset(&L, 0, sizeof(L));
@@ -522,6 +580,33 @@ int cb_tc_build_layer(cb_handle* h, int layer_id, const float* W, int K, int N) 
     L.n_tiles = N / L.BN;
     L.k_chunks = (K + BK - 1) / BK;
     L.Kpad = L.k_chunks * BK;
+    // k-chunks (of 32 input channels) per partial sum.  Reading a TMEM accumulator into registers costs tensor-pipe time
+    // (the drain of a 128x256 partial sum delays the MMAs by ~2 us, measured: profiles/r02_s1_*, r02_s3_*), so partial sums
+    // are as long as the error budget allows: 8 chunks = K 256 = 48 chained MMAs (a K=768 convolution is 3 partial sums,
+    // the K=256 ones a single accumulator as before), with the remaining truncation bias compensated in the weights
+    // (below).  Measured on the 4096 x 512 bench batch against the fp32 kernels / the float64 oracle (r02_s3_parity):
+    //   cpp  8: 0 windows with different greedy bases, max |dlogit| 3.9e-3, conv 11.9 ms     <- default
+    //   cpp 12: 2 windows, 5.7e-3, 11.5 ms;   one accumulator per tile: 3 windows, 1.0e-2, 10.0 ms;   cpp 2: 0, 1.2e-3, 20.7 ms
+    // CB_TC_CPP=n overrides it (n <= 3: low-order products of the whole partial sum first; n >= k_chunks: one accumulator).
+    static const int cpp_env = getenv("CB_TC_CPP") ? atoi(getenv("CB_TC_CPP")) : 8;
+    L.cpp = cpp_env > 0 && cpp_env < L.k_chunks ? cpp_env : L.k_chunks;
+    // TRUNCATION COMPENSATION.  The tensor core's fp32 accumulator rounds toward zero on every MMA, so an accumulated value
+    // shrinks by a small relative amount c per chained MMA (round-to-zero of a 24-bit significand loses half an ulp on
+    // average = 2^-24 * E[1/m] = 0.72 * 2^-24 for log-uniform significands m; CALIBRATED on the float64 oracle the constant is
+    // 0.42 * 2^-24: CNN-feature rms error 3.4e-6 uncompensated, 2.6e-7 at 0.4-0.45 -- profiles/r02_s2_diag, r02_s3_diag).
+    // A product that enters the chain at MMA number t of n is truncated (n - t + 1) times, so its weight is inflated by
+    // (1 + c*(n - t + 1)): first order, exact in expectation; what remains is the zero-mean part of the rounding errors, as in
+    // any fp32 summation.
+    const double comp_c = cb_tc_trunc_c();
+    const bool two_pass = L.cpp < MIN_STAGES;            // issue order of a partial sum (see gemm_tc_body)
+    auto comp = [&](int kc, int ks) {                   // inflation of the hi*hi products of K-step ks of chunk kc
+        const int p = kc / L.cpp, j = kc - p * L.cpp;
+        const int nck = (p + 1) * L.cpp <= L.k_chunks ? L.cpp : L.k_chunks - p * L.cpp;
+        const int steps = BK / 16;
+        // MMAs of the partial sum issued after and including this K-step's hi*hi product
+        const int after = two_pass ? (nck * steps - (j * steps + ks)) : 3 * (nck * steps - (j * steps + ks)) - 2;
+        return 1.0 + comp_c * (after + chain_after);
+    };
     float mx = 0.f;
     for (size_t i = 0; i < (size_t)K * N; ++i) mx = fmaxf(mx, fabsf(W[i]));
     int s = 0;
@@ -537,7 +622,7 @@ int cb_tc_build_layer(cb_handle* h, int layer_id, const float* W, int K, int N) 
                 for (int n = 0; n < L.BN; ++n)
                     for (int e = 0; e < 8; ++e) {
                         const int k = kc * BK + gq * 8 + e;
-                        const float w = k < K ? W[(size_t)k * N + nt * L.BN + n] * scale : 0.f;
+                        const float w = k < K ? (float)((double)W[(size_t)k * N + nt * L.BN + n] * scale * comp(kc, gq / 2)) : 0.f;
                         const __half hi = __float2half_rn(w);
                         const __half lo = __float2half_rn(w - __half2float(hi));
                         base[(size_t)gq * L.BN * 8 + n * 8 + e] = hi;
@@ -585,9 +670,9 @@ int cb_tc_prepare(cb_handle* h, const float* hw) {
     auto host = [&](const float* dev) { return hw + (dev - h->d_weights); };
     int rc;
     for (int b = 0; b < c.n_blocks; ++b) {
-        if (b > 0 && (rc = cb_tc_build_layer(h, b * 4 + 0, host(h->conv2a[b].W), C, C)) != CB_OK) return rc;
-        if ((rc = cb_tc_build_layer(h, b * 4 + 1, host(h->conv2b[b].W), c.k[b] * C, C)) != CB_OK) return rc;
-        if ((rc = cb_tc_build_layer(h, b * 4 + 2, host(h->convc[b].W), b == 0 ? C : 2 * C, C)) != CB_OK) return rc;
+        if (b > 0 && (rc = cb_tc_build_layer(h, b * 4 + 0, host(h->conv2a[b].W), C, C, 0)) != CB_OK) return rc;
+        if ((rc = cb_tc_build_layer(h, b * 4 + 1, host(h->conv2b[b].W), c.k[b] * C, C, 0)) != CB_OK) return rc;
+        if ((rc = cb_tc_build_layer(h, b * 4 + 2, host(h->convc[b].W), b == 0 ? C : 2 * C, C, 0)) != CB_OK) return rc;
     }
     // LSTM input projections.  Layer 0 reads the CNN feature image (K = C).  Later layers read the h image written by
     // the recurrence, whose planes are [fw: 13 k-groups (104 ch, 100 real)][bw: 13 k-groups]: K' = 208 with zero rows.
@@ -618,9 +703,11 @@ int cb_tc_prepare(cb_handle* h, const float* hw) {
             }
             for (int n = 0; n < N; ++n) {        // forget_bias 1.0 of TF's LSTMCell folded into the bias
                 const int nn = n % (4 * H);
-                bperm[(n / (4 * H)) * 4 * H + perm(nn)] = (bsrc[n] + (nn / H == 2 ? 1.0f : 0.0f)) * gate_scale(nn);
+                // (the bias rides through the recurrence's accumulator chain like the projection itself: same inflation)
+                bperm[(n / (4 * H)) * 4 * H + perm(nn)] =
+                    (float)((double)(bsrc[n] + (nn / H == 2 ? 1.0f : 0.0f)) * gate_scale(nn) * (1.0 + cb_tc_trunc_c() * CB_LSTM_TC_CHAIN));
             }
-            if ((rc = cb_tc_build_layer(h, 32 + l * 2 + d, W.data(), Kimg, N)) != CB_OK) return rc;
+            if ((rc = cb_tc_build_layer(h, 32 + l * 2 + d, W.data(), Kimg, N, CB_LSTM_TC_CHAIN)) != CB_OK) return rc;
             while (bias_all.size() & 3) bias_all.push_back(0.f);
             st->lstm_bias_off[l][d] = bias_all.size();
             bias_all.insert(bias_all.end(), bperm.begin(), bperm.end());
@@ -628,8 +715,7 @@ int cb_tc_prepare(cb_handle* h, const float* hw) {
     }
     CB_CUDA(cudaMalloc(&st->d_lstm_bias, bias_all.size() * sizeof(float)));
     CB_CUDA(cudaMemcpy(st->d_lstm_bias, bias_all.data(), bias_all.size() * sizeof(float), cudaMemcpyHostToDevice));
-    CB_CUDA(cudaMalloc(&st->d_range_flag, sizeof(int)));
-    CB_CUDA(cudaMemset(st->d_range_flag, 0, sizeof(int)));
+    st->d_range_flag = h->d_flag + CB_FLAG_TC_RANGE;     // sticky, reported by cb_check_deferred
     CB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
     CB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
     return cb_lstm_tc_prepare(h, hw);
@@ -640,10 +726,16 @@ void cb_tc_release(cb_handle* h) {
     TcState* st = (TcState*)h->tc;
     if (!st) return;
     for (auto& L : st->layers) { if (L.img) cudaFree(L.img); if (L.img2) cudaFree(L.img2); }
-    if (st->d_range_flag) cudaFree(st->d_range_flag);
     if (st->d_lstm_bias) cudaFree(st->d_lstm_bias);
     delete st;
     h->tc = nullptr;
+}
+
+// Mean relative shrink per truncating accumulator add (see cb_tc_build_layer).  CB_TC_BIAS overrides the factor E[1/m]
+// (0 switches the compensation off) for calibration runs.
+double cb_tc_trunc_c() {
+    static const double f = getenv("CB_TC_BIAS") ? atof(getenv("CB_TC_BIAS")) : 0.42;
+    return f * 5.9604644775390625e-08;      // * 2^-24
 }
 
 int* cb_tc_range_flag(cb_handle* h) { return h->tc ? ((TcState*)h->tc)->d_range_flag : nullptr; }
@@ -651,20 +743,6 @@ int* cb_tc_range_flag(cb_handle* h) { return h->tc ? ((TcState*)h->tc)->d_range_
 const float* cb_tc_lstm_bias(cb_handle* h, int layer, int d) {
     TcState* st = (TcState*)h->tc;
     return st->d_lstm_bias + st->lstm_bias_off[layer][d];
-}
-
-int cb_tc_check_range(cb_handle* h, cudaStream_t s) {
-    TcState* st = (TcState*)h->tc;
-    if (!st) return CB_OK;
-    int flag = 0;
-    CB_CUDA(cudaMemcpyAsync(&flag, st->d_range_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CB_CUDA(cudaStreamSynchronize(s));
-    if (flag) {
-        cudaMemsetAsync(st->d_range_flag, 0, sizeof(int), s);
-        cb_set_error("an activation exceeded the fp16 range of the tensor-core path; rerun with precision fp32");
-        return CB_ERR_RANGE;
-    }
-    return CB_OK;
 }
 
 int cb_launch_gemm_tc(cb_handle* h, const TcGemm& g, cudaStream_t s) {
@@ -688,13 +766,8 @@ int cb_launch_gemm_tc(cb_handle* h, const TcGemm& g, cudaStream_t s) {
     if (rc != CB_OK) return rc;
     q.g = g; q.img = L.img; q.BN = L.BN; q.n_tiles = L.n_tiles; q.k_chunks = L.k_chunks;
     q.m_tiles = g.T * (g.Bp / BM); q.out_scale = L.out_scale;
-    q.passes = h->precision == CB_PREC_TC_FAST ? 1 : 3;
     q.range_flag = st->d_range_flag;
-    static const int sweeps_env = getenv("CB_TC_SWEEPS") ? atoi(getenv("CB_TC_SWEEPS")) : 0;   // bit 0: projections, bit 1: convs
-    q.sweeps = (q.passes == 3 && ((L.n_tiles > 1 && (sweeps_env & 1)) ||
-                                  (L.n_tiles == 1 && ((sweeps_env & 2) || h->precision == CB_PREC_TC_PRECISE)))) ? 2 : 1;
-    static const int prefetch_env = getenv("CB_TC_PREFETCH") ? atoi(getenv("CB_TC_PREFETCH")) : PREFETCH_AHEAD;
-    q.prefetch_ahead = prefetch_env;
+    q.cpp = L.cpp;
     // CTA pairs (tcgen05 cta_group::2: M = 256 over two m-tiles, each CTA stages half of the B tile -- the single-CTA
     // kernel is bound by shared-memory bandwidth: three MMA passes re-read A and B, 96 B/clk + 62 B/clk of TMA writes
     // against the SM's 128 B/clk) whenever the m-tiles pair up; CB_TC_PAIR=0 forces the single-CTA kernel (A/B timing).
@@ -708,11 +781,20 @@ int cb_launch_gemm_tc(cb_handle* h, const TcGemm& g, cudaStream_t s) {
     // resident weights when the n-tile's image fits beside the A ring, the units can be dealt evenly over the n-tiles
     // and every unit gets enough m-tiles to amortise the weight load
     const int per_nt = units / L.n_tiles;
-    q.resident = L.n_tiles > 1 && smem_bytes_resident(L.BN / nc, L.k_chunks) <= SMEM_MAX && per_nt >= 1 &&
+    q.resident = L.n_tiles > 1 && smem_bytes_resident(L.BN / nc, L.k_chunks, MIN_STAGES) <= SMEM_MAX && per_nt >= 1 &&
                  m_units >= 8 * per_nt;
     const long long work = (long long)m_units * q.n_tiles;
     int grid = (int)(work < units ? work : units) * nc;
-    const size_t smem = q.resident ? smem_bytes_resident(L.BN / nc, L.k_chunks) : smem_bytes_for(L.BN / nc);
+    // as deep a ring as shared memory allows (the two-pass issue order holds cpp stages until their hi*hi products are out)
+    static const int stages_env = getenv("CB_TC_STAGES") ? atoi(getenv("CB_TC_STAGES")) : 0;
+    auto smem_for = [&](int stages) {
+        return q.resident ? smem_bytes_resident(L.BN / nc, L.k_chunks, stages) : smem_bytes_for(L.BN / nc, stages);
+    };
+    q.stages = MAX_STAGES;
+    while (q.stages > MIN_STAGES && smem_for(q.stages) > SMEM_MAX) --q.stages;
+    if (stages_env >= 2 && stages_env <= q.stages) q.stages = stages_env;
+    const size_t smem = smem_for(q.stages);
+    if (smem > SMEM_MAX) { cb_set_error("tensor-core path: layer %d needs %zu bytes of shared memory", g.layer_id, smem); return CB_ERR_ARG; }
     if (pair) {
         q.img = L.img2; q.tm_w = L.tm_w2;
         gemm_tc_pair_kernel<<<grid, NTHREADS, smem, s>>>(q);

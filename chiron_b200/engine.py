@@ -6,6 +6,7 @@ CUDA tensors (torch is plumbing for device memory and streams only) and pass raw
 from __future__ import annotations
 
 import ctypes
+import sys
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -63,18 +64,35 @@ def format_segments(file_pre: str, bases: np.ndarray, n_bases: np.ndarray) -> by
 
 
 class Basecaller:
-    def __init__(self, model: str = "DNA_default", device: int = 0, precision: str = "fp32",
+    def __init__(self, model: str = "DNA_default", device: int = 0, precision: str = "auto",
                  bn_mode: Optional[str] = None):
-        """``bn_mode``: None = what the model's blob header says; "population" / "batch" override it
+        """``precision``: "tc" = the tcgen05 tensor-core kernels (the production mode), "fp32" = the FFMA kernels,
+        "auto" (default) = "tc" whenever the model's topology is one the tensor-core kernels cover (the shipped
+        DNA_default / RNA_default and every residual stack of their shape), "fp32" otherwise (GRU cells, stem
+        convolutions, hidden != 100, batch-statistics BatchNorm) -- said once on stderr, never silently.
+        ``bn_mode``: None = what the model's blob header says; "population" / "batch" override it
         (cb_set_bn_mode; "batch" = HEAD's simple_global_bn, chiron/cnn.py:166-188, fp32 precision only)."""
         self.lib = _lib.load()
         self.cfg, _, blob = load_model(model)
         self.device = int(device)
-        self.precision = precision
         h = ctypes.c_void_p()
         buf = ctypes.create_string_buffer(blob, len(blob))
-        _lib.check(self.lib.cb_create(ctypes.cast(buf, ctypes.c_void_p), len(blob), self.device,
-                                      _lib.PRECISIONS[precision], ctypes.byref(h)), "cb_create")
+        if precision == "auto":
+            wants_batch_bn = bn_mode == "batch" or (bn_mode is None and getattr(self.cfg, "bn_mode", 0) == _lib.BN_BATCH)
+            rc = _lib.CB_ERR_ARG if wants_batch_bn else self.lib.cb_create(
+                ctypes.cast(buf, ctypes.c_void_p), len(blob), self.device, _lib.PREC_TC_SPLIT, ctypes.byref(h))
+            if rc == _lib.CB_OK:
+                precision = "tc"
+            elif rc == _lib.CB_ERR_ARG:
+                why = "batch-statistics BatchNorm" if wants_batch_bn else self.lib.cb_last_error().decode("utf-8", "replace")
+                sys.stderr.write("chiron_b200: model %s runs on the fp32 kernels (%s)\n" % (model, why))
+                precision = "fp32"
+            else:
+                _lib.check(rc, "cb_create")
+        self.precision = precision
+        if not h:
+            _lib.check(self.lib.cb_create(ctypes.cast(buf, ctypes.c_void_p), len(blob), self.device,
+                                          _lib.PRECISIONS[precision], ctypes.byref(h)), "cb_create")
         self.h = h
         if bn_mode is not None:
             rc = self.lib.cb_set_bn_mode(self.h, _lib.BN_MODES[bn_mode])
@@ -222,6 +240,13 @@ class Basecaller:
                                                bases.data_ptr(), n_bases.data_ptr(), ctypes.c_void_p(s)),
                        "cb_decode_beam")
         return bases, n_bases
+
+    def check_status(self, stream=None):
+        """Synchronise the stream and raise the deferred device-side errors of the asynchronous calls (cb_check_status):
+        an activation outside the fp16 range of the tensor-core path, a beam search that ran out of fallback workspaces."""
+        import torch
+        s = stream if stream is not None else torch.cuda.current_stream(torch.device("cuda", self.device)).cuda_stream
+        _lib.check(self.lib.cb_check_status(self.h, ctypes.c_void_p(s)), "cb_check_status")
 
     def debug_fetch(self, what: int, n_floats: int) -> np.ndarray:
         out = np.zeros(n_floats, dtype=np.float32)

@@ -223,12 +223,7 @@ def resolve_model(model: str) -> str:
             if fn.endswith(".cbw"):
                 return os.path.join(model, fn)
         if os.path.exists(os.path.join(model, "checkpoint")):
-            from .convert_weights import convert_checkpoint_dir
-            import tempfile
-            out = os.path.join(tempfile.gettempdir(), "chiron_b200_%s_%d.cbw" % (base, os.getpid()))
-            with open(out, "wb") as f:
-                f.write(convert_checkpoint_dir(model))
-            return out
+            return model                        # a TF checkpoint folder: load_model converts it in memory
     if os.path.exists(bundled_blob_path(base)):
         return bundled_blob_path(base)
     raise FileNotFoundError("cannot resolve model %r to a CBW1 weight blob" % model)
@@ -236,7 +231,11 @@ def resolve_model(model: str) -> str:
 
 def load_model(model: str) -> Tuple[ModelConfig, Dict[str, np.ndarray], bytes]:
     path = resolve_model(model)
-    with open(path, "rb") as f:
-        blob = f.read()
+    if os.path.isdir(path):                     # TF checkpoint folder: converted on the fly, nothing written to disk
+        from .convert_weights import convert_checkpoint_dir
+        blob = convert_checkpoint_dir(path)
+    else:
+        with open(path, "rb") as f:
+            blob = f.read()
     cfg, tensors = unpack_blob(blob)
     return cfg, tensors, blob

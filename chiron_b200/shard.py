@@ -43,3 +43,26 @@ def broadcast_blob(blob: bytes = None, src: int = 0, device=None) -> bytes:
         buf = torch.empty(int(n.item()), dtype=torch.uint8, device=dev)
     dist.broadcast(buf, src)
     return bytes(buf.cpu().numpy().tobytes())
+
+
+def gather_to_rank0(obj, timeout_s: float = 1800.0):
+    """Every rank's ``obj`` as a list on rank 0 (None elsewhere); [obj] when not launched distributed.  The one
+    control-plane exchange of a sharded `chiron call`: the per-rank timings that rank 0 merges into meta/all.meta
+    (SURVEY.md section 8e).  CPU tensors over a gloo group built from the torchrun environment (MASTER_ADDR/MASTER_PORT);
+    an already initialised process group is used as it is and left alone."""
+    rank, world = rank_world()
+    if world == 1:
+        return [obj]
+    import datetime
+    import torch.distributed as dist
+    own = not dist.is_initialized()
+    if own:
+        dist.init_process_group("gloo", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=timeout_s))
+    try:
+        group = dist.group.WORLD if dist.get_backend() == "gloo" else dist.new_group(backend="gloo")
+        out = [None] * world if rank == 0 else None
+        dist.gather_object(obj, out, dst=0, group=group)
+        return out
+    finally:
+        if own:
+            dist.destroy_process_group()

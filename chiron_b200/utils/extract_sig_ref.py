@@ -9,6 +9,7 @@ from __future__ import annotations
 import logging
 import os
 import shutil
+import sys
 import multiprocessing
 from multiprocessing import cpu_count
 
@@ -67,7 +68,7 @@ def _worker(job):
         return n
     except Exception as e:                       # extract_sig_ref.py:115-117: log and skip the file
         logger.error("Cannot extract file %s. %s" % (full, e))
-        return 0
+        return "Cannot extract file %s. %s" % (full, e)    # the parent logs it too: a spawned worker has no log handlers
 
 
 def extract(FLAGS) -> int:
@@ -108,5 +109,15 @@ def extract(FLAGS) -> int:
             counts = pool.map(_worker, jobs, chunksize=max(1, len(jobs) // (8 * threads)))
     else:
         counts = [_worker(j) for j in jobs]
-    FLAGS.count = int(sum(counts))
+    # Workers report a failure as its message: spawned workers do not inherit the parent's log handlers (the reference's
+    # forked ones did), so the parent writes log/extract.log and says how many files were skipped.
+    failures = [c for c in counts if isinstance(c, str)]
+    if threads > 1 and len(jobs) > 1:
+        for msg in failures:
+            logger.error(msg)
+    if failures:
+        print("chiron_b200: %d of %d input files could not be extracted (see %s)"
+              % (len(failures), len(jobs), os.path.join(FLAGS.log_folder, "extract.log")), file=sys.stderr)
+    FLAGS.count = int(sum(c for c in counts if not isinstance(c, str)))
+    FLAGS.skipped = len(failures)
     return FLAGS.count

@@ -39,11 +39,9 @@ enum {
 /* Arithmetic of the dense contractions (convolutions, LSTM gate GEMMs).  Accumulation is always fp32. */
 enum {
     CB_PREC_FP32 = 0,     /* fp32 FFMA SIMT kernels (reference-grade; slow path kept for A/B checks) */
-    CB_PREC_TC_SPLIT = 1, /* tcgen05 fp16 MMAs on hi/lo-split operands (3 MMAs per product, fp32-class error) */
-    CB_PREC_TC_FAST = 2,  /* tcgen05 single-pass fp16 MMAs (~1e-3 relative; not bit-parity safe) */
-    CB_PREC_TC_PRECISE = 3 /* CB_PREC_TC_SPLIT with the K range of every convolution swept twice -- all low-order products
-                            * first, then hi*hi -- so that only K/16 of the tensor core's truncating accumulator adds run at
-                            * full magnitude: about a third of the logit error of TC_SPLIT for +48 % convolution time */
+    CB_PREC_TC_SPLIT = 1  /* tcgen05 fp16 MMAs on hi/lo-split operands (3 MMAs per product), short-K partial sums added
+                           * in fp32 registers (the tensor core's accumulator truncates): fp32-class error.  The
+                           * production mode: `chiron call`, bench.py and the parity tests run it. */
 };
 
 /* BatchNorm statistics of the residual conv stack.  The shipped checkpoints hold pop_mean/pop_var and their graph uses
@@ -92,8 +90,9 @@ int cb_seq_len_out(cb_handle* h, const int32_t* seq_len_in, int B, int L, int32_
 int cb_forward(cb_handle* h, const float* x, const int32_t* seq_len_out, int B, int L,
                float* logits, float* path_prob, void* stream);
 
-/* Synchronise `stream` and report deferred device-side errors of the asynchronous calls above (CB_ERR_RANGE when an
- * activation left the fp16 range of the tensor-core path).  cb_basecall_host calls this itself. */
+/* Synchronise `stream` and report deferred device-side errors of the asynchronous calls (CB_ERR_RANGE when an activation
+ * left the fp16 range of the tensor-core path in cb_forward; CB_ERR_NOMEM when cb_decode_beam ran out of fallback
+ * workspaces).  The flags are sticky until reported.  cb_basecall_host and cb_basecall_collect call this themselves. */
 int cb_check_status(cb_handle* h, void* stream);
 
 /* tf.nn.ctc_greedy_decoder(merge_repeated=True) (chiron_eval.py:486-487).  Dense padded output replaces the
@@ -101,7 +100,10 @@ int cb_check_status(cb_handle* h, void* stream);
 int cb_decode_greedy(cb_handle* h, const float* logits, const int32_t* seq_len_out, int B, int T,
                      int8_t* bases, int32_t* n_bases, void* stream);
 
-/* tf.nn.ctc_beam_search_decoder(merge_repeated=False, beam_width, top_paths=1) (chiron_eval.py:489-492). */
+/* tf.nn.ctc_beam_search_decoder(merge_repeated=False, beam_width, top_paths=1) (chiron_eval.py:489-492).  Asynchronous like
+ * the other entry points: three passes are enqueued back to back (warp per window with a shared-memory trie; the windows
+ * whose trie outgrew it alone, one per CTA; what is still left over global workspaces that cannot overflow) and nothing is
+ * read back -- a failure of the last resort is reported by cb_check_status / cb_basecall_collect. */
 int cb_decode_beam(cb_handle* h, const float* logits, const int32_t* seq_len_out, int B, int T, int beam_width,
                    int8_t* bases, int32_t* n_bases, void* stream);
 

@@ -188,8 +188,9 @@ extern "C" int emu_greedy(const float* logits, const int32_t* lens, int B, int T
 }
 
 // CTC beam search: the warp-cooperative shared-memory kernel (warp = 1: logits from global memory, 2: staged in shared
-// memory) or the thread-per-window fallback (warp = 0), with
-// the pool sizes of cb_launch_beam.  Returns the overflow flag (0 = every window decoded), or a negative CB_ERR_* code.
+// memory; 16-bit trie nodes) or the thread-per-window kernel over global workspaces (warp = 0).  Returns 1 when a window
+// outgrew the pool (the cooperative kernels then report it as n_bases = -1, beam_kernel as an empty read), 0 when every
+// window decoded, or a negative CB_ERR_* code.
 extern "C" int emu_beam(int warp, const float* logits, const int32_t* lens, int B, int T, int C, int W, int pool,
                         int8_t* bases, int32_t* n_bases) {
     int overflow = 0;
@@ -210,7 +211,7 @@ extern "C" int emu_beam(int warp, const float* logits, const int32_t* lens, int 
         const size_t stride = cb_seq::align_up(cb_beam_work_bytes(W, pool), 16);
         std::vector<char> ws(stride * (size_t)B + 64);
         emu::launch((B + 63) / 64, 64, [&] {
-            cb_seq::beam_kernel(logits, lens, B, T, C, W, pool, ws.data(), stride, bases, n_bases, &overflow);
+            cb_seq::beam_kernel(logits, lens, B, T, C, W, pool, ws.data(), stride, bases, n_bases, &overflow, nullptr, 0);
         });
     }
     return overflow;
@@ -248,25 +249,33 @@ extern "C" int emu_gemm(const float* A, int lda, const float* W, const float* sh
 // The node pool cb_launch_beam gives the shared-memory beam search (cb_seq_kernels.cuh: beam_small_pool).
 extern "C" long long emu_beam_small_pool(int T, int W) { return cb_seq::beam_small_pool(T, W); }
 
-// The experimental two-pass beam search (CB_BEAM_RETRY): a first pass with a small pool that marks the windows overflowing it
-// (n_bases = -1), then beam_retry_kernel on the marked windows alone.  *n_marked receives how many windows the first pass
-// marked.  Returns the retry pass's overflow flag.
-extern "C" int emu_beam_retry(const float* logits, const int32_t* lens, int B, int T, int C, int W, int pool_first,
-                              int8_t* bases, int32_t* n_bases, int* n_marked) {
-    int overflow = 0;
+// The three passes of cb_launch_beam, exactly as it enqueues them: beam_warp_kernel with a first-pass pool of `pool_first`
+// nodes marks the windows that outgrow it (n_bases = -1), beam_retry_kernel redoes those alone with a pool of `pool_retry`
+// nodes (0 = the launcher's, what a CTA's shared memory holds), beam_kernel redoes what is still marked over `n_slots`
+// atomically claimed global workspaces that cannot overflow.  marked[0..2] receive the number of windows marked after each
+// pass (marked[2] > 0 only if the slots ran out).  Returns the sticky error flag of the last pass.
+extern "C" int emu_beam_passes(const float* logits, const int32_t* lens, int B, int T, int C, int W, int pool_first,
+                               int pool_retry, int n_slots, int8_t* bases, int32_t* n_bases, int* marked) {
+    int flag = 0, error = 0, slots = 0;
+    auto count = [&]() { int m = 0; for (int b = 0; b < B; ++b) m += n_bases[b] == -1; return m; };
     const size_t stride = cb_seq::beam_warp_stride(T, C, W, pool_first, false);
     emu::launch2d((B + cb_seq::BEAM_WARPS - 1) / cb_seq::BEAM_WARPS, 1, cb_seq::BEAM_WARPS * 32, stride * cb_seq::BEAM_WARPS, [&] {
-        cb_seq::beam_warp_kernel<false, true>(logits, lens, B, T, C, W, pool_first, (int)stride, bases, n_bases, &overflow);
+        cb_seq::beam_warp_kernel<false>(logits, lens, B, T, C, W, pool_first, (int)stride, bases, n_bases, &flag);
     });
-    int marked = 0;
-    for (int b = 0; b < B; ++b) marked += n_bases[b] == -1;
-    if (n_marked) *n_marked = marked;
-    if (!overflow) return marked ? -100 : 0;          // marks without the flag would be a bug
-    overflow = 0;
-    const long long pool_r = cb_seq::beam_retry_pool(T, W);
-    const size_t smem_r = cb_seq::align_up(cb_beam_work_bytes(W, (int)pool_r), 16);
+    marked[0] = count();
+    if ((marked[0] > 0) != (flag != 0)) return -100;          // marks without the flag (or the reverse) would be a bug
+    const long long pool_r = pool_retry > 0 ? pool_retry : cb_seq::beam_retry_pool(T, W);
+    const size_t smem_r = cb_seq::align_up(cb_beam_work_bytes<cb_seq::BeamIdx>(W, (int)pool_r), 16);
     emu::launch2d(B, 1, 32, smem_r, [&] {
-        cb_seq::beam_retry_kernel(logits, lens, B, T, C, W, (int)pool_r, bases, n_bases, &overflow);
+        cb_seq::beam_retry_kernel(logits, lens, B, T, C, W, (int)pool_r, bases, n_bases, &flag);
     });
-    return overflow;
+    marked[1] = count();
+    const int cap = 2 * W * (T + 1) + 2;
+    const size_t stride_g = cb_seq::align_up(cb_beam_work_bytes(W, cap), 16);
+    std::vector<char> ws(stride_g * (size_t)(n_slots > 0 ? n_slots : 1) + 64);
+    emu::launch((B + 63) / 64, 64, [&] {
+        cb_seq::beam_kernel(logits, lens, B, T, C, W, cap, ws.data(), stride_g, bases, n_bases, &error, &slots, n_slots);
+    });
+    marked[2] = count();
+    return error;
 }

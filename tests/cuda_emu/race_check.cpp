@@ -89,9 +89,10 @@ int main(int argc, char** argv) {
         for (int warp : {1, 2, 0})
             for (int W : {1, 5, 12})
                 if (emu_beam(warp, logits.data(), lens.data(), B, T, C, W, 2 * W * (T + 1) + 2, bases.data(), nbs.data()) != 0) return 4;
-        {   // the experimental two-pass search: a tiny first-pass pool so that windows are marked and retried
-            int marked = 0;
-            if (emu_beam_retry(logits.data(), lens.data(), B, T, C, 12, 2 * 12 + 2, bases.data(), nbs.data(), &marked) != 0) return 6;
+        {   // the launcher's three passes with tiny pools, so that windows are marked, retried and finished by the third pass
+            int marked[3] = {0, 0, 0};
+            if (emu_beam_passes(logits.data(), lens.data(), B, T, C, 12, 2 * 12 + 2, 3 * 12, B, bases.data(), nbs.data(), marked) != 0) return 6;
+            if (marked[2] != 0) return 7;
         }
         // ---- assembly: every kernel --------------------------------------------------------------------------------------------------
         std::uniform_int_distribution<int> base4(0, 3);

@@ -483,14 +483,16 @@ def test_decoders_on_the_reference_logits_sample(emu):
     sub = [0, 5, 9, 14, 20, 23]                        # emulation is slow: six windows go through the kernels ...
     for W in (30, 50):
         ref = O.ctc_decode_c(lg, lens, W)
-        pool = emu.emu_beam_small_pool(T, W)           # the launcher's pool: no window of real logits may overflow it
-        assert pool == (917 if W == 30 else 898) and pool >= 16 * W    # what four windows can hold in 192 KB of shared memory
+        pool = emu.emu_beam_small_pool(T, W)           # the first pass's pool: no window of these real logits overflows it
+        # 16W nodes grown into the slack of the occupancy step: 4 CTAs (16 warps) per SM at W=30, 2 at W=50 (26 B per node)
+        assert pool == (492 if W == 30 else 1014) and pool >= 16 * W
         small = 0
-        for b in range(B):                             # ... and all 24 through the same search, host-compiled (cb_selftest_beam)
-            row = np.ascontiguousarray(lg[b])
-            n = lib.cb_selftest_beam(row.ctypes.data_as(vp), int(lens[b]), C, W, pool, out.ctypes.data_as(vp))
-            assert n >= 0 and out[:n].tolist() == ref[b], (W, b, n)
-            small += lib.cb_selftest_beam(row.ctypes.data_as(vp), int(lens[b]), C, W, 6 * W, out.ctypes.data_as(vp)) == -2
+        for b in range(B):                             # ... and all 24 through the same search, host-compiled, with 32-bit
+            row = np.ascontiguousarray(lg[b])          # (beam_kernel) and 16-bit (shared-memory kernels) trie nodes
+            for fn in (lib.cb_selftest_beam, lib.cb_selftest_beam16):
+                n = fn(row.ctypes.data_as(vp), int(lens[b]), C, W, pool, out.ctypes.data_as(vp))
+                assert n >= 0 and out[:n].tolist() == ref[b], (W, b, n)
+            small += lib.cb_selftest_beam16(row.ctypes.data_as(vp), int(lens[b]), C, W, 6 * W, out.ctypes.data_as(vp)) == -2
         assert small >= 3                              # why the pool is not 6W: real logits overflow it regularly
         lg_s, lens_s = np.ascontiguousarray(lg[sub]), np.ascontiguousarray(lens[sub])
         for warp in ((1, 2) if W == 30 else (1,)):
@@ -505,21 +507,36 @@ def test_decoders_on_the_reference_logits_sample(emu):
     assert emu.emu_beam_small_pool(3, 30) == 2 * 30 * 4 + 2 and 64 <= emu.emu_beam_small_pool(300, 1) <= 128
 
 
-def test_experimental_two_pass_beam_search_on_real_logits(emu):
-    """CB_BEAM_RETRY (off by default, not yet run on a GPU): a first pass with a pool of 8W nodes marks the windows of the
-    reference's logits sample that overflow it, beam_retry_kernel redoes those alone with a CTA-sized pool; together they are
-    bit-identical to the C oracle."""
+def test_three_pass_beam_search_on_real_logits(emu):
+    """cb_launch_beam's three passes exactly as it enqueues them, on the reference's logits sample: a first pass whose pool
+    (here 6W nodes, so that windows DO overflow) marks the windows that outgrow it, beam_retry_kernel redoes those alone with
+    a CTA-sized pool, beam_kernel's slot mode finishes what is still marked; together bit-identical to the C oracle.  With a
+    starved retry pool the third pass does the work; with too few workspaces it raises the sticky error flag."""
     lg = np.load(os.path.join(os.path.dirname(HERE), "tests", "golden", "logits", "logits_sample_24.npy"))[:12]
     B, T, C = lg.shape
     lens = np.full(B, T, np.int32)
     lens[3] = 120
     W = 30
     vp = ctypes.c_void_p
-    bases = np.full((B, T), 9, np.int8)
-    n_bases = np.zeros(B, np.int32)
-    marked = ctypes.c_int(0)
-    rc = emu.emu_beam_retry(_fp(lg), lens.ctypes.data_as(vp), B, T, C, W, 6 * W, bases.ctypes.data_as(vp),
-                            n_bases.ctypes.data_as(vp), ctypes.byref(marked))
-    assert rc == 0 and 1 <= marked.value < B, (rc, marked.value)         # some windows overflow 6W, none the retry pool
-    assert [bases[b, :n_bases[b]].tolist() for b in range(B)] == O.ctc_decode_c(lg, lens, W)
+    ref = O.ctc_decode_c(lg, lens, W)
+
+    def run(pool_first, pool_retry, n_slots):
+        bases = np.full((B, T), 9, np.int8)
+        n_bases = np.zeros(B, np.int32)
+        marked = (ctypes.c_int * 3)()
+        rc = emu.emu_beam_passes(_fp(lg), lens.ctypes.data_as(vp), B, T, C, W, pool_first, pool_retry, n_slots,
+                                 bases.ctypes.data_as(vp), n_bases.ctypes.data_as(vp), marked)
+        return rc, list(marked), bases, n_bases
+
+    rc, marked, bases, n_bases = run(6 * W, 0, 4)
+    assert rc == 0 and 1 <= marked[0] < B and marked[1] == 0 and marked[2] == 0, (rc, marked)   # some overflow 6W, none the retry pool
+    assert [bases[b, :n_bases[b]].tolist() for b in range(B)] == ref
     assert all((bases[b, n_bases[b]:] == 0).all() for b in range(B))
+    rc, marked2, bases, n_bases = run(6 * W, 6 * W, B)             # a retry pool no larger than the first: the third pass decodes
+    assert rc == 0 and marked2[0] == marked2[1] == marked[0] and marked2[2] == 0, (rc, marked2)
+    assert [bases[b, :n_bases[b]].tolist() for b in range(B)] == ref
+    if marked[0] >= 2:                                           # fewer workspaces than marked windows: sticky error, rest decoded
+        rc, marked3, bases, n_bases = run(6 * W, 6 * W, 1)
+        assert rc == 1 and marked3[2] == 0
+        ok = [bases[b, :n_bases[b]].tolist() == ref[b] for b in range(B)]
+        assert sum(ok) == B - (marked[0] - 1) and all(n_bases[b] == 0 for b in range(B) if not ok[b])

@@ -12,10 +12,11 @@ L, JUMP, BEAM = 400, 390, 30
 B2I = {"A": 0, "C": 1, "G": 2, "T": 3}
 
 
-@pytest.fixture(scope="module")
-def caller():
+@pytest.fixture(scope="module", params=["tc", "fp32"])
+def caller(request):
+    """Both arithmetic modes: "tc" is what `chiron call` and bench.py run, "fp32" the FFMA kernels."""
     from chiron_b200.engine import Basecaller
-    bc = Basecaller("DNA_default", device=0, precision="fp32")
+    bc = Basecaller("DNA_default", device=0, precision=request.param)
     yield bc
     bc.close()
 

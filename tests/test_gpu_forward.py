@@ -9,11 +9,12 @@ from oracle import chiron_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-# Tolerance on CTC logits (|logit| <= ~20) against the float32 oracle; see DESIGN.md "Numerics".  The oracle itself
-# moves by 5e-4 between float32 and float64 (the three LSTM layers amplify rounding noise ~100x).  "fp32" = FFMA kernels
-# with round-to-nearest accumulation; "tc" = tcgen05 fp16 hi/lo split whose accumulator truncates (RZ) on every add
-# (measured maxima: 1.4e-2 on 9,600 frames, 3.7e-2 on 30,000 frames against the float64 oracle, no argmax flips).
-LOGIT_TOLS = {"fp32": 2e-3, "tc": 5e-2, "tc_precise": 2.5e-2}
+# Tolerance on CTC logits (|logit| <= ~20) against the oracle; see DESIGN.md "Numerics".  The float32 oracle itself moves by
+# 5.5e-4 against the float64 one (the three LSTM layers amplify rounding noise ~100x).  "fp32" = FFMA kernels with
+# round-to-nearest accumulation (measured maximum 9.7e-4 on 38,400 frames); "tc" = tcgen05 fp16 hi/lo split with short-K
+# partial sums and truncation compensation (measured maxima against the float64 oracle: 1.9e-3 on 38,400 frames of read1,
+# 3.9e-3 on 32,768 frames of the bench batch; the round-1 kernels: 1.8e-2 / 3.7e-2).
+LOGIT_TOLS = {"fp32": 2e-3, "tc": 5e-3}
 
 
 def _read1_windows(cfg, L=400, jump=390):
@@ -21,7 +22,7 @@ def _read1_windows(cfg, L=400, jump=390):
     return O.make_windows(O.normalize_signal(sig, cfg.sig_norm), L, jump)
 
 
-@pytest.fixture(scope="module", params=["fp32", "tc", "tc_precise"])
+@pytest.fixture(scope="module", params=["fp32", "tc"])
 def caller(request):
     from chiron_b200.engine import Basecaller
     bc = Basecaller("DNA_default", device=0, precision=request.param)
@@ -111,9 +112,10 @@ def test_full_row_groups_match_oracle(caller, dna_model):
 def test_full_size_batch_properties(dna_model):
     """BASELINE size (4096 windows x 512 samples, the bench workload) through size-independent properties:
     (1) a window's result does not depend on its batch (same rows alone in a 256-window batch: bit-identical logits);
-    (2) the tensor-core mode and the FFMA mode decode the same bases for >= 99.5 % of the windows (measured: 4087 of
-        4096; the tc logits carry ~1e-2 of accumulator-truncation noise, which flips near-tie argmaxes);
-    (3) 16 windows sampled from the big batch agree with the oracle within the stated tolerances, bases bit-exact."""
+    (2) the tensor-core mode -- the mode bench.py and `chiron call` run -- decodes EXACTLY the greedy bases the fp32 FFMA
+        mode decodes, for every one of the 4096 windows (the round-1 kernels differed in 9);
+    (3) 512 windows sampled from the big batch agree with the oracle: logits within the stated tolerances of the float64
+        oracle (262,144 frames), greedy bases bit-identical to the float32 oracle's in both modes."""
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from bench import synthetic_windows
@@ -129,14 +131,15 @@ def test_full_size_batch_properties(dna_model):
         assert np.array_equal(lg[sub], lg2) and np.array_equal(bases[sub], b2) and np.array_equal(nb[sub], n2)
         out[prec] = (bases, nb, lg)
         bc.close()
-    same = [(out["tc"][1][b] == out["fp32"][1][b]) and
-            np.array_equal(out["tc"][0][b, :out["tc"][1][b]], out["fp32"][0][b, :out["fp32"][1][b]]) for b in range(4096)]
-    assert sum(same) >= 0.995 * 4096, "tc and fp32 decode different bases in %d of 4096 windows" % (4096 - sum(same))
-    pick = np.random.default_rng(7).choice(4096, 16, replace=False)
-    ref = O.inference(x[pick], lens[pick], cfg, t)
-    ref_paths = O.ctc_greedy(ref, lens[pick])
+    differ = [b for b in range(4096) if out["tc"][1][b] != out["fp32"][1][b] or
+              not np.array_equal(out["tc"][0][b, :out["tc"][1][b]], out["fp32"][0][b, :out["fp32"][1][b]])]
+    assert not differ, "tc and fp32 decode different bases in %d of 4096 windows: %s" % (len(differ), differ[:10])
+    pick = np.sort(np.random.default_rng(7).choice(4096, 512, replace=False))
+    ref64 = O.inference(x[pick], lens[pick], cfg, t, np.float64)
+    ref_paths = O.ctc_greedy(ref64.astype(np.float32), lens[pick])
     for prec in ("tc", "fp32"):
         bases, nb, lg = out[prec]
-        assert np.abs(lg[pick] - ref).max() < LOGIT_TOLS[prec]
-        assert [bases[b, :nb[b]].tolist() for b in pick] == ref_paths
+        err = np.abs(lg[pick] - ref64).max()
+        assert err < LOGIT_TOLS[prec], "%s: max |dlogit| %.3e against the float64 oracle on 512 windows" % (prec, err)
+        assert [bases[b, :nb[b]].tolist() for b in pick] == ref_paths, prec
     assert 15 < out["fp32"][1].mean() < 30          # ~20.7 bases per 512-sample window on the bundled R9 reads

@@ -15,13 +15,19 @@ def _read(path):
         return f.read()
 
 
-def test_chiron_call_on_signal_folder_matches_golden_tree(tmp_path):
+@pytest.mark.parametrize("precision", [None, "fp32"], ids=["default_tc", "fp32"])
+def test_chiron_call_on_signal_folder_matches_golden_tree(tmp_path, precision):
     """`chiron call -p dna-pre` (batch 400, L 400, jump 390, beam 30): result/read1.fastq and segments/read1.fastq are
     byte-identical to the reference's files; read3's segments equal the golden ones after undoing the reference's
-    collation rotation (SURVEY.md finding 6) and its consensus is therefore produced from windows in true order."""
+    collation rotation (SURVEY.md finding 6) and its consensus is therefore produced from windows in true order.
+    Run as a user runs it (no --precision: the tensor-core kernels) and with the FFMA kernels."""
+    import json
     from chiron_b200 import entry
     out = str(tmp_path / "out")
-    entry.main(["call", "-i", os.path.join(GOLDEN, "DNA", "raw"), "-o", out, "-m", "DNA_default", "-p", "dna-pre"])
+    entry.main(["call", "-i", os.path.join(GOLDEN, "DNA", "raw"), "-o", out, "-m", "DNA_default", "-p", "dna-pre"]
+               + (["--precision", precision] if precision else []))
+    with open(os.path.join(out, "meta", "all.perf.json")) as f:
+        assert json.load(f)["precision"] == (precision or "tc")
     assert _read(os.path.join(out, "result", "read1.fastq")) == _read(os.path.join(GOLDEN, "DNA", "result", "read1.fastq"))
     assert _read(os.path.join(out, "segments", "read1.fastq")) == _read(os.path.join(GOLDEN, "DNA", "segments", "read1.fastq"))
     segs3 = read_fasta_records(os.path.join(out, "segments", "read3.fastq"))
@@ -41,7 +47,7 @@ def test_fast5_input_greedy_fasta_and_concise(tmp_path):
     src.mkdir()
     shutil.copy(os.path.join(GOLDEN, "fast5", "read1.fast5"), str(src / "read1.fast5"))
     out_a, out_b = str(tmp_path / "a"), str(tmp_path / "b")
-    common = ["-m", "DNA_default", "-l", "300", "-j", "290", "-b", "100", "--beam", "0", "-e", "fasta"]
+    common = ["-m", "DNA_default", "-l", "300", "-j", "290", "-b", "100", "--beam", "0", "-e", "fasta"]      # default precision: tc
     entry.main(["call", "-i", str(src), "-o", out_a] + common + ["--concise"])
     entry.main(["call", "-i", os.path.join(GOLDEN, "DNA", "raw", "read1.signal"), "-o", out_b] + common)
     fa = _read(os.path.join(out_a, "result", "read1.fasta"))
@@ -67,7 +73,7 @@ def test_batch_composition_does_not_change_results(tmp_path):
         flags = types.SimpleNamespace(input=os.path.join(GOLDEN, "DNA", "raw"), output=out, model="DNA_default", start=0,
                                       batch_size=bs, segment_len=400, jump=390, threads=0, beam=0, extension="fastq",
                                       concise=True, mode="dna", preset=None, recursive=True, reverse_fast5=False,
-                                      precision="fp32")
+                                      precision=None)
         chiron_eval.run(flags)
         outs.append(_read(os.path.join(out, "result", "read3.fastq")))
     os.environ.pop("CHIRON_B200_GPU_BATCH", None)
@@ -85,7 +91,7 @@ def test_two_slot_async_pipeline_matches_synchronous_call(dna_model):
     sig = O.read_signal_text(os.path.join(GOLDEN, "DNA", "raw", "read1.signal"))
     x, lens = O.make_windows(O.normalize_signal(sig, cfg.sig_norm), 300, 290)
     cuts = [(0, 40), (40, 150), (150, 151), (151, len(x))]
-    bc = Basecaller("DNA_default", device=0, precision="fp32")
+    bc = Basecaller("DNA_default", device=0)
     want = [bc.basecall_batch(x[a:b], lens[a:b], beam=0)[:3] for a, b in cuts]
     got, inflight = [], []
     for i, (a, b) in enumerate(cuts):
@@ -99,3 +105,44 @@ def test_two_slot_async_pipeline_matches_synchronous_call(dna_model):
     with pytest.raises(Exception):
         bc.basecall_collect((0, 1, bc.out_len(300)))          # empty slot
     bc.close()
+
+
+@pytest.mark.parametrize("jump,kernel,oracle_reads", [(270, "simple", (1, 3)), (290, "glue", (1, 2, 3, 4, 5)), (300, "stick", (1, 3))])
+def test_config1_five_reads_three_assembly_regimes(tmp_path, dna_model, jump, kernel, oracle_reads):
+    """BASELINE config 1 as stated: all five bundled reads (1,046,731 samples), `-l 300 -b 100 --beam 0`, in the default
+    (tensor-core) precision, at the three `-j` regimes that select the three assembly kernels (270 simple,
+    290 glue, 300 stick).  For every read: window coordinates, consensus and quality string equal the oracle's
+    simple_assembly of the decoded segments (the reference's easy_assembler restated, pinned by tests/golden/assembly_ref);
+    for the reads in ``oracle_reads`` (all five at -j 290) every window's greedy bases equal the CPU oracle's."""
+    import types
+    from chiron_b200 import chiron_eval
+    from oracle import chiron_oracle as O
+    cfg, t, _ = dna_model
+    L = 300
+    assert O.get_assembler_kernal(jump, L) == kernel
+    out = str(tmp_path / "out")
+    flags = types.SimpleNamespace(input=os.path.join(GOLDEN, "DNA", "raw"), output=out, model="DNA_default", start=0,
+                                  batch_size=100, segment_len=L, jump=jump, threads=0, beam=0, extension="fastq",
+                                  concise=False, mode="dna", preset=None, recursive=False, reverse_fast5=False, precision=None)
+    os.makedirs(out)
+    summary = chiron_eval.evaluation(flags)
+    assert flags.precision_used == "tc" and len(summary) == 5
+    assert sum(v["samples"] for v in summary.values()) == 1046731
+    for n in range(1, 6):
+        name = "read%d" % n
+        segs = read_fasta_records(os.path.join(out, "segments", name + ".fastq"))
+        info = summary[name + ".signal"]
+        pos = np.asarray(info["pos"])
+        assert len(segs) == int((pos >= 0).sum())
+        result = _read(os.path.join(out, "result", name + ".fastq")).split("\n")
+        if n in oracle_reads:                         # per-window bases against the oracle's forward pass + greedy decoder
+            sig = O.read_signal_text(os.path.join(GOLDEN, "DNA", "raw", name + ".signal"))
+            ref = O.basecall_signal(sig, cfg, t, L, jump, beam=0, batch=512)
+            assert segs == ref["segments"], "%s: windows decode differently from the oracle" % name
+            assert pos[pos >= 0].tolist() == ref["pos"].tolist()
+            assert result[1] == ref["consensus"] and result[3] == ref["qual"]
+        else:                                         # coordinates / consensus from the decoded segments themselves
+            cons, _, ref_pos = O.simple_assembly_qs(segs, None, jump / L, kernal=kernel)
+            assert pos[pos >= 0].tolist() == ref_pos.tolist()
+            assert result[1] == (O.index2base(np.argmax(cons, axis=0)) if cons.shape[1] else "")
+        assert result[0] == "@" + name and len(result[3]) == len(result[1])

@@ -14,7 +14,7 @@ from oracle import chiron_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 2e-3), ("tc", 3e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-3), ("tc", 5e-3)])
 def test_rna_default_matches_oracle(rna_model, precision, tol):
     from chiron_b200.engine import Basecaller
     cfg, t, _ = rna_model

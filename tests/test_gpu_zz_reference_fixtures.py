@@ -22,7 +22,7 @@ def test_cuda_assembly_reproduces_the_reference_assembler(path):
     for i, s in enumerate(segs):
         bases[i, :len(s)] = [BASE_IDX[c] for c in s]
         n_bases[i] = len(s)
-    bc = Basecaller("DNA_default", device=0, precision="fp32")
+    bc = Basecaller("DNA_default", device=0)
     for case in fx["cases"]:
         L = 400
         jump = int(round(case["jump_step_ratio"] * L))

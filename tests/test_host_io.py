@@ -87,7 +87,23 @@ def test_presets_and_kernel_choice():
                                            jump=None, threads=None, beam=None))
     assert [get_assembler_kernal(j, 300) for j in (270, 290, 300)] == ["simple", "glue", "stick"]
     files, d = list_input_files(types.SimpleNamespace(input=os.path.join(GOLDEN, "DNA", "raw"), recursive=True))
-    assert files == ["read1.signal", "read3.signal"]
+    assert files == ["read%d.signal" % i for i in range(1, 6)]
+
+
+def test_recursive_listing_keeps_sub_folder_paths(tmp_path):
+    """-r on a nested folder: the reference concatenates ``dirpath[dir_len:] + filename`` without a separator
+    (chiron_eval.py:283) and then cannot open the file; here the input name keeps its relative path and the output
+    prefix is flattened, so the read lands in the flat result/ segments/ meta/ folders."""
+    from chiron_b200.chiron_eval import output_prefix
+    (tmp_path / "sub" / "deep").mkdir(parents=True)
+    for rel in ("a.signal", "sub/b.signal", "sub/deep/c.fast5", "sub/notes.txt"):
+        (tmp_path / rel).write_text("1 2 3")
+    files, d = list_input_files(types.SimpleNamespace(input=str(tmp_path), recursive=True))
+    assert files == ["a.signal", os.path.join("sub", "b.signal"), os.path.join("sub", "deep", "c.fast5")]
+    assert all(os.path.exists(os.path.join(d, f)) for f in files)
+    assert [output_prefix(f) for f in files] == ["a", "sub__b", "sub__deep__c"]
+    files, _ = list_input_files(types.SimpleNamespace(input=str(tmp_path), recursive=False))
+    assert files == ["a.signal"]
 
 
 def test_read_assignment_is_a_balanced_partition():
@@ -158,7 +174,7 @@ def test_host_pipeline_end_to_end_with_a_stub_gpu(tmp_path, monkeypatch):
             submitted.append((slot, x.shape[0], int(seq_len.sum())))
             return super().basecall_submit(slot, x, seq_len, beam)
 
-    monkeypatch.setattr(chiron_eval, "Basecaller", lambda model, device=0, precision="fp32": Recorder(model))
+    monkeypatch.setattr(chiron_eval, "Basecaller", lambda model, device=0, precision="auto": Recorder(model))
     monkeypatch.setenv("CHIRON_B200_GPU_BATCH", "300")
     out = str(tmp_path / "out")
     args = types.SimpleNamespace(input=str(src), output=out, model="DNA_default", start=None, batch_size=None, segment_len=None,
@@ -171,7 +187,7 @@ def test_host_pipeline_end_to_end_with_a_stub_gpu(tmp_path, monkeypatch):
     assert {f for f in os.listdir(os.path.join(out, "meta"))} == {n + ".meta" for n in names} | {"all.meta", "all.perf.json"}
     with open(os.path.join(out, "meta", "all.perf.json")) as f:
         perf = json.load(f)
-    assert perf["reads"] == 8 and perf["samples"] == sum(n_samples.values()) and perf["precision"] == "tc"
+    assert perf["reads"] == 8 and perf["samples"] == sum(n_samples.values()) and perf["precision"] == "stub"
     assert perf["windows"] == sum(-(-n // 390) for n in n_samples.values())
     assert perf["Msamples_per_s"] > 0 and perf["world_size"] == 1 and perf["segment_len"] == 400 and perf["jump"] == 390
     # batching: windows are packed ACROSS reads into batches of >= 400 (the flag; the GPU batch was forced to 300), slots
@@ -187,37 +203,92 @@ def test_host_pipeline_end_to_end_with_a_stub_gpu(tmp_path, monkeypatch):
     assert open(os.path.join(out, "result", "empty.fastq")).read() == "@empty\n\n+\n\n"
 
 
-def test_read_sharding_of_the_host_pipeline_with_a_stub_gpu(tmp_path, monkeypatch):
-    """Two ranks (RANK / WORLD_SIZE as torchrun sets them) each basecall their own reads and write their own files: the
-    result files of the ranks partition the input, and each rank leaves its own all.rank<r>.meta / .perf.json."""
-    import json
-    import shutil
+def _sharded_call_worker(rank, world, port, src, out, q):
+    """One rank of a read-sharded `chiron call` with the GPU stubbed (spawned: its own interpreter, like torchrun's)."""
     import sys
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "tools"))
     from call_bench import StubCaller
     from chiron_b200 import chiron_eval
+    chiron_eval.Basecaller = lambda model, device=0, precision="auto": StubCaller(model)
+    args = types.SimpleNamespace(input=src, output=out, model="DNA_default", start=None, batch_size=None, segment_len=None,
+                                 jump=None, threads=2, beam=0, extension="fasta", concise=True, mode="dna", preset="dna-pre",
+                                 precision="auto", recursive=False)
+    chiron_eval.run(apply_preset(args))
+    q.put(rank)
+
+
+def test_read_sharding_of_the_host_pipeline_with_a_stub_gpu(tmp_path):
+    """Two ranks (separate processes with RANK / WORLD_SIZE / MASTER_* as torchrun sets them, gloo) basecall their own reads
+    into ONE output folder: the result files partition the input, each rank leaves all.rank<r>.meta / .perf.json, and
+    rank 0 merges them into meta/all.meta and meta/all.perf.json after one gather."""
+    import json
+    import multiprocessing as mp
+    import shutil
     src = tmp_path / "in"
     src.mkdir()
     for i in range(9):
         shutil.copy(os.path.join(GOLDEN, "DNA", "raw", "read1.signal" if i % 3 else "read3.signal"), str(src / ("r%02d.signal" % i)))
-    monkeypatch.setattr(chiron_eval, "Basecaller", lambda model, device=0, precision="fp32": StubCaller(model))
-    monkeypatch.setenv("WORLD_SIZE", "2")
-    done = []
+    out = str(tmp_path / "out")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 777) % 2000
+    procs = [ctx.Process(target=_sharded_call_worker, args=(r, 2, port, str(src), out, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    assert sorted(q.get(timeout=180) for _ in range(2)) == [0, 1]
+    for p in procs:
+        p.join(60)
+    assert {f[:-6] for f in os.listdir(os.path.join(out, "result"))} == {"r%02d" % i for i in range(9)}
+    per_rank = []
     for rank in (0, 1):
-        monkeypatch.setenv("RANK", str(rank))
-        monkeypatch.setenv("LOCAL_RANK", str(rank))
-        out = str(tmp_path / ("out%d" % rank))
-        args = types.SimpleNamespace(input=str(src), output=out, model="DNA_default", start=None, batch_size=None,
-                                     segment_len=None, jump=None, threads=2, beam=0, extension="fasta", concise=True, mode="dna",
-                                     preset="dna-pre", precision="fp32", recursive=False)
-        chiron_eval.run(apply_preset(args))
-        done.append({f[:-6] for f in os.listdir(os.path.join(out, "result"))})
         with open(os.path.join(out, "meta", "all.rank%d.perf.json" % rank)) as f:
-            perf = json.load(f)
-        assert perf["rank"] == rank and perf["world_size"] == 2 and perf["reads"] == len(done[-1])
+            per_rank.append(json.load(f))
+        assert per_rank[-1]["rank"] == rank and per_rank[-1]["world_size"] == 2
         assert os.path.exists(os.path.join(out, "meta", "all.rank%d.meta" % rank))
-    assert done[0] | done[1] == {"r%02d" % i for i in range(9)} and not (done[0] & done[1])
-    assert 3 <= len(done[0]) <= 6                                    # balanced by file size (shard.assign_reads)
+    assert 3 <= per_rank[0]["reads"] <= 6 and per_rank[0]["reads"] + per_rank[1]["reads"] == 9    # balanced by file size
+    with open(os.path.join(out, "meta", "all.perf.json")) as f:
+        merged = json.load(f)
+    assert merged["reads"] == 9 and merged["samples"] == per_rank[0]["samples"] + per_rank[1]["samples"]
+    assert merged["wall_s"] == max(r["wall_s"] for r in per_rank) and len(merged["per_rank"]) == 2
+    lines = open(os.path.join(out, "meta", "all.meta")).read().split("\n")
+    assert lines[0] == "# Wall_time Sys_time User_time Cpu_time" and len(lines[1].split()) == 4
+    assert abs(float(lines[1].split()[0]) - merged["wall_s"]) < 2e-3
+
+
+def test_batch_statistics_models_get_the_reference_batches(tmp_path, monkeypatch):
+    """A model whose BatchNorm uses the moments of the current batch (HEAD's simple_global_bn) must see the reference's
+    own batches: exactly -b windows each whatever CHIRON_B200_GPU_BATCH says, the last one wrap-padded to -b rows
+    (chiron_eval.py:322-329,352-358); with population statistics the same run packs >= gpu_batch windows per batch."""
+    import shutil
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "tools"))
+    from call_bench import StubCaller
+    from chiron_b200 import _lib, chiron_eval
+    src = tmp_path / "in"
+    src.mkdir()
+    for i in range(3):
+        shutil.copy(os.path.join(GOLDEN, "DNA", "raw", "read1.signal"), str(src / ("r%d.signal" % i)))
+    n_win = 3 * 161
+    for bn_mode, want_rows in ((_lib.BN_BATCH, [100] * 5), (_lib.BN_POPULATION, [300, n_win - 300])):
+        seen = []
+
+        class Recorder(StubCaller):
+            def basecall_submit(self, slot, x, seq_len, beam=0):
+                seen.append((x.copy(), seq_len.copy()))
+                return super().basecall_submit(slot, x, seq_len, beam)
+
+        monkeypatch.setattr(chiron_eval, "Basecaller", lambda model, device=0, precision="auto": Recorder(model, bn_mode))
+        monkeypatch.setenv("CHIRON_B200_GPU_BATCH", "300")
+        args = types.SimpleNamespace(input=str(src), output=str(tmp_path / ("out%d" % bn_mode)), model="DNA_default", start=0,
+                                     batch_size=100, segment_len=400, jump=390, threads=2, beam=0, extension="fasta",
+                                     concise=True, mode="dna", preset=None, precision="auto", recursive=False)
+        summary = chiron_eval.evaluation(args)
+        assert [len(x) for x, _ in seen] == want_rows
+        assert sum(v["windows"] for v in summary.values()) == n_win
+        if bn_mode == _lib.BN_BATCH:                      # 483 = 4 * 100 + 83: rows 83.. of the last batch repeat rows 0..
+            x, ln = seen[-1]
+            assert np.array_equal(x[83:], x[:17]) and np.array_equal(ln[83:], ln[:17])
 
 
 def test_multi_read_and_single_read_fast5_layouts(tmp_path):
@@ -280,7 +351,7 @@ def test_unreadable_input_fails_loudly_and_promptly(tmp_path, monkeypatch):
     shutil.copy(os.path.join(GOLDEN, "DNA", "raw", "read1.signal"), str(src / "a.signal"))
     (src / "b.signal").write_text("487 421 4x3 438\n")
     shutil.copy(os.path.join(GOLDEN, "DNA", "raw", "read1.signal"), str(src / "c.signal"))
-    monkeypatch.setattr(chiron_eval, "Basecaller", lambda model, device=0, precision="fp32": StubCaller(model))
+    monkeypatch.setattr(chiron_eval, "Basecaller", lambda model, device=0, precision="auto": StubCaller(model))
     args = types.SimpleNamespace(input=str(src), output=str(tmp_path / "out"), model="DNA_default", start=None, batch_size=None,
                                  segment_len=None, jump=None, threads=2, beam=0, extension="fastq", concise=False, mode="dna",
                                  preset="dna-pre", precision="fp32", recursive=False)
@@ -308,7 +379,7 @@ def test_chiron_call_cli_from_fast5_with_a_stub_gpu(tmp_path, monkeypatch):
     rng = np.random.default_rng(4)
     write_multi_read_fast5(str(src / "multi.fast5"), {"read_%02d" % i: (rng.integers(300, 800, size=900 + 400 * i).astype(np.int16),
                                                                        "uuid-%d" % i) for i in range(3)})
-    monkeypatch.setattr(chiron_eval, "Basecaller", lambda model, device=0, precision="fp32": StubCaller(model))
+    monkeypatch.setattr(chiron_eval, "Basecaller", lambda model, device=0, precision="auto": StubCaller(model))
     out = str(tmp_path / "out")
     entry.main(["call", "-i", str(src), "-o", out, "-p", "dna-pre", "--beam", "0", "-t", "2"])
     reads = ["multiread_00", "multiread_01", "multiread_02", "read1"]

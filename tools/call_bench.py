@@ -27,9 +27,11 @@ from chiron_b200.model import load_model
 class StubCaller:
     """Same surface as engine.Basecaller for evaluation(); returns ~20 bases per window without touching a GPU."""
 
-    def __init__(self, model):
+    def __init__(self, model, bn_mode=0):
         self.cfg, _, _ = load_model(model)
         self._rng = np.random.default_rng(0)
+        self.bn_mode = bn_mode
+        self.precision = "stub"
 
     def out_len(self, L):
         return self.cfg.out_len(L)

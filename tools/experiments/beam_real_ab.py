@@ -1,11 +1,10 @@
-"""Beam search on REAL logits (bootstrap windows of the bundled reads through the forward pass), for the next GPU session:
-the default launcher (one pass, pool sized for the tail), the experimental two-pass search (CB_BEAM_RETRY=1) and the
-thread-per-window fallback (CB_BEAM_SMEM=0).  One JSON line per (B, L, width): ms per decode, kernels launched per decode
-(1 = the fast path held, 2 = retry pass or fallback ran, 3 = both) and whether the outputs are identical."""
+"""Beam search on REAL logits (bootstrap windows of the bundled reads through the forward pass): the three-pass launcher
+with first-pass pools of 8W / 12W / the default (16W grown into the occupancy slack) / 24W nodes, and the thread-per-window
+kernel over global workspaces (CB_BEAM_SMEM=0).  One JSON line per (B, L, width): ms per decode (CUDA events on the launching
+stream), how many windows the first pass left marked, and whether all outputs are identical."""
 import json
 import os
 import sys
-import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
@@ -14,9 +13,10 @@ import torch
 from bench import synthetic_windows
 from chiron_b200.engine import Basecaller
 
-MODES = {"default": {}, "retry": {"CB_BEAM_RETRY": "1"}, "fallback": {"CB_BEAM_SMEM": "0"}}
-
-for B, L, W in ((4096, 512, 30), (4096, 400, 30), (512, 400, 30), (4096, 512, 50)):
+CASES = ((4096, 512, 30), (4096, 400, 30), (512, 400, 30), (4096, 512, 50), (1024, 512, 30))
+for B, L, W in CASES:
+    modes = {"pool_8W": {"CB_BEAM_POOL": str(8 * W)}, "pool_12W": {"CB_BEAM_POOL": str(12 * W)}, "default": {},
+             "pool_24W": {"CB_BEAM_POOL": str(24 * W)}, "global_kernel": {"CB_BEAM_SMEM": "0"}}
     bc = Basecaller("DNA_default", 0, "tc")
     xs, lens_h = synthetic_windows(B, L, 4321)
     x, lens = torch.from_numpy(xs).cuda(), torch.from_numpy(lens_h).cuda()
@@ -24,20 +24,24 @@ for B, L, W in ((4096, 512, 30), (4096, 400, 30), (512, 400, 30), (4096, 512, 50
     lg, _ = bc.forward_device(x, lo)
     torch.cuda.synchronize()
     res, outs = {}, {}
-    for mode, env in MODES.items():
-        for k in ("CB_BEAM_RETRY", "CB_BEAM_SMEM"):
+    for mode, env in modes.items():
+        for k in ("CB_BEAM_POOL", "CB_BEAM_SMEM"):
             os.environ.pop(k, None)
         os.environ.update(env)
         bases, nb = bc.decode_device(lg, lo, beam=W)            # warm-up (workspace, attributes)
         torch.cuda.synchronize()
-        n0, t0 = bc.launches, time.perf_counter()
-        reps = 1 if mode == "fallback" else 3
+        reps = 1 if mode == "global_kernel" else 3
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = bc.launches
+        e0.record()
         for _ in range(reps):
             bases, nb = bc.decode_device(lg, lo, beam=W)
+        e1.record()
         torch.cuda.synchronize()
-        res[mode] = {"ms": round((time.perf_counter() - t0) / reps * 1e3, 2), "launches_per_decode": (bc.launches - n0) / reps}
+        res[mode] = {"ms": round(e0.elapsed_time(e1) / reps, 2), "launches_per_decode": (bc.launches - n0) / reps}
         outs[mode] = (bases.cpu(), nb.cpu())
-    same = all(torch.equal(outs[m][0], outs["fallback"][0]) and torch.equal(outs[m][1], outs["fallback"][1]) for m in outs)
-    print(json.dumps({"B": B, "L": L, "beam": W, "bases_per_window": round(float(outs["fallback"][1].float().mean()), 1),
+        bc.check_status()
+    same = all(torch.equal(outs[m][0], outs["global_kernel"][0]) and torch.equal(outs[m][1], outs["global_kernel"][1]) for m in outs)
+    print(json.dumps({"B": B, "L": L, "beam": W, "bases_per_window": round(float(outs["default"][1].float().mean()), 1),
                       "modes": res, "identical": same}), flush=True)
     bc.close()

@@ -20,12 +20,15 @@ print("oracle f32 vs f64: fea max %.3e rms %.3e | logits max %.3e rms %.3e | |fe
       % (np.abs(fea32 - fea64).max(), np.sqrt(((fea32 - fea64) ** 2).mean()), np.abs(lg32 - lg64).max(),
          np.sqrt(((lg32 - lg64) ** 2).mean()), np.abs(fea64).max()))
 am64 = lg64.argmax(2)
-for prec in sys.argv[2:] or ["fp32", "tc", "tc_fast"]:
+for prec in sys.argv[2:] or ["fp32", "tc"]:
     bc = Basecaller("DNA_default", 0, prec)
     bases, nb, prob, lg = bc.basecall_batch(x, lens, want_logits=True)
     fea = bc.debug_fetch(0, fea64.size).reshape(fea64.shape)
     lasth = bc.debug_fetch(cfg.n_layers, lasth64.size).reshape(lasth64.shape)
     flips = int((lg.argmax(2) != am64).sum())
+    # relative bias of the CNN feature: least-squares slope of the error on the value (a truncating accumulator shrinks)
+    slope = float(((fea - fea64) * fea64).sum() / (fea64 * fea64).sum())
+    print("%-8s fea error slope %.3e (relative bias)" % (prec, slope))
     print("%-8s fea max %.3e rms %.3e | lasth max %.3e rms %.3e | logits max %.3e rms %.3e | argmax flips %d / %d"
           % (prec, np.abs(fea - fea64).max(), np.sqrt(((fea - fea64) ** 2).mean()), np.abs(lasth - lasth64).max(),
              np.sqrt(((lasth - lasth64) ** 2).mean()), np.abs(lg - lg64).max(), np.sqrt(((lg - lg64) ** 2).mean()),
