@@ -191,7 +191,7 @@ def evaluation(flags=None, caller: Optional[Basecaller] = None) -> Dict[str, dic
         file_pre = output_prefix(st.name)
         # the segment strings are built by the writer thread: this thread's job is to keep the GPU fed
         write_q.put((st.bases, st.n_bases, seq, [st.start_time, st.reading_time, basecall_time, assembly_time], file_pre, qual))
-        summary[st.name] = {"windows": st.n, "samples": st.samples, "bases": len(seq), "pos": pos}
+        summary[st.name] = {"windows": st.n, "samples": st.samples, "bases": len(seq), "pos": pos, "kept": st.n_bases > 0}
 
     # ---- finisher thread: per-read assembly off the GPU-feeding thread ---------------------------------------------------
     # cb_assemble_host synchronises its own (default) stream; while the forward kernels of two batches occupy the SMs the

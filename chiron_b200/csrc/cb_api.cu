@@ -395,6 +395,16 @@ extern "C" int cb_last_forward_profile(const cb_handle* h, float* ms, int* count
         if (cudaEventElapsedTime(&t, h->prof_ev[i][0], h->prof_ev[i][1]) != cudaSuccess) return 0;
         if (h->prof_cat[i] < m) { ms[h->prof_cat[i]] += t; count[h->prof_cat[i]]++; }
     }
+    static const bool dump = getenv("CB_PROF_DUMP") != nullptr;      // development: every timed launch of the forward, in order
+    if (dump) {
+        fprintf(stderr, "cb_forward launches (ms):");
+        for (int i = 0; i < h->prof_n; ++i) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, h->prof_ev[i][0], h->prof_ev[i][1]);
+            fprintf(stderr, " %d:%.3f", h->prof_cat[i], t);
+        }
+        fprintf(stderr, "\n");
+    }
     return m;
 }
 

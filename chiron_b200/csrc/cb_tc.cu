@@ -35,6 +35,10 @@
 #include "cb_internal.cuh"
 #include "cb_tc_common.cuh"
 
+#ifndef CB_TC_DEV
+#define CB_TC_DEV 0            // 1: timeline probe of the partial-sum hand-over (CB_TC_PROBE=<layer id>) compiled in
+#endif
+
 namespace {
 
 constexpr int BM = 128;          // rows (windows of one frame) per tile = UMMA M
@@ -42,7 +46,14 @@ constexpr int BK = 32;           // K elements per pipeline stage (2 UMMA K-step
 constexpr int MIN_STAGES = 4, MAX_STAGES = 6;   // depth of the operand ring (as many as fit in shared memory)
 constexpr int ACC_COLS = 128;    // accumulator columns an epilogue thread sums in registers (half of the widest tile)
 constexpr int N_EPI_WARPS = 8;   // two per TMEM lane quadrant (each takes half of the tile's columns)
-constexpr int NTHREADS = (N_EPI_WARPS + 2) * 32;   // 320
+// 12 warps = 3 warpgroups: two of epilogue warps, one holding the MMA warp, the loader warp and two idle warps.  The kernel
+// is compiled for 168 registers per thread (65536 / 384); setmaxnreg then moves registers from the third warpgroup to the
+// epilogue warps, which keep 128 fp32 partial-sum accumulators AND 64 columns of tcgen05.ld results in flight per thread.
+// (The single-CTA kernel -- the LSTM input projection, one accumulator per tile, HBM-write-bound -- keeps the plain 10-warp
+// layout: measured 2.75 instead of 2.22 ms per launch with the 12-warp layout.)
+constexpr int NTHREADS = (N_EPI_WARPS + 4) * 32;   // 384 (CTA-pair kernel)
+constexpr int NTHREADS1 = (N_EPI_WARPS + 2) * 32;  // 320 (single-CTA kernel)
+constexpr int EPI_REGS = 224, AUX_REGS = 56;       // 256 * 224 + 128 * 56 = 64512 <= 65536
 
 struct TcLayer {                 // one prepared weight image
     __half* img;                 // [n_tiles][k_chunks][2 (hi,lo)][4 k-groups][BN rows][8]
@@ -72,6 +83,10 @@ struct TcParams {
                                  // cpp*2 full-magnitude MMAs; the partial sums are added in registers
     int resident;                // 1: the CTA keeps its n-tile of W in shared memory (see header)
     int* range_flag;
+    long long* dbg;              // development probe (CB_TC_DEV): clock64 stamps of the first partial sums of CTA 0
+    uint32_t vec_off;            // byte offset of the cached epilogue vectors in shared memory (0 = read them with LDG)
+    int early_release;           // several partial sums per tile: give the TMEM buffer back before the output tile is written
+    int stagger;                 // units start this many fractions of a tile time apart (0 = together)
 };
 
 // Which (m-unit, n-tile) a scheduling unit (a CTA, or a CTA pair) works on in its i-th iteration.  Streaming mode: work
@@ -149,8 +164,421 @@ __device__ __forceinline__ void tma_w_g2s_pair(void* dst, const CUtensorMap* tm,
 
 // shared memory: q.stages x { A_hi[4][128][8], A_lo, B_hi[4][BNL][8], B_lo } halfs (BNL = BN / NC rows of the B tile live in
 // this CTA), then the barriers; resident mode: k_chunks x {B_hi, B_lo} first, stages hold A only.
-template <int NC>
+// MULTI: several partial sums per tile (q.cpp < q.k_chunks); the single-accumulator instantiation carries none of the
+// register-accumulation code (with it compiled in, the HBM-write-bound input projection ran 2.7 instead of 2.2 ms).
+template <int NC, bool MULTI>
 __device__ __forceinline__ void gemm_tc_body(const TcParams& q) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const TcGemm& g = q.g;
+    const int BN = q.BN, BNL = q.BN / NC;
+    const int STAGES = q.stages;
+    constexpr uint32_t a_bytes = BM * BK * 2;             // one of hi / lo
+    const uint32_t b_bytes = (uint32_t)BNL * BK * 2;
+    const uint32_t stage_bytes = q.resident ? 2 * a_bytes : 2 * a_bytes + 2 * b_bytes;
+    const uint32_t res_bytes = q.resident ? (uint32_t)q.k_chunks * 2 * b_bytes : 0;
+    uint8_t* ring = smem + res_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)STAGES * stage_bytes);
+    uint64_t* full_bar = bars;                            // [STAGES]  operands landed (pair: in BOTH CTAs; leader's barrier)
+    uint64_t* empty_bar = bars + MAX_STAGES;              // [STAGES]  MMAs that read the stage retired
+    uint64_t* acc_full = bars + 2 * MAX_STAGES;           // [2]       partial sum ready for the epilogue warps
+    uint64_t* acc_empty = bars + 2 * MAX_STAGES + 2;      // [2]       partial sum read (pair: by both CTAs; leader's)
+    uint64_t* w_bar = bars + 2 * MAX_STAGES + 4;          //           resident weights landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = NC == 2 ? cluster_ctarank() : 0;            // pair: rank 0 = leader (issues the MMAs)
+    const TileIter tiles(q, (int)blockIdx.x / NC, (int)gridDim.x / NC, q.m_tiles / NC);
+    const int tiles_per_frame = g.Bp / BM;
+    const int n_part = (q.k_chunks + q.cpp - 1) / q.cpp;  // partial sums per tile
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], NC * N_EPI_WARPS); }
+        mbar_init(w_bar, 1);
+        fence_barrier_init();
+        if (q.resident) {                                 // this CTA's part of its n-tile of W: one contiguous image
+            const uint32_t chunk = 2 * b_bytes;
+            mbar_arrive_expect_tx(w_bar, (uint32_t)q.k_chunks * chunk);
+            const int nt = tiles.nt_fixed;
+            for (int kc = 0; kc < q.k_chunks; ++kc)
+                bulk_g2s(smem + (size_t)kc * chunk, q.img + (((size_t)nt * q.k_chunks + kc) * NC + rank) * (chunk / 2), chunk, w_bar);
+            mbar_wait(w_bar, 0);
+        }
+    }
+    if (warp == N_EPI_WARPS) {                            // MMA warp owns the TMEM allocation (all 512 columns)
+        if constexpr (NC == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        }
+    }
+    if (q.vec_off) {
+        float* v = reinterpret_cast<float*>(smem + q.vec_off);
+        for (int i = threadIdx.x; i < BN; i += (int)blockDim.x) {
+            v[i] = __ldg(g.shift + i);
+            v[BN + i] = g.res ? __ldg(g.rw + i) : 0.f;
+            v[2 * BN + i] = g.res ? __ldg(g.rinv + i) : 0.f;
+            v[3 * BN + i] = g.res ? __ldg(g.rsh + i) : 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if constexpr (NC == 2) cluster_sync_all();            // both CTAs' barriers, weights and TMEM exist before any remote signal
+    const uint32_t tmem_base = *tmem_slot;
+    // epilogue vectors (BN shift, rank-1 residual terms) of a contraction whose N is one tile: read from shared memory in the
+    // emit (the per-16-column LDG round trips were the largest stall of the epilogue warps: ncu r02_s11)
+    float* epi_vec = reinterpret_cast<float*>(smem + q.vec_off);
+    const bool vec_cached = q.vec_off != 0;
+
+    if constexpr (NC == 2 && MULTI) {
+        if (warp < N_EPI_WARPS) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AUX_REGS));
+    }
+
+    if (warp < N_EPI_WARPS) {
+        // ============================ epilogue: partial sums TMEM -> registers (+=) -> scale/shift/residual/ReLU -> HBM =====
+        const int quad = warp & 3, chalf = warp >> 2;     // TMEM lane quadrant, which half of the tile's columns
+        const int first = ((BN / 16 + 1) / 2) * 16;       // BN is a multiple of 16; the two column halves are 16-col aligned
+        const int cbeg = chalf ? first : 0, cend = chalf ? BN : first;      // cend - cbeg <= ACC_COLS
+        uint32_t acc_empty_leader[2];
+        for (int b = 0; b < 2; ++b)
+            acc_empty_leader[b] = NC == 2 ? mapa_shared(smem_u32(&acc_empty[b]), 0) : smem_u32(&acc_empty[b]);
+        uint32_t it = 0, pit = 0;                          // tiles / partial sums this unit has worked on
+        bool overflow = false;
+        for (int mu, nt; tiles.get((int)it, mu, nt); ++it) {
+            const int mt = mu * NC + (int)rank;
+            const int to = mt / tiles_per_frame;
+            const int b = (mt - to * tiles_per_frame) * BM + quad * 32 + lane;
+            const bool row_ok = b < g.B;
+            float xr = 0.f;
+            if (g.res && row_ok) xr = __ldg(g.xT + (size_t)to * g.res_stride * g.Bp + b);
+            const size_t orow = (size_t)g.o.row0 + (size_t)to * g.Bp + b;
+            // 16 finished sums (columns n0..n0+15 of this thread's row) -> scale/shift/residual/ReLU -> HBM
+            auto emit = [&](int n0, const float (&sum)[16]) {
+                float o[16];
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const int n = n0 + q4 * 4;
+                    float4 sh;
+                    if (vec_cached) sh = *reinterpret_cast<const float4*>(epi_vec + n); else sh = ldg4(g.shift + n);
+                    o[q4 * 4 + 0] = fmaf(sum[q4 * 4 + 0], q.out_scale, sh.x);
+                    o[q4 * 4 + 1] = fmaf(sum[q4 * 4 + 1], q.out_scale, sh.y);
+                    o[q4 * 4 + 2] = fmaf(sum[q4 * 4 + 2], q.out_scale, sh.z);
+                    o[q4 * 4 + 3] = fmaf(sum[q4 * 4 + 3], q.out_scale, sh.w);
+                    if (g.res) {
+                        float4 w, iv, rs;
+                        if (vec_cached) {
+                            w = *reinterpret_cast<const float4*>(epi_vec + BN + n);
+                            iv = *reinterpret_cast<const float4*>(epi_vec + 2 * BN + n);
+                            rs = *reinterpret_cast<const float4*>(epi_vec + 3 * BN + n);
+                        } else {
+                            w = ldg4(g.rw + n); iv = ldg4(g.rinv + n); rs = ldg4(g.rsh + n);
+                        }
+                        o[q4 * 4 + 0] += fmaf(xr * w.x, iv.x, rs.x);
+                        o[q4 * 4 + 1] += fmaf(xr * w.y, iv.y, rs.y);
+                        o[q4 * 4 + 2] += fmaf(xr * w.z, iv.z, rs.z);
+                        o[q4 * 4 + 3] += fmaf(xr * w.w, iv.w, rs.w);
+                    }
+                }
+                if (g.relu) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) o[e] = fmaxf(o[e], 0.f);
+                }
+                if (g.out_mode == 2) {                    // hi/lo operand image for the next contraction
+#pragma unroll
+                    for (int h8 = 0; h8 < 2; ++h8) {
+                        float v8[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            v8[e] = o[h8 * 8 + e];
+                            overflow |= !(fabsf(v8[e]) <= 65504.f);
+                        }
+                        uint4 hi, lo;
+                        split8(v8, hi, lo);
+                        const size_t off = ((size_t)(g.o_plane0 + (n0 >> 3) + h8) * g.o.plane_rows + orow) * 8;
+                        *reinterpret_cast<uint4*>(g.o.hi + off) = hi;
+                        *reinterpret_cast<uint4*>(g.o.lo + off) = lo;
+                    }
+                } else {                                  // fp32 [to][n/4][Bp][4]: every store instruction of a warp writes
+                                                          // 512 contiguous bytes (16 full sectors)
+                    float4* dst = reinterpret_cast<float4*>(g.out) + ((size_t)to * (g.ldo >> 2) + (n0 >> 2)) * g.Bp + b;
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4)
+                        dst[(size_t)q4 * g.Bp] = make_float4(o[q4 * 4], o[q4 * 4 + 1], o[q4 * 4 + 2], o[q4 * 4 + 3]);
+                }
+            };
+            // This warp has read the buffer (pair: arrival on the leader's barrier).  RELAXED arrival: the default
+            // .release semantics make the warp wait until everything it stored before -- the whole output tile -- is
+            // visible at CTA / cluster scope (measured: 1,100 clocks per arrival, 2 us after an emit), and nothing of that
+            // needs ordering: the only hazard is the tensor core overwriting TMEM columns this warp still reads, and its
+            // tcgen05.ld results are complete (tcgen05.wait::ld) before the arrival is even issued.
+            auto release = [&](uint32_t buf) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (NC == 1)
+                        mbar_arrive(&acc_empty[buf]);
+                    else
+                        asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(acc_empty_leader[buf]) : "memory");
+                }
+            };
+            if constexpr (!MULTI) {
+                // one accumulator per tile: stream it out 16 columns at a time (TMEM -> registers costs tensor-pipe time:
+                // measured ~64 B/clk per SM and not overlapped with the MMAs, so every column is read exactly once)
+                const uint32_t buf = pit & 1, par = (pit >> 1) & 1;
+                ++pit;
+                mbar_wait(&acc_full[buf], par);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (uint32_t)BN;
+                for (int c0 = cbeg; c0 < cend; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + c0, v);
+                    tmem_ld_wait();
+                    if (!row_ok) continue;
+                    float sum[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) sum[e] = __uint_as_float(v[e]);
+                    emit(nt * BN + c0, sum);
+                }
+                release(buf);
+            } else {
+                // several partial sums per tile: all but the last are added up in registers, the last is streamed out
+                float acc[ACC_COLS];
+#pragma unroll
+                for (int e = 0; e < ACC_COLS; ++e) acc[e] = 0.f;
+                for (int p = 0; p < n_part; ++p, ++pit) {
+                    const uint32_t buf = pit & 1, par = (pit >> 1) & 1;
+                    const bool last = p == n_part - 1;
+                    const bool probe = CB_TC_DEV && q.dbg && blockIdx.x == 0 && warp == 0 && lane == 0 && pit >= 24 && pit < 56;
+                    if (CB_TC_DEV) { if (probe) q.dbg[(pit - 24) * 8 + 0] = clock64(); __syncwarp(); }
+                    mbar_wait(&acc_full[buf], par);
+                    tc_fence_after();
+                    if (CB_TC_DEV) { if (probe) q.dbg[(pit - 24) * 8 + 1] = clock64(); __syncwarp(); }
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (uint32_t)BN + (uint32_t)cbeg;
+                    if (!last || q.early_release) {
+                        // 64 columns in flight per wait (a tcgen05.ld round trip is ~190 clocks whatever its width); the
+                        // single-CTA kernel has no registers to spare for that (no setmaxnreg): 16 columns
+                                constexpr int DEPTH = NC == 2 ? 4 : 1;
+#pragma unroll
+                        for (int j = 0; j < ACC_COLS / 16; j += DEPTH) {
+                            if (cbeg + j * 16 < cend) {            // (warp-uniform)
+                                uint32_t v[DEPTH][16];
+#pragma unroll
+                                for (int d = 0; d < DEPTH; ++d)
+                                    if (cbeg + (j + d) * 16 < cend) tmem_ld16(taddr + (j + d) * 16, v[d]);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int d = 0; d < DEPTH; ++d)
+                                    if (cbeg + (j + d) * 16 < cend) {
+#pragma unroll
+                                        for (int e = 0; e < 16; ++e) acc[(j + d) * 16 + e] += __uint_as_float(v[d][e]);
+                                    }
+                            }
+                        }
+                    } else if (!q.early_release) {
+#pragma unroll
+                        for (int j = 0; j < ACC_COLS / 16; ++j) {
+                            if (cbeg + j * 16 < cend) {            // (warp-uniform)
+                                uint32_t v[16];
+                                tmem_ld16(taddr + j * 16, v);
+                                tmem_ld_wait();
+                                if (row_ok) {
+                                    float sum[16];
+#pragma unroll
+                                    for (int e = 0; e < 16; ++e) sum[e] = acc[j * 16 + e] + __uint_as_float(v[e]);
+                                    emit(nt * BN + cbeg + j * 16, sum);
+                                }
+                            }
+                        }
+                    }
+                    if (last && q.early_release) {
+                        // The output tile leaves from the registers AFTER the TMEM buffer went back to the tensor core: while
+                        // this warp is busy with scale/shift/ReLU/split and ~4 KB of stores per thread, the MMAs of the next
+                        // tile's second partial sum already run (with the buffer held until the last store was issued, the
+                        // tensor pipe idled for most of every emit: measured 7-9 k clocks per tile at 2 chunks per partial sum).
+                        if (CB_TC_DEV) { if (probe) q.dbg[(pit - 24) * 8 + 2] = clock64(); __syncwarp(); }
+                        release(buf);
+                        if (CB_TC_DEV) { if (probe) q.dbg[(pit - 24) * 8 + 3] = clock64(); __syncwarp(); }
+                        if (row_ok) {
+#pragma unroll
+                            for (int j = 0; j < ACC_COLS / 16; ++j) {
+                                if (cbeg + j * 16 < cend) {
+                                    float sum[16];
+#pragma unroll
+                                    for (int e = 0; e < 16; ++e) sum[e] = acc[j * 16 + e];
+                                    emit(nt * BN + cbeg + j * 16, sum);
+                                }
+                            }
+                        }
+                        continue;
+                    }
+                    if (CB_TC_DEV) { if (probe) q.dbg[(pit - 24) * 8 + 2] = clock64(); __syncwarp(); }
+                    release(buf);
+                    if (CB_TC_DEV) { if (probe) q.dbg[(pit - 24) * 8 + 3] = clock64(); __syncwarp(); }
+                }
+            }
+        }
+        if (overflow) atomicExch(q.range_flag, 1);
+    } else if (warp == N_EPI_WARPS) {
+        // ============================ MMA issuer (whole warp runs the loop, one elected lane issues; pair: leader CTA) ======
+        const bool leader = elect_one();
+        const uint32_t idesc = make_idesc_f16(BM * NC, BN);
+        constexpr uint32_t A_STEP = 2 * BM;               // two k-groups per UMMA K-step, in 16-byte units
+        const uint32_t B_STEP = 2 * (uint32_t)BNL;
+        // a partial sum's chunks are all resident at once (low-order products of every chunk first, then hi*hi) when the
+        // ring can hold them and still load ahead; longer partial sums order the products chunk by chunk
+        const bool two_pass = q.cpp < MIN_STAGES;
+        uint32_t kit = 0, it = 0, pit = 0;
+        auto stage_descs = [&](uint32_t k, int kc, uint64_t& dah, uint64_t& dal, uint64_t& dbh, uint64_t& dbl) {
+            const uint32_t s = k % (uint32_t)STAGES;
+            const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
+            const uint32_t sb = q.resident ? smem_u32(smem) + (uint32_t)kc * 2 * b_bytes : sa + 2 * a_bytes;
+            dah = make_desc(sa, BM * 16, 128); dal = make_desc(sa + a_bytes, BM * 16, 128);
+            dbh = make_desc(sb, BNL * 16, 128); dbl = make_desc(sb + b_bytes, BNL * 16, 128);
+            return s;
+        };
+        // (Tried and dropped: testing the next partial sum's barriers -- its TMEM buffer, its first operand stage -- while the
+        // current one still issues MMAs, to spare the barrier round trips at the boundary: neutral at 4 chunks per partial
+        // sum, 7-9 % slower at 2-3, where the extra cluster-scope tests sit between the two issue passes.)
+        if (rank == 0) {
+            for (int mu, nt; tiles.get((int)it, mu, nt); ++it) {
+                for (int p = 0; p < n_part; ++p, ++pit) {
+                    const uint32_t buf = pit & 1, par = (pit >> 1) & 1;
+                    const bool probe = CB_TC_DEV && q.dbg && blockIdx.x == 0 && leader && pit >= 24 && pit < 56;
+                    if (CB_TC_DEV) { if (probe) q.dbg[(pit - 24) * 8 + 4] = clock64(); }
+                    if (leader) {                         // the epilogue warps have read the previous contents of this buffer
+                        if constexpr (NC == 1) mbar_wait(&acc_empty[buf], par ^ 1); else mbar_wait_cluster(&acc_empty[buf], par ^ 1);
+                    }
+                    __syncwarp();
+                    tc_fence_after();
+                    if (CB_TC_DEV) { if (probe) q.dbg[(pit - 24) * 8 + 5] = clock64(); }
+                    const uint32_t d_tmem = tmem_base + buf * (uint32_t)BN;
+                    const int kc0 = p * q.cpp;
+                    const int nck = q.k_chunks - kc0 < q.cpp ? q.k_chunks - kc0 : q.cpp;
+                    uint64_t dah, dal, dbh, dbl;
+                    if (two_pass) {
+                        for (int j = 0; j < nck; ++j) {   // low-order products, while the accumulator is small
+                            const uint32_t s = stage_descs(kit + j, kc0 + j, dah, dal, dbh, dbl);
+                            if (leader) mbar_wait(&full_bar[s], ((kit + j) / (uint32_t)STAGES) & 1);
+                            __syncwarp();
+                            tc_fence_after();
+                            if (leader) {
+#pragma unroll
+                                for (int ks = 0; ks < BK / 16; ++ks) {
+                                    umma_f16_nc<NC>(d_tmem, dah + ks * A_STEP, dbl + ks * B_STEP, idesc, (j | ks) != 0);
+                                    umma_f16_nc<NC>(d_tmem, dal + ks * A_STEP, dbh + ks * B_STEP, idesc, 1);
+                                }
+                            }
+                        }
+                        for (int j = 0; j < nck; ++j) {
+                            const uint32_t s = stage_descs(kit + j, kc0 + j, dah, dal, dbh, dbl);
+                            if (leader) {
+#pragma unroll
+                                for (int ks = 0; ks < BK / 16; ++ks)
+                                    umma_f16_nc<NC>(d_tmem, dah + ks * A_STEP, dbh + ks * B_STEP, idesc, 1);
+                                umma_commit_nc<NC>(&empty_bar[s]);    // frees the stage (in both CTAs) once these MMAs retire
+                            }
+                        }
+                    } else {
+                        for (int j = 0; j < nck; ++j) {
+                            const uint32_t s = stage_descs(kit + j, kc0 + j, dah, dal, dbh, dbl);
+                            if (leader) mbar_wait(&full_bar[s], ((kit + j) / (uint32_t)STAGES) & 1);
+                            __syncwarp();
+                            tc_fence_after();
+                            if (leader) {
+#pragma unroll
+                                for (int ks = 0; ks < BK / 16; ++ks) {
+                                    umma_f16_nc<NC>(d_tmem, dah + ks * A_STEP, dbl + ks * B_STEP, idesc, (j | ks) != 0);
+                                    umma_f16_nc<NC>(d_tmem, dal + ks * A_STEP, dbh + ks * B_STEP, idesc, 1);
+                                    umma_f16_nc<NC>(d_tmem, dah + ks * A_STEP, dbh + ks * B_STEP, idesc, 1);
+                                }
+                                umma_commit_nc<NC>(&empty_bar[s]);
+                            }
+                        }
+                    }
+                    if (leader) umma_commit_nc<NC>(&acc_full[buf]);
+                    if (CB_TC_DEV) { if (probe) q.dbg[(pit - 24) * 8 + 6] = clock64(); }
+                    kit += (uint32_t)nck;
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == N_EPI_WARPS + 1) {
+        // ============================ loader: weight + activation images (TMA) ================================================
+        const bool leader = elect_one();
+        uint32_t kit = 0;
+        const int n0c = g.taps * g.a0_chunks_per_tap;     // k-chunks served by image a0
+        if (q.stagger > 0) {
+            // Every unit needs the same time per tile, so all SMs would write their output tiles in the same instant, in a
+            // burst bounded by the HBM write bandwidth (measured: ~12 k clocks per emit, in which the tensor pipe can run
+            // ahead by two partial sums only).  The units therefore start q.stagger-th fractions of a tile time apart and
+            // stay out of phase: the emits of different SMs interleave with the loads of the others.
+            const long long wait_clk = (long long)(((int)blockIdx.x / NC) % q.stagger) * q.k_chunks * 768 / q.stagger;
+            const long long t_begin = clock64();
+            while (clock64() - t_begin < wait_clk) { }
+        }
+        for (int it = 0, mu, nt; tiles.get(it, mu, nt); ++it) {
+            const int mt = mu * NC + (int)rank;
+            const int to = mt / tiles_per_frame;
+            const long long b0 = (long long)(mt - to * tiles_per_frame) * BM;
+            for (int kc = 0; kc < q.k_chunks; ++kc, ++kit) {
+                const uint32_t s = kit % (uint32_t)STAGES, ph = (kit / (uint32_t)STAGES) & 1;
+                // A-side box of k-chunk kc of this CTA's tile
+                const CUtensorMap* tm; int row, plane;
+                if (kc < n0c) {
+                    const int j = kc / g.a0_chunks_per_tap, cc = kc - j * g.a0_chunks_per_tap;
+                    row = (int)(g.a0.row0 + ((long long)to * g.stride + j - g.left) * g.Bp + b0);
+                    plane = g.a0_plane0 + cc * 4; tm = &q.tm_a0;
+                } else {
+                    row = (int)(g.a1.row0 + (long long)to * g.Bp + b0);
+                    plane = g.a1_plane0 + (kc - n0c) * 4; tm = &q.tm_a1;
+                }
+                uint8_t* st = ring + (size_t)s * stage_bytes;
+                if constexpr (NC == 1) {
+                    const __half* wsrc = q.img + ((size_t)nt * q.k_chunks + kc) * (2 * (size_t)BN * BK);
+                    if (leader) {
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+                        tma_img_g2s(st, tm, row, plane, &full_bar[s]);
+                        if (!q.resident) bulk_g2s(st + 2 * a_bytes, wsrc, 2 * b_bytes, &full_bar[s]);
+                    }
+                } else {
+                    // both CTAs fill their own stage; every byte is counted on the leader's barrier
+                    const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[s]), 0);
+                    const int wrow = (((nt * q.k_chunks + kc) * 2 + (int)rank) * BN) / 32;      // 2 KB rows of the weight image
+                    if (leader) {
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * stage_bytes);
+                        tma_img_g2s_pair(st, tm, row, plane, full_leader);
+                        if (!q.resident) tma_w_g2s_pair(st + 2 * a_bytes, &q.tm_w, wrow, full_leader);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if constexpr (NC == 2) cluster_sync_all();            // the leader's MMAs read the peer's shared memory and TMEM
+    if (warp == N_EPI_WARPS) {
+        tc_fence_after();
+        if constexpr (NC == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+    }
+}
+
+// ---- the single-CTA kernel (LSTM input projection): the body as it was before the CTA-pair kernel grew its register
+// accumulation machinery.  Kept verbatim: every later variant of the shared body ran this HBM-write-bound contraction at
+// 2.5-2.7 instead of 2.2 ms per launch (it reads its A operand twice from DRAM: the five CTAs that share an m-tile fall out
+// of step and lose the L2 / TMA request merging; ncu r02).
+// shared memory: q.stages x { A_hi[4][128][8], A_lo, B_hi[4][BNL][8], B_lo } halfs (BNL = BN / NC rows of the B tile live in
+// this CTA), then the barriers; resident mode: k_chunks x {B_hi, B_lo} first, stages hold A only.
+template <int NC>
+__device__ __forceinline__ void gemm_tc_body_v1(const TcParams& q) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const TcGemm& g = q.g;
     const int BN = q.BN, BNL = q.BN / NC;
@@ -458,9 +886,13 @@ __device__ __forceinline__ void gemm_tc_body(const TcParams& q) {
     }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams q) { gemm_tc_body<1>(q); }
+template <bool MULTI>
+__global__ void __launch_bounds__(NTHREADS1, 1) gemm_tc_kernel(const __grid_constant__ TcParams q) {
+    if constexpr (MULTI) gemm_tc_body<1, true>(q); else gemm_tc_body_v1<1>(q);
+}
+template <bool MULTI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) gemm_tc_pair_kernel(const __grid_constant__ TcParams q) {
-    gemm_tc_body<2>(q);
+    gemm_tc_body<2, MULTI>(q);
 }
 
 // x[B][L] -> xT[L][Bp]  (so that everything downstream reads the raw signal coalesced over windows)
@@ -580,15 +1012,21 @@ int cb_tc_build_layer(cb_handle* h, int layer_id, const float* W, int K, int N, 
     L.n_tiles = N / L.BN;
     L.k_chunks = (K + BK - 1) / BK;
     L.Kpad = L.k_chunks * BK;
-    // k-chunks (of 32 input channels) per partial sum.  Reading a TMEM accumulator into registers costs tensor-pipe time
-    // (the drain of a 128x256 partial sum delays the MMAs by ~2 us, measured: profiles/r02_s1_*, r02_s3_*), so partial sums
-    // are as long as the error budget allows: 8 chunks = K 256 = 48 chained MMAs (a K=768 convolution is 3 partial sums,
-    // the K=256 ones a single accumulator as before), with the remaining truncation bias compensated in the weights
-    // (below).  Measured on the 4096 x 512 bench batch against the fp32 kernels / the float64 oracle (r02_s3_parity):
-    //   cpp  8: 0 windows with different greedy bases, max |dlogit| 3.9e-3, conv 11.9 ms     <- default
-    //   cpp 12: 2 windows, 5.7e-3, 11.5 ms;   one accumulator per tile: 3 windows, 1.0e-2, 10.0 ms;   cpp 2: 0, 1.2e-3, 20.7 ms
-    // CB_TC_CPP=n overrides it (n <= 3: low-order products of the whole partial sum first; n >= k_chunks: one accumulator).
-    static const int cpp_env = getenv("CB_TC_CPP") ? atoi(getenv("CB_TC_CPP")) : 8;
+    // k-chunks (of 32 input channels) per partial sum = how many MMAs are chained into one TMEM accumulator (6 per chunk).
+    // The hand-over of a partial sum to the epilogue warps is not free (the MMA warp's issue loop, and the output tile of
+    // the previous tile still being written while only two partial sums fit in TMEM), so partial sums are as long as the
+    // error budget allows.  Measured on the 4096 x 512 bench batch (conv stack ms sustained / logit rms error against the
+    // float64 oracle; the fp32 FFMA kernels: 1.1e-5; profiles/r02_*):
+    //   convolutions:  1 accumulator per tile 9.5 ms / 1.1e-4    8 chunks 9.7 / 4.1e-5    4 chunks 12.0 / 2.4e-5
+    //                  3 chunks 12.7 / 1.7e-5   <- default         2 chunks 13.7 / 1.7e-5
+    //   (largest logit error on 262,144 frames: 1.6e-2 / 6.6e-3 / 5.4e-3 / 3.7e-3 at 8 / 4 / 3 / 2 chunks; fp32 kernels 4.1e-3;
+    //    greedy bases identical to the fp32 kernels' on all 4096 windows from 8 chunks down)
+    //   LSTM input projections (HBM-write-bound, K <= 256): one accumulator (2.2 ms; 2.9 ms with two partial sums)
+    // CB_TC_CPP / CB_TC_CPP_PROJ override (n <= 3: low-order products of the whole partial sum first; n >= k_chunks: one
+    // accumulator).
+    static const int cpp_conv = getenv("CB_TC_CPP") ? atoi(getenv("CB_TC_CPP")) : 3;
+    static const int cpp_proj = getenv("CB_TC_CPP_PROJ") ? atoi(getenv("CB_TC_CPP_PROJ")) : 8;
+    const int cpp_env = layer_id >= 32 ? cpp_proj : cpp_conv;
     L.cpp = cpp_env > 0 && cpp_env < L.k_chunks ? cpp_env : L.k_chunks;
     // TRUNCATION COMPENSATION.  The tensor core's fp32 accumulator rounds toward zero on every MMA, so an accumulated value
     // shrinks by a small relative amount c per chained MMA (round-to-zero of a 24-bit significand loses half an ulp on
@@ -716,8 +1154,10 @@ int cb_tc_prepare(cb_handle* h, const float* hw) {
     CB_CUDA(cudaMalloc(&st->d_lstm_bias, bias_all.size() * sizeof(float)));
     CB_CUDA(cudaMemcpy(st->d_lstm_bias, bias_all.data(), bias_all.size() * sizeof(float), cudaMemcpyHostToDevice));
     st->d_range_flag = h->d_flag + CB_FLAG_TC_RANGE;     // sticky, reported by cb_check_deferred
-    CB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-    CB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    CB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    CB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    CB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    CB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
     return cb_lstm_tc_prepare(h, hw);
 }
 
@@ -793,16 +1233,52 @@ int cb_launch_gemm_tc(cb_handle* h, const TcGemm& g, cudaStream_t s) {
     q.stages = MAX_STAGES;
     while (q.stages > MIN_STAGES && smem_for(q.stages) > SMEM_MAX) --q.stages;
     if (stages_env >= 2 && stages_env <= q.stages) q.stages = stages_env;
-    const size_t smem = smem_for(q.stages);
+    size_t smem = smem_for(q.stages);
+    q.vec_off = 0;
+    if (L.n_tiles == 1 && smem + 4 * (size_t)L.BN * sizeof(float) <= SMEM_MAX) {     // behind the ring and the barriers
+        q.vec_off = (uint32_t)smem;
+        smem += 4 * (size_t)L.BN * sizeof(float);
+    }
     if (smem > SMEM_MAX) { cb_set_error("tensor-core path: layer %d needs %zu bytes of shared memory", g.layer_id, smem); return CB_ERR_ARG; }
+    q.dbg = nullptr;
+    static const int early_env = getenv("CB_TC_EARLY") ? atoi(getenv("CB_TC_EARLY")) : 1;
+    static const int stagger_env = getenv("CB_TC_STAGGER") ? atoi(getenv("CB_TC_STAGGER")) : 4;
+    q.early_release = early_env;
+    q.stagger = q.k_chunks > q.cpp ? stagger_env : 0;
+#if CB_TC_DEV
+    static long long* d_dbg = nullptr;
+    const int probe_layer = getenv("CB_TC_PROBE") ? atoi(getenv("CB_TC_PROBE")) : -1;
+    if (probe_layer == g.layer_id) {
+        if (!d_dbg) cudaMalloc(&d_dbg, 32 * 8 * sizeof(long long));
+        cudaMemset(d_dbg, 0, 32 * 8 * sizeof(long long));
+        q.dbg = d_dbg;
+    }
+#endif
+    static const int force_multi = getenv("CB_TC_FORCE_MULTI") ? atoi(getenv("CB_TC_FORCE_MULTI")) : 0;   // A/B
+    const bool multi = q.cpp < q.k_chunks || force_multi;
     if (pair) {
         q.img = L.img2; q.tm_w = L.tm_w2;
-        gemm_tc_pair_kernel<<<grid, NTHREADS, smem, s>>>(q);
+        if (multi) gemm_tc_pair_kernel<true><<<grid, NTHREADS, smem, s>>>(q);
+        else gemm_tc_pair_kernel<false><<<grid, NTHREADS, smem, s>>>(q);
     } else {
-        gemm_tc_kernel<<<grid, NTHREADS, smem, s>>>(q);
+        if (multi) gemm_tc_kernel<true><<<grid, NTHREADS1, smem, s>>>(q);
+        else gemm_tc_kernel<false><<<grid, NTHREADS1, smem, s>>>(q);
     }
     CB_CHECK_LAUNCH();
     h->launches++;
+#if CB_TC_DEV
+    if (q.dbg) {          // timeline of partial sums 24..55 of CTA 0: epilogue warp 0 and the MMA warp (clocks from the first stamp)
+        long long hb[32 * 8];
+        cudaStreamSynchronize(s);
+        cudaMemcpy(hb, q.dbg, sizeof(hb), cudaMemcpyDeviceToHost);
+        const long long t0 = hb[4];
+        fprintf(stderr, "layer %d: k_chunks %d cpp %d stages %d\n", g.layer_id, q.k_chunks, q.cpp, q.stages);
+        for (int i = 0; i < 32; ++i)
+            fprintf(stderr, "  partial %2d | mma: wait_empty %7lld got %7lld issued %7lld | epi: wait_full %7lld got %7lld drained %7lld released %7lld\n",
+                    24 + i, hb[i * 8 + 4] - t0, hb[i * 8 + 5] - t0, hb[i * 8 + 6] - t0, hb[i * 8 + 0] - t0, hb[i * 8 + 1] - t0,
+                    hb[i * 8 + 2] - t0, hb[i * 8 + 3] - t0);
+    }
+#endif
     return CB_OK;
 }
 

@@ -132,17 +132,17 @@ def test_config1_five_reads_three_assembly_regimes(tmp_path, dna_model, jump, ke
         name = "read%d" % n
         segs = read_fasta_records(os.path.join(out, "segments", name + ".fastq"))
         info = summary[name + ".signal"]
-        pos = np.asarray(info["pos"])
-        assert len(segs) == int((pos >= 0).sum())
+        pos, kept = np.asarray(info["pos"]), np.asarray(info["kept"])      # coordinates may be negative (simple kernel)
+        assert len(segs) == int(kept.sum()) and (pos[~kept] == -1).all()
         result = _read(os.path.join(out, "result", name + ".fastq")).split("\n")
         if n in oracle_reads:                         # per-window bases against the oracle's forward pass + greedy decoder
             sig = O.read_signal_text(os.path.join(GOLDEN, "DNA", "raw", name + ".signal"))
             ref = O.basecall_signal(sig, cfg, t, L, jump, beam=0, batch=512)
             assert segs == ref["segments"], "%s: windows decode differently from the oracle" % name
-            assert pos[pos >= 0].tolist() == ref["pos"].tolist()
+            assert pos[kept].tolist() == ref["pos"].tolist()
             assert result[1] == ref["consensus"] and result[3] == ref["qual"]
         else:                                         # coordinates / consensus from the decoded segments themselves
             cons, _, ref_pos = O.simple_assembly_qs(segs, None, jump / L, kernal=kernel)
-            assert pos[pos >= 0].tolist() == ref_pos.tolist()
+            assert pos[kept].tolist() == ref_pos.tolist()
             assert result[1] == (O.index2base(np.argmax(cons, axis=0)) if cons.shape[1] else "")
         assert result[0] == "@" + name and len(result[3]) == len(result[1])

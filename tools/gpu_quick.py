@@ -18,3 +18,5 @@ for B, L in shapes:
         ms = bc.last_forward_ms()
         print(prec, B, L, "ms conv/lstm/head/total", [round(v, 2) for v in ms],
               "Msamples/s %.2f" % (B * L / ms[3] / 1e3), "mean bases/window %.1f" % nb.float().mean().item(), flush=True)
+if os.environ.get("CB_PROF_DUMP"):
+    bc.last_forward_profile()
