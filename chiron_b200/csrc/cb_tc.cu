@@ -44,6 +44,8 @@ namespace {
 constexpr int BM = 128;          // rows (windows of one frame) per tile = UMMA M
 constexpr int BK = 32;           // K elements per pipeline stage (2 UMMA K-steps of 16)
 constexpr int MIN_STAGES = 4, MAX_STAGES = 6;   // depth of the operand ring (as many as fit in shared memory)
+constexpr int TWO_PASS_MAX = 4;  // partial sums of up to this many chunks (<= MIN_STAGES: they are all resident at once) issue the
+                                 // low-order products of every chunk first, then the hi*hi ones
 constexpr int ACC_COLS = 128;    // accumulator columns an epilogue thread sums in registers (half of the widest tile)
 constexpr int N_EPI_WARPS = 8;   // two per TMEM lane quadrant (each takes half of the tile's columns)
 // 12 warps = 3 warpgroups: two of epilogue warps, one holding the MMA warp, the loader warp and two idle warps.  The kernel
@@ -430,7 +432,7 @@ __device__ __forceinline__ void gemm_tc_body(const TcParams& q) {
         const uint32_t B_STEP = 2 * (uint32_t)BNL;
         // a partial sum's chunks are all resident at once (low-order products of every chunk first, then hi*hi) when the
         // ring can hold them and still load ahead; longer partial sums order the products chunk by chunk
-        const bool two_pass = q.cpp < MIN_STAGES;
+        const bool two_pass = q.cpp <= TWO_PASS_MAX;
         uint32_t kit = 0, it = 0, pit = 0;
         auto stage_descs = [&](uint32_t k, int kc, uint64_t& dah, uint64_t& dal, uint64_t& dbh, uint64_t& dbl) {
             const uint32_t s = k % (uint32_t)STAGES;
@@ -761,7 +763,7 @@ __device__ __forceinline__ void gemm_tc_body_v1(const TcParams& q) {
         const uint32_t B_STEP = 2 * (uint32_t)BNL;
         // a partial sum's chunks are all resident at once (low-order products of every chunk first, then hi*hi) when the
         // ring can hold them and still load ahead; longer partial sums order the products chunk by chunk
-        const bool two_pass = q.cpp < MIN_STAGES;
+        const bool two_pass = q.cpp <= TWO_PASS_MAX;
         uint32_t kit = 0, it = 0, pit = 0;
         auto stage_descs = [&](uint32_t k, int kc, uint64_t& dah, uint64_t& dal, uint64_t& dbh, uint64_t& dbl) {
             const uint32_t s = k % (uint32_t)STAGES;
@@ -1017,14 +1019,14 @@ int cb_tc_build_layer(cb_handle* h, int layer_id, const float* W, int K, int N, 
     // the previous tile still being written while only two partial sums fit in TMEM), so partial sums are as long as the
     // error budget allows.  Measured on the 4096 x 512 bench batch (conv stack ms sustained / logit rms error against the
     // float64 oracle; the fp32 FFMA kernels: 1.1e-5; profiles/r02_*):
-    //   convolutions:  1 accumulator per tile 9.5 ms / 1.1e-4    8 chunks 9.7 / 4.1e-5    4 chunks 12.0 / 2.4e-5
-    //                  3 chunks 12.7 / 1.7e-5   <- default         2 chunks 13.7 / 1.7e-5
-    //   (largest logit error on 262,144 frames: 1.6e-2 / 6.6e-3 / 5.4e-3 / 3.7e-3 at 8 / 4 / 3 / 2 chunks; fp32 kernels 4.1e-3;
+    //   convolutions:  1 accumulator per tile 9.5 ms / 1.1e-4    8 chunks (products interleaved) 9.7 / 4.1e-5
+    //                  4 chunks 12.0 / 1.8e-5   <- default         3 chunks 12.7 / 1.7e-5      2 chunks 13.7 / 1.7e-5
+    //   (largest logit error on 262,144 frames: 1.6e-2 / 6.1e-3 / 5.4e-3 / 3.7e-3 at 8 / 4 / 3 / 2 chunks; fp32 kernels 4.1e-3;
     //    greedy bases identical to the fp32 kernels' on all 4096 windows from 8 chunks down)
     //   LSTM input projections (HBM-write-bound, K <= 256): one accumulator (2.2 ms; 2.9 ms with two partial sums)
-    // CB_TC_CPP / CB_TC_CPP_PROJ override (n <= 3: low-order products of the whole partial sum first; n >= k_chunks: one
+    // CB_TC_CPP / CB_TC_CPP_PROJ override (n <= 4: low-order products of the whole partial sum first; n >= k_chunks: one
     // accumulator).
-    static const int cpp_conv = getenv("CB_TC_CPP") ? atoi(getenv("CB_TC_CPP")) : 3;
+    static const int cpp_conv = getenv("CB_TC_CPP") ? atoi(getenv("CB_TC_CPP")) : 4;
     static const int cpp_proj = getenv("CB_TC_CPP_PROJ") ? atoi(getenv("CB_TC_CPP_PROJ")) : 8;
     const int cpp_env = layer_id >= 32 ? cpp_proj : cpp_conv;
     L.cpp = cpp_env > 0 && cpp_env < L.k_chunks ? cpp_env : L.k_chunks;
@@ -1036,7 +1038,7 @@ int cb_tc_build_layer(cb_handle* h, int layer_id, const float* W, int K, int N, 
     // (1 + c*(n - t + 1)): first order, exact in expectation; what remains is the zero-mean part of the rounding errors, as in
     // any fp32 summation.
     const double comp_c = cb_tc_trunc_c();
-    const bool two_pass = L.cpp < MIN_STAGES;            // issue order of a partial sum (see gemm_tc_body)
+    const bool two_pass = L.cpp <= TWO_PASS_MAX;         // issue order of a partial sum (see gemm_tc_body)
     auto comp = [&](int kc, int ks) {                   // inflation of the hi*hi products of K-step ks of chunk kc
         const int p = kc / L.cpp, j = kc - p * L.cpp;
         const int nck = (p + 1) * L.cpp <= L.k_chunks ? L.cpp : L.k_chunks - p * L.cpp;

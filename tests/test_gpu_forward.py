@@ -13,8 +13,8 @@ pytestmark = pytest.mark.gpu
 # 5.5e-4 against the float64 one on 38,400 frames and by 1.2e-3 on 32,768 others (the three LSTM layers amplify rounding
 # noise ~100x, with a heavy tail: max / rms ~ 350).  "fp32" = FFMA kernels with round-to-nearest accumulation (measured
 # maxima against the float64 oracle: 9.7e-4 on 38,400 frames of read1, 4.1e-3 on 262,144 frames of the bench batch).
-# "tc" = tcgen05 fp16 hi/lo split with short-K partial sums and truncation compensation (1.0e-3 and 5.4e-3 on the same
-# frames; rms 1.7e-5 against 1.1e-5; the round-1 kernels: 1.8e-2 and 1.1e-4 rms).  Tests on <= 40,000 frames use LOGIT_TOLS;
+# "tc" = tcgen05 fp16 hi/lo split with short-K partial sums and truncation compensation (1.0e-3 and 6.1e-3 on the same
+# frames; rms 1.8e-5 against 1.1e-5; the round-1 kernels: 1.8e-2 and 1.1e-4 rms).  Tests on <= 40,000 frames use LOGIT_TOLS;
 # the 262,144-frame check of the bench batch uses LOGIT_TOLS_LARGE.
 LOGIT_TOLS = {"fp32": 2e-3, "tc": 5e-3}
 LOGIT_TOLS_LARGE = {"fp32": 6e-3, "tc": 8e-3}
@@ -118,7 +118,7 @@ def test_full_size_batch_properties(dna_model):
     (2) the tensor-core mode -- the mode bench.py and `chiron call` run -- decodes EXACTLY the greedy bases the fp32 FFMA
         mode decodes, for every one of the 4096 windows (the round-1 kernels differed in 9);
     (3) 512 windows sampled from the big batch agree with the oracle: logits of 262,144 frames within LOGIT_TOLS_LARGE of the
-        float64 oracle (measured: tc 5.4e-3, fp32 4.1e-3), greedy bases bit-identical to the float32 oracle's in both modes."""
+        float64 oracle (measured: tc 6.1e-3, fp32 4.1e-3), greedy bases bit-identical to the float32 oracle's in both modes."""
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from bench import synthetic_windows
