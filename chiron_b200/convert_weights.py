@@ -45,7 +45,27 @@ def _take_bn(raw, tensors, bn_modes, p: str, conv: str, required: bool) -> bool:
     return has_pop or has_head
 
 
+# CNN front ends of chiron/cnn.py:350-362 this package runs ("model" of model.json's "cnn" section); anything else is refused
+# by name, with the reason, before the variables are even looked at.
+SUPPORTED_CNN = {"dna_model1", "rna_model2", "rna_model3", "rna_test"}
+UNRUNNABLE_CNN = {
+    "rna_model1": "chiron/cnn.py:391-393 calls tf.nn.avg_pool(net, ksize, strides) without its required `padding` argument: "
+                  "the graph cannot be built at HEAD, so no checkpoint of this topology can exist",
+}
+
+
+def check_cnn_name(model_json: dict):
+    name = ((model_json or {}).get("cnn") or {}).get("model")
+    if name is None or name in SUPPORTED_CNN:
+        return
+    if name in UNRUNNABLE_CNN:
+        raise ValueError("CNN model %r is unrunnable in the reference itself: %s" % (name, UNRUNNABLE_CNN[name]))
+    raise ValueError("CNN model %r (chiron/cnn.py:350-362) is a research topology without shipped weights and is out of "
+                     "scope; supported: %s" % (name, ", ".join(sorted(SUPPORTED_CNN))))
+
+
 def convert_tensors(raw: Dict[str, np.ndarray], conv_attrs: Dict[str, dict], model_json: dict) -> bytes:
+    check_cnn_name(model_json)
     n_blocks = 0
     while "res_layer%d/branch2/conv2b/weights" % (n_blocks + 1) in raw:
         n_blocks += 1

@@ -67,7 +67,20 @@ int cb_launch_beam(cb_handle* h, const float* logits, const int32_t* lens, int B
     // the per-frame global row read (3-5 % when every window is resident anyway) but enlarges the footprint; reading the rows
     // from global memory (prefetched a frame ahead) keeps more CTAs resident per SM and wins as soon as the windows do not
     // fit in one wave.  So: stage iff the staged launch fits the budget and is a single wave (CB_BEAM_STAGE_LOGITS=0/1 forces).
+    // 16W nodes at 4-5 CTAs per SM, or 24W nodes (no window of the surveyed real logits outgrows that) at 2: in units of one
+    // window's search time a launch costs its number of waves, plus one more for the retry pass the smaller pool needs for its
+    // tail -- so a batch that fits one wave at 24W takes 24W (measured, 1024 x 512, W=30: 4.8 ms against 9.4).
     long long pool_s = beam_small_pool(T, W);
+    {
+        const long long pool_hi = beam_small_pool(T, W, 24);
+        auto waves = [&](long long pool) {
+            const long long cta = (long long)beam_warp_stride(T, C, W, (int)pool, false) * BEAM_WARPS + 1024;
+            const long long per_sm = (227LL * 1024) / cta;
+            const long long n = (B + BEAM_WARPS - 1) / BEAM_WARPS, slots = (long long)(h->sm_count > 0 ? h->sm_count : 148) * (per_sm > 0 ? per_sm : 1);
+            return (n + slots - 1) / slots;
+        };
+        if (pool_hi > pool_s && waves(pool_hi) < waves(pool_s) + 1) pool_s = pool_hi;
+    }
     if (getenv("CB_BEAM_POOL") && atoll(getenv("CB_BEAM_POOL")) >= 2LL * W + 2) pool_s = atoll(getenv("CB_BEAM_POOL"));   // A/B
     if (pool_s > 32767) pool_s = 32767;
     const size_t stride_staged = beam_warp_stride(T, C, W, (int)pool_s, true);

@@ -173,7 +173,12 @@ __device__ int beam_decode_warp(const float* __restrict__ lg, int len, int C, in
                 }
             }
             unsigned mask = __ballot_sync(FULL, flag);
-            if (lane == 0 && mask && !err) {
+            if (mask && !err) {
+                // The surviving candidates are taken in order -- an insertion moves the beam's bottom, which the next
+                // candidate's test reads -- but by the WHOLE warp: every lane follows the same (warp-uniform) decisions from
+                // broadcast shared-memory reads, lane 0 does the scalar writes, and the two O(W) steps of an insertion (closing
+                // the gap of the evicted leaf, finding the new bottom) are spread over the lanes.  On one lane they were
+                // ~3,000 clocks per insertion, and a new base is ~W insertions.
                 int cur_i = -1; bool cur_pass = false; float tot = 0.f;
                 while (mask) {
                     const int bit = __ffs(mask) - 1;
@@ -192,44 +197,76 @@ __device__ int beam_decode_warp(const float* __restrict__ lg, int len, int C, in
                     const float lab = inp[c] + prev;
                     if (!(lab > -INFINITY && (n_leaves < W || lab > bot_val))) {
                         if (ch >= 0 && k.nodes[ch].bframe == t) {
-                            k.bo_total[k.nodes[ch].bidx] = -INFINITY; k.bo_blank[k.nodes[ch].bidx] = -INFINITY;
+                            const int bi = k.nodes[ch].bidx;
+                            __syncwarp();
+                            if (lane == 0) { k.bo_total[bi] = -INFINITY; k.bo_blank[bi] = -INFINITY; }
+                            __syncwarp();
                         }
                         continue;
                     }
+                    __syncwarp();          // every lane has made this candidate's decision: nothing it read may change before
                     if (n_leaves == W) {                                       // evict the bottom beam
                         const int bs = k.leaves[bot];
-                        k.nodes[k.slot_node[bs]].slot = -1;
-                        for (int q = bot; q + 1 < n_leaves; ++q) k.leaves[q] = k.leaves[q + 1];
+                        const int bnode = k.slot_node[bs];
+                        __syncwarp();
+                        for (int base = bot; base + 1 < n_leaves; base += 32) {      // close the gap, 32 leaves at a time
+                            const int q = base + lane;
+                            const int v = (q + 1 < n_leaves) ? k.leaves[q + 1] : 0;
+                            __syncwarp();
+                            if (q + 1 < n_leaves) k.leaves[q] = v;
+                            __syncwarp();
+                        }
+                        if (lane == 0) { k.nodes[bnode].slot = -1; k.freel[n_free] = bs; }
                         --n_leaves;
-                        k.freel[n_free++] = bs;
+                        ++n_free;
+                        __syncwarp();
                     }
                     int node = ch;
                     if (node < 0) {
                         if (n_nodes == k.pool) {
-                            n_nodes = cb_beam_compact(k, n_nodes, n_leaves, nb, n_child);
+                            __syncwarp();
+                            int m = 0;
+                            if (lane == 0) m = cb_beam_compact(k, n_nodes, n_leaves, nb, n_child);
+                            n_nodes = __shfl_sync(FULL, m, 0);
+                            __syncwarp();
                             if (n_nodes == k.pool) { err = 1; break; }
                         }
                         node = n_nodes++;
-                        BeamNodeS& nn = k.nodes[node];
-                        nn.parent = (BeamIdx)k.bnode[i]; nn.label = (BeamIdx)c; nn.slot = -1; nn.bidx = 0; nn.bframe = -1;
-                        for (int q = 0; q < CB_BEAM_MAX_CHILD; ++q) nn.child[q] = -1;
-                        k.nodes[k.bnode[i]].child[c] = node;
+                        const int parent = k.bnode[i];                         // (after a compaction: the renumbered node)
+                        if (lane == 0) {
+                            BeamNodeS& nn = k.nodes[node];
+                            nn.parent = (BeamIdx)parent; nn.label = (BeamIdx)c; nn.slot = -1; nn.bidx = 0; nn.bframe = -1;
+                            for (int q = 0; q < CB_BEAM_MAX_CHILD; ++q) nn.child[q] = -1;
+                            k.nodes[parent].child[c] = (BeamIdx)node;
+                        }
                     }
-                    const int s = k.freel[--n_free];
-                    k.slot_node[s] = node;
-                    k.nodes[node].slot = s;
-                    k.nb[s] = -INFINITY; k.nl[s] = lab; k.nt[s] = lab;
-                    k.ot[s] = k.ob[s] = -INFINITY;
-                    k.leaves[n_leaves++] = s;
-                    bot = 0;
-                    for (int q = 1; q < n_leaves; ++q) if (k.nt[k.leaves[q]] < k.nt[k.leaves[bot]]) bot = q;
-                    bot_val = k.nt[k.leaves[bot]];
+                    const int s = k.freel[n_free - 1];
+                    --n_free;
+                    if (lane == 0) {
+                        k.slot_node[s] = node;
+                        k.nodes[node].slot = (BeamIdx)s;
+                        k.nb[s] = -INFINITY; k.nl[s] = lab; k.nt[s] = lab;
+                        k.ot[s] = k.ob[s] = -INFINITY;
+                        k.leaves[n_leaves] = s;
+                    }
+                    ++n_leaves;
+                    __syncwarp();
+                    // new bottom = first minimum in push order
+                    float bv = INFINITY; int bq = 0x7fffffff;
+                    for (int q = lane; q < n_leaves; q += 32) {
+                        const float v = k.nt[k.leaves[q]];
+                        if (bq == 0x7fffffff || v < bv) { bv = v; bq = q; }  // ascending q per lane: keeps its lowest index per value
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const float ov = __shfl_xor_sync(FULL, bv, off);
+                        const int oq = __shfl_xor_sync(FULL, bq, off);
+                        if (oq != 0x7fffffff && (bq == 0x7fffffff || ov < bv || (ov == bv && oq < bq))) { bv = ov; bq = oq; }
+                    }
+                    bot = bq; bot_val = bv;
                 }
             }
-            __syncwarp();
-            n_leaves = __shfl_sync(FULL, n_leaves, 0); n_free = __shfl_sync(FULL, n_free, 0);
-            n_nodes = __shfl_sync(FULL, n_nodes, 0); bot = __shfl_sync(FULL, bot, 0);
-            bot_val = __shfl_sync(FULL, bot_val, 0); err = __shfl_sync(FULL, err, 0);
+            __syncwarp();          // (n_leaves, n_free, n_nodes, bot, bot_val, err are warp-uniform: every lane kept them)
         }
         if (err) return -2;
     }
@@ -487,10 +524,10 @@ inline size_t beam_warp_stride(int T, int C, int W, int pool, bool staged) {
 // (nodes are free up to the next occupancy step) and bounded by what four windows hold in 192 KB and by the
 // never-overflows bound 2W(T+1)+2.  At W=30 that is 5 CTAs = 20 warps per SM (26 bytes per node with 16-bit indices).
 constexpr long long BEAM_SMEM_BUDGET = 192 * 1024;          // of the 200 KB the launcher opts in to
-inline long long beam_small_pool(int T, int W) {
+inline long long beam_small_pool(int T, int W, int mult = 16) {
     const long long cap = 2LL * W * (T + 1) + 2;
     const long long node = (long long)(sizeof(BeamNodeS) + sizeof(BeamIdx)), fixed = 12LL * 4 * W + 32;
-    long long pool = 16LL * W;
+    long long pool = (long long)mult * W;
     const long long fit = (BEAM_SMEM_BUDGET / BEAM_WARPS - fixed) / node;
     if (pool > fit) pool = fit;
     if (pool < 64 && fit >= 64) pool = 64;

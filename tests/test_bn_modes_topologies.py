@@ -5,6 +5,8 @@ chiron/cnn.py:555-566).
 No checkpoint trained at HEAD or with those topologies ships with the reference, so the oracle's restatement of them is
 "parity unpinned" against the reference itself; what pins it here is an INDEPENDENT restatement with torch's own
 conv1d / batch_norm / LSTM-free primitives on CPU (torch is not used by the oracle), plus structural identities."""
+import os
+
 import numpy as np
 import pytest
 
@@ -264,3 +266,25 @@ def test_converter_recognises_the_stem_convolution(head_literal):
     x = _signal(3, 75)
     want = O.cnn_forward(x, cfg, t, bn_mode=int(head_literal))
     assert np.array_equal(O.cnn_forward(x, cfg2, t2), want) and want.shape == (3, 11, 16)
+
+
+def test_rna_model1_is_unrunnable_in_the_reference_and_says_so():
+    """`rna_model1` (chiron/cnn.py:391-401) starts with tf.nn.avg_pool(net, ksize, strides) WITHOUT the
+    required `padding` argument, so the reference cannot even build that graph at HEAD and no checkpoint of it can exist.
+    The converter refuses it by name and says why (it does not silently skip it); research topologies without shipped
+    weights are refused as out of scope; the names the package runs pass."""
+    import re
+    from chiron_b200.convert_weights import SUPPORTED_CNN, check_cnn_name, convert_tensors
+    with pytest.raises(ValueError, match="unrunnable in the reference.*avg_pool.*padding"):
+        convert_tensors({}, {}, {"cnn": {"model": "rna_model1"}})
+    for name in ("res_x", "variant_wavnet", "incp_v2", "custom", "gate_conv_net", "dynamic_net"):
+        with pytest.raises(ValueError, match="out of scope"):
+            check_cnn_name({"cnn": {"model": name}})
+    for name in sorted(SUPPORTED_CNN) + [None]:
+        check_cnn_name({"cnn": {"model": name}} if name else {})
+    ref_cnn = os.path.join("/root/reference", "chiron", "cnn.py")
+    if os.path.exists(ref_cnn):                       # in the build container: the claim, checked against the reference source
+        src = open(ref_cnn).read()
+        body = src[src.index("def RNA_model1"):src.index("def dynamic_net")]
+        call = re.search(r"tf\.nn\.avg_pool\(([^)]*)\)", body).group(1)
+        assert "padding" not in call

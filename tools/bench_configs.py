@@ -5,11 +5,12 @@ Prints one JSON document (device-resident inputs, CUDA events on the launching s
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+from bench import synthetic_windows
 from chiron_b200.engine import Basecaller
 
-def run(bc, B, L, beam, iters=5, warm=3):
-    x = torch.randn(B, L, device="cuda") * 0.43 - 0.16
-    lens = torch.full((B,), L, dtype=torch.int32, device="cuda")
+def run(bc, B, L, beam, iters=5, warm=3, model="DNA_default"):
+    xs, lens_h = synthetic_windows(B, L, 1234, model)       # bootstrap windows of the bundled reads
+    x, lens = torch.from_numpy(xs).cuda(), torch.from_numpy(lens_h).cuda()
     lo = bc.seq_len_out_device(lens, L)
     def step():
         logits, prob = bc.forward_device(x, lo)
@@ -28,7 +29,7 @@ def run(bc, B, L, beam, iters=5, warm=3):
             "windows_per_s": round(B / ms * 1e3, 1), "per_category_ms": prof}
 
 prec = sys.argv[1] if len(sys.argv) > 1 else "tc"
-out = {"precision": prec, "inputs": "parametric synthetic signal (randn*0.43-0.16), full windows, resident in HBM"}
+out = {"precision": prec, "inputs": "bootstrap windows cut from the bundled normalised reads (seed 1234), full windows, resident in HBM"}
 dna = Basecaller("DNA_default", 0, prec)
 out["config2_dna_1024x512_greedy"] = run(dna, 1024, 512, 0)
 sweep = []
@@ -40,7 +41,7 @@ for L in (300, 512, 1024, 2048):
 out["config5_sweep_dna_greedy"] = sweep
 dna.close()
 rna = Basecaller("RNA_default", 0, prec)
-out["config3_rna_512x500_beam50"] = run(rna, 512, 500, 50)
-out["config3_rna_512x500_greedy"] = run(rna, 512, 500, 0)
+out["config3_rna_512x500_beam50"] = run(rna, 512, 500, 50, model="RNA_default")
+out["config3_rna_512x500_greedy"] = run(rna, 512, 500, 0, model="RNA_default")
 rna.close()
 print(json.dumps(out))

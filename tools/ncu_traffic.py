@@ -1,4 +1,4 @@
-"""profiles/r01_traffic.json from the `ncu --set full` captures of one evidence pass (run here: ncu is installed, no GPU needed).
+"""profiles/r0N_traffic.json from the `ncu --set full` captures of one evidence pass (run here: ncu is installed, no GPU needed).
 
     python tools/ncu_traffic.py gpurun_out/<tag> [precision] [batch]
 
@@ -37,10 +37,8 @@ def main():
             d = dict(zip(hdr, r))
             cat = name
             if cat is None:   # gemm_tc_kernel: the resident-weight launches (N = 8H) are the LSTM input projection
-                su = u["launch__shared_mem_per_block_dynamic"]
-                smem = f(d, "launch__shared_mem_per_block_dynamic") * (1e3 if su.startswith("Kbyte") else 1e6 if su.startswith("Mbyte") else 1.0)
-                kname = d.get("Kernel Name", "")
-                cat = "conv" if ("pair" in kname or abs(smem - 196864) < 1) else "lstm_in"
+                kname = d.get("Kernel Name", "")      # the CTA-pair kernel = convolutions, the single-CTA kernel = input projection
+                cat = "conv" if "pair" in kname else "lstm_in"
             rd = f(d, "dram__bytes_read.sum") * scale[u["dram__bytes_read.sum"]]
             wr = f(d, "dram__bytes_write.sum") * scale[u["dram__bytes_write.sum"]]
             c = cats.setdefault(cat, {"launches": 0, "dram_read": 0.0, "dram_write": 0.0, "ms": 0.0, "tensor_pct": 0.0,
