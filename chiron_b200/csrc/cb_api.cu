@@ -579,7 +579,14 @@ extern "C" int cb_decode_beam(cb_handle* h, const float* logits, const int32_t* 
                               int8_t* bases, int32_t* n_bases, void* stream) {
     if (!h || !logits || !seq_len_out || !bases || !n_bases || B < 0 || T < 1 || beam_width < 1) { cb_set_error("cb_decode_beam: bad arguments"); return CB_ERR_ARG; }
     CB_CUDA(cudaSetDevice(h->device));
-    return cb_launch_beam(h, logits, seq_len_out, B, T, beam_width, bases, n_bases, (cudaStream_t)stream);
+    return cb_launch_beam(h, logits, seq_len_out, B, T, beam_width, bases, n_bases, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int cb_decode_beam_scored(cb_handle* h, const float* logits, const int32_t* seq_len_out, int B, int T, int beam_width,
+                                     int8_t* bases, int32_t* n_bases, float* log_prob, void* stream) {
+    if (!h || !logits || !seq_len_out || !bases || !n_bases || !log_prob || B < 0 || T < 1 || beam_width < 1) { cb_set_error("cb_decode_beam_scored: bad arguments"); return CB_ERR_ARG; }
+    CB_CUDA(cudaSetDevice(h->device));
+    return cb_launch_beam(h, logits, seq_len_out, B, T, beam_width, bases, n_bases, log_prob, (cudaStream_t)stream);
 }
 
 extern "C" int cb_assemble(cb_handle* h, const int8_t* bases, const int32_t* n_bases, const float* path_prob,
@@ -629,7 +636,7 @@ extern "C" int cb_basecall_host(cb_handle* h, const float* x, const int32_t* seq
     if ((rc = cb_launch_seq_len(h, d_in, B, L, T, d_len, s)) != CB_OK) return rc;
     if ((rc = cb_forward(h, d_x, d_len, B, L, d_lg, d_prob, s)) != CB_OK) return rc;
     if (beam_width == 0) rc = cb_launch_greedy(h, d_lg, d_len, B, T, d_bases, d_nb, s);
-    else rc = cb_launch_beam(h, d_lg, d_len, B, T, beam_width, d_bases, d_nb, s);
+    else rc = cb_launch_beam(h, d_lg, d_len, B, T, beam_width, d_bases, d_nb, nullptr, s);
     if (rc != CB_OK) return rc;
     CB_CUDA(cudaMemcpyAsync(bases, d_bases, (size_t)B * T, cudaMemcpyDeviceToHost, s));
     CB_CUDA(cudaMemcpyAsync(n_bases, d_nb, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
@@ -704,7 +711,7 @@ extern "C" int cb_basecall_submit(cb_handle* h, int slot, const float* x, const 
     if ((rc = cb_launch_seq_len(h, (const int32_t*)(dev + o.d_in), B, L, T, d_len, s)) != CB_OK) return rc;
     if ((rc = cb_forward(h, (const float*)(dev + o.d_x), d_len, B, L, d_lg, (float*)(dev + o.d_prob), s)) != CB_OK) return rc;
     if (beam_width == 0) rc = cb_launch_greedy(h, d_lg, d_len, B, T, (int8_t*)(dev + o.d_bases), (int32_t*)(dev + o.d_nb), s);
-    else rc = cb_launch_beam(h, d_lg, d_len, B, T, beam_width, (int8_t*)(dev + o.d_bases), (int32_t*)(dev + o.d_nb), s);
+    else rc = cb_launch_beam(h, d_lg, d_len, B, T, beam_width, (int8_t*)(dev + o.d_bases), (int32_t*)(dev + o.d_nb), nullptr, s);
     if (rc != CB_OK) return rc;
     CB_CUDA(cudaEventRecord(sl.compute_done, s));
     CB_CUDA(cudaStreamWaitEvent(h->pipe_out, sl.compute_done, 0));

@@ -143,7 +143,7 @@ int cb_launch_seq_len(cb_handle* h, const int32_t* in, int B, int L, int T, int3
 int cb_launch_greedy(cb_handle* h, const float* logits, const int32_t* lens, int B, int T, int8_t* bases,
                      int32_t* n_bases, cudaStream_t s);
 int cb_launch_beam(cb_handle* h, const float* logits, const int32_t* lens, int B, int T, int W, int8_t* bases,
-                   int32_t* n_bases, cudaStream_t s);
+                   int32_t* n_bases, float* scores, cudaStream_t s);      // scores: top-path log probability [B] or null
 int cb_launch_assemble(cb_handle* h, const int8_t* bases, const int32_t* n_bases, const float* path_prob, int n_windows,
                        int T, int jump, int L, int kernel, int8_t* consensus, char* qual, int32_t* pos,
                        int32_t* out_len, int max_len, cudaStream_t s);

@@ -38,7 +38,7 @@ __global__ void fill_i32_kernel(int32_t* p, int n, int32_t v) {
 // cb_basecall_host report it as CB_ERR_NOMEM.  No host synchronisation here.
 // CB_BEAM_SMEM=0 skips passes 1-2 and runs beam_kernel on every window (tests, A/B).
 int cb_launch_beam(cb_handle* h, const float* logits, const int32_t* lens, int B, int T, int W, int8_t* bases,
-                   int32_t* n_bases, cudaStream_t s) {
+                   int32_t* n_bases, float* scores, cudaStream_t s) {
     if (B <= 0) return CB_OK;
     if (W < 1 || W > 4096) { cb_set_error("beam width %d out of range", W); return CB_ERR_ARG; }
     const int C = h->cfg.n_class;
@@ -49,7 +49,7 @@ int cb_launch_beam(cb_handle* h, const float* logits, const int32_t* lens, int B
         int rc = ensure_buf(&h->beam_ws, &h->beam_ws_bytes, stride_g * (size_t)B, "beam workspace");
         if (rc != CB_OK) return rc;
         beam_kernel<<<(B + 63) / 64, 64, 0, s>>>(logits, lens, B, T, C, W, (int)cap, (char*)h->beam_ws, stride_g, bases, n_bases,
-                                                 h->d_flag + CB_FLAG_BEAM_ERROR, nullptr, 0);
+                                                 h->d_flag + CB_FLAG_BEAM_ERROR, nullptr, 0, scores);
         CB_CHECK_LAUNCH();
         h->launches++;
         return CB_OK;
@@ -103,12 +103,12 @@ int cb_launch_beam(cb_handle* h, const float* logits, const int32_t* lens, int B
             fe = cudaFuncSetAttribute(beam_warp_kernel<true>, (cudaFuncAttribute)attr, 200 * 1024);
             if (fe == cudaSuccess)
                 beam_warp_kernel<true><<<grid, BEAM_WARPS * 32, smem, s>>>(logits, lens, B, T, C, W, (int)pool_s, (int)stride, bases,
-                                                                          n_bases, h->d_flag + CB_FLAG_BEAM_MARKED);
+                                                                          n_bases, h->d_flag + CB_FLAG_BEAM_MARKED, scores);
         } else {
             fe = cudaFuncSetAttribute(beam_warp_kernel<false>, (cudaFuncAttribute)attr, 200 * 1024);
             if (fe == cudaSuccess)
                 beam_warp_kernel<false><<<grid, BEAM_WARPS * 32, smem, s>>>(logits, lens, B, T, C, W, (int)pool_s, (int)stride, bases,
-                                                                           n_bases, h->d_flag + CB_FLAG_BEAM_MARKED);
+                                                                           n_bases, h->d_flag + CB_FLAG_BEAM_MARKED, scores);
         }
         if (fe == cudaSuccess) fe = cudaGetLastError();
         if (fe == cudaSuccess) { pass1 = true; h->launches++; }
@@ -126,7 +126,7 @@ int cb_launch_beam(cb_handle* h, const float* logits, const int32_t* lens, int B
         const cudaError_t fe = cudaFuncSetAttribute(beam_retry_kernel, (cudaFuncAttribute)attr, 200 * 1024);
         if (fe == cudaSuccess) {
             beam_retry_kernel<<<B, 32, smem_r, s>>>(logits, lens, B, T, C, W, (int)pool_r, bases, n_bases,
-                                                    h->d_flag + CB_FLAG_BEAM_MARKED);
+                                                    h->d_flag + CB_FLAG_BEAM_MARKED, scores);
             if (cudaGetLastError() == cudaSuccess) h->launches++;
         } else {
             (void)cudaGetLastError();
@@ -134,7 +134,7 @@ int cb_launch_beam(cb_handle* h, const float* logits, const int32_t* lens, int B
     }
     // ---- pass 3: windows still marked, over global workspaces that cannot overflow
     beam_kernel<<<(B + 63) / 64, 64, 0, s>>>(logits, lens, B, T, C, W, (int)cap, (char*)h->beam_ws, stride_g, bases, n_bases,
-                                             h->d_flag + CB_FLAG_BEAM_ERROR, h->d_flag + CB_FLAG_BEAM_SLOTS, (int)n_slots);
+                                             h->d_flag + CB_FLAG_BEAM_ERROR, h->d_flag + CB_FLAG_BEAM_SLOTS, (int)n_slots, scores);
     CB_CHECK_LAUNCH();
     h->launches++;
     return CB_OK;

@@ -102,8 +102,11 @@ CB_HD inline int cb_beam_compact(CbBeamWorkT<I>& k, int n_nodes, int n_leaves, i
 
 // logits: [T][C] row-major rows of one window; returns the number of decoded labels written to out, or -2 when the
 // node pool is too small even after compaction.
+// `score` (may be null): newp.total of the best beam, i.e. the path log probability TopPaths() reports -- the `log_prob`
+// output of tf.nn.ctc_beam_search_decoder (chiron/export_test.py:36-40).
 template <typename I>
-CB_HD inline int cb_beam_decode_one(const float* logits, int len, int C, int W, CbBeamWorkT<I> k, int8_t* out) {
+CB_HD inline int cb_beam_decode_one(const float* logits, int len, int C, int W, CbBeamWorkT<I> k, int8_t* out,
+                                    float* score = nullptr) {
     const int blank = C - 1, n_child = C - 1;
     int n_nodes = 1, n_leaves = 1, n_free = 0;
     k.nodes[0].parent = -1; k.nodes[0].label = -1; k.nodes[0].slot = 0; k.nodes[0].bidx = 0; k.nodes[0].bframe = -1;
@@ -203,6 +206,7 @@ CB_HD inline int cb_beam_decode_one(const float* logits, int len, int C, int W, 
     }
     int best = 0;
     for (int i = 1; i < n_leaves; ++i) if (k.nt[k.leaves[i]] > k.nt[k.leaves[best]]) best = i;
+    if (score) *score = k.nt[k.leaves[best]];
     int n = 0;
     for (int cur = k.slot_node[k.leaves[best]]; k.nodes[cur].parent >= 0; cur = k.nodes[cur].parent) ++n;
     int i = n - 1;

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(64) beam_kernel(const float* __restrict__ logi
                                                   int B, int T, int C, int W, int pool, char* __restrict__ work,
                                                   size_t work_stride, int8_t* __restrict__ bases,
                                                   int32_t* __restrict__ n_bases, int* __restrict__ overflow,
-                                                  int* __restrict__ slot_counter, int n_slots) {
+                                                  int* __restrict__ slot_counter, int n_slots, float* __restrict__ scores) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     int8_t* dst = bases + (size_t)b * T;
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(64) beam_kernel(const float* __restrict__ logi
     int len = lens[b];
     len = len < 0 ? 0 : (len > T ? T : len);
     CbBeamWork k = cb_beam_work_carve(work + ws * work_stride, W, pool);
-    int n = cb_beam_decode_one(logits + (size_t)b * T * C, len, C, W, k, dst);
+    int n = cb_beam_decode_one(logits + (size_t)b * T * C, len, C, W, k, dst, scores ? scores + b : nullptr);
     if (n < 0) { atomicExch(overflow, 1); n = 0; }
     for (int i = n; i < T; ++i) dst[i] = 0;
     n_bases[b] = n;
@@ -75,7 +75,8 @@ typedef CbBeamNodeT<BeamIdx> BeamNodeS;
 
 // `lg` is the window's logits [len][C] in shared memory (staged by the caller) or in global memory; either way the row of
 // frame t + 1 is fetched into registers while frame t is processed, so its latency hides behind the frame's work.
-__device__ int beam_decode_warp(const float* __restrict__ lg, int len, int C, int W, BeamWorkS k, int8_t* out, int lane) {
+__device__ int beam_decode_warp(const float* __restrict__ lg, int len, int C, int W, BeamWorkS k, int8_t* out, int lane,
+                                float* score) {
     const unsigned FULL = 0xffffffffu;
     const int blank = C - 1, n_child = C - 1;
     int n_nodes = 1, n_leaves = 1, n_free = 0, err = 0;
@@ -274,6 +275,7 @@ __device__ int beam_decode_warp(const float* __restrict__ lg, int len, int C, in
     if (lane == 0) {
         int best = 0;
         for (int i = 1; i < n_leaves; ++i) if (k.nt[k.leaves[i]] > k.nt[k.leaves[best]]) best = i;
+        if (score) *score = k.nt[k.leaves[best]];
         for (int cur = k.slot_node[k.leaves[best]]; k.nodes[cur].parent >= 0; cur = k.nodes[cur].parent) ++n;
         int i = n - 1;
         for (int cur = k.slot_node[k.leaves[best]]; k.nodes[cur].parent >= 0; cur = k.nodes[cur].parent)
@@ -290,7 +292,7 @@ template <bool STAGED>
 __global__ void __launch_bounds__(BEAM_WARPS * 32) beam_warp_kernel(const float* __restrict__ logits, const int32_t* __restrict__ lens,
                                                                     int B, int T, int C, int W, int pool, int stride,
                                                                     int8_t* __restrict__ bases, int32_t* __restrict__ n_bases,
-                                                                    int* __restrict__ marked) {
+                                                                    int* __restrict__ marked, float* __restrict__ scores) {
 #ifdef CB_HOST_EMU
     char* beam_sm = reinterpret_cast<char*>(emu::dyn_smem());
 #else
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(BEAM_WARPS * 32) beam_warp_kernel(const float*
     }
     int8_t* dst = bases + (size_t)b * T;
     BeamWorkS k = cb_beam_work_carve<BeamIdx>(base + work_off, W, pool);
-    int n = beam_decode_warp(lg, len, C, W, k, dst, lane);
+    int n = beam_decode_warp(lg, len, C, W, k, dst, lane, scores ? scores + b : nullptr);
     if (n < 0) { if (lane == 0) atomicExch(marked, 1); n = -1; }
     __syncwarp();
     for (int i = (n < 0 ? 0 : n) + lane; i < T; i += 32) dst[i] = 0;
@@ -326,7 +328,8 @@ __global__ void __launch_bounds__(BEAM_WARPS * 32) beam_warp_kernel(const float*
 // overflows even this pool stays marked (for beam_kernel's slot mode) and raises *marked.
 __global__ void __launch_bounds__(32) beam_retry_kernel(const float* __restrict__ logits, const int32_t* __restrict__ lens, int B, int T,
                                                         int C, int W, int pool, int8_t* __restrict__ bases,
-                                                        int32_t* __restrict__ n_bases, int* __restrict__ marked) {
+                                                        int32_t* __restrict__ n_bases, int* __restrict__ marked,
+                                                        float* __restrict__ scores) {
 #ifdef CB_HOST_EMU
     char* beam_sm = reinterpret_cast<char*>(emu::dyn_smem());
 #else
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(32) beam_retry_kernel(const float* __restrict_
     len = len < 0 ? 0 : (len > T ? T : len);
     int8_t* dst = bases + (size_t)b * T;
     BeamWorkS k = cb_beam_work_carve<BeamIdx>(beam_sm, W, pool);
-    int n = beam_decode_warp(logits + (size_t)b * T * C, len, C, W, k, dst, lane);
+    int n = beam_decode_warp(logits + (size_t)b * T * C, len, C, W, k, dst, lane, scores ? scores + b : nullptr);
     if (n < 0) { if (lane == 0) atomicExch(marked, 1); n = -1; }
     __syncwarp();
     for (int i = (n < 0 ? 0 : n) + lane; i < T; i += 32) dst[i] = 0;

@@ -223,7 +223,9 @@ class Basecaller:
                                            ctypes.c_void_p(s)), "cb_seq_len_out")
         return out
 
-    def decode_device(self, logits, seq_len_out, beam: int = 0, bases=None, n_bases=None, stream=None):
+    def decode_device(self, logits, seq_len_out, beam: int = 0, bases=None, n_bases=None, stream=None, log_prob=None):
+        """``log_prob``: a float32 [B] device tensor that receives the beam search's top-path log probability
+        (cb_decode_beam_scored; beam > 0 only)."""
         import torch
         B, T, _ = logits.shape
         if bases is None:
@@ -235,11 +237,51 @@ class Basecaller:
             _lib.check(self.lib.cb_decode_greedy(self.h, logits.data_ptr(), seq_len_out.data_ptr(), B, T,
                                                  bases.data_ptr(), n_bases.data_ptr(), ctypes.c_void_p(s)),
                        "cb_decode_greedy")
+        elif log_prob is not None:
+            _lib.check(self.lib.cb_decode_beam_scored(self.h, logits.data_ptr(), seq_len_out.data_ptr(), B, T, int(beam),
+                                                      bases.data_ptr(), n_bases.data_ptr(), log_prob.data_ptr(),
+                                                      ctypes.c_void_p(s)), "cb_decode_beam_scored")
         else:
             _lib.check(self.lib.cb_decode_beam(self.h, logits.data_ptr(), seq_len_out.data_ptr(), B, T, int(beam),
                                                bases.data_ptr(), n_bases.data_ptr(), ctypes.c_void_p(s)),
                        "cb_decode_beam")
         return bases, n_bases
+
+    def predict(self, x: np.ndarray, seq_len: np.ndarray, beam_width: int = 30) -> dict:
+        """The reference's serving signature as one call (chiron/export_test.py:24-40,103-113; what
+        chiron/chiron_client.py:207-228 sends and reads back): ``{x [N,L] f32, seq_len [N] i32}`` ->
+        ``{indices, values, dense_shape, logits, prob_logits, log_prob}``.
+
+        ``indices [n,2] / values [n] / dense_shape [2]`` (int64) are the SparseTensor ``predict[0]`` of
+        tf.nn.ctc_beam_search_decoder(merge_repeated=False) in row-major order, ``logits [N,T,C]``, ``prob_logits [N]`` =
+        path_prob(logits), ``log_prob [N,1]`` = the decoder's score of the top path.  ``seq_len`` is divided by the model's
+        stride ratio with tf.round like output_list() does (cb_seq_len_out).  Runs forward + beam search on the device;
+        host<->device copies go through torch (plumbing)."""
+        import torch
+        if beam_width < 1:
+            raise ValueError("the serving signature decodes with a beam search: beam_width >= 1")
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        seq_len = np.ascontiguousarray(seq_len, dtype=np.int32).reshape(-1)
+        if x.ndim != 2 or seq_len.shape[0] != x.shape[0]:
+            raise ValueError("x must be [N, L] and seq_len [N]")
+        N, L = x.shape
+        dev = torch.device("cuda", self.device)
+        with torch.cuda.device(dev):
+            dx = torch.from_numpy(x).to(dev)
+            dlen = self.seq_len_out_device(torch.from_numpy(seq_len).to(dev), L)
+            logits, prob = self.forward_device(dx, dlen)
+            score = torch.zeros((N,), dtype=torch.float32, device=dev)
+            bases, n_bases = self.decode_device(logits, dlen, beam=int(beam_width), log_prob=score)
+            self.check_status()
+            bases, n_bases = bases.cpu().numpy(), n_bases.cpu().numpy()
+            out_logits, prob, score = logits.cpu().numpy(), prob.cpu().numpy(), score.cpu().numpy()
+        T = bases.shape[1]
+        keep = np.arange(T)[None, :] < n_bases[:, None]
+        rows, cols = np.nonzero(keep)                      # row-major: the order TF emits the sparse entries in
+        return {"indices": np.stack([rows, cols], axis=1).astype(np.int64),
+                "values": bases[rows, cols].astype(np.int64),
+                "dense_shape": np.array([N, int(n_bases.max()) if N else 0], dtype=np.int64),
+                "logits": out_logits, "prob_logits": prob, "log_prob": score.reshape(N, 1)}
 
     def check_status(self, stream=None):
         """Synchronise the stream and raise the deferred device-side errors of the asynchronous calls (cb_check_status):

@@ -107,6 +107,13 @@ int cb_decode_greedy(cb_handle* h, const float* logits, const int32_t* seq_len_o
 int cb_decode_beam(cb_handle* h, const float* logits, const int32_t* seq_len_out, int B, int T, int beam_width,
                    int8_t* bases, int32_t* n_bases, void* stream);
 
+/* The same search, also returning the decoder's second output: log_prob[B] = the log probability TopPaths() reports for the
+ * decoded path (newp.total of the best beam; per-frame max-subtracted logits, TF 1.15) -- the `log_prob` tensor of the
+ * serving signature {x, seq_len} -> {indices, values, dense_shape, logits, prob_logits, log_prob} (chiron/export_test.py:36-40,
+ * 103-113).  The reference holds no fixture for it: pinned to the oracle's restatement only. */
+int cb_decode_beam_scored(cb_handle* h, const float* logits, const int32_t* seq_len_out, int B, int T, int beam_width,
+                          int8_t* bases, int32_t* n_bases, float* log_prob, void* stream);
+
 /* simple_assembly(_qs) + argmax + qs() for ONE read (easy_assembler.py:302-335,393-442; chiron_eval.py:152-174,457).
  * bases[n_windows,T] / n_bases[n_windows] / path_prob[n_windows] in TRUE window order (empty windows are skipped like
  * sparse2dense does).  Outputs: consensus[max_len] int8 base indices, qual[max_len] phred+33 chars (may be NULL),

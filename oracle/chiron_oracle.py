@@ -574,3 +574,21 @@ def ctc_decode_c(logits: np.ndarray, lens: np.ndarray, beam_width: int = 0) -> L
     if (out_len < 0).any():
         raise MemoryError("oracle_ctc_beam failed")
     return [out[b, :out_len[b]].tolist() for b in range(B)]
+
+
+def ctc_beam_scores_c(logits: np.ndarray, lens: np.ndarray, beam_width: int):
+    """Beam search through the C restatement, with the top path's score (newp.total of the best beam: the `log_prob`
+    output of tf.nn.ctc_beam_search_decoder as chiron/export_test.py:36-40 exposes it).  Returns (paths, scores[B])."""
+    import ctypes
+    lg = np.ascontiguousarray(logits, dtype=np.float32)
+    B, T, C = lg.shape
+    ln = np.ascontiguousarray(lens, dtype=np.int32)
+    out = np.zeros((B, max(T, 1)), dtype=np.int32)
+    out_len = np.zeros(B, dtype=np.int32)
+    scores = np.zeros(B, dtype=np.float32)
+    fp, ip = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)
+    _clib().oracle_ctc_beam_batch_scored(lg.ctypes.data_as(fp), B, T, C, ln.ctypes.data_as(ip), int(beam_width),
+                                         out.ctypes.data_as(ip), out_len.ctypes.data_as(ip), scores.ctypes.data_as(fp))
+    if (out_len < 0).any():
+        raise MemoryError("oracle_ctc_beam failed")
+    return [out[b, :out_len[b]].tolist() for b in range(B)], scores

@@ -32,7 +32,14 @@ static int bottom_of(const node_t* nd, const int* leaves, int n) {
 }
 
 /* logits [T][C] row major, blank = C-1 (C <= 9).  Returns the decoded length (labels in out[0..T)), -1 on OOM. */
+static int oracle_ctc_beam_scored(const float* logits, int T, int C, int len, int W, int* out, float* score);
 int oracle_ctc_beam(const float* logits, int T, int C, int len, int W, int* out) {
+    return oracle_ctc_beam_scored(logits, T, C, len, W, out, 0);
+}
+
+/* score (may be NULL): newp.total of the best beam = what TopPaths() reports as the path's log probability (the
+ * `log_prob` output of tf.nn.ctc_beam_search_decoder in TF 1.15: inputs are max-subtracted per frame, not soft-maxed). */
+static int oracle_ctc_beam_scored(const float* logits, int T, int C, int len, int W, int* out, float* score) {
     const int blank = C - 1;
     size_t cap = 1 + (size_t)(len > 0 ? len : 1) * (size_t)W * (size_t)(C - 1);
     node_t* nd = (node_t*)malloc(cap * sizeof(node_t));
@@ -121,6 +128,7 @@ int oracle_ctc_beam(const float* logits, int T, int C, int len, int W, int* out)
     int best = 0;
     for (int i = 1; i < n_leaves; ++i)
         if (nd[leaves[i]].n_total > nd[leaves[best]].n_total) best = i;
+    if (score) *score = nd[leaves[best]].n_total;
     int n = 0, cur = leaves[best];
     while (nd[cur].parent >= 0) { ++n; cur = nd[cur].parent; }
     cur = leaves[best];
@@ -147,6 +155,12 @@ int oracle_ctc_greedy(const float* logits, int T, int C, int len, int* out) {
 void oracle_ctc_beam_batch(const float* logits, int B, int T, int C, const int* lens, int W, int* out, int* out_len) {
     for (int b = 0; b < B; ++b)
         out_len[b] = oracle_ctc_beam(logits + (size_t)b * T * C, T, C, lens[b], W, out + (size_t)b * T);
+}
+
+void oracle_ctc_beam_batch_scored(const float* logits, int B, int T, int C, const int* lens, int W, int* out, int* out_len,
+                                  float* scores) {
+    for (int b = 0; b < B; ++b)
+        out_len[b] = oracle_ctc_beam_scored(logits + (size_t)b * T * C, T, C, lens[b], W, out + (size_t)b * T, scores + b);
 }
 
 void oracle_ctc_greedy_batch(const float* logits, int B, int T, int C, const int* lens, int* out, int* out_len) {

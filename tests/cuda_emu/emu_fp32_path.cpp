@@ -191,8 +191,8 @@ extern "C" int emu_greedy(const float* logits, const int32_t* lens, int B, int T
 // memory; 16-bit trie nodes) or the thread-per-window kernel over global workspaces (warp = 0).  Returns 1 when a window
 // outgrew the pool (the cooperative kernels then report it as n_bases = -1, beam_kernel as an empty read), 0 when every
 // window decoded, or a negative CB_ERR_* code.
-extern "C" int emu_beam(int warp, const float* logits, const int32_t* lens, int B, int T, int C, int W, int pool,
-                        int8_t* bases, int32_t* n_bases) {
+static int emu_beam_impl(int warp, const float* logits, const int32_t* lens, int B, int T, int C, int W, int pool,
+                         int8_t* bases, int32_t* n_bases, float* scores) {
     int overflow = 0;
     if (pool < 2 * W + 2) return CB_ERR_ARG;
     if (warp) {
@@ -201,20 +201,30 @@ extern "C" int emu_beam(int warp, const float* logits, const int32_t* lens, int 
         const unsigned grid = (B + cb_seq::BEAM_WARPS - 1) / cb_seq::BEAM_WARPS;
         if (staged)
             emu::launch2d(grid, 1, cb_seq::BEAM_WARPS * 32, stride * cb_seq::BEAM_WARPS, [&] {
-                cb_seq::beam_warp_kernel<true>(logits, lens, B, T, C, W, pool, (int)stride, bases, n_bases, &overflow);
+                cb_seq::beam_warp_kernel<true>(logits, lens, B, T, C, W, pool, (int)stride, bases, n_bases, &overflow, scores);
             });
         else
             emu::launch2d(grid, 1, cb_seq::BEAM_WARPS * 32, stride * cb_seq::BEAM_WARPS, [&] {
-                cb_seq::beam_warp_kernel<false>(logits, lens, B, T, C, W, pool, (int)stride, bases, n_bases, &overflow);
+                cb_seq::beam_warp_kernel<false>(logits, lens, B, T, C, W, pool, (int)stride, bases, n_bases, &overflow, scores);
             });
     } else {
         const size_t stride = cb_seq::align_up(cb_beam_work_bytes(W, pool), 16);
         std::vector<char> ws(stride * (size_t)B + 64);
         emu::launch((B + 63) / 64, 64, [&] {
-            cb_seq::beam_kernel(logits, lens, B, T, C, W, pool, ws.data(), stride, bases, n_bases, &overflow, nullptr, 0);
+            cb_seq::beam_kernel(logits, lens, B, T, C, W, pool, ws.data(), stride, bases, n_bases, &overflow, nullptr, 0, scores);
         });
     }
     return overflow;
+}
+
+extern "C" int emu_beam(int warp, const float* logits, const int32_t* lens, int B, int T, int C, int W, int pool,
+                        int8_t* bases, int32_t* n_bases) {
+    return emu_beam_impl(warp, logits, lens, B, T, C, W, pool, bases, n_bases, nullptr);
+}
+// ... also returning the top path's log probability per window (cb_decode_beam_scored)
+extern "C" int emu_beam_scored(int warp, const float* logits, const int32_t* lens, int B, int T, int C, int W, int pool,
+                               int8_t* bases, int32_t* n_bases, float* scores) {
+    return emu_beam_impl(warp, logits, lens, B, T, C, W, pool, bases, n_bases, scores);
 }
 
 // Overlap assembly of one read: the five kernels of cb_launch_assemble with its grids and workspace plan.
@@ -260,21 +270,21 @@ extern "C" int emu_beam_passes(const float* logits, const int32_t* lens, int B, 
     auto count = [&]() { int m = 0; for (int b = 0; b < B; ++b) m += n_bases[b] == -1; return m; };
     const size_t stride = cb_seq::beam_warp_stride(T, C, W, pool_first, false);
     emu::launch2d((B + cb_seq::BEAM_WARPS - 1) / cb_seq::BEAM_WARPS, 1, cb_seq::BEAM_WARPS * 32, stride * cb_seq::BEAM_WARPS, [&] {
-        cb_seq::beam_warp_kernel<false>(logits, lens, B, T, C, W, pool_first, (int)stride, bases, n_bases, &flag);
+        cb_seq::beam_warp_kernel<false>(logits, lens, B, T, C, W, pool_first, (int)stride, bases, n_bases, &flag, nullptr);
     });
     marked[0] = count();
     if ((marked[0] > 0) != (flag != 0)) return -100;          // marks without the flag (or the reverse) would be a bug
     const long long pool_r = pool_retry > 0 ? pool_retry : cb_seq::beam_retry_pool(T, W);
     const size_t smem_r = cb_seq::align_up(cb_beam_work_bytes<cb_seq::BeamIdx>(W, (int)pool_r), 16);
     emu::launch2d(B, 1, 32, smem_r, [&] {
-        cb_seq::beam_retry_kernel(logits, lens, B, T, C, W, (int)pool_r, bases, n_bases, &flag);
+        cb_seq::beam_retry_kernel(logits, lens, B, T, C, W, (int)pool_r, bases, n_bases, &flag, nullptr);
     });
     marked[1] = count();
     const int cap = 2 * W * (T + 1) + 2;
     const size_t stride_g = cb_seq::align_up(cb_beam_work_bytes(W, cap), 16);
     std::vector<char> ws(stride_g * (size_t)(n_slots > 0 ? n_slots : 1) + 64);
     emu::launch((B + 63) / 64, 64, [&] {
-        cb_seq::beam_kernel(logits, lens, B, T, C, W, cap, ws.data(), stride_g, bases, n_bases, &error, &slots, n_slots);
+        cb_seq::beam_kernel(logits, lens, B, T, C, W, cap, ws.data(), stride_g, bases, n_bases, &error, &slots, n_slots, nullptr);
     });
     marked[2] = count();
     return error;

@@ -319,6 +319,38 @@ def test_beam_search_kernels_are_bit_identical_to_the_c_oracle(emu, warp):
     assert compared >= 7 and set(overflowed) <= {13, 30}      # random logits: wide beams may outgrow the small pool
 
 
+@pytest.mark.parametrize("warp", [1, 2, 0], ids=["beam_warp_kernel", "beam_warp_kernel_staged", "beam_kernel"])
+def test_beam_search_kernels_report_the_top_path_score(emu, warp):
+    """cb_decode_beam_scored: the `log_prob` output of the serving signature (chiron/export_test.py:36-40,103-113) = the
+    score TopPaths() reports for the decoded path.  Every kernel variant against the C oracle's restatement, bit for bit
+    (same libm on the host), and against an independent check: at width 1 with no pruning pressure the score of an
+    all-blank path is the sum of the per-frame max-subtracted blank logits."""
+    rng = np.random.default_rng(77)
+    B, T, C = 7, 30, 5
+    lg = rng.normal(size=(B, T, C)).astype(np.float32) * 2
+    lg[:, :, C - 1] += 1.5
+    lg[6] = -8.0
+    lg[6, :, C - 1] = 0.25                        # blank wins every frame by a wide margin
+    lens = np.array([T, 0, 1, 17, T, 9, T], np.int32)
+    vp = ctypes.c_void_p
+    for W in (1, 4, 30):
+        pool = 2 * W * (T + 1) + 2
+        bases = np.full((B, T), 9, np.int8)
+        n_bases = np.full(B, -1, np.int32)
+        scores = np.full(B, np.nan, np.float32)
+        assert emu.emu_beam_scored(warp, _fp(lg), lens.ctypes.data_as(vp), B, T, C, W, pool, bases.ctypes.data_as(vp),
+                                   n_bases.ctypes.data_as(vp), _fp(scores)) == 0
+        paths, ref = O.ctc_beam_scores_c(lg, lens, W)
+        assert [bases[b, :n_bases[b]].tolist() for b in range(B)] == paths
+        assert np.array_equal(scores, ref), (W, scores, ref)
+        assert scores[1] == 0.0 and n_bases[6] == 0           # empty window: log(1); all-blank window decodes to nothing
+    # all-blank path, width 1: only the blank extension survives, its score is the sum of (blank - max) = 0 per frame
+    one = np.zeros(B, np.float32)
+    emu.emu_beam_scored(warp, _fp(lg), lens.ctypes.data_as(vp), B, T, C, 1, 2 * (T + 1) + 2, bases.ctypes.data_as(vp),
+                        n_bases.ctypes.data_as(vp), _fp(one))
+    assert one[6] == 0.0
+
+
 def test_assembly_kernels_reproduce_the_reference_fixtures(emu):
     """asm_compact -> asm_disp -> asm_scan -> asm_vote -> asm_finish (with the launcher's grids and workspace plan) on the
     fixtures produced by the reference's own easy_assembler + qs() (tests/golden/assembly_ref): consensus, quality string

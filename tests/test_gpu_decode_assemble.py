@@ -152,3 +152,30 @@ def test_cooperative_beam_kernel_is_bit_identical_to_the_sequential_one(caller):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+
+
+def test_serving_signature_predict(caller, dna_model):
+    """{x, seq_len} -> {indices, values, dense_shape, logits, prob_logits, log_prob} (chiron/export_test.py:103-113): the
+    sparse triple is the golden read1 segments, logits / prob_logits the oracle's, and log_prob the score the oracle's
+    restatement of TopPaths() gives on the SAME logits (device expf/log1pf vs glibc: a few ulp over 400 frames)."""
+    cfg, t, _ = dna_model
+    sig = O.read_signal_text(os.path.join(GOLDEN, "DNA", "raw", "read1.signal"))
+    x, lens = O.make_windows(O.normalize_signal(sig, cfg.sig_norm), L, JUMP)
+    x, lens = x[-24:], lens[-24:]                         # incl. the ragged last window
+    out = caller.predict(x, lens, beam_width=BEAM)
+    N, T = len(x), out["logits"].shape[1]
+    assert out["logits"].shape == (N, T, 5) and out["prob_logits"].shape == (N,) and out["log_prob"].shape == (N, 1)
+    ref = O.inference(x, lens, cfg, t)
+    assert np.abs(out["logits"] - ref).max() < 5e-3
+    assert np.allclose(out["prob_logits"], O.path_prob(ref), atol=1e-3)
+    len_out = O.seq_len_out(lens, L / T)
+    paths, scores = O.ctc_beam_scores_c(out["logits"], len_out, BEAM)
+    golden = read_fasta_records(os.path.join(GOLDEN, "DNA", "segments", "read1.fastq"))[-N:]
+    assert [O.index2base(p) for p in paths] == golden
+    rows = out["indices"][:, 0]
+    got = [out["values"][rows == b].tolist() for b in range(N)]
+    assert got == paths
+    assert all((out["indices"][rows == b, 1] == np.arange((rows == b).sum())).all() for b in range(N))
+    assert out["dense_shape"].tolist() == [N, max(len(p) for p in paths)]
+    assert out["indices"].dtype == np.int64 and out["values"].dtype == np.int64
+    assert np.allclose(out["log_prob"][:, 0], scores, rtol=0, atol=2e-3), np.abs(out["log_prob"][:, 0] - scores).max()

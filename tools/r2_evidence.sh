@@ -21,7 +21,7 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 4
 # head / generator / transpose / greedy / path_prob, beam search, assembly
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 11 -c 11 -f -o $out/prof_gemm \
     python tools/gpu_quick.py tc 4096 512 > $out/ncu_gemm.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm_tc_kernel -s 3 -c 3 -f -o $out/prof_lstm \
+timeout 600 ncu --set full --clock-control none -k regex:lstm_tc_kernel -s 3 -c 3 -f -o $out/prof_lstm \
     python tools/gpu_quick.py tc 4096 512 > $out/ncu_lstm.log 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:"head_tmajor|gen_conv2a|transpose_x|greedy|path_prob|seq_len" -s 6 -c 6 -f -o $out/prof_small \
     python tools/gpu_quick.py tc 4096 512 > $out/ncu_small.log 2>&1
@@ -36,4 +36,9 @@ timeout 120 python tools/call_bench.py --reads 800 --fmt signal --beam 30 > $out
 timeout 120 python tools/call_bench.py --reads 800 --fmt signal --stub > $out/call_signal_stub.json 2> $out/call_signal_stub.err
 timeout 400 python tools/experiments/beam_real_ab.py > $out/beam_real_ab.jsonl 2> $out/beam_real_ab.err
 cat $out/call_signal.json $out/call_fast5.json $out/call_signal_beam30.json
-ls -la $out
+# gpurun brings back at most 64 MiB: summarise the captures on the box and drop the reports
+for r in gemm lstm small beam asm; do python tools/ncu_summary.py $out/prof_$r.ncu-rep > $out/ncu_$r.txt 2>&1; done
+python tools/ncu_traffic.py $out tc 4096 > $out/traffic.json 2> $out/traffic.err
+ncu -i $out/prof_gemm.ncu-rep --page source --csv > $out/ncu_gemm_source.csv 2>/dev/null; gzip -f $out/ncu_gemm_source.csv
+rm -f $out/*.ncu-rep
+ls -la $out; du -sh $out
