@@ -112,6 +112,63 @@ struct TileIter {
 };
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// 16-byte store of a finished output element group.  CB_TC_STCS=1: streaming (evict-first) stores -- the output image is
+// consumed by the NEXT launch, 2 GB later; it has no business staying in L2 (A/B switch).
+#ifndef CB_TC_STCS
+#define CB_TC_STCS 0
+#endif
+__device__ __forceinline__ void st_out(uint4* p, const uint4& v) {
+#if CB_TC_STCS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
+__device__ __forceinline__ float4 lds4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// Lean emit of 16 finished sums (tile columns n..n+15 of this thread's row) of a convolution: x 2^-s + shift (+ rank-1
+// residual) -> ReLU -> hi/lo split -> two 16-byte stores per k-group plane.  vec_s: shared-memory address of the cached
+// epilogue vectors [shift | rw | rinv | rsh][BN]; hi_row / lo_row: this row in plane o_plane0 of the output image (uint4
+// units); mx: running maximum of the outputs (the fp16 range check, once per kernel instead of once per element).
+template <bool RES>
+__device__ __forceinline__ void emit16_image(const float (&sum)[16], int n, uint32_t vec_s, int BN, float out_scale, float xr,
+                                             uint4* hi_row, uint4* lo_row, size_t plane_rows, float& mx) {
+    float o[16];
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+        const uint32_t a = vec_s + (uint32_t)(n + q4 * 4) * 4u;
+        const float4 sh = lds4(a);
+        o[q4 * 4 + 0] = fmaf(sum[q4 * 4 + 0], out_scale, sh.x);
+        o[q4 * 4 + 1] = fmaf(sum[q4 * 4 + 1], out_scale, sh.y);
+        o[q4 * 4 + 2] = fmaf(sum[q4 * 4 + 2], out_scale, sh.z);
+        o[q4 * 4 + 3] = fmaf(sum[q4 * 4 + 3], out_scale, sh.w);
+        if constexpr (RES) {
+            const float4 w = lds4(a + (uint32_t)BN * 4u), iv = lds4(a + (uint32_t)BN * 8u), rs = lds4(a + (uint32_t)BN * 12u);
+            o[q4 * 4 + 0] += fmaf(xr * w.x, iv.x, rs.x);
+            o[q4 * 4 + 1] += fmaf(xr * w.y, iv.y, rs.y);
+            o[q4 * 4 + 2] += fmaf(xr * w.z, iv.z, rs.z);
+            o[q4 * 4 + 3] += fmaf(xr * w.w, iv.w, rs.w);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) { o[e] = fmaxf(o[e], 0.f); mx = fmaxf(mx, o[e]); }
+#pragma unroll
+    for (int h8 = 0; h8 < 2; ++h8) {
+        float v8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v8[e] = o[h8 * 8 + e];
+        uint4 hi, lo;
+        split8(v8, hi, lo);
+        const size_t off = (size_t)((n >> 3) + h8) * plane_rows;
+        st_out(hi_row + off, hi);
+        st_out(lo_row + off, lo);
+    }
+}
 
 // ---- PTX of the two flavours: NC = 1 (one CTA per tile) and NC = 2 (CTA pair, tcgen05 cta_group::2) -------------------------
 template <int NC>
@@ -168,7 +225,13 @@ __device__ __forceinline__ void tma_w_g2s_pair(void* dst, const CUtensorMap* tm,
 // this CTA), then the barriers; resident mode: k_chunks x {B_hi, B_lo} first, stages hold A only.
 // MULTI: several partial sums per tile (q.cpp < q.k_chunks); the single-accumulator instantiation carries none of the
 // register-accumulation code (with it compiled in, the HBM-write-bound input projection ran 2.7 instead of 2.2 ms).
-template <int NC, bool MULTI>
+// EPI: epilogue code path.  0 = generic (every TcGemm flag read at run time).  1 / 2 = the convolutions' path (ReLU, operand
+// image out, one n-tile, epilogue vectors cached in shared memory; 2 = with the rank-1 residual of block-1 conv2c): the same
+// arithmetic in the same order, compiled without the run-time flag tests, the generic-to-shared address conversions and the
+// per-store 64-bit address products of the generic lambda.  ncu (profiles/r02_e1_ncu_gemm_source.csv.gz) showed the generic
+// emit as 383 SASS instructions per 16 columns = 3,064 per output tile and warp: with two epilogue warps per scheduler the
+// emit is ISSUE-bound (10.6 k clocks per tile, in which the tensor pipe can only run two partial sums ahead).
+template <int NC, bool MULTI, int EPI>
 __device__ __forceinline__ void gemm_tc_body(const TcParams& q) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const TcGemm& g = q.g;
@@ -250,6 +313,8 @@ __device__ __forceinline__ void gemm_tc_body(const TcParams& q) {
             acc_empty_leader[b] = NC == 2 ? mapa_shared(smem_u32(&acc_empty[b]), 0) : smem_u32(&acc_empty[b]);
         uint32_t it = 0, pit = 0;                          // tiles / partial sums this unit has worked on
         bool overflow = false;
+        float out_max = 0.f;                               // EPI > 0: largest output written (>= 0 after the ReLU)
+        const uint32_t vec_s = smem_u32(smem + q.vec_off);
         for (int mu, nt; tiles.get((int)it, mu, nt); ++it) {
             const int mt = mu * NC + (int)rank;
             const int to = mt / tiles_per_frame;
@@ -258,8 +323,14 @@ __device__ __forceinline__ void gemm_tc_body(const TcParams& q) {
             float xr = 0.f;
             if (g.res && row_ok) xr = __ldg(g.xT + (size_t)to * g.res_stride * g.Bp + b);
             const size_t orow = (size_t)g.o.row0 + (size_t)to * g.Bp + b;
+            uint4* const hi_row = reinterpret_cast<uint4*>(g.o.hi) + (size_t)g.o_plane0 * g.o.plane_rows + orow;
+            uint4* const lo_row = reinterpret_cast<uint4*>(g.o.lo) + (size_t)g.o_plane0 * g.o.plane_rows + orow;
             // 16 finished sums (columns n0..n0+15 of this thread's row) -> scale/shift/residual/ReLU -> HBM
             auto emit = [&](int n0, const float (&sum)[16]) {
+                if constexpr (EPI > 0) {                  // (one n-tile: n0 is the tile column)
+                    emit16_image<EPI == 2>(sum, n0, vec_s, BN, q.out_scale, xr, hi_row, lo_row, (size_t)g.o.plane_rows, out_max);
+                    return;
+                }
                 float o[16];
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
@@ -301,8 +372,8 @@ __device__ __forceinline__ void gemm_tc_body(const TcParams& q) {
                         uint4 hi, lo;
                         split8(v8, hi, lo);
                         const size_t off = ((size_t)(g.o_plane0 + (n0 >> 3) + h8) * g.o.plane_rows + orow) * 8;
-                        *reinterpret_cast<uint4*>(g.o.hi + off) = hi;
-                        *reinterpret_cast<uint4*>(g.o.lo + off) = lo;
+                        st_out(reinterpret_cast<uint4*>(g.o.hi + off), hi);
+                        st_out(reinterpret_cast<uint4*>(g.o.lo + off), lo);
                     }
                 } else {                                  // fp32 [to][n/4][Bp][4]: every store instruction of a warp writes
                                                           // 512 contiguous bytes (16 full sectors)
@@ -423,7 +494,7 @@ __device__ __forceinline__ void gemm_tc_body(const TcParams& q) {
                 }
             }
         }
-        if (overflow) atomicExch(q.range_flag, 1);
+        if (overflow || !(out_max <= 65504.f)) atomicExch(q.range_flag, 1);
     } else if (warp == N_EPI_WARPS) {
         // ============================ MMA issuer (whole warp runs the loop, one elected lane issues; pair: leader CTA) ======
         const bool leader = elect_one();
@@ -890,11 +961,11 @@ __device__ __forceinline__ void gemm_tc_body_v1(const TcParams& q) {
 
 template <bool MULTI>
 __global__ void __launch_bounds__(NTHREADS1, 1) gemm_tc_kernel(const __grid_constant__ TcParams q) {
-    if constexpr (MULTI) gemm_tc_body<1, true>(q); else gemm_tc_body_v1<1>(q);
+    if constexpr (MULTI) gemm_tc_body<1, true, 0>(q); else gemm_tc_body_v1<1>(q);
 }
-template <bool MULTI>
+template <bool MULTI, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) gemm_tc_pair_kernel(const __grid_constant__ TcParams q) {
-    gemm_tc_body<2, MULTI>(q);
+    gemm_tc_body<2, MULTI, EPI>(q);
 }
 
 // x[B][L] -> xT[L][Bp]  (so that everything downstream reads the raw signal coalesced over windows)
@@ -1028,7 +1099,10 @@ int cb_tc_build_layer(cb_handle* h, int layer_id, const float* W, int K, int N, 
     // accumulator).
     static const int cpp_conv = getenv("CB_TC_CPP") ? atoi(getenv("CB_TC_CPP")) : 4;
     static const int cpp_proj = getenv("CB_TC_CPP_PROJ") ? atoi(getenv("CB_TC_CPP_PROJ")) : 8;
-    const int cpp_env = layer_id >= 32 ? cpp_proj : cpp_conv;
+    // CB_TC_CPP_K256 / CB_TC_CPP_K512: the same for the convolutions with K <= 256 / K = 512 only (the HBM-bound 1x1 layers)
+    static const int cpp_k256 = getenv("CB_TC_CPP_K256") ? atoi(getenv("CB_TC_CPP_K256")) : cpp_conv;
+    static const int cpp_k512 = getenv("CB_TC_CPP_K512") ? atoi(getenv("CB_TC_CPP_K512")) : cpp_conv;
+    const int cpp_env = layer_id >= 32 ? cpp_proj : (L.k_chunks <= 8 ? cpp_k256 : (L.k_chunks <= 16 ? cpp_k512 : cpp_conv));
     L.cpp = cpp_env > 0 && cpp_env < L.k_chunks ? cpp_env : L.k_chunks;
     // TRUNCATION COMPENSATION.  The tensor core's fp32 accumulator rounds toward zero on every MMA, so an accumulated value
     // shrinks by a small relative amount c per chained MMA (round-to-zero of a 24-bit significand loses half an ulp on
@@ -1158,8 +1232,12 @@ int cb_tc_prepare(cb_handle* h, const float* hw) {
     st->d_range_flag = h->d_flag + CB_FLAG_TC_RANGE;     // sticky, reported by cb_check_deferred
     CB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
     CB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-    CB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-    CB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    CB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    CB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    CB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    CB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    CB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    CB_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
     return cb_lstm_tc_prepare(h, hw);
 }
 
@@ -1260,8 +1338,18 @@ int cb_launch_gemm_tc(cb_handle* h, const TcGemm& g, cudaStream_t s) {
     const bool multi = q.cpp < q.k_chunks || force_multi;
     if (pair) {
         q.img = L.img2; q.tm_w = L.tm_w2;
-        if (multi) gemm_tc_pair_kernel<true><<<grid, NTHREADS, smem, s>>>(q);
-        else gemm_tc_pair_kernel<false><<<grid, NTHREADS, smem, s>>>(q);
+        // the convolutions' specialised epilogue (see gemm_tc_body): ReLU'd operand image out of one n-tile, vectors cached
+        static const int lean_env = getenv("CB_TC_LEAN_EPI") ? atoi(getenv("CB_TC_LEAN_EPI")) : 1;      // 0: generic (A/B)
+        const int epi = (lean_env && q.vec_off && L.n_tiles == 1 && g.relu && g.out_mode == 2) ? (g.res ? 2 : 1) : 0;
+        if (multi) {
+            if (epi == 2) gemm_tc_pair_kernel<true, 2><<<grid, NTHREADS, smem, s>>>(q);
+            else if (epi == 1) gemm_tc_pair_kernel<true, 1><<<grid, NTHREADS, smem, s>>>(q);
+            else gemm_tc_pair_kernel<true, 0><<<grid, NTHREADS, smem, s>>>(q);
+        } else {
+            if (epi == 2) gemm_tc_pair_kernel<false, 2><<<grid, NTHREADS, smem, s>>>(q);
+            else if (epi == 1) gemm_tc_pair_kernel<false, 1><<<grid, NTHREADS, smem, s>>>(q);
+            else gemm_tc_pair_kernel<false, 0><<<grid, NTHREADS, smem, s>>>(q);
+        }
     } else {
         if (multi) gemm_tc_kernel<true><<<grid, NTHREADS1, smem, s>>>(q);
         else gemm_tc_kernel<false><<<grid, NTHREADS1, smem, s>>>(q);
