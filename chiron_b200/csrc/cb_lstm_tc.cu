@@ -127,9 +127,14 @@ __device__ __forceinline__ void split4(const float (&v)[4], uint2& hi, uint2& lo
 // Written for <= 72 registers (25 warps per SM): per-step addresses are rebuilt from 32-bit element indices (every
 // tensor has < 2^32 16-byte elements, checked by the launcher) instead of being carried as 64-bit pointers, and the
 // items are processed one after the other (4 cells of instruction-level parallelism, 6 warps per scheduler).
+// REMOTE (CB_LSTM_EXCH=remote, see lstm_tc_kernel): every h value is ALSO stored straight into the peer CTA's buffer
+// (st.shared::cluster at hbuf_peer), and a warp signals once per step -- after its last item -- on h_full[s & 1] of BOTH
+// CTAs; local_done is unused.
+template <bool REMOTE>
 __device__ __forceinline__ void gate_loop(const LstmTcParams& q, uint32_t hbuf_s, uint64_t* local_done, uint64_t* acc_ready,
                                           uint64_t* pre_done, uint32_t tmem_base, int warp, int lane, int dir, int b0,
-                                          int hg_base, int hlA, int hlB, int hlX) {
+                                          int hg_base, int hlA, int hlB, int hlX, uint32_t hbuf_peer, uint64_t* h_full,
+                                          uint32_t h_full_peer) {
     const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;
     const int b = b0 + row;
@@ -243,6 +248,11 @@ __device__ __forceinline__ void gate_loop(const LstmTcParams& q, uint32_t hbuf_s
                 const uint32_t off = h_hi + (uint32_t)kg * (RM * 16) + (hg & 1) * 8;
                 asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(off), "r"(hi.x), "r"(hi.y) : "memory");
                 asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(off + HS_BYTES), "r"(lo.x), "r"(lo.y) : "memory");
+                if constexpr (REMOTE) {
+                    const uint32_t offp = off - hbuf_s + hbuf_peer;        // the same place in the peer's buffer
+                    asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(offp), "r"(hi.x), "r"(hi.y) : "memory");
+                    asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(offp + HS_BYTES), "r"(lo.x), "r"(lo.y) : "memory");
+                }
                 if (q.write_img && !(CB_LSTM_DEV && (q.dbg_flags & 2))) {
                     // uint2 element ((dir*13 + kg)*plane_rows + row0 + t*Bp + b)*2 + (hg&1)
                     const uint32_t g2 = ((uint32_t)(dir * KG + kg) * (uint32_t)q.o_img.plane_rows + (uint32_t)q.o_img.row0 +
@@ -252,11 +262,25 @@ __device__ __forceinline__ void gate_loop(const LstmTcParams& q, uint32_t hbuf_s
                 }
             }
             if (CB_LSTM_DEV) { if (probe) q.dbg[((s - 100) * 32 + warp) * 8 + 3 * phase + 2] = clock64(); __syncwarp(); }
-            // this warp's h rows of the phase are in the CTA's buffer: let the exchange thread ship them to the peer
-            fence_proxy_async();           // generic-proxy h writes -> visible to the async proxy (bulk copy, tensor core)
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&local_done[phase]);
+            if constexpr (REMOTE) {
+                if (phase == 1) {
+                    // this warp's h values of the step sit in both CTAs' buffers: generic-proxy writes (shared::cta and
+                    // shared::cluster) -> visible to the async proxy (the tensor cores of both CTAs), then one arrival per CTA
+                    fence_proxy_async_all();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&h_full[s & 1]);
+                        mbar_arrive_cluster(h_full_peer + (uint32_t)(s & 1) * 8u);
+                    }
+                }
+            } else {
+                // this warp's h rows of the phase are in the CTA's buffer: let the exchange thread ship them to the peer
+                fence_proxy_async();       // generic-proxy h writes -> visible to the async proxy (bulk copy, tensor core)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&local_done[phase]);
+            }
         }
         if (s + 2 < q.T) load_pre(s + 2);
         if (s + 4 < q.T) prefetch_l2(s + 4);
@@ -265,6 +289,13 @@ __device__ __forceinline__ void gate_loop(const LstmTcParams& q, uint32_t hbuf_s
     tmem_st_wait();
 }
 
+// REMOTE = false (default): warp 0 waits for the phase's gate warps and ships the finished K-groups with two
+// cp.async.bulk shared::cta -> shared::cluster per phase.  REMOTE = true (CB_LSTM_EXCH=remote, kept as a measured negative
+// result): the gate threads store every h value into both CTAs' buffers themselves (st.shared / st.shared::cluster) and
+// each warp arrives once per step on h_full[s & 1] of both CTAs -- bit-identical, but 3.5 instead of 2.4 ms per launch at
+// 4096 x 512 (profiles/r02_s19_lstm_exchange_ab.txt): 8-byte remote stores move far fewer bytes per clock over the
+// SM-to-SM network than bulk copies (DSMEM: ~17 B/clk per SM pair), and the proxy fence waits for their acknowledgements.
+template <bool REMOTE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) lstm_tc_kernel(const LstmTcParams q) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* w_hi = smem;
@@ -278,7 +309,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) lstm_tc
     uint64_t* pre_done = bars + 6;     // [2] by step parity: the gate warps parked the step's input projection in its
                                        //     accumulator buffer (two barriers: a warp arrives for step s+1 without
                                        //     having waited on anything since its arrival for step s)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* h_full = bars + 8;       // [2] REMOTE: by step parity -- every gate warp of BOTH CTAs stored its h(s) here
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
@@ -305,6 +337,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) lstm_tc
         mbar_init(&acc_ready[1], 1);
         mbar_init(&pre_done[0], GATE_WARPS);
         mbar_init(&pre_done[1], GATE_WARPS);
+        mbar_init(&h_full[0], 2 * GATE_WARPS);
+        mbar_init(&h_full[1], 2 * GATE_WARPS);
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -344,7 +378,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) lstm_tc
         for (int s = 0; s < q.T; ++s) {
             if (leader) {
                 mbar_wait(&pre_done[s & 1], (s >> 1) & 1);     // pre(s) sits in accumulator buffer s&1
-                if (s > 0) mbar_wait_cluster(h_ready, (s - 1) & 1);   // peer's half of h(s-1) landed (own half: local_done, below)
+                if (s > 0) {
+                    if constexpr (REMOTE) mbar_wait_cluster(&h_full[(s - 1) & 1], ((s - 1) >> 1) & 1);   // all of h(s-1), both halves
+                    else mbar_wait_cluster(h_ready, (s - 1) & 1);   // peer's half of h(s-1) landed (own half: local_done, below)
+                }
             }
             __syncwarp();
             tc_fence_after();
@@ -370,23 +407,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) lstm_tc
                     umma_commit(&acc_ready[phase]);
                 }
             }
-            // arm this step's receive barrier BEFORE shipping my half (the peer can only send h(s+1) after it got
-            // my h(s), so bytes of different steps never meet in one barrier phase)
-            if (leader) mbar_arrive_expect_tx(h_ready, peer_bytes);
-            const uint32_t buf_off = (uint32_t)(s & 1) * (2 * HS_BYTES);
+            if constexpr (!REMOTE) {
+                // arm this step's receive barrier BEFORE shipping my half (the peer can only send h(s+1) after it got
+                // my h(s), so bytes of different steps never meet in one barrier phase)
+                if (leader) mbar_arrive_expect_tx(h_ready, peer_bytes);
+                const uint32_t buf_off = (uint32_t)(s & 1) * (2 * HS_BYTES);
 #pragma unroll
-            for (int phase = 0; phase < 2; ++phase) {
-                const uint32_t off = buf_off + (phase ? offB : offA), len = phase ? lenB : lenA;
-                if (leader) {
-                    mbar_wait(&local_done[phase], s & 1);      // my gate warps wrote the phase's K-groups of h(s)
-                    bulk_s2s_cluster(hbuf_peer + off, hbuf + off, len, h_ready_peer);                        // hi image rows
-                    bulk_s2s_cluster(hbuf_peer + off + HS_BYTES, hbuf + off + HS_BYTES, len, h_ready_peer);  // lo image rows
+                for (int phase = 0; phase < 2; ++phase) {
+                    const uint32_t off = buf_off + (phase ? offB : offA), len = phase ? lenB : lenA;
+                    if (leader) {
+                        mbar_wait(&local_done[phase], s & 1);      // my gate warps wrote the phase's K-groups of h(s)
+                        bulk_s2s_cluster(hbuf_peer + off, hbuf + off, len, h_ready_peer);                        // hi image rows
+                        bulk_s2s_cluster(hbuf_peer + off + HS_BYTES, hbuf + off + HS_BYTES, len, h_ready_peer);  // lo image rows
+                    }
                 }
             }
             __syncwarp();
             tc_fence_after();                              // gate warps released the accumulator (local_done[1])
         }
-        if (leader) mbar_wait_cluster(h_ready, (q.T - 1) & 1);   // the peer's last copies into my shared memory have landed
+        // the peer's last writes into my shared memory have landed
+        if (leader) {
+            if constexpr (REMOTE) mbar_wait_cluster(&h_full[(q.T - 1) & 1], ((q.T - 1) >> 1) & 1);
+            else mbar_wait_cluster(h_ready, (q.T - 1) & 1);
+        }
         __syncwarp();
     } else {
         // ============================ gate warps ======================================================================
@@ -395,7 +438,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) lstm_tc
         // seventh half-group, which goes to slot 0.
         const int slot = (warp - 1) >> 2;
         const int hlA = slot, hlB = SLOTS + slot, hlX = (rank && slot == 0) ? 2 * SLOTS : -1;
-        gate_loop(q, smem_u32(hbuf), local_done, acc_ready, pre_done, tmem_base, warp, lane, dir, b0, hg_base, hlA, hlB, hlX);
+        const uint32_t peer = rank ^ 1u;
+        gate_loop<REMOTE>(q, smem_u32(hbuf), local_done, acc_ready, pre_done, tmem_base, warp, lane, dir, b0, hg_base, hlA, hlB, hlX,
+                          mapa_shared(smem_u32(hbuf), peer), h_full, mapa_shared(smem_u32(h_full), peer));
     }
 
     tc_fence_before();
@@ -445,7 +490,8 @@ int cb_lstm_tc_prepare(cb_handle* h, const float* hw) {
             CB_CUDA(cudaMalloc(&st->wimg[l][d], img.size() * sizeof(__half)));
             CB_CUDA(cudaMemcpy(st->wimg[l][d], img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
         }
-    CB_CUDA(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    CB_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    CB_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     return CB_OK;
 }
 
@@ -483,7 +529,9 @@ int cb_launch_lstm_tc(cb_handle* h, const LstmProblem& p, const CbImg* o_img, in
     if (probe && !d_dbg) { cudaMalloc(&d_dbg, 4 * 32 * 8 * sizeof(long long)); cudaMemset(d_dbg, 0, 4 * 32 * 8 * sizeof(long long)); }
     q.dbg = probe ? d_dbg : nullptr;
     q.dbg_flags = getenv("CB_LSTM_DBG") ? atoi(getenv("CB_LSTM_DBG")) : 0;
-    lstm_tc_kernel<<<dim3(2 * (q.Bp / RM), 2), NTHREADS, SMEM_BYTES, s>>>(q);     // clusters of 2 along x
+    static const bool remote_exchange = getenv("CB_LSTM_EXCH") && !strcmp(getenv("CB_LSTM_EXCH"), "remote");      // A/B
+    if (!remote_exchange) lstm_tc_kernel<false><<<dim3(2 * (q.Bp / RM), 2), NTHREADS, SMEM_BYTES, s>>>(q);     // clusters of 2 along x
+    else lstm_tc_kernel<true><<<dim3(2 * (q.Bp / RM), 2), NTHREADS, SMEM_BYTES, s>>>(q);
     CB_CHECK_LAUNCH();
     h->launches++;
     if (q.dbg && p.layer == 0) {          // development probe: print the timeline of steps 100..103 of CTA (0,0)

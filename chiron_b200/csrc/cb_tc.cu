@@ -283,9 +283,11 @@ __device__ __forceinline__ void gemm_tc_body(const TcParams& q) {
         float* v = reinterpret_cast<float*>(smem + q.vec_off);
         for (int i = threadIdx.x; i < BN; i += (int)blockDim.x) {
             v[i] = __ldg(g.shift + i);
-            v[BN + i] = g.res ? __ldg(g.rw + i) : 0.f;
-            v[2 * BN + i] = g.res ? __ldg(g.rinv + i) : 0.f;
-            v[3 * BN + i] = g.res ? __ldg(g.rsh + i) : 0.f;
+            if (g.res) {                                  // (the launcher reserves the three residual vectors only then)
+                v[BN + i] = __ldg(g.rw + i);
+                v[2 * BN + i] = __ldg(g.rinv + i);
+                v[3 * BN + i] = __ldg(g.rsh + i);
+            }
         }
     }
     tc_fence_before();
@@ -1310,14 +1312,17 @@ int cb_launch_gemm_tc(cb_handle* h, const TcGemm& g, cudaStream_t s) {
     auto smem_for = [&](int stages) {
         return q.resident ? smem_bytes_resident(L.BN / nc, L.k_chunks, stages) : smem_bytes_for(L.BN / nc, stages);
     };
+    // epilogue vectors of a one-n-tile contraction cached behind the ring and the barriers: shift, and the three rank-1
+    // residual vectors when there is a residual (a 7-stage ring, which the plain convolutions then fit, measured neutral: r02_s20)
+    const size_t vec_bytes = L.n_tiles == 1 ? (g.res ? 4 : 1) * (size_t)L.BN * sizeof(float) : 0;
     q.stages = MAX_STAGES;
-    while (q.stages > MIN_STAGES && smem_for(q.stages) > SMEM_MAX) --q.stages;
+    while (q.stages > MIN_STAGES && smem_for(q.stages) + vec_bytes > SMEM_MAX) --q.stages;
     if (stages_env >= 2 && stages_env <= q.stages) q.stages = stages_env;
     size_t smem = smem_for(q.stages);
     q.vec_off = 0;
-    if (L.n_tiles == 1 && smem + 4 * (size_t)L.BN * sizeof(float) <= SMEM_MAX) {     // behind the ring and the barriers
+    if (vec_bytes && smem + vec_bytes <= SMEM_MAX) {
         q.vec_off = (uint32_t)smem;
-        smem += 4 * (size_t)L.BN * sizeof(float);
+        smem += vec_bytes;
     }
     if (smem > SMEM_MAX) { cb_set_error("tensor-core path: layer %d needs %zu bytes of shared memory", g.layer_id, smem); return CB_ERR_ARG; }
     q.dbg = nullptr;
