@@ -45,6 +45,7 @@ constexpr int NHG = 25;            // half-groups (4 hidden units = 16 gate colu
 constexpr int NMAX = 208;          // widest column slice of a CTA
 constexpr int ACC1_COL = 224;      // TMEM: accumulator of even steps at columns [0,208), of odd steps at [224,432)
 constexpr int C_COL = 448;         // TMEM columns 448..499 hold the cell state c[row][local unit]
+constexpr int OWN_KS0 = 3;         // K-steps [0, 3) multiply rank 0's hidden units (K-groups 0-5 = units 0-47), [3, 7) rank 1's
 constexpr int GATE_WARPS = 24;
 constexpr int SLOTS = GATE_WARPS / 4;   // gate warps per TMEM lane quadrant
 constexpr int NTHREADS = (1 + GATE_WARPS) * 32;
@@ -295,7 +296,7 @@ __device__ __forceinline__ void gate_loop(const LstmTcParams& q, uint32_t hbuf_s
 // each warp arrives once per step on h_full[s & 1] of both CTAs -- bit-identical, but 3.5 instead of 2.4 ms per launch at
 // 4096 x 512 (profiles/r02_s19_lstm_exchange_ab.txt): 8-byte remote stores move far fewer bytes per clock over the
 // SM-to-SM network than bulk copies (DSMEM: ~17 B/clk per SM pair), and the proxy fence waits for their acknowledgements.
-template <bool REMOTE>
+template <bool REMOTE, bool SPLIT_K>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) lstm_tc_kernel(const LstmTcParams q) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* w_hi = smem;
@@ -380,32 +381,50 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) lstm_tc
                 mbar_wait(&pre_done[s & 1], (s >> 1) & 1);     // pre(s) sits in accumulator buffer s&1
                 if (s > 0) {
                     if constexpr (REMOTE) mbar_wait_cluster(&h_full[(s - 1) & 1], ((s - 1) >> 1) & 1);   // all of h(s-1), both halves
-                    else mbar_wait_cluster(h_ready, (s - 1) & 1);   // peer's half of h(s-1) landed (own half: local_done, below)
+                    else if constexpr (!SPLIT_K) mbar_wait_cluster(h_ready, (s - 1) & 1);   // peer's half of h(s-1) landed (own half: local_done, below)
                 }
             }
             __syncwarp();
             tc_fence_after();
             const uint32_t hb = smem_u32(hbuf) + (uint32_t)((s + 1) & 1) * (2 * HS_BYTES);     // h(s-1) lives in buffer (s-1)&1
             const uint64_t da_hi = make_desc(hb, RM * 16, 128), da_lo = make_desc(hb + HS_BYTES, RM * 16, 128);
-#pragma unroll
-            for (int phase = 0; phase < 2; ++phase) {
+            // K-steps [k0, k1) of one column phase: low-order products first, then hi*hi
+            auto issue = [&](int phase, int k0, int k1) {
                 const uint32_t d = tmem_base + ((s & 1) ? ACC1_COL : 0) + (phase ? NA : 0);
                 const uint32_t idesc = phase ? idescB : idescA;
                 const uint32_t brow = phase ? NA : 0;          // 16 B units
-                if (leader) {
-                    if (s > 0) {                               // h(0) = 0: the first step has no recurrent term;
-                                                               // later steps accumulate on top of the parked projection
-#pragma unroll
-                        for (int ks = 0; ks < KG_A / 2; ++ks) {   // low-order products first
-                            umma_f16(d, da_hi + ks * A_STEP, db_lo + (ks * B_STEP + brow), idesc, 1);
-                            umma_f16(d, da_lo + ks * A_STEP, db_hi + (ks * B_STEP + brow), idesc, 1);
-                        }
-#pragma unroll
-                        for (int ks = 0; ks < KG_A / 2; ++ks)
-                            umma_f16(d, da_hi + ks * A_STEP, db_hi + (ks * B_STEP + brow), idesc, 1);
-                    }
-                    umma_commit(&acc_ready[phase]);
+                for (int ks = k0; ks < k1; ++ks) {
+                    umma_f16(d, da_hi + ks * A_STEP, db_lo + (ks * B_STEP + brow), idesc, 1);
+                    umma_f16(d, da_lo + ks * A_STEP, db_hi + (ks * B_STEP + brow), idesc, 1);
                 }
+                for (int ks = k0; ks < k1; ++ks) umma_f16(d, da_hi + ks * A_STEP, db_hi + (ks * B_STEP + brow), idesc, 1);
+            };
+            if constexpr (REMOTE || !SPLIT_K) {
+#pragma unroll
+                for (int phase = 0; phase < 2; ++phase)
+                    if (leader) {
+                        if (s > 0) issue(phase, 0, KG_A / 2);  // h(0) = 0: the first step has no recurrent term; later steps
+                                                               // accumulate on top of the parked projection
+                        umma_commit(&acc_ready[phase]);
+                    }
+            } else {
+                // OWN HALF FIRST.  The K-steps split exactly between the CTAs (rank 0's units = K-steps 0-2, rank 1's = 3-6),
+                // and this CTA's own half of h(s-1) is complete as soon as its gate warps are (local_done of step s-1, waited
+                // for before the copies below were issued).  Its products -- for both column phases -- are issued while the
+                // peer's half is still on the wire; only the peer's K-steps of the first column phase (9-12 MMAs instead of
+                // 21) remain between the arrival of h and the first gate math of the step.
+                const int own0 = rank ? OWN_KS0 : 0, own1 = rank ? KG_A / 2 : OWN_KS0;
+                const int peer0 = rank ? 0 : OWN_KS0, peer1 = rank ? OWN_KS0 : KG_A / 2;
+                if (leader && s > 0) { issue(0, own0, own1); issue(1, own0, own1); }
+                if (leader && s > 0) mbar_wait_cluster(h_ready, (s - 1) & 1);     // peer's half of h(s-1) landed
+                __syncwarp();
+                tc_fence_after();
+#pragma unroll
+                for (int phase = 0; phase < 2; ++phase)
+                    if (leader) {
+                        if (s > 0) issue(phase, peer0, peer1);
+                        umma_commit(&acc_ready[phase]);
+                    }
             }
             if constexpr (!REMOTE) {
                 // arm this step's receive barrier BEFORE shipping my half (the peer can only send h(s+1) after it got
@@ -452,6 +471,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) lstm_tc
     }
 }
 
+}  // namespace
+
+// CB_LSTM_SPLITK=0: one sweep over K per column phase after the whole h arrived (the round-1 issue order; A/B)
+bool cb_lstm_tc_split_k() {
+    static const bool on = getenv("CB_LSTM_SPLITK") && atoi(getenv("CB_LSTM_SPLITK")) != 0;
+    return on;
+}
+
+namespace {
+
 struct LstmTcState {
     __half* wimg[CB_MAX_LAYERS][2];
 };
@@ -478,9 +507,19 @@ int cb_lstm_tc_prepare(cb_handle* h, const float* hw) {
                         const int u = (n / 16) * 4 + (n & 3), gate = (n >> 2) & 3;
                         // -log2(e) folded into the i/f/o columns, -2*log2(e) into the j columns (see lstm_cell)
                         const float sc = gate == 1 ? -2.f * 1.4426950408889634f : -1.4426950408889634f;
-                        // truncation compensation (cb_tc_build_layer): the hi*hi product of K-step g/2 is the
-                        // (g/2 + 1)-th of the 7 last MMAs of the step's chain
-                        const double comp = 1.0 + cb_tc_trunc_c() * (KG_A / 2 - g / 2);
+                        // truncation compensation (cb_tc_build_layer): truncating adds from this K-step's hi*hi product
+                        // to the end of the step's chain.  One sweep over K: it is the (g/2 + 1)-th of the 7 last MMAs.
+                        // Own half first (the default): a column of rank r sees [own low-order, own hi*hi, peer low-order,
+                        // peer hi*hi]; rank 0 owns K-steps 0-2 and columns 0-191.
+                        int after = KG_A / 2 - g / 2;
+                        if (cb_lstm_tc_split_k()) {
+                            const int ks = g / 2, col_rank = n < 192 ? 0 : 1;
+                            const bool own = (ks < OWN_KS0) == (col_rank == 0);
+                            const int n_own = col_rank ? KG_A / 2 - OWN_KS0 : OWN_KS0, n_peer = KG_A / 2 - n_own;
+                            const int j = ks < OWN_KS0 ? ks : ks - OWN_KS0;          // position inside its half
+                            after = own ? (n_own - j) + 3 * n_peer : n_peer - j;
+                        }
+                        const double comp = 1.0 + cb_tc_trunc_c() * after;
                         const float w = k < H ? (float)((double)W[(size_t)k * H4 + gate * H + u] * sc * comp) : 0.f;
                         const __half hi = __float2half_rn(w);
                         const __half lo = __float2half_rn(w - __half2float(hi));
@@ -490,8 +529,9 @@ int cb_lstm_tc_prepare(cb_handle* h, const float* hw) {
             CB_CUDA(cudaMalloc(&st->wimg[l][d], img.size() * sizeof(__half)));
             CB_CUDA(cudaMemcpy(st->wimg[l][d], img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
         }
-    CB_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    CB_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    CB_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    CB_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    CB_CUDA(cudaFuncSetAttribute(lstm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     return CB_OK;
 }
 
@@ -530,8 +570,10 @@ int cb_launch_lstm_tc(cb_handle* h, const LstmProblem& p, const CbImg* o_img, in
     q.dbg = probe ? d_dbg : nullptr;
     q.dbg_flags = getenv("CB_LSTM_DBG") ? atoi(getenv("CB_LSTM_DBG")) : 0;
     static const bool remote_exchange = getenv("CB_LSTM_EXCH") && !strcmp(getenv("CB_LSTM_EXCH"), "remote");      // A/B
-    if (!remote_exchange) lstm_tc_kernel<false><<<dim3(2 * (q.Bp / RM), 2), NTHREADS, SMEM_BYTES, s>>>(q);     // clusters of 2 along x
-    else lstm_tc_kernel<true><<<dim3(2 * (q.Bp / RM), 2), NTHREADS, SMEM_BYTES, s>>>(q);
+    const dim3 grid(2 * (q.Bp / RM), 2);                 // clusters of 2 along x
+    if (remote_exchange) lstm_tc_kernel<true, false><<<grid, NTHREADS, SMEM_BYTES, s>>>(q);
+    else if (cb_lstm_tc_split_k()) lstm_tc_kernel<false, true><<<grid, NTHREADS, SMEM_BYTES, s>>>(q);
+    else lstm_tc_kernel<false, false><<<grid, NTHREADS, SMEM_BYTES, s>>>(q);
     CB_CHECK_LAUNCH();
     h->launches++;
     if (q.dbg && p.layer == 0) {          // development probe: print the timeline of steps 100..103 of CTA (0,0)
