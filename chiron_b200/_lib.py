@@ -52,6 +52,7 @@ SIGNATURES = {
     "cb_launch_count": (c_longlong, [c_void_p]),
     "cb_last_forward_ms": (c_int, [c_void_p, POINTER(c_float), c_int]),
     "cb_enable_timing": (None, [c_void_p, c_int]),
+    "cb_reserve_sms": (c_int, [c_void_p, c_int]),
     "cb_last_forward_profile": (c_int, [c_void_p, POINTER(c_float), POINTER(c_int), c_int]),
     "cb_debug_fetch": (c_longlong, [c_void_p, c_int, c_void_p, c_size_t]),
     "cb_host_alloc": (c_void_p, [c_size_t]),

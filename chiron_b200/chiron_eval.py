@@ -185,8 +185,11 @@ def evaluation(flags=None, caller: Optional[Basecaller] = None) -> Dict[str, dic
     def assemble_read(st: _ReadState):
         basecall_time = time.time() - st.start_time
         kernal = get_assembler_kernal(jump, L)
-        seq, qual, pos = caller.assemble(st.bases, st.n_bases, st.prob if with_qs else None, jump, L, kernel=kernal,
-                                         with_qs=with_qs)
+        if os.environ.get("CHIRON_B200_SKIP_ASSEMBLY") == "1":         # development: what the per-read assembly costs the run
+            seq, qual, pos = "", ("" if with_qs else None), np.zeros(st.n, np.int32)
+        else:
+            seq, qual, pos = caller.assemble(st.bases, st.n_bases, st.prob if with_qs else None, jump, L, kernel=kernal,
+                                             with_qs=with_qs)
         assembly_time = time.time() - st.start_time
         file_pre = output_prefix(st.name)
         # the segment strings are built by the writer thread: this thread's job is to keep the GPU fed
@@ -216,6 +219,10 @@ def evaluation(flags=None, caller: Optional[Basecaller] = None) -> Dict[str, dic
 
     finisher_thread = threading.Thread(target=finisher, name="chiron-finisher", daemon=True)
     if use_finisher:
+        # the assembly kernels of finished reads run next to the forward kernels of the following batches: keep a few SMs
+        # out of the persistent contraction grids so that they find a slot (cb_reserve_sms; +7 % on files -> fastq)
+        if hasattr(caller, "reserve_sms"):
+            caller.reserve_sms(int(os.environ.get("CHIRON_B200_RESERVE_SMS", "4")))
         finisher_thread.start()
 
     def finish(st: _ReadState):

@@ -92,6 +92,7 @@ extern "C" int cb_create(const void* blob, size_t nbytes, int device, int precis
 
     cb_handle* h = new cb_handle();
     memset(h, 0, sizeof(*h));
+    if (const char* rs = getenv("CB_RESERVE_SMS")) { const int n = atoi(rs); h->reserve_sms = n > 0 && n <= 16 ? (n + 1) & ~1 : 0; }
     h->device = device;
     h->precision = precision;
     CbConfig& c = h->cfg;
@@ -372,6 +373,12 @@ extern "C" int cb_precision(const cb_handle* h) { return h ? h->precision : CB_E
 extern "C" size_t cb_workspace_bytes(const cb_handle* h) { return h ? h->ws_bytes + h->ws_bytes_tc + h->stage_bytes + h->beam_ws_bytes + h->asm_ws_bytes : 0; }
 extern "C" long long cb_launch_count(const cb_handle* h) { return h ? h->launches : 0; }
 extern "C" void cb_enable_timing(cb_handle* h, int on) { if (h) h->timing = on; }
+
+extern "C" int cb_reserve_sms(cb_handle* h, int n) {
+    if (!h || n < 0 || n > 16) { cb_set_error("cb_reserve_sms: n must be 0..16"); return CB_ERR_ARG; }
+    h->reserve_sms = (n + 1) & ~1;
+    return CB_OK;
+}
 
 extern "C" int cb_last_forward_ms(const cb_handle* h, float* ms, int n) {
     if (!h || !ms || !h->have_ms) return 0;

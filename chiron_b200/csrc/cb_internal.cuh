@@ -98,6 +98,7 @@ struct cb_handle {
     void* asm_ws; size_t asm_ws_bytes;
     int* d_flag;
     long long launches;
+    int reserve_sms;                  // SMs left out of the persistent GEMM grids (cb_reserve_sms)
     int timing; cudaEvent_t ev[8]; int have_ms;
     // per-launch profile of the last cb_forward (timing on): event pairs tagged with a kernel category
     cudaEvent_t prof_ev[CB_PROF_MAX][2]; int prof_cat[CB_PROF_MAX]; int prof_n; int prof_ready;

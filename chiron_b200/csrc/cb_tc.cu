@@ -1297,7 +1297,7 @@ int cb_launch_gemm_tc(cb_handle* h, const TcGemm& g, cudaStream_t s) {
     const bool pair = pair_env && L.img2 && q.m_tiles % 2 == 0 && h->sm_count % 2 == 0 && (L.n_tiles == 1 || pair_env == 2);
     const int nc = pair ? 2 : 1;
     static const int sms_env = getenv("CB_TC_GEMM_SMS") ? atoi(getenv("CB_TC_GEMM_SMS")) : 0;   // experiment: cap the grid
-    const int sms = sms_env > 0 && sms_env < h->sm_count ? sms_env : h->sm_count;
+    const int sms = sms_env > 0 && sms_env < h->sm_count ? sms_env : h->sm_count - h->reserve_sms;     // (cb_reserve_sms)
     const int units = sms / nc;                           // scheduling units: CTAs or CTA pairs
     const int m_units = q.m_tiles / nc;
     // resident weights when the n-tile's image fits beside the A ring, the units can be dealt evenly over the n-tiles

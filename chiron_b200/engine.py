@@ -122,6 +122,11 @@ class Basecaller:
     def launches(self) -> int:
         return int(self.lib.cb_launch_count(self.h))
 
+    def reserve_sms(self, n: int):
+        """Leave ``n`` SMs out of the persistent contraction grids (cb_reserve_sms): for pipelines that run small kernels
+        of another stream next to the forward pass, like evaluation()'s per-read assembly."""
+        _lib.check(self.lib.cb_reserve_sms(self.h, int(n)), "cb_reserve_sms")
+
     def enable_timing(self, on: bool = True):
         self.lib.cb_enable_timing(self.h, int(on))
 

@@ -169,6 +169,14 @@ long long cb_host_windows(const float* sig, size_t n, int jump, int L, float* x,
 long long cb_host_format_segments(const char* name, const int8_t* bases, const int32_t* n_bases, int n_windows, int T,
                                   char* out, size_t cap);
 
+/* Leave `n` SMs (0..16, rounded up to even) out of the grids of the persistent tensor-core contractions of this handle.
+ * For callers that run other small kernels next to the forward pass -- evaluation() assembles finished reads on a second
+ * stream while the next batches run: a persistent grid that fills every SM makes each of those kernels wait for a kernel
+ * boundary and then delays one CTA of the next contraction by its run time (measured on files -> fastq, 1 x B200:
+ * 61.7 Msamples/s with n = 0, 64.8 / 66.0 / 65.2 with n = 2 / 4 / 8; the resident step itself does not slow down, it runs
+ * at the power cap).  Default 0 (CB_RESERVE_SMS overrides).  No reference counterpart: TF's executor owns the device there. */
+int cb_reserve_sms(cb_handle* h, int n);
+
 /* -- introspection for tests / benchmarks ----------------------------------------------------------------------------- */
 
 /* Number of kernels this library has launched on the handle since creation (bench.py's gpu_launches). */
