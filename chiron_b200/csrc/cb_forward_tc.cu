@@ -21,7 +21,8 @@ struct TcWorkspace {
     void* base; size_t bytes;
     int B, L;                     // geometry the images were zeroed for
     CbImg a0;                     // block-1 conv2a output: L frames + the 'SAME' padding frames of conv2b
-    CbImg conv[3];                // block activations: T frames + one zero frame in front and behind
+    CbImg conv[3];                // block activations: T frames + the zero frames the widest later block's 'SAME' padding
+                                  // reads in front of and behind them (one each for width 3)
     CbImg himg;                   // LSTM layer output, planes [fw 13][bw 13]
     float* xT;                    // [L][Bp] transposed raw windows
     float* pre;                   // [T][8H][Bp]
@@ -35,7 +36,12 @@ int ensure_ws(cb_handle* h, int B, int L, int T, int Bp, int pad0, int left0, cu
     const CbConfig& c = h->cfg;
     const int planes = c.channels / 8;
     const long long rows_a0 = (long long)(L + pad0) * Bp;
-    const long long rows_c = (long long)(T + 2) * Bp;
+    int pad_l = 1, pad_r = 1;                                 // stride-1 blocks after the first: left (k-1)/2, right k-1-left
+    for (int b = 1; b < c.n_blocks; ++b) {
+        const int l = (c.k[b] - 1) / 2, r = c.k[b] - 1 - l;
+        pad_l = l > pad_l ? l : pad_l; pad_r = r > pad_r ? r : pad_r;
+    }
+    const long long rows_c = (long long)(T + pad_l + pad_r) * Bp;
     const long long rows_h = (long long)T * Bp;
     const int hplanes = 32;       // 26 real k-group planes (2 x 13) + zero planes the K padding reads
     size_t off = 0;
@@ -61,7 +67,7 @@ int ensure_ws(cb_handle* h, int B, int L, int T, int Bp, int pad0, int left0, cu
     w->a0.plane_rows = rows_a0; w->a0.row0 = (long long)left0 * Bp; w->a0.planes = planes;
     for (int i = 0; i < 3; ++i) {
         w->conv[i].hi = (__half*)(base + o_conv[i][0]); w->conv[i].lo = (__half*)(base + o_conv[i][1]);
-        w->conv[i].plane_rows = rows_c; w->conv[i].row0 = Bp; w->conv[i].planes = planes;
+        w->conv[i].plane_rows = rows_c; w->conv[i].row0 = (long long)pad_l * Bp; w->conv[i].planes = planes;
     }
     w->himg.hi = (__half*)(base + o_h[0]); w->himg.lo = (__half*)(base + o_h[1]);
     w->himg.plane_rows = rows_h; w->himg.row0 = 0; w->himg.planes = hplanes;

@@ -1178,8 +1178,8 @@ int cb_tc_prepare(cb_handle* h, const float* hw) {
     const CbConfig& c = h->cfg;
     const int C = c.channels, H = c.hidden;
     for (int b = 1; b < c.n_blocks; ++b)
-        if (c.stride[b] != 1 || c.k[b] != 3) {
-            cb_set_error("tensor-core path supports stride-1, width-3 residual blocks after the first; use precision fp32");
+        if (c.stride[b] != 1 || c.k[b] < 1) {      // any width: a tap is a frame shift of the same operand image
+            cb_set_error("tensor-core path supports stride-1 residual blocks after the first; use precision fp32");
             return CB_ERR_ARG;
         }
     if (C % 32) { cb_set_error("tensor-core path needs channels %% 32 == 0"); return CB_ERR_ARG; }

@@ -128,6 +128,38 @@ def test_five_block_rna_test_topology_matches_oracle(tmp_path, precision, tol):
     bc.close()
 
 
+def test_wide_stride1_blocks_on_the_tensor_core_path(tmp_path):
+    """Residual blocks of widths other than 3 after the first one (even and odd: 'SAME' pads (k-1)/2 in front, the rest
+    behind) on the tcgen05 kernels: a conv tap is a frame shift of the operand image, whose zero frames are sized for the
+    widest block.  Random-init weights, oracle in float64; `auto` precision must pick the tensor-core kernels."""
+    from chiron_b200.engine import Basecaller
+    cfg, t, path = _random_model(tmp_path, "wide", n_blocks=4, k=[5, 7, 4, 1], stride=[2, 1, 1, 1], branch1_bn_mask=0b0110)
+    rng = np.random.default_rng(8)
+    B, L = 140, 150
+    x = rng.normal(-0.16, 0.43, size=(B, L)).astype(np.float32)
+    lens = rng.integers(1, L + 1, size=B).astype(np.int32)
+    lens[:3] = L
+    for b in range(B):
+        x[b, lens[b]:] = 0
+    T = cfg.out_len(L)
+    lens_o = O.seq_len_out(lens, L / T)
+    ref_fea = O.cnn_forward(x, cfg, t, np.float64)
+    ref = O.inference(x, lens_o, cfg, t, np.float64)
+    bc = Basecaller(path, device=0, precision="auto")
+    assert bc.precision == "tc" and bc.out_len(L) == T
+    bases, n_bases, prob, logits = bc.basecall_batch(x, lens, beam=0, want_logits=True)
+    fea = bc.debug_fetch(0, ref_fea.size).reshape(ref_fea.shape)
+    assert np.abs(fea - ref_fea).max() < 2e-3 * max(1.0, np.abs(ref_fea).max())
+    assert np.abs(logits - ref).max() < 5e-3
+    assert _assert_greedy_matches_where_decisive(bases, n_bases, ref, lens_o, 5e-3) > 0
+    bc.close()
+    # the same blob on the FFMA kernels: both paths agree with the oracle, hence with each other
+    bf = Basecaller(path, device=0, precision="fp32")
+    _, _, _, lg32 = bf.basecall_batch(x, lens, beam=0, want_logits=True)
+    assert np.abs(lg32 - ref).max() < 2e-3
+    bf.close()
+
+
 @pytest.mark.parametrize("bn_mode", ["population", "batch"])
 def test_strided_wide_blocks_match_oracle_fp32(tmp_path, bn_mode):
     """Blocks with stride > 1 and widths other than 3 after the first one (dynamic_net-style stacks, chiron/cnn.py:401-452),
