@@ -92,6 +92,10 @@ __device__ int beam_decode_warp(const float* __restrict__ lg, int len, int C, in
     n_free = __shfl_sync(FULL, n_free, 0);
     __syncwarp();
     const int bpc = 32 / n_child;                        // branches per chunk of the extension loop
+    // candidate number -> (branch, child) without an integer division when n_child is a power of two (4 for ACGT + blank:
+    // the software division was ~25 of the ~60 instructions every surviving candidate cost)
+    const int cshift = (n_child & (n_child - 1)) == 0 ? __ffs(n_child) - 1 : -1;
+    int n_evict = 0;                                     // evictions so far in this window (warp-uniform)
     float inp[8], row[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) row[c] = (c < C && len > 0) ? lg[c] : 0.f;
@@ -159,9 +163,10 @@ __device__ int beam_decode_warp(const float* __restrict__ lg, int len, int C, in
         }
         // extension loop, chunks of bpc whole branches
         for (int ib = 0; ib < nb; ib += bpc) {
-            bool flag = false;
+            bool flag = false, idle = false;
             {
-                const int i = ib + lane / n_child, c = lane % n_child;
+                const int i = ib + (cshift >= 0 ? lane >> cshift : lane / n_child);
+                const int c = cshift >= 0 ? lane & (n_child - 1) : lane % n_child;
                 if (lane < bpc * n_child && i < nb) {
                     const float tot = k.bo_total[i];
                     if (tot > -INFINITY && (n_leaves < W || tot > bot_val)) {
@@ -170,10 +175,18 @@ __device__ int beam_decode_warp(const float* __restrict__ lg, int len, int C, in
                         const float prev = (c == k.nodes[bn].label) ? k.bo_blank[i] : tot;
                         const float lab = inp[c] + prev;
                         flag = (lab > -INFINITY && (n_leaves < W || lab > bot_val)) || (ch >= 0 && k.nodes[ch].bframe == t);
+                        // A candidate whose child is an active beam is skipped by the sequential code without any effect
+                        // ("already an active beam"), and a beam only stops being active by an eviction: as long as no
+                        // eviction has happened since this test, such a candidate needs no second look at all.  On real
+                        // logits that is most of what survives the filter (the likely next base of every beam already
+                        // exists as its child): ~13 survivors per frame, a new base only every ~23 frames.
+                        idle = flag && ch >= 0 && k.nodes[ch].slot >= 0;
                     }
                 }
             }
             unsigned mask = __ballot_sync(FULL, flag);
+            const unsigned idle_mask = __ballot_sync(FULL, idle);
+            const int evict0 = n_evict;
             if (mask && !err) {
                 // The surviving candidates are taken in order -- an insertion moves the beam's bottom, which the next
                 // candidate's test reads -- but by the WHOLE warp: every lane follows the same (warp-uniform) decisions from
@@ -181,10 +194,13 @@ __device__ int beam_decode_warp(const float* __restrict__ lg, int len, int C, in
                 // the gap of the evicted leaf, finding the new bottom) are spread over the lanes.  On one lane they were
                 // ~3,000 clocks per insertion, and a new base is ~W insertions.
                 int cur_i = -1; bool cur_pass = false; float tot = 0.f;
+                if ((mask & ~idle_mask) == 0) mask = 0;         // only idle survivors: nothing can be inserted, so nothing evicted
                 while (mask) {
                     const int bit = __ffs(mask) - 1;
                     mask &= mask - 1;
-                    const int i = ib + bit / n_child, c = bit % n_child;
+                    if (((idle_mask >> bit) & 1u) && n_evict == evict0) continue;
+                    const int i = ib + (cshift >= 0 ? bit >> cshift : bit / n_child);
+                    const int c = cshift >= 0 ? bit & (n_child - 1) : bit % n_child;
                     if (i != cur_i) {                      // the branch's entry test, with the state of this moment
                         cur_i = i;
                         tot = k.bo_total[i];
@@ -220,6 +236,7 @@ __device__ int beam_decode_warp(const float* __restrict__ lg, int len, int C, in
                         if (lane == 0) { k.nodes[bnode].slot = -1; k.freel[n_free] = bs; }
                         --n_leaves;
                         ++n_free;
+                        ++n_evict;
                         __syncwarp();
                     }
                     int node = ch;
