@@ -161,6 +161,32 @@ __device__ int beam_decode_warp(const float* __restrict__ lg, int len, int C, in
             const int oi = __shfl_xor_sync(FULL, bot, off);
             if (oi != 0x7fffffff && (bot == 0x7fffffff || ov < bot_val || (ov == bot_val && oi < bot))) { bot_val = ov; bot = oi; }
         }
+        // QUIET FRAMES.  One branch per lane, its children unrolled (the loads of a branch are made once, the child loads are
+        // independent): is there any candidate in the whole frame that survives the filter and is not idle (see below)?  The
+        // test uses the state the first chunk would see, and as long as nothing is processed nothing changes, so every chunk
+        // would come to the same conclusion: no candidate to look at.  On real logits ~85 % of the frames are like that, and
+        // the four chunk filters -- eight dependent shared-memory loads each -- were a fifth of the kernel.
+        {
+            bool live = false;
+            for (int i = lane; i < nb; i += 32) {
+                const float tot = k.bo_total[i];
+                if (tot > -INFINITY && (n_leaves < W || tot > bot_val)) {
+                    const int bn = k.bnode[i];
+                    const int label = k.nodes[bn].label;
+                    const float blank_prev = k.bo_blank[i];
+#pragma unroll
+                    for (int c = 0; c < CB_BEAM_MAX_CHILD; ++c) {
+                        if (c < n_child) {
+                            const int ch = k.nodes[bn].child[c];
+                            const float lab = inp[c] + (c == label ? blank_prev : tot);
+                            const bool flag = (lab > -INFINITY && (n_leaves < W || lab > bot_val)) || (ch >= 0 && k.nodes[ch].bframe == t);
+                            live |= flag && !(ch >= 0 && k.nodes[ch].slot >= 0);
+                        }
+                    }
+                }
+            }
+            if (!__any_sync(FULL, live)) continue;
+        }
         // extension loop, chunks of bpc whole branches
         for (int ib = 0; ib < nb; ib += bpc) {
             bool flag = false, idle = false;

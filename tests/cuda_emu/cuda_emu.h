@@ -148,6 +148,7 @@ static inline unsigned __ballot_sync(unsigned, bool pred) {
     }
     return m;
 }
+static inline bool __any_sync(unsigned mask, bool pred) { return __ballot_sync(mask, pred) != 0; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline void __syncwarp(unsigned = 0xffffffffu) {
