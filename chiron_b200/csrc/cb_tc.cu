@@ -700,6 +700,16 @@ __device__ __forceinline__ void gemm_tc_body_v1(const TcParams& q) {
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
         }
     }
+    // Resident mode binds the CTA to ONE n-tile: its BN entries of the shift vector (the LSTM bias) are read once into shared
+    // memory.  Read with LDG per 16 columns they were the largest stall of this kernel -- source-level ncu: 34 % of all
+    // samples on the FFMAs that wait for them (profiles/r02_s31_proj_source_sass.csv.gz), i.e. the epilogue, not the HBM
+    // write, set the tile time.
+    const uint32_t vec_s = smem_u32(smem + q.vec_off);
+    const int vec_n0 = tiles.nt_fixed * BN;
+    if (q.vec_off) {
+        float* v = reinterpret_cast<float*>(smem + q.vec_off);
+        for (int i = threadIdx.x; i < BN; i += (int)blockDim.x) v[i] = __ldg(g.shift + vec_n0 + i);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -730,7 +740,7 @@ __device__ __forceinline__ void gemm_tc_body_v1(const TcParams& q) {
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
                     const int n = n0 + q4 * 4;
-                    const float4 sh = ldg4(g.shift + n);
+                    const float4 sh = q.vec_off ? lds4(vec_s + (uint32_t)(n - vec_n0) * 4u) : ldg4(g.shift + n);
                     o[q4 * 4 + 0] = fmaf(sum[q4 * 4 + 0], q.out_scale, sh.x);
                     o[q4 * 4 + 1] = fmaf(sum[q4 * 4 + 1], q.out_scale, sh.y);
                     o[q4 * 4 + 2] = fmaf(sum[q4 * 4 + 2], q.out_scale, sh.z);
@@ -1314,7 +1324,12 @@ int cb_launch_gemm_tc(cb_handle* h, const TcGemm& g, cudaStream_t s) {
     };
     // epilogue vectors of a one-n-tile contraction cached behind the ring and the barriers: shift, and the three rank-1
     // residual vectors when there is a residual (a 7-stage ring, which the plain convolutions then fit, measured neutral: r02_s20)
-    const size_t vec_bytes = L.n_tiles == 1 ? (g.res ? 4 : 1) * (size_t)L.BN * sizeof(float) : 0;
+    //  -- and the bound n-tile's slice of the shift vector in resident mode (single-CTA, single-accumulator kernel)
+    static const int force_multi = getenv("CB_TC_FORCE_MULTI") ? atoi(getenv("CB_TC_FORCE_MULTI")) : 0;   // A/B
+    const bool multi = q.cpp < q.k_chunks || force_multi;
+    static const int proj_vec_env = getenv("CB_TC_PROJ_VEC") ? atoi(getenv("CB_TC_PROJ_VEC")) : 1;        // A/B
+    const size_t vec_bytes = L.n_tiles == 1 ? (g.res ? 4 : 1) * (size_t)L.BN * sizeof(float)
+                                            : (q.resident && !pair && !multi && !g.res && proj_vec_env ? (size_t)L.BN * sizeof(float) : 0);
     q.stages = MAX_STAGES;
     while (q.stages > MIN_STAGES && smem_for(q.stages) + vec_bytes > SMEM_MAX) --q.stages;
     if (stages_env >= 2 && stages_env <= q.stages) q.stages = stages_env;
@@ -1339,8 +1354,6 @@ int cb_launch_gemm_tc(cb_handle* h, const TcGemm& g, cudaStream_t s) {
         q.dbg = d_dbg;
     }
 #endif
-    static const int force_multi = getenv("CB_TC_FORCE_MULTI") ? atoi(getenv("CB_TC_FORCE_MULTI")) : 0;   // A/B
-    const bool multi = q.cpp < q.k_chunks || force_multi;
     if (pair) {
         q.img = L.img2; q.tm_w = L.tm_w2;
         // the convolutions' specialised epilogue (see gemm_tc_body): ReLU'd operand image out of one n-tile, vectors cached
