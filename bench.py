@@ -124,7 +124,26 @@ class ClockSampler:
         self._stop = threading.Event()
         self._t = None
 
+    def _run_nvml(self):
+        """NVML directly (the source nvidia-smi reads): a sample every 10 ms instead of one per process start."""
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        flag = lambda bits, m: "Active" if bits & m else "Not Active"
+        while not self._stop.is_set():
+            bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            self.rows.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx),
+                              "%.2f" % (nv.nvmlDeviceGetPowerUsage(h) / 1e3),
+                              flag(bits, nv.nvmlClocksThrottleReasonHwSlowdown), flag(bits, nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                              flag(bits, nv.nvmlClocksThrottleReasonSwThermalSlowdown), flag(bits, nv.nvmlClocksThrottleReasonSwPowerCap)])
+            self._stop.wait(0.01)
+
     def _run(self):
+        try:
+            return self._run_nvml()
+        except Exception:
+            pass                                   # no NVML binding: one nvidia-smi process per sample
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
