@@ -105,11 +105,6 @@ extern "C" int cb_create(const void* blob, size_t nbytes, int device, int precis
     if (c.stem_k < 0 || c.stem_k > 64 || (c.stem_k > 0) != (c.stem_stride > 0) || c.stem_stride < 0) {
         delete h; cb_set_error("cb_create: bad stem convolution geometry in blob header"); return CB_ERR_BLOB;
     }
-    if (c.stem_k > 0 && precision != CB_PREC_FP32) {
-        delete h;
-        cb_set_error("cb_create: models with a stem convolution (RNA_model2/3) run on the CB_PREC_FP32 path only");
-        return CB_ERR_ARG;
-    }
     if (c.cell_type == CB_CELL_GRU && precision != CB_PREC_FP32) {
         delete h;
         cb_set_error("cb_create: GRU cells run on the CB_PREC_FP32 path only (the tensor-core recurrence is an LSTM kernel)");

@@ -35,9 +35,9 @@ int ensure_ws(cb_handle* h, int B, int L, int T, int Bp, int pad0, int left0, cu
     if (!w) { w = new TcWorkspace(); memset(w, 0, sizeof(*w)); h->tc_ws = w; }
     const CbConfig& c = h->cfg;
     const int planes = c.channels / 8;
-    const long long rows_a0 = (long long)(L + pad0) * Bp;
+    const long long rows_a0 = c.stem_k > 0 ? Bp : (long long)(L + pad0) * Bp;      // (stem models have no rank-1 block)
     int pad_l = 1, pad_r = 1;                                 // stride-1 blocks after the first: left (k-1)/2, right k-1-left
-    for (int b = 1; b < c.n_blocks; ++b) {
+    for (int b = c.stem_k > 0 ? 0 : 1; b < c.n_blocks; ++b) {
         const int l = (c.k[b] - 1) / 2, r = c.k[b] - 1 - l;
         pad_l = l > pad_l ? l : pad_l; pad_r = r > pad_r ? r : pad_r;
     }
@@ -101,8 +101,9 @@ int cb_forward_tc(cb_handle* h, const float* x, const int32_t* seq_len_out, int 
                   float* path_prob, cudaStream_t s) {
     const CbConfig& c = h->cfg;
     const int C = c.channels, H = c.hidden;
-    const int st0 = c.stride[0], k0 = c.k[0];
-    const int T = (L + st0 - 1) / st0;                        // frames after block 1; later blocks have stride 1
+    const bool stem = c.stem_k > 0;                           // RNA_model2/3: a strided stem conv, then stride-1 blocks only
+    const int st0 = stem ? c.stem_stride : c.stride[0], k0 = stem ? c.stem_k : c.k[0];
+    const int T = (L + st0 - 1) / st0;                        // frames after block 1 (the stem); later blocks have stride 1
     int pad0 = (T - 1) * st0 + k0 - L; if (pad0 < 0) pad0 = 0;   // TF 'SAME'
     const int left0 = pad0 / 2;
     const int Bp = (B + 127) / 128 * 128;
@@ -120,6 +121,15 @@ int cb_forward_tc(cb_handle* h, const float* x, const int32_t* seq_len_out, int 
         g.N = C; g.relu = 1; g.out_mode = 2;
         return g;
     };
+    // ---- stem models: the stem convolution writes the operand image every block (the first included) then reads ----------
+    int xi = 1;
+    if (stem) {
+        int pi = cb_prof_begin(h, CB_CAT_CONV, s);
+        rc = cb_launch_transpose_x(h, x, B, L, Bp, w->xT, s);
+        if (rc == CB_OK) rc = cb_launch_stem_image(h, w->xT, B, Bp, L, T, left0, w->conv[xi], s);
+        cb_prof_end(h, pi, s);
+        if (rc != CB_OK) return rc;
+    } else
     // ---- block 1 (cnn.py:383-384): conv2a is a rank-1 function of the raw signal ----------------------------------------
     {
         int pi = cb_prof_begin(h, CB_CAT_CONV, s);
@@ -136,8 +146,7 @@ int cb_forward_tc(cb_handle* h, const float* x, const int32_t* seq_len_out, int 
         g.o = w->conv[1];
         if ((rc = timed_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
     }
-    int xi = 1;
-    for (int b = 1; b < c.n_blocks; ++b) {
+    for (int b = stem ? 0 : 1; b < c.n_blocks; ++b) {
         const int ai = (xi + 1) % 3, bi = (xi + 2) % 3;
         TcGemm g = base_gemm(b * 4 + 0);                          // conv2a 1x1
         g.a0 = w->conv[xi]; g.shift = h->conv2a[b].shift; g.o = w->conv[ai];

@@ -121,6 +121,7 @@ double cb_tc_trunc_c();                    // mean relative shrink per truncatin
 #define CB_LSTM_TC_CHAIN 21                // MMAs the recurrence chains on top of the pre-loaded input projection
 int cb_launch_transpose_x(cb_handle* h, const float* x, int B, int L, int Bp, float* xT, cudaStream_t s);
 int cb_launch_gen_conv2a(cb_handle* h, const float* xT, int B, int Bp, int L, const CbImg& o, cudaStream_t s);
+int cb_launch_stem_image(cb_handle* h, const float* xT, int B, int Bp, int L, int t_out, int left, const CbImg& o, cudaStream_t s);
 int cb_launch_lstm_tc(cb_handle* h, const LstmProblem& p, const CbImg* o_img, int write_f32, cudaStream_t s);
 int cb_tc_prepare(cb_handle* h, const float* host_weights);   // build fp16 hi/lo operand images from d_weights layout
 void cb_tc_release(cb_handle* h);

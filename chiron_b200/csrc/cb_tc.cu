@@ -1020,6 +1020,38 @@ __global__ void __launch_bounds__(256) gen_conv2a_kernel(const float* __restrict
     }
 }
 
+// Stem convolution of RNA_model2 / RNA_model3 (conv_layer(net, [1, k, 1, C], strides = s) + BN + ReLU, cnn.py:454-476) written
+// straight into an operand image: the arithmetic of stem_conv_kernel (cb_stem_kernel.cuh: taps in order, fmaf, then the folded
+// BN as one fmaf), one thread per (output frame, window, k-group), consecutive threads = consecutive windows.
+__global__ void __launch_bounds__(256) stem_image_kernel(const float* __restrict__ xT, int B, int Bp, int L, int t_out, int k,
+                                                         int stride, int left, int planes, const float* __restrict__ w,
+                                                         const float* __restrict__ inv, const float* __restrict__ shift, CbImg o) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int to = blockIdx.y;
+    if (b >= B || to >= t_out) return;
+    for (int kg = 0; kg < planes; ++kg) {
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        for (int j = 0; j < k; ++j) {
+            const int ti = to * stride + j - left;
+            if (ti < 0 || ti >= L) continue;
+            const float xv = __ldg(xT + (size_t)ti * Bp + b);
+            const float* wj = w + (size_t)j * planes * 8 + kg * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = fmaf(xv, __ldg(wj + e), acc[e]);
+        }
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = fmaxf(fmaf(acc[e], __ldg(inv + kg * 8 + e), __ldg(shift + kg * 8 + e)), 0.f);
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        const size_t off = ((size_t)kg * o.plane_rows + o.row0 + (size_t)to * Bp + b) * 8;
+        *reinterpret_cast<uint4*>(o.hi + off) = hi;
+        *reinterpret_cast<uint4*>(o.lo + off) = lo;
+    }
+}
+
 // TMA view of an operand image: dim0 = 8-byte elements along the rows of a plane (2 per 16-byte row), dim1 = plane,
 // dim2 = hi | lo (the two allocations of an image; lo lies behind hi in the workspace).
 int make_img_map(const CbImg& img, CUtensorMap* tm) {
@@ -1195,10 +1227,15 @@ int cb_tc_prepare(cb_handle* h, const float* hw) {
     if (C % 32) { cb_set_error("tensor-core path needs channels %% 32 == 0"); return CB_ERR_ARG; }
     auto host = [&](const float* dev) { return hw + (dev - h->d_weights); };
     int rc;
+    if (c.stem_k > 0 && c.stride[0] != 1) {
+        cb_set_error("tensor-core path: a stem convolution needs a stride-1 first block; use precision fp32");
+        return CB_ERR_ARG;
+    }
     for (int b = 0; b < c.n_blocks; ++b) {
-        if (b > 0 && (rc = cb_tc_build_layer(h, b * 4 + 0, host(h->conv2a[b].W), C, C, 0)) != CB_OK) return rc;
+        const bool rank1 = b == 0 && c.stem_k == 0;         // block 1 of a model without a stem reads the raw signal
+        if (!rank1 && (rc = cb_tc_build_layer(h, b * 4 + 0, host(h->conv2a[b].W), C, C, 0)) != CB_OK) return rc;
         if ((rc = cb_tc_build_layer(h, b * 4 + 1, host(h->conv2b[b].W), c.k[b] * C, C, 0)) != CB_OK) return rc;
-        if ((rc = cb_tc_build_layer(h, b * 4 + 2, host(h->convc[b].W), b == 0 ? C : 2 * C, C, 0)) != CB_OK) return rc;
+        if ((rc = cb_tc_build_layer(h, b * 4 + 2, host(h->convc[b].W), rank1 ? C : 2 * C, C, 0)) != CB_OK) return rc;
     }
     // LSTM input projections.  Layer 0 reads the CNN feature image (K = C).  Later layers read the h image written by
     // the recurrence, whose planes are [fw: 13 k-groups (104 ch, 100 real)][bw: 13 k-groups]: K' = 208 with zero rows.
@@ -1392,6 +1429,15 @@ int cb_launch_gemm_tc(cb_handle* h, const TcGemm& g, cudaStream_t s) {
 
 int cb_launch_transpose_x(cb_handle* h, const float* x, int B, int L, int Bp, float* xT, cudaStream_t s) {
     transpose_x_kernel<<<dim3((Bp + 31) / 32, (L + 31) / 32), dim3(32, 8), 0, s>>>(x, B, L, Bp, xT);
+    CB_CHECK_LAUNCH();
+    h->launches++;
+    return CB_OK;
+}
+
+int cb_launch_stem_image(cb_handle* h, const float* xT, int B, int Bp, int L, int t_out, int left, const CbImg& o, cudaStream_t s) {
+    if (t_out > 65535) { cb_set_error("segment_len too large for the stem grid"); return CB_ERR_ARG; }
+    stem_image_kernel<<<dim3((B + 255) / 256, t_out), 256, 0, s>>>(xT, B, Bp, L, t_out, h->cfg.stem_k, h->cfg.stem_stride, left,
+                                                                  h->cfg.channels / 8, h->stem.w, h->stem.inv, h->stem.shift, o);
     CB_CHECK_LAUNCH();
     h->launches++;
     return CB_OK;

@@ -82,5 +82,17 @@ def test_stem_convolution_model_matches_oracle_fp32(tmp_path, bn_mode):
     assert np.abs(fea - ref_fea).max() < 1e-3 * max(1.0, np.abs(ref_fea).max())
     assert np.abs(logits - ref).max() < (1e-2 if bn_mode == "batch" else 2e-3)
     bc.close()
-    with pytest.raises(_lib.ChironB200Error):       # the tensor-core conv stack has no stem: refused loudly
-        Basecaller(path, device=0, precision="tc")
+    if bn_mode == "batch":
+        with pytest.raises(_lib.ChironB200Error):   # batch statistics live on the fp32 kernels: refused loudly
+            Basecaller(path, device=0, precision="tc", bn_mode="batch")
+        return
+    # the same blob on the tensor-core kernels: the stem convolution writes the operand image, and the first block is an
+    # ordinary 256-channel block (cb_forward_tc); "auto" must pick them
+    bt = Basecaller(path, device=0, precision="auto")
+    assert bt.precision == "tc" and bt.out_len(L) == T
+    bases_t, n_t, prob_t, logits_t = bt.basecall_batch(x, lens, beam=0, want_logits=True)
+    fea_t = bt.debug_fetch(0, ref_fea.size).reshape(ref_fea.shape)
+    assert np.abs(fea_t - ref_fea).max() < 2e-3 * max(1.0, np.abs(ref_fea).max())
+    assert np.abs(logits_t - ref).max() < 5e-3
+    assert np.array_equal(n_t, n_bases) and np.array_equal(bases_t, bases)       # greedy bases: tc == fp32 kernels
+    bt.close()
