@@ -36,10 +36,13 @@ int ensure_ws(cb_handle* h, int B, int L, int T, int Bp, int pad0, int left0, cu
     const CbConfig& c = h->cfg;
     const int planes = c.channels / 8;
     const long long rows_a0 = c.stem_k > 0 ? Bp : (long long)(L + pad0) * Bp;      // (stem models have no rank-1 block)
-    int pad_l = 1, pad_r = 1;                                 // stride-1 blocks after the first: left (k-1)/2, right k-1-left
-    for (int b = c.stem_k > 0 ? 0 : 1; b < c.n_blocks; ++b) {
-        const int l = (c.k[b] - 1) / 2, r = c.k[b] - 1 - l;
+    int pad_l = 1, pad_r = 1;                                 // TF 'SAME' of the blocks after the first (the stem): frames they
+    for (int b = c.stem_k > 0 ? 0 : 1, t = T; b < c.n_blocks; ++b) {      // read in front of / behind their input's data
+        const int to = (t + c.stride[b] - 1) / c.stride[b];
+        int pad = (to - 1) * c.stride[b] + c.k[b] - t; if (pad < 0) pad = 0;
+        const int l = pad / 2, r = pad - l;
         pad_l = l > pad_l ? l : pad_l; pad_r = r > pad_r ? r : pad_r;
+        t = to;
     }
     const long long rows_c = (long long)(T + pad_l + pad_r) * Bp;
     const long long rows_h = (long long)T * Bp;
@@ -146,19 +149,35 @@ int cb_forward_tc(cb_handle* h, const float* x, const int32_t* seq_len_out, int 
         g.o = w->conv[1];
         if ((rc = timed_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
     }
+    int Tc = T;                                                   // frames of the current block input
     for (int b = stem ? 0 : 1; b < c.n_blocks; ++b) {
         const int ai = (xi + 1) % 3, bi = (xi + 2) % 3;
+        const int sb = c.stride[b], kb = c.k[b];
+        const int To = (Tc + sb - 1) / sb;                        // TF 'SAME': ceil(T / stride) output frames
+        int pad = (To - 1) * sb + kb - Tc; if (pad < 0) pad = 0;
+        const int left = pad / 2, right = pad - left;
         TcGemm g = base_gemm(b * 4 + 0);                          // conv2a 1x1
-        g.a0 = w->conv[xi]; g.shift = h->conv2a[b].shift; g.o = w->conv[ai];
+        g.T = Tc; g.a0 = w->conv[xi]; g.shift = h->conv2a[b].shift; g.o = w->conv[ai];
         if ((rc = timed_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
-        g = base_gemm(b * 4 + 1);                                 // conv2b 1x3: three frame-shifted views of the same image
-        g.a0 = w->conv[ai]; g.taps = c.k[b]; g.left = (c.k[b] - 1) / 2; g.shift = h->conv2b[b].shift; g.o = w->conv[bi];
+        if (Tc < T && right > 0) {
+            // After a strided block the images hold fewer frames than they did before: the frames conv2b's padding reads
+            // behind the data are leftovers of an earlier, longer tensor.  Zero them (one strided memset per hi / lo).
+            const CbImg& im = w->conv[ai];
+            const size_t pitch = (size_t)im.plane_rows * 16, width = (size_t)right * Bp * 16;
+            CB_CUDA(cudaMemset2DAsync((char*)im.hi + ((size_t)im.row0 + (size_t)Tc * Bp) * 16, pitch, 0, width, im.planes, s));
+            CB_CUDA(cudaMemset2DAsync((char*)im.lo + ((size_t)im.row0 + (size_t)Tc * Bp) * 16, pitch, 0, width, im.planes, s));
+        }
+        g = base_gemm(b * 4 + 1);                                 // conv2b 1xk: frame-shifted (and strided) views of one image
+        g.T = To; g.a0 = w->conv[ai]; g.taps = kb; g.left = left; g.stride = sb; g.shift = h->conv2b[b].shift; g.o = w->conv[bi];
         if ((rc = timed_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
-        g = base_gemm(b * 4 + 2);                                 // conv2c ++ branch1(X), ReLU
-        g.a0 = w->conv[bi]; g.a1 = w->conv[xi]; g.a1_chunks = cpt; g.shift = h->convc[b].shift; g.o = w->conv[ai];
+        g = base_gemm(b * 4 + 2);                                 // conv2c ++ branch1(X) (1x1, the block's stride), ReLU
+        g.T = To; g.a0 = w->conv[bi]; g.a1 = w->conv[xi]; g.a1_chunks = cpt; g.a1_stride = sb; g.shift = h->convc[b].shift;
+        g.o = w->conv[ai];
         if ((rc = timed_gemm(h, g, s, CB_CAT_CONV)) != CB_OK) return rc;
         xi = ai;
+        Tc = To;
     }
+    const int Tf = Tc;                                            // frames the LSTM stack and the head see (= cb_out_len(L))
     w->fea_idx = xi;
     if (h->timing) CB_CUDA(cudaEventRecord(h->ev[1], s));
 
@@ -169,7 +188,7 @@ int cb_forward_tc(cb_handle* h, const float* x, const int32_t* seq_len_out, int 
         for (int d = 0; d < n_gemm; ++d) {
             TcGemm g;
             memset(&g, 0, sizeof(g));
-            g.layer_id = 32 + l * 2 + d; g.T = T; g.B = B; g.Bp = Bp; g.taps = 1; g.stride = 1;
+            g.layer_id = 32 + l * 2 + d; g.T = Tf; g.B = B; g.Bp = Bp; g.taps = 1; g.stride = 1;
             if (l == 0) { g.a0 = w->conv[xi]; g.a0_chunks_per_tap = cpt; }
             else if (n_gemm == 1) { g.a0 = w->himg; g.a0_chunks_per_tap = 7; }                 // K' = 208 -> 7 chunks
             else { g.a0 = w->himg; g.a0_plane0 = d * 13; g.a0_chunks_per_tap = 4; }            // K' = 104 -> 4 chunks
@@ -180,7 +199,7 @@ int cb_forward_tc(cb_handle* h, const float* x, const int32_t* seq_len_out, int 
         }
         LstmProblem lp;
         memset(&lp, 0, sizeof(lp));
-        lp.B = B; lp.T = T; lp.H = H; lp.pre = w->pre; lp.ld_pre = Bp; lp.lens = seq_len_out; lp.out = w->out; lp.ldo = 2 * H;
+        lp.B = B; lp.T = Tf; lp.H = H; lp.pre = w->pre; lp.ld_pre = Bp; lp.lens = seq_len_out; lp.out = w->out; lp.ldo = 2 * H;
         lp.layer = l;
         const int pi = cb_prof_begin(h, CB_CAT_LSTM_REC, s);
         rc = cb_launch_lstm_tc(h, lp, last ? nullptr : &w->himg, last ? 1 : 0, s);
@@ -191,13 +210,13 @@ int cb_forward_tc(cb_handle* h, const float* x, const int32_t* seq_len_out, int 
 
     {
         const int pi = cb_prof_begin(h, CB_CAT_HEAD, s);
-        rc = cb_launch_head_tmajor(h, w->out, B, Bp, T, logits, s);
+        rc = cb_launch_head_tmajor(h, w->out, B, Bp, Tf, logits, s);
         cb_prof_end(h, pi, s);
         if (rc != CB_OK) return rc;
     }
-    if (path_prob && (rc = cb_launch_path_prob(h, logits, B, T, path_prob, s)) != CB_OK) return rc;
+    if (path_prob && (rc = cb_launch_path_prob(h, logits, B, Tf, path_prob, s)) != CB_OK) return rc;
     if (h->timing) { CB_CUDA(cudaEventRecord(h->ev[3], s)); h->have_ms = 1; }
-    h->last_B = B; h->last_T = T; h->last_Bp = Bp; h->last_tmajor = 1;
+    h->last_B = B; h->last_T = Tf; h->last_Bp = Bp; h->last_tmajor = 1;
     return CB_OK;
 }
 

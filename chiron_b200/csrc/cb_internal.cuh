@@ -44,6 +44,7 @@ struct TcGemm {
     CbImg a0, a1;
     int a0_plane0, a1_plane0;                 // first k-group plane of each source
     int a0_chunks_per_tap, taps, left, stride, a1_chunks;     // K = (taps*a0_chunks_per_tap + a1_chunks) * 32
+    int a1_stride;            // frame stride of the appended 1x1 branch input (0 = 1: the strided branch1 of a strided block)
     int N; const float* shift; int relu;
     int res; const float* xT; int res_stride; const float *rw, *rinv, *rsh;   // + (xT[to*res_stride][b]*rw)*rinv + rsh
     int out_mode;             // 1 fp32 time-major out[to][ldo][Bp]; 2 operand image o

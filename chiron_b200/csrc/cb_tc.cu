@@ -608,7 +608,7 @@ __device__ __forceinline__ void gemm_tc_body(const TcParams& q) {
                     row = (int)(g.a0.row0 + ((long long)to * g.stride + j - g.left) * g.Bp + b0);
                     plane = g.a0_plane0 + cc * 4; tm = &q.tm_a0;
                 } else {
-                    row = (int)(g.a1.row0 + (long long)to * g.Bp + b0);
+                    row = (int)(g.a1.row0 + (long long)to * (g.a1_stride > 1 ? g.a1_stride : 1) * g.Bp + b0);
                     plane = g.a1_plane0 + (kc - n0c) * 4; tm = &q.tm_a1;
                 }
                 uint8_t* st = ring + (size_t)s * stage_bytes;
@@ -933,7 +933,7 @@ __device__ __forceinline__ void gemm_tc_body_v1(const TcParams& q) {
                     row = (int)(g.a0.row0 + ((long long)to * g.stride + j - g.left) * g.Bp + b0);
                     plane = g.a0_plane0 + cc * 4; tm = &q.tm_a0;
                 } else {
-                    row = (int)(g.a1.row0 + (long long)to * g.Bp + b0);
+                    row = (int)(g.a1.row0 + (long long)to * (g.a1_stride > 1 ? g.a1_stride : 1) * g.Bp + b0);
                     plane = g.a1_plane0 + (kc - n0c) * 4; tm = &q.tm_a1;
                 }
                 uint8_t* st = ring + (size_t)s * stage_bytes;
@@ -1220,8 +1220,8 @@ int cb_tc_prepare(cb_handle* h, const float* hw) {
     const CbConfig& c = h->cfg;
     const int C = c.channels, H = c.hidden;
     for (int b = 1; b < c.n_blocks; ++b)
-        if (c.stride[b] != 1 || c.k[b] < 1) {      // any width: a tap is a frame shift of the same operand image
-            cb_set_error("tensor-core path supports stride-1 residual blocks after the first; use precision fp32");
+        if (c.stride[b] < 1 || c.k[b] < 1) {       // any width and stride: a tap is a frame shift of the same operand image,
+            cb_set_error("bad block geometry");    // a stride multiplies the frame index (conv2b and the 1x1 branch input)
             return CB_ERR_ARG;
         }
     if (C % 32) { cb_set_error("tensor-core path needs channels %% 32 == 0"); return CB_ERR_ARG; }

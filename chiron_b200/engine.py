@@ -68,9 +68,8 @@ class Basecaller:
                  bn_mode: Optional[str] = None):
         """``precision``: "tc" = the tcgen05 tensor-core kernels (the production mode), "fp32" = the FFMA kernels,
         "auto" (default) = "tc" whenever the model's topology is one the tensor-core kernels cover (the shipped
-        DNA_default / RNA_default, residual stacks of any depth and width with stride-1 blocks after the first, the stem
-        models RNA_model2/3), "fp32" otherwise (GRU cells, strided later blocks, hidden != 100, batch-statistics
-        BatchNorm) -- said once on stderr, never silently.
+        DNA_default / RNA_default, residual stacks of any depth, width and stride, the stem models RNA_model2/3),
+        "fp32" otherwise (GRU cells, hidden != 100, batch-statistics BatchNorm) -- said once on stderr, never silently.
         ``bn_mode``: None = what the model's blob header says; "population" / "batch" override it
         (cb_set_bn_mode; "batch" = HEAD's simple_global_bn, chiron/cnn.py:166-188, fp32 precision only)."""
         self.lib = _lib.load()

@@ -160,6 +160,40 @@ def test_wide_stride1_blocks_on_the_tensor_core_path(tmp_path):
     bf.close()
 
 
+def test_strided_blocks_on_the_tensor_core_path(tmp_path):
+    """Blocks with stride > 1 after the first one (dynamic_net-style stacks, chiron/cnn.py:401-452) on the tcgen05 kernels:
+    conv2b multiplies the frame index of its taps, the 1x1 branch reads every stride-th frame of the block input, and the
+    frames behind a shortened tensor are re-zeroed for the next 'SAME' padding.  Float64 oracle; also == the FFMA kernels."""
+    from chiron_b200.engine import Basecaller
+    cfg, t, path = _random_model(tmp_path, "strided_tc", n_blocks=5, k=[5, 3, 7, 3, 4], stride=[2, 1, 3, 1, 2],
+                                 branch1_bn_mask=0b10101)
+    rng = np.random.default_rng(12)
+    B, L = 140, 301
+    x = rng.normal(-0.16, 0.43, size=(B, L)).astype(np.float32)
+    lens = rng.integers(1, L + 1, size=B).astype(np.int32)
+    lens[:3] = L
+    for b in range(B):
+        x[b, lens[b]:] = 0
+    T = cfg.out_len(L)
+    assert T == 26                                   # 301 -> 151 -> 151 -> 51 -> 51 -> 26
+    lens_o = O.seq_len_out(lens, L / T)
+    ref_fea = O.cnn_forward(x, cfg, t, np.float64)
+    ref = O.inference(x, lens_o, cfg, t, np.float64)
+    bc = Basecaller(path, device=0, precision="auto")
+    assert bc.precision == "tc" and bc.out_len(L) == T
+    for _ in range(2):                               # twice: the second pass meets the leftovers of the first in every image
+        bases, n_bases, prob, logits = bc.basecall_batch(x, lens, beam=0, want_logits=True)
+        fea = bc.debug_fetch(0, ref_fea.size).reshape(ref_fea.shape)
+        assert np.abs(fea - ref_fea).max() < 2e-3 * max(1.0, np.abs(ref_fea).max())
+        assert np.abs(logits - ref).max() < 5e-3
+    assert _assert_greedy_matches_where_decisive(bases, n_bases, ref, lens_o, 5e-3) > 0
+    bc.close()
+    bf = Basecaller(path, device=0, precision="fp32")
+    _, _, _, lg32 = bf.basecall_batch(x, lens, beam=0, want_logits=True)
+    assert np.abs(lg32 - ref).max() < 2e-3
+    bf.close()
+
+
 @pytest.mark.parametrize("bn_mode", ["population", "batch"])
 def test_strided_wide_blocks_match_oracle_fp32(tmp_path, bn_mode):
     """Blocks with stride > 1 and widths other than 3 after the first one (dynamic_net-style stacks, chiron/cnn.py:401-452),
