@@ -349,6 +349,7 @@ extern "C" int cb_destroy(cb_handle* h) {
     if (h->pipe_in) cudaStreamDestroy(h->pipe_in);
     if (h->pipe_compute) cudaStreamDestroy(h->pipe_compute);
     if (h->pipe_out) cudaStreamDestroy(h->pipe_out);
+    if (h->asm_stream) cudaStreamDestroy(h->asm_stream);
     if (h->asm_stage) cudaFree(h->asm_stage);
     if (h->beam_ws) cudaFree(h->beam_ws);
     if (h->asm_ws) cudaFree(h->asm_ws);
@@ -770,7 +771,9 @@ extern "C" int cb_assemble_host(cb_handle* h, const int8_t* bases, const int32_t
     int8_t* d_cons = (int8_t*)p; p += sz_c;
     char* d_qual = (char*)p; p += sz_c;
     int32_t* d_len = (int32_t*)p;
-    cudaStream_t s = 0;
+    // a stream of its own, non-blocking: the legacy default stream would serialise with every blocking stream of the caller
+    if (!h->asm_stream) CB_CUDA(cudaStreamCreateWithFlags(&h->asm_stream, cudaStreamNonBlocking));
+    cudaStream_t s = h->asm_stream;
     int rc = CB_OK;
     cudaError_t e = cudaSuccess;
     if (n_windows > 0) {

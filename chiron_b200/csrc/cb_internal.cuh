@@ -89,6 +89,7 @@ struct cb_handle {
         int B, L, T, busy;
     } pipe[2];
     cudaStream_t pipe_in, pipe_compute, pipe_out;
+    cudaStream_t asm_stream;          // cb_assemble_host's own non-blocking stream (created on first use)
     void* asm_stage; size_t asm_stage_bytes;   // device staging of cb_assemble_host (grow-only: no cudaFree in the read loop)
     const float* fea;                  // CNN feature of the last forward (debug fetch)
     void* tc;                          // tensor-core path state (cb_tc.cu)
