@@ -169,10 +169,15 @@ def test_host_pipeline_end_to_end_with_a_stub_gpu(tmp_path, monkeypatch):
     (src / "notes.txt").write_text("ignored")
     submitted = []
 
+    reserved = []
+
     class Recorder(StubCaller):
         def basecall_submit(self, slot, x, seq_len, beam=0):
             submitted.append((slot, x.shape[0], int(seq_len.sum())))
             return super().basecall_submit(slot, x, seq_len, beam)
+
+        def reserve_sms(self, n):              # cb_reserve_sms: asked for once, before the first batch, when a finisher runs
+            reserved.append((n, len(submitted)))
 
     monkeypatch.setattr(chiron_eval, "Basecaller", lambda model, device=0, precision="auto": Recorder(model))
     monkeypatch.setenv("CHIRON_B200_GPU_BATCH", "300")
@@ -181,6 +186,7 @@ def test_host_pipeline_end_to_end_with_a_stub_gpu(tmp_path, monkeypatch):
                                  jump=None, threads=3, beam=0, extension="fastq", concise=False, mode="dna", preset="dna-pre",
                                  precision="tc", recursive=False)
     chiron_eval.run(apply_preset(args))
+    assert reserved == [(4, 0)]
     names = sorted(n_samples) + ["empty"]
     for sub in ("result", "segments"):
         assert sorted(os.listdir(os.path.join(out, sub))) == sorted(n + ".fastq" for n in names)
